@@ -1,0 +1,351 @@
+"""ctypes front-end of the CPU oracle (oracle/tg_oracle.c) plus the task-level restatement.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+
+Parity status: raster + kinematics pinned by the reference's fixtures; dynamics PARITY UNPINNED
+(pybullet not available) - see oracle/tg_oracle.h.
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ASSETS = os.path.join(HERE, "..", "tactile_gym_b200", "assets")  # compiled DATA only (json/npz)
+
+MAXL, MAXD = 16, 8
+
+
+class OrModel(C.Structure):
+    _fields_ = [
+        ("nlinks", C.c_int), ("ndof", C.c_int),
+        ("parent", C.c_int * MAXL), ("jtype", C.c_int * MAXL), ("dof_of_link", C.c_int * MAXL), ("link_of_dof", C.c_int * MAXD),
+        ("joint_xyz", (C.c_double * 3) * MAXL), ("joint_rpy", (C.c_double * 3) * MAXL), ("axis", (C.c_double * 3) * MAXL),
+        ("inertial_xyz", (C.c_double * 3) * MAXL), ("inertial_rpy", (C.c_double * 3) * MAXL),
+        ("mass", C.c_double * MAXL), ("inertia", (C.c_double * 3) * MAXL),
+        ("tcp_link", C.c_int), ("body_link", C.c_int),
+        ("gravity", C.c_double * 3), ("dt", C.c_double), ("solver_iters", C.c_int),
+        ("lin_damping", C.c_double), ("ang_damping", C.c_double), ("joint_damping", C.c_double),
+        ("workframe_pos", C.c_double * 3), ("workframe_rpy", C.c_double * 3), ("tcp_lims", (C.c_double * 2) * 6),
+        ("max_force", C.c_double), ("pos_gain", C.c_double), ("vel_gain", C.c_double), ("mg400_slave", C.c_int),
+        ("cam_pos", C.c_double * 3), ("cam_rpy", C.c_double * 3), ("fov_deg", C.c_double), ("focal_dist", C.c_double),
+        ("near_", C.c_double), ("far_", C.c_double),
+    ]
+
+
+class OrState(C.Structure):
+    _fields_ = [
+        ("q", C.c_double * MAXD), ("qd", C.c_double * MAXD), ("motor_mode", C.c_int * MAXD),
+        ("target_pos", C.c_double * MAXD), ("target_vel", C.c_double * MAXD), ("kp", C.c_double * MAXD),
+        ("kd", C.c_double * MAXD), ("max_force", C.c_double * MAXD),
+    ]
+
+
+_lib = None
+
+
+def build(force=False):
+    so = os.path.join(HERE, "libtg_oracle.so")
+    src = os.path.join(HERE, "tg_oracle.c")
+    if force or not os.path.isfile(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-s"])
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(HERE, "libtg_oracle.so")
+        if not os.path.isfile(so):
+            build()
+        _lib = C.CDLL(so)
+        _lib.or_robot_reset.restype = C.c_int
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def load_model(arm, sensor, typ, workframe_pos, workframe_rpy, tcp_lims, gravity=(0, 0, -9.81), dt=1.0 / 240.0):
+    """Scene constants: base_tactile_env.py:125-130 (gravity, 150 iterations), base_robot_arm.py:24-25
+    (damping 0.04 / 0.04 / 0.01), ur5.py:19-21 & mg400.py:27-29 (max_force 1000, gains 1)."""
+    with open(os.path.join(ASSETS, "models", "%s_%s_%s.json" % (arm, typ, sensor))) as f:
+        mj = json.load(f)
+    with open(os.path.join(ASSETS, "sensors.json")) as f:
+        sj = json.load(f)[sensor]
+    m = OrModel()
+    links = mj["links"]
+    m.nlinks = len(links)
+    names = [l["link_name"] for l in links]
+    nd = 0
+    for i, l in enumerate(links):
+        m.parent[i] = l["parent"]
+        m.jtype[i] = 1 if l["joint_type"] == 1 else 0
+        m.dof_of_link[i] = -1
+        if l["joint_type"] == 1:
+            m.dof_of_link[i] = nd
+            m.link_of_dof[nd] = i
+            nd += 1
+        for c in range(3):
+            m.joint_xyz[i][c] = l["joint_xyz"][c]
+            m.joint_rpy[i][c] = l["joint_rpy"][c]
+            m.axis[i][c] = l["axis"][c]
+            m.inertial_xyz[i][c] = l["inertial_xyz"][c]
+            m.inertial_rpy[i][c] = l["inertial_rpy"][c]
+            m.inertia[i][c] = l["inertia_diag"][c]
+        m.mass[i] = l["mass"]
+    m.ndof = nd
+    m.tcp_link = names.index("tcp_link")
+    m.body_link = names.index(sensor + "_body_link")
+    for c in range(3):
+        m.gravity[c] = gravity[c]
+        m.workframe_pos[c] = workframe_pos[c]
+        m.workframe_rpy[c] = workframe_rpy[c]
+        m.cam_pos[c] = sj["types"][typ]["cam_pos"][c]
+        m.cam_rpy[c] = sj["types"][typ]["cam_rpy"][c]
+    for i in range(6):
+        m.tcp_lims[i][0] = tcp_lims[i][0]
+        m.tcp_lims[i][1] = tcp_lims[i][1]
+    m.dt = dt
+    m.solver_iters = 150
+    m.lin_damping = 0.04
+    m.ang_damping = 0.04
+    m.joint_damping = 0.01
+    m.max_force, m.pos_gain, m.vel_gain = 1000.0, 1.0, 1.0
+    m.mg400_slave = 1 if arm == "mg400" else 0
+    m.fov_deg, m.focal_dist, m.near_, m.far_ = sj["fov"], sj["focal_dist"], sj["near"], sj["far"]
+    m._names = names
+    m._control_links = [i for i, l in enumerate(links) if l["joint_type"] == 1]
+    return m
+
+
+def load_refimg(sensor, typ, S):
+    d = np.load(os.path.join(ASSETS, "refimg", "%s_%s_%d.npz" % (sensor, typ, S)))
+    return (np.ascontiguousarray(d["nodef_dep"], dtype=np.float32), np.ascontiguousarray(d["nodef_gray"], dtype=np.float32),
+            np.ascontiguousarray(d["border_mask"], dtype=np.uint8))
+
+
+def rest_pose(env, arm, sensor, typ, model):
+    with open(os.path.join(ASSETS, "rest_poses.json")) as f:
+        rp = json.load(f)[env][arm]
+    rp = rp[sensor][typ] if sensor in rp else rp[typ]
+    rp = np.asarray(rp, dtype=np.float64)
+    return rp[model._control_links].copy()
+
+
+# ---------------------------------------------------------------- thin wrappers
+def link_states(m, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    P = np.zeros((MAXL, 3)); Q = np.zeros((MAXL, 4))
+    lib().or_link_states(C.byref(m), _dptr(q), _dptr(P), _dptr(Q))
+    return P[: m.nlinks], Q[: m.nlinks]
+
+
+def link_frames(m, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    P = np.zeros((MAXL, 3)); R = np.zeros((MAXL, 9))
+    lib().or_link_frames(C.byref(m), _dptr(q), _dptr(P), _dptr(R))
+    return P[: m.nlinks], R[: m.nlinks].reshape(-1, 3, 3)
+
+
+def jacobian(m, q, link):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    J = np.zeros((6, MAXD))
+    lib().or_jacobian(C.byref(m), _dptr(q), C.c_int(link), _dptr(J))
+    return J[:, : m.ndof]
+
+
+def inverse_dynamics(m, q, qd, qdd=None):
+    q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
+    tau = np.zeros(MAXD)
+    qa = np.ascontiguousarray(qdd, dtype=np.float64) if qdd is not None else None
+    lib().or_inverse_dynamics(C.byref(m), _dptr(q), _dptr(qd), _dptr(qa) if qa is not None else None, _dptr(tau))
+    return tau[: m.ndof]
+
+
+def forward_dynamics(m, q, qd, tau, with_damping=False):
+    q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
+    tau = np.ascontiguousarray(tau, dtype=np.float64)
+    out = np.zeros(MAXD)
+    lib().or_forward_dynamics(C.byref(m), _dptr(q), _dptr(qd), _dptr(tau), C.c_int(int(with_damping)), _dptr(out))
+    return out[: m.ndof]
+
+
+def mass_matrix_inverse(m, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    A = np.zeros((MAXD, MAXD))
+    lib().or_mass_matrix_inverse(C.byref(m), _dptr(q), _dptr(A))
+    return A[: m.ndof, : m.ndof]
+
+
+def tcp_pose_workframe(m, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    p = np.zeros(3); r = np.zeros(3)
+    lib().or_tcp_pose_workframe(C.byref(m), _dptr(q), _dptr(p), _dptr(r))
+    return p, r
+
+
+def quat_from_euler(rpy):
+    rpy = np.ascontiguousarray(rpy, dtype=np.float64); q = np.zeros(4)
+    lib().or_quat_from_euler(_dptr(rpy), _dptr(q))
+    return q
+
+
+def euler_from_quat(q):
+    q = np.ascontiguousarray(q, dtype=np.float64); r = np.zeros(3)
+    lib().or_euler_from_quat(_dptr(q), _dptr(r))
+    return r
+
+
+def camera_frame(m, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    e, f, u, r = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3)
+    lib().or_camera_frame(C.byref(m), _dptr(q), _dptr(e), _dptr(f), _dptr(u), _dptr(r))
+    return e, f, u, r
+
+
+def depth_image(eye, fwd, up, right, fov, near, far, S, tris):
+    tris = np.ascontiguousarray(tris, dtype=np.float32)
+    out = np.zeros((S, S), dtype=np.float32)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (eye, fwd, up, right)]
+    lib().or_depth_image(_dptr(a[0]), _dptr(a[1]), _dptr(a[2]), _dptr(a[3]), C.c_double(fov), C.c_double(near), C.c_double(far),
+                         C.c_int(S), tris.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(len(tris)), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def tactile_image(m, q, S, tris_world, refimg, border_on=True, want_depth=False):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    tris = np.ascontiguousarray(tris_world, dtype=np.float64).reshape(-1, 9)
+    dep, gray, mask = refimg
+    img = np.zeros((S, S), dtype=np.uint8)
+    dout = np.zeros((S, S), dtype=np.float32) if want_depth else None
+    lib().or_tactile_image(C.byref(m), _dptr(q), C.c_int(S), _dptr(tris), C.c_int(len(tris)),
+                           dep.ctypes.data_as(C.POINTER(C.c_float)), gray.ctypes.data_as(C.POINTER(C.c_float)),
+                           mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(int(border_on)),
+                           img.ctypes.data_as(C.POINTER(C.c_ubyte)), dout.ctypes.data_as(C.POINTER(C.c_float)) if want_depth else None)
+    return (img, dout) if want_depth else img
+
+
+# ---------------------------------------------------------------- gym <= 0.21 seeding
+def gym_np_random(seed):
+    """gym.utils.seeding.np_random of gym <= 0.21 (base_tactile_env.py:61-64): a numpy RandomState seeded
+    with the 32-bit words of sha512(str(seed))[:8].  [EXT: gym is unpinned in requirements.txt; the reference
+    calls RandomState-only methods (randint), so the RandomState era is the one restated.]"""
+    if seed is None:
+        seed = int.from_bytes(os.urandom(4), "little")
+    h = hashlib.sha512(str(seed).encode("utf8")).digest()[:8]
+    h += b"\0" * 4  # gym's _bigint_from_bytes pads len%4==0 input with 4 zero bytes
+    words = struct.unpack("%dI" % (len(h) // 4), h)
+    big = sum(2 ** (32 * i) * v for i, v in enumerate(words))
+    ints = []
+    while big > 0:
+        big, mod = divmod(big, 2 ** 32)
+        ints.append(mod)
+    rng = np.random.RandomState()
+    rng.seed(ints or [0])
+    return rng
+
+
+# ---------------------------------------------------------------- edge_follow task restatement
+class EdgeFollowOracle:
+    """Restates EdgeFollowEnv (rl_envs/exploration/edge_follow/edge_follow_env.py) + BaseTactileEnv.step
+    (rl_envs/base_tactile_env.py:166-185) on top of the C oracle.  One env instance."""
+
+    def __init__(self, image_size=128, arm="ur5", sensor="tactip", max_steps=200, movement_mode="xy",
+                 noise_mode="rand_height", seed=None):
+        self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
+        self.max_steps, self.movement_mode, self.noise_mode = max_steps, movement_mode, noise_mode
+        lims = np.zeros((6, 2))
+        if arm == "mg400":  # edge_follow_env.py:73-80
+            self.edge_pos = [0.33, 0.0, 0.0]; self.edge_len = 0.105
+            lims[0], lims[1], lims[2], lims[5] = (-0.15, 0.15), (-0.11, 0.11), (-0.1, 0.1), (-np.pi, np.pi)
+            stim = "short_edge"
+        else:  # :81-88
+            self.edge_pos = [0.65, 0.0, 0.0]; self.edge_len = 0.175
+            lims[0], lims[1], lims[2], lims[5] = (-0.175, 0.175), (-0.175, 0.175), (-0.1, 0.1), (-np.pi, np.pi)
+            stim = "long_edge"
+        self.edge_height = 0.035
+        self.embed_dist = 0.0035
+        self.workframe_pos = np.array([self.edge_pos[0], self.edge_pos[1], self.edge_height])
+        self.workframe_rpy = np.array([-np.pi, 0.0, np.pi / 2])
+        self.m = load_model(arm, sensor, self.typ, self.workframe_pos, self.workframe_rpy, lims)
+        self.rest = rest_pose("edge_follow", arm, sensor, self.typ, self.m)
+        self.ref = load_refimg(sensor, self.typ, image_size)
+        self.tris_local = np.load(os.path.join(ASSETS, "stimuli", stim + ".npz"))["tris"]
+        self.s = OrState()
+        self.repeat = int(np.floor((1.0 / 10.0) / (1.0 / 240.0)))
+        self.termination_dist = 0.01
+        self.np_random = gym_np_random(seed)
+        self.max_pos_vel, self.max_ang_vel = 0.01, 5.0 * (np.pi / 180)
+        self.steps = 0
+        self.last_reset_substeps = 0
+
+    def seed(self, seed):
+        self.np_random = gym_np_random(seed)
+
+    # edge_follow_env.py:285-299
+    def draw(self):
+        embed = self.embed_dist
+        if self.noise_mode == "rand_height":
+            lo, hi = {"tactip": (0.0015, 0.0065), "digit": (0.0011, 0.0028), "digitac": (0.0015, 0.0045)}[self.sensor]
+            embed = self.np_random.uniform(lo, hi)
+        ang = self.np_random.uniform(-np.pi, np.pi)
+        return embed, ang
+
+    def reset(self, draws=None):
+        self.steps = 0
+        self.embed_dist, self.edge_ang = self.draw() if draws is None else draws
+        # update_edge :237-283
+        c, s_ = np.cos(self.edge_ang), np.sin(self.edge_ang)
+        self.goal_pos = np.array([self.edge_pos[0] + self.edge_len * c, self.edge_pos[1] + self.edge_len * s_, self.edge_pos[2] + self.edge_height])
+        self.edge_end_points = np.array([
+            [self.edge_pos[0] - self.edge_len * c, self.edge_pos[1] - self.edge_len * s_, self.edge_pos[2] + self.edge_height],
+            [self.edge_pos[0] + self.edge_len * c, self.edge_pos[1] + self.edge_len * s_, self.edge_pos[2] + self.edge_height]])
+        pos = np.array([0.0, 0.0, self.embed_dist]); rpy = np.zeros(3)
+        self.last_reset_substeps = lib().or_robot_reset(C.byref(self.m), C.byref(self.s), _dptr(self.rest), _dptr(pos), _dptr(rpy))
+        self.reward, self.done = self.step_data()
+        return self.observation()
+
+    def stimulus_world(self):
+        q = quat_from_euler([0.0, 0.0, self.edge_ang])
+        R = np.zeros(9); lib().or_mat_from_quat(_dptr(q), _dptr(R)); R = R.reshape(3, 3)
+        return self.tris_local @ R.T + np.array(self.edge_pos)
+
+    def observation(self):
+        q = np.array(self.s.q[: self.m.ndof])
+        return tactile_image(self.m, q, self.S, self.stimulus_world(), self.ref, border_on=True)[..., None]
+
+    def tcp_world(self):
+        P, Q = link_states(self.m, np.array(self.s.q[: self.m.ndof]))
+        return P[self.m.tcp_link], Q[self.m.tcp_link]
+
+    def step_data(self):
+        p, _ = self.tcp_world()
+        goal_dist = np.linalg.norm(p[:2] - self.goal_pos[:2])
+        p1, p2 = self.edge_end_points[0, :2], self.edge_end_points[1, :2]
+        edge_dist = np.abs(np.cross(p2 - p1, p1 - p[:2])) / np.linalg.norm(p2 - p1)
+        done = bool(goal_dist < self.termination_dist or self.steps >= self.max_steps)
+        return -(1.0 * goal_dist + 10.0 * edge_dist), done
+
+    def encode_scale(self, action):
+        enc = np.zeros(6)
+        a = np.asarray(action, dtype=np.float64)
+        idx = {"xy": [0, 1], "xyz": [0, 1, 2], "xyRz": [0, 1, 5], "xyzRz": [0, 1, 2, 5]}[self.movement_mode]
+        enc[idx] = a
+        enc = np.clip(enc, -0.25, 0.25)
+        amax = np.array([self.max_pos_vel] * 3 + [0.0, 0.0, self.max_ang_vel])
+        amin = -amax
+        return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
+
+    def step(self, action):
+        v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
+        self.steps += 1
+        lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
+        self.reward, self.done = self.step_data()
+        return self.observation(), self.reward, self.done, {}

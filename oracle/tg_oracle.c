@@ -1,0 +1,842 @@
+/*
+ * oracle/tg_oracle.c - CPU restatement of the tactile_gym hot path.  See tg_oracle.h for the
+ * parity status of each part.  TEST INFRASTRUCTURE ONLY - never linked into the product.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no FMA contraction, so the float32
+ * post-process reproduces numpy's arithmetic bit for bit).
+ */
+#include "tg_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ small linear algebra */
+typedef double v3[3];
+typedef double m3[9]; /* row major */
+
+static void v3set(v3 a, double x, double y, double z) { a[0] = x; a[1] = y; a[2] = z; }
+static void v3cpy(v3 a, const v3 b) { a[0] = b[0]; a[1] = b[1]; a[2] = b[2]; }
+static void v3add(v3 o, const v3 a, const v3 b) { o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; }
+static void v3sub(v3 o, const v3 a, const v3 b) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static void v3scale(v3 o, const v3 a, double s) { o[0] = a[0] * s; o[1] = a[1] * s; o[2] = a[2] * s; }
+static void v3axpy(v3 o, double s, const v3 a) { o[0] += a[0] * s; o[1] += a[1] * s; o[2] += a[2] * s; }
+static double v3dot(const v3 a, const v3 b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static double v3norm(const v3 a) { return sqrt(v3dot(a, a)); }
+static void v3cross(v3 o, const v3 a, const v3 b)
+{
+    double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static void m3mulv(v3 o, const m3 M, const v3 a)
+{
+    double x = M[0] * a[0] + M[1] * a[1] + M[2] * a[2];
+    double y = M[3] * a[0] + M[4] * a[1] + M[5] * a[2];
+    double z = M[6] * a[0] + M[7] * a[1] + M[8] * a[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static void m3tmulv(v3 o, const m3 M, const v3 a)
+{
+    double x = M[0] * a[0] + M[3] * a[1] + M[6] * a[2];
+    double y = M[1] * a[0] + M[4] * a[1] + M[7] * a[2];
+    double z = M[2] * a[0] + M[5] * a[1] + M[8] * a[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static void m3mul(m3 o, const m3 A, const m3 B)
+{
+    m3 t;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    memcpy(o, t, sizeof(m3));
+}
+static void m3tmul(m3 o, const m3 A, const m3 B) /* A^T B */
+{
+    m3 t;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+    memcpy(o, t, sizeof(m3));
+}
+static void m3ident(m3 o) { memset(o, 0, sizeof(m3)); o[0] = o[4] = o[8] = 1.0; }
+
+/* URDF fixed-axis rpy -> matrix, R = Rz(yaw) Ry(pitch) Rx(roll) */
+static void m3rpy(m3 R, const v3 rpy)
+{
+    double cr = cos(rpy[0]), sr = sin(rpy[0]), cp = cos(rpy[1]), sp = sin(rpy[1]), cy = cos(rpy[2]), sy = sin(rpy[2]);
+    R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+    R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+    R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+}
+/* rotation by angle about a (not necessarily unit) axis: bullet builds btQuaternion(axis, angle) */
+static void m3axis_angle(m3 R, const v3 axis_in, double ang)
+{
+    v3 a; double n = v3norm(axis_in);
+    v3scale(a, axis_in, n > 0 ? 1.0 / n : 0.0);
+    double c = cos(ang), s = sin(ang), t = 1 - c;
+    R[0] = t * a[0] * a[0] + c;        R[1] = t * a[0] * a[1] - s * a[2]; R[2] = t * a[0] * a[2] + s * a[1];
+    R[3] = t * a[0] * a[1] + s * a[2]; R[4] = t * a[1] * a[1] + c;        R[5] = t * a[1] * a[2] - s * a[0];
+    R[6] = t * a[0] * a[2] - s * a[1]; R[7] = t * a[1] * a[2] + s * a[0]; R[8] = t * a[2] * a[2] + c;
+}
+
+/* ------------------------------------------------------------------ pybullet frame helpers */
+/* p.getQuaternionFromEuler: btQuaternion::setEulerZYX(yaw, pitch, roll); quaternions are [x,y,z,w] */
+void or_quat_from_euler(const double rpy[3], double q[4])
+{
+    double hr = rpy[0] * 0.5, hp = rpy[1] * 0.5, hy = rpy[2] * 0.5;
+    double cr = cos(hr), sr = sin(hr), cp = cos(hp), sp = sin(hp), cy = cos(hy), sy = sin(hy);
+    q[0] = sr * cp * cy - cr * sp * sy;
+    q[1] = cr * sp * cy + sr * cp * sy;
+    q[2] = cr * cp * sy - sr * sp * cy;
+    q[3] = cr * cp * cy + sr * sp * sy;
+}
+/* p.getEulerFromQuaternion (bullet getEulerZYX with the +-0.99999 gimbal guard) */
+void or_euler_from_quat(const double q[4], double rpy[3])
+{
+    double sqx = q[0] * q[0], sqy = q[1] * q[1], sqz = q[2] * q[2], squ = q[3] * q[3];
+    double sarg = -2.0 * (q[0] * q[2] - q[3] * q[1]);
+    if (sarg <= -0.99999) { rpy[1] = -0.5 * M_PI; rpy[0] = 0; rpy[2] = 2 * atan2(q[0], -q[1]); }
+    else if (sarg >= 0.99999) { rpy[1] = 0.5 * M_PI; rpy[0] = 0; rpy[2] = 2 * atan2(-q[0], q[1]); }
+    else {
+        rpy[1] = asin(sarg);
+        rpy[0] = atan2(2 * (q[1] * q[2] + q[3] * q[0]), squ - sqx - sqy + sqz);
+        rpy[2] = atan2(2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz);
+    }
+}
+static void quat_mul(double o[4], const double a[4], const double b[4])
+{
+    double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+void or_mat_from_quat(const double q[4], double R[9])
+{
+    double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    double s = 2.0 / d;
+    double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    R[0] = 1 - (yy + zz); R[1] = xy - wz;       R[2] = xz + wy;
+    R[3] = xy + wz;       R[4] = 1 - (xx + zz); R[5] = yz - wx;
+    R[6] = xz - wy;       R[7] = yz + wx;       R[8] = 1 - (xx + yy);
+}
+static void quat_from_mat(double q[4], const m3 R) /* btMatrix3x3::getRotation */
+{
+    double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+        double s = sqrt(tr + 1.0);
+        q[3] = s * 0.5; s = 0.5 / s;
+        q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+    } else {
+        int i = R[0] < R[4] ? (R[4] < R[8] ? 2 : 1) : (R[0] < R[8] ? 2 : 0);
+        int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q[i] = s * 0.5; s = 0.5 / s;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * s;
+        q[j] = (R[3 * j + i] + R[3 * i + j]) * s;
+        q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+    }
+}
+void or_mul_transforms(const double pa[3], const double qa[4], const double pb[3], const double qb[4], double po[3], double qo[4])
+{
+    m3 R; v3 t;
+    or_mat_from_quat(qa, R);
+    m3mulv(t, R, pb);
+    v3add(po, pa, t);
+    quat_mul(qo, qa, qb);
+}
+void or_invert_transform(const double p[3], const double q[4], double po[3], double qo[4])
+{
+    m3 R; v3 t;
+    double qi[4] = {-q[0], -q[1], -q[2], q[3]};
+    or_mat_from_quat(qi, R);
+    m3mulv(t, R, p);
+    po[0] = -t[0]; po[1] = -t[1]; po[2] = -t[2];
+    memcpy(qo, qi, sizeof(qi));
+}
+
+/* ------------------------------------------------------------------ kinematics */
+typedef struct {
+    m3 Rl[OR_MAXL]; v3 pl[OR_MAXL]; /* world pose of the URDF link frames */
+    m3 Rc[OR_MAXL]; v3 pc[OR_MAXL]; /* world pose of the inertial (COM) frames */
+    v3 aw[OR_MAXL];                 /* joint axis, world, unit */
+} Kin;
+
+static void kin_compute(const OrModel* m, const double* q, Kin* k)
+{
+    for (int i = 0; i < m->nlinks; i++) {
+        m3 Rj, Rq, Rp, Rin; v3 pp, t;
+        int p = m->parent[i];
+        if (p < 0) { m3ident(Rp); v3set(pp, 0, 0, 0); }
+        else { memcpy(Rp, k->Rl[p], sizeof(m3)); v3cpy(pp, k->pl[p]); }
+        m3rpy(Rj, m->joint_rpy[i]);
+        m3mulv(t, Rp, m->joint_xyz[i]);
+        v3add(k->pl[i], pp, t);
+        m3mul(k->Rl[i], Rp, Rj);
+        if (m->jtype[i] == 1) {
+            m3axis_angle(Rq, m->axis[i], q[m->dof_of_link[i]]);
+            m3mul(k->Rl[i], k->Rl[i], Rq);
+        }
+        double n = v3norm(m->axis[i]);
+        v3 au; v3scale(au, m->axis[i], n > 0 ? 1 / n : 0);
+        m3mulv(k->aw[i], k->Rl[i], au);
+        m3rpy(Rin, m->inertial_rpy[i]);
+        m3mul(k->Rc[i], k->Rl[i], Rin);
+        m3mulv(t, k->Rl[i], m->inertial_xyz[i]);
+        v3add(k->pc[i], k->pl[i], t);
+    }
+}
+
+void or_link_states(const OrModel* m, const double* q, double pos[][3], double quat[][4])
+{
+    Kin k; kin_compute(m, q, &k);
+    for (int i = 0; i < m->nlinks; i++) { v3cpy(pos[i], k.pc[i]); quat_from_mat(quat[i], k.Rc[i]); }
+}
+
+void or_link_frames(const OrModel* m, const double* q, double pos[][3], double R[][9])
+{
+    Kin k; kin_compute(m, q, &k);
+    for (int i = 0; i < m->nlinks; i++) { v3cpy(pos[i], k.pl[i]); memcpy(R[i], k.Rl[i], sizeof(m3)); }
+}
+
+void or_jacobian(const OrModel* m, const double* q, int link, double J[6][OR_MAXD])
+{
+    Kin k; kin_compute(m, q, &k);
+    for (int r = 0; r < 6; r++) for (int c = 0; c < OR_MAXD; c++) J[r][c] = 0;
+    for (int i = link; i >= 0; i = m->parent[i]) {
+        if (m->jtype[i] != 1) continue;
+        int d = m->dof_of_link[i];
+        v3 r, lin; v3sub(r, k.pc[link], k.pl[i]); v3cross(lin, k.aw[i], r);
+        for (int c = 0; c < 3; c++) { J[c][d] = lin[c]; J[3 + c][d] = k.aw[i][c]; }
+    }
+}
+
+void or_link_velocity(const OrModel* m, const double* q, const double* qd, int link, double lin[3], double ang[3])
+{
+    double J[6][OR_MAXD];
+    or_jacobian(m, q, link, J);
+    for (int c = 0; c < 3; c++) {
+        lin[c] = ang[c] = 0;
+        for (int d = 0; d < m->ndof; d++) { lin[c] += J[c][d] * qd[d]; ang[c] += J[3 + c][d] * qd[d]; }
+    }
+}
+
+/* pb.calculateInverseDynamics: recursive Newton-Euler in the world frame, gravity as a base acceleration.
+ * No damping terms (bullet's inverse-dynamics tree does not model them). */
+void or_inverse_dynamics(const OrModel* m, const double* q, const double* qd, const double* qdd, double* tau)
+{
+    Kin k; kin_compute(m, q, &k);
+    v3 w[OR_MAXL], al[OR_MAXL], ap[OR_MAXL]; /* ang vel, ang acc, lin acc of the link-frame origin */
+    v3 F[OR_MAXL], N[OR_MAXL];               /* accumulated force, and moment about the link-frame origin */
+    for (int i = 0; i < m->nlinks; i++) {
+        int p = m->parent[i];
+        v3 wp, alp, app, pp;
+        if (p < 0) { v3set(wp, 0, 0, 0); v3set(alp, 0, 0, 0); v3scale(app, m->gravity, -1.0); v3set(pp, 0, 0, 0); }
+        else { v3cpy(wp, w[p]); v3cpy(alp, al[p]); v3cpy(app, ap[p]); v3cpy(pp, k.pl[p]); }
+        v3 r, t, t2;
+        v3sub(r, k.pl[i], pp);
+        /* a_pivot = a_p + alpha_p x r + w_p x (w_p x r) */
+        v3cross(t, alp, r); v3add(ap[i], app, t);
+        v3cross(t, wp, r); v3cross(t2, wp, t); v3add(ap[i], ap[i], t2);
+        v3cpy(w[i], wp); v3cpy(al[i], alp);
+        if (m->jtype[i] == 1) {
+            int d = m->dof_of_link[i];
+            v3 jv; v3scale(jv, k.aw[i], qd[d]);
+            v3add(w[i], wp, jv);
+            v3axpy(al[i], qdd ? qdd[d] : 0.0, k.aw[i]);
+            v3cross(t, wp, jv); v3add(al[i], al[i], t);
+        }
+        /* COM acceleration */
+        v3 rc, ac; v3sub(rc, k.pc[i], k.pl[i]);
+        v3cross(t, al[i], rc); v3add(ac, ap[i], t);
+        v3cross(t, w[i], rc); v3cross(t2, w[i], t); v3add(ac, ac, t2);
+        v3scale(F[i], ac, m->mass[i]);
+        /* N_com = I alpha + w x I w, I = Rc diag Rc^T */
+        v3 wl, all, Iw, Ial, nl, nw;
+        m3tmulv(wl, k.Rc[i], w[i]); m3tmulv(all, k.Rc[i], al[i]);
+        for (int c = 0; c < 3; c++) { Iw[c] = m->inertia[i][c] * wl[c]; Ial[c] = m->inertia[i][c] * all[c]; }
+        v3cross(nl, wl, Iw); v3add(nl, nl, Ial);
+        m3mulv(nw, k.Rc[i], nl);
+        v3cross(t, rc, F[i]); v3add(N[i], nw, t);
+    }
+    for (int i = m->nlinks - 1; i >= 0; i--) {
+        if (m->jtype[i] == 1) tau[m->dof_of_link[i]] = v3dot(k.aw[i], N[i]);
+        int p = m->parent[i];
+        if (p >= 0) {
+            v3 r, t; v3sub(r, k.pl[i], k.pl[p]);
+            v3cross(t, r, F[i]);
+            v3add(N[p], N[p], N[i]); v3add(N[p], N[p], t);
+            v3add(F[p], F[p], F[i]);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ spatial algebra (COM-local frames) */
+/* spatial vectors: [angular(3), linear(3)]; forces: [torque(3), force(3)] */
+typedef double sv[6];
+typedef double sm[36];
+
+typedef struct {
+    m3 E[OR_MAXL]; /* rotation parent COM frame -> this COM frame */
+    v3 r[OR_MAXL]; /* this COM minus parent COM, in PARENT COM coordinates */
+    sv S[OR_MAXL]; /* motion subspace in this COM frame */
+    m3 Rc[OR_MAXL];
+    sv v[OR_MAXL], c[OR_MAXL];
+    sm IA[OR_MAXL];
+    sv pA[OR_MAXL], U[OR_MAXL];
+    double Dinv[OR_MAXL], u[OR_MAXL];
+} Aba;
+
+static void x_motion(sv o, const m3 E, const v3 r, const sv a) /* parent -> child */
+{
+    v3 t, lin;
+    m3mulv(o, E, a);
+    v3cross(t, a, r);       /* w x r */
+    v3add(lin, a + 3, t);   /* v + w x r */
+    m3mulv(o + 3, E, lin);
+}
+static void xt_force_acc(sv acc, const m3 E, const v3 r, const sv f) /* child -> parent, accumulate */
+{
+    v3 fp, np, t;
+    m3tmulv(fp, E, f + 3);
+    m3tmulv(np, E, f);
+    v3cross(t, r, fp);
+    for (int c = 0; c < 3; c++) { acc[c] += np[c] + t[c]; acc[3 + c] += fp[c]; }
+}
+static void x_matrix(sm X, const m3 E, const v3 r) /* 6x6 motion transform parent -> child */
+{
+    /* [ E 0 ; -E rx  E ] with (w x r) = -rx w */
+    m3 rx = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0}, Erx;
+    m3mul(Erx, E, rx);
+    memset(X, 0, sizeof(sm));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            X[6 * i + j] = E[3 * i + j];
+            X[6 * (i + 3) + j + 3] = E[3 * i + j];
+            X[6 * (i + 3) + j] = -Erx[3 * i + j];
+        }
+}
+static void sm_mulv(sv o, const sm M, const sv a)
+{
+    sv t;
+    for (int i = 0; i < 6; i++) { t[i] = 0; for (int j = 0; j < 6; j++) t[i] += M[6 * i + j] * a[j]; }
+    memcpy(o, t, sizeof(sv));
+}
+static double sv_dot(const sv a, const sv b) { double s = 0; for (int i = 0; i < 6; i++) s += a[i] * b[i]; return s; }
+static void cross_motion(sv o, const sv v, const sv mvec) /* v x m */
+{
+    v3 a, b, c;
+    v3cross(a, v, mvec);
+    v3cross(b, v, mvec + 3);
+    v3cross(c, v + 3, mvec);
+    v3cpy(o, a); v3add(o + 3, b, c);
+}
+
+/* First ABA sweep + articulated inertias.  Restates btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof:
+ * link quantities live in each link's COM frame, gravity enters as a link force, per-link velocity damping
+ * f = -m v (k + k|v|), n = -I w (k + k|w|) is folded into the zero-acceleration force. */
+static void aba_setup(const OrModel* m, const double* q, const double* qd, const double* tau, int with_vel_terms, Aba* A)
+{
+    Kin k; kin_compute(m, q, &k);
+    for (int i = 0; i < m->nlinks; i++) {
+        int p = m->parent[i];
+        m3 Rp; v3 pp, dw, Rin_axis, d;
+        if (p < 0) { m3ident(Rp); v3set(pp, 0, 0, 0); } else { memcpy(Rp, k.Rc[p], sizeof(m3)); v3cpy(pp, k.pc[p]); }
+        memcpy(A->Rc[i], k.Rc[i], sizeof(m3));
+        m3tmul(A->E[i], k.Rc[i], Rp);
+        v3sub(dw, k.pc[i], pp);
+        m3tmulv(A->r[i], Rp, dw);
+        memset(A->S[i], 0, sizeof(sv));
+        if (m->jtype[i] == 1) {
+            m3tmulv(Rin_axis, k.Rc[i], k.aw[i]);            /* axis in COM frame */
+            v3sub(dw, k.pc[i], k.pl[i]); m3tmulv(d, k.Rc[i], dw); /* pivot -> COM in COM frame */
+            v3cpy(A->S[i], Rin_axis);
+            v3cross(A->S[i] + 3, Rin_axis, d);
+        }
+        /* velocities */
+        sv vp = {0, 0, 0, 0, 0, 0};
+        if (p >= 0) memcpy(vp, A->v[p], sizeof(sv));
+        x_motion(A->v[i], A->E[i], A->r[i], vp);
+        sv vj = {0, 0, 0, 0, 0, 0};
+        if (m->jtype[i] == 1 && with_vel_terms) for (int c = 0; c < 6; c++) vj[c] = A->S[i][c] * qd[m->dof_of_link[i]];
+        if (!with_vel_terms) memset(A->v[i], 0, sizeof(sv));
+        for (int c = 0; c < 6; c++) A->v[i][c] += vj[c];
+        cross_motion(A->c[i], A->v[i], vj);
+        /* isolated spatial inertia at COM */
+        memset(A->IA[i], 0, sizeof(sm));
+        for (int c = 0; c < 3; c++) { A->IA[i][7 * c] = m->inertia[i][c]; A->IA[i][7 * (c + 3)] = m->mass[i]; }
+        /* zero-acceleration force */
+        v3 gl, Iw, t;
+        m3tmulv(gl, k.Rc[i], m->gravity);
+        for (int c = 0; c < 3; c++) { A->pA[i][c] = 0; A->pA[i][3 + c] = -m->mass[i] * gl[c]; }
+        if (with_vel_terms) {
+            const double* w = A->v[i]; const double* vl = A->v[i] + 3;
+            for (int c = 0; c < 3; c++) Iw[c] = m->inertia[i][c] * w[c];
+            v3cross(t, w, Iw); for (int c = 0; c < 3; c++) A->pA[i][c] += t[c];
+            v3cross(t, w, vl); for (int c = 0; c < 3; c++) A->pA[i][3 + c] += m->mass[i] * t[c];
+            double ka = m->ang_damping * (1.0 + v3norm(w)), kl = m->lin_damping * (1.0 + v3norm(vl));
+            for (int c = 0; c < 3; c++) { A->pA[i][c] += Iw[c] * ka; A->pA[i][3 + c] += m->mass[i] * vl[c] * kl; }
+        } else {
+            memset(A->pA[i], 0, sizeof(sv)); /* delta solves: no bias */
+        }
+    }
+    /* tips -> base */
+    for (int i = m->nlinks - 1; i >= 0; i--) {
+        int p = m->parent[i];
+        sm Ia; sv pa;
+        memcpy(Ia, A->IA[i], sizeof(sm)); memcpy(pa, A->pA[i], sizeof(sv));
+        if (m->jtype[i] == 1) {
+            int d = m->dof_of_link[i];
+            sm_mulv(A->U[i], A->IA[i], A->S[i]);
+            double D = sv_dot(A->S[i], A->U[i]);
+            A->Dinv[i] = 1.0 / D;
+            A->u[i] = (tau ? tau[d] : 0.0) - sv_dot(A->S[i], A->pA[i]);
+            for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) Ia[6 * a + b] -= A->U[i][a] * A->Dinv[i] * A->U[i][b];
+            sv Iac; sm_mulv(Iac, Ia, A->c[i]);
+            for (int a = 0; a < 6; a++) pa[a] += Iac[a] + A->U[i][a] * A->Dinv[i] * A->u[i];
+        } else {
+            sv Iac; sm_mulv(Iac, Ia, A->c[i]);
+            for (int a = 0; a < 6; a++) pa[a] += Iac[a];
+        }
+        if (p >= 0) {
+            sm X, T;
+            x_matrix(X, A->E[i], A->r[i]);
+            /* IA[p] += X^T Ia X */
+            for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) { double s = 0; for (int c = 0; c < 6; c++) s += Ia[6 * a + c] * X[6 * c + b]; T[6 * a + b] = s; }
+            for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) { double s = 0; for (int c = 0; c < 6; c++) s += X[6 * c + a] * T[6 * c + b]; A->IA[p][6 * a + b] += s; }
+            xt_force_acc(A->pA[p], A->E[i], A->r[i], pa);
+        }
+    }
+}
+
+static void aba_accel(const OrModel* m, const Aba* A, double* qdd)
+{
+    sv a[OR_MAXL];
+    for (int i = 0; i < m->nlinks; i++) {
+        int p = m->parent[i];
+        sv ap = {0, 0, 0, 0, 0, 0};
+        if (p >= 0) memcpy(ap, a[p], sizeof(sv));
+        x_motion(a[i], A->E[i], A->r[i], ap);
+        for (int c = 0; c < 6; c++) a[i][c] += A->c[i][c];
+        if (m->jtype[i] == 1) {
+            double qa = A->Dinv[i] * (A->u[i] - sv_dot(A->U[i], a[i]));
+            qdd[m->dof_of_link[i]] = qa;
+            for (int c = 0; c < 6; c++) a[i][c] += A->S[i][c] * qa;
+        }
+    }
+}
+
+/* btMultiBody::calcAccelerationDeltasMultiDof: response qdd = M^-1 f to a generalized force, reusing U, D */
+static void aba_delta(const OrModel* m, const Aba* A, const double* f, double* out)
+{
+    sv p[OR_MAXL], a[OR_MAXL]; double u[OR_MAXL];
+    memset(p, 0, sizeof(p));
+    for (int i = m->nlinks - 1; i >= 0; i--) {
+        sv pa; memcpy(pa, p[i], sizeof(sv));
+        if (m->jtype[i] == 1) {
+            u[i] = f[m->dof_of_link[i]] - sv_dot(A->S[i], p[i]);
+            for (int c = 0; c < 6; c++) pa[c] += A->U[i][c] * A->Dinv[i] * u[i];
+        }
+        if (m->parent[i] >= 0) xt_force_acc(p[m->parent[i]], A->E[i], A->r[i], pa);
+    }
+    for (int i = 0; i < m->nlinks; i++) {
+        int pi = m->parent[i];
+        sv ap = {0, 0, 0, 0, 0, 0};
+        if (pi >= 0) memcpy(ap, a[pi], sizeof(sv));
+        x_motion(a[i], A->E[i], A->r[i], ap);
+        if (m->jtype[i] == 1) {
+            double qa = A->Dinv[i] * (u[i] - sv_dot(A->U[i], a[i]));
+            out[m->dof_of_link[i]] = qa;
+            for (int c = 0; c < 6; c++) a[i][c] += A->S[i][c] * qa;
+        }
+    }
+}
+
+void or_mass_matrix_inverse(const OrModel* m, const double* q, double Minv[OR_MAXD][OR_MAXD])
+{
+    static double zero[OR_MAXD];
+    Aba A; aba_setup(m, q, zero, NULL, 0, &A);
+    for (int j = 0; j < m->ndof; j++) {
+        double f[OR_MAXD] = {0}, o[OR_MAXD];
+        f[j] = 1.0;
+        aba_delta(m, &A, f, o);
+        for (int i = 0; i < m->ndof; i++) Minv[i][j] = o[i];
+    }
+}
+
+void or_forward_dynamics(const OrModel* m, const double* q, const double* qd, const double* tau, int with_damping, double* qdd)
+{
+    OrModel mm = *m;
+    if (!with_damping) { mm.lin_damping = 0; mm.ang_damping = 0; }
+    Aba A; aba_setup(&mm, q, qd, tau, 1, &A);
+    aba_accel(&mm, &A, qdd);
+}
+
+/* ------------------------------------------------------------------ stepSimulation
+ * [EXT] btMultiBodyDynamicsWorld::internalSingleStepSimulation for one fixed-base multibody with
+ * joint motors only:
+ *   1. joint damping torque -= jointDamping * qd  (PhysicsServer applies it before each step)
+ *   2. ABA (gravity, gyroscopic, link damping, applied torques); qd += dt * qdd
+ *   3. one constraint row per motor: J = e_i, response = M^-1 e_i, target velocity
+ *        rhs_v = kp * erp(=1) * (pos_target - q)/dt + qd + kd * (vel_target - qd),  |impulse| <= force * dt
+ *   4. projected Gauss-Seidel, numSolverIterations sweeps; the sweep direction alternates
+ *      (even iterations back to front); early exit only when a sweep's largest impulse change is
+ *      exactly 0 (leastSquaresResidualThreshold = 0)
+ *   5. qd += delta; q += dt * qd
+ * Call site: robots/arms/robot.py:141; parameters rl_envs/base_tactile_env.py:127-130.
+ */
+void or_step_simulation(const OrModel* m, OrState* s, const double* tau_applied)
+{
+    int n = m->ndof;
+    double tau[OR_MAXD] = {0}, qdd[OR_MAXD];
+    for (int i = 0; i < n; i++) tau[i] = (tau_applied ? tau_applied[i] : 0.0) - m->joint_damping * s->qd[i];
+    Aba A; aba_setup(m, s->q, s->qd, tau, 1, &A);
+    aba_accel(m, &A, qdd);
+    for (int i = 0; i < n; i++) s->qd[i] += m->dt * qdd[i];
+
+    /* constraint rows */
+    double resp[OR_MAXD][OR_MAXD], diaginv[OR_MAXD], rhs[OR_MAXD], lim[OR_MAXD], applied[OR_MAXD], dv[OR_MAXD];
+    int rows[OR_MAXD], nrows = 0;
+    for (int i = 0; i < n; i++) {
+        double maximp = s->max_force[i] * m->dt;
+        if (maximp == 0) continue;
+        double f[OR_MAXD] = {0}; f[i] = 1.0;
+        aba_delta(m, &A, f, resp[nrows]);
+        double denom = resp[nrows][i];
+        diaginv[nrows] = denom > 2.2204460492503131e-16 ? 1.0 / denom : 0.0;
+        double v = s->qd[i];
+        double kp = s->motor_mode[i] == 1 ? s->kp[i] : 0.0;
+        double tp = s->motor_mode[i] == 1 ? s->target_pos[i] : 0.0;
+        double pos_stab = 1.0 * (tp - s->q[i]) / m->dt;
+        double rhs_v = kp * pos_stab + v + s->kd[i] * (s->target_vel[i] - v);
+        rhs[nrows] = (rhs_v - v) * diaginv[nrows];
+        lim[nrows] = maximp; applied[nrows] = 0; rows[nrows] = i;
+        nrows++;
+    }
+    for (int i = 0; i < n; i++) dv[i] = 0;
+    for (int it = 0; it < m->solver_iters; it++) {
+        double resid = 0;
+        for (int jj = 0; jj < nrows; jj++) {
+            int r = (it & 1) ? jj : nrows - 1 - jj;
+            int d = rows[r];
+            double delta = rhs[r] - dv[d] * diaginv[r];
+            double sum = applied[r] + delta;
+            if (sum < -lim[r]) { delta = -lim[r] - applied[r]; applied[r] = -lim[r]; }
+            else if (sum > lim[r]) { delta = lim[r] - applied[r]; applied[r] = lim[r]; }
+            else applied[r] = sum;
+            for (int i = 0; i < n; i++) dv[i] += resp[r][i] * delta;
+            if (delta * delta > resid) resid = delta * delta;
+        }
+        if (resid <= 0) break;
+    }
+    for (int i = 0; i < n; i++) { s->qd[i] += dv[i]; s->q[i] += m->dt * s->qd[i]; }
+}
+
+/* Robot.step_sim (robot.py:131-141): gravity compensation (base_robot_arm.py:174-189) then stepSimulation */
+void or_step_sim(const OrModel* m, OrState* s)
+{
+    double tau[OR_MAXD];
+    or_inverse_dynamics(m, s->q, s->qd, NULL, tau);
+    or_step_simulation(m, s, tau);
+}
+
+/* ------------------------------------------------------------------ control */
+static void workframe_quat(const OrModel* m, double q[4]) { or_quat_from_euler(m->workframe_rpy, q); }
+
+/* get_current_TCP_pos_vel_workframe pose part (base_robot_arm.py:153-172, worldframe_to_workframe :62-74) */
+void or_tcp_pose_workframe(const OrModel* m, const double* q, double pos[3], double rpy[3])
+{
+    double P[OR_MAXL][3], Q[OR_MAXL][4], rpy_w[3], qw[4], wq[4], ip[3], iq[4], oq[4];
+    or_link_states(m, q, P, Q);
+    or_euler_from_quat(Q[m->tcp_link], rpy_w);
+    or_quat_from_euler(rpy_w, qw);
+    workframe_quat(m, wq);
+    or_invert_transform(m->workframe_pos, wq, ip, iq);
+    or_mul_transforms(ip, iq, P[m->tcp_link], qw, pos, oq);
+    or_euler_from_quat(oq, rpy);
+}
+
+/* solve A x = b (n x n) by LU with partial pivoting; returns smallest |pivot| / largest |pivot| */
+static double lu_solve(int n, double A[][OR_MAXD], double* b, double* x)
+{
+    double M[OR_MAXD][OR_MAXD + 1];
+    double pmin = 1e300, pmax = 0;
+    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) M[i][j] = A[i][j]; M[i][n] = b[i]; }
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++) if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+        if (piv != c) for (int j = 0; j <= n; j++) { double t = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = t; }
+        double p = fabs(M[c][c]);
+        if (p < pmin) pmin = p;
+        if (p > pmax) pmax = p;
+        if (p == 0) continue;
+        for (int r = c + 1; r < n; r++) {
+            double f = M[r][c] / M[c][c];
+            for (int j = c; j <= n; j++) M[r][j] -= f * M[c][j];
+        }
+    }
+    for (int r = n - 1; r >= 0; r--) {
+        double sacc = M[r][n];
+        for (int j = r + 1; j < n; j++) sacc -= M[r][j] * x[j];
+        x[r] = M[r][r] != 0 ? sacc / M[r][r] : 0;
+    }
+    return pmax > 0 ? pmin / pmax : 0;
+}
+
+/* x = pinv(J) v for a 6 x n Jacobian via one-sided Jacobi SVD of J^T (n x 6), rcond = 1e-15 like numpy */
+static void pinv_apply(int n, double J[6][OR_MAXD], const double v[6], double* x)
+{
+    /* work on W = J^T (n rows, 6 cols); orthogonalise columns: W V = U S */
+    double W[OR_MAXD][6], V[6][6];
+    for (int i = 0; i < n; i++) for (int j = 0; j < 6; j++) W[i][j] = J[j][i];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) V[i][j] = i == j;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+        for (int p = 0; p < 5; p++) for (int qq = p + 1; qq < 6; qq++) {
+            double a = 0, b = 0, c = 0;
+            for (int i = 0; i < n; i++) { a += W[i][p] * W[i][p]; b += W[i][qq] * W[i][qq]; c += W[i][p] * W[i][qq]; }
+            if (fabs(c) <= 1e-300 || fabs(c) <= 1e-17 * sqrt(a * b)) continue;
+            off += fabs(c);
+            double zeta = (b - a) / (2 * c);
+            double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+            double cs = 1 / sqrt(1 + t * t), sn = cs * t;
+            for (int i = 0; i < n; i++) { double wp = W[i][p], wq = W[i][qq]; W[i][p] = cs * wp - sn * wq; W[i][qq] = sn * wp + cs * wq; }
+            for (int i = 0; i < 6; i++) { double vp = V[i][p], vq = V[i][qq]; V[i][p] = cs * vp - sn * vq; V[i][qq] = sn * vp + cs * vq; }
+        }
+        if (off == 0) break;
+    }
+    /* J^T = U S V^T  =>  J = V S U^T  => pinv(J) = U S^-1 V^T ; x = sum_k U_k (V_k . v) / s_k */
+    double sig[6], smax = 0;
+    for (int k = 0; k < 6; k++) { double a = 0; for (int i = 0; i < n; i++) a += W[i][k] * W[i][k]; sig[k] = sqrt(a); if (sig[k] > smax) smax = sig[k]; }
+    for (int i = 0; i < n; i++) x[i] = 0;
+    for (int k = 0; k < 6; k++) {
+        if (sig[k] <= 1e-15 * smax) continue;
+        double vk = 0; for (int j = 0; j < 6; j++) vk += V[j][k] * v[j];
+        for (int i = 0; i < n; i++) x[i] += (W[i][k] / sig[k]) * vk / sig[k];
+    }
+}
+
+void or_tcp_velocity_control(const OrModel* m, OrState* s, const double vels_work[6])
+{
+    /* check_TCP_vel_lims (base_robot_arm.py:357-380) */
+    double pos[3], rpy[3], v[6];
+    or_tcp_pose_workframe(m, s->q, pos, rpy);
+    for (int i = 0; i < 6; i++) {
+        double cur = i < 3 ? pos[i] : rpy[i - 3];
+        int ex = (cur < m->tcp_lims[i][0] && vels_work[i] < 0) || (cur > m->tcp_lims[i][1] && vels_work[i] > 0);
+        v[i] = ex ? 0.0 : vels_work[i];
+    }
+    /* workvel_to_worldvel (:96-105) */
+    double wq[4], R[9], vw[6];
+    workframe_quat(m, wq); or_mat_from_quat(wq, R);
+    m3mulv(vw, R, v); m3mulv(vw + 3, R, v + 3);
+    /* Jacobian at the TCP link, inverse or pseudo-inverse (:296-322) */
+    double J[6][OR_MAXD], qd_t[OR_MAXD];
+    or_jacobian(m, s->q, m->tcp_link, J);
+    int n = m->ndof, use_pinv = (n != 6) || m->mg400_slave;
+    if (!use_pinv) {
+        double A[OR_MAXD][OR_MAXD];
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[i][j] = J[i][j];
+        double rc = lu_solve(6, A, vw, qd_t);
+        if (rc < 1e-13) use_pinv = 1; /* numpy matrix_rank < 6  ->  pinv branch */
+    }
+    if (use_pinv) pinv_apply(n, J, vw, qd_t);
+    if (m->mg400_slave) { /* mg400.py:111-120 */
+        qd_t[n - 3] = qd_t[1]; qd_t[n - 2] = -qd_t[1]; qd_t[n - 1] = qd_t[1] + qd_t[2];
+    }
+    for (int i = 0; i < n; i++) {
+        s->motor_mode[i] = 0; s->target_vel[i] = qd_t[i]; s->kd[i] = m->vel_gain; s->kp[i] = 0; s->max_force[i] = m->max_force;
+    }
+}
+
+void or_apply_action(const OrModel* m, OrState* s, const double vels_work[6], int repeat)
+{
+    or_tcp_velocity_control(m, s, vels_work);
+    for (int i = 0; i < repeat; i++) or_step_sim(m, s);
+}
+
+/* [EXT] pybullet IK, IK2_VEL_DLS_WITH_ORIENTATION without null space: repeat up to 100 times
+ *   dq = (J^T J + diag(0.5))^-1 J^T e,  clamped so max|dq| <= 45 deg,
+ * e = [target_pos - pos ; axis-angle of target_orn * orn^-1], until |e_pos| < residualThreshold.
+ * End-effector frame: link origin + inertial-frame orientation (SURVEY 8(c) kinematics KAT).
+ * Call site: base_robot_arm.py:201-209. */
+void or_inverse_kinematics(const OrModel* m, const double* q0, const double target_pos[3], const double target_quat[4], double* q)
+{
+    int n = m->ndof;
+    for (int i = 0; i < n; i++) q[i] = q0[i];
+    for (int it = 0; it < 100; it++) {
+        double P[OR_MAXL][3], Q[OR_MAXL][4], J[6][OR_MAXD], e[6];
+        or_link_states(m, q, P, Q);
+        or_jacobian(m, q, m->tcp_link, J);
+        for (int c = 0; c < 3; c++) e[c] = target_pos[c] - P[m->tcp_link][c];
+        double res = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        if (it > 0 && res < 1e-8) break;
+        double qi[4] = {-Q[m->tcp_link][0], -Q[m->tcp_link][1], -Q[m->tcp_link][2], Q[m->tcp_link][3]}, dq[4];
+        quat_mul(dq, target_quat, qi);
+        double wv = dq[3] < -1 ? -1 : (dq[3] > 1 ? 1 : dq[3]);
+        double ang = 2 * acos(wv);
+        double sn = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
+        if (ang > M_PI) ang -= 2 * M_PI;
+        for (int c = 0; c < 3; c++) e[3 + c] = sn > 1e-300 ? ang * dq[c] / sn : 0.0;
+        double A[OR_MAXD][OR_MAXD], b[OR_MAXD], d[OR_MAXD];
+        for (int i = 0; i < n; i++) {
+            b[i] = 0; for (int r = 0; r < 6; r++) b[i] += J[r][i] * e[r];
+            for (int j = 0; j < n; j++) { A[i][j] = i == j ? 0.5 : 0.0; for (int r = 0; r < 6; r++) A[i][j] += J[r][i] * J[r][j]; }
+        }
+        lu_solve(n, A, b, d);
+        double mx = 0; for (int i = 0; i < n; i++) if (fabs(d[i]) > mx) mx = fabs(d[i]);
+        double sc = mx > M_PI / 4 ? (M_PI / 4) / mx : 1.0;
+        for (int i = 0; i < n; i++) q[i] += sc * d[i];
+    }
+}
+
+/* Robot.reset (robot.py:114-125): arm.reset (base_robot_arm.py:17-37) -> tcp_direct_workframe_move (:191-226)
+ * -> blocking_move(max_steps=1000, constant_vel=0.001) (robot.py:188-260).  Position motors set inside
+ * blocking_move pass no `forces`, so pybullet's default (1e5) applies [EXT]. */
+int or_robot_reset(const OrModel* m, OrState* s, const double* rest_q, const double tcp_pos_work[3], const double tcp_rpy_work[3])
+{
+    int n = m->ndof;
+    for (int i = 0; i < n; i++) {
+        s->q[i] = rest_q[i]; s->qd[i] = 0;
+        s->motor_mode[i] = 1; s->target_pos[i] = rest_q[i]; s->target_vel[i] = 0; s->kp[i] = m->pos_gain; s->kd[i] = m->vel_gain; s->max_force[i] = m->max_force;
+    }
+    /* workframe_to_worldframe (:47-60) */
+    double wq[4], tq[4], tpos[3], tquat[4], trpy[3], targ_orn[4], targ_j[OR_MAXD];
+    workframe_quat(m, wq);
+    or_quat_from_euler(tcp_rpy_work, tq);
+    or_mul_transforms(m->workframe_pos, wq, tcp_pos_work, tq, tpos, tquat);
+    or_euler_from_quat(tquat, trpy);
+    or_quat_from_euler(trpy, targ_orn);
+    or_inverse_kinematics(m, s->q, tpos, targ_orn, targ_j);
+    for (int i = 0; i < n; i++) { s->target_pos[i] = targ_j[i]; }
+    double cv = 0.001;
+    int steps = 0;
+    for (int it = 0; it < 1000; it++) {
+        double P[OR_MAXL][3], Q[OR_MAXL][4], diff[OR_MAXD], nrm = 0, curq[OR_MAXD], curqd[OR_MAXD];
+        or_link_states(m, s->q, P, Q);
+        int all_small = 1;
+        for (int i = 0; i < n; i++) { curq[i] = s->q[i]; curqd[i] = s->qd[i]; diff[i] = targ_j[i] - s->q[i]; nrm += diff[i] * diff[i]; }
+        nrm = sqrt(nrm);
+        for (int i = 0; i < n; i++) {
+            double vdir = nrm > 0 ? diff[i] / nrm : 0.0;
+            s->motor_mode[i] = 1; s->target_pos[i] = curq[i] + vdir * cv; s->target_vel[i] = 0;
+            s->kp[i] = m->pos_gain; s->kd[i] = m->vel_gain; s->max_force[i] = 100000.0;
+            if (!(fabs(diff[i]) < cv)) all_small = 0;
+        }
+        if (all_small) cv /= 2;
+        or_step_sim(m, s);
+        steps++;
+        double tot = 0, pe = 0, ip = 0;
+        for (int i = 0; i < n; i++) tot += fabs(curqd[i]);
+        for (int c = 0; c < 3; c++) pe += fabs(tpos[c] - P[m->tcp_link][c]);
+        for (int c = 0; c < 4; c++) ip += targ_orn[c] * Q[m->tcp_link][c];
+        double ca = 2 * ip * ip - 1; ca = ca < -1 ? -1 : (ca > 1 ? 1 : ca);
+        double oe = acos(ca);
+        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
+    }
+    return steps;
+}
+
+/* ------------------------------------------------------------------ tactile raster */
+/* TactileSensor.update_cam_frame + get_imgs camera vectors (tactile_sensor.py:150-229) */
+void or_camera_frame(const OrModel* m, const double* q, double eye[3], double fwd[3], double up[3], double right[3])
+{
+    double P[OR_MAXL][3], Q[OR_MAXL][4], cq[4], cp[3], co[4], R[9];
+    or_link_states(m, q, P, Q);
+    or_quat_from_euler(m->cam_rpy, cq);
+    or_mul_transforms(P[m->body_link], Q[m->body_link], m->cam_pos, cq, cp, co);
+    or_mat_from_quat(co, R);
+    v3 ex = {1, 0, 0}, ez = {0, 0, 1}, f, u, sdir;
+    m3mulv(f, R, ex); m3mulv(u, R, ez);
+    /* computeViewMatrix(eye, eye + focal*f, u): f = normalize(target-eye), s = normalize(f x up), u = s x f */
+    double fn = v3norm(f); v3scale(f, f, 1 / fn);
+    double un = v3norm(u); v3scale(u, u, 1 / un);
+    v3cross(sdir, f, u); double sn = v3norm(sdir); v3scale(sdir, sdir, 1 / sn);
+    v3cross(u, sdir, f);
+    v3cpy(eye, cp); v3cpy(fwd, f); v3cpy(up, u); v3cpy(right, sdir);
+}
+
+/* z-buffer by per-pixel ray casting (pixel centres; row 0 = top), window depth d = f/(f-n) (1 - n/z) */
+static void raster_tris_d(const double eye[3], const double fwd[3], const double up[3], const double right[3],
+                          double fov_deg, double near_, double far_, int S, const double* tris, int ntri, float* depth)
+{
+    double th = tan(fov_deg * (M_PI / 180.0) / 2.0);
+    for (int t = 0; t < ntri; t++) {
+        const double* T = tris + 9 * t;
+        /* eye-space vertices (x right, y up, z forward) */
+        double ve[3][3]; int all_front = 1;
+        for (int k = 0; k < 3; k++) {
+            v3 d; v3sub(d, T + 3 * k, eye);
+            ve[k][0] = v3dot(d, right); ve[k][1] = v3dot(d, up); ve[k][2] = v3dot(d, fwd);
+            if (ve[k][2] <= 1e-6) all_front = 0;
+        }
+        int c0 = 0, c1 = S - 1, r0 = 0, r1 = S - 1;
+        if (all_front) {
+            double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+            for (int k = 0; k < 3; k++) {
+                double x = ve[k][0] / (ve[k][2] * th), y = ve[k][1] / (ve[k][2] * th);
+                if (x < xmin) xmin = x; if (x > xmax) xmax = x; if (y < ymin) ymin = y; if (y > ymax) ymax = y;
+            }
+            c0 = (int)floor((xmin + 1) * 0.5 * S - 0.5) - 1; c1 = (int)ceil((xmax + 1) * 0.5 * S - 0.5) + 1;
+            r0 = (int)floor((1 - ymax) * 0.5 * S - 0.5) - 1; r1 = (int)ceil((1 - ymin) * 0.5 * S - 0.5) + 1;
+            if (c0 < 0) c0 = 0; if (r0 < 0) r0 = 0; if (c1 > S - 1) c1 = S - 1; if (r1 > S - 1) r1 = S - 1;
+        }
+        v3 e1, e2; v3sub(e1, ve[1], ve[0]); v3sub(e2, ve[2], ve[0]);
+        for (int r = r0; r <= r1; r++)
+            for (int c = c0; c <= c1; c++) {
+                double xn = (c + 0.5) / S * 2 - 1, yn = 1 - (r + 0.5) / S * 2;
+                v3 dir = {xn * th, yn * th, 1.0}, pv, tv, qv;
+                /* Moller-Trumbore, origin at 0 */
+                v3cross(pv, dir, e2);
+                double det = v3dot(e1, pv);
+                if (fabs(det) < 1e-300) continue;
+                double inv = 1.0 / det;
+                v3scale(tv, ve[0], -1.0);
+                double u = v3dot(tv, pv) * inv;
+                if (u < -1e-12 || u > 1 + 1e-12) continue;
+                v3cross(qv, tv, e1);
+                double v = v3dot(dir, qv) * inv;
+                if (v < -1e-12 || u + v > 1 + 1e-12) continue;
+                double z = v3dot(e2, qv) * inv; /* dir.z = 1 -> t = z_eye */
+                if (z < near_ || z > far_) continue;
+                float d = (float)(far_ / (far_ - near_) * (1.0 - near_ / z));
+                if (d < depth[r * S + c]) depth[r * S + c] = d;
+            }
+    }
+}
+
+void or_depth_image(const double eye[3], const double fwd[3], const double up[3], const double right[3],
+                    double fov_deg, double near_, double far_, int S, const float* tris, int ntri, float* depth_out)
+{
+    double* td = (double*)malloc(sizeof(double) * 9 * (size_t)ntri);
+    for (long i = 0; i < 9L * ntri; i++) td[i] = tris[i];
+    for (int i = 0; i < S * S; i++) depth_out[i] = 1.0f;
+    raster_tris_d(eye, fwd, up, right, fov_deg, near_, far_, S, td, ntri, depth_out);
+    free(td);
+}
+
+/* TactileSensor.t_s_camera (tactile_sensor.py:261-294), float32 arithmetic like numpy */
+void or_tactile_image(const OrModel* m, const double* q, int S, const double* tris_world, int ntri,
+                      const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
+                      int border_on, unsigned char* img_out, float* depth_out)
+{
+    double eye[3], fwd[3], up[3], right[3];
+    or_camera_frame(m, q, eye, fwd, up, right);
+    float* cur = (float*)malloc(sizeof(float) * (size_t)S * S);
+    memcpy(cur, nodef_dep, sizeof(float) * (size_t)S * S);
+    raster_tris_d(eye, fwd, up, right, m->fov_deg, m->near_, m->far_, S, tris_world, ntri, cur);
+    const float eps = (float)1e-4, maxpen = (float)0.05;
+    for (int i = 0; i < S * S; i++) {
+        float diff = cur[i] - nodef_dep[i];
+        if (diff >= -eps && diff <= eps) diff = 0.0f;
+        float pen = fabsf(diff);
+        float cl = pen < 0.0f ? 0.0f : (pen > maxpen ? maxpen : pen);
+        float val = (cl / maxpen) * 255.0f;
+        unsigned char o = (unsigned char)val;
+        if (border_on && border_mask[i] == 1) o = (unsigned char)nodef_gray[i];
+        img_out[i] = o;
+        if (depth_out) depth_out[i] = cur[i];
+    }
+    free(cur);
+}

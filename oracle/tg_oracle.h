@@ -1,0 +1,116 @@
+/*
+ * oracle/tg_oracle.h - CPU restatement (plain C, fp64) of the tactile_gym hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product (tactile_gym_b200/) never does.
+ *
+ * PARITY STATUS
+ *   raster + tactile post-process : pinned by the reference's .npy reference images
+ *                                   (tests/test_oracle_raster.py).
+ *   kinematics                    : pinned by the reference's rest_poses <-> workframe design
+ *                                   identities (tests/test_oracle_kinematics.py).
+ *   dynamics (stepSimulation, IK) : PARITY UNPINNED.  The arithmetic lives in `pybullet`
+ *                                   (requirements.txt:6, ">=3.1.0", not vendored, not installed).
+ *                                   Restated from the published Bullet3 btMultiBody algorithm
+ *                                   (Featherstone ABA in link-COM frames + projected Gauss-Seidel
+ *                                   over multibody constraint rows); call sites anchored below.
+ *
+ * Every function cites the reference file:line (relative to /root/reference/tactile_gym/) it follows.
+ */
+#ifndef TG_ORACLE_H
+#define TG_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OR_MAXL 16 /* links  */
+#define OR_MAXD 8  /* dofs   */
+
+typedef struct {
+    int nlinks, ndof;
+    int parent[OR_MAXL];    /* bullet link index of parent, -1 = base */
+    int jtype[OR_MAXL];     /* 0 fixed, 1 revolute */
+    int dof_of_link[OR_MAXL]; /* -1 for fixed */
+    int link_of_dof[OR_MAXD];
+    double joint_xyz[OR_MAXL][3], joint_rpy[OR_MAXL][3], axis[OR_MAXL][3];
+    double inertial_xyz[OR_MAXL][3], inertial_rpy[OR_MAXL][3];
+    double mass[OR_MAXL], inertia[OR_MAXL][3];
+    int tcp_link, body_link;
+    /* physics parameters (base_tactile_env.py:125-130, base_robot_arm.py:24-25) */
+    double gravity[3], dt;
+    int solver_iters;
+    double lin_damping, ang_damping, joint_damping;
+    /* arm frames (base_robot_arm.py:39-46, set_TCP_lims :114-118) */
+    double workframe_pos[3], workframe_rpy[3];
+    double tcp_lims[6][2];
+    double max_force, pos_gain, vel_gain;
+    /* MG400 slaved joints (mg400.py:111-120): 1 = apply the parallelogram overwrite */
+    int mg400_slave;
+    /* camera (tactile_sensor.py:127-187) */
+    double cam_pos[3], cam_rpy[3], fov_deg, focal_dist, near_, far_;
+} OrModel;
+
+/* joint motor state (the btMultiBodyJointMotor each joint owns) */
+typedef struct {
+    double q[OR_MAXD], qd[OR_MAXD];
+    int motor_mode[OR_MAXD];   /* 0 = velocity, 1 = position */
+    double target_pos[OR_MAXD], target_vel[OR_MAXD], kp[OR_MAXD], kd[OR_MAXD], max_force[OR_MAXD];
+} OrState;
+
+/* ---- frame math (pybullet helpers used at base_robot_arm.py:47-118) ---- */
+void or_quat_from_euler(const double rpy[3], double q[4]);
+void or_euler_from_quat(const double q[4], double rpy[3]);
+void or_mul_transforms(const double pa[3], const double qa[4], const double pb[3], const double qb[4], double po[3], double qo[4]);
+void or_invert_transform(const double p[3], const double q[4], double po[3], double qo[4]);
+void or_mat_from_quat(const double q[4], double R[9]);
+
+/* ---- kinematics ---- */
+/* getLinkState(...)[0:2] of every link: world pose of the link's INERTIAL frame (base_robot_arm.py:136-151) */
+void or_link_states(const OrModel* m, const double* q, double pos[][3], double quat[][4]);
+/* world pose of every URDF link frame (getLinkState(...)[4:6]); R row-major.  Visual meshes live in these frames. */
+void or_link_frames(const OrModel* m, const double* q, double pos[][3], double R[][9]);
+/* pb.calculateJacobian(link, localPosition=0) (base_robot_arm.py:300-307): rows 0-2 linear, 3-5 angular; [6][ndof] */
+void or_jacobian(const OrModel* m, const double* q, int link, double J[6][OR_MAXD]);
+/* pb.calculateInverseDynamics(q, qd, 0) (base_robot_arm.py:174-179) */
+void or_inverse_dynamics(const OrModel* m, const double* q, const double* qd, const double* qdd, double* tau);
+/* world-frame velocity of a link's inertial frame origin (getLinkState(...)[6:8]) */
+void or_link_velocity(const OrModel* m, const double* q, const double* qd, int link, double lin[3], double ang[3]);
+
+/* ---- dynamics: one pb.stepSimulation() with extra joint torques tau (robot.py:131-141) ---- */
+void or_step_simulation(const OrModel* m, OrState* s, const double* tau_applied);
+/* Robot.step_sim(): gravity compensation + stepSimulation (robot.py:131-141) */
+void or_step_sim(const OrModel* m, OrState* s);
+/* joint-space mass matrix via ABA unit responses (test hook) */
+void or_mass_matrix_inverse(const OrModel* m, const double* q, double Minv[OR_MAXD][OR_MAXD]);
+/* forward dynamics qdd = ABA(q, qd, tau) without damping (test hook: RNEA(ABA(tau)) == tau) */
+void or_forward_dynamics(const OrModel* m, const double* q, const double* qd, const double* tau, int with_damping, double* qdd);
+
+/* ---- control ---- */
+/* BaseRobotArm.tcp_velocity_control (base_robot_arm.py:281-332, mg400.py:77-129) */
+void or_tcp_velocity_control(const OrModel* m, OrState* s, const double vels_work[6]);
+/* Robot.apply_action, TCP_velocity_control branch (robot.py:156-186) */
+void or_apply_action(const OrModel* m, OrState* s, const double vels_work[6], int repeat);
+/* BaseRobotArm.reset + tcp_direct_workframe_move + Robot.blocking_move (robot.py:114-125,188-260).
+ * returns number of substeps used */
+int or_robot_reset(const OrModel* m, OrState* s, const double* rest_q, const double tcp_pos_work[3], const double tcp_rpy_work[3]);
+/* pb.calculateInverseKinematics(..., maxNumIterations=100, residualThreshold=1e-8) (base_robot_arm.py:201-209) */
+void or_inverse_kinematics(const OrModel* m, const double* q0, const double target_pos[3], const double target_quat[4], double* q_out);
+void or_tcp_pose_workframe(const OrModel* m, const double* q, double pos[3], double rpy[3]);
+
+/* ---- tactile raster (tactile_sensor.py:150-294) ---- */
+/* camera pose from the body link: eye, and the 3 camera axes (forward, up, right) in world */
+void or_camera_frame(const OrModel* m, const double* q, double eye[3], double fwd[3], double up[3], double right[3]);
+/* window-space depth image of `ntri` world-space triangles composited over nodef_dep (float32), then the
+ * t_s_camera post-process -> uint8 [S*S].  depth_out (float32 [S*S]) may be NULL. */
+void or_tactile_image(const OrModel* m, const double* q, int S, const double* tris_world, int ntri,
+                      const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
+                      int border_on, unsigned char* img_out, float* depth_out);
+/* depth image only (no nodef composite): background = 1.0 (far plane).  Used by the fixture KAT. */
+void or_depth_image(const double eye[3], const double fwd[3], const double up[3], const double right[3],
+                    double fov_deg, double near_, double far_, int S, const float* tris, int ntri, float* depth_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
