@@ -1,0 +1,178 @@
+/*
+ * tactile_gym_b200.h - C ABI of the batched tactile-RL environment engine (libtactile_gym_b200.so).
+ *
+ * The reference (ac-93/tactile_gym) has no FFI of its own: its seam to native code is the pybullet
+ * C-extension, called ~100 times per env step through BulletClient.  This ABI sits one
+ * level up and replaces, for N envs at once, exactly the calls on the per-step hot path:
+ *
+ *   tg_step      <- BaseTactileEnv.step                      rl_envs/base_tactile_env.py:166-185
+ *                     encode/scale actions                   rl_envs/exploration/edge_follow/edge_follow_env.py:345-369,
+ *                                                            rl_envs/base_tactile_env.py:141-164
+ *                     Robot.apply_action                     robots/arms/robot.py:156-186
+ *                       tcp_velocity_control                 robots/arms/base_robot_arm.py:281-332 (pb.calculateJacobian :300)
+ *                       24 x Robot.step_sim                  robots/arms/robot.py:131-141
+ *                         pb.calculateInverseDynamics        robots/arms/base_robot_arm.py:174-179
+ *                         pb.stepSimulation                  robots/arms/robot.py:141
+ *                     get_step_data / reward / termination   rl_envs/exploration/edge_follow/edge_follow_env.py:371-452
+ *                     TactileSensor.get_imgs + t_s_camera    sensors/tactile_sensor.py:212-294 (pb.getCameraImage :239)
+ *   tg_reset     <- EdgeFollowEnv.reset / Robot.reset        edge_follow_env.py:311-336, robots/arms/robot.py:114-125,188-260
+ *                     pb.calculateInverseKinematics          robots/arms/base_robot_arm.py:201-209
+ *   tg_set_draws <- self.np_random.uniform(...) draws        edge_follow_env.py:293-297,240 (host generates them with the
+ *                                                            gym RandomState so seeds reproduce; the device consumes them)
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch types.  `d_*` arguments are DEVICE pointers owned by the
+ *     caller (e.g. torch.cuda tensors' data_ptr()); `h_*` are host pointers.
+ *   - every call returns 0 on success or a negative TG_E* code, never throws / exits; tg_last_error()
+ *     gives the thread-local message.
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*); no hidden syncs in
+ *     tg_step / tg_reset.  A TgWorld is not thread safe.  One world per device; one rank per GPU.
+ *   - there is no CPU fallback: without a CUDA device tg_create fails with TG_ENODEV.
+ */
+#ifndef TACTILE_GYM_B200_H
+#define TACTILE_GYM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_VERSION 100 /* 0.1.0 */
+
+#define TG_OK 0
+#define TG_EINVAL (-1)
+#define TG_ENODEV (-2)
+#define TG_ECUDA (-3)
+#define TG_ENOMEM (-4)
+#define TG_EUNSUPPORTED (-5)
+
+#define TG_MAXB 8     /* moving bodies == dofs of the arm */
+#define TG_MAXSUB 16  /* original URDF links that carry mass (per-link damping terms) */
+#define TG_MAXTRI 64  /* stimulus triangles per env */
+#define TG_MAXDRAW 4  /* random draws consumed per reset */
+
+/* arm topologies the kernels are specialised for */
+#define TG_TOPO_CHAIN6 0 /* UR5: 6 revolute joints in a serial chain               */
+#define TG_TOPO_MG400 1  /* MG400: 8 revolute joints, tree 0-1-2-3-4 + 0-5-6-7       */
+
+/* tasks */
+#define TG_TASK_EDGE_FOLLOW 0
+
+/* Reduced arm model: fixed joints are merged into their moving parent at asset-compile time
+ * (tactile_gym_b200/scene.py); `sub_*` keeps the original mass-carrying links for bullet's per-link
+ * velocity damping.  All vectors are in the owning body's frame (= URDF frame of its first link). */
+typedef struct {
+    int32_t topo, nb, nsub, pad0;
+    double jpos[TG_MAXB][3];   /* joint origin in the parent body's frame          */
+    double jrot[TG_MAXB][9];   /* parent body frame -> this body frame at q = 0     */
+    double axis[TG_MAXB][3];   /* unit joint axis in this body's frame              */
+    double mass[TG_MAXB];
+    double com[TG_MAXB][3];
+    double inertia[TG_MAXB][6]; /* about the COM, body frame: xx xy xz yy yz zz       */
+    int32_t sub_body[TG_MAXSUB];
+    double sub_mass[TG_MAXSUB];
+    double sub_com[TG_MAXSUB][3];
+    double sub_rot[TG_MAXSUB][9]; /* body frame -> that link's inertial frame           */
+    double sub_inertia[TG_MAXSUB][3];
+    int32_t tcp_body, cam_body;
+    double tcp_pos[3], tcp_rot[9]; /* TCP link's INERTIAL frame in tcp_body's frame (getLinkState()[0:2]) */
+    double cam_pos[3], cam_rot[9]; /* camera frame (body link inertial frame o cam_pos/cam_rpy)           */
+} TgArm;
+
+typedef struct {
+    double gravity[3];
+    double dt;              /* 1/240 */
+    int32_t solver_iters;   /* 150   */
+    int32_t substeps;       /* 24    */
+    double lin_damping, ang_damping, joint_damping; /* 0.04 0.04 0.01 */
+    double max_force, pos_gain, vel_gain;           /* 1000 1 1       */
+    double blocking_force;  /* 1e5: pybullet's default when setJointMotorControlArray gets no `forces` */
+    int32_t gravity_comp;   /* 1: Robot.step_sim's calculateInverseDynamics torque is applied */
+    int32_t pad0;
+} TgPhysics;
+
+typedef struct {
+    int32_t task, act_dim, max_steps, n_draws;
+    int32_t act_index[6];      /* policy action k -> slot of the 6-vector (x y z Rx Ry Rz), -1 unused */
+    double act_min, act_max;   /* +-0.25 */
+    double act_lo[6], act_hi[6]; /* per-slot affine range (m/s, rad/s) */
+    double workframe_pos[3], workframe_rpy[3];
+    double tcp_lims[6][2];
+    /* edge_follow */
+    double edge_pos[3], edge_len, edge_height, termination_dist;
+    double embed_lo, embed_hi; /* uniform range; lo == hi -> fixed */
+    double init_rpy[3];
+    double draw_default[TG_MAXDRAW];
+} TgTask;
+
+typedef struct {
+    int32_t image_size;  /* S */
+    int32_t border_on;
+    double fov_deg, near_, far_;
+    const float* h_nodef_dep;      /* [S*S] */
+    const float* h_nodef_gray;     /* [S*S] */
+    const uint8_t* h_border_mask;  /* [S*S] */
+    int32_t n_tri, pad0;
+    const double* h_tris;          /* [n_tri][3][3] stimulus triangles in the stimulus frame */
+} TgSensor;
+
+typedef struct {
+    int32_t n_envs;
+    int32_t lanes_per_warp; /* physics kernels: active lanes per warp (8/16/32), 0 = auto */
+    TgArm arm;
+    TgPhysics phys;
+    TgTask task;
+    TgSensor sensor;
+    const double* h_rest_q; /* [nb] */
+} TgConfig;
+
+typedef struct TgWorld TgWorld;
+
+int tg_version(void);
+const char* tg_last_error(void);
+
+int tg_create(const TgConfig* cfg, int device, TgWorld** out);
+int tg_destroy(TgWorld* w);
+
+/* Upload random draws for future resets: h_draws[n_envs][rounds][n_draws] (double).  The r-th reset of
+ * env i after this call consumes h_draws[i][r].  Synchronous host->device copy. */
+int tg_set_draws(TgWorld* w, const double* h_draws, int rounds);
+/* resets consumed per env since the last tg_set_draws (device->host, synchronises the stream) */
+int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream);
+
+/* Reset envs with d_mask[i] != 0 (NULL: all) and render their first observation into d_obs[i]. */
+int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream);
+
+/* One env step for all envs.  d_actions [N][act_dim] f32, d_obs [N][S][S][1] u8, d_reward [N] f32,
+ * d_done [N] u8.  Envs that finish are reset in place and d_obs holds their first observation of the new
+ * episode (VecEnv semantics); if d_term_obs != NULL their terminal observation is kept in d_term_obs[i]. */
+int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float* d_reward, uint8_t* d_done,
+            uint8_t* d_term_obs, void* stream);
+
+/* kernel-level entry points (tests, ncu) */
+int tg_physics_only(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, void* stream);
+int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream);
+int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream);
+
+/* state access (parity tests, checkpointing).  Layout: per env doubles
+ * [q(nb) qd(nb) tcp_pos(3) tcp_quat(4) embed edge_ang steps reset_substeps] */
+int tg_state_size(const TgWorld* w); /* doubles per env */
+int tg_get_state(TgWorld* w, double* h_state, void* stream);
+int tg_set_state(TgWorld* w, const double* h_state, void* stream);
+/* camera of every env as the raster sees it: [N][12] doubles eye, fwd, up, right */
+int tg_get_camera(TgWorld* w, double* h_cam, void* stream);
+
+/* test hooks on the dynamics kernels: inputs/outputs are HOST arrays, n rows */
+int tg_test_inverse_dynamics(TgWorld* w, int n, const double* h_q, const double* h_qd, double* h_tau);
+int tg_test_mass_matrix(TgWorld* w, int n, const double* h_q, double* h_M /* [n][nb][nb] */);
+int tg_test_substep(TgWorld* w, int n, int nsteps, double* h_q, double* h_qd, const double* h_target_vel);
+
+/* number of kernels launched by this library since creation (bench.py's gpu_launches) */
+long long tg_launch_count(const TgWorld* w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

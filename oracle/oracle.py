@@ -329,7 +329,8 @@ class EdgeFollowOracle:
         p, _ = self.tcp_world()
         goal_dist = np.linalg.norm(p[:2] - self.goal_pos[:2])
         p1, p2 = self.edge_end_points[0, :2], self.edge_end_points[1, :2]
-        edge_dist = np.abs(np.cross(p2 - p1, p1 - p[:2])) / np.linalg.norm(p2 - p1)
+        a_, b_ = p2 - p1, p1 - p[:2]
+        edge_dist = np.abs(a_[0] * b_[1] - a_[1] * b_[0]) / np.linalg.norm(p2 - p1)
         done = bool(goal_dist < self.termination_dist or self.steps >= self.max_steps)
         return -(1.0 * goal_dist + 10.0 * edge_dist), done
 

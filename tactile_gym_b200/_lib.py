@@ -1,0 +1,116 @@
+"""ctypes binding of libtactile_gym_b200.so (include/tactile_gym_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, creating a world raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtactile_gym_b200.so")
+
+TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 4
+TG_TOPO_CHAIN6, TG_TOPO_MG400 = 0, 1
+TG_TASK_EDGE_FOLLOW = 0
+
+D3 = C.c_double * 3
+D9 = C.c_double * 9
+
+
+class TgArm(C.Structure):
+    _fields_ = [
+        ("topo", C.c_int32), ("nb", C.c_int32), ("nsub", C.c_int32), ("pad0", C.c_int32),
+        ("jpos", D3 * TG_MAXB), ("jrot", D9 * TG_MAXB), ("axis", D3 * TG_MAXB),
+        ("mass", C.c_double * TG_MAXB), ("com", D3 * TG_MAXB), ("inertia", (C.c_double * 6) * TG_MAXB),
+        ("sub_body", C.c_int32 * TG_MAXSUB), ("sub_mass", C.c_double * TG_MAXSUB), ("sub_com", D3 * TG_MAXSUB),
+        ("sub_rot", D9 * TG_MAXSUB), ("sub_inertia", D3 * TG_MAXSUB),
+        ("tcp_body", C.c_int32), ("cam_body", C.c_int32),
+        ("tcp_pos", D3), ("tcp_rot", D9), ("cam_pos", D3), ("cam_rot", D9),
+    ]
+
+
+class TgPhysics(C.Structure):
+    _fields_ = [
+        ("gravity", D3), ("dt", C.c_double), ("solver_iters", C.c_int32), ("substeps", C.c_int32),
+        ("lin_damping", C.c_double), ("ang_damping", C.c_double), ("joint_damping", C.c_double),
+        ("max_force", C.c_double), ("pos_gain", C.c_double), ("vel_gain", C.c_double), ("blocking_force", C.c_double),
+        ("gravity_comp", C.c_int32), ("pad0", C.c_int32),
+    ]
+
+
+class TgTask(C.Structure):
+    _fields_ = [
+        ("task", C.c_int32), ("act_dim", C.c_int32), ("max_steps", C.c_int32), ("n_draws", C.c_int32),
+        ("act_index", C.c_int32 * 6), ("act_min", C.c_double), ("act_max", C.c_double),
+        ("act_lo", C.c_double * 6), ("act_hi", C.c_double * 6),
+        ("workframe_pos", D3), ("workframe_rpy", D3), ("tcp_lims", (C.c_double * 2) * 6),
+        ("edge_pos", D3), ("edge_len", C.c_double), ("edge_height", C.c_double), ("termination_dist", C.c_double),
+        ("embed_lo", C.c_double), ("embed_hi", C.c_double), ("init_rpy", D3), ("draw_default", C.c_double * TG_MAXDRAW),
+    ]
+
+
+class TgSensor(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int32), ("border_on", C.c_int32),
+        ("fov_deg", C.c_double), ("near_", C.c_double), ("far_", C.c_double),
+        ("h_nodef_dep", C.POINTER(C.c_float)), ("h_nodef_gray", C.POINTER(C.c_float)), ("h_border_mask", C.POINTER(C.c_uint8)),
+        ("n_tri", C.c_int32), ("pad0", C.c_int32), ("h_tris", C.POINTER(C.c_double)),
+    ]
+
+
+class TgConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("lanes_per_warp", C.c_int32),
+        ("arm", TgArm), ("phys", TgPhysics), ("task", TgTask), ("sensor", TgSensor),
+        ("h_rest_q", C.POINTER(C.c_double)),
+    ]
+
+
+EXPORTS = [
+    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_get_reset_counts", "tg_reset", "tg_step",
+    "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
+    "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_launch_count",
+]
+
+_lib = None
+
+
+class TgError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise TgError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(tactile_gym_b200 has no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.tg_last_error.restype = C.c_char_p
+    lib.tg_create.argtypes = [C.POINTER(TgConfig), C.c_int, C.POINTER(vp)]
+    lib.tg_destroy.argtypes = [vp]
+    lib.tg_set_draws.argtypes = [vp, vp, C.c_int]
+    lib.tg_get_reset_counts.argtypes = [vp, vp, vp]
+    lib.tg_reset.argtypes = [vp, vp, vp, vp]
+    lib.tg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.tg_physics_only.argtypes = [vp, vp, vp, vp, vp]
+    lib.tg_raster_only.argtypes = [vp, vp, vp]
+    lib.tg_reset_only.argtypes = [vp, vp, vp]
+    lib.tg_state_size.argtypes = [vp]
+    lib.tg_get_state.argtypes = [vp, vp, vp]
+    lib.tg_set_state.argtypes = [vp, vp, vp]
+    lib.tg_get_camera.argtypes = [vp, vp, vp]
+    lib.tg_test_inverse_dynamics.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.tg_test_mass_matrix.argtypes = [vp, C.c_int, vp, vp]
+    lib.tg_test_substep.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.tg_launch_count.argtypes = [vp]
+    lib.tg_launch_count.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TgError("tactile_gym_b200 error %d: %s" % (rc, load().tg_last_error().decode()))

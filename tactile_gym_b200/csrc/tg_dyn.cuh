@@ -1,0 +1,620 @@
+// tg_dyn.cuh - per-env articulated-body dynamics + constraint solve, one thread per env, fp64.
+//
+// Replaces, per physics substep, what the reference does with three pybullet calls
+// (robots/arms/robot.py:131-141):  calculateInverseDynamics (gravity compensation,
+// robots/arms/base_robot_arm.py:174-189) + setJointMotorControlArray(TORQUE_CONTROL) + stepSimulation.
+//
+// Design (B200-first, not a port of btMultiBody):
+//   * fixed joints are merged away at asset-compile time, so a UR5 is 6 bodies, not 11 links;
+//   * all spatial quantities are expressed in world axes about the WORLD ORIGIN, which makes composite
+//     inertias and wrenches plain sums over the subtree (no 6x6 transforms): joint-space inertia by CRBA,
+//     6x6 Cholesky inverse -> the constraint response matrix A = M^-1 that bullet builds column by column
+//     with calcAccelerationDeltasMultiDof;
+//   * the arm's topology is a template parameter: every loop unrolls, every array lives in registers;
+//   * the motor rows (J = e_i) are solved by the same projected Gauss-Seidel sweep bullet runs
+//     (numSolverIterations = 150, alternating sweep direction, impulse clamp force*dt, exact-zero
+//     residual exit), staged in registers rather than shared memory because a row is 6 numbers.
+// The CPU oracle (oracle/tg_oracle.c) restates bullet's own formulation (ABA in link-COM frames over all
+// 11 links); agreement between the two is the parity test.
+#pragma once
+#include <math.h>
+
+#include "../../include/tactile_gym_b200.h"
+
+#define TGD __device__ __forceinline__
+
+struct TopoChain6 {
+    static constexpr int NB = 6;
+    __host__ __device__ static constexpr int parent(int i) { return i - 1; }
+};
+struct TopoMG400 {
+    static constexpr int NB = 8;
+    __host__ __device__ static constexpr int parent(int i) { return i == 0 ? -1 : (i == 5 ? 0 : i - 1); }
+};
+
+// ---------------------------------------------------------------- small vector helpers
+TGD void v3cross(double* o, const double* a, const double* b)
+{
+    double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+TGD double v3dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+TGD void m3mulv(double* o, const double* M, const double* a)
+{
+    double x = M[0] * a[0] + M[1] * a[1] + M[2] * a[2];
+    double y = M[3] * a[0] + M[4] * a[1] + M[5] * a[2];
+    double z = M[6] * a[0] + M[7] * a[1] + M[8] * a[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+TGD void m3tmulv(double* o, const double* M, const double* a)
+{
+    double x = M[0] * a[0] + M[3] * a[1] + M[6] * a[2];
+    double y = M[1] * a[0] + M[4] * a[1] + M[7] * a[2];
+    double z = M[2] * a[0] + M[5] * a[1] + M[8] * a[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+TGD void m3mul(double* o, const double* A, const double* B)
+{
+    double t[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) o[i] = t[i];
+}
+
+// pybullet frame helpers (same formulas as the oracle; used for the TCP limit check and rewards)
+TGD void quat_from_euler(const double* rpy, double* q)
+{
+    double sr, cr, sp, cp, sy, cy;
+    sincos(rpy[0] * 0.5, &sr, &cr); sincos(rpy[1] * 0.5, &sp, &cp); sincos(rpy[2] * 0.5, &sy, &cy);
+    q[0] = sr * cp * cy - cr * sp * sy;
+    q[1] = cr * sp * cy + sr * cp * sy;
+    q[2] = cr * cp * sy - sr * sp * cy;
+    q[3] = cr * cp * cy + sr * sp * sy;
+}
+TGD void euler_from_quat(const double* q, double* rpy)
+{
+    double sqx = q[0] * q[0], sqy = q[1] * q[1], sqz = q[2] * q[2], squ = q[3] * q[3];
+    double sarg = -2.0 * (q[0] * q[2] - q[3] * q[1]);
+    if (sarg <= -0.99999) { rpy[1] = -0.5 * M_PI; rpy[0] = 0; rpy[2] = 2 * atan2(q[0], -q[1]); }
+    else if (sarg >= 0.99999) { rpy[1] = 0.5 * M_PI; rpy[0] = 0; rpy[2] = 2 * atan2(-q[0], q[1]); }
+    else {
+        rpy[1] = asin(sarg);
+        rpy[0] = atan2(2 * (q[1] * q[2] + q[3] * q[0]), squ - sqx - sqy + sqz);
+        rpy[2] = atan2(2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz);
+    }
+}
+TGD void quat_mul(double* o, const double* a, const double* b)
+{
+    double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+TGD void mat_from_quat(const double* q, double* R)
+{
+    double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    double s = 2.0 / d;
+    double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    R[0] = 1 - (yy + zz); R[1] = xy - wz;       R[2] = xz + wy;
+    R[3] = xy + wz;       R[4] = 1 - (xx + zz); R[5] = yz - wx;
+    R[6] = xz - wy;       R[7] = yz + wx;       R[8] = 1 - (xx + yy);
+}
+TGD void quat_from_mat(double* q, const double* R)
+{
+    double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+        double s = sqrt(tr + 1.0);
+        q[3] = s * 0.5; s = 0.5 / s;
+        q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+    } else if (R[0] >= R[4] && R[0] >= R[8]) {
+        double s = sqrt(R[0] - R[4] - R[8] + 1.0);
+        q[0] = s * 0.5; s = 0.5 / s;
+        q[3] = (R[7] - R[5]) * s; q[1] = (R[3] + R[1]) * s; q[2] = (R[6] + R[2]) * s;
+    } else if (R[4] >= R[8]) {
+        double s = sqrt(R[4] - R[8] - R[0] + 1.0);
+        q[1] = s * 0.5; s = 0.5 / s;
+        q[3] = (R[2] - R[6]) * s; q[2] = (R[7] + R[5]) * s; q[0] = (R[1] + R[3]) * s;
+    } else {
+        double s = sqrt(R[8] - R[0] - R[4] + 1.0);
+        q[2] = s * 0.5; s = 0.5 / s;
+        q[3] = (R[3] - R[1]) * s; q[0] = (R[2] + R[6]) * s; q[1] = (R[5] + R[7]) * s;
+    }
+}
+
+// ---------------------------------------------------------------- kinematics
+template <int NB>
+struct Kin {
+    double R[NB][9]; // world rotation of each body frame
+    double p[NB][3]; // world position of each joint origin (= body frame origin)
+    double a[NB][3]; // world joint axis
+};
+
+template <class T>
+TGD void fk(const TgArm& arm, const double* q, Kin<T::NB>& k)
+{
+#pragma unroll
+    for (int i = 0; i < T::NB; i++) {
+        constexpr int dummy = 0; (void)dummy;
+        const int p = T::parent(i);
+        double Rj[9];
+        if (p < 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) k.p[i][c] = arm.jpos[i][c];
+#pragma unroll
+            for (int c = 0; c < 9; c++) Rj[c] = arm.jrot[i][c];
+        } else {
+            double t[3];
+            m3mulv(t, k.R[p], arm.jpos[i]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) k.p[i][c] = k.p[p][c] + t[c];
+            m3mul(Rj, k.R[p], arm.jrot[i]);
+        }
+        double s, c;
+        sincos(q[i], &s, &c);
+        const double ax = arm.axis[i][0], ay = arm.axis[i][1], az = arm.axis[i][2], t1 = 1.0 - c;
+        double Rq[9] = {t1 * ax * ax + c,      t1 * ax * ay - s * az, t1 * ax * az + s * ay,
+                        t1 * ax * ay + s * az, t1 * ay * ay + c,      t1 * ay * az - s * ax,
+                        t1 * ax * az - s * ay, t1 * ay * az + s * ax, t1 * az * az + c};
+        m3mul(k.R[i], Rj, Rq);
+        m3mulv(k.a[i], k.R[i], arm.axis[i]);
+    }
+}
+
+// world pose of a frame rigidly attached to body b
+template <int NB>
+TGD void frame_pose(const Kin<NB>& k, int b, const double* lpos, const double* lrot, double* pos, double* R)
+{
+    double t[3];
+    m3mulv(t, k.R[b], lpos);
+    pos[0] = k.p[b][0] + t[0]; pos[1] = k.p[b][1] + t[1]; pos[2] = k.p[b][2] + t[2];
+    m3mul(R, k.R[b], lrot);
+}
+
+// ---------------------------------------------------------------- dynamics
+// Spatial inertia about the world origin, world axes: mass m, first moment h = m c, I_O (sym 6: xx xy xz yy yz zz)
+struct SpI {
+    double m, h[3], I[6];
+};
+TGD void spi_apply(const SpI& s, const double* w, const double* v, double* n, double* f)
+{   // momentum-like map: n = I_O w + h x v ; f = m v + w x h
+    double hv[3], wh[3];
+    v3cross(hv, s.h, v);
+    v3cross(wh, w, s.h);
+    n[0] = s.I[0] * w[0] + s.I[1] * w[1] + s.I[2] * w[2] + hv[0];
+    n[1] = s.I[1] * w[0] + s.I[3] * w[1] + s.I[4] * w[2] + hv[1];
+    n[2] = s.I[2] * w[0] + s.I[4] * w[1] + s.I[5] * w[2] + hv[2];
+    f[0] = s.m * v[0] + wh[0]; f[1] = s.m * v[1] + wh[1]; f[2] = s.m * v[2] + wh[2];
+}
+
+template <class T>
+TGD void body_inertias(const TgArm& arm, const Kin<T::NB>& k, SpI (&sp)[T::NB])
+{
+#pragma unroll
+    for (int i = 0; i < T::NB; i++) {
+        double cw[3], t[3];
+        m3mulv(t, k.R[i], arm.com[i]);
+        cw[0] = k.p[i][0] + t[0]; cw[1] = k.p[i][1] + t[1]; cw[2] = k.p[i][2] + t[2];
+        const double m = arm.mass[i];
+        // Iw = R Ic R^T
+        const double* I = arm.inertia[i];
+        double Ic[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]}, RI[9];
+        m3mul(RI, k.R[i], Ic);
+        const double* R = k.R[i];
+        double xx = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2];
+        double xy = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5];
+        double xz = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8];
+        double yy = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5];
+        double yz = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8];
+        double zz = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8];
+        const double c2 = v3dot(cw, cw);
+        sp[i].m = m;
+        sp[i].h[0] = m * cw[0]; sp[i].h[1] = m * cw[1]; sp[i].h[2] = m * cw[2];
+        sp[i].I[0] = xx + m * (c2 - cw[0] * cw[0]);
+        sp[i].I[1] = xy - m * cw[0] * cw[1];
+        sp[i].I[2] = xz - m * cw[0] * cw[2];
+        sp[i].I[3] = yy + m * (c2 - cw[1] * cw[1]);
+        sp[i].I[4] = yz - m * cw[1] * cw[2];
+        sp[i].I[5] = zz + m * (c2 - cw[2] * cw[2]);
+    }
+}
+
+// Joint-space inertia by the composite-rigid-body algorithm; M is full symmetric NB x NB.
+template <class T>
+TGD void crba(const Kin<T::NB>& k, SpI (&sp)[T::NB], double (&M)[T::NB][T::NB])
+{
+    constexpr int NB = T::NB;
+    // composite inertias: leaves -> root (plain sums about the common origin)
+#pragma unroll
+    for (int i = NB - 1; i >= 0; i--) {
+        const int p = T::parent(i);
+        if (p >= 0) {
+            sp[p].m += sp[i].m;
+#pragma unroll
+            for (int c = 0; c < 3; c++) sp[p].h[c] += sp[i].h[c];
+#pragma unroll
+            for (int c = 0; c < 6; c++) sp[p].I[c] += sp[i].I[c];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) M[i][j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        double lin[3], n[3], f[3];
+        v3cross(lin, k.p[i], k.a[i]); // velocity of the origin-coincident point for unit joint rate
+        spi_apply(sp[i], k.a[i], lin, n, f);
+#pragma unroll
+        for (int j = i; j >= 0; j--) {
+            // j runs over ancestors-or-self of i
+            bool anc = false;
+            {
+                int a = i;
+#pragma unroll
+                for (int s = 0; s < NB; s++) { if (a == j) anc = true; if (a >= 0) a = T::parent(a); }
+            }
+            if (anc) {
+                double lj[3];
+                v3cross(lj, k.p[j], k.a[j]);
+                double mij = v3dot(k.a[j], n) + v3dot(lj, f);
+                M[i][j] = mij; M[j][i] = mij;
+            }
+        }
+    }
+}
+
+// Cholesky inverse of an SPD NB x NB matrix (in registers)
+template <int NB>
+TGD void spd_inverse(const double (&M)[NB][NB], double (&Minv)[NB][NB])
+{
+    double L[NB][NB], Li[NB][NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        double d = M[j][j];
+#pragma unroll
+        for (int k2 = 0; k2 < j; k2++) d -= L[j][k2] * L[j][k2];
+        d = sqrt(d);
+        L[j][j] = d;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < NB; i++) {
+            double s = M[i][j];
+#pragma unroll
+            for (int k2 = 0; k2 < j; k2++) s -= L[i][k2] * L[j][k2];
+            L[i][j] = s * inv;
+        }
+    }
+    // Li = L^-1 (lower triangular)
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        Li[j][j] = 1.0 / L[j][j];
+#pragma unroll
+        for (int i = j + 1; i < NB; i++) {
+            double s = 0;
+#pragma unroll
+            for (int k2 = j; k2 < i; k2++) s -= L[i][k2] * Li[k2][j];
+            Li[i][j] = s / L[i][i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double s = 0;
+#pragma unroll
+            for (int k2 = i; k2 < NB; k2++) s += Li[k2][i] * Li[k2][j];
+            Minv[i][j] = s; Minv[j][i] = s;
+        }
+}
+
+// body velocities about the world origin: w[i], vO[i] (velocity of the body-fixed point at the origin)
+template <class T>
+TGD void velocities(const Kin<T::NB>& k, const double* qd, double (&w)[T::NB][3], double (&vO)[T::NB][3])
+{
+#pragma unroll
+    for (int i = 0; i < T::NB; i++) {
+        const int p = T::parent(i);
+        double lin[3];
+        v3cross(lin, k.p[i], k.a[i]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            w[i][c] = (p >= 0 ? w[p][c] : 0.0) + k.a[i][c] * qd[i];
+            vO[i][c] = (p >= 0 ? vO[p][c] : 0.0) + lin[c] * qd[i];
+        }
+    }
+}
+
+// Generalised force of bullet's per-link velocity damping (btMultiBody ABA: f = -m v (k + k|v|) at each
+// link COM, n = -I w (k + k|w|) in the link's inertial frame), accumulated over each joint's subtree.
+template <class T>
+TGD void damping_forces(const TgArm& arm, const TgPhysics& ph, const Kin<T::NB>& k, const double (&w)[T::NB][3],
+                        const double (&vO)[T::NB][3], double* Q)
+{
+    constexpr int NB = T::NB;
+    double Nw[NB][3], Fw[NB][3];
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { Nw[i][c] = 0; Fw[i][c] = 0; }
+#pragma unroll
+    for (int s = 0; s < TG_MAXSUB; s++) {
+        if (s < arm.nsub) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                if (arm.sub_body[s] == b) {
+                    double t[3], x[3], v[3], wl[3], nl[3], nw[3], Rs[9], xf[3];
+                    m3mulv(t, k.R[b], arm.sub_com[s]);
+                    x[0] = k.p[b][0] + t[0]; x[1] = k.p[b][1] + t[1]; x[2] = k.p[b][2] + t[2];
+                    v3cross(v, w[b], x);
+                    v[0] += vO[b][0]; v[1] += vO[b][1]; v[2] += vO[b][2];
+                    m3mul(Rs, k.R[b], arm.sub_rot[s]);
+                    m3tmulv(wl, Rs, w[b]);
+                    const double ka = ph.ang_damping * (1.0 + sqrt(v3dot(wl, wl)));
+                    const double kl = ph.lin_damping * (1.0 + sqrt(v3dot(v, v)));
+#pragma unroll
+                    for (int c = 0; c < 3; c++) nl[c] = -arm.sub_inertia[s][c] * wl[c] * ka;
+                    m3mulv(nw, Rs, nl);
+                    double f[3] = {-arm.sub_mass[s] * v[0] * kl, -arm.sub_mass[s] * v[1] * kl, -arm.sub_mass[s] * v[2] * kl};
+                    v3cross(xf, x, f);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { Nw[b][c] += nw[c] + xf[c]; Fw[b][c] += f[c]; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = NB - 1; i >= 0; i--) {
+        double lin[3];
+        v3cross(lin, k.p[i], k.a[i]);
+        Q[i] = v3dot(k.a[i], Nw[i]) + v3dot(lin, Fw[i]);
+        const int p = T::parent(i);
+        if (p >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { Nw[p][c] += Nw[i][c]; Fw[p][c] += Fw[i][c]; }
+        }
+    }
+}
+
+// Recursive Newton-Euler, tau = M qdd + C(q,qd) + G   (pb.calculateInverseDynamics, base_robot_arm.py:174-179)
+// `sp` must hold the ISOLATED body inertias (before crba() makes them composite).
+template <class T>
+TGD void rnea(const TgPhysics& ph, const Kin<T::NB>& k, const SpI (&sp)[T::NB], const double* qd, const double* qdd, double* tau)
+{
+    constexpr int NB = T::NB;
+    double w[NB][3], v[NB][3], aw[NB][3], av[NB][3], N[NB][3], F[NB][3];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const int p = T::parent(i);
+        double lin[3], jw[3], jv[3], c1[3], c2[3], c3[3];
+        v3cross(lin, k.p[i], k.a[i]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            jw[c] = k.a[i][c] * qd[i]; jv[c] = lin[c] * qd[i];
+            w[i][c] = (p >= 0 ? w[p][c] : 0.0) + jw[c];
+            v[i][c] = (p >= 0 ? v[p][c] : 0.0) + jv[c];
+        }
+        // spatial motion cross  v_i x (S qd) = [w x jw ; w x jv + v x jw]
+        v3cross(c1, w[i], jw); v3cross(c2, w[i], jv); v3cross(c3, v[i], jw);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            aw[i][c] = (p >= 0 ? aw[p][c] : 0.0) + k.a[i][c] * (qdd ? qdd[i] : 0.0) + c1[c];
+            av[i][c] = (p >= 0 ? av[p][c] : -ph.gravity[c]) + lin[c] * (qdd ? qdd[i] : 0.0) + c2[c] + c3[c];
+        }
+        // f = I a + v x* (I v)
+        double n1[3], f1[3], n2[3], f2[3], t1[3], t2[3], t3[3];
+        spi_apply(sp[i], aw[i], av[i], n1, f1);
+        spi_apply(sp[i], w[i], v[i], n2, f2);
+        v3cross(t1, w[i], n2); v3cross(t2, v[i], f2); v3cross(t3, w[i], f2);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { N[i][c] = n1[c] + t1[c] + t2[c]; F[i][c] = f1[c] + t3[c]; }
+    }
+#pragma unroll
+    for (int i = NB - 1; i >= 0; i--) {
+        double lin[3];
+        v3cross(lin, k.p[i], k.a[i]);
+        tau[i] = v3dot(k.a[i], N[i]) + v3dot(lin, F[i]);
+        const int p = T::parent(i);
+        if (p >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { N[p][c] += N[i][c]; F[p][c] += F[i][c]; }
+        }
+    }
+}
+
+// Joint motors of one env: all control joints share mode / gains / force limit (that is how the
+// reference drives them: base_robot_arm.py:27-37, 325-332, robot.py:228-236)
+template <int NB>
+struct Motors {
+    int mode;            // 0 velocity, 1 position
+    double kp, kd, max_force;
+    double target_pos[NB], target_vel[NB];
+};
+
+// One Robot.step_sim(): gravity compensation + stepSimulation with motor rows only.
+// Returns the number of PGS sweeps executed (diagnostics).
+template <class T>
+TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, const Motors<T::NB>& mot)
+{
+    constexpr int NB = T::NB;
+    double A[NB][NB]; // M^-1
+    double qdd[NB];
+    {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        SpI sp[NB];
+        body_inertias<T>(arm, k, sp);
+        double tau[NB];
+        {
+            double w[NB][3], vO[NB][3];
+            velocities<T>(k, qd, w, vO);
+            damping_forces<T>(arm, ph, k, w, vO, tau);
+        }
+        if (!ph.gravity_comp) {
+            // no compensation torque: the bias forces act.  (With compensation on - the only mode the
+            // reference uses, robot.py:138 - tau_gc = RNEA(q, qd, 0) cancels the bias identically, so
+            // neither is evaluated.)
+            double bias[NB];
+            rnea<T>(ph, k, sp, qd, nullptr, bias);
+#pragma unroll
+            for (int i = 0; i < NB; i++) tau[i] -= bias[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NB; i++) tau[i] -= ph.joint_damping * qd[i];
+        double M[NB][NB];
+        crba<T>(k, sp, M);
+        spd_inverse<NB>(M, A);
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            double s = 0;
+#pragma unroll
+            for (int j = 0; j < NB; j++) s += A[i][j] * tau[j];
+            qdd[i] = s;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) qd[i] += ph.dt * qdd[i];
+
+    // motor rows
+    double rhs[NB], dinv[NB], applied[NB], dv[NB];
+    const double lim = mot.max_force * ph.dt;
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const double denom = A[i][i];
+        dinv[i] = denom > 2.2204460492503131e-16 ? 1.0 / denom : 0.0;
+        const double v = qd[i];
+        const double pos_stab = mot.mode == 1 ? mot.kp * ((mot.target_pos[i] - q[i]) / ph.dt) : 0.0;
+        const double rhs_v = pos_stab + v + mot.kd * (mot.target_vel[i] - v);
+        rhs[i] = (rhs_v - v) * dinv[i];
+        applied[i] = 0; dv[i] = 0;
+    }
+    int it = 0;
+    if (lim != 0.0) {
+#pragma unroll 1
+        for (; it < ph.solver_iters; it++) {
+            double resid = 0;
+            if (it & 1) {
+#pragma unroll
+                for (int r = 0; r < NB; r++) {
+                    double delta = rhs[r] - dv[r] * dinv[r];
+                    const double sum = applied[r] + delta;
+                    if (sum < -lim) { delta = -lim - applied[r]; applied[r] = -lim; }
+                    else if (sum > lim) { delta = lim - applied[r]; applied[r] = lim; }
+                    else applied[r] = sum;
+#pragma unroll
+                    for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
+                    resid = fmax(resid, delta * delta);
+                }
+            } else {
+#pragma unroll
+                for (int r = NB - 1; r >= 0; r--) {
+                    double delta = rhs[r] - dv[r] * dinv[r];
+                    const double sum = applied[r] + delta;
+                    if (sum < -lim) { delta = -lim - applied[r]; applied[r] = -lim; }
+                    else if (sum > lim) { delta = lim - applied[r]; applied[r] = lim; }
+                    else applied[r] = sum;
+#pragma unroll
+                    for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
+                    resid = fmax(resid, delta * delta);
+                }
+            }
+            if (resid <= 0.0) { it++; break; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) { qd[i] += dv[i]; q[i] += ph.dt * qd[i]; }
+    return it;
+}
+
+// ---------------------------------------------------------------- TCP helpers
+// getLinkState(tcp)[0:2] and the workframe pose built from it (base_robot_arm.py:136-172)
+template <class T>
+TGD void tcp_world(const TgArm& arm, const Kin<T::NB>& k, double* pos, double* quat)
+{
+    double R[9];
+#pragma unroll
+    for (int b = 0; b < T::NB; b++)
+        if (arm.tcp_body == b) { frame_pose<T::NB>(k, b, arm.tcp_pos, arm.tcp_rot, pos, R); }
+    quat_from_mat(quat, R);
+}
+
+TGD void world_to_work(const TgTask& task, const double* pos, const double* quat, double* wpos, double* wrpy)
+{
+    // worldframe_to_workframe (base_robot_arm.py:62-74): rpy -> quat -> inverse workframe -> rpy
+    double rpy_w[3], qw[4], wq[4], wqi[4], R[9], d[3], oq[4];
+    euler_from_quat(quat, rpy_w);
+    quat_from_euler(rpy_w, qw);
+    quat_from_euler(task.workframe_rpy, wq);
+    wqi[0] = -wq[0]; wqi[1] = -wq[1]; wqi[2] = -wq[2]; wqi[3] = wq[3];
+    mat_from_quat(wqi, R);
+    // inverse transform: p' = R^-1 (p - t) computed as bullet does: inv_pos = -(R^-1 t); out = inv_pos + R^-1 p
+    double it[3], ip[3];
+    m3mulv(it, R, task.workframe_pos);
+    m3mulv(ip, R, pos);
+    d[0] = -it[0] + ip[0]; d[1] = -it[1] + ip[1]; d[2] = -it[2] + ip[2];
+    wpos[0] = d[0]; wpos[1] = d[1]; wpos[2] = d[2];
+    quat_mul(oq, wqi, qw);
+    euler_from_quat(oq, wrpy);
+}
+
+// solve the 6x6 system J x = v by LU with partial pivoting, all in registers; returns min|pivot|/max|pivot|
+TGD double solve6(double (&Mx)[6][7], double* x)
+{
+    double pmin = 1e300, pmax = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        // pivot search + swap by value
+#pragma unroll
+        for (int r = c + 1; r < 6; r++) {
+            if (fabs(Mx[r][c]) > fabs(Mx[c][c])) {
+#pragma unroll
+                for (int j = 0; j < 7; j++) { double t = Mx[c][j]; Mx[c][j] = Mx[r][j]; Mx[r][j] = t; }
+            }
+        }
+        const double pv = fabs(Mx[c][c]);
+        pmin = fmin(pmin, pv); pmax = fmax(pmax, pv);
+        const double inv = pv > 0 ? 1.0 / Mx[c][c] : 0.0;
+#pragma unroll
+        for (int r = c + 1; r < 6; r++) {
+            const double f = Mx[r][c] * inv;
+#pragma unroll
+            for (int j = c; j < 7; j++) Mx[r][j] -= f * Mx[c][j];
+        }
+    }
+#pragma unroll
+    for (int r = 5; r >= 0; r--) {
+        double s = Mx[r][6];
+#pragma unroll
+        for (int j = r + 1; j < 6; j++) s -= Mx[r][j] * x[j];
+        x[r] = Mx[r][r] != 0.0 ? s / Mx[r][r] : 0.0;
+    }
+    return pmax > 0 ? pmin / pmax : 0.0;
+}
+
+// geometric Jacobian of the TCP point, world frame: rows 0-2 linear, 3-5 angular (pb.calculateJacobian)
+template <class T>
+TGD void tcp_jacobian(const TgArm& arm, const Kin<T::NB>& k, const double* tcp_pos, double (&J)[6][T::NB])
+{
+#pragma unroll
+    for (int j = 0; j < T::NB; j++) {
+        bool anc = false;
+        {
+            int a = arm.tcp_body;
+#pragma unroll
+            for (int s = 0; s < T::NB; s++) { if (a == j) anc = true; if (a >= 0) { int pa = -1;
+#pragma unroll
+                for (int b = 0; b < T::NB; b++) if (a == b) pa = T::parent(b);
+                a = pa; } }
+        }
+        double r[3] = {tcp_pos[0] - k.p[j][0], tcp_pos[1] - k.p[j][1], tcp_pos[2] - k.p[j][2]}, lin[3];
+        v3cross(lin, k.a[j], r);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { J[c][j] = anc ? lin[c] : 0.0; J[3 + c][j] = anc ? k.a[j][c] : 0.0; }
+    }
+}

@@ -1,0 +1,377 @@
+// tg_env.cuh - env-level kernels (one thread per env): step, reset.
+//
+//   step_kernel   <- BaseTactileEnv.step (rl_envs/base_tactile_env.py:166-185) up to, not including, the
+//                    tactile render: action encode/scale, tcp_velocity_control, 24 x step_sim, step data.
+//   reset_kernel  <- EdgeFollowEnv.reset (edge_follow_env.py:311-336) / Robot.reset (robot.py:114-125):
+//                    rest pose, IK, blocking move.
+// Both leave behind, per env, the camera frame and stimulus pose the raster kernel consumes.
+#pragma once
+#include "tg_dyn.cuh"
+
+struct EnvBuffers {
+    int n;
+    int lanes;            // active lanes per warp
+    double* q;            // [NB][N]
+    double* qd;           // [NB][N]
+    double* embed;        // [N]
+    double* edge_ang;     // [N]
+    int* steps;           // [N]
+    int* reset_substeps;  // [N]
+    int* reset_count;     // [N] draws consumed since tg_set_draws
+    const double* draws;  // [N][rounds][n_draws] or null
+    int draw_rounds;
+    double* cam;          // [N][12] eye fwd up right
+    double* stim;         // [N][12] R(9) t(3) of the stimulus frame
+    double* tcp;          // [N][7] tcp world pos + quat (state export)
+    const double* rest_q; // [NB]
+};
+
+TGD int env_index(const EnvBuffers& b)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (lane >= b.lanes) return -1;
+    const int e = warp * b.lanes + lane;
+    return e < b.n ? e : -1;
+}
+
+// camera frame (sensors/tactile_sensor.py:150-229): eye, forward = R ex, up = R ez, then computeViewMatrix's
+// orthonormalisation: f = norm(target - eye), s = norm(f x up), u = s x f
+template <class T>
+TGD void write_camera(const TgArm& arm, const Kin<T::NB>& k, double* cam)
+{
+    double pos[3], R[9];
+#pragma unroll
+    for (int b = 0; b < T::NB; b++)
+        if (arm.cam_body == b) frame_pose<T::NB>(k, b, arm.cam_pos, arm.cam_rot, pos, R);
+    double f[3] = {R[0], R[3], R[6]}, u[3] = {R[2], R[5], R[8]}, s[3];
+    double fn = 1.0 / sqrt(v3dot(f, f)); f[0] *= fn; f[1] *= fn; f[2] *= fn;
+    double un = 1.0 / sqrt(v3dot(u, u)); u[0] *= un; u[1] *= un; u[2] *= un;
+    v3cross(s, f, u);
+    double sn = 1.0 / sqrt(v3dot(s, s)); s[0] *= sn; s[1] *= sn; s[2] *= sn;
+    v3cross(u, s, f);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { cam[c] = pos[c]; cam[3 + c] = f[c]; cam[6 + c] = u[c]; cam[9 + c] = s[c]; }
+}
+
+// edge_follow reward / termination (edge_follow_env.py:371-452)
+TGD void edge_step_data(const TgTask& task, const double* tcp_pos, double edge_ang, int steps, float* reward, unsigned char* done)
+{
+    double s, c;
+    sincos(edge_ang, &s, &c);
+    const double gx = task.edge_pos[0] + task.edge_len * c, gy = task.edge_pos[1] + task.edge_len * s;
+    const double p1x = task.edge_pos[0] - task.edge_len * c, p1y = task.edge_pos[1] - task.edge_len * s;
+    const double dx = tcp_pos[0] - gx, dy = tcp_pos[1] - gy;
+    const double goal_dist = sqrt(dx * dx + dy * dy);
+    // |cross(p2 - p1, p1 - p3)| / |p2 - p1|
+    const double ex = gx - p1x, ey = gy - p1y;
+    const double fx = p1x - tcp_pos[0], fy = p1y - tcp_pos[1];
+    const double edge_dist = fabs(ex * fy - ey * fx) / sqrt(ex * ex + ey * ey);
+    *reward = (float)(-((1.0 * goal_dist) + (10.0 * edge_dist) + (1.0 * 0.0)));
+    *done = (goal_dist < task.termination_dist || steps >= task.max_steps) ? 1 : 0;
+}
+
+template <class T>
+__global__ void __launch_bounds__(128)
+step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
+            EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done)
+{
+    constexpr int NB = T::NB;
+    const int e = env_index(b);
+    if (e < 0) return;
+    double q[NB], qd[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) { q[i] = b.q[(size_t)i * b.n + e]; qd[i] = b.qd[(size_t)i * b.n + e]; }
+
+    // encode_actions + scale_actions (edge_follow_env.py:345-369, base_tactile_env.py:141-164)
+    double v[6];
+    {
+        double enc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++)
+            if (kk < task.act_dim) {
+                const double a = (double)actions[(size_t)e * task.act_dim + kk];
+#pragma unroll
+                for (int s = 0; s < 6; s++) if (task.act_index[kk] == s) enc[s] = a;
+            }
+        const double in_range = task.act_max - task.act_min;
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            const double a = fmin(fmax(enc[s], task.act_min), task.act_max);
+            v[s] = (((a - task.act_min) * (task.act_hi[s] - task.act_lo[s])) / in_range) + task.act_lo[s];
+        }
+    }
+    Motors<NB> mot;
+    mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
+    {
+        // tcp_velocity_control (base_robot_arm.py:281-332)
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4], wp[3], wr[3];
+        tcp_world<T>(arm, k, tp, tq);
+        world_to_work(task, tp, tq, wp, wr);
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            const double cur = s < 3 ? wp[s] : wr[s - 3];
+            const bool ex = (cur < task.tcp_lims[s][0] && v[s] < 0) || (cur > task.tcp_lims[s][1] && v[s] > 0);
+            if (ex) v[s] = 0.0;
+        }
+        double wq[4], R[9], vw[6];
+        quat_from_euler(task.workframe_rpy, wq);
+        mat_from_quat(wq, R);
+        m3mulv(vw, R, v); m3mulv(vw + 3, R, v + 3);
+        double J[6][NB];
+        tcp_jacobian<T>(arm, k, tp, J);
+        if (NB == 6) {
+            double Mx[6][7];
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) Mx[r][c] = J[r][c];
+                Mx[r][6] = vw[r];
+            }
+            solve6(Mx, mot.target_vel);
+        } else {
+            // TODO(mg400): pseudo-inverse path
+#pragma unroll
+            for (int i = 0; i < NB; i++) mot.target_vel[i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;
+    }
+#pragma unroll 1
+    for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, mot);
+
+    const int steps = b.steps[e] + 1;
+    b.steps[e] = steps;
+#pragma unroll
+    for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = q[i]; b.qd[(size_t)i * b.n + e] = qd[i]; }
+    {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4];
+        tcp_world<T>(arm, k, tp, tq);
+        float r; unsigned char d;
+        edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
+        reward[e] = r; done[e] = d;
+        write_camera<T>(arm, k, b.cam + (size_t)e * 12);
+#pragma unroll
+        for (int c = 0; c < 3; c++) b.tcp[(size_t)e * 7 + c] = tp[c];
+#pragma unroll
+        for (int c = 0; c < 4; c++) b.tcp[(size_t)e * 7 + 3 + c] = tq[c];
+    }
+}
+
+// pb.calculateInverseKinematics as restated in oracle/tg_oracle.c:or_inverse_kinematics (base_robot_arm.py:201-209)
+template <class T>
+TGD void inverse_kinematics(const TgArm& arm, double* q, const double* tpos, const double* tquat)
+{
+    constexpr int NB = T::NB;
+    static_assert(NB == 6 || NB == 8, "topology");
+#pragma unroll 1
+    for (int it = 0; it < 100; it++) {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4], e[6];
+        tcp_world<T>(arm, k, tp, tq);
+        e[0] = tpos[0] - tp[0]; e[1] = tpos[1] - tp[1]; e[2] = tpos[2] - tp[2];
+        const double res = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        if (it > 0 && res < 1e-8) break;
+        double qi[4] = {-tq[0], -tq[1], -tq[2], tq[3]}, dq[4];
+        quat_mul(dq, tquat, qi);
+        const double wv = fmin(fmax(dq[3], -1.0), 1.0);
+        double ang = 2 * acos(wv);
+        const double sn = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
+        if (ang > M_PI) ang -= 2 * M_PI;
+#pragma unroll
+        for (int c = 0; c < 3; c++) e[3 + c] = sn > 1e-300 ? ang * dq[c] / sn : 0.0;
+        double J[6][NB];
+        tcp_jacobian<T>(arm, k, tp, J);
+        if (NB == 6) {
+            double Mx[6][7], d[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                double bi = 0;
+#pragma unroll
+                for (int r = 0; r < 6; r++) bi += J[r][i] * e[r];
+                Mx[i][6] = bi;
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    double s = i == j ? 0.5 : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 6; r++) s += J[r][i] * J[r][j];
+                    Mx[i][j] = s;
+                }
+            }
+            solve6(Mx, d);
+            double mx = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(d[i]));
+            const double sc = mx > M_PI / 4 ? (M_PI / 4) / mx : 1.0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) q[i] += sc * d[i];
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(128)
+reset_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
+             EnvBuffers b, const unsigned char* __restrict__ mask)
+{
+    constexpr int NB = T::NB;
+    const int e = env_index(b);
+    if (e < 0) return;
+    if (mask && !mask[e]) return;
+
+    // reset_task draws (edge_follow_env.py:285-299): embed_dist then edge_ang
+    double draw[TG_MAXDRAW];
+#pragma unroll
+    for (int d = 0; d < TG_MAXDRAW; d++) draw[d] = task.draw_default[d];
+    {
+        const int cnt = b.reset_count[e];
+        if (b.draws && cnt < b.draw_rounds) {
+#pragma unroll
+            for (int d = 0; d < TG_MAXDRAW; d++)
+                if (d < task.n_draws) draw[d] = b.draws[((size_t)e * b.draw_rounds + cnt) * task.n_draws + d];
+        }
+        b.reset_count[e] = cnt + 1;
+    }
+    const double embed = draw[0], edge_ang = draw[1];
+    b.embed[e] = embed; b.edge_ang[e] = edge_ang; b.steps[e] = 0;
+    {
+        double s, c;
+        sincos(edge_ang * 0.5, &s, &c);
+        double qz[4] = {0, 0, s, c}, R[9]; // getQuaternionFromEuler([0,0,ang]) (edge_follow_env.py:241)
+        mat_from_quat(qz, R);
+#pragma unroll
+        for (int i = 0; i < 9; i++) b.stim[(size_t)e * 12 + i] = R[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) b.stim[(size_t)e * 12 + 9 + i] = task.edge_pos[i];
+    }
+
+    double q[NB], qd[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) { q[i] = b.rest_q[i]; qd[i] = 0.0; }
+    // workframe_to_worldframe (base_robot_arm.py:47-60) of the init pose [0,0,embed], init_rpy
+    double tpos[3], targ_orn[4];
+    {
+        double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
+        const double lp[3] = {0.0, 0.0, embed};
+        quat_from_euler(task.workframe_rpy, wq);
+        quat_from_euler(task.init_rpy, tq);
+        mat_from_quat(wq, R);
+        m3mulv(t, R, lp);
+        tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
+        quat_mul(oq, wq, tq);
+        euler_from_quat(oq, rpy);
+        quat_from_euler(rpy, targ_orn);
+    }
+    double targ_j[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) targ_j[i] = q[i];
+    inverse_kinematics<T>(arm, targ_j, tpos, targ_orn);
+
+    // Robot.blocking_move(max_steps=1000, constant_vel=0.001) (robot.py:188-260)
+    Motors<NB> mot;
+    mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.blocking_force;
+    double cv = 0.001;
+    int nsteps = 0;
+#pragma unroll 1
+    for (int it = 0; it < 1000; it++) {
+        double tp[3], tq[4];
+        {
+            Kin<NB> k;
+            fk<T>(arm, q, k);
+            tcp_world<T>(arm, k, tp, tq);
+        }
+        double nrm = 0, tot = 0;
+        bool all_small = true;
+        double diff[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) { diff[i] = targ_j[i] - q[i]; nrm += diff[i] * diff[i]; tot += fabs(qd[i]); }
+        nrm = sqrt(nrm);
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const double vdir = nrm > 0 ? diff[i] / nrm : 0.0;
+            mot.target_pos[i] = q[i] + vdir * cv; mot.target_vel[i] = 0.0;
+            if (!(fabs(diff[i]) < cv)) all_small = false;
+        }
+        if (all_small) cv *= 0.5;
+        substep<T>(arm, ph, q, qd, mot);
+        nsteps++;
+        const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
+        const double ip = targ_orn[0] * tq[0] + targ_orn[1] * tq[1] + targ_orn[2] * tq[2] + targ_orn[3] * tq[3];
+        const double ca = fmin(fmax(2 * ip * ip - 1, -1.0), 1.0);
+        const double oe = acos(ca);
+        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
+    }
+    b.reset_substeps[e] = nsteps;
+#pragma unroll
+    for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = q[i]; b.qd[(size_t)i * b.n + e] = qd[i]; }
+    {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4];
+        tcp_world<T>(arm, k, tp, tq);
+        write_camera<T>(arm, k, b.cam + (size_t)e * 12);
+#pragma unroll
+        for (int c = 0; c < 3; c++) b.tcp[(size_t)e * 7 + c] = tp[c];
+#pragma unroll
+        for (int c = 0; c < 4; c++) b.tcp[(size_t)e * 7 + 3 + c] = tq[c];
+    }
+}
+
+// ---------------------------------------------------------------- test hooks
+template <class T>
+__global__ void test_id_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, int n,
+                               const double* q_in, const double* qd_in, double* tau_out)
+{
+    constexpr int NB = T::NB;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double q[NB], qd[NB], tau[NB];
+    for (int i = 0; i < NB; i++) { q[i] = q_in[e * NB + i]; qd[i] = qd_in[e * NB + i]; }
+    Kin<NB> k;
+    fk<T>(arm, q, k);
+    SpI sp[NB];
+    body_inertias<T>(arm, k, sp);
+    rnea<T>(ph, k, sp, qd, nullptr, tau);
+    for (int i = 0; i < NB; i++) tau_out[e * NB + i] = tau[i];
+}
+
+template <class T>
+__global__ void test_mass_kernel(const __grid_constant__ TgArm arm, int n, const double* q_in, double* M_out)
+{
+    constexpr int NB = T::NB;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double q[NB];
+    for (int i = 0; i < NB; i++) q[i] = q_in[e * NB + i];
+    Kin<NB> k;
+    fk<T>(arm, q, k);
+    SpI sp[NB];
+    body_inertias<T>(arm, k, sp);
+    double M[NB][NB];
+    crba<T>(k, sp, M);
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) M_out[(e * NB + i) * NB + j] = M[i][j];
+}
+
+template <class T>
+__global__ void test_substep_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, int n, int nsteps,
+                                    double* q_io, double* qd_io, const double* target_vel)
+{
+    constexpr int NB = T::NB;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double q[NB], qd[NB];
+    Motors<NB> mot;
+    mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
+    for (int i = 0; i < NB; i++) { q[i] = q_io[e * NB + i]; qd[i] = qd_io[e * NB + i]; mot.target_vel[i] = target_vel[e * NB + i]; mot.target_pos[i] = 0; }
+#pragma unroll 1
+    for (int s = 0; s < nsteps; s++) substep<T>(arm, ph, q, qd, mot);
+    for (int i = 0; i < NB; i++) { q_io[e * NB + i] = q[i]; qd_io[e * NB + i] = qd[i]; }
+}

@@ -1,0 +1,370 @@
+// tg_world.cu - C ABI of libtactile_gym_b200.so (include/tactile_gym_b200.h): world lifetime, buffers, launches.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tg_env.cuh"
+#include "tg_raster.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(TG_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct TgWorld {
+    TgConfig cfg;
+    int device = 0;
+    int n = 0, nb = 0, S = 0;
+    int sm_count = 0;
+    EnvBuffers eb{};
+    RasterArgs ra{};
+    std::vector<void*> allocs;
+    double* d_draws = nullptr;
+    unsigned char* d_done_internal = nullptr;
+    float* d_reward_internal = nullptr;
+    size_t raster_smem = 0;
+    int raster_grid = 0;
+    long long launches = 0;
+};
+
+template <class Tp>
+static int dalloc(TgWorld* w, Tp** p, size_t count)
+{
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, count * sizeof(Tp));
+    if (e != cudaSuccess) return fail(TG_ENOMEM, "cudaMalloc(%zu) failed: %s", count * sizeof(Tp), cudaGetErrorString(e));
+    cudaMemset(v, 0, count * sizeof(Tp));
+    w->allocs.push_back(v);
+    *p = static_cast<Tp*>(v);
+    return TG_OK;
+}
+
+extern "C" int tg_version(void) { return TG_VERSION; }
+extern "C" const char* tg_last_error(void) { return g_err.c_str(); }
+
+extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
+{
+    if (!cfg || !out) return fail(TG_EINVAL, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(TG_ENODEV, "no CUDA device: tactile_gym_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(TG_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    if (cfg->n_envs <= 0) return fail(TG_EINVAL, "n_envs must be > 0");
+    const int S = cfg->sensor.image_size;
+    if (S != 64 && S != 128 && S != 256) return fail(TG_EINVAL, "image_size must be 64, 128 or 256 (got %d)", S);
+    if (cfg->arm.topo == TG_TOPO_CHAIN6 && cfg->arm.nb != 6) return fail(TG_EINVAL, "CHAIN6 topology needs nb == 6");
+    if (cfg->arm.topo == TG_TOPO_MG400) return fail(TG_EUNSUPPORTED, "MG400 topology: velocity control path not built yet");
+    if (cfg->arm.topo != TG_TOPO_CHAIN6) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
+    if (cfg->task.task != TG_TASK_EDGE_FOLLOW) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+    if (cfg->sensor.n_tri <= 0 || cfg->sensor.n_tri > 32) return fail(TG_EINVAL, "n_tri must be in 1..32");
+    if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->sensor.h_tris || !cfg->h_rest_q)
+        return fail(TG_EINVAL, "null table pointer in config");
+    CK(cudaSetDevice(device));
+
+    TgWorld* w = new TgWorld();
+    w->cfg = *cfg;
+    w->device = device;
+    w->n = cfg->n_envs; w->nb = cfg->arm.nb; w->S = S;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    w->sm_count = prop.multiProcessorCount;
+    const int n = w->n, nb = w->nb;
+    int lanes = cfg->lanes_per_warp;
+    if (lanes != 8 && lanes != 16 && lanes != 32) {
+        // fill the machine: one warp per SM sub-partition before packing lanes
+        const long slots = (long)w->sm_count * 4;
+        lanes = n <= slots * 8 ? 8 : (n <= slots * 16 ? 16 : 32);
+    }
+    EnvBuffers& b = w->eb;
+    b.n = n; b.lanes = lanes;
+    int rc;
+    double* rest = nullptr;
+    if ((rc = dalloc(w, &b.q, (size_t)nb * n)) || (rc = dalloc(w, &b.qd, (size_t)nb * n)) || (rc = dalloc(w, &b.embed, n)) ||
+        (rc = dalloc(w, &b.edge_ang, n)) || (rc = dalloc(w, &b.steps, n)) || (rc = dalloc(w, &b.reset_substeps, n)) ||
+        (rc = dalloc(w, &b.reset_count, n)) || (rc = dalloc(w, &b.cam, (size_t)12 * n)) || (rc = dalloc(w, &b.stim, (size_t)12 * n)) ||
+        (rc = dalloc(w, &b.tcp, (size_t)7 * n)) || (rc = dalloc(w, &rest, nb)) || (rc = dalloc(w, &w->d_done_internal, n)) ||
+        (rc = dalloc(w, &w->d_reward_internal, n))) {
+        tg_destroy(w);
+        return rc;
+    }
+    CK(cudaMemcpy(rest, cfg->h_rest_q, sizeof(double) * nb, cudaMemcpyHostToDevice));
+    b.rest_q = rest;
+    b.draws = nullptr; b.draw_rounds = 0;
+
+    // raster tables: border pixels get nodef = -1 and the baked grey value (tactile_sensor.py:289-292)
+    {
+        const size_t px = (size_t)S * S;
+        std::vector<float> nd(px);
+        std::vector<uint8_t> base(px);
+        for (size_t i = 0; i < px; i++) {
+            const bool border = cfg->sensor.border_on && cfg->sensor.h_border_mask[i] == 1;
+            nd[i] = border ? -1.0f : cfg->sensor.h_nodef_dep[i];
+            base[i] = border ? (uint8_t)cfg->sensor.h_nodef_gray[i] : 0;
+        }
+        float* dn; uint8_t* db; double* dt;
+        if ((rc = dalloc(w, &dn, px)) || (rc = dalloc(w, &db, px)) || (rc = dalloc(w, &dt, (size_t)cfg->sensor.n_tri * 9))) { tg_destroy(w); return rc; }
+        CK(cudaMemcpy(dn, nd.data(), px * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db, base.data(), px, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dt, cfg->sensor.h_tris, sizeof(double) * 9 * cfg->sensor.n_tri, cudaMemcpyHostToDevice));
+        RasterArgs& r = w->ra;
+        r.n = n; r.S = S; r.bands = S == 256 ? 4 : 1; r.ntri = cfg->sensor.n_tri;
+        r.th = tan(cfg->sensor.fov_deg * (M_PI / 180.0) / 2.0);
+        r.near_ = cfg->sensor.near_; r.far_ = cfg->sensor.far_;
+        r.F = cfg->sensor.far_ / (cfg->sensor.far_ - cfg->sensor.near_);
+        r.nodef = dn; r.base = db; r.tris = dt; r.cam = b.cam; r.stim = b.stim; r.mask = nullptr; r.obs = nullptr; r.term_obs = nullptr;
+        const size_t band_px = px / r.bands;
+        w->raster_smem = band_px * 5 + sizeof(TriCoef) * RASTER_BATCH * r.ntri;
+        CK(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->raster_smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel, RASTER_THREADS, w->raster_smem));
+        if (per_sm < 1) { tg_destroy(w); return fail(TG_ECUDA, "raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
+        int grid = w->sm_count * per_sm;
+        grid -= grid % r.bands;
+        const int need = ((n + RASTER_BATCH - 1) / RASTER_BATCH) * r.bands;
+        if (grid > need) grid = need;
+        w->raster_grid = grid;
+    }
+    *out = w;
+    return TG_OK;
+}
+
+extern "C" int tg_destroy(TgWorld* w)
+{
+    if (!w) return TG_OK;
+    cudaSetDevice(w->device);
+    for (void* p : w->allocs) cudaFree(p);
+    if (w->d_draws) cudaFree(w->d_draws);
+    delete w;
+    return TG_OK;
+}
+
+extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds)
+{
+    if (!w || !h_draws || rounds <= 0) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    CK(cudaDeviceSynchronize());
+    if (w->d_draws) { cudaFree(w->d_draws); w->d_draws = nullptr; }
+    const size_t cnt = (size_t)w->n * rounds * w->cfg.task.n_draws;
+    CK(cudaMalloc(&w->d_draws, cnt * sizeof(double)));
+    CK(cudaMemcpy(w->d_draws, h_draws, cnt * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemset(w->eb.reset_count, 0, sizeof(int) * w->n));
+    w->eb.draws = w->d_draws; w->eb.draw_rounds = rounds;
+    return TG_OK;
+}
+
+extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)
+{
+    if (!w || !h_counts) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    CK(cudaMemcpyAsync(h_counts, w->eb.reset_count, sizeof(int) * w->n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return TG_OK;
+}
+
+static dim3 env_grid(const TgWorld* w)
+{
+    const int per_block = 4 * w->eb.lanes; // 128 threads = 4 warps
+    return dim3((w->n + per_block - 1) / per_block);
+}
+
+static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, uint8_t* term, cudaStream_t st)
+{
+    RasterArgs r = w->ra;
+    r.obs = d_obs; r.mask = mask; r.term_obs = term;
+    raster_kernel<<<w->raster_grid, RASTER_THREADS, w->raster_smem, st>>>(r);
+    w->launches++;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
+{
+    reset_kernel<TopoChain6><<<env_grid(w), 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, mask);
+    w->launches++;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, cudaStream_t st)
+{
+    step_kernel<TopoChain6><<<env_grid(w), 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done);
+    w->launches++;
+    CK(cudaGetLastError());
+    return TG_OK;
+}
+
+extern "C" int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream)
+{
+    if (!w || !d_obs) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    int rc;
+    if ((rc = launch_reset(w, d_mask, (cudaStream_t)stream))) return rc;
+    return launch_raster(w, d_obs, d_mask, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream)
+{
+    if (!w) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    return launch_reset(w, d_mask, (cudaStream_t)stream);
+}
+
+extern "C" int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_term_obs, void* stream)
+{
+    if (!w || !d_actions || !d_obs || !d_reward || !d_done) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = launch_step(w, d_actions, d_reward, d_done, st))) return rc;
+    if ((rc = launch_raster(w, d_obs, nullptr, nullptr, st))) return rc;   // observation of every env (terminal one for done envs)
+    if ((rc = launch_reset(w, d_done, st))) return rc;                      // finished envs start their next episode
+    return launch_raster(w, d_obs, d_done, d_term_obs, st);                 // ... and get its first observation
+}
+
+extern "C" int tg_physics_only(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, void* stream)
+{
+    if (!w || !d_actions) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    return launch_step(w, d_actions, d_reward ? d_reward : w->d_reward_internal, d_done ? d_done : w->d_done_internal, (cudaStream_t)stream);
+}
+
+extern "C" int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream)
+{
+    if (!w || !d_obs) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    return launch_raster(w, d_obs, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int tg_state_size(const TgWorld* w) { return w ? 2 * w->nb + 7 + 4 : 0; }
+
+extern "C" int tg_get_state(TgWorld* w, double* h, void* stream)
+{
+    if (!w || !h) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = w->n, nb = w->nb, sz = tg_state_size(w);
+    std::vector<double> q((size_t)nb * n), qd((size_t)nb * n), tcp((size_t)7 * n), emb(n), ang(n);
+    std::vector<int> steps(n), rs(n);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(q.data(), w->eb.q, sizeof(double) * nb * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(qd.data(), w->eb.qd, sizeof(double) * nb * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tcp.data(), w->eb.tcp, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(emb.data(), w->eb.embed, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ang.data(), w->eb.edge_ang, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(steps.data(), w->eb.steps, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rs.data(), w->eb.reset_substeps, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    for (int e = 0; e < n; e++) {
+        double* o = h + (size_t)e * sz;
+        for (int i = 0; i < nb; i++) { o[i] = q[(size_t)i * n + e]; o[nb + i] = qd[(size_t)i * n + e]; }
+        for (int c = 0; c < 7; c++) o[2 * nb + c] = tcp[(size_t)e * 7 + c];
+        o[2 * nb + 7] = emb[e]; o[2 * nb + 8] = ang[e]; o[2 * nb + 9] = steps[e]; o[2 * nb + 10] = rs[e];
+    }
+    return TG_OK;
+}
+
+extern "C" int tg_set_state(TgWorld* w, const double* h, void* stream)
+{
+    if (!w || !h) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = w->n, nb = w->nb, sz = tg_state_size(w);
+    std::vector<double> q((size_t)nb * n), qd((size_t)nb * n), emb(n), ang(n);
+    std::vector<int> steps(n);
+    for (int e = 0; e < n; e++) {
+        const double* o = h + (size_t)e * sz;
+        for (int i = 0; i < nb; i++) { q[(size_t)i * n + e] = o[i]; qd[(size_t)i * n + e] = o[nb + i]; }
+        emb[e] = o[2 * nb + 7]; ang[e] = o[2 * nb + 8]; steps[e] = (int)o[2 * nb + 9];
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(w->eb.q, q.data(), sizeof(double) * nb * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->eb.qd, qd.data(), sizeof(double) * nb * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->eb.embed, emb.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->eb.edge_ang, ang.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->eb.steps, steps.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    return TG_OK;
+}
+
+extern "C" int tg_get_camera(TgWorld* w, double* h_cam, void* stream)
+{
+    if (!w || !h_cam) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaMemcpy(h_cam, w->eb.cam, sizeof(double) * 12 * w->n, cudaMemcpyDeviceToHost));
+    return TG_OK;
+}
+
+// ------------------------------------------------------------ test hooks
+template <class F>
+static int with_tmp(TgWorld* w, int n, int nb, const double* h_a, const double* h_b, size_t out_count, double* h_out, bool out_is_a, F launch)
+{
+    double *da = nullptr, *db = nullptr, *dout = nullptr;
+    CK(cudaSetDevice(w->device));
+    CK(cudaMalloc(&da, sizeof(double) * n * nb));
+    CK(cudaMemcpy(da, h_a, sizeof(double) * n * nb, cudaMemcpyHostToDevice));
+    if (h_b) { CK(cudaMalloc(&db, sizeof(double) * n * nb)); CK(cudaMemcpy(db, h_b, sizeof(double) * n * nb, cudaMemcpyHostToDevice)); }
+    if (!out_is_a) CK(cudaMalloc(&dout, sizeof(double) * out_count));
+    launch(da, db, dout);
+    w->launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && !out_is_a) e = cudaMemcpy(h_out, dout, sizeof(double) * out_count, cudaMemcpyDeviceToHost);
+    cudaFree(da); if (db) cudaFree(db); if (dout) cudaFree(dout);
+    if (e != cudaSuccess) return fail(TG_ECUDA, "test hook failed: %s", cudaGetErrorString(e));
+    return TG_OK;
+}
+
+extern "C" int tg_test_inverse_dynamics(TgWorld* w, int n, const double* h_q, const double* h_qd, double* h_tau)
+{
+    if (!w || n <= 0) return fail(TG_EINVAL, "bad arguments");
+    return with_tmp(w, n, w->nb, h_q, h_qd, (size_t)n * w->nb, h_tau, false, [&](double* q, double* qd, double* out) {
+        test_id_kernel<TopoChain6><<<(n + 63) / 64, 64>>>(w->cfg.arm, w->cfg.phys, n, q, qd, out);
+    });
+}
+
+extern "C" int tg_test_mass_matrix(TgWorld* w, int n, const double* h_q, double* h_M)
+{
+    if (!w || n <= 0) return fail(TG_EINVAL, "bad arguments");
+    return with_tmp(w, n, w->nb, h_q, nullptr, (size_t)n * w->nb * w->nb, h_M, false, [&](double* q, double*, double* out) {
+        test_mass_kernel<TopoChain6><<<(n + 63) / 64, 64>>>(w->cfg.arm, n, q, out);
+    });
+}
+
+extern "C" int tg_test_substep(TgWorld* w, int n, int nsteps, double* h_q, double* h_qd, const double* h_target_vel)
+{
+    if (!w || n <= 0) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    const size_t bytes = sizeof(double) * n * w->nb;
+    double *q, *qd, *tv;
+    CK(cudaMalloc(&q, bytes)); CK(cudaMalloc(&qd, bytes)); CK(cudaMalloc(&tv, bytes));
+    CK(cudaMemcpy(q, h_q, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(qd, h_qd, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tv, h_target_vel, bytes, cudaMemcpyHostToDevice));
+    test_substep_kernel<TopoChain6><<<(n + 31) / 32, 32>>>(w->cfg.arm, w->cfg.phys, n, nsteps, q, qd, tv);
+    w->launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(h_q, q, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_qd, qd, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(q); cudaFree(qd); cudaFree(tv);
+    if (e != cudaSuccess) return fail(TG_ECUDA, "test_substep failed: %s", cudaGetErrorString(e));
+    return TG_OK;
+}
+
+extern "C" long long tg_launch_count(const TgWorld* w) { return w ? w->launches : 0; }

@@ -1,0 +1,237 @@
+"""Batched world: N env instances of one task on one GPU, driven through the C ABI.
+
+`TactileWorld` owns the TgWorld handle and the torch.cuda tensors the kernels write into
+(obs uint8 [N,S,S,1], reward f32 [N], done u8 [N]).  Everything is enqueued on torch's current stream;
+`step()` does not synchronise.  Random draws for resets are produced on the host by one numpy
+RandomState per env - seeded exactly like the reference's gym seeding - and uploaded in rounds.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import scene, seeding
+
+DRAW_ROUNDS = 64        # resets per env covered by one upload
+DRAW_CHECK_EVERY = 32   # steps between (synchronising) checks of how many draws were consumed
+
+
+def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
+    """EdgeFollowEnv.__init__ (rl_envs/exploration/edge_follow/edge_follow_env.py:23-134) as a TgConfig.
+    Returns (cfg, keepalive) - keepalive holds the numpy arrays the config points into."""
+    arm_type = env_modes["arm_type"]
+    if "tactile_sensor_name" not in env_modes:
+        raise KeyError("env_modes['tactile_sensor_name'] is required (edge_follow_env.py:59)")
+    sensor = env_modes["tactile_sensor_name"]
+    movement_mode = env_modes["movement_mode"]
+    control_mode = env_modes["control_mode"]
+    noise_mode = env_modes["noise_mode"]
+    if control_mode != "TCP_velocity_control":
+        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built (SURVEY 8(f) item 4)" % control_mode)
+    if arm_type not in ("ur5", "mg400"):
+        raise ValueError("Incorrect arm type specified {}".format(arm_type))
+    typ = "standard"
+    S = int(image_size[0])
+    mj = scene.load_model_json(arm_type, sensor, typ)
+    sj = scene.load_sensor_json(sensor, typ)
+    cam = sj["types"][typ]
+    arm, control_links = scene.reduce_model(mj, sensor, cam["cam_pos"], cam["cam_rpy"])
+
+    cfg = L.TgConfig()
+    cfg.n_envs = n_envs
+    cfg.lanes_per_warp = lanes_per_warp
+    cfg.arm = arm
+    cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 10.0) / (1.0 / 240.0))))
+
+    t = cfg.task
+    t.task = L.TG_TASK_EDGE_FOLLOW
+    t.max_steps = int(max_steps)
+    idx = {"xy": [0, 1], "xyz": [0, 1, 2], "xyRz": [0, 1, 5], "xyzRz": [0, 1, 2, 5]}[movement_mode]
+    t.act_dim = len(idx)
+    for k in range(6):
+        t.act_index[k] = idx[k] if k < len(idx) else -1
+    t.act_min, t.act_max = -0.25, 0.25
+    max_pos_vel, max_ang_vel = 0.01, 5.0 * (np.pi / 180)          # edge_follow_env.py:155-165
+    hi = [max_pos_vel] * 3 + [0.0, 0.0, max_ang_vel]
+    for k in range(6):
+        t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
+    lims = np.zeros((6, 2))
+    if arm_type == "mg400":                                        # :72-80
+        edge_pos, edge_len, stim = [0.33, 0.0, 0.0], 0.105, "short_edge"
+        lims[0], lims[1], lims[2], lims[5] = (-0.15, 0.15), (-0.11, 0.11), (-0.1, 0.1), (-np.pi, np.pi)
+    else:                                                          # :81-88
+        edge_pos, edge_len, stim = [0.65, 0.0, 0.0], 0.175, "long_edge"
+        lims[0], lims[1], lims[2], lims[5] = (-0.175, 0.175), (-0.175, 0.175), (-0.1, 0.1), (-np.pi, np.pi)
+    edge_height = 0.035
+    wf_pos = [edge_pos[0], edge_pos[1], edge_height]               # :106-107
+    wf_rpy = [-np.pi, 0.0, np.pi / 2]
+    for k in range(3):
+        t.workframe_pos[k], t.workframe_rpy[k] = wf_pos[k], wf_rpy[k]
+        t.edge_pos[k] = edge_pos[k]
+        t.init_rpy[k] = 0.0
+    for k in range(6):
+        t.tcp_lims[k][0], t.tcp_lims[k][1] = lims[k]
+    t.edge_len, t.edge_height, t.termination_dist = edge_len, edge_height, 0.01
+    embed_default = 0.0035                                         # :91-96
+    if noise_mode == "rand_height":                                # :291-297
+        t.embed_lo, t.embed_hi = {"tactip": (0.0015, 0.0065), "digit": (0.0011, 0.0028), "digitac": (0.0015, 0.0045)}[sensor]
+    else:
+        t.embed_lo = t.embed_hi = embed_default
+    t.n_draws = 2
+    t.draw_default[0], t.draw_default[1] = embed_default, 0.0
+
+    dep, gray, mask = scene.load_refimg(sensor, typ, S)
+    tris = scene.load_stimulus(stim)
+    rest = scene.load_rest_pose("edge_follow", arm_type, sensor, typ, control_links)
+    s = cfg.sensor
+    s.image_size, s.border_on = S, 1                               # turn_off_border=False (:119)
+    s.fov_deg, s.near_, s.far_ = sj["fov"], sj["near"], sj["far"]
+    s.h_nodef_dep = dep.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_nodef_gray = gray.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+    s.n_tri = len(tris)
+    s.h_tris = tris.ctypes.data_as(C.POINTER(C.c_double))
+    cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
+    return cfg, (dep, gray, mask, tris, rest)
+
+
+class TactileWorld:
+    """N envs of one task on one device."""
+
+    def __init__(self, cfg, keepalive, device=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise L.TgError("no CUDA device visible: tactile_gym_b200 has no CPU fallback")
+        self.torch = torch
+        self.lib = L.load()
+        self.cfg, self._keep = cfg, keepalive
+        self.device = torch.device("cuda", device)
+        self.n, self.S, self.act_dim = cfg.n_envs, cfg.sensor.image_size, cfg.task.act_dim
+        self.nb = cfg.arm.nb
+        h = C.c_void_p()
+        L.check(self.lib.tg_create(C.byref(cfg), device, C.byref(h)))
+        self.h = h
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((self.n, self.S, self.S, 1), dtype=torch.uint8, device=self.device)
+            self.term_obs = torch.zeros_like(self.obs)
+            self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+        self._rngs = [seeding.np_random(None)[0] for _ in range(self.n)]
+        self._host_draws = None
+        self._steps_since_check = 0
+        self._upload_draws(fresh=True)
+
+    # ------------------------------------------------------------------ seeding / draws
+    def seed(self, seeds):
+        """seeds: one int (env i gets seed + i, the make_vec_env convention) or a list of per-env seeds."""
+        if seeds is None or isinstance(seeds, (int, np.integer)):
+            seeds = [None if seeds is None else int(seeds) + i for i in range(self.n)]
+        out = []
+        for i, s in enumerate(seeds):
+            self._rngs[i], sd = seeding.np_random(s)
+            out.append(sd)
+        self._upload_draws(fresh=True)
+        return out
+
+    def _draw(self, rng, rounds):
+        """reset_task + update_edge draws (edge_follow_env.py:293-297, 240): [embed_dist,] edge_ang per reset"""
+        t = self.cfg.task
+        out = np.empty((rounds, 2))
+        if t.embed_lo != t.embed_hi:
+            u = rng.random_sample(2 * rounds)
+            out[:, 0] = t.embed_lo + (t.embed_hi - t.embed_lo) * u[0::2]
+            out[:, 1] = -np.pi + (np.pi - (-np.pi)) * u[1::2]
+        else:
+            u = rng.random_sample(rounds)
+            out[:, 0] = t.embed_lo
+            out[:, 1] = -np.pi + (np.pi - (-np.pi)) * u
+        return out
+
+    def _upload_draws(self, fresh=False):
+        if fresh or self._host_draws is None:
+            self._host_draws = np.stack([self._draw(r, DRAW_ROUNDS) for r in self._rngs])
+        else:
+            counts = np.zeros(self.n, dtype=np.int32)
+            L.check(self.lib.tg_get_reset_counts(self.h, counts.ctypes.data, self._stream()))
+            if counts.max() == 0:
+                return
+            for i in np.nonzero(counts)[0]:
+                c = min(int(counts[i]), DRAW_ROUNDS)
+                self._host_draws[i] = np.concatenate([self._host_draws[i, c:], self._draw(self._rngs[i], c)])
+        arr = np.ascontiguousarray(self._host_draws, dtype=np.float64)
+        L.check(self.lib.tg_set_draws(self.h, arr.ctypes.data, DRAW_ROUNDS))
+        self._steps_since_check = 0
+
+    def set_draws(self, draws):
+        """Explicit draws [N, rounds, 2] (parity tests)."""
+        arr = np.ascontiguousarray(draws, dtype=np.float64)
+        assert arr.shape[0] == self.n and arr.shape[2] == self.cfg.task.n_draws
+        L.check(self.lib.tg_set_draws(self.h, arr.ctypes.data, arr.shape[1]))
+        self._host_draws = None
+        self._steps_since_check = -(10 ** 9)
+
+    # ------------------------------------------------------------------ stepping
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, mask=None):
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+            mp = mask.data_ptr()
+        L.check(self.lib.tg_reset(self.h, mp, self.obs.data_ptr(), self._stream()))
+        return self.obs
+
+    def step(self, actions, want_terminal_obs=False):
+        """actions: float32 cuda tensor [N, act_dim].  Returns (obs, reward, done) tensors (no sync)."""
+        a = actions
+        if a.device != self.device or a.dtype != self.torch.float32 or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=self.torch.float32).contiguous()
+        if a.shape != (self.n, self.act_dim):
+            raise ValueError("actions must have shape (%d, %d), got %s" % (self.n, self.act_dim, tuple(a.shape)))
+        L.check(self.lib.tg_step(self.h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                 self.term_obs.data_ptr() if want_terminal_obs else None, self._stream()))
+        self._steps_since_check += 1
+        if self._steps_since_check >= DRAW_CHECK_EVERY:
+            self._upload_draws()
+        return self.obs, self.reward, self.done
+
+    def physics_only(self, actions):
+        L.check(self.lib.tg_physics_only(self.h, actions.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
+
+    def raster_only(self):
+        L.check(self.lib.tg_raster_only(self.h, self.obs.data_ptr(), self._stream()))
+        return self.obs
+
+    # ------------------------------------------------------------------ state
+    def state_size(self):
+        return self.lib.tg_state_size(self.h)
+
+    def get_state(self):
+        st = np.zeros((self.n, self.state_size()))
+        L.check(self.lib.tg_get_state(self.h, st.ctypes.data, self._stream()))
+        return st
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, dtype=np.float64)
+        L.check(self.lib.tg_set_state(self.h, st.ctypes.data, self._stream()))
+
+    def get_camera(self):
+        cam = np.zeros((self.n, 12))
+        L.check(self.lib.tg_get_camera(self.h, cam.ctypes.data, self._stream()))
+        return cam
+
+    def launch_count(self):
+        return int(self.lib.tg_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.tg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -1,0 +1,189 @@
+"""Host-side scene compiler: compiled assets (json / npz) -> the POD structs of the C ABI.
+
+The URDF link table written by tools/compile_assets.py keeps pybullet's link order and frames.  Here the
+fixed joints are folded into their moving parent ("reduced model"), which is what the CUDA kernels run on:
+a UR5 becomes 6 bodies, an MG400 8.  Frames the reference reads through getLinkState()[0:2] (the
+INERTIAL frame of tcp_link and of <sensor>_body_link, robots/arms/base_robot_arm.py:136-151,
+sensors/tactile_sensor.py:150-187) are kept as rigid offsets on their owning body.
+"""
+import json
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+def rpy_to_mat(rpy):
+    r, p, y = rpy
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    return np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                     [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                     [-sp, cp * sr, cp * cr]])
+
+
+def quat_to_mat(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def quat_from_euler(rpy):
+    """p.getQuaternionFromEuler"""
+    hr, hp, hy = rpy[0] * 0.5, rpy[1] * 0.5, rpy[2] * 0.5
+    cr, sr, cp, sp, cy, sy = np.cos(hr), np.sin(hr), np.cos(hp), np.sin(hp), np.cos(hy), np.sin(hy)
+    return np.array([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy])
+
+
+def load_model_json(arm, sensor, typ):
+    path = os.path.join(ASSETS, "models", "%s_%s_%s.json" % (arm, typ, sensor))
+    if not os.path.isfile(path):
+        raise ValueError("no compiled model for arm_type=%r tactile_sensor_name=%r type=%r" % (arm, sensor, typ))
+    with open(path) as f:
+        return json.load(f)
+
+
+def load_sensor_json(sensor, typ):
+    with open(os.path.join(ASSETS, "sensors.json")) as f:
+        sj = json.load(f)
+    if sensor not in sj or typ not in sj[sensor]["types"]:
+        raise ValueError("unknown tactile sensor %r / %r" % (sensor, typ))
+    return sj[sensor]
+
+
+def load_rest_pose(env, arm, sensor, typ, control_links):
+    with open(os.path.join(ASSETS, "rest_poses.json")) as f:
+        rp = json.load(f)[env][arm]
+    rp = rp[sensor][typ] if sensor in rp else rp[typ]
+    return np.asarray(rp, dtype=np.float64)[control_links].copy()
+
+
+def load_refimg(sensor, typ, S):
+    path = os.path.join(ASSETS, "refimg", "%s_%s_%d.npz" % (sensor, typ, S))
+    if not os.path.isfile(path):
+        raise ValueError("no reference images for %s/%s at %dx%d" % (sensor, typ, S, S))
+    d = np.load(path)
+    return (np.ascontiguousarray(d["nodef_dep"], dtype=np.float32), np.ascontiguousarray(d["nodef_gray"], dtype=np.float32),
+            np.ascontiguousarray(d["border_mask"], dtype=np.uint8))
+
+
+def load_stimulus(name):
+    return np.ascontiguousarray(np.load(os.path.join(ASSETS, "stimuli", name + ".npz"))["tris"], dtype=np.float64)
+
+
+def reduce_model(mj, sensor, cam_pos, cam_rpy):
+    """Fold fixed joints; returns (TgArm, control_links)."""
+    links = mj["links"]
+    n = len(links)
+    names = [l["link_name"] for l in links]
+    moving = [i for i, l in enumerate(links) if l["joint_type"] == 1]
+    body_of_link = [-1] * n           # owning moving body (index into `moving`), -1 = static base
+    T_body_link = [None] * n          # (R, t): link frame expressed in its owning body's frame (q = 0)
+    arm = L.TgArm()
+    arm.nb = len(moving)
+    if arm.nb > L.TG_MAXB:
+        raise ValueError("arm has %d dofs (max %d)" % (arm.nb, L.TG_MAXB))
+    arm.topo = L.TG_TOPO_CHAIN6 if arm.nb == 6 else L.TG_TOPO_MG400
+    expected_parent = {L.TG_TOPO_CHAIN6: [-1, 0, 1, 2, 3, 4], L.TG_TOPO_MG400: [-1, 0, 1, 2, 3, 0, 5, 6]}[arm.topo]
+    for i, l in enumerate(links):
+        p = l["parent"]
+        Rj, tj = rpy_to_mat(l["joint_rpy"]), np.array(l["joint_xyz"], dtype=np.float64)
+        if p < 0:
+            Rp, tp, pb = np.eye(3), np.zeros(3), -1
+        else:
+            Rp, tp, pb = T_body_link[p][0], T_body_link[p][1], body_of_link[p]
+        R, t = Rp @ Rj, tp + Rp @ tj      # child link frame in the parent's owning body frame
+        if l["joint_type"] == 1:
+            b = moving.index(i)
+            if pb != expected_parent[b]:
+                raise ValueError("unexpected arm topology at %s" % names[i])
+            a = np.array(l["axis"], dtype=np.float64)
+            a = a / np.linalg.norm(a)
+            for c in range(3):
+                arm.jpos[b][c] = t[c]
+                arm.axis[b][c] = a[c]
+            for c in range(9):
+                arm.jrot[b][c] = R.reshape(-1)[c]
+            body_of_link[i] = b
+            T_body_link[i] = (np.eye(3), np.zeros(3))
+        elif l["joint_type"] == 0:
+            body_of_link[i] = pb
+            T_body_link[i] = (R, t)
+        else:
+            raise ValueError("joint type of %s not supported" % names[i])
+    # composite inertias + damping sub-links
+    nsub = 0
+    for b in range(arm.nb):
+        parts = []
+        for i, l in enumerate(links):
+            if body_of_link[i] != b or l["mass"] <= 0:
+                continue
+            R, t = T_body_link[i]
+            Rin = R @ rpy_to_mat(l["inertial_rpy"])
+            c = t + R @ np.array(l["inertial_xyz"], dtype=np.float64)
+            I = Rin @ np.diag(l["inertia_diag"]) @ Rin.T
+            parts.append((l["mass"], c, I))
+            if nsub >= L.TG_MAXSUB:
+                raise ValueError("too many mass-carrying links")
+            arm.sub_body[nsub] = b
+            arm.sub_mass[nsub] = l["mass"]
+            for k in range(3):
+                arm.sub_com[nsub][k] = c[k]
+                arm.sub_inertia[nsub][k] = l["inertia_diag"][k]
+            for k in range(9):
+                arm.sub_rot[nsub][k] = Rin.reshape(-1)[k]
+            nsub += 1
+        m = sum(p[0] for p in parts)
+        if m <= 0:
+            raise ValueError("body %d has no mass" % b)
+        com = sum(p[0] * p[1] for p in parts) / m
+        I = np.zeros((3, 3))
+        for mi, ci, Ii in parts:
+            d = ci - com
+            I += Ii + mi * (d.dot(d) * np.eye(3) - np.outer(d, d))
+        arm.mass[b] = m
+        for k in range(3):
+            arm.com[b][k] = com[k]
+        for k, (r, c) in enumerate([(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]):
+            arm.inertia[b][k] = I[r, c]
+    arm.nsub = nsub
+
+    def inertial_frame(link_name):
+        i = names.index(link_name)
+        R, t = T_body_link[i]
+        l = links[i]
+        return body_of_link[i], t + R @ np.array(l["inertial_xyz"], dtype=np.float64), R @ rpy_to_mat(l["inertial_rpy"])
+
+    b, t, R = inertial_frame("tcp_link")
+    arm.tcp_body = b
+    for k in range(3):
+        arm.tcp_pos[k] = t[k]
+    for k in range(9):
+        arm.tcp_rot[k] = R.reshape(-1)[k]
+    b, t, R = inertial_frame(sensor + "_body_link")
+    Rc = quat_to_mat(quat_from_euler(cam_rpy))   # multiplyTransforms(body, cam) (tactile_sensor.py:184-187)
+    tc, Rc = t + R @ np.array(cam_pos, dtype=np.float64), R @ Rc
+    arm.cam_body = b
+    for k in range(3):
+        arm.cam_pos[k] = tc[k]
+    for k in range(9):
+        arm.cam_rot[k] = Rc.reshape(-1)[k]
+    return arm, moving
+
+
+def default_physics(substeps=24, gravity=(0.0, 0.0, -9.81)):
+    """base_tactile_env.py:125-130, base_robot_arm.py:24-25, ur5.py:19-21."""
+    p = L.TgPhysics()
+    for c in range(3):
+        p.gravity[c] = gravity[c]
+    p.dt = 1.0 / 240.0
+    p.solver_iters = 150
+    p.substeps = substeps
+    p.lin_damping, p.ang_damping, p.joint_damping = 0.04, 0.04, 0.01
+    p.max_force, p.pos_gain, p.vel_gain = 1000.0, 1.0, 1.0
+    p.blocking_force = 100000.0
+    p.gravity_comp = 1
+    return p

@@ -1,0 +1,130 @@
+"""SB3-VecEnv-shaped front end of the batched engine.
+
+Stands where stable_baselines3's SubprocVecEnv stands in the reference's training set-up
+(tactile_gym/sb3_helpers/rl_utils.py:17-35): same surface (num_envs, observation_space, action_space,
+reset, step_async / step_wait / step, seed, close, get_attr / set_attr / env_method, env_is_wrapped),
+numpy in / numpy out, auto-reset with infos[i]["terminal_observation"], Monitor-style
+infos[i]["episode"] = {"r", "l", "t"}.  `step_tensor` is the device-resident path (no host copies).
+"""
+import time
+
+import numpy as np
+
+from . import spaces
+from .engine import TactileWorld, edge_follow_config
+
+try:  # pragma: no cover
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:  # noqa: BLE001
+    _VecEnvBase = object
+
+CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config}
+
+
+class TactileVecEnv(_VecEnvBase):
+    def __init__(self, env_id, n_envs, seed=None, env_kwargs=None, device=0, lanes_per_warp=0):
+        kw = dict(env_kwargs or {})
+        if env_id not in CONFIG_BUILDERS:
+            raise NotImplementedError("%s is not built yet in tactile_gym_b200" % env_id)
+        env_modes = kw.get("env_modes")
+        if env_modes is None:
+            raise ValueError("env_kwargs['env_modes'] is required")
+        if kw.get("show_gui") or kw.get("show_tactile"):
+            raise ValueError("show_gui / show_tactile are not available in the batched engine")
+        if env_modes.get("observation_mode", "tactile") != "tactile":
+            raise NotImplementedError("only observation_mode='tactile' is built")
+        image_size = kw.get("image_size", [64, 64])
+        max_steps = kw.get("max_steps", 250)
+        cfg, keep = CONFIG_BUILDERS[env_id](env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp)
+        self.world = TactileWorld(cfg, keep, device=device)
+        self.num_envs = n_envs
+        S = int(image_size[0])
+        self.observation_space = spaces.Dict({"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)})
+        self.action_space = spaces.Box(low=-0.25, high=0.25, shape=(self.world.act_dim,), dtype=np.float32)
+        self.metadata = {"render.modes": ["rgb_array"]}
+        self._actions = None
+        self._ep_ret = np.zeros(n_envs, dtype=np.float64)
+        self._ep_len = np.zeros(n_envs, dtype=np.int64)
+        self._t0 = time.time()
+        torch = self.world.torch
+        self._pin_actions = torch.zeros((n_envs, self.world.act_dim), dtype=torch.float32).pin_memory()
+        self._pin_obs = torch.zeros((n_envs, S, S, 1), dtype=torch.uint8).pin_memory()
+        self._pin_term = torch.zeros((n_envs, S, S, 1), dtype=torch.uint8).pin_memory()
+        self._pin_rew = torch.zeros(n_envs, dtype=torch.float32).pin_memory()
+        self._pin_done = torch.zeros(n_envs, dtype=torch.uint8).pin_memory()
+        if seed is not None:
+            self.seed(seed)
+        self.h2d_bytes_per_step = self._pin_actions.numel() * 4
+        self.d2h_bytes_per_step = self._pin_obs.numel() + self._pin_rew.numel() * 4 + self._pin_done.numel()
+
+    # ---------------------------------------------------------------- VecEnv API (host numpy)
+    def seed(self, seed=None):
+        return self.world.seed(seed)
+
+    def reset(self):
+        self.world.reset()
+        self._pin_obs.copy_(self.world.obs, non_blocking=True)
+        self.world.torch.cuda.synchronize(self.world.device)
+        self._ep_ret[:] = 0
+        self._ep_len[:] = 0
+        return {"tactile": self._pin_obs.numpy().copy()}
+
+    def step_async(self, actions):
+        torch = self.world.torch
+        self._pin_actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, -1)))
+        a = self._pin_actions.to(self.world.device, non_blocking=True)
+        self.world.step(a, want_terminal_obs=True)
+        self._pin_obs.copy_(self.world.obs, non_blocking=True)
+        self._pin_rew.copy_(self.world.reward, non_blocking=True)
+        self._pin_done.copy_(self.world.done, non_blocking=True)
+
+    def step_wait(self):
+        torch = self.world.torch
+        torch.cuda.synchronize(self.world.device)
+        rew = self._pin_rew.numpy().copy()
+        done = self._pin_done.numpy().astype(bool)
+        self._ep_ret += rew
+        self._ep_len += 1
+        infos = [{} for _ in range(self.num_envs)]
+        if done.any():
+            idx = np.nonzero(done)[0]
+            term = self.world.term_obs[torch.as_tensor(idx, device=self.world.device)].cpu().numpy()
+            for k, i in enumerate(idx):
+                infos[i]["terminal_observation"] = {"tactile": term[k]}
+                infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
+                self._ep_ret[i] = 0
+                self._ep_len[i] = 0
+        return {"tactile": self._pin_obs.numpy().copy()}, rew, done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    # ---------------------------------------------------------------- device-resident path
+    def step_tensor(self, actions):
+        """actions: cuda float32 [N, act_dim] -> (obs, reward, done) cuda tensors; nothing synchronises."""
+        return self.world.step(actions)
+
+    def close(self):
+        self.world.close()
+
+    def get_attr(self, attr_name, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [getattr(self, attr_name) for _ in range(n)]
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [getattr(self, method_name)(*args, **kwargs) for _ in range(n)]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [False] * n
+
+    def get_images(self):
+        return [np.repeat(o, 3, axis=2) for o in self.world.obs.cpu().numpy()]
+
+    def render(self, mode="rgb_array"):
+        return self.get_images()[0]

@@ -1,0 +1,218 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances: joint state 1e-9 (fp64 both sides, different formulations), TCP pose / reward
+1e-6 (north_star allows 1e-3), tactile image <= 1 LSB with >= 99.9% of pixels identical (north_star: 2/255).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _world(edge_modes, n, S=128, max_steps=200, lanes=0):
+    import tactile_gym_b200 as tg
+
+    return tg.make_vec("edge_follow-v0", n, env_kwargs={"env_modes": edge_modes, "image_size": [S, S], "max_steps": max_steps},
+                       lanes_per_warp=lanes)
+
+
+def _draws(rng, n, rounds=4):
+    return np.stack([rng.uniform(0.0015, 0.0065, (n, rounds)), rng.uniform(-np.pi, np.pi, (n, rounds))], axis=2)
+
+
+def _img_close(a, b):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return d.max(), (d != 0).mean()
+
+
+def test_dynamics_hooks_match_oracle(oracle, edge_modes):
+    env = _world(edge_modes, 4)
+    w = env.world
+    m = oracle.load_model("ur5", "tactip", "standard", [0.65, 0, 0.035], [-np.pi, 0, np.pi / 2], np.zeros((6, 2)))
+    rest = oracle.rest_pose("edge_follow", "ur5", "tactip", "standard", m)
+    rng = np.random.RandomState(0)
+    n = 64
+    q = rest + rng.uniform(-0.5, 0.5, (n, 6)); qd = rng.uniform(-1, 1, (n, 6))
+    from tactile_gym_b200 import _lib as L
+
+    tau = np.zeros((n, 6))
+    L.check(w.lib.tg_test_inverse_dynamics(w.h, n, q.ctypes.data, qd.ctypes.data, tau.ctypes.data))
+    M = np.zeros((n, 6, 6))
+    L.check(w.lib.tg_test_mass_matrix(w.h, n, q.ctypes.data, M.ctypes.data))
+    for i in range(n):
+        assert np.allclose(tau[i], oracle.inverse_dynamics(m, q[i], qd[i]), atol=1e-9)
+        assert np.allclose(M[i] @ oracle.mass_matrix_inverse(m, q[i]), np.eye(6), atol=1e-8)
+    # 24 substeps with velocity motors
+    tv = rng.uniform(-0.05, 0.05, (n, 6))
+    q2, qd2 = q.copy(), qd.copy() * 0.01
+    q_in, qd_in = q2.copy(), qd2.copy()
+    L.check(w.lib.tg_test_substep(w.h, n, 24, q2.ctypes.data, qd2.ctypes.data, tv.ctypes.data))
+    for i in range(n):
+        s = oracle.OrState()
+        for k in range(6):
+            s.q[k] = q_in[i, k]; s.qd[k] = qd_in[i, k]; s.motor_mode[k] = 0; s.target_vel[k] = tv[i, k]; s.kd[k] = 1.0; s.max_force[k] = 1000.0
+        for _ in range(24):
+            oracle.lib().or_step_sim(C.byref(m), C.byref(s))
+        assert np.allclose(q2[i], np.array(s.q[:6]), atol=1e-10)
+        assert np.allclose(qd2[i], np.array(s.qd[:6]), atol=1e-9)
+    env.close()
+
+
+@pytest.mark.parametrize("S", [64, 128, 256])
+def test_reset_and_steps_match_oracle(oracle, edge_modes, S):
+    n, steps = 12, 6
+    env = _world(edge_modes, n, S=S)
+    rng = np.random.RandomState(S)
+    draws = _draws(rng, n)
+    env.world.set_draws(draws)
+    obs = env.reset()["tactile"]
+    st = env.world.get_state()
+    refs = []
+    for i in range(n):
+        r = oracle.EdgeFollowOracle(image_size=S)
+        o = r.reset(draws=tuple(draws[i, 0]))
+        refs.append(r)
+        assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=1e-9)
+        assert int(st[i, 22]) == r.last_reset_substeps
+        mx, frac = _img_close(o, obs[i])
+        assert mx <= 1 and frac < 1e-3, (i, mx, frac)
+        assert (obs[i][..., 0][r.ref[2] == 0] > 0).sum() > 20   # something is actually pressed into the skin
+    for k in range(steps):
+        act = rng.uniform(-0.3, 0.3, (n, 2)).astype(np.float32)   # beyond +-0.25: exercises the clip
+        o2, rew, done, infos = env.step(act)
+        st = env.world.get_state()
+        for i, r in enumerate(refs):
+            o, rr, dd, _ = r.step(act[i])
+            assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=1e-9)
+            assert np.allclose(st[i, 6:12], np.array(r.s.qd[:6]), atol=1e-8)
+            p, qq = r.tcp_world()
+            assert np.allclose(st[i, 12:15], p, atol=1e-9)
+            assert abs(rr - rew[i]) < 1e-6 and bool(dd) == bool(done[i])
+            mx, frac = _img_close(o, o2["tactile"][i])
+            assert mx <= 1 and frac < 1e-3, (k, i, mx, frac)
+    env.close()
+
+
+def test_tcp_limits_zero_the_velocity(oracle, edge_modes):
+    """check_TCP_vel_lims (base_robot_arm.py:357-380): drive into the +x limit (0.175 m) and stay there."""
+    env = _world(edge_modes, 2, S=64, max_steps=10000)
+    env.world.set_draws(np.array([[[0.0035, 0.3]], [[0.0035, -2.0]]]))
+    env.reset()
+    refs = [oracle.EdgeFollowOracle(image_size=64, max_steps=10000) for _ in range(2)]
+    refs[0].reset(draws=(0.0035, 0.3)); refs[1].reset(draws=(0.0035, -2.0))
+    act = np.array([[0.25, 0.0], [0.25, 0.25]], dtype=np.float32)
+    for k in range(190):
+        _, _, done, _ = env.step(act)
+        for i in range(2):
+            refs[i].step(act[i])
+    st = env.world.get_state()
+    for i in range(2):
+        assert np.allclose(st[i, :6], np.array(refs[i].s.q[:6]), atol=1e-8)
+        p, _ = oracle.tcp_pose_workframe(refs[i].m, np.array(refs[i].s.q[:6]))
+        assert 0.175 < p[0] < 0.1775
+    env.close()
+
+
+def test_autoreset_and_terminal_observation(oracle, edge_modes):
+    n, S = 6, 64
+    env = _world(edge_modes, n, S=S, max_steps=3)
+    rng = np.random.RandomState(5)
+    draws = _draws(rng, n, rounds=3)
+    env.world.set_draws(draws)
+    env.reset()
+    refs = []
+    for i in range(n):
+        r = oracle.EdgeFollowOracle(image_size=S, max_steps=3)
+        r.reset(draws=tuple(draws[i, 0]))
+        refs.append(r)
+    for k in range(3):
+        act = rng.uniform(-0.25, 0.25, (n, 2)).astype(np.float32)
+        obs, rew, done, infos = env.step(act)
+        last = [r.step(act[i]) for i, r in enumerate(refs)]
+    assert done.all()
+    for i, r in enumerate(refs):
+        assert _img_close(infos[i]["terminal_observation"]["tactile"], last[i][0])[0] <= 1
+        assert infos[i]["episode"]["l"] == 3
+        o = r.reset(draws=tuple(draws[i, 1]))          # second round of draws
+        assert _img_close(o, obs["tactile"][i])[0] <= 1
+    st = env.world.get_state()
+    assert (st[:, 21] == 0).all()                       # step counters restarted
+    env.close()
+
+
+def test_lane_packing_is_invisible(edge_modes):
+    """8 / 16 / 32 active lanes per warp is a scheduling choice only: identical results."""
+    res = []
+    for lanes in (8, 16, 32):
+        env = _world(edge_modes, 40, S=64, lanes=lanes)
+        rng = np.random.RandomState(1)
+        env.world.set_draws(_draws(rng, 40))
+        env.reset()
+        for _ in range(3):
+            env.step(rng.uniform(-0.25, 0.25, (40, 2)).astype(np.float32))
+        res.append((env.world.get_state(), env.world.obs.cpu().numpy()))
+        env.close()
+    for st, ob in res[1:]:
+        assert np.array_equal(st, res[0][0]) and np.array_equal(ob, res[0][1])
+
+
+def test_seeded_vec_env_reproduces_gym_rng_stream(oracle, edge_modes):
+    """env i seeded with seed + i, draws in the reference's order: embed_dist then edge_ang (edge_follow_env.py:293,240)."""
+    n = 5
+    env = _world(edge_modes, n, S=64)
+    env.seed(100)
+    env.reset()
+    st = env.world.get_state()
+    for i in range(n):
+        rng = oracle.gym_np_random(100 + i)
+        embed = rng.uniform(0.0015, 0.0065); ang = rng.uniform(-np.pi, np.pi)
+        assert st[i, 19] == embed and st[i, 20] == ang
+    env.close()
+
+
+def test_gym_env_surface(edge_modes):
+    import tactile_gym_b200 as tg
+
+    env = tg.make("edge_follow-v0", max_steps=5, image_size=[64, 64], env_modes=edge_modes)
+    assert env.action_space.shape == (2,) and env.observation_space["tactile"].shape == (64, 64, 1)
+    assert env.seed(3) == [3]
+    o = env.reset()
+    assert o["tactile"].dtype == np.uint8 and o["tactile"].shape == (64, 64, 1)
+    for k in range(5):
+        o, r, d, info = env.step(env.action_space.sample())
+        assert isinstance(r, float) and isinstance(d, bool) and info == {}
+    assert d is True
+    env.close()
+
+
+def test_full_size_properties(edge_modes):
+    """BASELINE config 2 size (4096 x 128^2): size-independent properties instead of an oracle run."""
+    import torch
+
+    n = 4096
+    env = _world(edge_modes, n, S=128)
+    env.seed(1)
+    obs = env.reset()["tactile"]
+    from tactile_gym_b200 import scene
+
+    dep, gray, mask = scene.load_refimg("tactip", "standard", 128)
+    # border pixels are the baked grey image for every env; non-border pixels are bounded by full scale
+    assert (obs[:, mask == 1, 0] == gray[mask == 1].astype(np.uint8)[None]).all()
+    assert (obs[:, mask == 0, 0] > 0).any(axis=1).all()
+    # idempotence: rendering the same state twice gives the same bytes
+    a = env.world.raster_only().clone()
+    b = env.world.raster_only()
+    assert torch.equal(a, b)
+    # zero action keeps every env where it is
+    st0 = env.world.get_state()
+    env.step(np.zeros((n, 2), dtype=np.float32))
+    st1 = env.world.get_state()
+    assert np.abs(st1[:, 12:15] - st0[:, 12:15]).max() < 1e-6
+    # opposite actions move the TCP by opposite amounts (linearity of the velocity map)
+    act = np.tile(np.array([[0.2, -0.1]], dtype=np.float32), (n, 1))
+    env.step(act); st2 = env.world.get_state()
+    env.step(-act); st3 = env.world.get_state()
+    assert np.abs((st2[:, 12:15] - st1[:, 12:15]) + (st3[:, 12:15] - st2[:, 12:15])).max() < 1e-6
+    assert np.allclose(np.linalg.norm(st2[:, 12:14] - st1[:, 12:14], axis=1), np.hypot(0.008, 0.004) * 0.1, atol=1e-5)
+    env.close()

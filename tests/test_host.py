@@ -1,0 +1,109 @@
+"""CPU: host logic - scene compiler, config builder, registry, seeding, C-ABI exports (no GPU calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reduced_model_matches_link_table(oracle, edge_modes):
+    """Folding the fixed joints keeps total mass and the TCP / camera frames of the 11-link table."""
+    from tactile_gym_b200 import scene
+    from tactile_gym_b200.engine import edge_follow_config
+
+    cfg, keep = edge_follow_config(edge_modes, [128, 128], 200, 8)
+    a = cfg.arm
+    assert a.nb == 6 and a.topo == 0
+    mj = scene.load_model_json("ur5", "tactip", "standard")
+    moving_or_below = sum(l["mass"] for l in mj["links"][1:])  # all but base_link
+    assert abs(sum(a.mass[i] for i in range(6)) - moving_or_below) < 1e-12
+    # world TCP pose from the reduced model (python FK) == oracle's link-table FK
+    m = oracle.load_model("ur5", "tactip", "standard", [0.65, 0, 0.035], [-np.pi, 0, np.pi / 2], np.zeros((6, 2)))
+    q = np.array(keep[4])
+    R, p = np.eye(3), np.zeros(3)
+    for b in range(6):
+        p = p + R @ np.array(a.jpos[b][:])
+        ax = np.array(a.axis[b][:]); c, s = np.cos(q[b]), np.sin(q[b])
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R = R @ np.array(a.jrot[b][:]).reshape(3, 3) @ (np.eye(3) + s * K + (1 - c) * K @ K)
+    tcp = p + R @ np.array(a.tcp_pos[:])
+    P, Q = oracle.link_states(m, q)
+    assert np.allclose(tcp, P[m.tcp_link], atol=1e-12)
+    eye, *_ = oracle.camera_frame(m, q)
+    assert np.allclose(p + R @ np.array(a.cam_pos[:]), eye, atol=1e-12)
+
+
+def test_config_rejects_bad_modes(edge_modes):
+    from tactile_gym_b200.engine import edge_follow_config
+
+    bad = dict(edge_modes); del bad["tactile_sensor_name"]
+    with pytest.raises(KeyError):
+        edge_follow_config(bad, [128, 128], 200, 1)
+    bad = dict(edge_modes, arm_type="pr2")
+    with pytest.raises(ValueError):
+        edge_follow_config(bad, [128, 128], 200, 1)
+    bad = dict(edge_modes, control_mode="TCP_position_control")
+    with pytest.raises(NotImplementedError):
+        edge_follow_config(bad, [128, 128], 200, 1)
+
+
+def test_registry_ids():
+    import tactile_gym_b200 as tg
+
+    assert "edge_follow-v0" in tg.REGISTRY
+    with pytest.raises(KeyError):
+        tg.make("no_such_env-v0")
+    with pytest.raises(NotImplementedError):
+        tg.make("object_roll-v0")
+
+
+def test_seeding_matches_oracle_restatement(oracle):
+    from tactile_gym_b200 import seeding
+
+    for s in (0, 1, 12345):
+        a, _ = seeding.np_random(s)
+        assert np.array_equal(a.uniform(size=4), oracle.gym_np_random(s).uniform(size=4))
+    with pytest.raises(ValueError):
+        seeding.np_random(-1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "tactile_gym_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert not re.search(r"#include\s*[<\"].*oracle", src), f
+                assert "libtg_oracle" not in src, f
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/tactile_gym_b200.h declares."""
+    import __graft_entry__ as g
+    from tactile_gym_b200 import _lib
+
+    g.build()
+    header = open(os.path.join(ROOT, "include", "tactile_gym_b200.h")).read()
+    declared = set(re.findall(r"\b(tg_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tg_version() == 100
+
+
+def test_no_gpu_fails_loudly(edge_modes):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import tactile_gym_b200 as tg
+    from tactile_gym_b200._lib import TgError
+
+    with pytest.raises(TgError):
+        tg.make("edge_follow-v0", env_modes=edge_modes, image_size=[64, 64])

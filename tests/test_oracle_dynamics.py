@@ -1,0 +1,48 @@
+"""CPU: self-consistency of the oracle's dynamics (the only pybullet-free checks there are):
+RNEA(q, qd, ABA(q, qd, tau)) == tau, M^-1 symmetric positive definite, motor-only step reaches the target."""
+import ctypes as C
+
+import numpy as np
+
+
+def _model(oracle):
+    m = oracle.load_model("ur5", "tactip", "standard", [0.65, 0, 0.035], [-np.pi, 0, np.pi / 2], np.zeros((6, 2)))
+    return m, oracle.rest_pose("edge_follow", "ur5", "tactip", "standard", m)
+
+
+def test_rnea_aba_identity(oracle):
+    m, rest = _model(oracle)
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        q = rest + rng.uniform(-0.5, 0.5, 6); qd = rng.uniform(-1, 1, 6); tau = rng.uniform(-5, 5, 6)
+        qdd = oracle.forward_dynamics(m, q, qd, tau)
+        assert np.allclose(oracle.inverse_dynamics(m, q, qd, qdd), tau, atol=1e-10)
+
+
+def test_minv_spd_and_consistent_with_rnea(oracle):
+    m, rest = _model(oracle)
+    Minv = oracle.mass_matrix_inverse(m, rest)
+    assert np.allclose(Minv, Minv.T, atol=1e-12)
+    assert np.linalg.eigvalsh(Minv).min() > 0
+    # column j of M = RNEA(q, 0, e_j) - RNEA(q, 0, 0)
+    g = oracle.inverse_dynamics(m, rest, np.zeros(6), np.zeros(6))
+    M = np.stack([oracle.inverse_dynamics(m, rest, np.zeros(6), np.eye(6)[j]) - g for j in range(6)], axis=1)
+    assert np.allclose(M @ Minv, np.eye(6), atol=1e-9)
+
+
+def test_velocity_motor_reaches_target(oracle):
+    m, rest = _model(oracle)
+    s = oracle.OrState()
+    tv = np.array([0.02, -0.01, 0.015, 0.01, -0.02, 0.03])
+    for i in range(6):
+        s.q[i] = rest[i]; s.qd[i] = 0; s.motor_mode[i] = 0; s.target_vel[i] = tv[i]; s.kd[i] = 1.0; s.max_force[i] = 1000.0
+    oracle.lib().or_step_sim(C.byref(m), C.byref(s))
+    assert np.allclose(np.array(s.qd[:6]), tv, atol=1e-12)
+    assert np.allclose(np.array(s.q[:6]), rest + tv / 240.0, atol=1e-12)
+
+
+def test_gym_seeding_is_deterministic(oracle):
+    a = oracle.gym_np_random(7).uniform(size=3)
+    b = oracle.gym_np_random(7).uniform(size=3)
+    c = oracle.gym_np_random(8).uniform(size=3)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
