@@ -71,6 +71,8 @@ typedef struct {
     double mass[TG_MAXB];
     double com[TG_MAXB][3];
     double inertia[TG_MAXB][6]; /* about the COM, body frame: xx xy xz yy yz zz       */
+    int32_t sub_start[TG_MAXB + 1]; /* sub-links of body b are sub_start[b] .. sub_start[b+1]-1 */
+    int32_t pad1;
     int32_t sub_body[TG_MAXSUB];
     double sub_mass[TG_MAXSUB];
     double sub_com[TG_MAXSUB][3];
@@ -88,6 +90,7 @@ typedef struct {
     int32_t substeps;       /* 24    */
     double lin_damping, ang_damping, joint_damping; /* 0.04 0.04 0.01 */
     double max_force, pos_gain, vel_gain;           /* 1000 1 1       */
+    double solver_residual_threshold; /* 1e-7: pybullet's default solverResidualThreshold [EXT] */
     double blocking_force;  /* 1e5: pybullet's default when setJointMotorControlArray gets no `forces` */
     int32_t gravity_comp;   /* 1: Robot.step_sim's calculateInverseDynamics torque is applied */
     int32_t pad0;

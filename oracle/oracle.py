@@ -29,7 +29,7 @@ class OrModel(C.Structure):
         ("inertial_xyz", (C.c_double * 3) * MAXL), ("inertial_rpy", (C.c_double * 3) * MAXL),
         ("mass", C.c_double * MAXL), ("inertia", (C.c_double * 3) * MAXL),
         ("tcp_link", C.c_int), ("body_link", C.c_int),
-        ("gravity", C.c_double * 3), ("dt", C.c_double), ("solver_iters", C.c_int),
+        ("gravity", C.c_double * 3), ("dt", C.c_double), ("solver_iters", C.c_int), ("solver_residual_threshold", C.c_double),
         ("lin_damping", C.c_double), ("ang_damping", C.c_double), ("joint_damping", C.c_double),
         ("workframe_pos", C.c_double * 3), ("workframe_rpy", C.c_double * 3), ("tcp_lims", (C.c_double * 2) * 6),
         ("max_force", C.c_double), ("pos_gain", C.c_double), ("vel_gain", C.c_double), ("mg400_slave", C.c_int),
@@ -114,6 +114,7 @@ def load_model(arm, sensor, typ, workframe_pos, workframe_rpy, tcp_lims, gravity
         m.tcp_lims[i][1] = tcp_lims[i][1]
     m.dt = dt
     m.solver_iters = 150
+    m.solver_residual_threshold = 1e-7
     m.lin_damping = 0.04
     m.ang_damping = 0.04
     m.joint_damping = 0.01

@@ -480,9 +480,11 @@ void or_forward_dynamics(const OrModel* m, const double* q, const double* qd, co
  *   2. ABA (gravity, gyroscopic, link damping, applied torques); qd += dt * qdd
  *   3. one constraint row per motor: J = e_i, response = M^-1 e_i, target velocity
  *        rhs_v = kp * erp(=1) * (pos_target - q)/dt + qd + kd * (vel_target - qd),  |impulse| <= force * dt
- *   4. projected Gauss-Seidel, numSolverIterations sweeps; the sweep direction alternates
- *      (even iterations back to front); early exit only when a sweep's largest impulse change is
- *      exactly 0 (leastSquaresResidualThreshold = 0)
+ *   4. projected Gauss-Seidel, at most numSolverIterations sweeps; the sweep direction alternates
+ *      (even iterations back to front); after each sweep the solver stops if the largest squared
+ *      velocity-level change of any row, (deltaImpulse / jacDiagABInv)^2, is <= solverResidualThreshold
+ *      (pybullet's default 1e-7, PyBullet Quickstart Guide, setPhysicsEngineParameter; the reference
+ *      does not override it)
  *   5. qd += delta; q += dt * qd
  * Call site: robots/arms/robot.py:141; parameters rl_envs/base_tactile_env.py:127-130.
  */
@@ -526,9 +528,10 @@ void or_step_simulation(const OrModel* m, OrState* s, const double* tau_applied)
             else if (sum > lim[r]) { delta = lim[r] - applied[r]; applied[r] = lim[r]; }
             else applied[r] = sum;
             for (int i = 0; i < n; i++) dv[i] += resp[r][i] * delta;
-            if (delta * delta > resid) resid = delta * delta;
+            double dvel = diaginv[r] != 0 ? delta / diaginv[r] : 0.0;
+            if (dvel * dvel > resid) resid = dvel * dvel;
         }
-        if (resid <= 0) break;
+        if (resid <= m->solver_residual_threshold) break;
     }
     for (int i = 0; i < n; i++) { s->qd[i] += dv[i]; s->q[i] += m->dt * s->qd[i]; }
 }

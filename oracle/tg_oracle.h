@@ -40,6 +40,7 @@ typedef struct {
     /* physics parameters (base_tactile_env.py:125-130, base_robot_arm.py:24-25) */
     double gravity[3], dt;
     int solver_iters;
+    double solver_residual_threshold; /* [EXT] pybullet default solverResidualThreshold = 1e-7 (not overridden at base_tactile_env.py:127-130) */
     double lin_damping, ang_damping, joint_damping;
     /* arm frames (base_robot_arm.py:39-46, set_TCP_lims :114-118) */
     double workframe_pos[3], workframe_rpy[3];

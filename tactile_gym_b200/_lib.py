@@ -21,6 +21,7 @@ class TgArm(C.Structure):
         ("topo", C.c_int32), ("nb", C.c_int32), ("nsub", C.c_int32), ("pad0", C.c_int32),
         ("jpos", D3 * TG_MAXB), ("jrot", D9 * TG_MAXB), ("axis", D3 * TG_MAXB),
         ("mass", C.c_double * TG_MAXB), ("com", D3 * TG_MAXB), ("inertia", (C.c_double * 6) * TG_MAXB),
+        ("sub_start", C.c_int32 * (TG_MAXB + 1)), ("pad1", C.c_int32),
         ("sub_body", C.c_int32 * TG_MAXSUB), ("sub_mass", C.c_double * TG_MAXSUB), ("sub_com", D3 * TG_MAXSUB),
         ("sub_rot", D9 * TG_MAXSUB), ("sub_inertia", D3 * TG_MAXSUB),
         ("tcp_body", C.c_int32), ("cam_body", C.c_int32),
@@ -32,7 +33,7 @@ class TgPhysics(C.Structure):
     _fields_ = [
         ("gravity", D3), ("dt", C.c_double), ("solver_iters", C.c_int32), ("substeps", C.c_int32),
         ("lin_damping", C.c_double), ("ang_damping", C.c_double), ("joint_damping", C.c_double),
-        ("max_force", C.c_double), ("pos_gain", C.c_double), ("vel_gain", C.c_double), ("blocking_force", C.c_double),
+        ("max_force", C.c_double), ("pos_gain", C.c_double), ("vel_gain", C.c_double), ("solver_residual_threshold", C.c_double), ("blocking_force", C.c_double),
         ("gravity_comp", C.c_int32), ("pad0", C.c_int32),
     ]
 

@@ -12,8 +12,8 @@
 //     with calcAccelerationDeltasMultiDof;
 //   * the arm's topology is a template parameter: every loop unrolls, every array lives in registers;
 //   * the motor rows (J = e_i) are solved by the same projected Gauss-Seidel sweep bullet runs
-//     (numSolverIterations = 150, alternating sweep direction, impulse clamp force*dt, exact-zero
-//     residual exit), staged in registers rather than shared memory because a row is 6 numbers.
+//     (numSolverIterations = 150, alternating sweep direction, impulse clamp force*dt, pybullet's
+//     solverResidualThreshold exit), staged in registers rather than shared memory because a row is 6 numbers.
 // The CPU oracle (oracle/tg_oracle.c) restates bullet's own formulation (ABA in link-COM frames over all
 // 11 links); agreement between the two is the parity test.
 #pragma once
@@ -270,19 +270,19 @@ TGD void crba(const Kin<T::NB>& k, SpI (&sp)[T::NB], double (&M)[T::NB][T::NB])
     }
 }
 
-// Cholesky inverse of an SPD NB x NB matrix (in registers)
+// Cholesky inverse of an SPD NB x NB matrix (in registers).  One rsqrt per column, no divisions.
 template <int NB>
 TGD void spd_inverse(const double (&M)[NB][NB], double (&Minv)[NB][NB])
 {
-    double L[NB][NB], Li[NB][NB];
+    double L[NB][NB], Li[NB][NB], dinv[NB];
 #pragma unroll
     for (int j = 0; j < NB; j++) {
         double d = M[j][j];
 #pragma unroll
         for (int k2 = 0; k2 < j; k2++) d -= L[j][k2] * L[j][k2];
-        d = sqrt(d);
-        L[j][j] = d;
-        const double inv = 1.0 / d;
+        const double inv = rsqrt(d);
+        dinv[j] = inv;
+        L[j][j] = d * inv;
 #pragma unroll
         for (int i = j + 1; i < NB; i++) {
             double s = M[i][j];
@@ -294,13 +294,13 @@ TGD void spd_inverse(const double (&M)[NB][NB], double (&Minv)[NB][NB])
     // Li = L^-1 (lower triangular)
 #pragma unroll
     for (int j = 0; j < NB; j++) {
-        Li[j][j] = 1.0 / L[j][j];
+        Li[j][j] = dinv[j];
 #pragma unroll
         for (int i = j + 1; i < NB; i++) {
             double s = 0;
 #pragma unroll
             for (int k2 = j; k2 < i; k2++) s -= L[i][k2] * Li[k2][j];
-            Li[i][j] = s / L[i][i];
+            Li[i][j] = s * dinv[i];
         }
     }
 #pragma unroll
@@ -344,29 +344,27 @@ TGD void damping_forces(const TgArm& arm, const TgPhysics& ph, const Kin<T::NB>&
 #pragma unroll
         for (int c = 0; c < 3; c++) { Nw[i][c] = 0; Fw[i][c] = 0; }
 #pragma unroll
-    for (int s = 0; s < TG_MAXSUB; s++) {
-        if (s < arm.nsub) {
+    for (int b = 0; b < NB; b++) {
+        // mass-carrying URDF links merged into body b (sorted by body at scene-compile time)
+#pragma unroll 1
+        for (int s = arm.sub_start[b]; s < arm.sub_start[b + 1]; s++) {
+            double t[3], x[3], v[3], wl[3], nl[3], nw[3], Rs[9], xf[3];
+            m3mulv(t, k.R[b], arm.sub_com[s]);
+            x[0] = k.p[b][0] + t[0]; x[1] = k.p[b][1] + t[1]; x[2] = k.p[b][2] + t[2];
+            v3cross(v, w[b], x);
+            v[0] += vO[b][0]; v[1] += vO[b][1]; v[2] += vO[b][2];
+            m3mul(Rs, k.R[b], arm.sub_rot[s]);
+            m3tmulv(wl, Rs, w[b]);
+            const double ka = ph.ang_damping * (1.0 + sqrt(v3dot(wl, wl)));
+            const double kl = ph.lin_damping * (1.0 + sqrt(v3dot(v, v)));
 #pragma unroll
-            for (int b = 0; b < NB; b++) {
-                if (arm.sub_body[s] == b) {
-                    double t[3], x[3], v[3], wl[3], nl[3], nw[3], Rs[9], xf[3];
-                    m3mulv(t, k.R[b], arm.sub_com[s]);
-                    x[0] = k.p[b][0] + t[0]; x[1] = k.p[b][1] + t[1]; x[2] = k.p[b][2] + t[2];
-                    v3cross(v, w[b], x);
-                    v[0] += vO[b][0]; v[1] += vO[b][1]; v[2] += vO[b][2];
-                    m3mul(Rs, k.R[b], arm.sub_rot[s]);
-                    m3tmulv(wl, Rs, w[b]);
-                    const double ka = ph.ang_damping * (1.0 + sqrt(v3dot(wl, wl)));
-                    const double kl = ph.lin_damping * (1.0 + sqrt(v3dot(v, v)));
+            for (int c = 0; c < 3; c++) nl[c] = -arm.sub_inertia[s][c] * wl[c] * ka;
+            m3mulv(nw, Rs, nl);
+            const double ms = arm.sub_mass[s];
+            double f[3] = {-ms * v[0] * kl, -ms * v[1] * kl, -ms * v[2] * kl};
+            v3cross(xf, x, f);
 #pragma unroll
-                    for (int c = 0; c < 3; c++) nl[c] = -arm.sub_inertia[s][c] * wl[c] * ka;
-                    m3mulv(nw, Rs, nl);
-                    double f[3] = {-arm.sub_mass[s] * v[0] * kl, -arm.sub_mass[s] * v[1] * kl, -arm.sub_mass[s] * v[2] * kl};
-                    v3cross(xf, x, f);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { Nw[b][c] += nw[c] + xf[c]; Fw[b][c] += f[c]; }
-                }
-            }
+            for (int c = 0; c < 3; c++) { Nw[b][c] += nw[c] + xf[c]; Fw[b][c] += f[c]; }
         }
     }
 #pragma unroll
@@ -481,7 +479,7 @@ TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, co
 #pragma unroll
     for (int i = 0; i < NB; i++) qd[i] += ph.dt * qdd[i];
 
-    // motor rows
+    // motor rows: J = e_i, response column A[:, i], |impulse| <= force * dt
     double rhs[NB], dinv[NB], applied[NB], dv[NB];
     const double lim = mot.max_force * ph.dt;
 #pragma unroll
@@ -494,6 +492,20 @@ TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, co
         rhs[i] = (rhs_v - v) * dinv[i];
         applied[i] = 0; dv[i] = 0;
     }
+    // Projected Gauss-Seidel: sweeps alternate direction (even: back to front); stop when the largest
+    // squared velocity-level change of a sweep is <= solverResidualThreshold (pybullet default 1e-7) [EXT].
+    // The clamp is written with selects: same values as bullet's if/else chain, no divergence.
+    auto row = [&](int r, double& resid) {
+        double delta = rhs[r] - dv[r] * dinv[r];
+        const double sum = applied[r] + delta;
+        const bool lo = sum < -lim, hi = sum > lim;
+        delta = lo ? (-lim - applied[r]) : (hi ? (lim - applied[r]) : delta);
+        applied[r] = lo ? -lim : (hi ? lim : sum);
+#pragma unroll
+        for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
+        const double dvel = delta * A[r][r];
+        resid = fmax(resid, dvel * dvel);
+    };
     int it = 0;
     if (lim != 0.0) {
 #pragma unroll 1
@@ -501,30 +513,12 @@ TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, co
             double resid = 0;
             if (it & 1) {
 #pragma unroll
-                for (int r = 0; r < NB; r++) {
-                    double delta = rhs[r] - dv[r] * dinv[r];
-                    const double sum = applied[r] + delta;
-                    if (sum < -lim) { delta = -lim - applied[r]; applied[r] = -lim; }
-                    else if (sum > lim) { delta = lim - applied[r]; applied[r] = lim; }
-                    else applied[r] = sum;
-#pragma unroll
-                    for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
-                    resid = fmax(resid, delta * delta);
-                }
+                for (int r = 0; r < NB; r++) row(r, resid);
             } else {
 #pragma unroll
-                for (int r = NB - 1; r >= 0; r--) {
-                    double delta = rhs[r] - dv[r] * dinv[r];
-                    const double sum = applied[r] + delta;
-                    if (sum < -lim) { delta = -lim - applied[r]; applied[r] = -lim; }
-                    else if (sum > lim) { delta = lim - applied[r]; applied[r] = lim; }
-                    else applied[r] = sum;
-#pragma unroll
-                    for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
-                    resid = fmax(resid, delta * delta);
-                }
+                for (int r = NB - 1; r >= 0; r--) row(r, resid);
             }
-            if (resid <= 0.0) { it++; break; }
+            if (resid <= ph.solver_residual_threshold) { it++; break; }
         }
     }
 #pragma unroll

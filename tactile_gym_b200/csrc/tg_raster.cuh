@@ -9,15 +9,24 @@
 // z-tested against nodef_dep.
 //
 // Kernel shape (HBM-write bound; algorithmic bytes/env = S*S obs + 192 B camera/stimulus state):
-//   * persistent CTAs, grid = 2 x #SMs; each CTA owns one row band (S*S/bands pixels) of a strided set of
-//     envs, so the band of nodef_dep (f32) and of the pre-baked border image (u8) is fetched ONCE per CTA
-//     by TMA bulk copies (cp.async.bulk + mbarrier) into shared memory and reused for every env;
-//   * per env, ntri threads turn camera + stimulus pose into fp64 homogeneous edge equations
-//     (b = M^-1 d, inside <=> all b_i >= 0, 1/z = sum b_i: exact per-pixel clipping, no vertex projection);
-//   * each thread owns 16-pixel row spans: spans outside every triangle's screen bbox are a straight
-//     shared-memory -> HBM copy of the baked row; others evaluate the edge equations per pixel;
-//   * the post-process is done in float32 with numpy's operation order, output written as one 16-byte
-//     store per span (a warp writes 512 contiguous bytes).
+//   * persistent CTAs, grid = #SMs x CTAs/SM; each CTA owns one row band, whose slice of nodef_dep (f32) and
+//     of the pre-baked border image (u8) is fetched ONCE per CTA by TMA bulk copies (cp.async.bulk +
+//     mbarrier) into shared memory and reused for every env;
+//   * after that there is no block-level synchronisation: each WARP renders whole env images (band slices)
+//     on its own, taking env indices in a strided order;
+//   * per env, lanes 0..ntri-1 turn camera + stimulus pose into homogeneous edge equations in pixel
+//     coordinates (b = M^-1 d: inside <=> all b_i >= 0, 1/z_eye = sum b_i; exact per-pixel clipping, no
+//     vertex projection) - fp64 coefficients plus float copies with an error margin;
+//   * every 8 x 64 pixel tile is classified per triangle from its four corner pixels (edge functions are
+//     affine): outside / inside / partial; one lane per tile, masks travel by warp shuffle;
+//   * a lane owns 16 consecutive pixels of a row.  Tiles no triangle touches are a straight shared-memory ->
+//     HBM copy of the baked row.  Inside triangles cost one DFMA + compare per pixel (nearest = largest
+//     1/z); partial ones are first classified per 16-pixel span from its two end pixels, and only spans an
+//     edge really crosses are tested per pixel, in float, falling back to the fp64 equations inside the
+//     float error margin - so coverage and depth equal the fp64 oracle's;
+//   * the post-process is float32 with numpy's operation order (the division by 0.05f is replaced by a
+//     reciprocal + 2 FMA sequence verified exhaustively to give the same uint8, tools/check_quantize.c);
+//     one 16-byte store per lane, a warp stores 8 rows x 64 B = 16 full 32-byte sectors.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,25 +34,30 @@
 #include "../../include/tactile_gym_b200.h"
 
 #define RASTER_THREADS 512
-#define RASTER_BATCH 4 // envs set up per barrier
+#define RASTER_WARPS (RASTER_THREADS / 32)
+#define TILE_ROWS 8
+#define TILE_COLS 64
+#define RASTER_MAXTRI 32
 
 struct TriCoef {
-    double r0[3], r1[3], r2[3]; // rows of M^-1: b_i = r_i . (dx, dy, 1)
-    int c_lo, c_hi, r_lo, r_hi; // screen bbox (inclusive); r_lo > r_hi -> culled
+    double eA[4], eB[4], eC[4]; // fp64: b_i(c, r) = eA[i] c + eB[i] r + eC[i], i = 0..2; index 3 = w = sum b_i = 1/z_eye
+    float fA[4], fB[4], fC[4];  // float copies
+    float margin;               // |float evaluation error| bound for any of the four functions
+    int valid;
 };
 
 struct RasterArgs {
     int n, S, bands, ntri;
-    double th;          // tan(fov/2)
+    double th;             // tan(fov/2)
     double F, near_, far_; // F = far/(far-near)
-    const float* nodef;      // [S*S], border pixels = -1
-    const uint8_t* base;     // [S*S], border pixels = (u8)nodef_gray, others 0
-    const double* tris;      // [ntri][9] stimulus-frame triangles
-    const double* cam;       // [N][12]
-    const double* stim;      // [N][12]
-    const uint8_t* mask;     // optional [N]
-    uint8_t* obs;            // [N][S*S]
-    uint8_t* term_obs;       // optional [N][S*S]: previous obs of masked envs is copied here first
+    const float* nodef;    // [S*S], border pixels = -1
+    const uint8_t* base;   // [S*S], border pixels = (u8)nodef_gray, others 0
+    const double* tris;    // [ntri][9] stimulus-frame triangles
+    const double* cam;     // [N][12]
+    const double* stim;    // [N][12]
+    const uint8_t* mask;   // optional [N]
+    uint8_t* obs;          // [N][S*S]
+    uint8_t* term_obs;     // optional [N][S*S]: previous obs of masked envs is copied here first
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,9 +72,8 @@ __device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gm
 
 __device__ __forceinline__ void tri_setup(const RasterArgs& a, const double* cam, const double* stim, const double* tl, TriCoef& o)
 {
-    // world vertices -> eye space (x right, y up, z forward)
+    // stimulus frame -> world -> eye space (x right, y up, z forward)
     double ve[3][3];
-    bool front = true;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const double* v = tl + 3 * k;
@@ -70,45 +83,71 @@ __device__ __forceinline__ void tri_setup(const RasterArgs& a, const double* cam
         ve[k][0] = w[0] * cam[9] + w[1] * cam[10] + w[2] * cam[11];
         ve[k][1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
         ve[k][2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
-        if (ve[k][2] <= 1e-6) front = false;
     }
-    // M = [p0 p1 p2] columns; M^-1 rows = (p1 x p2, p2 x p0, p0 x p1) / det
+    // M = [p0 p1 p2] (columns); rows of M^-1 = (p1 x p2, p2 x p0, p0 x p1) / det
     double c0[3], c1[3], c2[3];
     c0[0] = ve[1][1] * ve[2][2] - ve[1][2] * ve[2][1]; c0[1] = ve[1][2] * ve[2][0] - ve[1][0] * ve[2][2]; c0[2] = ve[1][0] * ve[2][1] - ve[1][1] * ve[2][0];
     c1[0] = ve[2][1] * ve[0][2] - ve[2][2] * ve[0][1]; c1[1] = ve[2][2] * ve[0][0] - ve[2][0] * ve[0][2]; c1[2] = ve[2][0] * ve[0][1] - ve[2][1] * ve[0][0];
     c2[0] = ve[0][1] * ve[1][2] - ve[0][2] * ve[1][1]; c2[1] = ve[0][2] * ve[1][0] - ve[0][0] * ve[1][2]; c2[2] = ve[0][0] * ve[1][1] - ve[0][1] * ve[1][0];
     const double det = ve[0][0] * c0[0] + ve[0][1] * c0[1] + ve[0][2] * c0[2];
-    const int S = a.S;
-    o.c_lo = 0; o.c_hi = S - 1; o.r_lo = 0; o.r_hi = S - 1;
-    if (fabs(det) < 1e-300) { o.r_lo = 1; o.r_hi = 0; return; }
-    const double inv = 1.0 / det;
+    o.valid = 0;
+    if (fabs(det) < 1e-300) return;
+    o.valid = 1;
+    const double inv = 1.0 / det, S = a.S;
+    // b_i = r_i.x dx + r_i.y dy + r_i.z with dx = th ((2c+1)/S - 1), dy = th (1 - (2r+1)/S)
+    const double kx = a.th * 2.0 / S, x0 = a.th * (1.0 / S - 1.0), y0 = a.th * (1.0 - 1.0 / S);
+    const double* rows[3] = {c0, c1, c2};
+    o.eA[3] = o.eB[3] = o.eC[3] = 0.0;
+    float mg = 0.f;
 #pragma unroll
-    for (int c = 0; c < 3; c++) { o.r0[c] = c0[c] * inv; o.r1[c] = c1[c] * inv; o.r2[c] = c2[c] * inv; }
-    if (front) {
-        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const double x = ve[k][0] / (ve[k][2] * a.th), y = ve[k][1] / (ve[k][2] * a.th);
-            xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
-        }
-        const double cl = floor((xmin + 1) * 0.5 * S - 0.5) - 1, ch = ceil((xmax + 1) * 0.5 * S - 0.5) + 1;
-        const double rl = floor((1 - ymax) * 0.5 * S - 0.5) - 1, rh = ceil((1 - ymin) * 0.5 * S - 0.5) + 1;
-        o.c_lo = (int)fmax(cl, 0.0); o.c_hi = (int)fmin(ch, (double)(S - 1));
-        o.r_lo = (int)fmax(rl, 0.0); o.r_hi = (int)fmin(rh, (double)(S - 1));
-        if (ch < 0 || rh < 0 || cl > S - 1 || rl > S - 1) { o.r_lo = 1; o.r_hi = 0; }
+    for (int i = 0; i < 3; i++) {
+        const double rx = rows[i][0] * inv, ry = rows[i][1] * inv, rz = rows[i][2] * inv;
+        o.eA[i] = rx * kx; o.eB[i] = -ry * kx; o.eC[i] = rx * x0 + ry * y0 + rz;
+        o.eA[3] += o.eA[i]; o.eB[3] += o.eB[i]; o.eC[3] += o.eC[i];
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        o.fA[i] = (float)o.eA[i]; o.fB[i] = (float)o.eB[i]; o.fC[i] = (float)o.eC[i];
+        mg = fmaxf(mg, (float)((fabs(o.eA[i]) + fabs(o.eB[i])) * S + fabs(o.eC[i])));
+    }
+    o.margin = mg * 2e-6f;
 }
 
-// t_s_camera's float32 arithmetic (tactile_sensor.py:268-284)
+// exact (fp64) inside test with the oracle's tolerance: lambda_i >= -1e-12, w > 0
+__device__ __noinline__ bool inside_exact(const TriCoef& t, int c, int r)
+{
+    const double b0 = t.eA[0] * c + t.eB[0] * r + t.eC[0];
+    const double b1 = t.eA[1] * c + t.eB[1] * r + t.eC[1];
+    const double b2 = t.eA[2] * c + t.eB[2] * r + t.eC[2];
+    const double w = b0 + b1 + b2;
+    const double tol = -1e-12 * w;
+    return w > 0.0 && b0 >= tol && b1 >= tol && b2 >= tol;
+}
+
+// rare path: the nearest covering triangle is in front of the near plane -> GL clips it and the next one shows
+__device__ __noinline__ double slow_pixel(const TriCoef* tc, int ntri, int c, int r, double w_near, double w_far)
+{
+    double best = 0.0;
+    for (int t = 0; t < ntri; t++) {
+        if (!tc[t].valid || !inside_exact(tc[t], c, r)) continue;
+        const double w = tc[t].eA[3] * c + tc[t].eB[3] * r + tc[t].eC[3];
+        if (w <= w_near && w >= w_far && w > best) best = w;
+    }
+    return best;
+}
+
+// t_s_camera's float32 arithmetic (tactile_sensor.py:268-284).  uint8(((clip(pen, 0, 0.05) / 0.05) * 255)):
+// q = pen / 0.05f is computed as q0 = pen * 20, q = fma(fma(-0.05f, q0, pen), 20, q0); over all 1.03e9 floats
+// in [0, 0.05f] the resulting uint8 equals the IEEE-division one (tools/check_quantize.c, tests/test_host.py).
 __device__ __forceinline__ uint32_t quantize(float cur, float nd)
 {
     float diff = cur - nd;
-    const float eps = 1e-4f, maxpen = 0.05f;
+    const float eps = 1e-4f, maxpen = 0.05f, rcp = 20.0f;
     if (diff >= -eps && diff <= eps) diff = 0.0f;
-    float pen = fabsf(diff);
-    pen = fminf(fmaxf(pen, 0.0f), maxpen);
-    const float val = __fmul_rn(__fdiv_rn(pen, maxpen), 255.0f);
-    return (uint32_t)__float2uint_rz(val);
+    const float pen = fminf(fabsf(diff), maxpen);
+    const float q0 = __fmul_rn(pen, rcp);
+    const float q = __fmaf_rn(__fmaf_rn(-maxpen, q0, pen), rcp, q0);
+    return (uint32_t)__float2uint_rz(__fmul_rn(q, 255.0f));
 }
 
 __global__ void __launch_bounds__(RASTER_THREADS)
@@ -118,9 +157,10 @@ raster_kernel(const RasterArgs a)
     const int S = a.S, band_rows = S / a.bands, band_px = band_rows * S;
     float* s_nodef = reinterpret_cast<float*>(smem_raw);
     uint8_t* s_base = smem_raw + (size_t)band_px * 4;
-    TriCoef* s_tri = reinterpret_cast<TriCoef*>(smem_raw + (size_t)band_px * 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TriCoef* tc = reinterpret_cast<TriCoef*>(smem_raw + (size_t)band_px * 5) + warp * a.ntri; // this warp's equations
+    const int tiles_x = S / TILE_COLS, tiles_y = band_rows / TILE_ROWS, n_tiles = tiles_x * tiles_y; // <= 32
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_env[RASTER_BATCH];
 
     const int band = blockIdx.x % a.bands;
     const int lane_cta = blockIdx.x / a.bands, n_cta = gridDim.x / a.bands;
@@ -146,84 +186,114 @@ raster_kernel(const RasterArgs a)
         }
     }
 
-    const int spans_per_row = S / 16, n_spans = band_rows * spans_per_row;
-    const double inv_S = 1.0 / S;
+    const double w_near = 1.0 / a.near_, w_far = 1.0 / a.far_;
+    const double Fn = a.F * a.near_;
 
-    for (int e0 = lane_cta * RASTER_BATCH; e0 < a.n; e0 += n_cta * RASTER_BATCH) {
-        __syncthreads(); // previous batch done with s_tri / s_env
-        if (threadIdx.x < RASTER_BATCH) {
-            const int e = e0 + threadIdx.x;
-            s_env[threadIdx.x] = (e < a.n && (!a.mask || a.mask[e])) ? e : -1;
-        }
-        if (threadIdx.x < RASTER_BATCH * a.ntri) {
-            const int bi = threadIdx.x / a.ntri, t = threadIdx.x % a.ntri, e = e0 + bi;
-            if (e < a.n && (!a.mask || a.mask[e]))
-                tri_setup(a, a.cam + (size_t)e * 12, a.stim + (size_t)e * 12, a.tris + 9 * t, s_tri[bi * a.ntri + t]);
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int bi = 0; bi < RASTER_BATCH; bi++) {
-            const int e = s_env[bi];
-            if (e < 0) continue;
-            const TriCoef* tc = s_tri + bi * a.ntri;
-            uint8_t* out = a.obs + (size_t)e * S * S + (size_t)row0 * S;
-            uint8_t* tout = a.term_obs ? a.term_obs + (size_t)e * S * S + (size_t)row0 * S : nullptr;
-            for (int sp = threadIdx.x; sp < n_spans; sp += RASTER_THREADS) {
-                const int lr = sp / spans_per_row, c0 = (sp % spans_per_row) * 16, r = row0 + lr;
-                const int off = lr * S + c0;
-                if (tout) *reinterpret_cast<uint4*>(tout + off) = *reinterpret_cast<const uint4*>(out + off);
-                uint4 res = *reinterpret_cast<const uint4*>(s_base + off);
-                // which triangles can touch this span?
-                uint32_t hit = 0;
-                for (int t = 0; t < a.ntri; t++)
-                    if (r >= tc[t].r_lo && r <= tc[t].r_hi && c0 + 15 >= tc[t].c_lo && c0 <= tc[t].c_hi) hit |= 1u << t;
-                if (hit) {
-                    float nd[16], cur[16];
-                    {
-                        const float4* p = reinterpret_cast<const float4*>(s_nodef + off);
+    // one env image (band slice) per warp iteration
+    for (int e = lane_cta * RASTER_WARPS + warp; e < a.n; e += n_cta * RASTER_WARPS) {
+        if (a.mask && !a.mask[e]) continue;
+        __syncwarp();
+        if (lane < a.ntri) tri_setup(a, a.cam + (size_t)e * 12, a.stim + (size_t)e * 12, a.tris + 9 * lane, tc[lane]);
+        __syncwarp();
+        // tile classification: lane = tile
+        uint32_t my_in = 0, my_part = 0;
+        if (lane < n_tiles) {
+            const float cl = (float)((lane % tiles_x) * TILE_COLS), ch = cl + (TILE_COLS - 1);
+            const float rl = (float)(row0 + (lane / tiles_x) * TILE_ROWS), rh = rl + (TILE_ROWS - 1);
+            for (int t = 0; t < a.ntri; t++) {
+                const TriCoef& c = tc[t];
+                if (!c.valid) continue;
+                bool all_in = true, out = false;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const float4 v = p[k];
-                            nd[4 * k] = v.x; nd[4 * k + 1] = v.y; nd[4 * k + 2] = v.z; nd[4 * k + 3] = v.w;
-                        }
+                for (int k = 0; k < 4; k++) {
+                    const float kl = fmaf(c.fB[k], rl, c.fC[k]), kh = fmaf(c.fB[k], rh, c.fC[k]);
+                    const float v00 = fmaf(c.fA[k], cl, kl), v01 = fmaf(c.fA[k], ch, kl), v10 = fmaf(c.fA[k], cl, kh), v11 = fmaf(c.fA[k], ch, kh);
+                    const float lo = fminf(fminf(v00, v01), fminf(v10, v11)), hi = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+                    all_in = all_in && (lo > c.margin);
+                    out = out || (hi < -c.margin);
+                }
+                if (!out) { if (all_in) my_in |= 1u << t; else my_part |= 1u << t; }
+            }
+        }
+        uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
+        uint8_t* term_e = a.term_obs ? a.term_obs + (size_t)e * S * S + (size_t)row0 * S : nullptr;
+        for (int tile = 0; tile < n_tiles; tile++) {
+            uint32_t in_m = __shfl_sync(0xffffffffu, my_in, tile), part_m = __shfl_sync(0xffffffffu, my_part, tile);
+            const int lr = (tile / tiles_x) * TILE_ROWS + (lane >> 2), c0 = (tile % tiles_x) * TILE_COLS + (lane & 3) * 16;
+            const int r = row0 + lr, off = lr * S + c0;
+            if (term_e) *reinterpret_cast<uint4*>(term_e + off) = *reinterpret_cast<const uint4*>(obs_e + off);
+            uint4 res = *reinterpret_cast<const uint4*>(s_base + off);
+            if (in_m | part_m) {
+                double best[16]; // largest 1/z_eye over covering triangles, 0 = none
+#pragma unroll
+                for (int k = 0; k < 16; k++) best[k] = 0.0;
+                while (in_m) {
+                    const int t = __ffs(in_m) - 1;
+                    in_m &= in_m - 1;
+                    const double wA = tc[t].eA[3];
+                    const double w0 = wA * c0 + (tc[t].eB[3] * r + tc[t].eC[3]);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const double w = wA * k + w0;
+                        if (w > best[k]) best[k] = w;
                     }
-#pragma unroll
-                    for (int k = 0; k < 16; k++) cur[k] = nd[k];
-                    const double dy = (1.0 - (r + 0.5) * inv_S * 2.0) * a.th;
-                    while (hit) {
-                        const int t = __ffs(hit) - 1;
-                        hit &= hit - 1;
-                        const TriCoef c = tc[t];
-                        const double k0 = c.r0[1] * dy + c.r0[2], k1 = c.r1[1] * dy + c.r1[2], k2 = c.r2[1] * dy + c.r2[2];
+                }
+                while (part_m) {
+                    const int t = __ffs(part_m) - 1;
+                    part_m &= part_m - 1;
+                    const TriCoef& c = tc[t];
+                    const float fr = (float)r, fc0 = (float)c0, mg = c.margin;
+                    const float k0 = fmaf(c.fB[0], fr, c.fC[0]), k1 = fmaf(c.fB[1], fr, c.fC[1]);
+                    const float k2 = fmaf(c.fB[2], fr, c.fC[2]), k3 = fmaf(c.fB[3], fr, c.fC[3]);
+                    // span classification from its two end pixels
+                    const float a0 = fmaf(c.fA[0], fc0, k0), a1 = fmaf(c.fA[1], fc0, k1), a2 = fmaf(c.fA[2], fc0, k2), a3 = fmaf(c.fA[3], fc0, k3);
+                    const float z0 = fmaf(c.fA[0], 15.0f, a0), z1 = fmaf(c.fA[1], 15.0f, a1), z2 = fmaf(c.fA[2], 15.0f, a2), z3 = fmaf(c.fA[3], 15.0f, a3);
+                    const float lo = fminf(fminf(fminf(a0, z0), fminf(a1, z1)), fminf(fminf(a2, z2), fminf(a3, z3)));
+                    const float hx = fminf(fminf(fmaxf(a0, z0), fmaxf(a1, z1)), fminf(fmaxf(a2, z2), fmaxf(a3, z3)));
+                    if (hx < -mg) continue; // some function is negative over the whole span
+                    const double wA = c.eA[3];
+                    const double w0 = wA * c0 + (c.eB[3] * r + c.eC[3]);
+                    if (lo > mg) {
 #pragma unroll
                         for (int k = 0; k < 16; k++) {
-                            const double dx = ((c0 + k + 0.5) * inv_S * 2.0 - 1.0) * a.th;
-                            const double b0 = c.r0[0] * dx + k0, b1 = c.r1[0] * dx + k1, b2 = c.r2[0] * dx + k2;
-                            const double w = b0 + b1 + b2;
-                            const double tol = -1e-12 * w;
-                            if (w > 0.0 && b0 >= tol && b1 >= tol && b2 >= tol && w * a.near_ <= 1.0 && w * a.far_ >= 1.0) {
-                                const float d = (float)(a.F * (1.0 - a.near_ * w));
-                                cur[k] = fminf(cur[k], d);
-                            }
+                            const double w = wA * k + w0;
+                            if (w > best[k]) best[k] = w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const float fk = (float)k;
+                            const float m = fminf(fminf(fmaf(c.fA[0], fk, a0), fmaf(c.fA[1], fk, a1)), fminf(fmaf(c.fA[2], fk, a2), fmaf(c.fA[3], fk, a3)));
+                            bool in = m > mg;
+                            if (!in && m >= -mg) in = inside_exact(c, c0 + k, r);
+                            const double w = wA * k + w0;
+                            if (in && w > best[k]) best[k] = w;
                         }
                     }
-                    uint32_t wds[4];
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++) {
-                        uint32_t wd = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const float n0 = nd[4 * k4 + k];
-                            const uint32_t basev = ((k4 == 0 ? res.x : k4 == 1 ? res.y : k4 == 2 ? res.z : res.w) >> (8 * k)) & 0xffu;
-                            const uint32_t qv = n0 < 0.0f ? basev : quantize(cur[4 * k4 + k], n0);
-                            wd |= qv << (8 * k);
-                        }
-                        wds[k4] = wd;
-                    }
-                    res = make_uint4(wds[0], wds[1], wds[2], wds[3]);
                 }
-                *reinterpret_cast<uint4*>(out + off) = res;
+                float nd[16];
+                {
+                    const float4* p = reinterpret_cast<const float4*>(s_nodef + off);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float4 v = p[k];
+                        nd[4 * k] = v.x; nd[4 * k + 1] = v.y; nd[4 * k + 2] = v.z; nd[4 * k + 3] = v.w;
+                    }
+                }
+                uint32_t wds[4] = {res.x, res.y, res.z, res.w};
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    // closer than the near plane (never happens for a stimulus under the skin) is clipped like GL does
+                    if (best[k] > w_near) best[k] = slow_pixel(tc, a.ntri, c0 + k, r, w_near, w_far);
+                    if (best[k] >= w_far && nd[k] >= 0.0f) {
+                        const float d = (float)(a.F - Fn * best[k]);
+                        const uint32_t qv = quantize(fminf(nd[k], d), nd[k]);
+                        wds[k >> 2] |= qv << (8 * (k & 3)); // non-border pixels have base == 0
+                    }
+                }
+                res = make_uint4(wds[0], wds[1], wds[2], wds[3]);
             }
+            *reinterpret_cast<uint4*>(obs_e + off) = res;
         }
     }
 }

@@ -89,10 +89,14 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     w->sm_count = prop.multiProcessorCount;
     const int n = w->n, nb = w->nb;
     int lanes = cfg->lanes_per_warp;
-    if (lanes != 8 && lanes != 16 && lanes != 32) {
-        // fill the machine: one warp per SM sub-partition before packing lanes
-        const long slots = (long)w->sm_count * 4;
-        lanes = n <= slots * 8 ? 8 : (n <= slots * 16 ? 16 : 32);
+    if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) {
+        // The per-env work is one long dependent fp64 chain and a warp costs the same issue slots whether 1 or
+        // 32 lanes are active, so the kernel time is the chain latency as long as every SM sub-partition has
+        // about one warp: give each of the 4 x #SM schedulers a warp before packing more lanes into a warp
+        // (measured on B200, N = 4096: 1 lane/warp 1.28 ms, 2: 0.66, 4: 0.34, 8: 0.22, 32: 0.22).
+        const long target_warps = (long)w->sm_count * 4;
+        lanes = 32;
+        while (lanes > 1 && (long)(n + lanes / 2 - 1) / (lanes / 2) <= target_warps) lanes >>= 1;
     }
     EnvBuffers& b = w->eb;
     b.n = n; b.lanes = lanes;
@@ -132,14 +136,14 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         r.F = cfg->sensor.far_ / (cfg->sensor.far_ - cfg->sensor.near_);
         r.nodef = dn; r.base = db; r.tris = dt; r.cam = b.cam; r.stim = b.stim; r.mask = nullptr; r.obs = nullptr; r.term_obs = nullptr;
         const size_t band_px = px / r.bands;
-        w->raster_smem = band_px * 5 + sizeof(TriCoef) * RASTER_BATCH * r.ntri;
+        w->raster_smem = band_px * 5 + sizeof(TriCoef) * RASTER_WARPS * r.ntri;
         CK(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->raster_smem));
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel, RASTER_THREADS, w->raster_smem));
         if (per_sm < 1) { tg_destroy(w); return fail(TG_ECUDA, "raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
         int grid = w->sm_count * per_sm;
         grid -= grid % r.bands;
-        const int need = ((n + RASTER_BATCH - 1) / RASTER_BATCH) * r.bands;
+        const int need = ((n + RASTER_WARPS - 1) / RASTER_WARPS) * r.bands;
         if (grid > need) grid = need;
         w->raster_grid = grid;
     }

@@ -118,6 +118,7 @@ def reduce_model(mj, sensor, cam_pos, cam_rpy):
     nsub = 0
     for b in range(arm.nb):
         parts = []
+        arm.sub_start[b] = nsub
         for i, l in enumerate(links):
             if body_of_link[i] != b or l["mass"] <= 0:
                 continue
@@ -150,6 +151,8 @@ def reduce_model(mj, sensor, cam_pos, cam_rpy):
         for k, (r, c) in enumerate([(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]):
             arm.inertia[b][k] = I[r, c]
     arm.nsub = nsub
+    for b in range(arm.nb, L.TG_MAXB + 1):
+        arm.sub_start[b] = nsub
 
     def inertial_frame(link_name):
         i = names.index(link_name)
@@ -184,6 +187,7 @@ def default_physics(substeps=24, gravity=(0.0, 0.0, -9.81)):
     p.substeps = substeps
     p.lin_damping, p.ang_damping, p.joint_damping = 0.04, 0.04, 0.01
     p.max_force, p.pos_gain, p.vel_gain = 1000.0, 1.0, 1.0
+    p.solver_residual_threshold = 1e-7
     p.blocking_force = 100000.0
     p.gravity_comp = 1
     return p

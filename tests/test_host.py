@@ -107,3 +107,13 @@ def test_no_gpu_fails_loudly(edge_modes):
 
     with pytest.raises(TgError):
         tg.make("edge_follow-v0", env_modes=edge_modes, image_size=[64, 64])
+
+
+def test_quantize_shortcut_is_exact(tmp_path):
+    """tg_raster.cuh replaces pen / 0.05f by a reciprocal + 2 FMA; the uint8 result must never differ.
+    (every 7th float of [0, 0.05f] here - 147 M values; run tools/check_quantize.c without arguments for all 1.03e9)"""
+    exe = str(tmp_path / "check_quantize")
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tools", "check_quantize.c"), "-lm"])
+    out = subprocess.run([exe, "7"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert " 0 uint8 mismatches" in out.stdout

@@ -1,0 +1,23 @@
+"""Short workload for ncu: BASELINE config 2 (edge_follow-v0, UR5+TacTip 128x128, 4096 envs), a few steps."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import tactile_gym_b200 as tg
+
+modes = {"movement_mode": "xy", "control_mode": "TCP_velocity_control", "noise_mode": "rand_height",
+         "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "tactip"}
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+env = tg.make_vec("edge_follow-v0", n, seed=1, env_kwargs={"env_modes": modes, "image_size": [S, S], "max_steps": 200})
+env.reset()
+g = torch.Generator(device="cuda"); g.manual_seed(0)
+for k in range(steps):
+    a = (torch.rand((n, 2), device="cuda", generator=g) - 0.5) * 0.5
+    env.step_tensor(a)
+torch.cuda.synchronize()
+if len(sys.argv) > 4 and sys.argv[4] == "raster":
+    for k in range(3):
+        env.world.raster_only()
+    torch.cuda.synchronize()
+env.close()
