@@ -43,7 +43,9 @@ struct TriCoef {
     double eA[4], eB[4], eC[4]; // fp64: b_i(c, r) = eA[i] c + eB[i] r + eC[i], i = 0..2; index 3 = w = sum b_i = 1/z_eye
     float fA[4], fB[4], fC[4];  // float copies
     float margin;               // |float evaluation error| bound for any of the four functions
-    int valid;
+    int valid;                  // 0: degenerate (plane through the eye), 1: usable
+    float c_lo, c_hi, r_lo, r_hi; // conservative screen bbox in pixel units (whole image if a vertex is behind the eye)
+    int clipped, pad;           // 1: some vertex is nearer than the near plane -> per-pixel range checks needed
 };
 
 struct RasterArgs {
@@ -94,6 +96,22 @@ __device__ __forceinline__ void tri_setup(const RasterArgs& a, const double* cam
     if (fabs(det) < 1e-300) return;
     o.valid = 1;
     const double inv = 1.0 / det, S = a.S;
+    {
+        const bool front = ve[0][2] > 1e-6 && ve[1][2] > 1e-6 && ve[2][2] > 1e-6;
+        o.clipped = !(ve[0][2] >= a.near_ && ve[1][2] >= a.near_ && ve[2][2] >= a.near_) || ve[0][2] > a.far_ || ve[1][2] > a.far_ || ve[2][2] > a.far_;
+        o.c_lo = 0.f; o.c_hi = (float)(S - 1); o.r_lo = 0.f; o.r_hi = (float)(S - 1);
+        if (front) {
+            double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double x = ve[k][0] / (ve[k][2] * a.th), y = ve[k][1] / (ve[k][2] * a.th);
+                xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+            }
+            // pixel c has x_ndc = (2c+1)/S - 1; pad by one pixel
+            o.c_lo = (float)((xmin + 1) * 0.5 * S - 0.5 - 1.0); o.c_hi = (float)((xmax + 1) * 0.5 * S - 0.5 + 1.0);
+            o.r_lo = (float)((1 - ymax) * 0.5 * S - 0.5 - 1.0); o.r_hi = (float)((1 - ymin) * 0.5 * S - 0.5 + 1.0);
+        }
+    }
     // b_i = r_i.x dx + r_i.y dy + r_i.z with dx = th ((2c+1)/S - 1), dy = th (1 - (2r+1)/S)
     const double kx = a.th * 2.0 / S, x0 = a.th * (1.0 / S - 1.0), y0 = a.th * (1.0 - 1.0 / S);
     const double* rows[3] = {c0, c1, c2};
@@ -195,15 +213,22 @@ raster_kernel(const RasterArgs a)
         __syncwarp();
         if (lane < a.ntri) tri_setup(a, a.cam + (size_t)e * 12, a.stim + (size_t)e * 12, a.tris + 9 * lane, tc[lane]);
         __syncwarp();
-        // tile classification: lane = tile
+        // tile classification: lane = tile.  A triangle is dropped for a tile when its screen bbox misses it, when
+        // one edge function is negative at all four corner pixels, or when a triangle that covers the whole
+        // tile is nearer at all four corners (both 1/z are affine, so nearer everywhere: exact occlusion cull).
         uint32_t my_in = 0, my_part = 0;
+        int any_clipped = 0;
+        for (int t = 0; t < a.ntri; t++) any_clipped |= tc[t].valid & tc[t].clipped;
         if (lane < n_tiles) {
             const float cl = (float)((lane % tiles_x) * TILE_COLS), ch = cl + (TILE_COLS - 1);
             const float rl = (float)(row0 + (lane / tiles_x) * TILE_ROWS), rh = rl + (TILE_ROWS - 1);
+            float dom[4] = {-1e30f, -1e30f, -1e30f, -1e30f}; // certified lower bound of 1/z of the nearest covering triangle
+            int dom_t = -1;
             for (int t = 0; t < a.ntri; t++) {
                 const TriCoef& c = tc[t];
-                if (!c.valid) continue;
+                if (!c.valid || c.c_hi < cl || c.c_lo > ch || c.r_hi < rl || c.r_lo > rh) continue;
                 bool all_in = true, out = false;
+                float wv[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const float kl = fmaf(c.fB[k], rl, c.fC[k]), kh = fmaf(c.fB[k], rh, c.fC[k]);
@@ -211,8 +236,33 @@ raster_kernel(const RasterArgs a)
                     const float lo = fminf(fminf(v00, v01), fminf(v10, v11)), hi = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
                     all_in = all_in && (lo > c.margin);
                     out = out || (hi < -c.margin);
+                    if (k == 3) { wv[0] = v00; wv[1] = v01; wv[2] = v10; wv[3] = v11; }
                 }
-                if (!out) { if (all_in) my_in |= 1u << t; else my_part |= 1u << t; }
+                if (out) continue;
+                if (all_in) {
+                    my_in |= 1u << t;
+                    if (!any_clipped && wv[0] - c.margin > dom[0]) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) dom[k] = wv[k] - c.margin;
+                        dom_t = t;
+                    }
+                } else my_part |= 1u << t;
+            }
+            if (my_in && !any_clipped) {
+                // second pass: drop everything the dominating in-triangle hides
+                uint32_t keep_in = 0, keep_part = 0, cand = my_in | my_part;
+                while (cand) {
+                    const int t = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const TriCoef& c = tc[t];
+                    const float kl = fmaf(c.fB[3], rl, c.fC[3]), kh = fmaf(c.fB[3], rh, c.fC[3]);
+                    const float w0 = fmaf(c.fA[3], cl, kl) + c.margin, w1 = fmaf(c.fA[3], ch, kl) + c.margin;
+                    const float w2 = fmaf(c.fA[3], cl, kh) + c.margin, w3 = fmaf(c.fA[3], ch, kh) + c.margin;
+                    const bool hidden = w0 < dom[0] && w1 < dom[1] && w2 < dom[2] && w3 < dom[3];
+                    const bool is_dom = t == dom_t;
+                    if (!hidden || is_dom) { if ((my_in >> t) & 1u) keep_in |= 1u << t; else keep_part |= 1u << t; }
+                }
+                my_in = keep_in; my_part = keep_part;
             }
         }
         uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
@@ -225,8 +275,18 @@ raster_kernel(const RasterArgs a)
             uint4 res = *reinterpret_cast<const uint4*>(s_base + off);
             if (in_m | part_m) {
                 double best[16]; // largest 1/z_eye over covering triangles, 0 = none
+                if (part_m == 0 && (in_m & (in_m - 1)) == 0) {
+                    // one triangle covers the whole tile and nothing else survives: one DFMA per pixel
+                    const int t = __ffs(in_m) - 1;
+                    const double wA = tc[t].eA[3];
+                    const double w0 = wA * c0 + (tc[t].eB[3] * r + tc[t].eC[3]);
 #pragma unroll
-                for (int k = 0; k < 16; k++) best[k] = 0.0;
+                    for (int k = 0; k < 16; k++) best[k] = wA * k + w0;
+                    in_m = 0;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) best[k] = 0.0;
+                }
                 while (in_m) {
                     const int t = __ffs(in_m) - 1;
                     in_m &= in_m - 1;
@@ -284,8 +344,11 @@ raster_kernel(const RasterArgs a)
 #pragma unroll
                 for (int k = 0; k < 16; k++) {
                     // closer than the near plane (never happens for a stimulus under the skin) is clipped like GL does
-                    if (best[k] > w_near) best[k] = slow_pixel(tc, a.ntri, c0 + k, r, w_near, w_far);
-                    if (best[k] >= w_far && nd[k] >= 0.0f) {
+                    if (any_clipped) {
+                        if (best[k] > w_near) best[k] = slow_pixel(tc, a.ntri, c0 + k, r, w_near, w_far);
+                        if (best[k] < w_far) best[k] = 0.0;
+                    }
+                    if (best[k] > 0.0 && nd[k] >= 0.0f) {
                         const float d = (float)(a.F - Fn * best[k]);
                         const uint32_t qv = quantize(fminf(nd[k], d), nd[k]);
                         wds[k >> 2] |= qv << (8 * (k & 3)); // non-border pixels have base == 0

@@ -1,0 +1,62 @@
+"""CPU, world_size 2, gloo: the N > 1 plumbing (index sharding, seeds, the optional all-gather, max-over-ranks)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tactile_gym_b200 import distributed as D
+
+    n_local, S = 3, 4
+    lo, hi = D.shard_range(rank, world, n_local)
+    seeds = D.shard_seeds(100, rank, n_local)
+    obs = torch.full((n_local, S, S, 1), rank, dtype=torch.uint8) + torch.arange(n_local, dtype=torch.uint8).view(-1, 1, 1, 1) * 10
+    rew = torch.arange(lo, hi, dtype=torch.float32)
+    done = torch.tensor([(i % 2) for i in range(lo, hi)], dtype=torch.uint8)
+    g_obs, g_rew, g_done = D.all_gather_batch(obs, rew, done)
+    mx = D.max_over_ranks([1.0 + rank, 5.0 - rank], "cpu")
+    q.put((rank, lo, hi, seeds, g_obs.shape, g_rew.tolist(), g_done.tolist(), g_obs[:, 0, 0, 0].tolist(), mx))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_gather_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, s0, shp0, rew0, done0, o0, mx0), (r1, lo1, hi1, s1, shp1, rew1, done1, o1, mx1) = res
+    assert (lo0, hi0, lo1, hi1) == (0, 3, 3, 6)
+    assert s0 + s1 == [100, 101, 102, 103, 104, 105]          # seeds follow the global env index
+    assert tuple(shp0) == (6, 4, 4, 1)
+    assert rew0 == rew1 == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]      # rank-major == global index order
+    assert done0 == done1 == [0, 1, 0, 1, 0, 1]
+    assert o0 == o1 == [0, 10, 20, 1, 11, 21]
+    assert mx0 == mx1 == [2.0, 5.0]
+
+
+def test_single_process_is_a_no_op():
+    from tactile_gym_b200 import distributed as D
+
+    o, r, d = torch.zeros(2, 4, 4, 1), torch.zeros(2), torch.zeros(2)
+    assert D.all_gather_batch(o, r, d)[0] is o
+    assert D.max_over_ranks([3.0], "cpu") == [3.0]
