@@ -142,6 +142,11 @@ int tg_destroy(TgWorld* w);
 /* Upload random draws for future resets: h_draws[n_envs][rounds][n_draws] (double).  The r-th reset of
  * env i after this call consumes h_draws[i][r].  Synchronous host->device copy. */
 int tg_set_draws(TgWorld* w, const double* h_draws, int rounds);
+/* Same upload, but the sequence CONTINUES: pre-computed standby episodes (which already consumed their draws) stay
+ * valid.  h_draws[i][0] must be env i's first unconsumed draw (see tg_get_reset_counts). */
+int tg_refill_draws(TgWorld* w, const double* h_draws, int rounds);
+/* 1 if a finished env ever found no standby episode (cannot happen when episodes last >= 2 steps); synchronises */
+int tg_pipeline_error(TgWorld* w, void* stream);
 /* resets consumed per env since the last tg_set_draws (device->host, synchronises the stream) */
 int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream);
 

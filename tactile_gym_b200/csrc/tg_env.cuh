@@ -1,16 +1,26 @@
-// tg_env.cuh - env-level kernels (one thread per env): step, reset.
+// tg_env.cuh - env-level kernels (one thread per env): step (+ standby resets), reset.
 //
 //   step_kernel   <- BaseTactileEnv.step (rl_envs/base_tactile_env.py:166-185) up to, not including, the
 //                    tactile render: action encode/scale, tcp_velocity_control, 24 x step_sim, step data.
-//   reset_kernel  <- EdgeFollowEnv.reset (edge_follow_env.py:311-336) / Robot.reset (robot.py:114-125):
+//   reset_env     <- EdgeFollowEnv.reset (edge_follow_env.py:311-336) / Robot.reset (robot.py:114-125):
 //                    rest pose, IK, blocking move.
 // Both leave behind, per env, the camera frame and stimulus pose the raster kernel consumes.
+//
+// Reset pipeline.  A reset depends only on the env's next random draws, never on the episode that just ended
+// (arm.reset() rewinds to the rest pose, robot.py:114-125).  So every env keeps a STANDBY start-of-episode
+// state computed ahead of time.  When an env finishes, step_kernel swaps the standby in (a copy) instead of
+// running IK + blocking move on the critical path, and the extra blocks of the NEXT step launch recompute
+// the standby while the other envs step.  Draws are consumed in episode order, so the sequence of episodes is
+// exactly the sequential one.  Needs episodes of >= 2 steps (tg_create checks max_steps; a miss raises a
+// sticky error flag instead of guessing).
 #pragma once
 #include "tg_dyn.cuh"
 
 struct EnvBuffers {
     int n;
-    int lanes;            // active lanes per warp
+    int lanes;            // active lanes per warp in the step role
+    int step_blocks;      // blocks [0, step_blocks) step envs, the rest recompute standbys
+    int pipeline;         // 1: standby reset pipeline on
     double* q;            // [NB][N]
     double* qd;           // [NB][N]
     double* embed;        // [N]
@@ -24,6 +34,20 @@ struct EnvBuffers {
     double* stim;         // [N][12] R(9) t(3) of the stimulus frame
     double* tcp;          // [N][7] tcp world pos + quat (state export)
     const double* rest_q; // [NB]
+    // standby start-of-episode state
+    double *sb_q, *sb_qd, *sb_embed, *sb_ang, *sb_cam, *sb_stim, *sb_tcp;
+    int* sb_substeps;
+    unsigned char* sb_ready; // [N]
+    // camera / stimulus of the state an env terminated in (for the terminal observation)
+    double *term_cam, *term_stim;
+    int* error_flag;         // sticky: 1 = a finished env found no standby
+};
+
+// one env's start-of-episode state
+template <int NB>
+struct EpisodeStart {
+    double q[NB], qd[NB], embed, edge_ang, cam[12], stim[12], tcp[7];
+    int substeps;
 };
 
 TGD int env_index(const EnvBuffers& b)
@@ -71,12 +95,227 @@ TGD void edge_step_data(const TgTask& task, const double* tcp_pos, double edge_a
     *done = (goal_dist < task.termination_dist || steps >= task.max_steps) ? 1 : 0;
 }
 
+// pb.calculateInverseKinematics as restated in oracle/tg_oracle.c:or_inverse_kinematics (base_robot_arm.py:201-209)
+template <class T>
+TGD void inverse_kinematics(const TgArm& arm, double* q, const double* tpos, const double* tquat)
+{
+    constexpr int NB = T::NB;
+    static_assert(NB == 6 || NB == 8, "topology");
+#pragma unroll 1
+    for (int it = 0; it < 100; it++) {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4], e[6];
+        tcp_world<T>(arm, k, tp, tq);
+        e[0] = tpos[0] - tp[0]; e[1] = tpos[1] - tp[1]; e[2] = tpos[2] - tp[2];
+        const double res = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        if (it > 0 && res < 1e-8) break;
+        double qi[4] = {-tq[0], -tq[1], -tq[2], tq[3]}, dq[4];
+        quat_mul(dq, tquat, qi);
+        const double wv = fmin(fmax(dq[3], -1.0), 1.0);
+        double ang = 2 * acos(wv);
+        const double sn = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
+        if (ang > M_PI) ang -= 2 * M_PI;
+#pragma unroll
+        for (int c = 0; c < 3; c++) e[3 + c] = sn > 1e-300 ? ang * dq[c] / sn : 0.0;
+        double J[6][NB];
+        tcp_jacobian<T>(arm, k, tp, J);
+        if (NB == 6) {
+            double Mx[6][7], d[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                double bi = 0;
+#pragma unroll
+                for (int r = 0; r < 6; r++) bi += J[r][i] * e[r];
+                Mx[i][6] = bi;
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    double s = i == j ? 0.5 : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 6; r++) s += J[r][i] * J[r][j];
+                    Mx[i][j] = s;
+                }
+            }
+            solve6(Mx, d);
+            double mx = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(d[i]));
+            const double sc = mx > M_PI / 4 ? (M_PI / 4) / mx : 1.0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) q[i] += sc * d[i];
+        }
+    }
+}
+
+// One reset of env e: consumes the env's next draws and returns the start-of-episode state.
+template <class T>
+__device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e,
+                                       EpisodeStart<T::NB>& out)
+{
+    constexpr int NB = T::NB;
+    // reset_task draws (edge_follow_env.py:285-299): embed_dist then edge_ang
+    double draw[TG_MAXDRAW];
+#pragma unroll
+    for (int d = 0; d < TG_MAXDRAW; d++) draw[d] = task.draw_default[d];
+    {
+        const int cnt = b.reset_count[e];
+        if (b.draws && cnt < b.draw_rounds) {
+#pragma unroll
+            for (int d = 0; d < TG_MAXDRAW; d++)
+                if (d < task.n_draws) draw[d] = b.draws[((size_t)e * b.draw_rounds + cnt) * task.n_draws + d];
+        }
+        b.reset_count[e] = cnt + 1;
+    }
+    const double embed = draw[0], edge_ang = draw[1];
+    out.embed = embed; out.edge_ang = edge_ang;
+    {
+        double s, c;
+        sincos(edge_ang * 0.5, &s, &c);
+        double qz[4] = {0, 0, s, c}, R[9]; // getQuaternionFromEuler([0,0,ang]) (edge_follow_env.py:241)
+        mat_from_quat(qz, R);
+#pragma unroll
+        for (int i = 0; i < 9; i++) out.stim[i] = R[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) out.stim[9 + i] = task.edge_pos[i];
+    }
+    double q[NB], qd[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) { q[i] = b.rest_q[i]; qd[i] = 0.0; }
+    // workframe_to_worldframe (base_robot_arm.py:47-60) of the init pose [0,0,embed], init_rpy
+    double tpos[3], targ_orn[4];
+    {
+        double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
+        const double lp[3] = {0.0, 0.0, embed};
+        quat_from_euler(task.workframe_rpy, wq);
+        quat_from_euler(task.init_rpy, tq);
+        mat_from_quat(wq, R);
+        m3mulv(t, R, lp);
+        tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
+        quat_mul(oq, wq, tq);
+        euler_from_quat(oq, rpy);
+        quat_from_euler(rpy, targ_orn);
+    }
+    double targ_j[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) targ_j[i] = q[i];
+    inverse_kinematics<T>(arm, targ_j, tpos, targ_orn);
+
+    // Robot.blocking_move(max_steps=1000, constant_vel=0.001) (robot.py:188-260)
+    Motors<NB> mot;
+    mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.blocking_force;
+    double cv = 0.001;
+    int nsteps = 0;
+#pragma unroll 1
+    for (int it = 0; it < 1000; it++) {
+        double tp[3], tq[4];
+        {
+            Kin<NB> k;
+            fk<T>(arm, q, k);
+            tcp_world<T>(arm, k, tp, tq);
+        }
+        double nrm = 0, tot = 0;
+        bool all_small = true;
+        double diff[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) { diff[i] = targ_j[i] - q[i]; nrm += diff[i] * diff[i]; tot += fabs(qd[i]); }
+        nrm = sqrt(nrm);
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const double vdir = nrm > 0 ? diff[i] / nrm : 0.0;
+            mot.target_pos[i] = q[i] + vdir * cv; mot.target_vel[i] = 0.0;
+            if (!(fabs(diff[i]) < cv)) all_small = false;
+        }
+        if (all_small) cv *= 0.5;
+        substep<T>(arm, ph, q, qd, mot);
+        nsteps++;
+        const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
+        const double ip = targ_orn[0] * tq[0] + targ_orn[1] * tq[1] + targ_orn[2] * tq[2] + targ_orn[3] * tq[3];
+        const double ca = fmin(fmax(2 * ip * ip - 1, -1.0), 1.0);
+        const double oe = acos(ca);
+        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
+    }
+    out.substeps = nsteps;
+#pragma unroll
+    for (int i = 0; i < NB; i++) { out.q[i] = q[i]; out.qd[i] = qd[i]; }
+    {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4];
+        tcp_world<T>(arm, k, tp, tq);
+        write_camera<T>(arm, k, out.cam);
+#pragma unroll
+        for (int c = 0; c < 3; c++) out.tcp[c] = tp[c];
+#pragma unroll
+        for (int c = 0; c < 4; c++) out.tcp[3 + c] = tq[c];
+    }
+}
+
+template <int NB>
+TGD void store_live(const EnvBuffers& b, int e, const EpisodeStart<NB>& s)
+{
+#pragma unroll
+    for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = s.q[i]; b.qd[(size_t)i * b.n + e] = s.qd[i]; }
+    b.embed[e] = s.embed; b.edge_ang[e] = s.edge_ang; b.steps[e] = 0; b.reset_substeps[e] = s.substeps;
+#pragma unroll
+    for (int c = 0; c < 12; c++) { b.cam[(size_t)e * 12 + c] = s.cam[c]; b.stim[(size_t)e * 12 + c] = s.stim[c]; }
+#pragma unroll
+    for (int c = 0; c < 7; c++) b.tcp[(size_t)e * 7 + c] = s.tcp[c];
+}
+
+template <int NB>
+TGD void store_standby(const EnvBuffers& b, int e, const EpisodeStart<NB>& s)
+{
+#pragma unroll
+    for (int i = 0; i < NB; i++) { b.sb_q[(size_t)i * b.n + e] = s.q[i]; b.sb_qd[(size_t)i * b.n + e] = s.qd[i]; }
+    b.sb_embed[e] = s.embed; b.sb_ang[e] = s.edge_ang; b.sb_substeps[e] = s.substeps;
+#pragma unroll
+    for (int c = 0; c < 12; c++) { b.sb_cam[(size_t)e * 12 + c] = s.cam[c]; b.sb_stim[(size_t)e * 12 + c] = s.stim[c]; }
+#pragma unroll
+    for (int c = 0; c < 7; c++) b.sb_tcp[(size_t)e * 7 + c] = s.tcp[c];
+    __threadfence();
+    b.sb_ready[e] = 1;
+}
+
+// swap the standby in as the live state of env e (a copy); the slot is recomputed by the next launch
+template <int NB>
+TGD void consume_standby(const EnvBuffers& b, int e)
+{
+#pragma unroll
+    for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = b.sb_q[(size_t)i * b.n + e]; b.qd[(size_t)i * b.n + e] = b.sb_qd[(size_t)i * b.n + e]; }
+    b.embed[e] = b.sb_embed[e]; b.edge_ang[e] = b.sb_ang[e]; b.steps[e] = 0; b.reset_substeps[e] = b.sb_substeps[e];
+#pragma unroll
+    for (int c = 0; c < 12; c++) { b.cam[(size_t)e * 12 + c] = b.sb_cam[(size_t)e * 12 + c]; b.stim[(size_t)e * 12 + c] = b.sb_stim[(size_t)e * 12 + c]; }
+#pragma unroll
+    for (int c = 0; c < 7; c++) b.tcp[(size_t)e * 7 + c] = b.sb_tcp[(size_t)e * 7 + c];
+    __threadfence();
+    b.sb_ready[e] = 0;
+}
+
+// standby role: threads scan the envs and recompute every missing standby
+template <class T>
+TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int first_block)
+{
+    const int t = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
+    const int nt = (gridDim.x - first_block) * blockDim.x;
+    for (int e = t; e < b.n; e += nt) {
+        if (b.sb_ready[e]) continue;
+        EpisodeStart<T::NB> s;
+        reset_env<T>(arm, ph, task, b, e, s);
+        store_standby<T::NB>(b, e, s);
+    }
+}
+
+// autoreset: 1 = finished envs start their next episode inside this launch (VecEnv semantics)
 template <class T>
 __global__ void __launch_bounds__(128)
 step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
-            EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done)
+            EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
 {
     constexpr int NB = T::NB;
+    if ((int)blockIdx.x >= b.step_blocks) {
+        standby_role<T>(arm, ph, task, b, b.step_blocks);
+        return;
+    }
     const int e = env_index(b);
     if (e < 0) return;
     double q[NB], qd[NB];
@@ -146,14 +385,21 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     b.steps[e] = steps;
 #pragma unroll
     for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = q[i]; b.qd[(size_t)i * b.n + e] = qd[i]; }
-    {
-        Kin<NB> k;
-        fk<T>(arm, q, k);
-        double tp[3], tq[4];
-        tcp_world<T>(arm, k, tp, tq);
-        float r; unsigned char d;
-        edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
-        reward[e] = r; done[e] = d;
+    Kin<NB> k;
+    fk<T>(arm, q, k);
+    double tp[3], tq[4];
+    tcp_world<T>(arm, k, tp, tq);
+    float r; unsigned char d;
+    edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
+    reward[e] = r; done[e] = d;
+    if (d && autoreset && b.pipeline) {
+        // terminal camera for the terminal observation, then the standby becomes the live state
+        write_camera<T>(arm, k, b.term_cam + (size_t)e * 12);
+#pragma unroll
+        for (int c = 0; c < 12; c++) b.term_stim[(size_t)e * 12 + c] = b.stim[(size_t)e * 12 + c];
+        if (b.sb_ready[e]) consume_standby<NB>(b, e);
+        else *b.error_flag = 1;
+    } else {
         write_camera<T>(arm, k, b.cam + (size_t)e * 12);
 #pragma unroll
         for (int c = 0; c < 3; c++) b.tcp[(size_t)e * 7 + c] = tp[c];
@@ -162,164 +408,34 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     }
 }
 
-// pb.calculateInverseKinematics as restated in oracle/tg_oracle.c:or_inverse_kinematics (base_robot_arm.py:201-209)
-template <class T>
-TGD void inverse_kinematics(const TgArm& arm, double* q, const double* tpos, const double* tquat)
-{
-    constexpr int NB = T::NB;
-    static_assert(NB == 6 || NB == 8, "topology");
-#pragma unroll 1
-    for (int it = 0; it < 100; it++) {
-        Kin<NB> k;
-        fk<T>(arm, q, k);
-        double tp[3], tq[4], e[6];
-        tcp_world<T>(arm, k, tp, tq);
-        e[0] = tpos[0] - tp[0]; e[1] = tpos[1] - tp[1]; e[2] = tpos[2] - tp[2];
-        const double res = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-        if (it > 0 && res < 1e-8) break;
-        double qi[4] = {-tq[0], -tq[1], -tq[2], tq[3]}, dq[4];
-        quat_mul(dq, tquat, qi);
-        const double wv = fmin(fmax(dq[3], -1.0), 1.0);
-        double ang = 2 * acos(wv);
-        const double sn = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
-        if (ang > M_PI) ang -= 2 * M_PI;
-#pragma unroll
-        for (int c = 0; c < 3; c++) e[3 + c] = sn > 1e-300 ? ang * dq[c] / sn : 0.0;
-        double J[6][NB];
-        tcp_jacobian<T>(arm, k, tp, J);
-        if (NB == 6) {
-            double Mx[6][7], d[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                double bi = 0;
-#pragma unroll
-                for (int r = 0; r < 6; r++) bi += J[r][i] * e[r];
-                Mx[i][6] = bi;
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    double s = i == j ? 0.5 : 0.0;
-#pragma unroll
-                    for (int r = 0; r < 6; r++) s += J[r][i] * J[r][j];
-                    Mx[i][j] = s;
-                }
-            }
-            solve6(Mx, d);
-            double mx = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(d[i]));
-            const double sc = mx > M_PI / 4 ? (M_PI / 4) / mx : 1.0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) q[i] += sc * d[i];
-        }
-    }
-}
-
+// explicit reset of the masked envs.  With the pipeline on, an env's standby IS its next episode: take it and
+// compute the following one, so draws stay in episode order.
 template <class T>
 __global__ void __launch_bounds__(128)
 reset_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
              EnvBuffers b, const unsigned char* __restrict__ mask)
 {
-    constexpr int NB = T::NB;
     const int e = env_index(b);
     if (e < 0) return;
     if (mask && !mask[e]) return;
+    EpisodeStart<T::NB> s;
+    if (b.pipeline) {
+        if (!b.sb_ready[e]) { reset_env<T>(arm, ph, task, b, e, s); store_standby<T::NB>(b, e, s); }
+        consume_standby<T::NB>(b, e);
+        reset_env<T>(arm, ph, task, b, e, s);
+        store_standby<T::NB>(b, e, s);
+    } else {
+        reset_env<T>(arm, ph, task, b, e, s);
+        store_live<T::NB>(b, e, s);
+    }
+}
 
-    // reset_task draws (edge_follow_env.py:285-299): embed_dist then edge_ang
-    double draw[TG_MAXDRAW];
-#pragma unroll
-    for (int d = 0; d < TG_MAXDRAW; d++) draw[d] = task.draw_default[d];
-    {
-        const int cnt = b.reset_count[e];
-        if (b.draws && cnt < b.draw_rounds) {
-#pragma unroll
-            for (int d = 0; d < TG_MAXDRAW; d++)
-                if (d < task.n_draws) draw[d] = b.draws[((size_t)e * b.draw_rounds + cnt) * task.n_draws + d];
-        }
-        b.reset_count[e] = cnt + 1;
-    }
-    const double embed = draw[0], edge_ang = draw[1];
-    b.embed[e] = embed; b.edge_ang[e] = edge_ang; b.steps[e] = 0;
-    {
-        double s, c;
-        sincos(edge_ang * 0.5, &s, &c);
-        double qz[4] = {0, 0, s, c}, R[9]; // getQuaternionFromEuler([0,0,ang]) (edge_follow_env.py:241)
-        mat_from_quat(qz, R);
-#pragma unroll
-        for (int i = 0; i < 9; i++) b.stim[(size_t)e * 12 + i] = R[i];
-#pragma unroll
-        for (int i = 0; i < 3; i++) b.stim[(size_t)e * 12 + 9 + i] = task.edge_pos[i];
-    }
-
-    double q[NB], qd[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) { q[i] = b.rest_q[i]; qd[i] = 0.0; }
-    // workframe_to_worldframe (base_robot_arm.py:47-60) of the init pose [0,0,embed], init_rpy
-    double tpos[3], targ_orn[4];
-    {
-        double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
-        const double lp[3] = {0.0, 0.0, embed};
-        quat_from_euler(task.workframe_rpy, wq);
-        quat_from_euler(task.init_rpy, tq);
-        mat_from_quat(wq, R);
-        m3mulv(t, R, lp);
-        tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
-        quat_mul(oq, wq, tq);
-        euler_from_quat(oq, rpy);
-        quat_from_euler(rpy, targ_orn);
-    }
-    double targ_j[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) targ_j[i] = q[i];
-    inverse_kinematics<T>(arm, targ_j, tpos, targ_orn);
-
-    // Robot.blocking_move(max_steps=1000, constant_vel=0.001) (robot.py:188-260)
-    Motors<NB> mot;
-    mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.blocking_force;
-    double cv = 0.001;
-    int nsteps = 0;
-#pragma unroll 1
-    for (int it = 0; it < 1000; it++) {
-        double tp[3], tq[4];
-        {
-            Kin<NB> k;
-            fk<T>(arm, q, k);
-            tcp_world<T>(arm, k, tp, tq);
-        }
-        double nrm = 0, tot = 0;
-        bool all_small = true;
-        double diff[NB];
-#pragma unroll
-        for (int i = 0; i < NB; i++) { diff[i] = targ_j[i] - q[i]; nrm += diff[i] * diff[i]; tot += fabs(qd[i]); }
-        nrm = sqrt(nrm);
-#pragma unroll
-        for (int i = 0; i < NB; i++) {
-            const double vdir = nrm > 0 ? diff[i] / nrm : 0.0;
-            mot.target_pos[i] = q[i] + vdir * cv; mot.target_vel[i] = 0.0;
-            if (!(fabs(diff[i]) < cv)) all_small = false;
-        }
-        if (all_small) cv *= 0.5;
-        substep<T>(arm, ph, q, qd, mot);
-        nsteps++;
-        const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
-        const double ip = targ_orn[0] * tq[0] + targ_orn[1] * tq[1] + targ_orn[2] * tq[2] + targ_orn[3] * tq[3];
-        const double ca = fmin(fmax(2 * ip * ip - 1, -1.0), 1.0);
-        const double oe = acos(ca);
-        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
-    }
-    b.reset_substeps[e] = nsteps;
-#pragma unroll
-    for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = q[i]; b.qd[(size_t)i * b.n + e] = qd[i]; }
-    {
-        Kin<NB> k;
-        fk<T>(arm, q, k);
-        double tp[3], tq[4];
-        tcp_world<T>(arm, k, tp, tq);
-        write_camera<T>(arm, k, b.cam + (size_t)e * 12);
-#pragma unroll
-        for (int c = 0; c < 3; c++) b.tcp[(size_t)e * 7 + c] = tp[c];
-#pragma unroll
-        for (int c = 0; c < 4; c++) b.tcp[(size_t)e * 7 + 3 + c] = tq[c];
-    }
+// recompute every missing standby (after tg_set_draws invalidated them)
+template <class T>
+__global__ void __launch_bounds__(128)
+standby_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task, EnvBuffers b)
+{
+    standby_role<T>(arm, ph, task, b, 0);
 }
 
 // ---------------------------------------------------------------- test hooks

@@ -1,6 +1,7 @@
 // tg_world.cu - C ABI of libtactile_gym_b200.so (include/tactile_gym_b200.h): world lifetime, buffers, launches.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -43,6 +44,7 @@ struct TgWorld {
     float* d_reward_internal = nullptr;
     size_t raster_smem = 0;
     int raster_grid = 0;
+    int standby_blocks = 0;
     long long launches = 0;
 };
 
@@ -113,6 +115,17 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     CK(cudaMemcpy(rest, cfg->h_rest_q, sizeof(double) * nb, cudaMemcpyHostToDevice));
     b.rest_q = rest;
     b.draws = nullptr; b.draw_rounds = 0;
+    // standby reset pipeline (tg_env.cuh): needs episodes of at least 2 steps
+    b.pipeline = cfg->task.max_steps >= 2 ? 1 : 0;
+    b.step_blocks = (n + 4 * lanes - 1) / (4 * lanes);
+    if ((rc = dalloc(w, &b.sb_q, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_qd, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_embed, n)) ||
+        (rc = dalloc(w, &b.sb_ang, n)) || (rc = dalloc(w, &b.sb_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.sb_stim, (size_t)12 * n)) ||
+        (rc = dalloc(w, &b.sb_tcp, (size_t)7 * n)) || (rc = dalloc(w, &b.sb_substeps, n)) || (rc = dalloc(w, &b.sb_ready, n)) ||
+        (rc = dalloc(w, &b.term_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.term_stim, (size_t)12 * n)) || (rc = dalloc(w, &b.error_flag, 1))) {
+        tg_destroy(w);
+        return rc;
+    }
+    w->standby_blocks = b.pipeline ? std::max(8, std::min(64, w->sm_count / 2)) : 0;
 
     // raster tables: border pixels get nodef = -1 and the baked grey value (tactile_sensor.py:289-292)
     {
@@ -161,7 +174,7 @@ extern "C" int tg_destroy(TgWorld* w)
     return TG_OK;
 }
 
-extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds)
+static int set_draws_impl(TgWorld* w, const double* h_draws, int rounds, int invalidate)
 {
     if (!w || !h_draws || rounds <= 0) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
@@ -172,7 +185,28 @@ extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds)
     CK(cudaMemcpy(w->d_draws, h_draws, cnt * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemset(w->eb.reset_count, 0, sizeof(int) * w->n));
     w->eb.draws = w->d_draws; w->eb.draw_rounds = rounds;
+    if (invalidate && w->eb.pipeline) {
+        // a new draw sequence starts: standbys computed from the old one are recomputed now
+        CK(cudaMemset(w->eb.sb_ready, 0, w->n));
+        standby_kernel<TopoChain6><<<(w->n + 127) / 128, 128>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb);
+        w->launches++;
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
     return TG_OK;
+}
+
+extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds) { return set_draws_impl(w, h_draws, rounds, 1); }
+extern "C" int tg_refill_draws(TgWorld* w, const double* h_draws, int rounds) { return set_draws_impl(w, h_draws, rounds, 0); }
+
+extern "C" int tg_pipeline_error(TgWorld* w, void* stream)
+{
+    if (!w) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, w->eb.error_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return flag;
 }
 
 extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)
@@ -184,16 +218,13 @@ extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)
     return TG_OK;
 }
 
-static dim3 env_grid(const TgWorld* w)
-{
-    const int per_block = 4 * w->eb.lanes; // 128 threads = 4 warps
-    return dim3((w->n + per_block - 1) / per_block);
-}
+static dim3 env_grid(const TgWorld* w) { return dim3(w->eb.step_blocks); } // 128 threads = 4 warps = 4 * lanes envs
 
-static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, uint8_t* term, cudaStream_t st)
+static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, uint8_t* term, cudaStream_t st, bool terminal_state = false)
 {
     RasterArgs r = w->ra;
     r.obs = d_obs; r.mask = mask; r.term_obs = term;
+    if (terminal_state) { r.cam = w->eb.term_cam; r.stim = w->eb.term_stim; }
     raster_kernel<<<w->raster_grid, RASTER_THREADS, w->raster_smem, st>>>(r);
     w->launches++;
     CK(cudaGetLastError());
@@ -208,9 +239,10 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
     return TG_OK;
 }
 
-static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, cudaStream_t st)
+static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, int autoreset, cudaStream_t st)
 {
-    step_kernel<TopoChain6><<<env_grid(w), 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done);
+    const dim3 grid(w->eb.step_blocks + w->standby_blocks); // the extra blocks recompute consumed standbys meanwhile
+    step_kernel<TopoChain6><<<grid, 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done, autoreset);
     w->launches++;
     CK(cudaGetLastError());
     return TG_OK;
@@ -238,7 +270,14 @@ extern "C" int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float
     CK(cudaSetDevice(w->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = launch_step(w, d_actions, d_reward, d_done, st))) return rc;
+    if (w->eb.pipeline) {
+        // finished envs swap their standby start-of-episode state in inside step_kernel: 2 launches per step
+        if ((rc = launch_step(w, d_actions, d_reward, d_done, 1, st))) return rc;
+        if ((rc = launch_raster(w, d_obs, nullptr, nullptr, st))) return rc;            // first obs of the new episode for done envs
+        if (d_term_obs) return launch_raster(w, d_term_obs, d_done, nullptr, st, true);  // their terminal obs, on request
+        return TG_OK;
+    }
+    if ((rc = launch_step(w, d_actions, d_reward, d_done, 1, st))) return rc;
     if ((rc = launch_raster(w, d_obs, nullptr, nullptr, st))) return rc;   // observation of every env (terminal one for done envs)
     if ((rc = launch_reset(w, d_done, st))) return rc;                      // finished envs start their next episode
     return launch_raster(w, d_obs, d_done, d_term_obs, st);                 // ... and get its first observation
@@ -248,7 +287,7 @@ extern "C" int tg_physics_only(TgWorld* w, const float* d_actions, float* d_rewa
 {
     if (!w || !d_actions) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
-    return launch_step(w, d_actions, d_reward ? d_reward : w->d_reward_internal, d_done ? d_done : w->d_done_internal, (cudaStream_t)stream);
+    return launch_step(w, d_actions, d_reward ? d_reward : w->d_reward_internal, d_done ? d_done : w->d_done_internal, 0, (cudaStream_t)stream);
 }
 
 extern "C" int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream)

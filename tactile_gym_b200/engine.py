@@ -160,7 +160,8 @@ class TactileWorld:
                 c = min(int(counts[i]), DRAW_ROUNDS)
                 self._host_draws[i] = np.concatenate([self._host_draws[i, c:], self._draw(self._rngs[i], c)])
         arr = np.ascontiguousarray(self._host_draws, dtype=np.float64)
-        L.check(self.lib.tg_set_draws(self.h, arr.ctypes.data, DRAW_ROUNDS))
+        # fresh sequence (seed()): pre-computed standby episodes are recomputed; refill: they stay valid
+        L.check((self.lib.tg_set_draws if fresh else self.lib.tg_refill_draws)(self.h, arr.ctypes.data, DRAW_ROUNDS))
         self._steps_since_check = 0
 
     def set_draws(self, draws):
@@ -221,6 +222,10 @@ class TactileWorld:
         cam = np.zeros((self.n, 12))
         L.check(self.lib.tg_get_camera(self.h, cam.ctypes.data, self._stream()))
         return cam
+
+    def pipeline_error(self):
+        """True if a finished env ever found no pre-computed standby episode (never, for episodes of >= 2 steps)"""
+        return bool(self.lib.tg_pipeline_error(self.h, self._stream()))
 
     def launch_count(self):
         return int(self.lib.tg_launch_count(self.h))

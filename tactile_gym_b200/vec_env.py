@@ -48,8 +48,11 @@ class TactileVecEnv(_VecEnvBase):
         self._t0 = time.time()
         torch = self.world.torch
         self._pin_actions = torch.zeros((n_envs, self.world.act_dim), dtype=torch.float32).pin_memory()
-        self._pin_obs = torch.zeros((n_envs, S, S, 1), dtype=torch.uint8).pin_memory()
-        self._pin_term = torch.zeros((n_envs, S, S, 1), dtype=torch.uint8).pin_memory()
+        # two pinned observation buffers, used alternately: the arrays handed out are views (no 64 MB host copy);
+        # an observation stays valid until the step after next
+        self._pin_obs2 = [torch.zeros((n_envs, S, S, 1), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._flip = 0
+        self._pin_obs = self._pin_obs2[0]
         self._pin_rew = torch.zeros(n_envs, dtype=torch.float32).pin_memory()
         self._pin_done = torch.zeros(n_envs, dtype=torch.uint8).pin_memory()
         if seed is not None:
@@ -61,20 +64,25 @@ class TactileVecEnv(_VecEnvBase):
     def seed(self, seed=None):
         return self.world.seed(seed)
 
+    def _next_obs_buffer(self):
+        self._flip ^= 1
+        self._pin_obs = self._pin_obs2[self._flip]
+        return self._pin_obs
+
     def reset(self):
         self.world.reset()
-        self._pin_obs.copy_(self.world.obs, non_blocking=True)
+        self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
         self.world.torch.cuda.synchronize(self.world.device)
         self._ep_ret[:] = 0
         self._ep_len[:] = 0
-        return {"tactile": self._pin_obs.numpy().copy()}
+        return {"tactile": self._pin_obs.numpy()}
 
     def step_async(self, actions):
         torch = self.world.torch
         self._pin_actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, -1)))
         a = self._pin_actions.to(self.world.device, non_blocking=True)
         self.world.step(a, want_terminal_obs=True)
-        self._pin_obs.copy_(self.world.obs, non_blocking=True)
+        self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
         self._pin_rew.copy_(self.world.reward, non_blocking=True)
         self._pin_done.copy_(self.world.done, non_blocking=True)
 
@@ -94,7 +102,7 @@ class TactileVecEnv(_VecEnvBase):
                 infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
                 self._ep_ret[i] = 0
                 self._ep_len[i] = 0
-        return {"tactile": self._pin_obs.numpy().copy()}, rew, done, infos
+        return {"tactile": self._pin_obs.numpy()}, rew, done, infos
 
     def step(self, actions):
         self.step_async(actions)

@@ -140,6 +140,7 @@ def test_free_running_episode_stays_close(oracle, edge_modes):
         assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=1e-5)
         assert np.allclose(st[i, 12:15], r.tcp_world()[0], atol=1e-5)
     assert np.mean(exact) > 0.998
+    assert not env.world.pipeline_error()
     env.close()
 
 
@@ -187,6 +188,7 @@ def test_autoreset_and_terminal_observation(oracle, edge_modes):
         assert _img_close(o, obs["tactile"][i])[0] <= 1
     st = env.world.get_state()
     assert (st[:, 21] == 0).all()                       # step counters restarted
+    assert not env.world.pipeline_error()               # every finished env found its pre-computed next episode
     env.close()
 
 
