@@ -117,8 +117,10 @@ typedef struct {
     const float* h_nodef_dep;      /* [S*S] */
     const float* h_nodef_gray;     /* [S*S] */
     const uint8_t* h_border_mask;  /* [S*S] */
-    int32_t n_tri, pad0;
-    const double* h_tris;          /* [n_tri][3][3] stimulus triangles in the stimulus frame */
+    int32_t n_prim, pad0;
+    const double* h_prims;         /* [n_prim][4][3] stimulus primitives in the stimulus frame: convex planar polygons
+                                      with 3 or 4 vertices (coplanar triangle pairs merged; unused 4th vertex ignored) */
+    const int32_t* h_prim_nv;      /* [n_prim] vertex counts */
 } TgSensor;
 
 typedef struct {

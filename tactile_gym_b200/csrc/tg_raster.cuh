@@ -5,28 +5,27 @@
 //
 // What makes it cheap ("decisive simplification"): the camera is rigidly attached to the
 // sensor, so everything but the stimulus is static in the camera frame and already baked into the
-// reference's nodef_dep / border_mask / nodef_gray images.  Per env only the few stimulus triangles are
-// z-tested against nodef_dep.
+// reference's nodef_dep / border_mask / nodef_gray images.  Per env only the few stimulus primitives are
+// z-tested against nodef_dep.  Primitives are convex planar polygons with 3 or 4 vertices (coplanar triangle
+// pairs of the stimulus mesh are merged into quads at scene-compile time: same coverage, same plane).
 //
 // Kernel shape (HBM-write bound; algorithmic bytes/env = S*S obs + 192 B camera/stimulus state):
-//   * persistent CTAs, grid = #SMs x CTAs/SM; each CTA owns one row band, whose slice of nodef_dep (f32) and
-//     of the pre-baked border image (u8) is fetched ONCE per CTA by TMA bulk copies (cp.async.bulk +
-//     mbarrier) into shared memory and reused for every env;
-//   * after that there is no block-level synchronisation: each WARP renders whole env images (band slices)
-//     on its own, taking env indices in a strided order;
-//   * per env, lanes 0..ntri-1 turn camera + stimulus pose into homogeneous edge equations in pixel
-//     coordinates (b = M^-1 d: inside <=> all b_i >= 0, 1/z_eye = sum b_i; exact per-pixel clipping, no
-//     vertex projection) - fp64 coefficients plus float copies with an error margin;
-//   * every 8 x 64 pixel tile is classified per triangle from its four corner pixels (edge functions are
-//     affine): outside / inside / partial; one lane per tile, masks travel by warp shuffle;
-//   * a lane owns 16 consecutive pixels of a row.  Tiles no triangle touches are a straight shared-memory ->
-//     HBM copy of the baked row.  Inside triangles cost one DFMA + compare per pixel (nearest = largest
-//     1/z); partial ones are first classified per 16-pixel span from its two end pixels, and only spans an
-//     edge really crosses are tested per pixel, in float, falling back to the fp64 equations inside the
-//     float error margin - so coverage and depth equal the fp64 oracle's;
-//   * the post-process is float32 with numpy's operation order (the division by 0.05f is replaced by a
-//     reciprocal + 2 FMA sequence verified exhaustively to give the same uint8, tools/check_quantize.c);
-//     one 16-byte store per lane, a warp stores 8 rows x 64 B = 16 full 32-byte sectors.
+//   * persistent CTAs, grid = #SMs; each CTA owns one row band, whose slice of nodef_dep (f32) and of the
+//     pre-baked border image (u8) is fetched ONCE per CTA by TMA bulk copies (cp.async.bulk + mbarrier) into
+//     shared memory and reused for every env; after that there is no block-level synchronisation: each WARP
+//     renders whole env images (band slices) on its own;
+//   * per env, one lane per primitive builds homogeneous edge equations in pixel coordinates (inside <=> all
+//     E_i >= 0; 1/z_eye is affine in the pixel, hence so is the un-quantised output value
+//     val = 5100 (nodef - d), d = F - F near / z): fp64 coefficients + float copies with an error margin;
+//   * BIN: every 8 x 64 tile is classified per primitive from its corner pixels (out / in / partial, bbox
+//     reject, exact occlusion cull); the baked row is copied to HBM; 16-pixel spans that a primitive really
+//     touches and that contain skin pixels are compacted into a small per-warp list;
+//   * SHADE: 32 listed spans at a time, one per lane - all lanes busy.  Covered pixels take
+//     max over primitives of an affine float function, one FFMA with nodef, clamp, truncate;
+//   * EXACT PATCH-UP: the float path carries a proven error bound (1e-3 of an output LSB); pixels whose value
+//     is closer than that to a quantisation step, or closer than the float margin to a primitive edge, are
+//     queued and recomputed with the oracle's arithmetic (fp64 depth -> float32 numpy post-process), so the
+//     bytes equal the CPU oracle's.  About 0.3 % of the covered pixels take this path.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,29 +36,41 @@
 #define RASTER_WARPS (RASTER_THREADS / 32)
 #define TILE_ROWS 8
 #define TILE_COLS 64
-#define RASTER_MAXTRI 32
+#define RASTER_MAXPRIM 16
+#define SPAN_LIST 64   // per-warp compacted span list (entries)
+#define EXACT_QUEUE 96 // per-warp queue of pixels for the exact path
+#define VAL_SCALE 5100.0f // 255 / 0.05
+#define VAL_BOUND 1.0e-3f // proven bound on |float value - oracle value|
 
-struct TriCoef {
-    double eA[4], eB[4], eC[4]; // fp64: b_i(c, r) = eA[i] c + eB[i] r + eC[i], i = 0..2; index 3 = w = sum b_i = 1/z_eye
-    float fA[4], fB[4], fC[4];  // float copies
-    float margin;               // |float evaluation error| bound for any of the four functions
-    int valid;                  // 0: degenerate (plane through the eye), 1: usable
-    float c_lo, c_hi, r_lo, r_hi; // conservative screen bbox in pixel units (whole image if a vertex is behind the eye)
-    int clipped, pad;           // 1: some vertex is nearer than the near plane -> per-pixel range checks needed
+struct PrimCoef {
+    double eA[5], eB[5], eC[5]; // fp64: E_i(c, r) = eA[i] c + eB[i] r + eC[i], i < 4 edges; index 4 = w = 1/z_eye
+    float fA[5], fB[5], fC[5];  // float copies
+    float vA, vB, vC;           // float: V(c, r) = 5100 (nd_ref - F + F near w(c, r))  -> val = 5100 (nodef - nd_ref) + V
+    float margin;               // bound on the float evaluation error of any of the five functions
+    float c_lo, c_hi, r_lo, r_hi; // conservative screen bbox in pixel units
+    int valid, clipped;         // clipped: a vertex is outside [near, far] -> per-pixel range checks needed
 };
 
 struct RasterArgs {
-    int n, S, bands, ntri;
+    int n, S, bands, nprim;
     double th;             // tan(fov/2)
     double F, near_, far_; // F = far/(far-near)
     const float* nodef;    // [S*S], border pixels = -1
     const uint8_t* base;   // [S*S], border pixels = (u8)nodef_gray, others 0
-    const double* tris;    // [ntri][9] stimulus-frame triangles
+    const double* prims;   // [nprim][4][3] stimulus-frame polygons
+    const int* prim_nv;    // [nprim] 3 or 4
     const double* cam;     // [N][12]
     const double* stim;    // [N][12]
     const uint8_t* mask;   // optional [N]
     uint8_t* obs;          // [N][S*S]
-    uint8_t* term_obs;     // optional [N][S*S]: previous obs of masked envs is copied here first
+    float nd_ref;          // reference depth: the float path works on (nodef - nd_ref) to keep magnitudes (and errors) small
+};
+
+struct SpanEntry {
+    uint16_t off16;  // span index inside the band (pixel offset / 16)
+    uint16_t in_m;   // primitives covering the whole span
+    uint16_t part_m; // primitives crossing it
+    uint16_t pad;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,13 +83,13 @@ __device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gm
                  : "memory");
 }
 
-__device__ __forceinline__ void tri_setup(const RasterArgs& a, const double* cam, const double* stim, const double* tl, TriCoef& o)
+__device__ __forceinline__ void prim_setup(const RasterArgs& a, const double* cam, const double* stim, const double* pl, int nv, PrimCoef& o)
 {
     // stimulus frame -> world -> eye space (x right, y up, z forward)
-    double ve[3][3];
+    double ve[4][3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const double* v = tl + 3 * k;
+    for (int k = 0; k < 4; k++) {
+        const double* v = pl + 3 * (k < nv ? k : nv - 1);
         double w[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) w[c] = stim[3 * c] * v[0] + stim[3 * c + 1] * v[1] + stim[3 * c + 2] * v[2] + stim[9 + c] - cam[c];
@@ -86,72 +97,70 @@ __device__ __forceinline__ void tri_setup(const RasterArgs& a, const double* cam
         ve[k][1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
         ve[k][2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
     }
-    // M = [p0 p1 p2] (columns); rows of M^-1 = (p1 x p2, p2 x p0, p0 x p1) / det
-    double c0[3], c1[3], c2[3];
-    c0[0] = ve[1][1] * ve[2][2] - ve[1][2] * ve[2][1]; c0[1] = ve[1][2] * ve[2][0] - ve[1][0] * ve[2][2]; c0[2] = ve[1][0] * ve[2][1] - ve[1][1] * ve[2][0];
-    c1[0] = ve[2][1] * ve[0][2] - ve[2][2] * ve[0][1]; c1[1] = ve[2][2] * ve[0][0] - ve[2][0] * ve[0][2]; c1[2] = ve[2][0] * ve[0][1] - ve[2][1] * ve[0][0];
-    c2[0] = ve[0][1] * ve[1][2] - ve[0][2] * ve[1][1]; c2[1] = ve[0][2] * ve[1][0] - ve[0][0] * ve[1][2]; c2[2] = ve[0][0] * ve[1][1] - ve[0][1] * ve[1][0];
-    const double det = ve[0][0] * c0[0] + ve[0][1] * c0[1] + ve[0][2] * c0[2];
+    const double S = a.S;
+    // plane: n . p = n . v0 ; along the pixel ray p = z d (d.z = 1):  1/z = (n . d) / (n . v0)
+    double e1[3] = {ve[1][0] - ve[0][0], ve[1][1] - ve[0][1], ve[1][2] - ve[0][2]};
+    double e2[3] = {ve[2][0] - ve[0][0], ve[2][1] - ve[0][1], ve[2][2] - ve[0][2]};
+    double nrm[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const double nd0 = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
+    const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
     o.valid = 0;
-    if (fabs(det) < 1e-300) return;
+    if (!(fabs(nd0) > 1e-12 * nn * (fabs(ve[0][0]) + fabs(ve[0][1]) + fabs(ve[0][2]) + 1e-300))) return; // edge-on or degenerate
     o.valid = 1;
-    const double inv = 1.0 / det, S = a.S;
-    {
-        const bool front = ve[0][2] > 1e-6 && ve[1][2] > 1e-6 && ve[2][2] > 1e-6;
-        o.clipped = !(ve[0][2] >= a.near_ && ve[1][2] >= a.near_ && ve[2][2] >= a.near_) || ve[0][2] > a.far_ || ve[1][2] > a.far_ || ve[2][2] > a.far_;
-        o.c_lo = 0.f; o.c_hi = (float)(S - 1); o.r_lo = 0.f; o.r_hi = (float)(S - 1);
-        if (front) {
-            double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const double x = ve[k][0] / (ve[k][2] * a.th), y = ve[k][1] / (ve[k][2] * a.th);
-                xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
-            }
-            // pixel c has x_ndc = (2c+1)/S - 1; pad by one pixel
-            o.c_lo = (float)((xmin + 1) * 0.5 * S - 0.5 - 1.0); o.c_hi = (float)((xmax + 1) * 0.5 * S - 0.5 + 1.0);
-            o.r_lo = (float)((1 - ymax) * 0.5 * S - 0.5 - 1.0); o.r_hi = (float)((1 - ymin) * 0.5 * S - 0.5 + 1.0);
-        }
-    }
-    // b_i = r_i.x dx + r_i.y dy + r_i.z with dx = th ((2c+1)/S - 1), dy = th (1 - (2r+1)/S)
+    // d = (dx, dy, 1), dx = th ((2c+1)/S - 1), dy = th (1 - (2r+1)/S): a row vector g . d becomes A c + B r + C
     const double kx = a.th * 2.0 / S, x0 = a.th * (1.0 / S - 1.0), y0 = a.th * (1.0 - 1.0 / S);
-    const double* rows[3] = {c0, c1, c2};
-    o.eA[3] = o.eB[3] = o.eC[3] = 0.0;
-    float mg = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const double rx = rows[i][0] * inv, ry = rows[i][1] * inv, rz = rows[i][2] * inv;
-        o.eA[i] = rx * kx; o.eB[i] = -ry * kx; o.eC[i] = rx * x0 + ry * y0 + rz;
-        o.eA[3] += o.eA[i]; o.eB[3] += o.eB[i]; o.eC[3] += o.eC[i];
-    }
+    auto affine = [&](const double* g, double scale, int i) {
+        o.eA[i] = g[0] * scale * kx; o.eB[i] = -g[1] * scale * kx; o.eC[i] = (g[0] * x0 + g[1] * y0 + g[2]) * scale;
+    };
+    affine(nrm, 1.0 / nd0, 4);
+    double cen[3] = {0, 0, 0};
+    for (int k = 0; k < nv; k++) { cen[0] += ve[k][0]; cen[1] += ve[k][1]; cen[2] += ve[k][2]; }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
+        if (i < nv) {
+            const double* p = ve[i];
+            const double* q = ve[i + 1 < nv ? i + 1 : 0];
+            double g[3] = {p[1] * q[2] - p[2] * q[1], p[2] * q[0] - p[0] * q[2], p[0] * q[1] - p[1] * q[0]};
+            const double sgn = (g[0] * cen[0] + g[1] * cen[1] + g[2] * cen[2]) >= 0 ? 1.0 : -1.0;
+            const double gl = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+            affine(g, gl > 0 ? sgn / gl : 0.0, i);
+        } else { o.eA[i] = 0; o.eB[i] = 0; o.eC[i] = 1.0; } // unused edge slot: always inside
+    }
+    float mg = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
         o.fA[i] = (float)o.eA[i]; o.fB[i] = (float)o.eB[i]; o.fC[i] = (float)o.eC[i];
-        mg = fmaxf(mg, (float)((fabs(o.eA[i]) + fabs(o.eB[i])) * S + fabs(o.eC[i])));
+        if (i < nv || i == 4) mg = fmaxf(mg, (float)((fabs(o.eA[i]) + fabs(o.eB[i])) * S + fabs(o.eC[i])));
     }
     o.margin = mg * 2e-6f;
-}
-
-// exact (fp64) inside test with the oracle's tolerance: lambda_i >= -1e-12, w > 0
-__device__ __noinline__ bool inside_exact(const TriCoef& t, int c, int r)
-{
-    const double b0 = t.eA[0] * c + t.eB[0] * r + t.eC[0];
-    const double b1 = t.eA[1] * c + t.eB[1] * r + t.eC[1];
-    const double b2 = t.eA[2] * c + t.eB[2] * r + t.eC[2];
-    const double w = b0 + b1 + b2;
-    const double tol = -1e-12 * w;
-    return w > 0.0 && b0 >= tol && b1 >= tol && b2 >= tol;
-}
-
-// rare path: the nearest covering triangle is in front of the near plane -> GL clips it and the next one shows
-__device__ __noinline__ double slow_pixel(const TriCoef* tc, int ntri, int c, int r, double w_near, double w_far)
-{
-    double best = 0.0;
-    for (int t = 0; t < ntri; t++) {
-        if (!tc[t].valid || !inside_exact(tc[t], c, r)) continue;
-        const double w = tc[t].eA[3] * c + tc[t].eB[3] * r + tc[t].eC[3];
-        if (w <= w_near && w >= w_far && w > best) best = w;
+    const double Fn = a.F * a.near_;
+    o.vA = (float)(5100.0 * Fn * o.eA[4]); o.vB = (float)(5100.0 * Fn * o.eB[4]); o.vC = (float)(5100.0 * (Fn * o.eC[4] - a.F + (double)a.nd_ref));
+    bool front = true, clipped = false;
+    for (int k = 0; k < nv; k++) {
+        if (!(ve[k][2] > 1e-6)) front = false;
+        if (!(ve[k][2] >= a.near_) || ve[k][2] > a.far_) clipped = true;
     }
-    return best;
+    o.clipped = clipped;
+    o.c_lo = 0.f; o.c_hi = (float)(S - 1); o.r_lo = 0.f; o.r_hi = (float)(S - 1);
+    if (front) {
+        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+        for (int k = 0; k < nv; k++) {
+            const double x = ve[k][0] / (ve[k][2] * a.th), y = ve[k][1] / (ve[k][2] * a.th);
+            xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+        }
+        o.c_lo = (float)((xmin + 1) * 0.5 * S - 0.5 - 1.0); o.c_hi = (float)((xmax + 1) * 0.5 * S - 0.5 + 1.0);
+        o.r_lo = (float)((1 - ymax) * 0.5 * S - 0.5 - 1.0); o.r_hi = (float)((1 - ymin) * 0.5 * S - 0.5 + 1.0);
+    }
+}
+
+// exact (fp64) coverage: all edge functions >= -1e-12 (they are normalised to unit gradient), in front of the eye
+__device__ __forceinline__ bool inside_exact(const PrimCoef& t, int c, int r, double& w)
+{
+    w = t.eA[4] * c + t.eB[4] * r + t.eC[4];
+    bool in = w > 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) in = in && (t.eA[i] * c + t.eB[i] * r + t.eC[i] >= -1e-12);
+    return in;
 }
 
 // t_s_camera's float32 arithmetic (tactile_sensor.py:268-284).  uint8(((clip(pen, 0, 0.05) / 0.05) * 255)):
@@ -168,6 +177,23 @@ __device__ __forceinline__ uint32_t quantize(float cur, float nd)
     return (uint32_t)__float2uint_rz(__fmul_rn(q, 255.0f));
 }
 
+// the oracle's arithmetic for one pixel: nearest covering primitive in fp64, GL near/far clipping, float32 post-process
+__device__ __noinline__ uint32_t exact_pixel(const RasterArgs& a, const PrimCoef* pc, int c, int r, float nd, uint32_t basev)
+{
+    if (nd < 0.0f) return basev;
+    const double w_near = 1.0 / a.near_, w_far = 1.0 / a.far_;
+    double best = 0.0;
+    for (int t = 0; t < a.nprim; t++) {
+        if (!pc[t].valid) continue;
+        double w;
+        if (!inside_exact(pc[t], c, r, w)) continue;
+        if (w <= w_near && w >= w_far && w > best) best = w;
+    }
+    if (best <= 0.0) return 0u;
+    const float d = (float)(a.F - a.F * a.near_ * best);
+    return quantize(fminf(nd, d), nd);
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS)
 raster_kernel(const RasterArgs a)
 {
@@ -175,8 +201,16 @@ raster_kernel(const RasterArgs a)
     const int S = a.S, band_rows = S / a.bands, band_px = band_rows * S;
     float* s_nodef = reinterpret_cast<float*>(smem_raw);
     uint8_t* s_base = smem_raw + (size_t)band_px * 4;
+    uint32_t* s_skin = reinterpret_cast<uint32_t*>(smem_raw + (size_t)band_px * 5); // 1 bit per 16-px span: has a non-border pixel
+    const int n_spans = band_px / 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TriCoef* tc = reinterpret_cast<TriCoef*>(smem_raw + (size_t)band_px * 5) + warp * a.ntri; // this warp's equations
+    unsigned char* wbase = smem_raw + (size_t)band_px * 5 + (size_t)((n_spans + 31) / 32) * 4;
+    wbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wbase) + 15) & ~uintptr_t(15));
+    const size_t per_warp = sizeof(PrimCoef) * RASTER_MAXPRIM + sizeof(SpanEntry) * SPAN_LIST + sizeof(uint16_t) * EXACT_QUEUE + 16;
+    PrimCoef* pc = reinterpret_cast<PrimCoef*>(wbase + per_warp * warp);
+    SpanEntry* s_list = reinterpret_cast<SpanEntry*>(pc + RASTER_MAXPRIM);
+    uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_list + SPAN_LIST);
+    int* s_qcnt = reinterpret_cast<int*>(s_queue + EXACT_QUEUE);
     const int tiles_x = S / TILE_COLS, tiles_y = band_rows / TILE_ROWS, n_tiles = tiles_x * tiles_y; // <= 32
     __shared__ __align__(8) uint64_t bar;
 
@@ -203,40 +237,125 @@ raster_kernel(const RasterArgs a)
                          : "memory");
         }
     }
+    // span skin bitmap (once per CTA)
+    for (int w0 = threadIdx.x; w0 < (n_spans + 31) / 32; w0 += RASTER_THREADS) {
+        uint32_t bits = 0;
+        for (int j = 0; j < 32 && w0 * 32 + j < n_spans; j++) {
+            const float* p = s_nodef + (size_t)(w0 * 32 + j) * 16;
+            bool skin = false;
+            for (int k = 0; k < 16; k++) skin = skin || (p[k] >= 0.0f);
+            bits |= (skin ? 1u : 0u) << j;
+        }
+        s_skin[w0] = bits;
+    }
+    __syncthreads();
 
-    const double w_near = 1.0 / a.near_, w_far = 1.0 / a.far_;
-    const double Fn = a.F * a.near_;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int any_clipped = 0; // set per env: a primitive crosses the near/far planes -> the float path does not apply
+
+    // shade one listed span (this lane's), float fast path; uncertain pixels go to the exact queue
+    auto shade = [&](const SpanEntry en, uint8_t* obs_e) {
+        const int off = (int)en.off16 * 16;
+        const int lr = off / S, c0 = off - lr * S, r = row0 + lr;
+        const float fr = (float)r, fc0 = (float)c0;
+        float vb[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) vb[k] = -1e30f;
+        uint32_t unc = 0; // pixels whose coverage is within the float margin of an edge
+        uint32_t m = en.in_m;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            const float vA = pc[t].vA, v0 = fmaf(vA, fc0, fmaf(pc[t].vB, fr, pc[t].vC));
+#pragma unroll
+            for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], fmaf(vA, (float)k, v0));
+        }
+        m = en.part_m;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            const PrimCoef& c = pc[t];
+            const float mg = c.margin;
+            float a0[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++) a0[i] = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i]));
+            const float vA = c.vA, v0 = fmaf(vA, fc0, fmaf(c.vB, fr, c.vC));
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const float fk = (float)k;
+                const float lo = fminf(fminf(fmaf(c.fA[0], fk, a0[0]), fmaf(c.fA[1], fk, a0[1])),
+                                       fminf(fminf(fmaf(c.fA[2], fk, a0[2]), fmaf(c.fA[3], fk, a0[3])), fmaf(c.fA[4], fk, a0[4])));
+                if (lo > mg) vb[k] = fmaxf(vb[k], fmaf(vA, fk, v0));
+                else if (lo >= -mg) unc |= 1u << k;
+            }
+        }
+        float nd[16];
+        {
+            const float4* p = reinterpret_cast<const float4*>(s_nodef + off);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 v = p[k];
+                nd[4 * k] = v.x; nd[4 * k + 1] = v.y; nd[4 * k + 2] = v.z; nd[4 * k + 3] = v.w;
+            }
+        }
+        const uint4 bres = *reinterpret_cast<const uint4*>(s_base + off);
+        uint32_t wds[4] = {bres.x, bres.y, bres.z, bres.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            // val = 5100 (nodef - d).  nodef - nd_ref is exact (Sterbenz); uncovered pixels have vb = -1e30 -> 0;
+            // border pixels (nd = -1) are excluded explicitly
+            const float val = nd[k] >= 0.0f ? fmaf(nd[k] - a.nd_ref, VAL_SCALE, vb[k]) : -1e30f;
+            const float cl = fminf(fmaxf(val, 0.0f), 255.0f);
+            const uint32_t u = __float2uint_rz(cl);
+            // quantisation step within the error bound?  (val in (-B, 255 + B) and |val - round(val)| < B)
+            if (fabsf(val - rintf(val)) < VAL_BOUND && val > -VAL_BOUND && val < 255.0f + VAL_BOUND) unc |= 1u << k;
+            wds[k >> 2] |= u << (8 * (k & 3));
+        }
+        *reinterpret_cast<uint4*>(obs_e + off) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        if (any_clipped) unc = 0xffffu; // near/far clipping in play: every pixel of the span takes the exact path
+        while (unc) {
+            const int k = __ffs(unc) - 1;
+            unc &= unc - 1;
+            if (nd[k] >= 0.0f) {
+                const int pos = atomicAdd(s_qcnt, 1);
+                if (pos < EXACT_QUEUE) s_queue[pos] = (uint16_t)(off + k);
+                else { // queue full (pathological): patch right away
+                    atomicSub(s_qcnt, 1);
+                    obs_e[off + k] = (uint8_t)exact_pixel(a, pc, c0 + k, r, nd[k], 0u);
+                }
+            }
+        }
+    };
 
     // one env image (band slice) per warp iteration
     for (int e = lane_cta * RASTER_WARPS + warp; e < a.n; e += n_cta * RASTER_WARPS) {
         if (a.mask && !a.mask[e]) continue;
         __syncwarp();
-        if (lane < a.ntri) tri_setup(a, a.cam + (size_t)e * 12, a.stim + (size_t)e * 12, a.tris + 9 * lane, tc[lane]);
+        if (lane == 0) *s_qcnt = 0;
+        if (lane < a.nprim) prim_setup(a, a.cam + (size_t)e * 12, a.stim + (size_t)e * 12, a.prims + 12 * lane, a.prim_nv[lane], pc[lane]);
         __syncwarp();
-        // tile classification: lane = tile.  A triangle is dropped for a tile when its screen bbox misses it, when
-        // one edge function is negative at all four corner pixels, or when a triangle that covers the whole
-        // tile is nearer at all four corners (both 1/z are affine, so nearer everywhere: exact occlusion cull).
+        // ---- tile classification: lane = tile (bbox reject, corner tests, exact occlusion cull)
         uint32_t my_in = 0, my_part = 0;
-        int any_clipped = 0;
-        for (int t = 0; t < a.ntri; t++) any_clipped |= tc[t].valid & tc[t].clipped;
+        any_clipped = 0;
+        for (int t = 0; t < a.nprim; t++) any_clipped |= pc[t].valid & pc[t].clipped;
         if (lane < n_tiles) {
             const float cl = (float)((lane % tiles_x) * TILE_COLS), ch = cl + (TILE_COLS - 1);
             const float rl = (float)(row0 + (lane / tiles_x) * TILE_ROWS), rh = rl + (TILE_ROWS - 1);
-            float dom[4] = {-1e30f, -1e30f, -1e30f, -1e30f}; // certified lower bound of 1/z of the nearest covering triangle
+            float dom[4] = {-1e30f, -1e30f, -1e30f, -1e30f}; // certified lower bound of 1/z of the nearest covering primitive
             int dom_t = -1;
-            for (int t = 0; t < a.ntri; t++) {
-                const TriCoef& c = tc[t];
+            for (int t = 0; t < a.nprim; t++) {
+                const PrimCoef& c = pc[t];
                 if (!c.valid || c.c_hi < cl || c.c_lo > ch || c.r_hi < rl || c.r_lo > rh) continue;
                 bool all_in = true, out = false;
                 float wv[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 0; k < 5; k++) {
                     const float kl = fmaf(c.fB[k], rl, c.fC[k]), kh = fmaf(c.fB[k], rh, c.fC[k]);
                     const float v00 = fmaf(c.fA[k], cl, kl), v01 = fmaf(c.fA[k], ch, kl), v10 = fmaf(c.fA[k], cl, kh), v11 = fmaf(c.fA[k], ch, kh);
                     const float lo = fminf(fminf(v00, v01), fminf(v10, v11)), hi = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
                     all_in = all_in && (lo > c.margin);
                     out = out || (hi < -c.margin);
-                    if (k == 3) { wv[0] = v00; wv[1] = v01; wv[2] = v10; wv[3] = v11; }
+                    if (k == 4) { wv[0] = v00; wv[1] = v01; wv[2] = v10; wv[3] = v11; }
                 }
                 if (out) continue;
                 if (all_in) {
@@ -248,115 +367,80 @@ raster_kernel(const RasterArgs a)
                     }
                 } else my_part |= 1u << t;
             }
-            if (my_in && !any_clipped) {
-                // second pass: drop everything the dominating in-triangle hides
+            if (dom_t >= 0) {
+                // drop everything the dominating covering primitive hides (1/z affine: nearer at 4 corners = nearer everywhere)
                 uint32_t keep_in = 0, keep_part = 0, cand = my_in | my_part;
                 while (cand) {
                     const int t = __ffs(cand) - 1;
                     cand &= cand - 1;
-                    const TriCoef& c = tc[t];
-                    const float kl = fmaf(c.fB[3], rl, c.fC[3]), kh = fmaf(c.fB[3], rh, c.fC[3]);
-                    const float w0 = fmaf(c.fA[3], cl, kl) + c.margin, w1 = fmaf(c.fA[3], ch, kl) + c.margin;
-                    const float w2 = fmaf(c.fA[3], cl, kh) + c.margin, w3 = fmaf(c.fA[3], ch, kh) + c.margin;
+                    const PrimCoef& c = pc[t];
+                    const float kl = fmaf(c.fB[4], rl, c.fC[4]), kh = fmaf(c.fB[4], rh, c.fC[4]);
+                    const float w0 = fmaf(c.fA[4], cl, kl) + c.margin, w1 = fmaf(c.fA[4], ch, kl) + c.margin;
+                    const float w2 = fmaf(c.fA[4], cl, kh) + c.margin, w3 = fmaf(c.fA[4], ch, kh) + c.margin;
                     const bool hidden = w0 < dom[0] && w1 < dom[1] && w2 < dom[2] && w3 < dom[3];
-                    const bool is_dom = t == dom_t;
-                    if (!hidden || is_dom) { if ((my_in >> t) & 1u) keep_in |= 1u << t; else keep_part |= 1u << t; }
+                    if (!hidden || t == dom_t) { if ((my_in >> t) & 1u) keep_in |= 1u << t; else keep_part |= 1u << t; }
                 }
                 my_in = keep_in; my_part = keep_part;
             }
         }
         uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
-        uint8_t* term_e = a.term_obs ? a.term_obs + (size_t)e * S * S + (size_t)row0 * S : nullptr;
+        int cnt = 0; // entries in the span list (warp-uniform)
+        // ---- BIN: copy the baked row, list the spans that need shading
         for (int tile = 0; tile < n_tiles; tile++) {
-            uint32_t in_m = __shfl_sync(0xffffffffu, my_in, tile), part_m = __shfl_sync(0xffffffffu, my_part, tile);
+            const uint32_t in_m = __shfl_sync(0xffffffffu, my_in, tile), part_m = __shfl_sync(0xffffffffu, my_part, tile);
             const int lr = (tile / tiles_x) * TILE_ROWS + (lane >> 2), c0 = (tile % tiles_x) * TILE_COLS + (lane & 3) * 16;
-            const int r = row0 + lr, off = lr * S + c0;
-            if (term_e) *reinterpret_cast<uint4*>(term_e + off) = *reinterpret_cast<const uint4*>(obs_e + off);
-            uint4 res = *reinterpret_cast<const uint4*>(s_base + off);
-            if (in_m | part_m) {
-                double best[16]; // largest 1/z_eye over covering triangles, 0 = none
-                if (part_m == 0 && (in_m & (in_m - 1)) == 0) {
-                    // one triangle covers the whole tile and nothing else survives: one DFMA per pixel
-                    const int t = __ffs(in_m) - 1;
-                    const double wA = tc[t].eA[3];
-                    const double w0 = wA * c0 + (tc[t].eB[3] * r + tc[t].eC[3]);
+            const int off = lr * S + c0, span = off >> 4;
+            *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(s_base + off);
+            if ((in_m | part_m) == 0) continue;
+            const bool skin = (s_skin[span >> 5] >> (span & 31)) & 1u;
+            uint32_t sp_in = in_m, sp_part = 0;
+            if (skin && part_m) {
+                const float fr = (float)(row0 + lr), fc0 = (float)c0;
+                uint32_t m = part_m;
+                while (m) {
+                    const int t = __ffs(m) - 1;
+                    m &= m - 1;
+                    const PrimCoef& c = pc[t];
+                    float lo = 1e30f, hx = 1e30f;
 #pragma unroll
-                    for (int k = 0; k < 16; k++) best[k] = wA * k + w0;
-                    in_m = 0;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) best[k] = 0.0;
-                }
-                while (in_m) {
-                    const int t = __ffs(in_m) - 1;
-                    in_m &= in_m - 1;
-                    const double wA = tc[t].eA[3];
-                    const double w0 = wA * c0 + (tc[t].eB[3] * r + tc[t].eC[3]);
-#pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        const double w = wA * k + w0;
-                        if (w > best[k]) best[k] = w;
+                    for (int i = 0; i < 5; i++) {
+                        const float a0 = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i])), z0 = fmaf(c.fA[i], 15.0f, a0);
+                        lo = fminf(lo, fminf(a0, z0));
+                        hx = fminf(hx, fmaxf(a0, z0));
                     }
+                    if (hx < -c.margin) continue;         // one function is negative over the whole span
+                    if (lo > c.margin) sp_in |= 1u << t;  // span fully inside
+                    else sp_part |= 1u << t;
                 }
-                while (part_m) {
-                    const int t = __ffs(part_m) - 1;
-                    part_m &= part_m - 1;
-                    const TriCoef& c = tc[t];
-                    const float fr = (float)r, fc0 = (float)c0, mg = c.margin;
-                    const float k0 = fmaf(c.fB[0], fr, c.fC[0]), k1 = fmaf(c.fB[1], fr, c.fC[1]);
-                    const float k2 = fmaf(c.fB[2], fr, c.fC[2]), k3 = fmaf(c.fB[3], fr, c.fC[3]);
-                    // span classification from its two end pixels
-                    const float a0 = fmaf(c.fA[0], fc0, k0), a1 = fmaf(c.fA[1], fc0, k1), a2 = fmaf(c.fA[2], fc0, k2), a3 = fmaf(c.fA[3], fc0, k3);
-                    const float z0 = fmaf(c.fA[0], 15.0f, a0), z1 = fmaf(c.fA[1], 15.0f, a1), z2 = fmaf(c.fA[2], 15.0f, a2), z3 = fmaf(c.fA[3], 15.0f, a3);
-                    const float lo = fminf(fminf(fminf(a0, z0), fminf(a1, z1)), fminf(fminf(a2, z2), fminf(a3, z3)));
-                    const float hx = fminf(fminf(fmaxf(a0, z0), fmaxf(a1, z1)), fminf(fmaxf(a2, z2), fmaxf(a3, z3)));
-                    if (hx < -mg) continue; // some function is negative over the whole span
-                    const double wA = c.eA[3];
-                    const double w0 = wA * c0 + (c.eB[3] * r + c.eC[3]);
-                    if (lo > mg) {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const double w = wA * k + w0;
-                            if (w > best[k]) best[k] = w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const float fk = (float)k;
-                            const float m = fminf(fminf(fmaf(c.fA[0], fk, a0), fmaf(c.fA[1], fk, a1)), fminf(fmaf(c.fA[2], fk, a2), fmaf(c.fA[3], fk, a3)));
-                            bool in = m > mg;
-                            if (!in && m >= -mg) in = inside_exact(c, c0 + k, r);
-                            const double w = wA * k + w0;
-                            if (in && w > best[k]) best[k] = w;
-                        }
-                    }
-                }
-                float nd[16];
-                {
-                    const float4* p = reinterpret_cast<const float4*>(s_nodef + off);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const float4 v = p[k];
-                        nd[4 * k] = v.x; nd[4 * k + 1] = v.y; nd[4 * k + 2] = v.z; nd[4 * k + 3] = v.w;
-                    }
-                }
-                uint32_t wds[4] = {res.x, res.y, res.z, res.w};
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    // closer than the near plane (never happens for a stimulus under the skin) is clipped like GL does
-                    if (any_clipped) {
-                        if (best[k] > w_near) best[k] = slow_pixel(tc, a.ntri, c0 + k, r, w_near, w_far);
-                        if (best[k] < w_far) best[k] = 0.0;
-                    }
-                    if (best[k] > 0.0 && nd[k] >= 0.0f) {
-                        const float d = (float)(a.F - Fn * best[k]);
-                        const uint32_t qv = quantize(fminf(nd[k], d), nd[k]);
-                        wds[k >> 2] |= qv << (8 * (k & 3)); // non-border pixels have base == 0
-                    }
-                }
-                res = make_uint4(wds[0], wds[1], wds[2], wds[3]);
             }
-            *reinterpret_cast<uint4*>(obs_e + off) = res;
+            const bool active = skin && (sp_in | sp_part);
+            const uint32_t bal = __ballot_sync(0xffffffffu, active);
+            if (active) {
+                SpanEntry en;
+                en.off16 = (uint16_t)span; en.in_m = (uint16_t)sp_in; en.part_m = (uint16_t)sp_part; en.pad = 0;
+                s_list[cnt + __popc(bal & lt_mask)] = en;
+            }
+            cnt += __popc(bal);
+            __syncwarp();
+            if (cnt >= 32) {
+                // ---- SHADE a full batch of 32 spans
+                const SpanEntry en = s_list[lane];
+                const SpanEntry tail = s_list[32 + lane];
+                __syncwarp();
+                shade(en, obs_e);
+                if (lane < cnt - 32) s_list[lane] = tail;
+                cnt -= 32;
+                __syncwarp();
+            }
+        }
+        if (lane < cnt) shade(s_list[lane], obs_e);
+        __syncwarp();
+        // ---- EXACT PATCH-UP of the queued pixels
+        const int qn = min(*s_qcnt, EXACT_QUEUE);
+        for (int i = lane; i < qn; i += 32) {
+            const int off = s_queue[i];
+            const int lr = off / S, c = off - lr * S;
+            obs_e[off] = (uint8_t)exact_pixel(a, pc, c, row0 + lr, s_nodef[off], s_base[off]);
         }
     }
 }

@@ -77,8 +77,8 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->arm.topo == TG_TOPO_MG400) return fail(TG_EUNSUPPORTED, "MG400 topology: velocity control path not built yet");
     if (cfg->arm.topo != TG_TOPO_CHAIN6) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
     if (cfg->task.task != TG_TASK_EDGE_FOLLOW) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
-    if (cfg->sensor.n_tri <= 0 || cfg->sensor.n_tri > 32) return fail(TG_EINVAL, "n_tri must be in 1..32");
-    if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->sensor.h_tris || !cfg->h_rest_q)
+    if (cfg->sensor.n_prim <= 0 || cfg->sensor.n_prim > RASTER_MAXPRIM) return fail(TG_EINVAL, "n_prim must be in 1..%d", RASTER_MAXPRIM);
+    if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->sensor.h_prims || !cfg->sensor.h_prim_nv || !cfg->h_rest_q)
         return fail(TG_EINVAL, "null table pointer in config");
     CK(cudaSetDevice(device));
 
@@ -137,19 +137,28 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             nd[i] = border ? -1.0f : cfg->sensor.h_nodef_dep[i];
             base[i] = border ? (uint8_t)cfg->sensor.h_nodef_gray[i] : 0;
         }
-        float* dn; uint8_t* db; double* dt;
-        if ((rc = dalloc(w, &dn, px)) || (rc = dalloc(w, &db, px)) || (rc = dalloc(w, &dt, (size_t)cfg->sensor.n_tri * 9))) { tg_destroy(w); return rc; }
+        float* dn; uint8_t* db; double* dt; int* dnv;
+        const int np = cfg->sensor.n_prim;
+        for (int i = 0; i < np; i++)
+            if (cfg->sensor.h_prim_nv[i] != 3 && cfg->sensor.h_prim_nv[i] != 4) { tg_destroy(w); return fail(TG_EINVAL, "primitive %d has %d vertices", i, cfg->sensor.h_prim_nv[i]); }
+        if ((rc = dalloc(w, &dn, px)) || (rc = dalloc(w, &db, px)) || (rc = dalloc(w, &dt, (size_t)np * 12)) || (rc = dalloc(w, &dnv, np))) { tg_destroy(w); return rc; }
         CK(cudaMemcpy(dn, nd.data(), px * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(db, base.data(), px, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dt, cfg->sensor.h_tris, sizeof(double) * 9 * cfg->sensor.n_tri, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dt, cfg->sensor.h_prims, sizeof(double) * 12 * np, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dnv, cfg->sensor.h_prim_nv, sizeof(int) * np, cudaMemcpyHostToDevice));
+        float ndmin = 1e30f, ndmax = -1e30f;
+        for (size_t i = 0; i < px; i++) if (nd[i] >= 0.0f) { ndmin = std::min(ndmin, nd[i]); ndmax = std::max(ndmax, nd[i]); }
         RasterArgs& r = w->ra;
-        r.n = n; r.S = S; r.bands = S == 256 ? 4 : 1; r.ntri = cfg->sensor.n_tri;
+        r.nd_ref = ndmin <= ndmax ? 0.5f * (ndmin + ndmax) : 0.5f;
+        if (ndmin <= ndmax && !(ndmin >= 0.5f * r.nd_ref && ndmax <= 2.0f * r.nd_ref)) { tg_destroy(w); return fail(TG_EUNSUPPORTED, "nodef_dep range [%g, %g] too wide for the float path", ndmin, ndmax); }
+        r.n = n; r.S = S; r.bands = S == 256 ? 4 : 1; r.nprim = np; r.prim_nv = dnv;
         r.th = tan(cfg->sensor.fov_deg * (M_PI / 180.0) / 2.0);
         r.near_ = cfg->sensor.near_; r.far_ = cfg->sensor.far_;
         r.F = cfg->sensor.far_ / (cfg->sensor.far_ - cfg->sensor.near_);
-        r.nodef = dn; r.base = db; r.tris = dt; r.cam = b.cam; r.stim = b.stim; r.mask = nullptr; r.obs = nullptr; r.term_obs = nullptr;
+        r.nodef = dn; r.base = db; r.prims = dt; r.cam = b.cam; r.stim = b.stim; r.mask = nullptr; r.obs = nullptr;
         const size_t band_px = px / r.bands;
-        w->raster_smem = band_px * 5 + sizeof(TriCoef) * RASTER_WARPS * r.ntri;
+        const size_t per_warp = sizeof(PrimCoef) * RASTER_MAXPRIM + sizeof(SpanEntry) * SPAN_LIST + sizeof(uint16_t) * EXACT_QUEUE + 16;
+        w->raster_smem = band_px * 5 + ((band_px / 16 + 31) / 32) * 4 + 16 + per_warp * RASTER_WARPS;
         CK(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->raster_smem));
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel, RASTER_THREADS, w->raster_smem));
@@ -220,10 +229,10 @@ extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)
 
 static dim3 env_grid(const TgWorld* w) { return dim3(w->eb.step_blocks); } // 128 threads = 4 warps = 4 * lanes envs
 
-static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, uint8_t* term, cudaStream_t st, bool terminal_state = false)
+static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaStream_t st, bool terminal_state = false)
 {
     RasterArgs r = w->ra;
-    r.obs = d_obs; r.mask = mask; r.term_obs = term;
+    r.obs = d_obs; r.mask = mask;
     if (terminal_state) { r.cam = w->eb.term_cam; r.stim = w->eb.term_stim; }
     raster_kernel<<<w->raster_grid, RASTER_THREADS, w->raster_smem, st>>>(r);
     w->launches++;
@@ -254,7 +263,7 @@ extern "C" int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void*
     CK(cudaSetDevice(w->device));
     int rc;
     if ((rc = launch_reset(w, d_mask, (cudaStream_t)stream))) return rc;
-    return launch_raster(w, d_obs, d_mask, nullptr, (cudaStream_t)stream);
+    return launch_raster(w, d_obs, d_mask, (cudaStream_t)stream);
 }
 
 extern "C" int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream)
@@ -273,14 +282,15 @@ extern "C" int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float
     if (w->eb.pipeline) {
         // finished envs swap their standby start-of-episode state in inside step_kernel: 2 launches per step
         if ((rc = launch_step(w, d_actions, d_reward, d_done, 1, st))) return rc;
-        if ((rc = launch_raster(w, d_obs, nullptr, nullptr, st))) return rc;            // first obs of the new episode for done envs
-        if (d_term_obs) return launch_raster(w, d_term_obs, d_done, nullptr, st, true);  // their terminal obs, on request
+        if ((rc = launch_raster(w, d_obs, nullptr, st))) return rc;            // first obs of the new episode for done envs
+        if (d_term_obs) return launch_raster(w, d_term_obs, d_done, st, true);  // their terminal obs, on request
         return TG_OK;
     }
+    // sequential path (episodes shorter than 2 steps): terminal obs, reset, then every env's observation
     if ((rc = launch_step(w, d_actions, d_reward, d_done, 1, st))) return rc;
-    if ((rc = launch_raster(w, d_obs, nullptr, nullptr, st))) return rc;   // observation of every env (terminal one for done envs)
-    if ((rc = launch_reset(w, d_done, st))) return rc;                      // finished envs start their next episode
-    return launch_raster(w, d_obs, d_done, d_term_obs, st);                 // ... and get its first observation
+    if (d_term_obs && (rc = launch_raster(w, d_term_obs, d_done, st))) return rc;
+    if ((rc = launch_reset(w, d_done, st))) return rc;
+    return launch_raster(w, d_obs, nullptr, st);
 }
 
 extern "C" int tg_physics_only(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, void* stream)
@@ -294,7 +304,7 @@ extern "C" int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream)
 {
     if (!w || !d_obs) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
-    return launch_raster(w, d_obs, nullptr, nullptr, (cudaStream_t)stream);
+    return launch_raster(w, d_obs, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int tg_state_size(const TgWorld* w) { return w ? 2 * w->nb + 7 + 4 : 0; }

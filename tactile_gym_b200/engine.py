@@ -89,10 +89,12 @@ def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     s.h_nodef_dep = dep.ctypes.data_as(C.POINTER(C.c_float))
     s.h_nodef_gray = gray.ctypes.data_as(C.POINTER(C.c_float))
     s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
-    s.n_tri = len(tris)
-    s.h_tris = tris.ctypes.data_as(C.POINTER(C.c_double))
+    prims, prim_nv = scene.merge_coplanar(tris)
+    s.n_prim = len(prims)
+    s.h_prims = prims.ctypes.data_as(C.POINTER(C.c_double))
+    s.h_prim_nv = prim_nv.ctypes.data_as(C.POINTER(C.c_int32))
     cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
-    return cfg, (dep, gray, mask, tris, rest)
+    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv)
 
 
 class TactileWorld:

@@ -74,6 +74,64 @@ def load_stimulus(name):
     return np.ascontiguousarray(np.load(os.path.join(ASSETS, "stimuli", name + ".npz"))["tris"], dtype=np.float64)
 
 
+def merge_coplanar(tris, tol=1e-9):
+    """Stimulus triangles [T,3,3] -> convex planar primitives [P,4,3] + vertex counts [P].
+
+    Two triangles that share an edge, lie in one plane and whose union is a convex quadrilateral become one quad
+    (the OBJ quads of the box stimuli, fan-triangulated by the loader, come back as quads).  The union has the same
+    pixel coverage and the same plane, so the render is unchanged; the raster just sees half as many primitives.
+    """
+    tris = np.asarray(tris, dtype=np.float64)
+    used = np.zeros(len(tris), dtype=bool)
+    prims, nv = [], []
+
+    def normal(t):
+        n = np.cross(t[1] - t[0], t[2] - t[0])
+        l = np.linalg.norm(n)
+        return n / l if l > 0 else n
+
+    for i in range(len(tris)):
+        if used[i]:
+            continue
+        used[i] = True
+        a, na = tris[i], normal(tris[i])
+        quad = None
+        for j in range(i + 1, len(tris)):
+            if used[j]:
+                continue
+            b, nb = tris[j], normal(tris[j])
+            scale = max(np.abs(a).max(), 1e-12)
+            if np.linalg.norm(na - nb) > 1e-9 or abs(np.dot(na, b[0] - a[0])) > tol * max(scale, 1.0):
+                continue
+            # shared edge (as vertex pairs)
+            shared = [(p, q) for p in range(3) for q in range(3) if np.allclose(a[p], b[q], atol=tol, rtol=0)]
+            if len(shared) != 2:
+                continue
+            pa = [p for p, _ in shared]
+            qb = [q for _, q in shared]
+            oa = [p for p in range(3) if p not in pa][0]          # a's vertex not on the shared edge
+            ob = [q for q in range(3) if q not in qb][0]
+            # walk a's vertices in order, inserting b's free vertex between the two shared ones
+            k = (oa + 1) % 3
+            cand = np.array([a[oa], a[k], b[ob], a[(k + 1) % 3]])
+            # convex and consistently oriented?
+            ok = True
+            for m in range(4):
+                e1 = cand[(m + 1) % 4] - cand[m]
+                e2 = cand[(m + 2) % 4] - cand[(m + 1) % 4]
+                if np.dot(np.cross(e1, e2), na) <= 1e-14:
+                    ok = False
+            if ok:
+                quad = cand
+                used[j] = True
+                break
+        if quad is not None:
+            prims.append(quad); nv.append(4)
+        else:
+            prims.append(np.vstack([a, a[2:3]])); nv.append(3)
+    return np.ascontiguousarray(np.array(prims), dtype=np.float64), np.ascontiguousarray(np.array(nv), dtype=np.int32)
+
+
 def reduce_model(mj, sensor, cam_pos, cam_rpy):
     """Fold fixed joints; returns (TgArm, control_links)."""
     links = mj["links"]
