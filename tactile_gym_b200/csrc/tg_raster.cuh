@@ -30,15 +30,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/tactile_gym_b200.h"
 
 #define RASTER_THREADS 512
 #define RASTER_WARPS (RASTER_THREADS / 32)
 #define TILE_ROWS 8
 #define TILE_COLS 64
-#define RASTER_MAXPRIM 16
-#define SPAN_LIST 64   // per-warp compacted span list (entries)
-#define EXACT_QUEUE 96 // per-warp queue of pixels for the exact path
+#define RASTER_MAXPRIM 12
+#define SPAN_LIST 64   // per-warp compacted span lists (entries each; there are two)
+#define EXACT_QUEUE 640 // per-warp queue of pixels for the exact path (a shade batch adds <= 512; flushed above 128)
 #define VAL_SCALE 5100.0f // 255 / 0.05
 #define VAL_BOUND 1.0e-3f // proven bound on |float value - oracle value|
 
@@ -46,7 +48,9 @@ struct PrimCoef {
     double eA[5], eB[5], eC[5]; // fp64: E_i(c, r) = eA[i] c + eB[i] r + eC[i], i < 4 edges; index 4 = w = 1/z_eye
     float fA[5], fB[5], fC[5];  // float copies
     float vA, vB, vC;           // float: V(c, r) = 5100 (nd_ref - F + F near w(c, r))  -> val = 5100 (nodef - nd_ref) + V
-    float margin;               // bound on the float evaluation error of any of the five functions
+    float margin;               // bound on the float evaluation error of the edge functions
+    float wmargin;              // ... of w = 1/z_eye
+    int steep;                  // 1: V varies too fast for the float value bound -> its pixels take the exact path
     float c_lo, c_hi, r_lo, r_hi; // conservative screen bbox in pixel units
     int valid, clipped;         // clipped: a vertex is outside [near, far] -> per-pixel range checks needed
 };
@@ -72,6 +76,8 @@ struct SpanEntry {
     uint16_t part_m; // primitives crossing it
     uint16_t pad;
 };
+
+#define RASTER_PER_WARP_SMEM (sizeof(PrimCoef) * RASTER_MAXPRIM + sizeof(SpanEntry) * SPAN_LIST * 2 + sizeof(uint32_t) * EXACT_QUEUE + 16)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -130,11 +136,15 @@ __device__ __forceinline__ void prim_setup(const RasterArgs& a, const double* ca
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         o.fA[i] = (float)o.eA[i]; o.fB[i] = (float)o.eB[i]; o.fC[i] = (float)o.eC[i];
-        if (i < nv || i == 4) mg = fmaxf(mg, (float)((fabs(o.eA[i]) + fabs(o.eB[i])) * S + fabs(o.eC[i])));
+        if (i < nv) mg = fmaxf(mg, (float)((fabs(o.eA[i]) + fabs(o.eB[i])) * S + fabs(o.eC[i])));
     }
     o.margin = mg * 2e-6f;
+    o.wmargin = (float)((fabs(o.eA[4]) + fabs(o.eB[4])) * S + fabs(o.eC[4])) * 2e-6f;
     const double Fn = a.F * a.near_;
-    o.vA = (float)(5100.0 * Fn * o.eA[4]); o.vB = (float)(5100.0 * Fn * o.eB[4]); o.vC = (float)(5100.0 * (Fn * o.eC[4] - a.F + (double)a.nd_ref));
+    const double dvA = 5100.0 * Fn * o.eA[4], dvB = 5100.0 * Fn * o.eB[4], dvC = 5100.0 * (Fn * o.eC[4] - a.F + (double)a.nd_ref);
+    o.vA = (float)dvA; o.vB = (float)dvB; o.vC = (float)dvC;
+    // float evaluation of V: ~4 roundings at the magnitude of its terms; it must stay well inside VAL_BOUND
+    o.steep = ((fabs(dvA) + fabs(dvB)) * S + fabs(dvC)) * 2.4e-7 > 0.5 * VAL_BOUND;
     bool front = true, clipped = false;
     for (int k = 0; k < nv; k++) {
         if (!(ve[k][2] > 1e-6)) front = false;
@@ -178,13 +188,14 @@ __device__ __forceinline__ uint32_t quantize(float cur, float nd)
 }
 
 // the oracle's arithmetic for one pixel: nearest covering primitive in fp64, GL near/far clipping, float32 post-process
-__device__ __noinline__ uint32_t exact_pixel(const RasterArgs& a, const PrimCoef* pc, int c, int r, float nd, uint32_t basev)
+__device__ __forceinline__ uint32_t exact_pixel(const RasterArgs& a, const PrimCoef* pc, uint32_t cand, int c, int r, float nd, uint32_t basev)
 {
     if (nd < 0.0f) return basev;
     const double w_near = 1.0 / a.near_, w_far = 1.0 / a.far_;
     double best = 0.0;
-    for (int t = 0; t < a.nprim; t++) {
-        if (!pc[t].valid) continue;
+    while (cand) { // primitives that can touch this pixel's span (tile + span classification are conservative)
+        const int t = __ffs(cand) - 1;
+        cand &= cand - 1;
         double w;
         if (!inside_exact(pc[t], c, r, w)) continue;
         if (w <= w_near && w >= w_far && w > best) best = w;
@@ -204,12 +215,11 @@ raster_kernel(const RasterArgs a)
     uint32_t* s_skin = reinterpret_cast<uint32_t*>(smem_raw + (size_t)band_px * 5); // 1 bit per 16-px span: has a non-border pixel
     const int n_spans = band_px / 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem_raw + (size_t)band_px * 5 + (size_t)((n_spans + 31) / 32) * 4;
-    wbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wbase) + 15) & ~uintptr_t(15));
-    const size_t per_warp = sizeof(PrimCoef) * RASTER_MAXPRIM + sizeof(SpanEntry) * SPAN_LIST + sizeof(uint16_t) * EXACT_QUEUE + 16;
-    PrimCoef* pc = reinterpret_cast<PrimCoef*>(wbase + per_warp * warp);
+    const size_t wbase = ((size_t)band_px * 5 + (size_t)((n_spans + 31) / 32) * 4 + 15) & ~size_t(15);
+    const size_t per_warp = RASTER_PER_WARP_SMEM;
+    PrimCoef* pc = reinterpret_cast<PrimCoef*>(smem_raw + wbase + per_warp * warp);
     SpanEntry* s_list = reinterpret_cast<SpanEntry*>(pc + RASTER_MAXPRIM);
-    uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_list + SPAN_LIST);
+    uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_list + 2 * SPAN_LIST);
     int* s_qcnt = reinterpret_cast<int*>(s_queue + EXACT_QUEUE);
     const int tiles_x = S / TILE_COLS, tiles_y = band_rows / TILE_ROWS, n_tiles = tiles_x * tiles_y; // <= 32
     __shared__ __align__(8) uint64_t bar;
@@ -251,42 +261,49 @@ raster_kernel(const RasterArgs a)
     __syncthreads();
 
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const int sh_S = 31 - __clz(S), sh_tx = 31 - __clz(tiles_x); // S and tiles_x are powers of two
     int any_clipped = 0; // set per env: a primitive crosses the near/far planes -> the float path does not apply
+    SpanEntry* l_in = s_list;             // spans covered by whole primitives only
+    SpanEntry* l_pt = s_list + SPAN_LIST; // spans some primitive edge crosses
 
-    // shade one listed span (this lane's), float fast path; uncertain pixels go to the exact queue
-    auto shade = [&](const SpanEntry en, uint8_t* obs_e) {
+    // shade one listed span (this lane's): float fast path; uncertain pixels go to the exact queue
+    auto shade = [&](const SpanEntry en, uint8_t* obs_e, auto with_part) {
         const int off = (int)en.off16 * 16;
-        const int lr = off / S, c0 = off - lr * S, r = row0 + lr;
+        const int lr = off >> sh_S, c0 = off & (S - 1), r = row0 + lr;
         const float fr = (float)r, fc0 = (float)c0;
         float vb[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) vb[k] = -1e30f;
-        uint32_t unc = 0; // pixels whose coverage is within the float margin of an edge
+        uint32_t unc = 0; // pixels that need the exact path
         uint32_t m = en.in_m;
         while (m) {
             const int t = __ffs(m) - 1;
             m &= m - 1;
+            if (pc[t].steep) { unc = 0xffffu; continue; } // whole span covered by a steep primitive
             const float vA = pc[t].vA, v0 = fmaf(vA, fc0, fmaf(pc[t].vB, fr, pc[t].vC));
 #pragma unroll
             for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], fmaf(vA, (float)k, v0));
         }
-        m = en.part_m;
-        while (m) {
-            const int t = __ffs(m) - 1;
-            m &= m - 1;
-            const PrimCoef& c = pc[t];
-            const float mg = c.margin;
-            float a0[5];
+        if constexpr (decltype(with_part)::value) {
+            m = en.part_m;
+            while (m) {
+                const int t = __ffs(m) - 1;
+                m &= m - 1;
+                const PrimCoef& c = pc[t];
+                const float mg = c.margin, sc = c.margin / fmaxf(c.wmargin, 1e-30f); // w is compared on the edges' margin scale
+                const bool steep = c.steep;
+                float a0[5];
 #pragma unroll
-            for (int i = 0; i < 5; i++) a0[i] = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i]));
-            const float vA = c.vA, v0 = fmaf(vA, fc0, fmaf(c.vB, fr, c.vC));
+                for (int i = 0; i < 5; i++) a0[i] = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i]));
+                const float vA = c.vA, v0 = fmaf(vA, fc0, fmaf(c.vB, fr, c.vC));
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const float fk = (float)k;
-                const float lo = fminf(fminf(fmaf(c.fA[0], fk, a0[0]), fmaf(c.fA[1], fk, a0[1])),
-                                       fminf(fminf(fmaf(c.fA[2], fk, a0[2]), fmaf(c.fA[3], fk, a0[3])), fmaf(c.fA[4], fk, a0[4])));
-                if (lo > mg) vb[k] = fmaxf(vb[k], fmaf(vA, fk, v0));
-                else if (lo >= -mg) unc |= 1u << k;
+                for (int k = 0; k < 16; k++) {
+                    const float fk = (float)k;
+                    const float lo = fminf(fminf(fmaf(c.fA[0], fk, a0[0]), fmaf(c.fA[1], fk, a0[1])),
+                                           fminf(fminf(fmaf(c.fA[2], fk, a0[2]), fmaf(c.fA[3], fk, a0[3])), fmaf(c.fA[4], fk, a0[4]) * sc));
+                    if (lo > mg && !steep) vb[k] = fmaxf(vb[k], fmaf(vA, fk, v0));
+                    else if (lo >= -mg) unc |= 1u << k; // within the margin of an edge, or on a steep primitive
+                }
             }
         }
         float nd[16];
@@ -300,31 +317,42 @@ raster_kernel(const RasterArgs a)
         }
         const uint4 bres = *reinterpret_cast<const uint4*>(s_base + off);
         uint32_t wds[4] = {bres.x, bres.y, bres.z, bres.w};
+        uint32_t nd_skin = 0;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             // val = 5100 (nodef - d).  nodef - nd_ref is exact (Sterbenz); uncovered pixels have vb = -1e30 -> 0;
-            // border pixels (nd = -1) are excluded explicitly
-            const float val = nd[k] >= 0.0f ? fmaf(nd[k] - a.nd_ref, VAL_SCALE, vb[k]) : -1e30f;
-            const float cl = fminf(fmaxf(val, 0.0f), 255.0f);
-            const uint32_t u = __float2uint_rz(cl);
+            // border pixels (nd = -1) keep the baked byte
+            const bool skin = nd[k] >= 0.0f;
+            nd_skin |= (skin ? 1u : 0u) << k;
+            const float val = skin ? fmaf(nd[k] - a.nd_ref, VAL_SCALE, vb[k]) : -1e30f;
+            const uint32_t u = __float2uint_rz(fminf(fmaxf(val, 0.0f), 255.0f));
             // quantisation step within the error bound?  (val in (-B, 255 + B) and |val - round(val)| < B)
             if (fabsf(val - rintf(val)) < VAL_BOUND && val > -VAL_BOUND && val < 255.0f + VAL_BOUND) unc |= 1u << k;
             wds[k >> 2] |= u << (8 * (k & 3));
         }
         *reinterpret_cast<uint4*>(obs_e + off) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
         if (any_clipped) unc = 0xffffu; // near/far clipping in play: every pixel of the span takes the exact path
+        unc &= nd_skin;
+        const uint32_t cand = ((uint32_t)(en.in_m | en.part_m)) << 16;
         while (unc) {
             const int k = __ffs(unc) - 1;
             unc &= unc - 1;
-            if (nd[k] >= 0.0f) {
-                const int pos = atomicAdd(s_qcnt, 1);
-                if (pos < EXACT_QUEUE) s_queue[pos] = (uint16_t)(off + k);
-                else { // queue full (pathological): patch right away
-                    atomicSub(s_qcnt, 1);
-                    obs_e[off + k] = (uint8_t)exact_pixel(a, pc, c0 + k, r, nd[k], 0u);
-                }
-            }
+            s_queue[atomicAdd(s_qcnt, 1)] = cand | (uint32_t)(off + k);
         }
+    };
+
+    // EXACT PATCH-UP of the queued pixels (whole warp)
+    auto flush_queue = [&](uint8_t* obs_e) {
+        __syncwarp();
+        const int qn = *s_qcnt;
+        for (int i = lane; i < qn; i += 32) {
+            const uint32_t q = s_queue[i];
+            const int off = (int)(q & 0xffffu);
+            obs_e[off] = (uint8_t)exact_pixel(a, pc, q >> 16, off & (S - 1), row0 + (off >> sh_S), s_nodef[off], s_base[off]);
+        }
+        __syncwarp();
+        if (lane == 0) *s_qcnt = 0;
+        __syncwarp();
     };
 
     // one env image (band slice) per warp iteration
@@ -339,8 +367,8 @@ raster_kernel(const RasterArgs a)
         any_clipped = 0;
         for (int t = 0; t < a.nprim; t++) any_clipped |= pc[t].valid & pc[t].clipped;
         if (lane < n_tiles) {
-            const float cl = (float)((lane % tiles_x) * TILE_COLS), ch = cl + (TILE_COLS - 1);
-            const float rl = (float)(row0 + (lane / tiles_x) * TILE_ROWS), rh = rl + (TILE_ROWS - 1);
+            const float cl = (float)((lane & (tiles_x - 1)) * TILE_COLS), ch = cl + (TILE_COLS - 1);
+            const float rl = (float)(row0 + (lane >> sh_tx) * TILE_ROWS), rh = rl + (TILE_ROWS - 1);
             float dom[4] = {-1e30f, -1e30f, -1e30f, -1e30f}; // certified lower bound of 1/z of the nearest covering primitive
             int dom_t = -1;
             for (int t = 0; t < a.nprim; t++) {
@@ -353,16 +381,17 @@ raster_kernel(const RasterArgs a)
                     const float kl = fmaf(c.fB[k], rl, c.fC[k]), kh = fmaf(c.fB[k], rh, c.fC[k]);
                     const float v00 = fmaf(c.fA[k], cl, kl), v01 = fmaf(c.fA[k], ch, kl), v10 = fmaf(c.fA[k], cl, kh), v11 = fmaf(c.fA[k], ch, kh);
                     const float lo = fminf(fminf(v00, v01), fminf(v10, v11)), hi = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
-                    all_in = all_in && (lo > c.margin);
-                    out = out || (hi < -c.margin);
+                    const float mgk = k == 4 ? c.wmargin : c.margin;
+                    all_in = all_in && (lo > mgk);
+                    out = out || (hi < -mgk);
                     if (k == 4) { wv[0] = v00; wv[1] = v01; wv[2] = v10; wv[3] = v11; }
                 }
                 if (out) continue;
                 if (all_in) {
                     my_in |= 1u << t;
-                    if (!any_clipped && wv[0] - c.margin > dom[0]) {
+                    if (!any_clipped && wv[0] - c.wmargin > dom[0]) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) dom[k] = wv[k] - c.margin;
+                        for (int k = 0; k < 4; k++) dom[k] = wv[k] - c.wmargin;
                         dom_t = t;
                     }
                 } else my_part |= 1u << t;
@@ -375,8 +404,8 @@ raster_kernel(const RasterArgs a)
                     cand &= cand - 1;
                     const PrimCoef& c = pc[t];
                     const float kl = fmaf(c.fB[4], rl, c.fC[4]), kh = fmaf(c.fB[4], rh, c.fC[4]);
-                    const float w0 = fmaf(c.fA[4], cl, kl) + c.margin, w1 = fmaf(c.fA[4], ch, kl) + c.margin;
-                    const float w2 = fmaf(c.fA[4], cl, kh) + c.margin, w3 = fmaf(c.fA[4], ch, kh) + c.margin;
+                    const float w0 = fmaf(c.fA[4], cl, kl) + c.wmargin, w1 = fmaf(c.fA[4], ch, kl) + c.wmargin;
+                    const float w2 = fmaf(c.fA[4], cl, kh) + c.wmargin, w3 = fmaf(c.fA[4], ch, kh) + c.wmargin;
                     const bool hidden = w0 < dom[0] && w1 < dom[1] && w2 < dom[2] && w3 < dom[3];
                     if (!hidden || t == dom_t) { if ((my_in >> t) & 1u) keep_in |= 1u << t; else keep_part |= 1u << t; }
                 }
@@ -384,63 +413,69 @@ raster_kernel(const RasterArgs a)
             }
         }
         uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
-        int cnt = 0; // entries in the span list (warp-uniform)
-        // ---- BIN: copy the baked row, list the spans that need shading
-        for (int tile = 0; tile < n_tiles; tile++) {
-            const uint32_t in_m = __shfl_sync(0xffffffffu, my_in, tile), part_m = __shfl_sync(0xffffffffu, my_part, tile);
-            const int lr = (tile / tiles_x) * TILE_ROWS + (lane >> 2), c0 = (tile % tiles_x) * TILE_COLS + (lane & 3) * 16;
-            const int off = lr * S + c0, span = off >> 4;
-            *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(s_base + off);
-            if ((in_m | part_m) == 0) continue;
-            const bool skin = (s_skin[span >> 5] >> (span & 31)) & 1u;
-            uint32_t sp_in = in_m, sp_part = 0;
-            if (skin && part_m) {
-                const float fr = (float)(row0 + lr), fc0 = (float)c0;
-                uint32_t m = part_m;
-                while (m) {
-                    const int t = __ffs(m) - 1;
-                    m &= m - 1;
-                    const PrimCoef& c = pc[t];
-                    float lo = 1e30f, hx = 1e30f;
+        int cnt_in = 0, cnt_pt = 0; // entries in the two span lists (warp-uniform)
+        for (int tile = 0; tile <= n_tiles; tile++) {
+            const bool drain = tile == n_tiles;
+            if (!drain) {
+                // ---- BIN: copy the baked row, list the spans that need shading
+                const uint32_t in_m = __shfl_sync(0xffffffffu, my_in, tile), part_m = __shfl_sync(0xffffffffu, my_part, tile);
+                const int lr = (tile >> sh_tx) * TILE_ROWS + (lane >> 2), c0 = (tile & (tiles_x - 1)) * TILE_COLS + (lane & 3) * 16;
+                const int off = (lr << sh_S) + c0, span = off >> 4;
+                *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(s_base + off);
+                if ((in_m | part_m) == 0) continue;
+                const bool skin = (s_skin[span >> 5] >> (span & 31)) & 1u;
+                uint32_t sp_in = in_m, sp_part = 0;
+                if (skin && part_m) {
+                    const float fr = (float)(row0 + lr), fc0 = (float)c0;
+                    uint32_t m = part_m;
+                    while (m) {
+                        const int t = __ffs(m) - 1;
+                        m &= m - 1;
+                        const PrimCoef& c = pc[t];
+                        float lo = 1e30f, hx = 1e30f; // margins subtracted: > 0 means certainly positive
 #pragma unroll
-                    for (int i = 0; i < 5; i++) {
-                        const float a0 = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i])), z0 = fmaf(c.fA[i], 15.0f, a0);
-                        lo = fminf(lo, fminf(a0, z0));
-                        hx = fminf(hx, fmaxf(a0, z0));
+                        for (int i = 0; i < 5; i++) {
+                            const float mgi = i == 4 ? c.wmargin : c.margin;
+                            const float a0 = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i])), z0 = fmaf(c.fA[i], 15.0f, a0);
+                            lo = fminf(lo, fminf(a0, z0) - mgi);
+                            hx = fminf(hx, fmaxf(a0, z0) + mgi);
+                        }
+                        if (hx < 0.0f) continue;                     // one function is negative over the whole span
+                        if (lo > 0.0f && !c.steep) sp_in |= 1u << t; // span fully inside
+                        else sp_part |= 1u << t;
                     }
-                    if (hx < -c.margin) continue;         // one function is negative over the whole span
-                    if (lo > c.margin) sp_in |= 1u << t;  // span fully inside
-                    else sp_part |= 1u << t;
                 }
-            }
-            const bool active = skin && (sp_in | sp_part);
-            const uint32_t bal = __ballot_sync(0xffffffffu, active);
-            if (active) {
+                const bool act_in = skin && sp_in && !sp_part, act_pt = skin && sp_part;
+                const uint32_t bal_in = __ballot_sync(0xffffffffu, act_in), bal_pt = __ballot_sync(0xffffffffu, act_pt);
                 SpanEntry en;
                 en.off16 = (uint16_t)span; en.in_m = (uint16_t)sp_in; en.part_m = (uint16_t)sp_part; en.pad = 0;
-                s_list[cnt + __popc(bal & lt_mask)] = en;
-            }
-            cnt += __popc(bal);
-            __syncwarp();
-            if (cnt >= 32) {
-                // ---- SHADE a full batch of 32 spans
-                const SpanEntry en = s_list[lane];
-                const SpanEntry tail = s_list[32 + lane];
-                __syncwarp();
-                shade(en, obs_e);
-                if (lane < cnt - 32) s_list[lane] = tail;
-                cnt -= 32;
+                if (act_in) l_in[cnt_in + __popc(bal_in & lt_mask)] = en;
+                if (act_pt) l_pt[cnt_pt + __popc(bal_pt & lt_mask)] = en;
+                cnt_in += __popc(bal_in); cnt_pt += __popc(bal_pt);
                 __syncwarp();
             }
-        }
-        if (lane < cnt) shade(s_list[lane], obs_e);
-        __syncwarp();
-        // ---- EXACT PATCH-UP of the queued pixels
-        const int qn = min(*s_qcnt, EXACT_QUEUE);
-        for (int i = lane; i < qn; i += 32) {
-            const int off = s_queue[i];
-            const int lr = off / S, c = off - lr * S;
-            obs_e[off] = (uint8_t)exact_pixel(a, pc, c, row0 + lr, s_nodef[off], s_base[off]);
+            // ---- SHADE: full batches of 32 spans (or what is left when draining), one span per lane
+            if (cnt_in >= 32 || (drain && cnt_in > 0)) {
+                const int nb = min(cnt_in, 32);
+                const SpanEntry en = l_in[lane], tl = l_in[32 + lane];
+                __syncwarp();
+                if (lane < nb) shade(en, obs_e, std::false_type{});
+                if (lane < cnt_in - nb) l_in[lane] = tl;
+                cnt_in -= nb;
+                __syncwarp();
+                if (*s_qcnt > EXACT_QUEUE - 512) flush_queue(obs_e); // the next batch can add up to 512 entries
+            }
+            if (cnt_pt >= 32 || (drain && cnt_pt > 0)) {
+                const int nb = min(cnt_pt, 32);
+                const SpanEntry en = l_pt[lane], tl = l_pt[32 + lane];
+                __syncwarp();
+                if (lane < nb) shade(en, obs_e, std::true_type{});
+                if (lane < cnt_pt - nb) l_pt[lane] = tl;
+                cnt_pt -= nb;
+                __syncwarp();
+                if (*s_qcnt > EXACT_QUEUE - 512) flush_queue(obs_e);
+            }
+            if (drain) flush_queue(obs_e);
         }
     }
 }

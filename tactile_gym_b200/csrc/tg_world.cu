@@ -157,8 +157,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         r.F = cfg->sensor.far_ / (cfg->sensor.far_ - cfg->sensor.near_);
         r.nodef = dn; r.base = db; r.prims = dt; r.cam = b.cam; r.stim = b.stim; r.mask = nullptr; r.obs = nullptr;
         const size_t band_px = px / r.bands;
-        const size_t per_warp = sizeof(PrimCoef) * RASTER_MAXPRIM + sizeof(SpanEntry) * SPAN_LIST + sizeof(uint16_t) * EXACT_QUEUE + 16;
-        w->raster_smem = band_px * 5 + ((band_px / 16 + 31) / 32) * 4 + 16 + per_warp * RASTER_WARPS;
+        w->raster_smem = band_px * 5 + ((band_px / 16 + 31) / 32) * 4 + 16 + RASTER_PER_WARP_SMEM * RASTER_WARPS;
         CK(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->raster_smem));
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel, RASTER_THREADS, w->raster_smem));
