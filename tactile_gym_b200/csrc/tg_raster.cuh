@@ -50,7 +50,8 @@ struct PrimCoef {
     float vA, vB, vC;           // float: V(c, r) = 5100 (nd_ref - F + F near w(c, r))  -> val = 5100 (nodef - nd_ref) + V
     float margin;               // bound on the float evaluation error of the edge functions
     float wmargin;              // ... of w = 1/z_eye
-    int steep;                  // 1: V varies too fast for the float value bound -> its pixels take the exact path
+    int steep;                  // 1: V varies too fast for the float value bound -> V is evaluated in fp64
+    double dvA, dvB, dvC;       // fp64 V coefficients (used for steep primitives)
     float c_lo, c_hi, r_lo, r_hi; // conservative screen bbox in pixel units
     int valid, clipped;         // clipped: a vertex is outside [near, far] -> per-pixel range checks needed
 };
@@ -143,6 +144,7 @@ __device__ __forceinline__ void prim_setup(const RasterArgs& a, const double* ca
     const double Fn = a.F * a.near_;
     const double dvA = 5100.0 * Fn * o.eA[4], dvB = 5100.0 * Fn * o.eB[4], dvC = 5100.0 * (Fn * o.eC[4] - a.F + (double)a.nd_ref);
     o.vA = (float)dvA; o.vB = (float)dvB; o.vC = (float)dvC;
+    o.dvA = dvA; o.dvB = dvB; o.dvC = dvC;
     // float evaluation of V: ~4 roundings at the magnitude of its terms; it must stay well inside VAL_BOUND
     o.steep = ((fabs(dvA) + fabs(dvB)) * S + fabs(dvC)) * 2.4e-7 > 0.5 * VAL_BOUND;
     bool front = true, clipped = false;
@@ -224,8 +226,9 @@ raster_kernel(const RasterArgs a)
     const int tiles_x = S / TILE_COLS, tiles_y = band_rows / TILE_ROWS, n_tiles = tiles_x * tiles_y; // <= 32
     __shared__ __align__(8) uint64_t bar;
 
-    const int band = blockIdx.x % a.bands;
-    const int lane_cta = blockIdx.x / a.bands, n_cta = gridDim.x / a.bands;
+    const int sh_b = 31 - __clz(a.bands); // bands is a power of two
+    const int band = blockIdx.x & (a.bands - 1);
+    const int lane_cta = blockIdx.x >> sh_b, n_cta = gridDim.x >> sh_b;
     const int row0 = band * band_rows;
 
     // TMA bulk copies of this band's tables, once per CTA
@@ -279,7 +282,13 @@ raster_kernel(const RasterArgs a)
         while (m) {
             const int t = __ffs(m) - 1;
             m &= m - 1;
-            if (pc[t].steep) { unc = 0xffffu; continue; } // whole span covered by a steep primitive
+            if (pc[t].steep) {
+                // grazing primitive: V is a small difference of large terms -> evaluate it in fp64, round the result
+                const double dA = pc[t].dvA, d0 = dA * c0 + (pc[t].dvB * r + pc[t].dvC);
+#pragma unroll
+                for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], (float)(dA * k + d0));
+                continue;
+            }
             const float vA = pc[t].vA, v0 = fmaf(vA, fc0, fmaf(pc[t].vB, fr, pc[t].vC));
 #pragma unroll
             for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], fmaf(vA, (float)k, v0));
@@ -296,13 +305,14 @@ raster_kernel(const RasterArgs a)
 #pragma unroll
                 for (int i = 0; i < 5; i++) a0[i] = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i]));
                 const float vA = c.vA, v0 = fmaf(vA, fc0, fmaf(c.vB, fr, c.vC));
+                const double dA = c.dvA, d0 = steep ? dA * c0 + (c.dvB * r + c.dvC) : 0.0;
 #pragma unroll
                 for (int k = 0; k < 16; k++) {
                     const float fk = (float)k;
                     const float lo = fminf(fminf(fmaf(c.fA[0], fk, a0[0]), fmaf(c.fA[1], fk, a0[1])),
                                            fminf(fminf(fmaf(c.fA[2], fk, a0[2]), fmaf(c.fA[3], fk, a0[3])), fmaf(c.fA[4], fk, a0[4]) * sc));
-                    if (lo > mg && !steep) vb[k] = fmaxf(vb[k], fmaf(vA, fk, v0));
-                    else if (lo >= -mg) unc |= 1u << k; // within the margin of an edge, or on a steep primitive
+                    if (lo > mg) vb[k] = fmaxf(vb[k], steep ? (float)(dA * k + d0) : fmaf(vA, fk, v0));
+                    else if (lo >= -mg) unc |= 1u << k; // within the float margin of an edge
                 }
             }
         }
@@ -441,7 +451,7 @@ raster_kernel(const RasterArgs a)
                             hx = fminf(hx, fmaxf(a0, z0) + mgi);
                         }
                         if (hx < 0.0f) continue;                     // one function is negative over the whole span
-                        if (lo > 0.0f && !c.steep) sp_in |= 1u << t; // span fully inside
+                        if (lo > 0.0f) sp_in |= 1u << t;             // span fully inside
                         else sp_part |= 1u << t;
                     }
                 }

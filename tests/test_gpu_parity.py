@@ -267,3 +267,25 @@ def test_full_size_properties(edge_modes):
     assert np.abs(st3[:, 12:15] - st1[:, 12:15]).max() < 5e-6
     assert np.allclose(np.linalg.norm(st2[:, 12:14] - st1[:, 12:14], axis=1), np.hypot(0.008, 0.004) * 0.1, atol=1e-5)
     env.close()
+
+
+def test_draw_refill_keeps_the_rng_sequence(oracle, edge_modes):
+    """Many short episodes: draws are consumed in episode order across host refills of the device-side ring and
+    across the standby pipeline (which always holds one pre-computed episode)."""
+    n, max_steps, steps = 4, 2, 150
+    env = _world(edge_modes, n, S=64, max_steps=max_steps)
+    env.seed(7)
+    env.reset()
+    act = np.zeros((n, 2), dtype=np.float32)
+    for k in range(steps):
+        _, _, done, _ = env.step(act)
+        assert done.all() == ((k + 1) % max_steps == 0)
+    st = env.world.get_state()
+    episode = steps // max_steps          # index of the episode every env is in now
+    for i in range(n):
+        rng = oracle.gym_np_random(7 + i)
+        for _ in range(episode + 1):
+            embed = rng.uniform(0.0015, 0.0065); ang = rng.uniform(-np.pi, np.pi)
+        assert st[i, 19] == embed and st[i, 20] == ang
+    assert not env.world.pipeline_error()
+    env.close()
