@@ -557,38 +557,100 @@ TGD void world_to_work(const TgTask& task, const double* pos, const double* quat
     euler_from_quat(oq, wrpy);
 }
 
-// solve the 6x6 system J x = v by LU with partial pivoting, all in registers; returns min|pivot|/max|pivot|
-TGD double solve6(double (&Mx)[6][7], double* x)
+// solve the N x N system A x = b by LU with partial pivoting, all in registers (Mx is the augmented matrix);
+// returns min|pivot| / max|pivot|
+template <int N>
+TGD double solveN(double (&Mx)[N][N + 1], double* x)
 {
     double pmin = 1e300, pmax = 0;
 #pragma unroll
-    for (int c = 0; c < 6; c++) {
+    for (int c = 0; c < N; c++) {
         // pivot search + swap by value
 #pragma unroll
-        for (int r = c + 1; r < 6; r++) {
+        for (int r = c + 1; r < N; r++) {
             if (fabs(Mx[r][c]) > fabs(Mx[c][c])) {
 #pragma unroll
-                for (int j = 0; j < 7; j++) { double t = Mx[c][j]; Mx[c][j] = Mx[r][j]; Mx[r][j] = t; }
+                for (int j = 0; j < N + 1; j++) { double t = Mx[c][j]; Mx[c][j] = Mx[r][j]; Mx[r][j] = t; }
             }
         }
         const double pv = fabs(Mx[c][c]);
         pmin = fmin(pmin, pv); pmax = fmax(pmax, pv);
         const double inv = pv > 0 ? 1.0 / Mx[c][c] : 0.0;
 #pragma unroll
-        for (int r = c + 1; r < 6; r++) {
+        for (int r = c + 1; r < N; r++) {
             const double f = Mx[r][c] * inv;
 #pragma unroll
-            for (int j = c; j < 7; j++) Mx[r][j] -= f * Mx[c][j];
+            for (int j = c; j < N + 1; j++) Mx[r][j] -= f * Mx[c][j];
         }
     }
 #pragma unroll
-    for (int r = 5; r >= 0; r--) {
-        double s = Mx[r][6];
+    for (int r = N - 1; r >= 0; r--) {
+        double s = Mx[r][N];
 #pragma unroll
-        for (int j = r + 1; j < 6; j++) s -= Mx[r][j] * x[j];
+        for (int j = r + 1; j < N; j++) s -= Mx[r][j] * x[j];
         x[r] = Mx[r][r] != 0.0 ? s / Mx[r][r] : 0.0;
     }
     return pmax > 0 ? pmin / pmax : 0.0;
+}
+TGD double solve6(double (&Mx)[6][7], double* x) { return solveN<6>(Mx, x); }
+
+// x = pinv(J) v for a 6 x NB Jacobian: one-sided Jacobi SVD of J^T, singular values below 1e-15 * max dropped
+// (np.linalg.pinv's default rcond; base_robot_arm.py:316-319, mg400.py:109)
+template <int NB>
+TGD void pinv_apply(const double (&J)[6][NB], const double* v, double* x)
+{
+    double W[NB][6], V[6][6];
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) W[i][j] = J[j][i];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) V[i][j] = i == j ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+#pragma unroll
+        for (int p = 0; p < 5; p++)
+#pragma unroll
+            for (int q = p + 1; q < 6; q++) {
+                double a = 0, b = 0, c = 0;
+#pragma unroll
+                for (int i = 0; i < NB; i++) { a += W[i][p] * W[i][p]; b += W[i][q] * W[i][q]; c += W[i][p] * W[i][q]; }
+                if (!(fabs(c) <= 1e-300 || fabs(c) <= 1e-17 * sqrt(a * b))) {
+                    off += fabs(c);
+                    const double zeta = (b - a) / (2 * c);
+                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+                    const double cs = 1 / sqrt(1 + t * t), sn = cs * t;
+#pragma unroll
+                    for (int i = 0; i < NB; i++) { const double wp = W[i][p], wq = W[i][q]; W[i][p] = cs * wp - sn * wq; W[i][q] = sn * wp + cs * wq; }
+#pragma unroll
+                    for (int i = 0; i < 6; i++) { const double vp = V[i][p], vq = V[i][q]; V[i][p] = cs * vp - sn * vq; V[i][q] = sn * vp + cs * vq; }
+                }
+            }
+        if (off == 0) break;
+    }
+    double sig[6], smax = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double a = 0;
+#pragma unroll
+        for (int i = 0; i < NB; i++) a += W[i][k] * W[i][k];
+        sig[k] = sqrt(a); smax = fmax(smax, sig[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) x[i] = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        if (sig[k] > 1e-15 * smax) {
+            double vk = 0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) vk += V[j][k] * v[j];
+#pragma unroll
+            for (int i = 0; i < NB; i++) x[i] += (W[i][k] / sig[k]) * vk / sig[k];
+        }
+    }
 }
 
 // geometric Jacobian of the TCP point, world frame: rows 0-2 linear, 3-5 angular (pb.calculateJacobian)

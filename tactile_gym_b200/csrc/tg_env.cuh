@@ -120,29 +120,29 @@ TGD void inverse_kinematics(const TgArm& arm, double* q, const double* tpos, con
         for (int c = 0; c < 3; c++) e[3 + c] = sn > 1e-300 ? ang * dq[c] / sn : 0.0;
         double J[6][NB];
         tcp_jacobian<T>(arm, k, tp, J);
-        if (NB == 6) {
-            double Mx[6][7], d[6];
+        {
+            double Mx[NB][NB + 1], d[NB];
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
+            for (int i = 0; i < NB; i++) {
                 double bi = 0;
 #pragma unroll
                 for (int r = 0; r < 6; r++) bi += J[r][i] * e[r];
-                Mx[i][6] = bi;
+                Mx[i][NB] = bi;
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
+                for (int j = 0; j < NB; j++) {
                     double s = i == j ? 0.5 : 0.0;
 #pragma unroll
                     for (int r = 0; r < 6; r++) s += J[r][i] * J[r][j];
                     Mx[i][j] = s;
                 }
             }
-            solve6(Mx, d);
+            solveN<NB>(Mx, d);
             double mx = 0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(d[i]));
+            for (int i = 0; i < NB; i++) mx = fmax(mx, fabs(d[i]));
             const double sc = mx > M_PI / 4 ? (M_PI / 4) / mx : 1.0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) q[i] += sc * d[i];
+            for (int i = 0; i < NB; i++) q[i] += sc * d[i];
         }
     }
 }
@@ -361,19 +361,23 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         m3mulv(vw, R, v); m3mulv(vw + 3, R, v + 3);
         double J[6][NB];
         tcp_jacobian<T>(arm, k, tp, J);
+        bool use_pinv = NB != 6 || arm.topo == TG_TOPO_MG400;   // mg400.py:109 always uses the pseudo-inverse
         if (NB == 6) {
             double Mx[6][7];
 #pragma unroll
             for (int r = 0; r < 6; r++) {
 #pragma unroll
-                for (int c = 0; c < 6; c++) Mx[r][c] = J[r][c];
+                for (int c = 0; c < 6; c++) Mx[r][c] = J[r][c < NB ? c : 0];
                 Mx[r][6] = vw[r];
             }
-            solve6(Mx, mot.target_vel);
-        } else {
-            // TODO(mg400): pseudo-inverse path
-#pragma unroll
-            for (int i = 0; i < NB; i++) mot.target_vel[i] = 0.0;
+            if (solve6(Mx, mot.target_vel) < 1e-13) use_pinv = true; // np.linalg.matrix_rank(J) < 6 (base_robot_arm.py:316-319)
+        }
+        if (use_pinv) pinv_apply<NB>(J, vw, mot.target_vel);
+        if (arm.topo == TG_TOPO_MG400 && NB == 8) {
+            // parallelogram emulation (mg400.py:111-120): the three slaved joints follow j2_1 / j3_1
+            mot.target_vel[NB - 3] = mot.target_vel[1];
+            mot.target_vel[NB - 2] = -mot.target_vel[1];
+            mot.target_vel[NB - 1] = mot.target_vel[1] + mot.target_vel[2];
         }
 #pragma unroll
         for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;

@@ -14,6 +14,13 @@
 
 static thread_local std::string g_err;
 
+// kernels are specialised per arm topology
+#define TOPO_DISPATCH(w, CALL)                                         \
+    do {                                                               \
+        if ((w)->cfg.arm.topo == TG_TOPO_MG400) { using Topo = TopoMG400; CALL; } \
+        else { using Topo = TopoChain6; CALL; }                        \
+    } while (0)
+
 static int fail(int code, const char* fmt, ...)
 {
     char buf[512];
@@ -74,8 +81,8 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     const int S = cfg->sensor.image_size;
     if (S != 64 && S != 128 && S != 256) return fail(TG_EINVAL, "image_size must be 64, 128 or 256 (got %d)", S);
     if (cfg->arm.topo == TG_TOPO_CHAIN6 && cfg->arm.nb != 6) return fail(TG_EINVAL, "CHAIN6 topology needs nb == 6");
-    if (cfg->arm.topo == TG_TOPO_MG400) return fail(TG_EUNSUPPORTED, "MG400 topology: velocity control path not built yet");
-    if (cfg->arm.topo != TG_TOPO_CHAIN6) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
+    if (cfg->arm.topo == TG_TOPO_MG400 && cfg->arm.nb != 8) return fail(TG_EINVAL, "MG400 topology needs nb == 8");
+    if (cfg->arm.topo != TG_TOPO_CHAIN6 && cfg->arm.topo != TG_TOPO_MG400) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
     if (cfg->task.task != TG_TASK_EDGE_FOLLOW) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
     if (cfg->sensor.n_prim <= 0 || cfg->sensor.n_prim > RASTER_MAXPRIM) return fail(TG_EINVAL, "n_prim must be in 1..%d", RASTER_MAXPRIM);
     if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->sensor.h_prims || !cfg->sensor.h_prim_nv || !cfg->h_rest_q)
@@ -196,7 +203,7 @@ static int set_draws_impl(TgWorld* w, const double* h_draws, int rounds, int inv
     if (invalidate && w->eb.pipeline) {
         // a new draw sequence starts: standbys computed from the old one are recomputed now
         CK(cudaMemset(w->eb.sb_ready, 0, w->n));
-        standby_kernel<TopoChain6><<<(w->n + 127) / 128, 128>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb);
+        TOPO_DISPATCH(w, (standby_kernel<Topo><<<(w->n + 127) / 128, 128>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb)));
         w->launches++;
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
@@ -241,7 +248,7 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
 
 static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
 {
-    reset_kernel<TopoChain6><<<env_grid(w), 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, mask);
+    TOPO_DISPATCH(w, (reset_kernel<Topo><<<env_grid(w), 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, mask)));
     w->launches++;
     CK(cudaGetLastError());
     return TG_OK;
@@ -250,7 +257,7 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
 static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, int autoreset, cudaStream_t st)
 {
     const dim3 grid(w->eb.step_blocks + w->standby_blocks); // the extra blocks recompute consumed standbys meanwhile
-    step_kernel<TopoChain6><<<grid, 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done, autoreset);
+    TOPO_DISPATCH(w, (step_kernel<Topo><<<grid, 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done, autoreset)));
     w->launches++;
     CK(cudaGetLastError());
     return TG_OK;
@@ -387,7 +394,7 @@ extern "C" int tg_test_inverse_dynamics(TgWorld* w, int n, const double* h_q, co
 {
     if (!w || n <= 0) return fail(TG_EINVAL, "bad arguments");
     return with_tmp(w, n, w->nb, h_q, h_qd, (size_t)n * w->nb, h_tau, false, [&](double* q, double* qd, double* out) {
-        test_id_kernel<TopoChain6><<<(n + 63) / 64, 64>>>(w->cfg.arm, w->cfg.phys, n, q, qd, out);
+        TOPO_DISPATCH(w, (test_id_kernel<Topo><<<(n + 63) / 64, 64>>>(w->cfg.arm, w->cfg.phys, n, q, qd, out)));
     });
 }
 
@@ -395,7 +402,7 @@ extern "C" int tg_test_mass_matrix(TgWorld* w, int n, const double* h_q, double*
 {
     if (!w || n <= 0) return fail(TG_EINVAL, "bad arguments");
     return with_tmp(w, n, w->nb, h_q, nullptr, (size_t)n * w->nb * w->nb, h_M, false, [&](double* q, double*, double* out) {
-        test_mass_kernel<TopoChain6><<<(n + 63) / 64, 64>>>(w->cfg.arm, n, q, out);
+        TOPO_DISPATCH(w, (test_mass_kernel<Topo><<<(n + 63) / 64, 64>>>(w->cfg.arm, n, q, out)));
     });
 }
 
@@ -409,7 +416,7 @@ extern "C" int tg_test_substep(TgWorld* w, int n, int nsteps, double* h_q, doubl
     CK(cudaMemcpy(q, h_q, bytes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(qd, h_qd, bytes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(tv, h_target_vel, bytes, cudaMemcpyHostToDevice));
-    test_substep_kernel<TopoChain6><<<(n + 31) / 32, 32>>>(w->cfg.arm, w->cfg.phys, n, nsteps, q, qd, tv);
+    TOPO_DISPATCH(w, (test_substep_kernel<Topo><<<(n + 31) / 32, 32>>>(w->cfg.arm, w->cfg.phys, n, nsteps, q, qd, tv)));
     w->launches++;
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(h_q, q, bytes, cudaMemcpyDeviceToHost);

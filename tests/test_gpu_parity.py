@@ -289,3 +289,48 @@ def test_draw_refill_keeps_the_rng_sequence(oracle, edge_modes):
         assert st[i, 19] == embed and st[i, 20] == ang
     assert not env.world.pipeline_error()
     env.close()
+
+
+@pytest.mark.parametrize("arm,sensor", [("ur5", "digit"), ("ur5", "digitac"), ("mg400", "tactip"), ("mg400", "digitac")])
+def test_other_arms_and_sensors_match_oracle(oracle, edge_modes, arm, sensor):
+    """edge_follow-v0 on the other arm (MG400: 8-joint tree, pseudo-inverse velocity control with slaved joints,
+    mg400.py:77-129) and the other sensors (DIGIT / DigiTac: 40 deg camera, no border)."""
+    import tactile_gym_b200 as tg
+
+    modes = dict(edge_modes, arm_type=arm, tactile_sensor_name=sensor)
+    n, S, steps = 8, 128, 5
+    env = tg.make_vec("edge_follow-v0", n, env_kwargs={"env_modes": modes, "image_size": [S, S], "max_steps": 200})
+    rng = np.random.RandomState(3)
+    lo, hi = {"tactip": (0.0015, 0.0065), "digit": (0.0011, 0.0028), "digitac": (0.0015, 0.0045)}[sensor]
+    draws = np.stack([rng.uniform(lo, hi, (n, 2)), rng.uniform(-np.pi, np.pi, (n, 2))], axis=2)
+    env.world.set_draws(draws)
+    obs = env.reset()["tactile"]
+    st = env.world.get_state()
+    nb = env.world.nb
+    refs = []
+    for i in range(n):
+        r = oracle.EdgeFollowOracle(image_size=S, arm=arm, sensor=sensor)
+        r.reset(draws=tuple(draws[i, 0]))
+        refs.append(r)
+        assert np.allclose(st[i, :nb], np.array(r.s.q[:nb]), atol=5e-6)
+        for k in range(nb):
+            r.s.q[k] = st[i, k]; r.s.qd[k] = st[i, nb + k]
+        mx, frac = _img_close(r.observation(), obs[i])
+        assert mx <= 1 and frac < 1e-3, (i, mx, frac)
+        assert (obs[i] > 0).sum() > 20
+    for k in range(steps):
+        act = rng.uniform(-0.25, 0.25, (n, 2)).astype(np.float32)
+        for i, r in enumerate(refs):
+            for j in range(nb):
+                r.s.q[j] = st[i, j]; r.s.qd[j] = st[i, nb + j]
+        o2, rew, done, _ = env.step(act)
+        st = env.world.get_state()
+        for i, r in enumerate(refs):
+            o, rr, dd, _ = r.step(act[i])
+            assert np.allclose(st[i, :nb], np.array(r.s.q[:nb]), atol=1e-9)
+            assert np.allclose(st[i, nb:2 * nb], np.array(r.s.qd[:nb]), atol=1e-8)
+            assert np.allclose(st[i, 2 * nb:2 * nb + 3], r.tcp_world()[0], atol=1e-8)
+            assert abs(rr - rew[i]) < 1e-6 and bool(dd) == bool(done[i])
+            mx, frac = _img_close(o, o2["tactile"][i])
+            assert mx <= 1 and frac < 1e-3, (k, i, mx, frac)
+    env.close()
