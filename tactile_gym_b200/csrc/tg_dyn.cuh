@@ -136,35 +136,55 @@ struct Kin {
     double a[NB][3]; // world joint axis
 };
 
+// Body frames are world-aligned at q = 0 (scene.py:_align_body_frames), so R_i = R_parent . Rot(axis_i, q_i).
+// sc[i] = (sin q_i, cos q_i).
 template <class T>
-TGD void fk(const TgArm& arm, const double* q, Kin<T::NB>& k)
+TGD void fk_sc(const TgArm& arm, const double (&sc)[T::NB][2], Kin<T::NB>& k)
 {
 #pragma unroll
     for (int i = 0; i < T::NB; i++) {
-        constexpr int dummy = 0; (void)dummy;
         const int p = T::parent(i);
-        double Rj[9];
-        if (p < 0) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) k.p[i][c] = arm.jpos[i][c];
-#pragma unroll
-            for (int c = 0; c < 9; c++) Rj[c] = arm.jrot[i][c];
-        } else {
-            double t[3];
-            m3mulv(t, k.R[p], arm.jpos[i]);
-#pragma unroll
-            for (int c = 0; c < 3; c++) k.p[i][c] = k.p[p][c] + t[c];
-            m3mul(Rj, k.R[p], arm.jrot[i]);
-        }
-        double s, c;
-        sincos(q[i], &s, &c);
+        const double s = sc[i][0], c = sc[i][1];
         const double ax = arm.axis[i][0], ay = arm.axis[i][1], az = arm.axis[i][2], t1 = 1.0 - c;
         double Rq[9] = {t1 * ax * ax + c,      t1 * ax * ay - s * az, t1 * ax * az + s * ay,
                         t1 * ax * ay + s * az, t1 * ay * ay + c,      t1 * ay * az - s * ax,
                         t1 * ax * az - s * ay, t1 * ay * az + s * ax, t1 * az * az + c};
-        m3mul(k.R[i], Rj, Rq);
+        if (p < 0) {
+#pragma unroll
+            for (int c2 = 0; c2 < 3; c2++) k.p[i][c2] = arm.jpos[i][c2];
+#pragma unroll
+            for (int c2 = 0; c2 < 9; c2++) k.R[i][c2] = Rq[c2];
+        } else {
+            double t[3];
+            m3mulv(t, k.R[p], arm.jpos[i]);
+#pragma unroll
+            for (int c2 = 0; c2 < 3; c2++) k.p[i][c2] = k.p[p][c2] + t[c2];
+            m3mul(k.R[i], k.R[p], Rq);
+        }
         m3mulv(k.a[i], k.R[i], arm.axis[i]);
     }
+}
+
+template <class T>
+TGD void fk(const TgArm& arm, const double* q, Kin<T::NB>& k)
+{
+    double sc[T::NB][2];
+#pragma unroll
+    for (int i = 0; i < T::NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
+    fk_sc<T>(arm, sc, k);
+}
+
+// advance (sin q, cos q) by the small angle d = dt * qd: exact trig identity with a 6th-order Taylor of (sin d, cos d)
+// (|d| <= 2e-3 -> truncation < 1e-19); larger moves fall back to sincos
+TGD void sc_advance(double (&sc)[2], double q_new, double d)
+{
+    if (fabs(d) > 2e-3) { sincos(q_new, &sc[0], &sc[1]); return; }
+    const double d2 = d * d;
+    const double sd = d * (1.0 - d2 * (1.0 / 6.0) * (1.0 - d2 * (1.0 / 20.0)));
+    const double cd = 1.0 - d2 * 0.5 * (1.0 - d2 * (1.0 / 12.0) * (1.0 - d2 * (1.0 / 30.0)));
+    const double s = sc[0], c = sc[1];
+    sc[0] = s * cd + c * sd;
+    sc[1] = c * cd - s * sd;
 }
 
 // world pose of a frame rigidly attached to body b
@@ -340,32 +360,35 @@ TGD void damping_forces(const TgArm& arm, const TgPhysics& ph, const Kin<T::NB>&
     constexpr int NB = T::NB;
     double Nw[NB][3], Fw[NB][3];
 #pragma unroll
-    for (int i = 0; i < NB; i++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) { Nw[i][c] = 0; Fw[i][c] = 0; }
-#pragma unroll
     for (int b = 0; b < NB; b++) {
+        // |w| is the same in every frame: one norm per body.  The norms only scale a ~1e-4 N force by (1 + |v|), so a
+        // float square root (relative error 6e-8) is exact for every purpose here.
+        const double ka = ph.ang_damping * (1.0 + (double)sqrtf((float)v3dot(w[b], w[b])));
+        double wb[3], Nb[3] = {0, 0, 0}, Na[3] = {0, 0, 0}, Fa[3] = {0, 0, 0};
+        m3tmulv(wb, k.R[b], w[b]); // angular velocity in the body frame
         // mass-carrying URDF links merged into body b (sorted by body at scene-compile time)
 #pragma unroll 1
         for (int s = arm.sub_start[b]; s < arm.sub_start[b + 1]; s++) {
-            double t[3], x[3], v[3], wl[3], nl[3], nw[3], Rs[9], xf[3];
+            double t[3], x[3], v[3], wl[3], nl[3], nb[3], xf[3];
             m3mulv(t, k.R[b], arm.sub_com[s]);
             x[0] = k.p[b][0] + t[0]; x[1] = k.p[b][1] + t[1]; x[2] = k.p[b][2] + t[2];
             v3cross(v, w[b], x);
             v[0] += vO[b][0]; v[1] += vO[b][1]; v[2] += vO[b][2];
-            m3mul(Rs, k.R[b], arm.sub_rot[s]);
-            m3tmulv(wl, Rs, w[b]);
-            const double ka = ph.ang_damping * (1.0 + sqrt(v3dot(wl, wl)));
-            const double kl = ph.lin_damping * (1.0 + sqrt(v3dot(v, v)));
+            const double kl = ph.lin_damping * (1.0 + (double)sqrtf((float)v3dot(v, v)));
+            m3tmulv(wl, arm.sub_rot[s], wb);            // ... in the link's inertial frame
 #pragma unroll
             for (int c = 0; c < 3; c++) nl[c] = -arm.sub_inertia[s][c] * wl[c] * ka;
-            m3mulv(nw, Rs, nl);
+            m3mulv(nb, arm.sub_rot[s], nl);             // torque back in the body frame
             const double ms = arm.sub_mass[s];
             double f[3] = {-ms * v[0] * kl, -ms * v[1] * kl, -ms * v[2] * kl};
             v3cross(xf, x, f);
 #pragma unroll
-            for (int c = 0; c < 3; c++) { Nw[b][c] += nw[c] + xf[c]; Fw[b][c] += f[c]; }
+            for (int c = 0; c < 3; c++) { Nb[c] += nb[c]; Na[c] += xf[c]; Fa[c] += f[c]; }
         }
+        double nwv[3];
+        m3mulv(nwv, k.R[b], Nb);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { Nw[b][c] = nwv[c] + Na[c]; Fw[b][c] = Fa[c]; }
     }
 #pragma unroll
     for (int i = NB - 1; i >= 0; i--) {
@@ -438,14 +461,14 @@ struct Motors {
 // One Robot.step_sim(): gravity compensation + stepSimulation with motor rows only.
 // Returns the number of PGS sweeps executed (diagnostics).
 template <class T>
-TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, const Motors<T::NB>& mot)
+TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot)
 {
     constexpr int NB = T::NB;
     double A[NB][NB]; // M^-1
     double qdd[NB];
     {
         Kin<NB> k;
-        fk<T>(arm, q, k);
+        fk_sc<T>(arm, sc, k);
         SpI sp[NB];
         body_inertias<T>(arm, k, sp);
         double tau[NB];
@@ -522,7 +545,12 @@ TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, co
         }
     }
 #pragma unroll
-    for (int i = 0; i < NB; i++) { qd[i] += dv[i]; q[i] += ph.dt * qd[i]; }
+    for (int i = 0; i < NB; i++) {
+        qd[i] += dv[i];
+        const double d = ph.dt * qd[i];
+        q[i] += d;
+        sc_advance(sc[i], q[i], d);
+    }
     return it;
 }
 

@@ -205,12 +205,15 @@ __device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, co
     mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.blocking_force;
     double cv = 0.001;
     int nsteps = 0;
+    double sc[NB][2];
+#pragma unroll
+    for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
 #pragma unroll 1
     for (int it = 0; it < 1000; it++) {
         double tp[3], tq[4];
         {
             Kin<NB> k;
-            fk<T>(arm, q, k);
+            fk_sc<T>(arm, sc, k);
             tcp_world<T>(arm, k, tp, tq);
         }
         double nrm = 0, tot = 0;
@@ -226,7 +229,7 @@ __device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, co
             if (!(fabs(diff[i]) < cv)) all_small = false;
         }
         if (all_small) cv *= 0.5;
-        substep<T>(arm, ph, q, qd, mot);
+        substep<T>(arm, ph, q, qd, sc, mot);
         nsteps++;
         const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
         const double ip = targ_orn[0] * tq[0] + targ_orn[1] * tq[1] + targ_orn[2] * tq[2] + targ_orn[3] * tq[3];
@@ -382,8 +385,13 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
         for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;
     }
+    {
+        double sc[NB][2]; // (sin q, cos q): exact here, then advanced by the trig identity after every substep
+#pragma unroll
+        for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
 #pragma unroll 1
-    for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, mot);
+        for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, sc, mot);
+    }
 
     const int steps = b.steps[e] + 1;
     b.steps[e] = steps;
@@ -491,7 +499,9 @@ __global__ void test_substep_kernel(const __grid_constant__ TgArm arm, const __g
     Motors<NB> mot;
     mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
     for (int i = 0; i < NB; i++) { q[i] = q_io[e * NB + i]; qd[i] = qd_io[e * NB + i]; mot.target_vel[i] = target_vel[e * NB + i]; mot.target_pos[i] = 0; }
+    double sc[NB][2];
+    for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
 #pragma unroll 1
-    for (int s = 0; s < nsteps; s++) substep<T>(arm, ph, q, qd, mot);
+    for (int s = 0; s < nsteps; s++) substep<T>(arm, ph, q, qd, sc, mot);
     for (int i = 0; i < NB; i++) { q_io[e * NB + i] = q[i]; qd_io[e * NB + i] = qd[i]; }
 }

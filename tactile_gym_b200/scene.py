@@ -232,7 +232,43 @@ def reduce_model(mj, sensor, cam_pos, cam_rpy):
         arm.cam_pos[k] = tc[k]
     for k in range(9):
         arm.cam_rot[k] = Rc.reshape(-1)[k]
+    _align_body_frames(arm)
     return arm, moving
+
+
+def _align_body_frames(arm):
+    """Re-express every body-fixed quantity in a frame that is world-aligned at q = 0.
+
+    With A_i = A_parent . jrot_i, the rotated frame R_i' = R_i A_i^T obeys R_i' = R_parent' . Rot(A_i axis_i, q_i):
+    the constant joint rotation disappears from the forward kinematics (one 3x3 product per body per substep
+    saved); vectors become A_i v, tensors A_i I A_i^T, attached frames A_i R.  jrot becomes the identity."""
+    nb = arm.nb
+    parents = {0: [-1, 0, 1, 2, 3, 4], 1: [-1, 0, 1, 2, 3, 0, 5, 6]}[arm.topo]
+    A = []
+    for b in range(nb):
+        Ap = np.eye(3) if parents[b] < 0 else A[parents[b]]
+        A.append(Ap @ np.array(arm.jrot[b][:]).reshape(3, 3))
+    def setv(dst, v):
+        for k in range(len(v)):
+            dst[k] = float(v[k])
+    for b in range(nb):
+        Ap = np.eye(3) if parents[b] < 0 else A[parents[b]]
+        setv(arm.jpos[b], Ap @ np.array(arm.jpos[b][:]))
+        setv(arm.jrot[b], np.eye(3).reshape(-1))
+        setv(arm.axis[b], A[b] @ np.array(arm.axis[b][:]))
+        setv(arm.com[b], A[b] @ np.array(arm.com[b][:]))
+        I6 = arm.inertia[b][:]
+        I = np.array([[I6[0], I6[1], I6[2]], [I6[1], I6[3], I6[4]], [I6[2], I6[4], I6[5]]])
+        I = A[b] @ I @ A[b].T
+        setv(arm.inertia[b], [I[0, 0], I[0, 1], I[0, 2], I[1, 1], I[1, 2], I[2, 2]])
+    for s_ in range(arm.nsub):
+        Ab = A[arm.sub_body[s_]]
+        setv(arm.sub_com[s_], Ab @ np.array(arm.sub_com[s_][:]))
+        setv(arm.sub_rot[s_], (Ab @ np.array(arm.sub_rot[s_][:]).reshape(3, 3)).reshape(-1))
+    setv(arm.tcp_pos, A[arm.tcp_body] @ np.array(arm.tcp_pos[:]))
+    setv(arm.tcp_rot, (A[arm.tcp_body] @ np.array(arm.tcp_rot[:]).reshape(3, 3)).reshape(-1))
+    setv(arm.cam_pos, A[arm.cam_body] @ np.array(arm.cam_pos[:]))
+    setv(arm.cam_rot, (A[arm.cam_body] @ np.array(arm.cam_rot[:]).reshape(3, 3)).reshape(-1))
 
 
 def default_physics(substeps=24, gravity=(0.0, 0.0, -9.81)):
