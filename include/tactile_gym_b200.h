@@ -51,7 +51,7 @@ extern "C" {
 #define TG_MAXB 8     /* moving bodies == dofs of the arm */
 #define TG_MAXSUB 16  /* original URDF links that carry mass (per-link damping terms) */
 #define TG_MAXTRI 64  /* stimulus triangles per env */
-#define TG_MAXDRAW 4  /* random draws consumed per reset */
+#define TG_MAXDRAW 8  /* random draws consumed per reset */
 
 /* arm topologies the kernels are specialised for */
 #define TG_TOPO_CHAIN6 0 /* UR5: 6 revolute joints in a serial chain               */
@@ -59,6 +59,7 @@ extern "C" {
 
 /* tasks */
 #define TG_TASK_EDGE_FOLLOW 0
+#define TG_TASK_OBJECT_BALANCE 1
 
 /* Reduced arm model: fixed joints are merged into their moving parent at asset-compile time
  * (tactile_gym_b200/scene.py); `sub_*` keeps the original mass-carrying links for bullet's per-link
@@ -108,6 +109,16 @@ typedef struct {
     double embed_lo, embed_hi; /* uniform range; lo == hi -> fixed */
     double init_rpy[3];
     double draw_default[TG_MAXDRAW];
+    /* object_balance (object_balance_env.py): a free rigid body hanging on the TCP by a point-to-point constraint.
+     * draws per reset: gravity_z, embed_dist, fx, fy (signed fractions of the half base width where 0.1 N pushes down) */
+    double obj_mass, obj_inertia[3]; /* composite about the composite COM, body axes */
+    double obj_com_off[3];           /* composite COM minus base-link COM, body frame */
+    double obj_base_com[3];          /* base-link COM in the base LINK frame (the stimulus frame) */
+    double obj_init_rpy[3];          /* init_obj_rpy = (0, 0, -pi/2) */
+    double obj_base_w, obj_base_h;   /* 0.1, 0.0025 */
+    double obj_force;                /* 0.1 N */
+    double obj_term_deg, obj_term_pos; /* 35 deg, 0.1 m */
+    double p2p_erp, p2p_max_impulse; /* 0.2, 500 [EXT] */
 } TgTask;
 
 typedef struct {
@@ -167,7 +178,7 @@ int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream);
 int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream);
 
 /* state access (parity tests, checkpointing).  Layout: per env doubles
- * [q(nb) qd(nb) tcp_pos(3) tcp_quat(4) embed edge_ang steps reset_substeps] */
+ * [q(nb) qd(nb) tcp_pos(3) tcp_quat(4) embed edge_ang steps reset_substeps | obj pos(3) quat(4) vel(3) omg(3) gravity_z] */
 int tg_state_size(const TgWorld* w); /* doubles per env */
 int tg_get_state(TgWorld* w, double* h_state, void* stream);
 int tg_set_state(TgWorld* w, const double* h_state, void* stream);

@@ -351,3 +351,121 @@ class EdgeFollowOracle:
         lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
         self.reward, self.done = self.step_data()
         return self.observation(), self.reward, self.done, {}
+
+
+# ---------------------------------------------------------------- object_balance task restatement
+class OrObject(C.Structure):
+    _fields_ = [
+        ("enabled", C.c_int), ("mass", C.c_double), ("inertia", C.c_double * 3), ("com_off", C.c_double * 3),
+        ("pos", C.c_double * 3), ("quat", C.c_double * 4), ("vel", C.c_double * 3), ("omg", C.c_double * 3),
+        ("ext_force", C.c_double * 3), ("ext_pos", C.c_double * 3), ("ext_pending", C.c_int),
+        ("p2p_enabled", C.c_int), ("pivot_b", C.c_double * 3), ("erp", C.c_double), ("max_impulse", C.c_double),
+    ]
+
+
+def balance_draws(rng, sensor="tactip", rand_gravity=True, rand_embed_dist=True):
+    """Random draws of one ObjectBalanceEnv.reset in the reference's order: reset_task (gravity, embed_dist;
+    object_balance_env.py:300-313) then apply_random_force_base (choice, rand, choice, rand; :366-371)."""
+    g = rng.uniform(-1.0, -0.1) if rand_gravity else -0.1
+    embed_default = {"tactip": 0.0035, "digitac": 0.0015, "digit": 0.0015}[sensor]
+    lo, hi = {"tactip": (0.003, 0.006), "digitac": (0.001, 0.0025), "digit": (0.0015, 0.0025)}[sensor]
+    embed = rng.uniform(lo, hi) if rand_embed_dist else embed_default
+    fx = rng.choice([-1, 1]) * rng.rand()
+    fy = rng.choice([-1, 1]) * rng.rand()
+    return np.array([g, embed, fx, fy])
+
+
+class ObjectBalanceOracle:
+    """Restates ObjectBalanceEnv (rl_envs/nonprehensile_manipulation/object_balance/object_balance_env.py, object_mode
+    "pole") + BaseObjectEnv.reset (base_object_env.py) on top of the C oracle.  One env instance.
+
+    Deviation from the reference, shared with the product: Robot.reset() is run WITHOUT the pole in the world.  In the
+    reference the (fallen) pole of the previous episode still hangs on the constraint while the arm is repositioned and
+    is only teleported back afterwards (base_object_env.py reset order); its influence on the arm is bounded by the
+    solver residual (<= 3e-4 rad/s over <= 10 substeps, < 1e-5 rad) and is what makes resets independent of history."""
+
+    def __init__(self, image_size=256, sensor="tactip", max_steps=250, movement_mode="xy", rand_gravity=True,
+                 rand_embed_dist=True, seed=None):
+        self.S, self.sensor, self.max_steps, self.movement_mode = image_size, sensor, max_steps, movement_mode
+        self.rand_gravity, self.rand_embed_dist = rand_gravity, rand_embed_dist
+        self.workframe_pos = np.array([0.55, 0.0, 0.35]); self.workframe_rpy = np.zeros(3)
+        lims = np.zeros((6, 2))
+        lims[0], lims[1], lims[2] = (-0.1, 0.1), (-0.1, 0.1), (-0.1, 0.1)
+        a45 = 45 * np.pi / 180
+        lims[3], lims[4], lims[5] = (-a45, a45), (-a45, a45), (-a45, a45)
+        self.m = load_model("ur5", sensor, "standard", self.workframe_pos, self.workframe_rpy, lims)
+        self.rest = rest_pose("object_balance", "ur5", sensor, "standard", self.m)
+        self.ref = load_refimg(sensor, "standard", image_size)
+        self.tris_local = np.load(os.path.join(ASSETS, "stimuli", "pole.npz"))["tris"]
+        with open(os.path.join(ASSETS, "objects", "pole.json")) as f:
+            self.pole = json.load(f)
+        self.s = OrState(); self.o = OrObject()
+        self.repeat = int(np.floor((1.0 / 20.0) / (1.0 / 240.0)))
+        self.base_w, self.base_h = 0.1, 0.0025
+        self.init_rpy = np.array([0.0, 0.0, -np.pi / 2])
+        self.np_random = gym_np_random(seed)
+        self.steps = 0
+
+    def seed(self, seed):
+        self.np_random = gym_np_random(seed)
+
+    def reset(self, draws=None):
+        self.steps = 0
+        d = balance_draws(self.np_random, self.sensor, self.rand_gravity, self.rand_embed_dist) if draws is None else np.asarray(draws, dtype=np.float64)
+        g, self.embed_dist, fx, fy = d
+        self.m.gravity[2] = g
+        self.init_obj_pos = np.array([self.workframe_pos[0], self.workframe_pos[1], self.workframe_pos[2] + self.base_h / 2 - self.embed_dist])
+        pos = np.zeros(3); rpy = np.zeros(3)
+        self.last_reset_substeps = lib().or_robot_reset(C.byref(self.m), C.byref(self.s), _dptr(self.rest), _dptr(pos), _dptr(rpy))
+        o = self.o
+        o.enabled = 1; o.mass = self.pole["mass"]
+        q0 = quat_from_euler(self.init_rpy)
+        for c in range(3):
+            o.inertia[c] = self.pole["inertia_diag"][c]; o.com_off[c] = self.pole["com_off"][c]
+            o.pos[c] = self.init_obj_pos[c]; o.vel[c] = 0; o.omg[c] = 0
+        for c in range(4):
+            o.quat[c] = q0[c]
+        # apply_random_force_base(force_mag=0.1) (:360-381)
+        fpos = self.init_obj_pos + np.array([fx * self.base_w / 2, fy * self.base_w / 2, 0.0])
+        for c in range(3):
+            o.ext_force[c] = [0.0, 0.0, -0.1][c]; o.ext_pos[c] = fpos[c]
+        o.ext_pending = 1
+        o.p2p_enabled = 1; o.erp = 0.2; o.max_impulse = 500.0
+        o.pivot_b[0], o.pivot_b[1], o.pivot_b[2] = 0.0, 0.0, -self.base_h / 2 + self.embed_dist
+        self.reward, self.done = self.step_data()
+        return self.observation()
+
+    def stimulus_world(self):
+        R = np.zeros(9); q = np.array(self.o.quat[:])
+        lib().or_mat_from_quat(_dptr(q), _dptr(R)); R = R.reshape(3, 3)
+        t = np.array(self.o.pos[:]) - R @ np.array(self.pole["base_com"])   # base LINK frame from the base COM frame
+        return self.tris_local @ R.T + t
+
+    def observation(self):
+        q = np.array(self.s.q[: self.m.ndof])
+        return tactile_image(self.m, q, self.S, self.stimulus_world(), self.ref, border_on=True)[..., None]
+
+    def step_data(self):
+        rpy_deg = euler_from_quat(np.array(self.o.quat[:])) * 180 / np.pi
+        init_deg = self.init_rpy * 180 / np.pi
+        rpy_dist = np.abs(((rpy_deg - init_deg) + 180) % 360 - 180)
+        fall = bool(rpy_dist[0] > 35 or rpy_dist[1] > 35 or np.linalg.norm(np.array(self.o.pos[:]) - self.init_obj_pos) > 0.1)
+        return 1.0, bool(fall or self.steps >= self.max_steps)
+
+    def encode_scale(self, action):
+        enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
+        idx = {"xy": [0, 1], "xyz": [0, 1, 2], "RxRy": [3, 4], "xyRxRy": [0, 1, 3, 4]}[self.movement_mode]
+        enc[idx] = a
+        enc = np.clip(enc, -0.25, 0.25)
+        mv, ma = 0.01, 5.0 * (np.pi / 180)
+        amax = np.array([mv, mv, mv, ma, ma, 0.0]); amin = -amax
+        return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
+
+    def step(self, action):
+        v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
+        self.steps += 1
+        lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
+        for _ in range(self.repeat):
+            lib().or_step_sim_obj(C.byref(self.m), C.byref(self.s), C.byref(self.o))
+        self.reward, self.done = self.step_data()
+        return self.observation(), self.reward, self.done, {}

@@ -536,6 +536,139 @@ void or_step_simulation(const OrModel* m, OrState* s, const double* tau_applied)
     for (int i = 0; i < n; i++) { s->qd[i] += dv[i]; s->q[i] += m->dt * s->qd[i]; }
 }
 
+/* ------------------------------------------------------------------ stepSimulation with a free body + P2P constraint
+ * Same pipeline as or_step_simulation; the solver now sees 6 + 3 rows.  Rows keep creation order (motors were created
+ * with the robot, the constraint later, object_balance_env.py:110), sweeps alternate direction, same residual exit. */
+static void quat_rotate(const double q[4], const double v[3], double o[3]) { m3 R; or_mat_from_quat(q, R); m3mulv(o, R, v); }
+
+void or_step_sim_obj(const OrModel* m, OrState* s, OrObject* o)
+{
+    int n = m->ndof;
+    double tau_gc[OR_MAXD], tau[OR_MAXD], qdd[OR_MAXD];
+    or_inverse_dynamics(m, s->q, s->qd, NULL, tau_gc);
+    for (int i = 0; i < n; i++) tau[i] = tau_gc[i] - m->joint_damping * s->qd[i];
+    Aba A; aba_setup(m, s->q, s->qd, tau, 1, &A);
+    aba_accel(m, &A, qdd);
+    for (int i = 0; i < n; i++) s->qd[i] += m->dt * qdd[i];
+
+    /* object: unconstrained update about the composite COM (gravity, one-step external force, gyroscopic torque; no damping) */
+    m3 Rb, Iw; v3 dw, cw, vc;
+    double Iinv[3];
+    or_mat_from_quat(o->quat, Rb);
+    m3mulv(dw, Rb, o->com_off);
+    v3add(cw, o->pos, dw);
+    { v3 t; v3cross(t, o->omg, dw); v3add(vc, o->vel, t); }
+    for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / o->inertia[c];
+    {
+        v3 F = {m->gravity[0] * o->mass, m->gravity[1] * o->mass, m->gravity[2] * o->mass}, T = {0, 0, 0};
+        if (o->ext_pending) {
+            v3 r, t;
+            v3sub(r, o->ext_pos, cw); v3cross(t, r, o->ext_force);
+            v3add(F, F, o->ext_force); v3add(T, T, t);
+            o->ext_pending = 0;
+        }
+        v3 wl, Iwv, gy, Tl, al, aw;
+        m3tmulv(wl, Rb, o->omg);
+        for (int c = 0; c < 3; c++) Iwv[c] = o->inertia[c] * wl[c];
+        v3cross(gy, wl, Iwv);
+        m3tmulv(Tl, Rb, T);
+        for (int c = 0; c < 3; c++) al[c] = (Tl[c] - gy[c]) * Iinv[c];
+        m3mulv(aw, Rb, al);
+        for (int c = 0; c < 3; c++) { vc[c] += m->dt * F[c] / o->mass; o->omg[c] += m->dt * aw[c]; }
+        (void)Iw;
+    }
+
+    /* rows */
+    enum { MAXR = OR_MAXD + 3 };
+    double jr[MAXR][OR_MAXD], ur[MAXR][OR_MAXD], jbl[MAXR][3], jba[MAXR][3], ubl[MAXR][3], uba[MAXR][3];
+    double diaginv[MAXR], rhs[MAXR], lim[MAXR], applied[MAXR];
+    int nrows = 0;
+    for (int i = 0; i < n; i++) {
+        double maximp = s->max_force[i] * m->dt;
+        if (maximp == 0) continue;
+        double f[OR_MAXD] = {0}; f[i] = 1.0;
+        for (int d = 0; d < n; d++) jr[nrows][d] = f[d];
+        aba_delta(m, &A, f, ur[nrows]);
+        for (int c = 0; c < 3; c++) { jbl[nrows][c] = jba[nrows][c] = ubl[nrows][c] = uba[nrows][c] = 0; }
+        double denom = ur[nrows][i];
+        diaginv[nrows] = denom > 2.2204460492503131e-16 ? 1.0 / denom : 0.0;
+        double v = s->qd[i];
+        double kp = s->motor_mode[i] == 1 ? s->kp[i] : 0.0, tp = s->motor_mode[i] == 1 ? s->target_pos[i] : 0.0;
+        double rhs_v = kp * ((tp - s->q[i]) / m->dt) + v + s->kd[i] * (s->target_vel[i] - v);
+        rhs[nrows] = (rhs_v - v) * diaginv[nrows];
+        lim[nrows] = maximp; applied[nrows] = 0;
+        nrows++;
+    }
+    if (o->p2p_enabled) {
+        double P[OR_MAXL][3], Q[OR_MAXL][4], J[6][OR_MAXD];
+        or_link_states(m, s->q, P, Q);
+        or_jacobian(m, s->q, m->tcp_link, J);
+        v3 pa, pb, rb, t;
+        v3cpy(pa, P[m->tcp_link]);
+        quat_rotate(o->quat, o->pivot_b, t); v3add(pb, o->pos, t);
+        v3sub(rb, pb, cw);
+        for (int i = 0; i < 3; i++) {
+            int r = nrows;
+            v3 nA = {0, 0, 0}; nA[i] = -1.0;     /* on the arm: -e_i; on the object: +e_i */
+            double f[OR_MAXD];
+            for (int d = 0; d < n; d++) { jr[r][d] = -J[i][d]; f[d] = jr[r][d]; }
+            aba_delta(m, &A, f, ur[r]);
+            v3 nB = {0, 0, 0}; nB[i] = 1.0;
+            v3cpy(jbl[r], nB); v3cross(jba[r], rb, nB);
+            for (int c = 0; c < 3; c++) ubl[r][c] = jbl[r][c] / o->mass;
+            { v3 jl, ul; m3tmulv(jl, Rb, jba[r]); for (int c = 0; c < 3; c++) ul[c] = jl[c] * Iinv[c]; m3mulv(uba[r], Rb, ul); }
+            double denom = 0;
+            for (int d = 0; d < n; d++) denom += jr[r][d] * ur[r][d];
+            denom += v3dot(jbl[r], ubl[r]) + v3dot(jba[r], uba[r]);
+            diaginv[r] = denom > 2.2204460492503131e-16 ? 1.0 / denom : 0.0;
+            double rel = 0;
+            for (int d = 0; d < n; d++) rel += jr[r][d] * s->qd[d];
+            rel += v3dot(jbl[r], vc) + v3dot(jba[r], o->omg);
+            double pos_error = (pa[i] - pb[i]) * nA[i];              /* (pivotA - pivotB) . normal */
+            double positional = -pos_error * o->erp / m->dt;
+            rhs[r] = (positional + (0.0 - rel)) * diaginv[r];
+            lim[r] = o->max_impulse; applied[r] = 0;
+            nrows++;
+        }
+    }
+    double dv[OR_MAXD] = {0}, dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
+    for (int it = 0; it < m->solver_iters; it++) {
+        double resid = 0;
+        for (int jj = 0; jj < nrows; jj++) {
+            int r = (it & 1) ? jj : nrows - 1 - jj;
+            double dot = 0;
+            for (int d = 0; d < n; d++) dot += jr[r][d] * dv[d];
+            dot += v3dot(jbl[r], dvl) + v3dot(jba[r], dva);
+            double delta = rhs[r] - dot * diaginv[r];
+            double sum = applied[r] + delta;
+            if (sum < -lim[r]) { delta = -lim[r] - applied[r]; applied[r] = -lim[r]; }
+            else if (sum > lim[r]) { delta = lim[r] - applied[r]; applied[r] = lim[r]; }
+            else applied[r] = sum;
+            for (int d = 0; d < n; d++) dv[d] += ur[r][d] * delta;
+            for (int c = 0; c < 3; c++) { dvl[c] += ubl[r][c] * delta; dva[c] += uba[r][c] * delta; }
+            double dvel = diaginv[r] != 0 ? delta / diaginv[r] : 0.0;
+            if (dvel * dvel > resid) resid = dvel * dvel;
+        }
+        if (resid <= m->solver_residual_threshold) break;
+    }
+    for (int i = 0; i < n; i++) { s->qd[i] += dv[i]; s->q[i] += m->dt * s->qd[i]; }
+    /* object: apply, integrate (exponential map on the orientation), convert back to the base-link COM */
+    for (int c = 0; c < 3; c++) { vc[c] += dvl[c]; o->omg[c] += dva[c]; }
+    v3 cnew;
+    for (int c = 0; c < 3; c++) cnew[c] = cw[c] + m->dt * vc[c];
+    {
+        double wn = v3norm(o->omg), ang = wn * m->dt;
+        double dq[4] = {0, 0, 0, 1};
+        if (wn > 1e-300) { double sn = sin(0.5 * ang) / wn; dq[0] = o->omg[0] * sn; dq[1] = o->omg[1] * sn; dq[2] = o->omg[2] * sn; dq[3] = cos(0.5 * ang); }
+        double qn[4]; quat_mul(qn, dq, o->quat);
+        double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+        for (int c = 0; c < 4; c++) o->quat[c] = qn[c] / nn;
+    }
+    quat_rotate(o->quat, o->com_off, dw);
+    v3sub(o->pos, cnew, dw);
+    { v3 t; v3cross(t, o->omg, dw); v3sub(o->vel, vc, t); }
+}
+
 /* Robot.step_sim (robot.py:131-141): gravity compensation (base_robot_arm.py:174-189) then stepSimulation */
 void or_step_sim(const OrModel* m, OrState* s)
 {

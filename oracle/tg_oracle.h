@@ -59,6 +59,27 @@ typedef struct {
     double target_pos[OR_MAXD], target_vel[OR_MAXD], kp[OR_MAXD], kd[OR_MAXD], max_force[OR_MAXD];
 } OrState;
 
+/* free rigid body (a pybullet floating-base multibody whose links are fixed to the base, e.g. the balance pole)
+ * hanging on the arm by a point-to-point constraint (object_balance_env.py:261-283).  [EXT] conventions restated:
+ * get/resetBasePositionAndOrientation act on the base link's inertial (COM) frame; velocities are world-frame;
+ * createConstraint(JOINT_POINT2POINT) -> btMultiBodyPoint2Point: 3 rows along -x,-y,-z, Baumgarte term
+ * erp (0.2) * gap / dt, |impulse| <= 500; applyExternalForce(WORLD_FRAME) lasts one stepSimulation. */
+typedef struct {
+    int enabled;
+    double mass, inertia[3]; /* composite of base + fixed links about the composite COM, body axes */
+    double com_off[3];       /* composite COM minus base-link COM, body frame */
+    double pos[3], quat[4];  /* base-link COM pose (what getBasePositionAndOrientation returns) */
+    double vel[3], omg[3];   /* world velocity of the base-link COM, world angular velocity */
+    double ext_force[3], ext_pos[3]; /* pending applyExternalForce (world), consumed by the next step */
+    int ext_pending;
+    int p2p_enabled;
+    double pivot_b[3];       /* constraint pivot in the base-link COM frame (childFramePosition) */
+    double erp, max_impulse;
+} OrObject;
+
+/* Robot.step_sim() with the object in the world: gravity compensation + stepSimulation (motor rows + P2P rows) */
+void or_step_sim_obj(const OrModel* m, OrState* s, OrObject* o);
+
 /* ---- frame math (pybullet helpers used at base_robot_arm.py:47-118) ---- */
 void or_quat_from_euler(const double rpy[3], double q[4]);
 void or_euler_from_quat(const double q[4], double rpy[3]);

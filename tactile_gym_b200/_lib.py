@@ -8,9 +8,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtactile_gym_b200.so")
 
-TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 4
+TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 8
 TG_TOPO_CHAIN6, TG_TOPO_MG400 = 0, 1
-TG_TASK_EDGE_FOLLOW = 0
+TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE = 0, 1
 
 D3 = C.c_double * 3
 D9 = C.c_double * 9
@@ -46,6 +46,9 @@ class TgTask(C.Structure):
         ("workframe_pos", D3), ("workframe_rpy", D3), ("tcp_lims", (C.c_double * 2) * 6),
         ("edge_pos", D3), ("edge_len", C.c_double), ("edge_height", C.c_double), ("termination_dist", C.c_double),
         ("embed_lo", C.c_double), ("embed_hi", C.c_double), ("init_rpy", D3), ("draw_default", C.c_double * TG_MAXDRAW),
+        ("obj_mass", C.c_double), ("obj_inertia", D3), ("obj_com_off", D3), ("obj_base_com", D3), ("obj_init_rpy", D3),
+        ("obj_base_w", C.c_double), ("obj_base_h", C.c_double), ("obj_force", C.c_double),
+        ("obj_term_deg", C.c_double), ("obj_term_pos", C.c_double), ("p2p_erp", C.c_double), ("p2p_max_impulse", C.c_double),
     ]
 
 

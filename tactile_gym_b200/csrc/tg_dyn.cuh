@@ -458,13 +458,11 @@ struct Motors {
     double target_pos[NB], target_vel[NB];
 };
 
-// One Robot.step_sim(): gravity compensation + stepSimulation with motor rows only.
-// Returns the number of PGS sweeps executed (diagnostics).
+// First half of one Robot.step_sim(): gravity compensation + unconstrained velocity update; leaves A = M^-1.
 template <class T>
-TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot)
+TGD void robot_pre(const TgArm& arm, const TgPhysics& ph, const double* q, double* qd, const double (&sc)[T::NB][2], double (&A)[T::NB][T::NB])
 {
     constexpr int NB = T::NB;
-    double A[NB][NB]; // M^-1
     double qdd[NB];
     {
         Kin<NB> k;
@@ -501,6 +499,16 @@ TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, do
     }
 #pragma unroll
     for (int i = 0; i < NB; i++) qd[i] += ph.dt * qdd[i];
+}
+
+// One Robot.step_sim(): gravity compensation + stepSimulation with motor rows only.
+// Returns the number of PGS sweeps executed (diagnostics).
+template <class T>
+TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot)
+{
+    constexpr int NB = T::NB;
+    double A[NB][NB]; // M^-1
+    robot_pre<T>(arm, ph, q, qd, sc, A);
 
     // motor rows: J = e_i, response column A[:, i], |impulse| <= force * dt
     double rhs[NB], dinv[NB], applied[NB], dv[NB];
@@ -550,6 +558,208 @@ TGD int substep(const TgArm& arm, const TgPhysics& ph, double* q, double* qd, do
         const double d = ph.dt * qd[i];
         q[i] += d;
         sc_advance(sc[i], q[i], d);
+    }
+    return it;
+}
+
+template <class T> TGD void tcp_world(const TgArm& arm, const Kin<T::NB>& k, double* pos, double* quat);
+template <class T> TGD void tcp_jacobian(const TgArm& arm, const Kin<T::NB>& k, const double* tcp_pos, double (&J)[6][T::NB]);
+
+// Free rigid body hanging on the TCP by a point-to-point constraint (object_balance).  pos/quat: base-link COM
+// pose, vel: world velocity of that point, omg: world angular velocity.
+struct ObjState {
+    double pos[3], quat[4], vel[3], omg[3];
+    double ext_pos[3]; // world point where the one-step external force applies
+    int ext_pending;
+    double grav_z, pivot_z; // per-episode gravity; constraint pivot z in the base-link COM frame
+};
+
+// Robot.step_sim() with the object in the world: 6 motor rows + 3 point-to-point rows
+// ([EXT] btMultiBodyPoint2Point: rows along -x,-y,-z on the arm / +x,+y,+z on the object, Baumgarte erp * gap / dt).
+template <class T>
+TGD int substep_obj(const TgArm& arm, const TgPhysics& ph, const TgTask& task, double* q, double* qd, double (&sc)[T::NB][2],
+                    const Motors<T::NB>& mot, ObjState& o)
+{
+    constexpr int NB = T::NB;
+    constexpr int NR = NB + 3;
+    double A[NB][NB];
+    robot_pre<T>(arm, ph, q, qd, sc, A);
+
+    // object: unconstrained update about the composite COM (gravity, one-step external force, gyroscopic torque)
+    double Rb[9], dw[3], cw[3], vc[3], Iinv[3];
+    mat_from_quat(o.quat, Rb);
+    m3mulv(dw, Rb, task.obj_com_off);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { cw[c] = o.pos[c] + dw[c]; Iinv[c] = 1.0 / task.obj_inertia[c]; }
+    {
+        double t[3];
+        v3cross(t, o.omg, dw);
+#pragma unroll
+        for (int c = 0; c < 3; c++) vc[c] = o.vel[c] + t[c];
+        double F[3] = {0.0, 0.0, o.grav_z * task.obj_mass}, Tq[3] = {0, 0, 0};
+        if (o.ext_pending) {
+            const double ef[3] = {0.0, 0.0, -task.obj_force};
+            double r[3] = {o.ext_pos[0] - cw[0], o.ext_pos[1] - cw[1], o.ext_pos[2] - cw[2]};
+            v3cross(Tq, r, ef);
+            F[2] += ef[2];
+            o.ext_pending = 0;
+        }
+        double wl[3], Iwv[3], gy[3], Tl[3], al[3], aw[3];
+        m3tmulv(wl, Rb, o.omg);
+#pragma unroll
+        for (int c = 0; c < 3; c++) Iwv[c] = task.obj_inertia[c] * wl[c];
+        v3cross(gy, wl, Iwv);
+        m3tmulv(Tl, Rb, Tq);
+#pragma unroll
+        for (int c = 0; c < 3; c++) al[c] = (Tl[c] - gy[c]) * Iinv[c];
+        m3mulv(aw, Rb, al);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { vc[c] += ph.dt * F[c] / task.obj_mass; o.omg[c] += ph.dt * aw[c]; }
+    }
+
+    // rows 0..NB-1: motors (J = e_i); rows NB..NB+2: point-to-point
+    double ur[3][NB], jr[3][NB], jba[3][3], uba[3][3]; // p2p rows: arm jacobian / response, object angular jacobian / response
+    double rhs[NR], dinv[NR], diag[NR], applied[NR];
+    const double lim_m = mot.max_force * ph.dt;
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        diag[i] = A[i][i];
+        dinv[i] = diag[i] > 2.2204460492503131e-16 ? 1.0 / diag[i] : 0.0;
+        const double v = qd[i];
+        const double pos_stab = mot.mode == 1 ? mot.kp * ((mot.target_pos[i] - q[i]) / ph.dt) : 0.0;
+        const double rhs_v = pos_stab + v + mot.kd * (mot.target_vel[i] - v);
+        rhs[i] = (rhs_v - v) * dinv[i];
+        applied[i] = 0;
+    }
+    {
+        Kin<NB> k;
+        fk_sc<T>(arm, sc, k);
+        double pa[3], tq[4], J[6][NB], pb[3], rb[3], t[3];
+        tcp_world<T>(arm, k, pa, tq);
+        tcp_jacobian<T>(arm, k, pa, J);
+        const double pl[3] = {0.0, 0.0, o.pivot_z};
+        m3mulv(t, Rb, pl);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { pb[c] = o.pos[c] + t[c]; rb[c] = pb[c] - cw[c]; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double nB[3] = {0, 0, 0};
+            nB[i] = 1.0;
+            double denom = 0, rel = 0;
+#pragma unroll
+            for (int d = 0; d < NB; d++) jr[i][d] = -J[i][d];
+#pragma unroll
+            for (int d = 0; d < NB; d++) {
+                double u = 0;
+#pragma unroll
+                for (int e = 0; e < NB; e++) u += A[d][e] * jr[i][e];
+                ur[i][d] = u;
+                denom += jr[i][d] * u;
+                rel += jr[i][d] * qd[d];
+            }
+            double jl[3], ul[3];
+            v3cross(jba[i], rb, nB);
+            m3tmulv(jl, Rb, jba[i]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) ul[c] = jl[c] * Iinv[c];
+            m3mulv(uba[i], Rb, ul);
+            denom += 1.0 / task.obj_mass + v3dot(jba[i], uba[i]);
+            rel += vc[i] + v3dot(jba[i], o.omg);
+            diag[NB + i] = denom;
+            dinv[NB + i] = denom > 2.2204460492503131e-16 ? 1.0 / denom : 0.0;
+            const double pos_error = -(pa[i] - pb[i]);               // (pivotA - pivotB) . (-e_i)
+            const double positional = -pos_error * task.p2p_erp / ph.dt;
+            rhs[NB + i] = (positional - rel) * dinv[NB + i];
+            applied[NB + i] = 0;
+        }
+    }
+    double dv[NB], dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < NB; i++) dv[i] = 0;
+    auto row_m = [&](int r, double& resid) {
+        double delta = rhs[r] - dv[r] * dinv[r];
+        const double sum = applied[r] + delta;
+        const bool lo = sum < -lim_m, hi = sum > lim_m;
+        delta = lo ? (-lim_m - applied[r]) : (hi ? (lim_m - applied[r]) : delta);
+        applied[r] = lo ? -lim_m : (hi ? lim_m : sum);
+#pragma unroll
+        for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
+        const double dvel = delta * diag[r];
+        resid = fmax(resid, dvel * dvel);
+    };
+    auto row_p = [&](int i, double& resid) {
+        const int r = NB + i;
+        const double lim = task.p2p_max_impulse;
+        double dot = dvl[i] + v3dot(jba[i], dva);
+#pragma unroll
+        for (int d = 0; d < NB; d++) dot += jr[i][d] * dv[d];
+        double delta = rhs[r] - dot * dinv[r];
+        const double sum = applied[r] + delta;
+        const bool lo = sum < -lim, hi = sum > lim;
+        delta = lo ? (-lim - applied[r]) : (hi ? (lim - applied[r]) : delta);
+        applied[r] = lo ? -lim : (hi ? lim : sum);
+#pragma unroll
+        for (int d = 0; d < NB; d++) dv[d] += ur[i][d] * delta;
+        dvl[i] += delta / task.obj_mass;
+#pragma unroll
+        for (int c = 0; c < 3; c++) dva[c] += uba[i][c] * delta;
+        const double dvel = delta * diag[r];
+        resid = fmax(resid, dvel * dvel);
+    };
+    int it = 0;
+#pragma unroll 1
+    for (; it < ph.solver_iters; it++) {
+        double resid = 0;
+        if (it & 1) {
+            if (lim_m != 0.0) {
+#pragma unroll
+                for (int r = 0; r < NB; r++) row_m(r, resid);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++) row_p(i, resid);
+        } else {
+#pragma unroll
+            for (int i = 2; i >= 0; i--) row_p(i, resid);
+            if (lim_m != 0.0) {
+#pragma unroll
+                for (int r = NB - 1; r >= 0; r--) row_m(r, resid);
+            }
+        }
+        if (resid <= ph.solver_residual_threshold) { it++; break; }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        qd[i] += dv[i];
+        const double d = ph.dt * qd[i];
+        q[i] += d;
+        sc_advance(sc[i], q[i], d);
+    }
+    // object: apply the impulses, integrate (exponential map), back to the base-link COM
+    double cnew[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { vc[c] += dvl[c]; o.omg[c] += dva[c]; cnew[c] = cw[c] + ph.dt * vc[c]; }
+    {
+        const double wn = sqrt(v3dot(o.omg, o.omg)), ang = wn * ph.dt;
+        double dq[4] = {0, 0, 0, 1};
+        if (wn > 1e-300) {
+            double sn, cs;
+            sincos(0.5 * ang, &sn, &cs);
+            sn /= wn;
+            dq[0] = o.omg[0] * sn; dq[1] = o.omg[1] * sn; dq[2] = o.omg[2] * sn; dq[3] = cs;
+        }
+        double qn[4];
+        quat_mul(qn, dq, o.quat);
+        const double nn = 1.0 / sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) o.quat[c] = qn[c] * nn;
+    }
+    mat_from_quat(o.quat, Rb);
+    m3mulv(dw, Rb, task.obj_com_off);
+    {
+        double t[3];
+        v3cross(t, o.omg, dw);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { o.pos[c] = cnew[c] - dw[c]; o.vel[c] = vc[c] - t[c]; }
     }
     return it;
 }

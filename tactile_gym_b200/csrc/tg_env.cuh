@@ -34,6 +34,9 @@ struct EnvBuffers {
     double* stim;         // [N][12] R(9) t(3) of the stimulus frame
     double* tcp;          // [N][7] tcp world pos + quat (state export)
     const double* rest_q; // [NB]
+    // free object (object_balance): [N][13] pos quat vel omg, [N][4] ext force point + pending flag, [N] gravity_z
+    double *obj, *obj_ext, *grav;
+    double *sb_obj, *sb_obj_ext, *sb_grav;
     // standby start-of-episode state
     double *sb_q, *sb_qd, *sb_embed, *sb_ang, *sb_cam, *sb_stim, *sb_tcp;
     int* sb_substeps;
@@ -48,7 +51,58 @@ template <int NB>
 struct EpisodeStart {
     double q[NB], qd[NB], embed, edge_ang, cam[12], stim[12], tcp[7];
     int substeps;
+    ObjState obj; // object_balance only
 };
+
+TGD void obj_load(const double* o13, const double* e4, double g, double embed, const TgTask& task, ObjState& o)
+{
+#pragma unroll
+    for (int c = 0; c < 3; c++) { o.pos[c] = o13[c]; o.vel[c] = o13[7 + c]; o.omg[c] = o13[10 + c]; o.ext_pos[c] = e4[c]; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) o.quat[c] = o13[3 + c];
+    o.ext_pending = e4[3] != 0.0;
+    o.grav_z = g;
+    o.pivot_z = -task.obj_base_h * 0.5 + embed; // update_constraints (object_balance_env.py:285-293)
+}
+TGD void obj_store(double* o13, double* e4, const ObjState& o)
+{
+#pragma unroll
+    for (int c = 0; c < 3; c++) { o13[c] = o.pos[c]; o13[7 + c] = o.vel[c]; o13[10 + c] = o.omg[c]; e4[c] = o.ext_pos[c]; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) o13[3 + c] = o.quat[c];
+    e4[3] = o.ext_pending ? 1.0 : 0.0;
+}
+// stimulus frame of the object = its base LINK frame: R(quat), pos - R base_com
+TGD void obj_stim(const TgTask& task, const ObjState& o, double* stim)
+{
+    double R[9], t[3];
+    mat_from_quat(o.quat, R);
+    m3mulv(t, R, task.obj_base_com);
+#pragma unroll
+    for (int i = 0; i < 9; i++) stim[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) stim[9 + i] = o.pos[i] - t[i];
+}
+// object_balance reward / termination (object_balance_env.py:470-526): roll / pitch more than 35 deg from the initial
+// orientation, or the base more than 0.1 m from its initial position
+TGD void balance_step_data(const TgTask& task, const ObjState& o, double embed, int steps, float* reward, unsigned char* done)
+{
+    double rpy[3];
+    euler_from_quat(o.quat, rpy);
+    bool fall = false;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const double cur = rpy[c] * 180.0 / M_PI, ini = task.obj_init_rpy[c] * 180.0 / M_PI;
+        double m = fmod((cur - ini) + 180.0, 360.0);
+        if (m < 0) m += 360.0; // numpy's % has the sign of the divisor
+        if (fabs(m - 180.0) > task.obj_term_deg) fall = true;
+    }
+    const double ip[3] = {task.workframe_pos[0], task.workframe_pos[1], task.workframe_pos[2] + task.obj_base_h * 0.5 - embed};
+    const double dx = o.pos[0] - ip[0], dy = o.pos[1] - ip[1], dz = o.pos[2] - ip[2];
+    if (sqrt(dx * dx + dy * dy + dz * dz) > task.obj_term_pos) fall = true;
+    *reward = 1.0f;
+    *done = (fall || steps >= task.max_steps) ? 1 : 0;
+}
 
 TGD int env_index(const EnvBuffers& b)
 {
@@ -166,9 +220,11 @@ __device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, co
         }
         b.reset_count[e] = cnt + 1;
     }
-    const double embed = draw[0], edge_ang = draw[1];
+    const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
+    // edge_follow draws: embed_dist, edge_ang; object_balance draws: gravity_z, embed_dist, fx, fy
+    const double embed = balance ? draw[1] : draw[0], edge_ang = balance ? 0.0 : draw[1];
     out.embed = embed; out.edge_ang = edge_ang;
-    {
+    if (!balance) {
         double s, c;
         sincos(edge_ang * 0.5, &s, &c);
         double qz[4] = {0, 0, s, c}, R[9]; // getQuaternionFromEuler([0,0,ang]) (edge_follow_env.py:241)
@@ -185,7 +241,7 @@ __device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, co
     double tpos[3], targ_orn[4];
     {
         double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
-        const double lp[3] = {0.0, 0.0, embed};
+        const double lp[3] = {0.0, 0.0, balance ? 0.0 : embed}; // update_init_pose: edge_follow_env.py:301-309 / base_object_env.py
         quat_from_euler(task.workframe_rpy, wq);
         quat_from_euler(task.init_rpy, tq);
         mat_from_quat(wq, R);
@@ -251,6 +307,23 @@ __device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, co
 #pragma unroll
         for (int c = 0; c < 4; c++) out.tcp[3 + c] = tq[c];
     }
+    if (balance) {
+        // reset_object (object_balance_env.py:322-358): pole back at init_obj_pos / init_obj_orn, at rest, 0.1 N pushing
+        // down at a random point of the base plate during the next stepSimulation (apply_random_force_base :360-381)
+        ObjState& o = out.obj;
+        o.pos[0] = task.workframe_pos[0]; o.pos[1] = task.workframe_pos[1];
+        o.pos[2] = task.workframe_pos[2] + task.obj_base_h * 0.5 - embed;
+        quat_from_euler(task.obj_init_rpy, o.quat);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { o.vel[c] = 0.0; o.omg[c] = 0.0; }
+        o.ext_pos[0] = o.pos[0] + draw[2] * task.obj_base_w * 0.5;
+        o.ext_pos[1] = o.pos[1] + draw[3] * task.obj_base_w * 0.5;
+        o.ext_pos[2] = o.pos[2];
+        o.ext_pending = 1;
+        o.grav_z = draw[0];
+        o.pivot_z = -task.obj_base_h * 0.5 + embed;
+        obj_stim(task, o, out.stim);
+    }
 }
 
 template <int NB>
@@ -263,6 +336,7 @@ TGD void store_live(const EnvBuffers& b, int e, const EpisodeStart<NB>& s)
     for (int c = 0; c < 12; c++) { b.cam[(size_t)e * 12 + c] = s.cam[c]; b.stim[(size_t)e * 12 + c] = s.stim[c]; }
 #pragma unroll
     for (int c = 0; c < 7; c++) b.tcp[(size_t)e * 7 + c] = s.tcp[c];
+    if (b.obj) { obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, s.obj); b.grav[e] = s.obj.grav_z; }
 }
 
 template <int NB>
@@ -275,6 +349,7 @@ TGD void store_standby(const EnvBuffers& b, int e, const EpisodeStart<NB>& s)
     for (int c = 0; c < 12; c++) { b.sb_cam[(size_t)e * 12 + c] = s.cam[c]; b.sb_stim[(size_t)e * 12 + c] = s.stim[c]; }
 #pragma unroll
     for (int c = 0; c < 7; c++) b.sb_tcp[(size_t)e * 7 + c] = s.tcp[c];
+    if (b.obj) { obj_store(b.sb_obj + (size_t)e * 13, b.sb_obj_ext + (size_t)e * 4, s.obj); b.sb_grav[e] = s.obj.grav_z; }
     __threadfence();
     b.sb_ready[e] = 1;
 }
@@ -290,6 +365,13 @@ TGD void consume_standby(const EnvBuffers& b, int e)
     for (int c = 0; c < 12; c++) { b.cam[(size_t)e * 12 + c] = b.sb_cam[(size_t)e * 12 + c]; b.stim[(size_t)e * 12 + c] = b.sb_stim[(size_t)e * 12 + c]; }
 #pragma unroll
     for (int c = 0; c < 7; c++) b.tcp[(size_t)e * 7 + c] = b.sb_tcp[(size_t)e * 7 + c];
+    if (b.obj) {
+#pragma unroll
+        for (int c = 0; c < 13; c++) b.obj[(size_t)e * 13 + c] = b.sb_obj[(size_t)e * 13 + c];
+#pragma unroll
+        for (int c = 0; c < 4; c++) b.obj_ext[(size_t)e * 4 + c] = b.sb_obj_ext[(size_t)e * 4 + c];
+        b.grav[e] = b.sb_grav[e];
+    }
     __threadfence();
     b.sb_ready[e] = 0;
 }
@@ -385,12 +467,21 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
         for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;
     }
+    const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
+    ObjState ob;
     {
         double sc[NB][2]; // (sin q, cos q): exact here, then advanced by the trig identity after every substep
 #pragma unroll
         for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
+        if (balance) {
+            obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);
 #pragma unroll 1
-        for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, sc, mot);
+            for (int s = 0; s < ph.substeps; s++) substep_obj<T>(arm, ph, task, q, qd, sc, mot, ob);
+            obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, sc, mot);
+        }
     }
 
     const int steps = b.steps[e] + 1;
@@ -402,7 +493,10 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     double tp[3], tq[4];
     tcp_world<T>(arm, k, tp, tq);
     float r; unsigned char d;
-    edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
+    if (balance) {
+        balance_step_data(task, ob, b.embed[e], steps, &r, &d);
+        obj_stim(task, ob, b.stim + (size_t)e * 12); // the pole moves: the raster needs its pose every step
+    } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
     reward[e] = r; done[e] = d;
     if (d && autoreset && b.pipeline) {
         // terminal camera for the terminal observation, then the standby becomes the live state

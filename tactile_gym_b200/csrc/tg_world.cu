@@ -83,7 +83,10 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->arm.topo == TG_TOPO_CHAIN6 && cfg->arm.nb != 6) return fail(TG_EINVAL, "CHAIN6 topology needs nb == 6");
     if (cfg->arm.topo == TG_TOPO_MG400 && cfg->arm.nb != 8) return fail(TG_EINVAL, "MG400 topology needs nb == 8");
     if (cfg->arm.topo != TG_TOPO_CHAIN6 && cfg->arm.topo != TG_TOPO_MG400) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
-    if (cfg->task.task != TG_TASK_EDGE_FOLLOW) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+    if (cfg->task.task != TG_TASK_EDGE_FOLLOW && cfg->task.task != TG_TASK_OBJECT_BALANCE) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+    if (cfg->task.task == TG_TASK_OBJECT_BALANCE && !(cfg->task.obj_mass > 0 && cfg->task.obj_inertia[0] > 0 && cfg->task.obj_inertia[1] > 0 && cfg->task.obj_inertia[2] > 0))
+        return fail(TG_EINVAL, "object_balance needs a free object with positive mass and inertia");
+    if (cfg->task.n_draws < 0 || cfg->task.n_draws > TG_MAXDRAW) return fail(TG_EINVAL, "n_draws must be in 0..%d", TG_MAXDRAW);
     if (cfg->sensor.n_prim <= 0 || cfg->sensor.n_prim > RASTER_MAXPRIM) return fail(TG_EINVAL, "n_prim must be in 1..%d", RASTER_MAXPRIM);
     if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->sensor.h_prims || !cfg->sensor.h_prim_nv || !cfg->h_rest_q)
         return fail(TG_EINVAL, "null table pointer in config");
@@ -133,6 +136,13 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         return rc;
     }
     w->standby_blocks = b.pipeline ? std::max(8, std::min(64, w->sm_count / 2)) : 0;
+    if (cfg->task.task == TG_TASK_OBJECT_BALANCE) {
+        if ((rc = dalloc(w, &b.obj, (size_t)13 * n)) || (rc = dalloc(w, &b.obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.grav, n)) ||
+            (rc = dalloc(w, &b.sb_obj, (size_t)13 * n)) || (rc = dalloc(w, &b.sb_obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.sb_grav, n))) {
+            tg_destroy(w);
+            return rc;
+        }
+    }
 
     // raster tables: border pixels get nodef = -1 and the baked grey value (tactile_sensor.py:289-292)
     {
@@ -313,7 +323,7 @@ extern "C" int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream)
     return launch_raster(w, d_obs, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int tg_state_size(const TgWorld* w) { return w ? 2 * w->nb + 7 + 4 : 0; }
+extern "C" int tg_state_size(const TgWorld* w) { return w ? 2 * w->nb + 7 + 4 + 14 : 0; }
 
 extern "C" int tg_get_state(TgWorld* w, double* h, void* stream)
 {
@@ -336,6 +346,17 @@ extern "C" int tg_get_state(TgWorld* w, double* h, void* stream)
         for (int i = 0; i < nb; i++) { o[i] = q[(size_t)i * n + e]; o[nb + i] = qd[(size_t)i * n + e]; }
         for (int c = 0; c < 7; c++) o[2 * nb + c] = tcp[(size_t)e * 7 + c];
         o[2 * nb + 7] = emb[e]; o[2 * nb + 8] = ang[e]; o[2 * nb + 9] = steps[e]; o[2 * nb + 10] = rs[e];
+        for (int c = 0; c < 14; c++) o[2 * nb + 11 + c] = 0.0;
+    }
+    if (w->eb.obj) {
+        std::vector<double> ob((size_t)13 * n), gr(n);
+        CK(cudaMemcpy(ob.data(), w->eb.obj, sizeof(double) * 13 * n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(gr.data(), w->eb.grav, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < n; e++) {
+            double* o = h + (size_t)e * sz + 2 * nb + 11;
+            for (int c = 0; c < 13; c++) o[c] = ob[(size_t)e * 13 + c];
+            o[13] = gr[e];
+        }
     }
     return TG_OK;
 }
@@ -359,6 +380,16 @@ extern "C" int tg_set_state(TgWorld* w, const double* h, void* stream)
     CK(cudaMemcpy(w->eb.embed, emb.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->eb.edge_ang, ang.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->eb.steps, steps.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    if (w->eb.obj) {
+        std::vector<double> ob((size_t)13 * n), gr(n);
+        for (int e = 0; e < n; e++) {
+            const double* o = h + (size_t)e * sz + 2 * nb + 11;
+            for (int c = 0; c < 13; c++) ob[(size_t)e * 13 + c] = o[c];
+            gr[e] = o[13];
+        }
+        CK(cudaMemcpy(w->eb.obj, ob.data(), sizeof(double) * 13 * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(w->eb.grav, gr.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
     return TG_OK;
 }
 

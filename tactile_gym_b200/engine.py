@@ -97,10 +97,130 @@ def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     return cfg, (dep, gray, mask, tris, rest, prims, prim_nv)
 
 
+def _uniform53(a, b):
+    """numpy RandomState.random_sample from two raw 32-bit MT19937 outputs (genrand_res53)"""
+    return ((a >> np.uint32(5)).astype(np.float64) * 67108864.0 + (b >> np.uint32(6)).astype(np.float64)) / 9007199254740992.0
+
+
+def edge_follow_draws(task):
+    """reset_task + update_edge draws (edge_follow_env.py:293-297, 240): [embed_dist,] edge_ang per reset"""
+    lo, hi = task.embed_lo, task.embed_hi
+
+    def draw(rng, rounds):
+        out = np.empty((rounds, 2))
+        if lo != hi:
+            u = rng.random_sample(2 * rounds)
+            out[:, 0] = lo + (hi - lo) * u[0::2]
+            out[:, 1] = -np.pi + (np.pi - (-np.pi)) * u[1::2]
+        else:
+            u = rng.random_sample(rounds)
+            out[:, 0] = lo
+            out[:, 1] = -np.pi + (np.pi - (-np.pi)) * u
+        return out
+
+    return draw
+
+
+def object_balance_draws(rand_gravity, rand_embed_dist, embed_lo, embed_hi, embed_default):
+    """ObjectBalanceEnv draws per reset, in the reference's call order (object_balance_env.py:300-313, 366-371):
+    [uniform(-1,-0.1)] [uniform(embed range)] choice([-1,1]) rand() choice([-1,1]) rand().
+    The calls are emulated on the raw 32-bit MT19937 stream so that a whole batch of resets is drawn at once:
+    uniform / rand take two outputs (53-bit double), choice takes one (randint(0, 2) = output & 1)."""
+    per = (2 if rand_gravity else 0) + (2 if rand_embed_dist else 0) + 6
+
+    def draw(rng, rounds):
+        raw = rng.randint(0, 2 ** 32, size=per * rounds, dtype=np.uint32).reshape(rounds, per)
+        k = 0
+        out = np.empty((rounds, 4))
+        if rand_gravity:
+            out[:, 0] = -1.0 + (-0.1 - (-1.0)) * _uniform53(raw[:, k], raw[:, k + 1]); k += 2
+        else:
+            out[:, 0] = -0.1
+        if rand_embed_dist:
+            out[:, 1] = embed_lo + (embed_hi - embed_lo) * _uniform53(raw[:, k], raw[:, k + 1]); k += 2
+        else:
+            out[:, 1] = embed_default
+        for col in (2, 3):
+            sign = np.where((raw[:, k] & np.uint32(1)) == 0, -1.0, 1.0); k += 1
+            out[:, col] = sign * _uniform53(raw[:, k], raw[:, k + 1]); k += 2
+        return out
+
+    return draw
+
+
+def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
+    """ObjectBalanceEnv.__init__ (rl_envs/nonprehensile_manipulation/object_balance/object_balance_env.py:22-124,
+    object_mode 'pole') as a TgConfig.  Returns (cfg, keepalive, draw_fn)."""
+    import json
+    import os
+
+    arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
+    if env_modes.get("object_mode", "pole") != "pole":
+        raise NotImplementedError("object_mode %r: only 'pole' is built" % env_modes.get("object_mode"))
+    if env_modes["control_mode"] != "TCP_velocity_control":
+        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
+    if arm_type != "ur5":
+        raise ValueError("object_balance has rest poses for the ur5 only among the built arms (rest_poses.py)")
+    typ, S = "standard", int(image_size[0])
+    mj = scene.load_model_json(arm_type, sensor, typ)
+    sj = scene.load_sensor_json(sensor, typ)
+    cam = sj["types"][typ]
+    arm, control_links = scene.reduce_model(mj, sensor, cam["cam_pos"], cam["cam_rpy"])
+    cfg = L.TgConfig()
+    cfg.n_envs, cfg.lanes_per_warp, cfg.arm = n_envs, lanes_per_warp, arm
+    cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 20.0) / (1.0 / 240.0))))   # :33-35 -> 12
+    t = cfg.task
+    t.task, t.max_steps = L.TG_TASK_OBJECT_BALANCE, int(max_steps)
+    idx = {"xy": [0, 1], "xyz": [0, 1, 2], "RxRy": [3, 4], "xyRxRy": [0, 1, 3, 4]}[env_modes["movement_mode"]]   # :416-442
+    t.act_dim = len(idx)
+    for k in range(6):
+        t.act_index[k] = idx[k] if k < len(idx) else -1
+    t.act_min, t.act_max = -0.25, 0.25
+    mv, ma = 0.01, 5.0 * (np.pi / 180)                                                          # :141-151
+    hi = [mv, mv, mv, ma, ma, 0.0]
+    for k in range(6):
+        t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
+    wf_pos, a45 = [0.55, 0.0, 0.35], 45 * np.pi / 180                                            # :73-92
+    lims = [(-0.1, 0.1)] * 3 + [(-a45, a45)] * 3
+    for k in range(3):
+        t.workframe_pos[k], t.workframe_rpy[k], t.init_rpy[k] = wf_pos[k], 0.0, 0.0
+    for k in range(6):
+        t.tcp_lims[k][0], t.tcp_lims[k][1] = lims[k]
+    with open(os.path.join(scene.ASSETS, "objects", "pole.json")) as f:
+        pole = json.load(f)
+    t.obj_mass = pole["mass"]
+    for k in range(3):
+        t.obj_inertia[k], t.obj_com_off[k], t.obj_base_com[k] = pole["inertia_diag"][k], pole["com_off"][k], pole["base_com"][k]
+        t.obj_init_rpy[k] = [0.0, 0.0, -np.pi / 2][k]                                            # :207
+    t.obj_base_w, t.obj_base_h, t.obj_force = 0.1, 0.0025, 0.1                                  # :170-172, :339
+    t.obj_term_deg, t.obj_term_pos = 35.0, 0.1                                                   # :58-59
+    t.p2p_erp, t.p2p_max_impulse = 0.2, 500.0                                                    # [EXT] bullet / pybullet defaults
+    embed_default = {"tactip": 0.0035, "digitac": 0.0015, "digit": 0.0015}[sensor]               # :63-68
+    lo, hi_e = {"tactip": (0.003, 0.006), "digitac": (0.001, 0.0025), "digit": (0.0015, 0.0025)}[sensor]   # :307-312
+    t.n_draws = 4
+    t.draw_default[0], t.draw_default[1], t.draw_default[2], t.draw_default[3] = -0.1, embed_default, 0.0, 0.0
+    dep, gray, mask = scene.load_refimg(sensor, typ, S)
+    tris = scene.load_stimulus("pole")
+    rest = scene.load_rest_pose("object_balance", arm_type, sensor, typ, control_links)
+    s = cfg.sensor
+    s.image_size, s.border_on = S, 1
+    s.fov_deg, s.near_, s.far_ = sj["fov"], sj["near"], sj["far"]
+    s.h_nodef_dep = dep.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_nodef_gray = gray.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+    prims, prim_nv = scene.merge_coplanar(tris)
+    s.n_prim = len(prims)
+    s.h_prims = prims.ctypes.data_as(C.POINTER(C.c_double))
+    s.h_prim_nv = prim_nv.ctypes.data_as(C.POINTER(C.c_int32))
+    cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
+    draw = object_balance_draws(bool(env_modes.get("rand_gravity", False)), bool(env_modes.get("rand_embed_dist", False)), lo, hi_e, embed_default)
+    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv), draw
+
+
 class TactileWorld:
     """N envs of one task on one device."""
 
-    def __init__(self, cfg, keepalive, device=0):
+    def __init__(self, cfg, keepalive, device=0, draw_fn=None):
         import torch
 
         if not torch.cuda.is_available():
@@ -119,6 +239,7 @@ class TactileWorld:
             self.term_obs = torch.zeros_like(self.obs)
             self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+        self._draw = draw_fn if draw_fn is not None else edge_follow_draws(cfg.task)
         self._rngs = [seeding.np_random(None)[0] for _ in range(self.n)]
         self._host_draws = None
         self._steps_since_check = 0
@@ -134,20 +255,6 @@ class TactileWorld:
             self._rngs[i], sd = seeding.np_random(s)
             out.append(sd)
         self._upload_draws(fresh=True)
-        return out
-
-    def _draw(self, rng, rounds):
-        """reset_task + update_edge draws (edge_follow_env.py:293-297, 240): [embed_dist,] edge_ang per reset"""
-        t = self.cfg.task
-        out = np.empty((rounds, 2))
-        if t.embed_lo != t.embed_hi:
-            u = rng.random_sample(2 * rounds)
-            out[:, 0] = t.embed_lo + (t.embed_hi - t.embed_lo) * u[0::2]
-            out[:, 1] = -np.pi + (np.pi - (-np.pi)) * u[1::2]
-        else:
-            u = rng.random_sample(rounds)
-            out[:, 0] = t.embed_lo
-            out[:, 1] = -np.pi + (np.pi - (-np.pi)) * u
         return out
 
     def _upload_draws(self, fresh=False):
@@ -170,7 +277,7 @@ class TactileWorld:
     def set_draws(self, draws):
         """Explicit draws [N, rounds, 2] (parity tests)."""
         arr = np.ascontiguousarray(draws, dtype=np.float64)
-        assert arr.shape[0] == self.n and arr.shape[2] == self.cfg.task.n_draws
+        assert arr.shape[0] == self.n and arr.shape[2] == self.cfg.task.n_draws, arr.shape
         L.check(self.lib.tg_set_draws(self.h, arr.ctypes.data, arr.shape[1]))
         self._host_draws = None
         self._steps_since_check = -(10 ** 9)

@@ -11,14 +11,14 @@ import time
 import numpy as np
 
 from . import spaces
-from .engine import TactileWorld, edge_follow_config
+from .engine import TactileWorld, edge_follow_config, object_balance_config
 
 try:  # pragma: no cover
     from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
 except Exception:  # noqa: BLE001
     _VecEnvBase = object
 
-CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config}
+CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": object_balance_config}
 
 
 class TactileVecEnv(_VecEnvBase):
@@ -35,8 +35,9 @@ class TactileVecEnv(_VecEnvBase):
             raise NotImplementedError("only observation_mode='tactile' is built")
         image_size = kw.get("image_size", [64, 64])
         max_steps = kw.get("max_steps", 250)
-        cfg, keep = CONFIG_BUILDERS[env_id](env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp)
-        self.world = TactileWorld(cfg, keep, device=device)
+        built = CONFIG_BUILDERS[env_id](env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp)
+        cfg, keep, draw = built if len(built) == 3 else (built[0], built[1], None)
+        self.world = TactileWorld(cfg, keep, device=device, draw_fn=draw)
         self.num_envs = n_envs
         S = int(image_size[0])
         self.observation_space = spaces.Dict({"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)})

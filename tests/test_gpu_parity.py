@@ -334,3 +334,75 @@ def test_other_arms_and_sensors_match_oracle(oracle, edge_modes, arm, sensor):
             mx, frac = _img_close(o, o2["tactile"][i])
             assert mx <= 1 and frac < 1e-3, (k, i, mx, frac)
     env.close()
+
+
+BALANCE_MODES = {"movement_mode": "xy", "control_mode": "TCP_velocity_control", "object_mode": "pole", "rand_gravity": True,
+                 "rand_embed_dist": True, "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5",
+                 "tactile_sensor_name": "tactip"}
+
+
+def _sync_balance(ref, row, nb=6):
+    for k in range(nb):
+        ref.s.q[k] = row[k]; ref.s.qd[k] = row[nb + k]
+    o = row[2 * nb + 11:]
+    for c in range(3):
+        ref.o.pos[c] = o[c]; ref.o.vel[c] = o[7 + c]; ref.o.omg[c] = o[10 + c]
+    for c in range(4):
+        ref.o.quat[c] = o[3 + c]
+    ref.steps = int(row[2 * nb + 9])
+
+
+@pytest.mark.parametrize("S,movement", [(128, "xy"), (256, "xyRxRy")])
+def test_object_balance_matches_oracle(oracle, S, movement):
+    """object_balance-v0 (BASELINE config 5 at S = 256): free pole on a point-to-point constraint, per-episode gravity,
+    one-step random push, fall termination; each step compared from an identical state."""
+    import tactile_gym_b200 as tg
+
+    modes = dict(BALANCE_MODES, movement_mode=movement)
+    n = 6
+    env = tg.make_vec("object_balance-v0", n, env_kwargs={"env_modes": modes, "image_size": [S, S], "max_steps": 250})
+    rng = np.random.RandomState(S)
+    draws = np.stack([rng.uniform(-1.0, -0.1, (n, 2)), rng.uniform(0.003, 0.006, (n, 2)),
+                      rng.choice([-1, 1], (n, 2)) * rng.rand(n, 2), rng.choice([-1, 1], (n, 2)) * rng.rand(n, 2)], axis=2)
+    env.world.set_draws(draws)
+    obs = env.reset()["tactile"]
+    st = env.world.get_state()
+    refs = []
+    for i in range(n):
+        r = oracle.ObjectBalanceOracle(image_size=S, movement_mode=movement)
+        r.reset(draws=draws[i, 0])
+        refs.append(r)
+        assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=2e-6)
+        assert np.allclose(st[i, 23:26], np.array(r.o.pos[:]), atol=1e-12) and np.allclose(st[i, 26:30], np.array(r.o.quat[:]), atol=1e-12)
+        assert st[i, 36] == draws[i, 0, 0]
+        _sync_balance(r, st[i])
+        mx, frac = _img_close(r.observation(), obs[i])
+        assert mx <= 1 and frac < 1e-3, (i, mx, frac)
+        assert (obs[i][..., 0][r.ref[2] == 0] > 0).sum() > 100     # the base plate presses into the skin
+    ever_done = np.zeros(n, dtype=bool)
+    act_dim = env.world.act_dim
+    for k in range(45):
+        act = rng.uniform(-0.25, 0.25, (n, act_dim)).astype(np.float32) * (0.0 if k < 25 else 1.0)
+        o2, rew, done, infos = env.step(act)
+        st = env.world.get_state()
+        for i, r in enumerate(refs):
+            if ever_done[i]:
+                continue
+            o, rr, dd, _ = r.step(act[i])
+            assert rr == rew[i] == 1.0 and bool(dd) == bool(done[i]), (k, i)
+            if dd:
+                ever_done[i] = True       # the env auto-reset; the terminal observation is checked instead
+                mx, frac = _img_close(o, infos[i]["terminal_observation"]["tactile"])
+                assert mx <= 1 and frac < 2e-3, (k, i, mx, frac)
+                continue
+            tol = 5e-6 if k == 0 else 1e-9  # step 0 starts from the (noisy) reset state on both sides
+            assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=tol)
+            assert np.allclose(st[i, 23:26], np.array(r.o.pos[:]), atol=tol)
+            assert np.allclose(st[i, 26:30], np.array(r.o.quat[:]), atol=tol * 10)
+            assert np.allclose(st[i, 30:36], np.array(list(r.o.vel[:]) + list(r.o.omg[:])), atol=max(tol, 1e-8) * 100)
+            _sync_balance(r, st[i])
+            mx, frac = _img_close(r.observation(), o2["tactile"][i])
+            assert mx <= 1 and frac < 1e-3, (k, i, mx, frac)
+    assert ever_done.any()                # with no control for 25 steps some poles fall past 35 degrees
+    assert not env.world.pipeline_error()
+    env.close()

@@ -117,3 +117,29 @@ def test_quantize_shortcut_is_exact(tmp_path):
     out = subprocess.run([exe, "7"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert " 0 uint8 mismatches" in out.stdout
+
+
+def test_balance_draws_emulate_the_numpy_call_sequence(oracle):
+    """object_balance draws are generated in batches from the raw MT19937 stream; they must equal the reference's
+    sequence of np_random.uniform / choice / rand calls (object_balance_env.py:300-313, 366-371)."""
+    from tactile_gym_b200 import seeding
+    from tactile_gym_b200.engine import object_balance_draws
+
+    for rg, re_ in [(True, True), (False, True), (True, False), (False, False)]:
+        fn = object_balance_draws(rg, re_, 0.003, 0.006, 0.0035)
+        a = fn(seeding.np_random(11)[0], 9)
+        rng = seeding.np_random(11)[0]
+        b = np.array([oracle.balance_draws(rng, "tactip", rg, re_) for _ in range(9)])
+        assert np.array_equal(a, b)
+
+
+def test_pole_asset_composite():
+    import json
+
+    from tactile_gym_b200 import scene
+
+    pole = json.load(open(os.path.join(scene.ASSETS, "objects", "pole.json")))
+    assert abs(pole["mass"] - 0.11) < 1e-15
+    assert abs(pole["com_off"][2] - ((0.01 * 0.00125 + 0.1 * 0.05) / 0.11 - 0.00125)) < 1e-15
+    prims, nv = scene.merge_coplanar(scene.load_stimulus("pole"))
+    assert prims.shape == (12, 4, 3) and (nv == 4).all()

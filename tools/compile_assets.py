@@ -256,6 +256,65 @@ def parse_urdf(urdf_path, want_visual=(), want_collision=()):
     return {"root": roots[0], "links": out_links}, meshes
 
 
+def box_inertia(mass, size):
+    """[EXT] btBoxShape::calculateLocalInertia with the full box size (the URDF margin does not change it)."""
+    lx, ly, lz = size
+    return [mass / 12.0 * (ly * ly + lz * lz), mass / 12.0 * (lx * lx + lz * lz), mass / 12.0 * (lx * lx + ly * ly)]
+
+
+def compile_free_object(urdf_path):
+    """A floating-base URDF whose joints are all fixed (pole.urdf): per-link mass / inertial frame / inertia
+    ([EXT] from the collision box, like loadURDF does without URDF_USE_INERTIA_FROM_FILE), the composite rigid body
+    about the composite COM, and the visual triangles in the BASE LINK frame."""
+    root = ET.parse(urdf_path).getroot()
+    links = {l.get("name"): l for l in root.findall("link")}
+    joints = root.findall("joint")
+    children = {j.find("child").get("link") for j in joints}
+    base = [n for n in links if n not in children][0]
+    frames = {base: (np.eye(3), np.zeros(3))}
+    pending = list(joints)
+    while pending:
+        for j in list(pending):
+            par = j.find("parent").get("link")
+            if par in frames:
+                assert j.get("type") == "fixed", "free objects must be rigid"
+                o = j.find("origin")
+                Rj = rpy_to_mat(vec(o.get("rpy") if o is not None else None))
+                tj = np.array(vec(o.get("xyz") if o is not None else None))
+                Rp, tp = frames[par]
+                frames[j.find("child").get("link")] = (Rp @ Rj, tp + Rp @ tj)
+                pending.remove(j)
+    parts, tris = [], []
+    for name, l in links.items():
+        R, t = frames[name]
+        inert = l.find("inertial")
+        mass = atof(inert.find("mass").get("value"))
+        io = inert.find("origin")
+        ixyz = np.array(vec(io.get("xyz") if io is not None else None))
+        irpy = vec(io.get("rpy") if io is not None else None)
+        col = l.find("collision")
+        box = col.find("geometry").find("box")
+        assert box is not None, "only box collision shapes are compiled for free objects"
+        co = col.find("origin")
+        assert np.allclose(vec(co.get("xyz")), ixyz) and np.allclose(vec(co.get("rpy")), irpy), "collision origin must equal the inertial origin"
+        Id = box_inertia(mass, vec(box.get("size")))
+        Rin = R @ rpy_to_mat(irpy)
+        parts.append({"link": name, "mass": mass, "com": (t + R @ ixyz).tolist(), "R": Rin.tolist(), "inertia_diag": Id})
+        for v in l.findall("visual"):
+            tris.append(geom_vertices(urdf_path, v) @ R.T + t)
+    M = sum(p["mass"] for p in parts)
+    com = sum(p["mass"] * np.array(p["com"]) for p in parts) / M
+    I = np.zeros((3, 3))
+    for p in parts:
+        Rp = np.array(p["R"]); d = np.array(p["com"]) - com
+        I += Rp @ np.diag(p["inertia_diag"]) @ Rp.T + p["mass"] * (d.dot(d) * np.eye(3) - np.outer(d, d))
+    assert np.allclose(I, np.diag(np.diag(I)), atol=1e-15), "composite inertia must be diagonal in the base frame"
+    base_com = np.array(parts[[p["link"] for p in parts].index(base)]["com"])
+    obj = {"base_link": base, "mass": M, "inertia_diag": np.diag(I).tolist(), "base_com": base_com.tolist(),
+           "com_off": (com - base_com).tolist(), "parts": parts, "source": os.path.relpath(urdf_path, REF)}
+    return obj, np.concatenate(tris)
+
+
 def convex_hull_vertices(tris):
     from scipy.spatial import ConvexHull
 
@@ -328,6 +387,10 @@ SENSOR_CAMERAS = {
     },
 }
 
+OBJECTS = {
+    "pole": "rl_env_assets/nonprehensile_manipulation/object_balance/pole/pole.urdf",
+}
+
 STIMULI = {
     "long_edge": "rl_env_assets/exploration/edge_follow/edge_stimuli/long_edge_flat/long_edge.urdf",
     "short_edge": "rl_env_assets/exploration/edge_follow/edge_stimuli/long_edge_flat/short_edge.urdf",
@@ -398,6 +461,16 @@ def main():
         json.dump(rest, f, indent=1)
     with open(os.path.join(OUT, "sensors.json"), "w") as f:
         json.dump(SENSOR_CAMERAS, f, indent=1)
+
+    # free objects (floating-base bodies whose links are all fixed to the base): composite inertia + visual triangles
+    os.makedirs(os.path.join(OUT, "objects"), exist_ok=True)
+    for name, rel in OBJECTS.items():
+        urdf = os.path.join(ASSETS, rel)
+        obj, tris = compile_free_object(urdf)
+        with open(os.path.join(OUT, "objects", name + ".json"), "w") as f:
+            json.dump(obj, f, indent=1)
+        np.savez_compressed(os.path.join(OUT, "stimuli", name + ".npz"), tris=tris.astype(np.float64))
+        print("object", name, "mass", obj["mass"], "tris", tris.shape)
 
     for name, rel in STIMULI.items():
         urdf = os.path.join(ASSETS, rel)
