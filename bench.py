@@ -37,6 +37,19 @@ ALG_BYTES = IMG * IMG + 64
 WORKLOAD = "edge_follow-v0 ur5+tactip %dx%d, %d envs/GPU, max_steps %d, actions iid U(-0.25,0.25) seed 0" % (IMG, IMG, N_ENVS, MAX_STEPS)
 
 
+def select_workload(name):
+    """default: BASELINE config 2 (the one the metric is quoted on).  'balance': config 5 per GPU
+    (object_balance-v0 ur5+tactip 256x256, 16384 envs over 8 GPUs = 2048 envs/GPU) - for the profiles, not the driver."""
+    global MODES, ENV_ID, N_ENVS, IMG, MAX_STEPS, ALG_BYTES, WORKLOAD
+    if name == "balance":
+        MODES = {"movement_mode": "xy", "control_mode": "TCP_velocity_control", "object_mode": "pole", "rand_gravity": True,
+                 "rand_embed_dist": True, "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5",
+                 "tactile_sensor_name": "tactip"}
+        ENV_ID, N_ENVS, IMG, MAX_STEPS = "object_balance-v0", 2048, 256, 250
+        ALG_BYTES = IMG * IMG + 92      # SURVEY.md 8(d), config 5
+        WORKLOAD = "object_balance-v0 ur5+tactip %dx%d, %d envs/GPU, max_steps %d, actions iid U(-0.25,0.25) seed 0" % (IMG, IMG, N_ENVS, MAX_STEPS)
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -77,13 +90,19 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": clk[len(clk) // 2] if clk else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_port_rate(seconds, image_size=IMG, seed=0):
+def make_oracle_env(seed):
+    from oracle import oracle as O
+
+    if ENV_ID == "object_balance-v0":
+        return O.ObjectBalanceOracle(image_size=IMG, max_steps=MAX_STEPS, seed=seed)
+    return O.EdgeFollowOracle(image_size=IMG, max_steps=MAX_STEPS, seed=seed)
+
+
+def cpu_port_rate(seconds, seed=0):
     """steps/s of the CPU oracle on ONE core: same env, same action distribution, auto-reset on done."""
     import numpy as np
 
-    from oracle import oracle as O
-
-    env = O.EdgeFollowOracle(image_size=image_size, max_steps=MAX_STEPS, seed=seed)
+    env = make_oracle_env(seed)
     env.reset()
     rng = np.random.RandomState(seed)
     n, t0 = 0, time.perf_counter()
@@ -100,13 +119,13 @@ def cpu_port_rate(seconds, image_size=IMG, seed=0):
 _WORKER_ENV = None
 
 
-def _cpu_worker_init():
+def _cpu_worker_init(workload="edge"):
     global _WORKER_ENV
     import numpy as np
 
-    from oracle import oracle as O
+    select_workload(workload)
 
-    env = O.EdgeFollowOracle(image_size=IMG, max_steps=MAX_STEPS, seed=os.getpid())
+    env = make_oracle_env(os.getpid())
     env.reset()
     _WORKER_ENV = (env, np.random.RandomState(os.getpid()))
 
@@ -141,7 +160,7 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_step = 3.0  # seconds of CPU work per "step" sample
     vals = []
-    with mp.get_context("spawn").Pool(cores, initializer=_cpu_worker_init) as pool:
+    with mp.get_context("spawn").Pool(cores, initializer=_cpu_worker_init, initargs=(args.workload,)) as pool:
         for k in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             res = pool.map(_cpu_worker, [per_step] * cores, chunksize=1)
@@ -167,9 +186,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU")
+    ap.add_argument("--workload", default="edge", choices=["edge", "balance"])
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (0: the workload's)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
+    select_workload(args.workload)
+    if not args.envs:
+        args.envs = N_ENVS
     if args.impl == "reference":
         return run_reference(args)
 
