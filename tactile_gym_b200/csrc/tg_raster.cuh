@@ -379,13 +379,13 @@ raster_kernel(const RasterArgs a)
         if (lane < n_tiles) {
             const float cl = (float)((lane & (tiles_x - 1)) * TILE_COLS), ch = cl + (TILE_COLS - 1);
             const float rl = (float)(row0 + (lane >> sh_tx) * TILE_ROWS), rh = rl + (TILE_ROWS - 1);
-            float dom[4] = {-1e30f, -1e30f, -1e30f, -1e30f}; // certified lower bound of 1/z of the nearest covering primitive
+            double dom[4] = {-1e300, -1e300, -1e300, -1e300}; // lower bound of 1/z of the nearest covering primitive (fp64)
             int dom_t = -1;
+            const double dcl = cl, dch = ch, drl = rl, drh = rh;
             for (int t = 0; t < a.nprim; t++) {
                 const PrimCoef& c = pc[t];
                 if (!c.valid || c.c_hi < cl || c.c_lo > ch || c.r_hi < rl || c.r_lo > rh) continue;
                 bool all_in = true, out = false;
-                float wv[4];
 #pragma unroll
                 for (int k = 0; k < 5; k++) {
                     const float kl = fmaf(c.fB[k], rl, c.fC[k]), kh = fmaf(c.fB[k], rh, c.fC[k]);
@@ -394,15 +394,19 @@ raster_kernel(const RasterArgs a)
                     const float mgk = k == 4 ? c.wmargin : c.margin;
                     all_in = all_in && (lo > mgk);
                     out = out || (hi < -mgk);
-                    if (k == 4) { wv[0] = v00; wv[1] = v01; wv[2] = v10; wv[3] = v11; }
                 }
                 if (out) continue;
                 if (all_in) {
                     my_in |= 1u << t;
-                    if (!any_clipped && wv[0] - c.wmargin > dom[0]) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) dom[k] = wv[k] - c.wmargin;
-                        dom_t = t;
+                    if (!any_clipped) {
+                        // exact occlusion needs 1/z at the corners in fp64 (grazing primitives have huge float margins)
+                        const double em = 1e-12 * ((fabs(c.eA[4]) + fabs(c.eB[4])) * S + fabs(c.eC[4]));
+                        const double w0 = c.eA[4] * dcl + c.eB[4] * drl + c.eC[4] - em;
+                        if (w0 > dom[0]) {
+                            dom[0] = w0; dom[1] = c.eA[4] * dch + c.eB[4] * drl + c.eC[4] - em;
+                            dom[2] = c.eA[4] * dcl + c.eB[4] * drh + c.eC[4] - em; dom[3] = c.eA[4] * dch + c.eB[4] * drh + c.eC[4] - em;
+                            dom_t = t;
+                        }
                     }
                 } else my_part |= 1u << t;
             }
@@ -413,9 +417,9 @@ raster_kernel(const RasterArgs a)
                     const int t = __ffs(cand) - 1;
                     cand &= cand - 1;
                     const PrimCoef& c = pc[t];
-                    const float kl = fmaf(c.fB[4], rl, c.fC[4]), kh = fmaf(c.fB[4], rh, c.fC[4]);
-                    const float w0 = fmaf(c.fA[4], cl, kl) + c.wmargin, w1 = fmaf(c.fA[4], ch, kl) + c.wmargin;
-                    const float w2 = fmaf(c.fA[4], cl, kh) + c.wmargin, w3 = fmaf(c.fA[4], ch, kh) + c.wmargin;
+                    const double em = 1e-12 * ((fabs(c.eA[4]) + fabs(c.eB[4])) * S + fabs(c.eC[4]));
+                    const double w0 = c.eA[4] * dcl + c.eB[4] * drl + c.eC[4] + em, w1 = c.eA[4] * dch + c.eB[4] * drl + c.eC[4] + em;
+                    const double w2 = c.eA[4] * dcl + c.eB[4] * drh + c.eC[4] + em, w3 = c.eA[4] * dch + c.eB[4] * drh + c.eC[4] + em;
                     const bool hidden = w0 < dom[0] && w1 < dom[1] && w2 < dom[2] && w3 < dom[3];
                     if (!hidden || t == dom_t) { if ((my_in >> t) & 1u) keep_in |= 1u << t; else keep_part |= 1u << t; }
                 }
