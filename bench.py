@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="edge", choices=["edge", "balance"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (0: the workload's)")
+    ap.add_argument("--phases", default="staggered", choices=["staggered", "sync"],
+                    help="staggered: episode phases uniform in [0, max_steps) as in a long-running job, so every timed "
+                         "step carries its share of episode resets; sync: all envs start their episode together")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     select_workload(args.workload)
@@ -221,6 +224,10 @@ def main():
     env.reset()
     w = env.world
     dev = w.device
+    if args.phases == "staggered":
+        st = w.get_state()
+        st[:, st.shape[1] - 14 - 2] = np.random.RandomState(1000 + rank).randint(0, MAX_STEPS, size=n)   # the `steps` field
+        w.set_state(st)
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
     acts = (torch.rand((W + K, n, w.act_dim), device=dev, generator=gen) - 0.5) * 0.5
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -300,7 +307,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_envs": n * world, "parallelism": "env-sharded x%d, no data-path collective" % world,
                        "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events",
-                       "physics_ms": t_phys, "raster_ms": t_raster, "lanes_per_warp": int(w.cfg.lanes_per_warp)},
+                       "physics_ms": t_phys, "raster_ms": t_raster, "lanes_per_warp": int(w.cfg.lanes_per_warp), "episode_phases": args.phases},
             "e2e": {"value": n * world * Ke / (t_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step,
                     "d2h_bytes_per_step": env.d2h_bytes_per_step, "steps": Ke},
             "gpu_launches": int(launches),

@@ -158,8 +158,11 @@ int tg_set_draws(TgWorld* w, const double* h_draws, int rounds);
 /* Same upload, but the sequence CONTINUES: pre-computed standby episodes (which already consumed their draws) stay
  * valid.  h_draws[i][0] must be env i's first unconsumed draw (see tg_get_reset_counts). */
 int tg_refill_draws(TgWorld* w, const double* h_draws, int rounds);
-/* 1 if a finished env ever found no standby episode (cannot happen when episodes last >= 2 steps); synchronises */
+/* Sticky error flag of the reset pipeline (0: none; nothing raises it since the slots became resumable); synchronises */
 int tg_pipeline_error(TgWorld* w, void* stream);
+/* Number of episode ends so far that found their pre-computed next episode unfinished and completed it inline
+ * (exact either way; a performance counter: episodes shorter than the ~8 launches a rebuild takes).  Synchronises. */
+int tg_pipeline_stalls(TgWorld* w, void* stream);
 /* resets consumed per env since the last tg_set_draws (device->host, synchronises the stream) */
 int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream);
 

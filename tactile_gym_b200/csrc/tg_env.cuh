@@ -9,10 +9,14 @@
 // Reset pipeline.  A reset depends only on the env's next random draws, never on the episode that just ended
 // (arm.reset() rewinds to the rest pose, robot.py:114-125).  So every env keeps a STANDBY start-of-episode
 // state computed ahead of time.  When an env finishes, step_kernel swaps the standby in (a copy) instead of
-// running IK + blocking move on the critical path, and the extra blocks of the NEXT step launch recompute
-// the standby while the other envs step.  Draws are consumed in episode order, so the sequence of episodes is
-// exactly the sequential one.  Needs episodes of >= 2 steps (tg_create checks max_steps; a miss raises a
-// sticky error flag instead of guessing).
+// running IK + blocking move on the critical path.  The consumed slot is then rebuilt by the extra blocks of the
+// following step launches, RESUMABLY: one launch does the draws + IK, every later one RESET_CHUNK iterations of
+// the blocking move (about the length of an env step), the partial state living in the sb_* buffers, so a launch
+// that carries resets lasts no longer than one that does not.  Slots are handed between the step thread and the
+// standby threads through sb_ready (EMPTY / PARTIAL / BUSY / READY, atomicCAS + fences); an env that finishes
+// before its slot is READY claims it and completes it inline (counted in stall_count), so any episode length is
+// exact.  Draws are consumed in episode order and the chunk schedule is fixed (the incremental sin/cos are
+// re-synchronised every RESET_CHUNK iterations on every path), so results do not depend on who ran which chunk.
 #pragma once
 #include "tg_dyn.cuh"
 
@@ -40,10 +44,22 @@ struct EnvBuffers {
     // standby start-of-episode state
     double *sb_q, *sb_qd, *sb_embed, *sb_ang, *sb_cam, *sb_stim, *sb_tcp;
     int* sb_substeps;
-    unsigned char* sb_ready; // [N]
+    int* sb_ready;           // [N] slot state: SB_EMPTY / SB_READY / SB_PARTIAL / SB_BUSY
+    double *sb_targ, *sb_cv, *sb_draw; // partial resets: IK target joints [NB][N], blocking-move step [N], draws [N][TG_MAXDRAW]
     // camera / stimulus of the state an env terminated in (for the terminal observation)
     double *term_cam, *term_stim;
-    int* error_flag;         // sticky: 1 = a finished env found no standby
+    int* error_flag;         // sticky error flag (unused slots of the pipeline; kept for the C-ABI)
+    int* stall_count;        // episode ends that had to complete their standby inline
+};
+
+enum { SB_EMPTY = 0, SB_READY = 1, SB_PARTIAL = 2, SB_BUSY = 3 };
+#define RESET_CHUNK 20
+
+// a reset in flight (between draws + IK and the end of the blocking move)
+template <int NB>
+struct ResetState {
+    double q[NB], qd[NB], targ_j[NB], cv, embed, edge_ang, draw[TG_MAXDRAW];
+    int nsteps;
 };
 
 // one env's start-of-episode state
@@ -201,71 +217,68 @@ TGD void inverse_kinematics(const TgArm& arm, double* q, const double* tpos, con
     }
 }
 
-// One reset of env e: consumes the env's next draws and returns the start-of-episode state.
+// workframe_to_worldframe (base_robot_arm.py:47-60) of the init pose [0,0,embed], init_rpy
+TGD void reset_target(const TgTask& task, double embed, double* tpos, double* targ_orn)
+{
+    const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
+    double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
+    const double lp[3] = {0.0, 0.0, balance ? 0.0 : embed}; // update_init_pose: edge_follow_env.py:301-309 / base_object_env.py
+    quat_from_euler(task.workframe_rpy, wq);
+    quat_from_euler(task.init_rpy, tq);
+    mat_from_quat(wq, R);
+    m3mulv(t, R, lp);
+    tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
+    quat_mul(oq, wq, tq);
+    euler_from_quat(oq, rpy);
+    quat_from_euler(rpy, targ_orn);
+}
+
+// Reset, part 1: consume the env's next draws, rest pose, IK of the start pose.
 template <class T>
-__device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e,
-                                       EpisodeStart<T::NB>& out)
+__device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, const EnvBuffers& b, int e, ResetState<T::NB>& r)
 {
     constexpr int NB = T::NB;
     // reset_task draws (edge_follow_env.py:285-299): embed_dist then edge_ang
-    double draw[TG_MAXDRAW];
 #pragma unroll
-    for (int d = 0; d < TG_MAXDRAW; d++) draw[d] = task.draw_default[d];
+    for (int d = 0; d < TG_MAXDRAW; d++) r.draw[d] = task.draw_default[d];
     {
         const int cnt = b.reset_count[e];
         if (b.draws && cnt < b.draw_rounds) {
 #pragma unroll
             for (int d = 0; d < TG_MAXDRAW; d++)
-                if (d < task.n_draws) draw[d] = b.draws[((size_t)e * b.draw_rounds + cnt) * task.n_draws + d];
+                if (d < task.n_draws) r.draw[d] = b.draws[((size_t)e * b.draw_rounds + cnt) * task.n_draws + d];
         }
         b.reset_count[e] = cnt + 1;
     }
     const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
     // edge_follow draws: embed_dist, edge_ang; object_balance draws: gravity_z, embed_dist, fx, fy
-    const double embed = balance ? draw[1] : draw[0], edge_ang = balance ? 0.0 : draw[1];
-    out.embed = embed; out.edge_ang = edge_ang;
-    if (!balance) {
-        double s, c;
-        sincos(edge_ang * 0.5, &s, &c);
-        double qz[4] = {0, 0, s, c}, R[9]; // getQuaternionFromEuler([0,0,ang]) (edge_follow_env.py:241)
-        mat_from_quat(qz, R);
+    r.embed = balance ? r.draw[1] : r.draw[0];
+    r.edge_ang = balance ? 0.0 : r.draw[1];
 #pragma unroll
-        for (int i = 0; i < 9; i++) out.stim[i] = R[i];
-#pragma unroll
-        for (int i = 0; i < 3; i++) out.stim[9 + i] = task.edge_pos[i];
-    }
-    double q[NB], qd[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) { q[i] = b.rest_q[i]; qd[i] = 0.0; }
-    // workframe_to_worldframe (base_robot_arm.py:47-60) of the init pose [0,0,embed], init_rpy
+    for (int i = 0; i < NB; i++) { r.q[i] = b.rest_q[i]; r.qd[i] = 0.0; r.targ_j[i] = r.q[i]; }
     double tpos[3], targ_orn[4];
-    {
-        double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
-        const double lp[3] = {0.0, 0.0, balance ? 0.0 : embed}; // update_init_pose: edge_follow_env.py:301-309 / base_object_env.py
-        quat_from_euler(task.workframe_rpy, wq);
-        quat_from_euler(task.init_rpy, tq);
-        mat_from_quat(wq, R);
-        m3mulv(t, R, lp);
-        tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
-        quat_mul(oq, wq, tq);
-        euler_from_quat(oq, rpy);
-        quat_from_euler(rpy, targ_orn);
-    }
-    double targ_j[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) targ_j[i] = q[i];
-    inverse_kinematics<T>(arm, targ_j, tpos, targ_orn);
+    reset_target(task, r.embed, tpos, targ_orn);
+    inverse_kinematics<T>(arm, r.targ_j, tpos, targ_orn);
+    r.cv = 0.001;
+    r.nsteps = 0;
+}
 
-    // Robot.blocking_move(max_steps=1000, constant_vel=0.001) (robot.py:188-260)
+// Reset, part 2: up to RESET_CHUNK iterations of Robot.blocking_move(max_steps=1000, constant_vel=0.001)
+// (robot.py:188-260).  Returns true when the move has ended.
+template <class T>
+__device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph, const TgTask& task, ResetState<T::NB>& r)
+{
+    constexpr int NB = T::NB;
+    double tpos[3], targ_orn[4];
+    reset_target(task, r.embed, tpos, targ_orn);
     Motors<NB> mot;
     mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.blocking_force;
-    double cv = 0.001;
-    int nsteps = 0;
     double sc[NB][2];
 #pragma unroll
-    for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
+    for (int i = 0; i < NB; i++) sincos(r.q[i], &sc[i][0], &sc[i][1]);
 #pragma unroll 1
-    for (int it = 0; it < 1000; it++) {
+    for (int it = 0; it < RESET_CHUNK; it++) {
+        if (r.nsteps >= 1000) return true;
         double tp[3], tq[4];
         {
             Kin<NB> k;
@@ -276,29 +289,39 @@ __device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, co
         bool all_small = true;
         double diff[NB];
 #pragma unroll
-        for (int i = 0; i < NB; i++) { diff[i] = targ_j[i] - q[i]; nrm += diff[i] * diff[i]; tot += fabs(qd[i]); }
+        for (int i = 0; i < NB; i++) { diff[i] = r.targ_j[i] - r.q[i]; nrm += diff[i] * diff[i]; tot += fabs(r.qd[i]); }
         nrm = sqrt(nrm);
 #pragma unroll
         for (int i = 0; i < NB; i++) {
             const double vdir = nrm > 0 ? diff[i] / nrm : 0.0;
-            mot.target_pos[i] = q[i] + vdir * cv; mot.target_vel[i] = 0.0;
-            if (!(fabs(diff[i]) < cv)) all_small = false;
+            mot.target_pos[i] = r.q[i] + vdir * r.cv; mot.target_vel[i] = 0.0;
+            if (!(fabs(diff[i]) < r.cv)) all_small = false;
         }
-        if (all_small) cv *= 0.5;
-        substep<T>(arm, ph, q, qd, sc, mot);
-        nsteps++;
+        if (all_small) r.cv *= 0.5;
+        substep<T>(arm, ph, r.q, r.qd, sc, mot);
+        r.nsteps++;
         const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
         const double ip = targ_orn[0] * tq[0] + targ_orn[1] * tq[1] + targ_orn[2] * tq[2] + targ_orn[3] * tq[3];
         const double ca = fmin(fmax(2 * ip * ip - 1, -1.0), 1.0);
         const double oe = acos(ca);
-        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
+        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) return true;
     }
-    out.substeps = nsteps;
+    return r.nsteps >= 1000;
+}
+
+// Reset, part 3: the start-of-episode state the step and raster kernels consume.
+template <class T>
+__device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, const ResetState<T::NB>& r, EpisodeStart<T::NB>& out)
+{
+    constexpr int NB = T::NB;
+    const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
+    out.embed = r.embed; out.edge_ang = r.edge_ang;
+    out.substeps = r.nsteps;
 #pragma unroll
-    for (int i = 0; i < NB; i++) { out.q[i] = q[i]; out.qd[i] = qd[i]; }
+    for (int i = 0; i < NB; i++) { out.q[i] = r.q[i]; out.qd[i] = r.qd[i]; }
     {
         Kin<NB> k;
-        fk<T>(arm, q, k);
+        fk<T>(arm, r.q, k);
         double tp[3], tq[4];
         tcp_world<T>(arm, k, tp, tq);
         write_camera<T>(arm, k, out.cam);
@@ -307,23 +330,43 @@ __device__ __noinline__ void reset_env(const TgArm& arm, const TgPhysics& ph, co
 #pragma unroll
         for (int c = 0; c < 4; c++) out.tcp[3 + c] = tq[c];
     }
-    if (balance) {
+    if (!balance) {
+        double sn, cs;
+        sincos(r.edge_ang * 0.5, &sn, &cs);
+        double qz[4] = {0, 0, sn, cs}, R[9]; // getQuaternionFromEuler([0,0,ang]) (edge_follow_env.py:241)
+        mat_from_quat(qz, R);
+#pragma unroll
+        for (int i = 0; i < 9; i++) out.stim[i] = R[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) out.stim[9 + i] = task.edge_pos[i];
+    } else {
         // reset_object (object_balance_env.py:322-358): pole back at init_obj_pos / init_obj_orn, at rest, 0.1 N pushing
         // down at a random point of the base plate during the next stepSimulation (apply_random_force_base :360-381)
         ObjState& o = out.obj;
         o.pos[0] = task.workframe_pos[0]; o.pos[1] = task.workframe_pos[1];
-        o.pos[2] = task.workframe_pos[2] + task.obj_base_h * 0.5 - embed;
+        o.pos[2] = task.workframe_pos[2] + task.obj_base_h * 0.5 - r.embed;
         quat_from_euler(task.obj_init_rpy, o.quat);
 #pragma unroll
         for (int c = 0; c < 3; c++) { o.vel[c] = 0.0; o.omg[c] = 0.0; }
-        o.ext_pos[0] = o.pos[0] + draw[2] * task.obj_base_w * 0.5;
-        o.ext_pos[1] = o.pos[1] + draw[3] * task.obj_base_w * 0.5;
+        o.ext_pos[0] = o.pos[0] + r.draw[2] * task.obj_base_w * 0.5;
+        o.ext_pos[1] = o.pos[1] + r.draw[3] * task.obj_base_w * 0.5;
         o.ext_pos[2] = o.pos[2];
         o.ext_pending = 1;
-        o.grav_z = draw[0];
-        o.pivot_z = -task.obj_base_h * 0.5 + embed;
+        o.grav_z = r.draw[0];
+        o.pivot_z = -task.obj_base_h * 0.5 + r.embed;
         obj_stim(task, o, out.stim);
     }
+}
+
+// One whole reset of env e (same chunk schedule as the resumable path)
+template <class T>
+TGD void reset_env(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, EpisodeStart<T::NB>& out)
+{
+    ResetState<T::NB> r;
+    reset_begin<T>(arm, task, b, e, r);
+#pragma unroll 1
+    while (!reset_advance<T>(arm, ph, task, r)) {}
+    reset_finish<T>(arm, task, r, out);
 }
 
 template <int NB>
@@ -351,43 +394,106 @@ TGD void store_standby(const EnvBuffers& b, int e, const EpisodeStart<NB>& s)
     for (int c = 0; c < 7; c++) b.sb_tcp[(size_t)e * 7 + c] = s.tcp[c];
     if (b.obj) { obj_store(b.sb_obj + (size_t)e * 13, b.sb_obj_ext + (size_t)e * 4, s.obj); b.sb_grav[e] = s.obj.grav_z; }
     __threadfence();
-    b.sb_ready[e] = 1;
+    atomicExch(&b.sb_ready[e], SB_READY);
 }
 
-// swap the standby in as the live state of env e (a copy); the slot is recomputed by the next launch
+// partial reset <-> sb_* buffers (the slot is owned: SB_BUSY)
+template <int NB>
+TGD void store_partial(const EnvBuffers& b, int e, const ResetState<NB>& r)
+{
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        b.sb_q[(size_t)i * b.n + e] = r.q[i]; b.sb_qd[(size_t)i * b.n + e] = r.qd[i]; b.sb_targ[(size_t)i * b.n + e] = r.targ_j[i];
+    }
+    b.sb_embed[e] = r.embed; b.sb_ang[e] = r.edge_ang; b.sb_substeps[e] = r.nsteps; b.sb_cv[e] = r.cv;
+#pragma unroll
+    for (int d = 0; d < TG_MAXDRAW; d++) b.sb_draw[(size_t)e * TG_MAXDRAW + d] = r.draw[d];
+    __threadfence();
+    atomicExch(&b.sb_ready[e], SB_PARTIAL);
+}
+template <int NB>
+TGD void load_partial(const EnvBuffers& b, int e, ResetState<NB>& r)
+{
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        r.q[i] = __ldcg(b.sb_q + (size_t)i * b.n + e); r.qd[i] = __ldcg(b.sb_qd + (size_t)i * b.n + e); r.targ_j[i] = __ldcg(b.sb_targ + (size_t)i * b.n + e);
+    }
+    r.embed = __ldcg(b.sb_embed + e); r.edge_ang = __ldcg(b.sb_ang + e); r.nsteps = __ldcg(b.sb_substeps + e); r.cv = __ldcg(b.sb_cv + e);
+#pragma unroll
+    for (int d = 0; d < TG_MAXDRAW; d++) r.draw[d] = __ldcg(b.sb_draw + (size_t)e * TG_MAXDRAW + d);
+}
+
+// swap the standby in as the live state of env e (a copy); the slot is rebuilt by the following launches
 template <int NB>
 TGD void consume_standby(const EnvBuffers& b, int e)
 {
 #pragma unroll
-    for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = b.sb_q[(size_t)i * b.n + e]; b.qd[(size_t)i * b.n + e] = b.sb_qd[(size_t)i * b.n + e]; }
-    b.embed[e] = b.sb_embed[e]; b.edge_ang[e] = b.sb_ang[e]; b.steps[e] = 0; b.reset_substeps[e] = b.sb_substeps[e];
+    for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = __ldcg(b.sb_q + (size_t)i * b.n + e); b.qd[(size_t)i * b.n + e] = __ldcg(b.sb_qd + (size_t)i * b.n + e); }
+    b.embed[e] = __ldcg(b.sb_embed + e); b.edge_ang[e] = __ldcg(b.sb_ang + e); b.steps[e] = 0; b.reset_substeps[e] = __ldcg(b.sb_substeps + e);
 #pragma unroll
-    for (int c = 0; c < 12; c++) { b.cam[(size_t)e * 12 + c] = b.sb_cam[(size_t)e * 12 + c]; b.stim[(size_t)e * 12 + c] = b.sb_stim[(size_t)e * 12 + c]; }
+    for (int c = 0; c < 12; c++) { b.cam[(size_t)e * 12 + c] = __ldcg(b.sb_cam + (size_t)e * 12 + c); b.stim[(size_t)e * 12 + c] = __ldcg(b.sb_stim + (size_t)e * 12 + c); }
 #pragma unroll
-    for (int c = 0; c < 7; c++) b.tcp[(size_t)e * 7 + c] = b.sb_tcp[(size_t)e * 7 + c];
+    for (int c = 0; c < 7; c++) b.tcp[(size_t)e * 7 + c] = __ldcg(b.sb_tcp + (size_t)e * 7 + c);
     if (b.obj) {
 #pragma unroll
-        for (int c = 0; c < 13; c++) b.obj[(size_t)e * 13 + c] = b.sb_obj[(size_t)e * 13 + c];
+        for (int c = 0; c < 13; c++) b.obj[(size_t)e * 13 + c] = __ldcg(b.sb_obj + (size_t)e * 13 + c);
 #pragma unroll
-        for (int c = 0; c < 4; c++) b.obj_ext[(size_t)e * 4 + c] = b.sb_obj_ext[(size_t)e * 4 + c];
-        b.grav[e] = b.sb_grav[e];
+        for (int c = 0; c < 4; c++) b.obj_ext[(size_t)e * 4 + c] = __ldcg(b.sb_obj_ext + (size_t)e * 4 + c);
+        b.grav[e] = __ldcg(b.sb_grav + e);
     }
     __threadfence();
-    b.sb_ready[e] = 0;
+    atomicExch(&b.sb_ready[e], SB_EMPTY);
 }
 
-// standby role: threads scan the envs and recompute every missing standby
+// Work on the standby slot of env e if it is free to take: EMPTY -> draws + IK, PARTIAL -> one chunk of the
+// blocking move (complete: everything, to READY).
 template <class T>
-TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int first_block)
+TGD void standby_work(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, bool complete)
+{
+    const int s = atomicAdd(&b.sb_ready[e], 0);
+    if (s == SB_READY || s == SB_BUSY) return;
+    if (atomicCAS(&b.sb_ready[e], s, SB_BUSY) != s) return;
+    __threadfence();
+    ResetState<T::NB> r;
+    bool fin = false;
+    if (s == SB_EMPTY) reset_begin<T>(arm, task, b, e, r);
+    else { load_partial<T::NB>(b, e, r); fin = reset_advance<T>(arm, ph, task, r); }
+    if (complete) {
+#pragma unroll 1
+        while (!fin) fin = reset_advance<T>(arm, ph, task, r);
+    }
+    if (fin) {
+        EpisodeStart<T::NB> es;
+        reset_finish<T>(arm, task, r, es);
+        store_standby<T::NB>(b, e, es);
+    } else store_partial<T::NB>(b, e, r);
+}
+
+// the step thread of a finished env needs its standby NOW: wait for / complete the slot, then swap it in
+template <class T>
+TGD void acquire_standby(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e)
+{
+    bool stalled = false;
+#pragma unroll 1
+    for (;;) {
+        const int s = atomicAdd(&b.sb_ready[e], 0);
+        if (s == SB_READY) break;
+        stalled = true;
+        if (s == SB_BUSY) { __nanosleep(500); continue; } // a standby thread holds the slot for one chunk
+        standby_work<T>(arm, ph, task, b, e, true);
+    }
+    if (stalled) atomicAdd(b.stall_count, 1);
+    __threadfence();
+    consume_standby<T::NB>(b, e);
+}
+
+// standby role: threads scan the envs and advance every slot that is not READY
+template <class T>
+TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int first_block, bool complete)
 {
     const int t = (blockIdx.x - first_block) * blockDim.x + threadIdx.x;
     const int nt = (gridDim.x - first_block) * blockDim.x;
-    for (int e = t; e < b.n; e += nt) {
-        if (b.sb_ready[e]) continue;
-        EpisodeStart<T::NB> s;
-        reset_env<T>(arm, ph, task, b, e, s);
-        store_standby<T::NB>(b, e, s);
-    }
+    for (int e = t; e < b.n; e += nt) standby_work<T>(arm, ph, task, b, e, complete);
 }
 
 // autoreset: 1 = finished envs start their next episode inside this launch (VecEnv semantics)
@@ -398,7 +504,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 {
     constexpr int NB = T::NB;
     if ((int)blockIdx.x >= b.step_blocks) {
-        standby_role<T>(arm, ph, task, b, b.step_blocks);
+        standby_role<T>(arm, ph, task, b, b.step_blocks, false);
         return;
     }
     const int e = env_index(b);
@@ -503,8 +609,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         write_camera<T>(arm, k, b.term_cam + (size_t)e * 12);
 #pragma unroll
         for (int c = 0; c < 12; c++) b.term_stim[(size_t)e * 12 + c] = b.stim[(size_t)e * 12 + c];
-        if (b.sb_ready[e]) consume_standby<NB>(b, e);
-        else *b.error_flag = 1;
+        acquire_standby<T>(arm, ph, task, b, e);
     } else {
         write_camera<T>(arm, k, b.cam + (size_t)e * 12);
 #pragma unroll
@@ -526,10 +631,10 @@ reset_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysic
     if (mask && !mask[e]) return;
     EpisodeStart<T::NB> s;
     if (b.pipeline) {
-        if (!b.sb_ready[e]) { reset_env<T>(arm, ph, task, b, e, s); store_standby<T::NB>(b, e, s); }
+        // the standby IS the next episode (complete it if a rebuild is still in flight); the slot it leaves
+        // empty is rebuilt by the standby blocks of the following step launches
+        standby_work<T>(arm, ph, task, b, e, true);
         consume_standby<T::NB>(b, e);
-        reset_env<T>(arm, ph, task, b, e, s);
-        store_standby<T::NB>(b, e, s);
     } else {
         reset_env<T>(arm, ph, task, b, e, s);
         store_live<T::NB>(b, e, s);
@@ -541,7 +646,7 @@ template <class T>
 __global__ void __launch_bounds__(128)
 standby_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task, EnvBuffers b)
 {
-    standby_role<T>(arm, ph, task, b, 0);
+    standby_role<T>(arm, ph, task, b, 0, true);
 }
 
 // ---------------------------------------------------------------- test hooks

@@ -131,7 +131,9 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if ((rc = dalloc(w, &b.sb_q, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_qd, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_embed, n)) ||
         (rc = dalloc(w, &b.sb_ang, n)) || (rc = dalloc(w, &b.sb_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.sb_stim, (size_t)12 * n)) ||
         (rc = dalloc(w, &b.sb_tcp, (size_t)7 * n)) || (rc = dalloc(w, &b.sb_substeps, n)) || (rc = dalloc(w, &b.sb_ready, n)) ||
-        (rc = dalloc(w, &b.term_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.term_stim, (size_t)12 * n)) || (rc = dalloc(w, &b.error_flag, 1))) {
+        (rc = dalloc(w, &b.term_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.term_stim, (size_t)12 * n)) || (rc = dalloc(w, &b.error_flag, 1)) ||
+        (rc = dalloc(w, &b.stall_count, 1)) || (rc = dalloc(w, &b.sb_targ, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_cv, n)) ||
+        (rc = dalloc(w, &b.sb_draw, (size_t)TG_MAXDRAW * n))) {
         tg_destroy(w);
         return rc;
     }
@@ -212,7 +214,7 @@ static int set_draws_impl(TgWorld* w, const double* h_draws, int rounds, int inv
     w->eb.draws = w->d_draws; w->eb.draw_rounds = rounds;
     if (invalidate && w->eb.pipeline) {
         // a new draw sequence starts: standbys computed from the old one are recomputed now
-        CK(cudaMemset(w->eb.sb_ready, 0, w->n));
+        CK(cudaMemset(w->eb.sb_ready, 0, sizeof(int) * w->n));
         TOPO_DISPATCH(w, (standby_kernel<Topo><<<(w->n + 127) / 128, 128>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb)));
         w->launches++;
         CK(cudaGetLastError());
@@ -232,6 +234,16 @@ extern "C" int tg_pipeline_error(TgWorld* w, void* stream)
     CK(cudaMemcpyAsync(&flag, w->eb.error_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return flag;
+}
+
+extern "C" int tg_pipeline_stalls(TgWorld* w, void* stream)
+{
+    if (!w) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, w->eb.stall_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return cnt;
 }
 
 extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)

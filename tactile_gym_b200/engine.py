@@ -334,8 +334,12 @@ class TactileWorld:
         return cam
 
     def pipeline_error(self):
-        """True if a finished env ever found no pre-computed standby episode (never, for episodes of >= 2 steps)"""
+        """sticky error flag of the reset pipeline (always False since the standby slots became resumable)"""
         return bool(self.lib.tg_pipeline_error(self.h, self._stream()))
+
+    def pipeline_stalls(self):
+        """episode ends that had to finish their pre-computed next episode inline (exact, just slower)"""
+        return int(self.lib.tg_pipeline_stalls(self.h, self._stream()))
 
     def launch_count(self):
         return int(self.lib.tg_launch_count(self.h))

@@ -165,10 +165,12 @@ def test_tcp_limits_zero_the_velocity(oracle, edge_modes):
 
 
 def test_autoreset_and_terminal_observation(oracle, edge_modes):
+    """3-step episodes: every episode ends while its next episode is still being rebuilt in chunks by the standby
+    blocks, so this drives the slot hand-over (claim / wait / complete inline) as well as the VecEnv semantics."""
     n, S = 6, 64
     env = _world(edge_modes, n, S=S, max_steps=3)
     rng = np.random.RandomState(5)
-    draws = _draws(rng, n, rounds=3)
+    draws = _draws(rng, n, rounds=4)
     env.world.set_draws(draws)
     env.reset()
     refs = []
@@ -176,19 +178,47 @@ def test_autoreset_and_terminal_observation(oracle, edge_modes):
         r = oracle.EdgeFollowOracle(image_size=S, max_steps=3)
         r.reset(draws=tuple(draws[i, 0]))
         refs.append(r)
-    for k in range(3):
-        act = rng.uniform(-0.25, 0.25, (n, 2)).astype(np.float32)
-        obs, rew, done, infos = env.step(act)
-        last = [r.step(act[i]) for i, r in enumerate(refs)]
-    assert done.all()
-    for i, r in enumerate(refs):
-        assert _img_close(infos[i]["terminal_observation"]["tactile"], last[i][0])[0] <= 1
-        assert infos[i]["episode"]["l"] == 3
-        o = r.reset(draws=tuple(draws[i, 1]))          # second round of draws
-        assert _img_close(o, obs["tactile"][i])[0] <= 1
-    st = env.world.get_state()
-    assert (st[:, 21] == 0).all()                       # step counters restarted
-    assert not env.world.pipeline_error()               # every finished env found its pre-computed next episode
+    for ep in range(3):
+        for k in range(3):
+            act = rng.uniform(-0.25, 0.25, (n, 2)).astype(np.float32)
+            obs, rew, done, infos = env.step(act)
+            last = [r.step(act[i]) for i, r in enumerate(refs)]
+            assert done.all() == (k == 2) and done.any() == (k == 2)
+        for i, r in enumerate(refs):
+            assert _img_close(infos[i]["terminal_observation"]["tactile"], last[i][0])[0] <= 1
+            assert infos[i]["episode"]["l"] == 3
+            o = r.reset(draws=tuple(draws[i, ep + 1]))      # next round of draws
+            assert _img_close(o, obs["tactile"][i])[0] <= 1
+        st = env.world.get_state()
+        assert (st[:, 21] == 0).all()                       # step counters restarted
+        for i, r in enumerate(refs):
+            assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=2e-6)
+            assert st[i, 22] == r.last_reset_substeps
+    assert not env.world.pipeline_error()
+    assert env.world.pipeline_stalls() > 0                  # the episodes were shorter than a standby rebuild
+    env.close()
+
+
+def test_standby_rebuild_hides_behind_steps(oracle, edge_modes):
+    """Episodes longer than a rebuild: every finished env finds its next episode READY (no stall), and the episode it
+    starts is the oracle's for the same draws."""
+    n, S = 40, 64
+    env = _world(edge_modes, n, S=S, max_steps=14)
+    rng = np.random.RandomState(11)
+    draws = _draws(rng, n, rounds=4)
+    env.world.set_draws(draws)
+    env.reset()
+    for ep in range(3):
+        for k in range(14):
+            obs, rew, done, infos = env.step(rng.uniform(-0.25, 0.25, (n, 2)).astype(np.float32))
+        assert done.all()
+        st = env.world.get_state()
+        for i in (0, 7, 39):
+            r = oracle.EdgeFollowOracle(image_size=S, max_steps=14)
+            o = r.reset(draws=tuple(draws[i, ep + 1]))
+            assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=2e-6)
+            assert _img_close(o, obs["tactile"][i])[0] <= 1
+    assert env.world.pipeline_stalls() == 0
     env.close()
 
 
