@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtactile_gym_b200.so")
+LIB_PATH = os.environ.get("TG_LIB_OVERRIDE") or os.path.join(HERE, "libtactile_gym_b200.so")   # override: diagnostic builds (tools/)
 
 TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 8
 TG_TOPO_CHAIN6, TG_TOPO_MG400 = 0, 1

@@ -11,7 +11,7 @@
 // state computed ahead of time.  When an env finishes, step_kernel swaps the standby in (a copy) instead of
 // running IK + blocking move on the critical path.  The consumed slot is then rebuilt by the extra blocks of the
 // following step launches, RESUMABLY: one launch does the draws + IK, every later one RESET_CHUNK iterations of
-// the blocking move (about the length of an env step), the partial state living in the sb_* buffers, so a launch
+// the blocking move (a fraction of an env step's work), the partial state living in the sb_* buffers, so a launch
 // that carries resets lasts no longer than one that does not.  Slots are handed between the step thread and the
 // standby threads through sb_ready (EMPTY / PARTIAL / BUSY / READY, atomicCAS + fences); an env that finishes
 // before its slot is READY claims it and completes it inline (counted in stall_count), so any episode length is
@@ -25,6 +25,7 @@ struct EnvBuffers {
     int lanes;            // active lanes per warp in the step role
     int step_blocks;      // blocks [0, step_blocks) step envs, the rest recompute standbys
     int pipeline;         // 1: standby reset pipeline on
+    int ik_chunk, reset_chunk; // quantum sizes of the resumable reset (IK / blocking-move iterations per launch)
     double* q;            // [NB][N]
     double* qd;           // [NB][N]
     double* embed;        // [N]
@@ -45,6 +46,7 @@ struct EnvBuffers {
     double *sb_q, *sb_qd, *sb_embed, *sb_ang, *sb_cam, *sb_stim, *sb_tcp;
     int* sb_substeps;
     int* sb_ready;           // [N] slot state: SB_EMPTY / SB_READY / SB_PARTIAL / SB_BUSY
+    int* sb_ik;              // [N] partial resets: IK iteration (ResetState::ik_it)
     double *sb_targ, *sb_cv, *sb_draw; // partial resets: IK target joints [NB][N], blocking-move step [N], draws [N][TG_MAXDRAW]
     // camera / stimulus of the state an env terminated in (for the terminal observation)
     double *term_cam, *term_stim;
@@ -53,13 +55,16 @@ struct EnvBuffers {
 };
 
 enum { SB_EMPTY = 0, SB_READY = 1, SB_PARTIAL = 2, SB_BUSY = 3 };
-#define RESET_CHUNK 20
+#define RESET_CHUNK 6  // blocking-move iterations per quantum (a quarter of an env step's work: a standby warp may
+                       // carry an IK quantum and a move quantum one after the other, plus cold code)
+#define IK_CHUNK 8     // IK iterations per quantum
 
 // a reset in flight (between draws + IK and the end of the blocking move)
 template <int NB>
 struct ResetState {
     double q[NB], qd[NB], targ_j[NB], cv, embed, edge_ang, draw[TG_MAXDRAW];
     int nsteps;
+    int ik_it; // >= 0: the IK solve is at this iteration; -1: solved, the blocking move is running
 };
 
 // one env's start-of-episode state
@@ -166,20 +171,23 @@ TGD void edge_step_data(const TgTask& task, const double* tcp_pos, double edge_a
 }
 
 // pb.calculateInverseKinematics as restated in oracle/tg_oracle.c:or_inverse_kinematics (base_robot_arm.py:201-209)
+// Resumable: runs iterations [it, it + count) of the <= 100 and returns the next iteration, or -1 once the solve has
+// ended (converged or out of iterations).
 template <class T>
-TGD void inverse_kinematics(const TgArm& arm, double* q, const double* tpos, const double* tquat)
+TGD int ik_chunk(const TgArm& arm, double* q, const double* tpos, const double* tquat, int it, int count)
 {
     constexpr int NB = T::NB;
     static_assert(NB == 6 || NB == 8, "topology");
 #pragma unroll 1
-    for (int it = 0; it < 100; it++) {
+    for (int c = 0; c < count; c++, it++) {
+        if (it >= 100) return -1;
         Kin<NB> k;
         fk<T>(arm, q, k);
         double tp[3], tq[4], e[6];
         tcp_world<T>(arm, k, tp, tq);
         e[0] = tpos[0] - tp[0]; e[1] = tpos[1] - tp[1]; e[2] = tpos[2] - tp[2];
         const double res = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-        if (it > 0 && res < 1e-8) break;
+        if (it > 0 && res < 1e-8) return -1;
         double qi[4] = {-tq[0], -tq[1], -tq[2], tq[3]}, dq[4];
         quat_mul(dq, tquat, qi);
         const double wv = fmin(fmax(dq[3], -1.0), 1.0);
@@ -215,6 +223,7 @@ TGD void inverse_kinematics(const TgArm& arm, double* q, const double* tpos, con
             for (int i = 0; i < NB; i++) q[i] += sc * d[i];
         }
     }
+    return it >= 100 ? -1 : it;
 }
 
 // workframe_to_worldframe (base_robot_arm.py:47-60) of the init pose [0,0,embed], init_rpy
@@ -233,7 +242,7 @@ TGD void reset_target(const TgTask& task, double embed, double* tpos, double* ta
     quat_from_euler(rpy, targ_orn);
 }
 
-// Reset, part 1: consume the env's next draws, rest pose, IK of the start pose.
+// Reset, part 1: consume the env's next draws, rest pose; the IK of the start pose starts in reset_advance.
 template <class T>
 __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, const EnvBuffers& b, int e, ResetState<T::NB>& r)
 {
@@ -256,28 +265,31 @@ __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, c
     r.edge_ang = balance ? 0.0 : r.draw[1];
 #pragma unroll
     for (int i = 0; i < NB; i++) { r.q[i] = b.rest_q[i]; r.qd[i] = 0.0; r.targ_j[i] = r.q[i]; }
-    double tpos[3], targ_orn[4];
-    reset_target(task, r.embed, tpos, targ_orn);
-    inverse_kinematics<T>(arm, r.targ_j, tpos, targ_orn);
     r.cv = 0.001;
     r.nsteps = 0;
+    r.ik_it = 0;
 }
 
-// Reset, part 2: up to RESET_CHUNK iterations of Robot.blocking_move(max_steps=1000, constant_vel=0.001)
+// Reset, part 2, one quantum: IK_CHUNK iterations of the IK of the start pose (base_robot_arm.py:201-209), or, once
+// that is solved, up to RESET_CHUNK iterations of Robot.blocking_move(max_steps=1000, constant_vel=0.001)
 // (robot.py:188-260).  Returns true when the move has ended.
 template <class T>
-__device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph, const TgTask& task, ResetState<T::NB>& r)
+__device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, ResetState<T::NB>& r)
 {
     constexpr int NB = T::NB;
     double tpos[3], targ_orn[4];
     reset_target(task, r.embed, tpos, targ_orn);
+    if (r.ik_it >= 0) {
+        r.ik_it = ik_chunk<T>(arm, r.targ_j, tpos, targ_orn, r.ik_it, b.ik_chunk);
+        return false;
+    }
     Motors<NB> mot;
     mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.blocking_force;
     double sc[NB][2];
 #pragma unroll
     for (int i = 0; i < NB; i++) sincos(r.q[i], &sc[i][0], &sc[i][1]);
 #pragma unroll 1
-    for (int it = 0; it < RESET_CHUNK; it++) {
+    for (int it = 0; it < b.reset_chunk; it++) {
         if (r.nsteps >= 1000) return true;
         double tp[3], tq[4];
         {
@@ -365,7 +377,7 @@ TGD void reset_env(const TgArm& arm, const TgPhysics& ph, const TgTask& task, co
     ResetState<T::NB> r;
     reset_begin<T>(arm, task, b, e, r);
 #pragma unroll 1
-    while (!reset_advance<T>(arm, ph, task, r)) {}
+    while (!reset_advance<T>(arm, ph, task, b, r)) {}
     reset_finish<T>(arm, task, r, out);
 }
 
@@ -405,7 +417,7 @@ TGD void store_partial(const EnvBuffers& b, int e, const ResetState<NB>& r)
     for (int i = 0; i < NB; i++) {
         b.sb_q[(size_t)i * b.n + e] = r.q[i]; b.sb_qd[(size_t)i * b.n + e] = r.qd[i]; b.sb_targ[(size_t)i * b.n + e] = r.targ_j[i];
     }
-    b.sb_embed[e] = r.embed; b.sb_ang[e] = r.edge_ang; b.sb_substeps[e] = r.nsteps; b.sb_cv[e] = r.cv;
+    b.sb_embed[e] = r.embed; b.sb_ang[e] = r.edge_ang; b.sb_substeps[e] = r.nsteps; b.sb_cv[e] = r.cv; b.sb_ik[e] = r.ik_it;
 #pragma unroll
     for (int d = 0; d < TG_MAXDRAW; d++) b.sb_draw[(size_t)e * TG_MAXDRAW + d] = r.draw[d];
     __threadfence();
@@ -418,7 +430,7 @@ TGD void load_partial(const EnvBuffers& b, int e, ResetState<NB>& r)
     for (int i = 0; i < NB; i++) {
         r.q[i] = __ldcg(b.sb_q + (size_t)i * b.n + e); r.qd[i] = __ldcg(b.sb_qd + (size_t)i * b.n + e); r.targ_j[i] = __ldcg(b.sb_targ + (size_t)i * b.n + e);
     }
-    r.embed = __ldcg(b.sb_embed + e); r.edge_ang = __ldcg(b.sb_ang + e); r.nsteps = __ldcg(b.sb_substeps + e); r.cv = __ldcg(b.sb_cv + e);
+    r.embed = __ldcg(b.sb_embed + e); r.edge_ang = __ldcg(b.sb_ang + e); r.nsteps = __ldcg(b.sb_substeps + e); r.cv = __ldcg(b.sb_cv + e); r.ik_it = __ldcg(b.sb_ik + e);
 #pragma unroll
     for (int d = 0; d < TG_MAXDRAW; d++) r.draw[d] = __ldcg(b.sb_draw + (size_t)e * TG_MAXDRAW + d);
 }
@@ -457,10 +469,11 @@ TGD void standby_work(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
     ResetState<T::NB> r;
     bool fin = false;
     if (s == SB_EMPTY) reset_begin<T>(arm, task, b, e, r);
-    else { load_partial<T::NB>(b, e, r); fin = reset_advance<T>(arm, ph, task, r); }
+    else load_partial<T::NB>(b, e, r);
+    fin = reset_advance<T>(arm, ph, task, b, r);
     if (complete) {
 #pragma unroll 1
-        while (!fin) fin = reset_advance<T>(arm, ph, task, r);
+        while (!fin) fin = reset_advance<T>(arm, ph, task, b, r);
     }
     if (fin) {
         EpisodeStart<T::NB> es;

@@ -36,8 +36,9 @@
 
 #define RASTER_THREADS 512
 #define RASTER_WARPS (RASTER_THREADS / 32)
-#define TILE_ROWS 8
-#define TILE_COLS 64
+#define TILE_ROWS 16 // 16 x 32 pixel tiles = 32 spans of 16 px, one per lane (squarish: an oblique edge crosses fewer of them)
+#define TILE_COLS 32
+#define TILE_SPR_SHIFT 1 // log2(spans per tile row)
 #define RASTER_MAXPRIM 12
 #define SPAN_LIST 64   // per-warp compacted span lists (entries each; there are two)
 #define EXACT_QUEUE 640 // per-warp queue of pixels for the exact path (a shade batch adds <= 512; flushed above 128)
@@ -53,7 +54,8 @@ struct PrimCoef {
     int steep;                  // 1: V varies too fast for the float value bound -> V is evaluated in fp64
     double dvA, dvB, dvC;       // fp64 V coefficients (used for steep primitives)
     float c_lo, c_hi, r_lo, r_hi; // conservative screen bbox in pixel units
-    int valid, clipped;         // clipped: a vertex is outside [near, far] -> per-pixel range checks needed
+    int valid, clipped;         // clipped: a vertex is outside [near, far] -> tiles check the 1/z range of the plane
+    uint32_t behind;            // primitives whose plane this one lies entirely behind (or on: ties go to the lower index)
 };
 
 struct RasterArgs {
@@ -90,7 +92,8 @@ __device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gm
                  : "memory");
 }
 
-__device__ __forceinline__ void prim_setup(const RasterArgs& a, const double* cam, const double* stim, const double* pl, int nv, PrimCoef& o)
+// vp[k] = (column, row, 1/z) of vertex k in pixel units, meaningful when the return value (all vertices in front) is true
+__device__ __forceinline__ bool prim_setup(const RasterArgs& a, const double* cam, const double* stim, const double* pl, int nv, PrimCoef& o, double (*vp)[3])
 {
     // stimulus frame -> world -> eye space (x right, y up, z forward)
     double ve[4][3];
@@ -111,8 +114,8 @@ __device__ __forceinline__ void prim_setup(const RasterArgs& a, const double* ca
     double nrm[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
     const double nd0 = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
     const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
-    o.valid = 0;
-    if (!(fabs(nd0) > 1e-12 * nn * (fabs(ve[0][0]) + fabs(ve[0][1]) + fabs(ve[0][2]) + 1e-300))) return; // edge-on or degenerate
+    o.valid = 0; o.behind = 0;
+    if (!(fabs(nd0) > 1e-12 * nn * (fabs(ve[0][0]) + fabs(ve[0][1]) + fabs(ve[0][2]) + 1e-300))) return false; // edge-on or degenerate
     o.valid = 1;
     // d = (dx, dy, 1), dx = th ((2c+1)/S - 1), dy = th (1 - (2r+1)/S): a row vector g . d becomes A c + B r + C
     const double kx = a.th * 2.0 / S, x0 = a.th * (1.0 / S - 1.0), y0 = a.th * (1.0 - 1.0 / S);
@@ -159,11 +162,21 @@ __device__ __forceinline__ void prim_setup(const RasterArgs& a, const double* ca
         for (int k = 0; k < nv; k++) {
             const double x = ve[k][0] / (ve[k][2] * a.th), y = ve[k][1] / (ve[k][2] * a.th);
             xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+            vp[k][0] = (x + 1) * 0.5 * S - 0.5; vp[k][1] = (1 - y) * 0.5 * S - 0.5; vp[k][2] = 1.0 / ve[k][2];
         }
         o.c_lo = (float)((xmin + 1) * 0.5 * S - 0.5 - 1.0); o.c_hi = (float)((xmax + 1) * 0.5 * S - 0.5 + 1.0);
         o.r_lo = (float)((1 - ymax) * 0.5 * S - 0.5 - 1.0); o.r_hi = (float)((1 - ymin) * 0.5 * S - 0.5 + 1.0);
     }
+    return front;
 }
+
+// optional counters for tools/raster_stats.py (a separate diagnostic build; never in the product library)
+#ifdef TG_RASTER_STATS
+__device__ unsigned long long g_rstats[48];
+#define RSTAT(i, v) atomicAdd(&g_rstats[i], (unsigned long long)(v))
+#else
+#define RSTAT(i, v) ((void)0)
+#endif
 
 // exact (fp64) coverage: all edge functions >= -1e-12 (they are normalised to unit gradient), in front of the eye
 __device__ __forceinline__ bool inside_exact(const PrimCoef& t, int c, int r, double& w)
@@ -265,7 +278,6 @@ raster_kernel(const RasterArgs a)
 
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int sh_S = 31 - __clz(S), sh_tx = 31 - __clz(tiles_x); // S and tiles_x are powers of two
-    int any_clipped = 0; // set per env: a primitive crosses the near/far planes -> the float path does not apply
     SpanEntry* l_in = s_list;             // spans covered by whole primitives only
     SpanEntry* l_pt = s_list + SPAN_LIST; // spans some primitive edge crosses
 
@@ -314,6 +326,7 @@ raster_kernel(const RasterArgs a)
                     if (lo > mg) vb[k] = fmaxf(vb[k], steep ? (float)(dA * k + d0) : fmaf(vA, fk, v0));
                     else if (lo >= -mg) unc |= 1u << k; // within the float margin of an edge
                 }
+                RSTAT(4, __popc(unc));
             }
         }
         float nd[16];
@@ -341,8 +354,10 @@ raster_kernel(const RasterArgs a)
             wds[k >> 2] |= u << (8 * (k & 3));
         }
         *reinterpret_cast<uint4*>(obs_e + off) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-        if (any_clipped) unc = 0xffffu; // near/far clipping in play: every pixel of the span takes the exact path
+        if (en.pad) unc = 0xffffu; // near/far clipping in play in this tile: every pixel of the span takes the exact path
         unc &= nd_skin;
+        RSTAT(5, __popc(unc)); RSTAT(6, __popc(unc) * __popc((uint32_t)(en.in_m | en.part_m))); RSTAT(7, 1);
+        RSTAT(8, __popc((uint32_t)en.part_m));
         const uint32_t cand = ((uint32_t)(en.in_m | en.part_m)) << 16;
         while (unc) {
             const int k = __ffs(unc) - 1;
@@ -370,18 +385,52 @@ raster_kernel(const RasterArgs a)
         if (a.mask && !a.mask[e]) continue;
         __syncwarp();
         if (lane == 0) *s_qcnt = 0;
-        if (lane < a.nprim) prim_setup(a, a.cam + (size_t)e * 12, a.stim + (size_t)e * 12, a.prims + 12 * lane, a.prim_nv[lane], pc[lane]);
-        __syncwarp();
+        {
+            // per-primitive setup (lane = primitive), then the pairwise "entirely behind the other's plane" relation:
+            // 1/z of a plane is affine on the screen, so plane d is in front of polygon t everywhere iff it is at t's
+            // vertices.  Wherever d covers a whole tile, t cannot be seen there (grazing slivers, coplanar faces).
+            double vp[4][3];
+            bool front = false;
+            const int nv = lane < a.nprim ? a.prim_nv[lane] : 0;
+            if (lane < a.nprim) front = prim_setup(a, a.cam + (size_t)e * 12, a.stim + (size_t)e * 12, a.prims + 12 * lane, nv, pc[lane], vp);
+            __syncwarp();
+            uint32_t bh = 0;
+            if (lane < a.nprim && front && pc[lane].valid) {
+                for (int d = 0; d < a.nprim; d++) {
+                    const PrimCoef& o = pc[d];
+                    if (d == lane || !o.valid) continue;
+                    bool ok = true;
+                    for (int k = 0; k < nv; k++) {
+                        const double wd = o.eA[4] * vp[k][0] + o.eB[4] * vp[k][1] + o.eC[4];
+                        const double tol = 1e-11 * (fabs(o.eA[4] * vp[k][0]) + fabs(o.eB[4] * vp[k][1]) + fabs(o.eC[4]) + vp[k][2]);
+                        ok = ok && (wd - vp[k][2] >= -tol);
+                    }
+                    if (ok) bh |= 1u << d;
+                }
+            }
+            // coplanar pairs are behind each other: the lower index stays
+            if (lane < a.nprim) pc[lane].behind = bh;
+            __syncwarp();
+            uint32_t m = bh;
+            while (m) {
+                const int d = __ffs(m) - 1;
+                m &= m - 1;
+                if (((pc[d].behind >> lane) & 1u) && d > lane) bh &= ~(1u << d);
+            }
+            __syncwarp();
+            if (lane < a.nprim) pc[lane].behind = bh;
+            __syncwarp();
+        }
         // ---- tile classification: lane = tile (bbox reject, corner tests, exact occlusion cull)
-        uint32_t my_in = 0, my_part = 0;
-        any_clipped = 0;
-        for (int t = 0; t < a.nprim; t++) any_clipped |= pc[t].valid & pc[t].clipped;
+        uint32_t my_in = 0, my_part = 0; // bit 31 of my_part: near/far clipping can matter inside this tile
         if (lane < n_tiles) {
             const float cl = (float)((lane & (tiles_x - 1)) * TILE_COLS), ch = cl + (TILE_COLS - 1);
             const float rl = (float)(row0 + (lane >> sh_tx) * TILE_ROWS), rh = rl + (TILE_ROWS - 1);
-            double dom[4] = {-1e300, -1e300, -1e300, -1e300}; // lower bound of 1/z of the nearest covering primitive (fp64)
-            int dom_t = -1;
             const double dcl = cl, dch = ch, drl = rl, drh = rh;
+            const double w_near = 1.0 / a.near_, w_far = 1.0 / a.far_;
+            // pass 1: classify (bbox reject, corner tests with the float margins); a primitive with a vertex outside
+            // [near, far] only matters here if its plane leaves the 1/z range over this tile (1/z is affine)
+            bool tile_clipped = false;
             for (int t = 0; t < a.nprim; t++) {
                 const PrimCoef& c = pc[t];
                 if (!c.valid || c.c_hi < cl || c.c_lo > ch || c.r_hi < rl || c.r_lo > rh) continue;
@@ -396,23 +445,35 @@ raster_kernel(const RasterArgs a)
                     out = out || (hi < -mgk);
                 }
                 if (out) continue;
-                if (all_in) {
-                    my_in |= 1u << t;
-                    if (!any_clipped) {
-                        // exact occlusion needs 1/z at the corners in fp64 (grazing primitives have huge float margins)
-                        const double em = 1e-12 * ((fabs(c.eA[4]) + fabs(c.eB[4])) * S + fabs(c.eC[4]));
-                        const double w0 = c.eA[4] * dcl + c.eB[4] * drl + c.eC[4] - em;
-                        if (w0 > dom[0]) {
-                            dom[0] = w0; dom[1] = c.eA[4] * dch + c.eB[4] * drl + c.eC[4] - em;
-                            dom[2] = c.eA[4] * dcl + c.eB[4] * drh + c.eC[4] - em; dom[3] = c.eA[4] * dch + c.eB[4] * drh + c.eC[4] - em;
-                            dom_t = t;
-                        }
-                    }
-                } else my_part |= 1u << t;
+                if (all_in) my_in |= 1u << t; else my_part |= 1u << t;
+                if (c.clipped) {
+                    const double em = 1e-12 * ((fabs(c.eA[4]) + fabs(c.eB[4])) * S + fabs(c.eC[4]));
+                    const double w0 = c.eA[4] * dcl + c.eB[4] * drl + c.eC[4], w1 = c.eA[4] * dch + c.eB[4] * drl + c.eC[4];
+                    const double w2 = c.eA[4] * dcl + c.eB[4] * drh + c.eC[4], w3 = c.eA[4] * dch + c.eB[4] * drh + c.eC[4];
+                    const double lo = fmin(fmin(w0, w1), fmin(w2, w3)) - em, hi = fmax(fmax(w0, w1), fmax(w2, w3)) + em;
+                    if (!(lo > w_far && hi < w_near)) tile_clipped = true;
+                }
             }
-            if (dom_t >= 0) {
-                // drop everything the dominating covering primitive hides (1/z affine: nearer at 4 corners = nearer everywhere)
+            if (!tile_clipped && my_in) {
+                // pass 2: exact occlusion cull against the nearest covering primitive.  1/z at the corners in fp64
+                // (grazing primitives have huge float margins); 1/z affine: nearer at 4 corners = nearer everywhere
+                double dom[4] = {-1e300, -1e300, -1e300, -1e300};
+                int dom_t = -1;
+                uint32_t m = my_in;
+                while (m) {
+                    const int t = __ffs(m) - 1;
+                    m &= m - 1;
+                    const PrimCoef& c = pc[t];
+                    const double em = 1e-12 * ((fabs(c.eA[4]) + fabs(c.eB[4])) * S + fabs(c.eC[4]));
+                    const double w0 = c.eA[4] * dcl + c.eB[4] * drl + c.eC[4] - em;
+                    if (w0 > dom[0]) {
+                        dom[0] = w0; dom[1] = c.eA[4] * dch + c.eB[4] * drl + c.eC[4] - em;
+                        dom[2] = c.eA[4] * dcl + c.eB[4] * drh + c.eC[4] - em; dom[3] = c.eA[4] * dch + c.eB[4] * drh + c.eC[4] - em;
+                        dom_t = t;
+                    }
+                }
                 uint32_t keep_in = 0, keep_part = 0, cand = my_in | my_part;
+                const uint32_t cover = my_in;
                 while (cand) {
                     const int t = __ffs(cand) - 1;
                     cand &= cand - 1;
@@ -420,20 +481,30 @@ raster_kernel(const RasterArgs a)
                     const double em = 1e-12 * ((fabs(c.eA[4]) + fabs(c.eB[4])) * S + fabs(c.eC[4]));
                     const double w0 = c.eA[4] * dcl + c.eB[4] * drl + c.eC[4] + em, w1 = c.eA[4] * dch + c.eB[4] * drl + c.eC[4] + em;
                     const double w2 = c.eA[4] * dcl + c.eB[4] * drh + c.eC[4] + em, w3 = c.eA[4] * dch + c.eB[4] * drh + c.eC[4] + em;
-                    const bool hidden = w0 < dom[0] && w1 < dom[1] && w2 < dom[2] && w3 < dom[3];
+                    // hidden: its plane is behind the dominator's over the tile, or the whole polygon is behind the plane
+                    // of some primitive that covers the tile
+                    const bool hidden = (w0 < dom[0] && w1 < dom[1] && w2 < dom[2] && w3 < dom[3]) || (c.behind & cover) != 0;
                     if (!hidden || t == dom_t) { if ((my_in >> t) & 1u) keep_in |= 1u << t; else keep_part |= 1u << t; }
                 }
                 my_in = keep_in; my_part = keep_part;
+                RSTAT(1, 1);
             }
+            RSTAT(0, 1); RSTAT(2, __popc(my_in)); RSTAT(3, __popc(my_part)); RSTAT(11, tile_clipped ? 1 : 0);
+#ifdef TG_RASTER_STATS
+            for (int t = 0; t < a.nprim; t++) { if ((my_part >> t) & 1u) RSTAT(16 + t, 1); if ((my_in >> t) & 1u) RSTAT(32 + t, 1); }
+#endif
+            if (tile_clipped) my_part |= 0x80000000u;
         }
+        if (lane < a.nprim) { RSTAT(9, pc[lane].valid && pc[lane].steep ? 1 : 0); RSTAT(10, pc[lane].valid ? 1 : 0); }
         uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
         int cnt_in = 0, cnt_pt = 0; // entries in the two span lists (warp-uniform)
         for (int tile = 0; tile <= n_tiles; tile++) {
             const bool drain = tile == n_tiles;
             if (!drain) {
                 // ---- BIN: copy the baked row, list the spans that need shading
-                const uint32_t in_m = __shfl_sync(0xffffffffu, my_in, tile), part_m = __shfl_sync(0xffffffffu, my_part, tile);
-                const int lr = (tile >> sh_tx) * TILE_ROWS + (lane >> 2), c0 = (tile & (tiles_x - 1)) * TILE_COLS + (lane & 3) * 16;
+                const uint32_t in_m = __shfl_sync(0xffffffffu, my_in, tile), part_w = __shfl_sync(0xffffffffu, my_part, tile);
+                const uint32_t part_m = part_w & 0x7fffffffu, tile_clip = part_w >> 31;
+                const int lr = (tile >> sh_tx) * TILE_ROWS + (lane >> TILE_SPR_SHIFT), c0 = (tile & (tiles_x - 1)) * TILE_COLS + (lane & ((1 << TILE_SPR_SHIFT) - 1)) * 16;
                 const int off = (lr << sh_S) + c0, span = off >> 4;
                 *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(s_base + off);
                 if ((in_m | part_m) == 0) continue;
@@ -462,7 +533,7 @@ raster_kernel(const RasterArgs a)
                 const bool act_in = skin && sp_in && !sp_part, act_pt = skin && sp_part;
                 const uint32_t bal_in = __ballot_sync(0xffffffffu, act_in), bal_pt = __ballot_sync(0xffffffffu, act_pt);
                 SpanEntry en;
-                en.off16 = (uint16_t)span; en.in_m = (uint16_t)sp_in; en.part_m = (uint16_t)sp_part; en.pad = 0;
+                en.off16 = (uint16_t)span; en.in_m = (uint16_t)sp_in; en.part_m = (uint16_t)sp_part; en.pad = (uint16_t)tile_clip;
                 if (act_in) l_in[cnt_in + __popc(bal_in & lt_mask)] = en;
                 if (act_pt) l_pt[cnt_pt + __popc(bal_pt & lt_mask)] = en;
                 cnt_in += __popc(bal_in); cnt_pt += __popc(bal_pt);

@@ -127,12 +127,15 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     b.draws = nullptr; b.draw_rounds = 0;
     // standby reset pipeline (tg_env.cuh): needs episodes of at least 2 steps
     b.pipeline = cfg->task.max_steps >= 2 ? 1 : 0;
+    b.ik_chunk = IK_CHUNK; b.reset_chunk = RESET_CHUNK;
+    if (const char* ev = getenv("TG_IK_CHUNK")) b.ik_chunk = std::max(1, atoi(ev));       // tuning hooks
+    if (const char* ev = getenv("TG_RESET_CHUNK")) b.reset_chunk = std::max(1, atoi(ev));
     b.step_blocks = (n + 4 * lanes - 1) / (4 * lanes);
     if ((rc = dalloc(w, &b.sb_q, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_qd, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_embed, n)) ||
         (rc = dalloc(w, &b.sb_ang, n)) || (rc = dalloc(w, &b.sb_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.sb_stim, (size_t)12 * n)) ||
         (rc = dalloc(w, &b.sb_tcp, (size_t)7 * n)) || (rc = dalloc(w, &b.sb_substeps, n)) || (rc = dalloc(w, &b.sb_ready, n)) ||
         (rc = dalloc(w, &b.term_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.term_stim, (size_t)12 * n)) || (rc = dalloc(w, &b.error_flag, 1)) ||
-        (rc = dalloc(w, &b.stall_count, 1)) || (rc = dalloc(w, &b.sb_targ, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_cv, n)) ||
+        (rc = dalloc(w, &b.stall_count, 1)) || (rc = dalloc(w, &b.sb_targ, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_cv, n)) || (rc = dalloc(w, &b.sb_ik, n)) ||
         (rc = dalloc(w, &b.sb_draw, (size_t)TG_MAXDRAW * n))) {
         tg_destroy(w);
         return rc;
@@ -470,3 +473,15 @@ extern "C" int tg_test_substep(TgWorld* w, int n, int nsteps, double* h_q, doubl
 }
 
 extern "C" long long tg_launch_count(const TgWorld* w) { return w ? w->launches : 0; }
+
+#ifdef TG_RASTER_STATS
+// diagnostic build only (tools/raster_stats.py): read and clear the raster counters
+extern "C" int tg_debug_raster_stats(unsigned long long* out48)
+{
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out48, g_rstats, sizeof(unsigned long long) * 48));
+    unsigned long long z[48] = {0};
+    CK(cudaMemcpyToSymbol(g_rstats, z, sizeof(z)));
+    return TG_OK;
+}
+#endif

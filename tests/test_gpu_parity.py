@@ -203,18 +203,18 @@ def test_standby_rebuild_hides_behind_steps(oracle, edge_modes):
     """Episodes longer than a rebuild: every finished env finds its next episode READY (no stall), and the episode it
     starts is the oracle's for the same draws."""
     n, S = 40, 64
-    env = _world(edge_modes, n, S=S, max_steps=14)
+    env = _world(edge_modes, n, S=S, max_steps=40)
     rng = np.random.RandomState(11)
     draws = _draws(rng, n, rounds=4)
     env.world.set_draws(draws)
     env.reset()
     for ep in range(3):
-        for k in range(14):
+        for k in range(40):
             obs, rew, done, infos = env.step(rng.uniform(-0.25, 0.25, (n, 2)).astype(np.float32))
         assert done.all()
         st = env.world.get_state()
         for i in (0, 7, 39):
-            r = oracle.EdgeFollowOracle(image_size=S, max_steps=14)
+            r = oracle.EdgeFollowOracle(image_size=S, max_steps=40)
             o = r.reset(draws=tuple(draws[i, ep + 1]))
             assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=2e-6)
             assert _img_close(o, obs["tactile"][i])[0] <= 1
