@@ -60,6 +60,8 @@ extern "C" {
 /* tasks */
 #define TG_TASK_EDGE_FOLLOW 0
 #define TG_TASK_OBJECT_BALANCE 1
+#define TG_TASK_SURFACE_FOLLOW 2
+#define TG_SURF_N 64 /* heightfield rows = columns */
 
 /* Reduced arm model: fixed joints are merged into their moving parent at asset-compile time
  * (tactile_gym_b200/scene.py); `sub_*` keeps the original mass-carrying links for bullet's per-link
@@ -119,6 +121,14 @@ typedef struct {
     double obj_force;                /* 0.1 N */
     double obj_term_deg, obj_term_pos; /* 35 deg, 0.1 m */
     double p2p_erp, p2p_max_impulse; /* 0.2, 500 [EXT] */
+    /* surface_follow (base_surface_env.py, surface_follow_auto_env.py): a 64 x 64 OpenSimplex heightfield, new every
+     * episode.  draws per reset: OpenSimplex seed (randint(1e8), as a double), goal direction angle */
+    double surf_pos[3];              /* surface body position (also the x/y centre of the grid) */
+    double surf_grid, surf_range;    /* 0.006 m, 0.025 m */
+    double surf_interp, surf_extent; /* 0.05 noise zoom, 0.15 m goal distance / TCP limits */
+    double surf_embed;               /* embed_dist: 0.0025 tactip, 0.0015 digit / digitac */
+    double surf_drive;               /* constant drive along the goal direction: max_action x {1, 0.9, 0.7} */
+    double surf_w_norm;              /* weight of the normal-alignment term (0 for yz / xyz movement) */
 } TgTask;
 
 typedef struct {

@@ -469,3 +469,162 @@ class ObjectBalanceOracle:
             lib().or_step_sim_obj(C.byref(self.m), C.byref(self.s), C.byref(self.o))
         self.reward, self.done = self.step_data()
         return self.observation(), self.reward, self.done, {}
+
+
+# ---------------------------------------------------------------- surface_follow task restatement
+def surface_heights(seed_int, rows=64, cols=64, interp=0.05, rng=0.025):
+    """gen_heigtfield_simplex_2d (base_surface_env.py:311-327) for OpenSimplex(seed=seed_int)"""
+    h = np.zeros((rows, cols))
+    lib().or_surface_heights(C.c_longlong(int(seed_int)), rows, cols, C.c_double(interp), C.c_double(rng), _dptr(h))
+    return h
+
+
+def heightfield_local_vertices(h, grid=0.006):
+    """[EXT] what pybullet draws for createCollisionShape(GEOM_HEIGHTFIELD) (base_surface_env.py:402-424): the data is
+    stored as float32, the shape is centred on the middle of its min/max height (btHeightfieldTerrainShape local origin)
+    and on the grid centre, x = column index, y = row index (data index y * width + x); mesh vertices are float32."""
+    hf = h.astype(np.float32)
+    zc = 0.5 * (float(hf.min()) + float(hf.max()))
+    rows, cols = h.shape
+    x = ((np.arange(cols) - (cols - 1) / 2.0) * grid).astype(np.float32).astype(np.float64)
+    y = ((np.arange(rows) - (rows - 1) / 2.0) * grid).astype(np.float32).astype(np.float64)
+    z = (hf.astype(np.float64) - zc).astype(np.float32).astype(np.float64)
+    V = np.zeros((rows, cols, 3))
+    V[..., 0] = x[None, :]; V[..., 1] = y[:, None]; V[..., 2] = z
+    return V
+
+
+def heightfield_tris(V, i0, i1, j0, j1):
+    """[EXT] btHeightfieldTerrainShape::processAllTriangles with flipQuadEdges / diamond / zigzag off: cell (x=j, y=i) ->
+    (x,y),(x,y+1),(x+1,y) and (x+1,y),(x,y+1),(x+1,y+1).  Cells i0 <= i < i1, j0 <= j < j1."""
+    out = []
+    for i in range(i0, i1):
+        for j in range(j0, j1):
+            out.append([V[i, j], V[i + 1, j], V[i, j + 1]])
+            out.append([V[i, j + 1], V[i + 1, j], V[i + 1, j + 1]])
+    return np.array(out).reshape(-1, 3, 3)
+
+
+class SurfaceFollowOracle:
+    """Restates SurfaceFollowAutoEnv (rl_envs/exploration/surface_follow/surface_follow_auto/surface_follow_auto_env.py)
+    on BaseSurfaceEnv (rl_envs/exploration/surface_follow/base_surface_env.py), noise_mode "simplex", movement modes
+    "xyz" / "xyzRxRy".  One env instance.  The tip core <-> table contact (only reachable in the deepest valleys,
+    SURVEY.md 8a R5) is not modelled."""
+
+    def __init__(self, image_size=128, arm="ur5", sensor="digit", max_steps=200, movement_mode="xyzRxRy", seed=None):
+        self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
+        self.max_steps, self.movement_mode = max_steps, movement_mode
+        self.grid, self.hrange, self.rows, self.cols, self.interp, self.extent = 0.006, 0.025, 64, 64, 0.05, 0.15
+        wd = [0.33, 0.0, 0.0] if arm == "mg400" else [0.65, 0.0, 0.0]                  # base_surface_env.py:54-57
+        self.embed_dist = {"tactip": 0.0025, "digitac": 0.0015, "digit": 0.0015}[sensor]  # :67-75
+        self.surface_pos = np.array([wd[0], wd[1], self.hrange])                          # :261
+        self.workframe_pos = np.array([wd[0], wd[1], self.hrange]); self.workframe_rpy = np.array([-np.pi, 0.0, np.pi / 2])  # :111-114
+        lims = np.zeros((6, 2))
+        lims[0], lims[1], lims[2] = (-self.extent, self.extent), (-self.extent, self.extent), (-self.hrange, self.hrange)
+        lims[3], lims[4] = (-np.pi / 4, np.pi / 4), (-np.pi / 4, np.pi / 4)
+        self.m = load_model(arm, sensor, self.typ, self.workframe_pos, self.workframe_rpy, lims)
+        self.rest = rest_pose("surface_follow", arm, sensor, self.typ, self.m)
+        self.ref = load_refimg(sensor, self.typ, image_size)
+        # :264-271 x/y bins
+        self.x_bins = np.linspace(self.surface_pos[0] - (self.rows / 2) * self.grid, self.surface_pos[0] + (self.rows / 2) * self.grid, self.rows)
+        self.y_bins = np.linspace(self.surface_pos[1] - (self.cols / 2) * self.grid, self.surface_pos[1] + (self.cols / 2) * self.grid, self.cols)
+        self.s = OrState()
+        self.repeat = int(np.floor((1.0 / 10.0) / (1.0 / 240.0)))
+        self.termination_dist = 0.01
+        self.np_random = gym_np_random(seed)
+        self.steps = 0
+        self.last_reset_substeps = 0
+        R = np.zeros(9); lib().or_mat_from_quat(_dptr(quat_from_euler(self.workframe_rpy)), _dptr(R)); self.Rw = R.reshape(3, 3)
+
+    def seed(self, seed):
+        self.np_random = gym_np_random(seed)
+
+    def draw(self):
+        """reset_task order (:539-547): update_surface's randint(1e8) (:448), then make_goal's uniform(-pi, pi) (:508)"""
+        seed_int = self.np_random.randint(1e8)
+        ang = self.np_random.uniform(-np.pi, np.pi)
+        return float(seed_int), ang
+
+    def xy_to_surface_idx(self, x, y):   # :273-288
+        i = int(np.digitize(y, self.y_bins)); j = int(np.digitize(x, self.x_bins))
+        if i == self.cols: i -= 1
+        if j == self.rows: j -= 1
+        return i, j
+
+    def reset(self, draws=None):
+        self.steps = 0
+        seed_int, ang = self.draw() if draws is None else draws
+        self.h = surface_heights(int(seed_int), self.rows, self.cols, self.interp, self.hrange)
+        # update_surface :480-499: surface_array / normals
+        X, Y = np.meshgrid(self.x_bins, self.y_bins)
+        self.surface_array = np.dstack((X, Y, self.h + self.surface_pos[2]))
+        gy, gx = np.gradient(self.h, self.grid)
+        nrm = np.dstack((-gx, -gy, np.ones_like(self.h)))
+        self.surface_normals = nrm / np.linalg.norm(nrm, axis=2)[..., None]
+        self.V = heightfield_local_vertices(self.h, self.grid) + self.surface_pos
+        # make_goal :501-537
+        self.dirs = np.array([np.cos(ang), np.sin(ang), 0.0])
+        wdir = self.Rw @ self.dirs
+        g = [self.surface_pos[0] + self.extent * wdir[0], self.surface_pos[1] + self.extent * wdir[1]]
+        gi, gj = self.xy_to_surface_idx(g[0], g[1])
+        self.goal_pos = np.array([g[0], g[1], self.surface_array[gi, gj, 2]])
+        # update_init_pose :549-573 + Robot.reset
+        ch = self.h[self.rows // 2, self.cols // 2]
+        init_world = np.array([self.surface_pos[0], self.surface_pos[1], self.surface_pos[2] + ch - self.embed_dist])
+        pos = self.Rw.T @ (init_world - self.workframe_pos); rpy = np.zeros(3)
+        self.last_reset_substeps = lib().or_robot_reset(C.byref(self.m), C.byref(self.s), _dptr(self.rest), _dptr(np.ascontiguousarray(pos)), _dptr(rpy))
+        self.reward, self.done = self.step_data()
+        return self.observation()
+
+    def tcp_world(self):
+        P, Q = link_states(self.m, np.array(self.s.q[: self.m.ndof]))
+        return P[self.m.tcp_link], Q[self.m.tcp_link]
+
+    def stimulus_world(self, radius=0.06):
+        """the heightfield cells within `radius` (m) of the TCP in x/y (everything the tactile camera can see)"""
+        p, _ = self.tcp_world()
+        cx = (p[0] - self.surface_pos[0]) / self.grid + (self.cols - 1) / 2.0
+        cy = (p[1] - self.surface_pos[1]) / self.grid + (self.rows - 1) / 2.0
+        r = radius / self.grid
+        j0, j1 = int(max(0, np.floor(cx - r))), int(min(self.cols - 1, np.ceil(cx + r)))
+        i0, i1 = int(max(0, np.floor(cy - r))), int(min(self.rows - 1, np.ceil(cy + r)))
+        if i1 <= i0 or j1 <= j0:
+            return np.zeros((0, 3, 3))
+        return heightfield_tris(self.V, i0, i1, j0, j1)
+
+    def observation(self):
+        q = np.array(self.s.q[: self.m.ndof])
+        return tactile_image(self.m, q, self.S, self.stimulus_world(), self.ref, border_on=True)[..., None]
+
+    def step_data(self):   # :631-775 + surface_follow_auto_env.py:76-94
+        p, qt = self.tcp_world()
+        self.tip_i, self.tip_j = self.xy_to_surface_idx(p[0], p[1])
+        R = np.zeros(9); lib().or_mat_from_quat(_dptr(np.ascontiguousarray(qt)), _dptr(R)); R = R.reshape(3, 3)
+        done = bool(np.linalg.norm(p - self.goal_pos) < self.termination_dist or self.steps >= self.max_steps)
+        emb = p + R @ np.array([0.0, 0.0, -self.embed_dist])
+        surf_dist = abs(emb[2] - self.surface_array[self.tip_i, self.tip_j, 2])
+        n = self.surface_normals[self.tip_i, self.tip_j]
+        v = R @ np.array([0.0, 0.0, -1.0])
+        cos_dist = 1 - np.dot(n, v) / (np.linalg.norm(n) * np.linalg.norm(v))
+        w_norm = 0.0 if self.movement_mode in ("yz", "xyz") else 1.0
+        return -(1.0 * surf_dist + w_norm * cos_dist), done
+
+    def encode_scale(self, action):   # surface_follow_auto_env.py:27-57, base_tactile_env.py:141-164
+        enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
+        k = {"tactip": 1.0, "digitac": 0.9, "digit": 0.7}[self.sensor]
+        enc[0] = self.dirs[0] * 0.25 * k; enc[1] = self.dirs[1] * 0.25 * k
+        if self.movement_mode == "xyz":
+            enc[2] = a[0]
+        else:
+            enc[2], enc[3], enc[4] = a[0], a[1], a[2]
+        enc = np.clip(enc, -0.25, 0.25)
+        mv, ma = 0.01, 5.0 * (np.pi / 180)
+        amax = np.array([mv, mv, mv, ma, ma, 0.0]); amin = -amax
+        return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
+
+    def step(self, action):
+        v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
+        self.steps += 1
+        lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
+        self.reward, self.done = self.step_data()
+        return self.observation(), self.reward, self.done, {}

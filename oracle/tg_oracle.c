@@ -976,3 +976,84 @@ void or_tactile_image(const OrModel* m, const double* q, int S, const double* tr
     }
     free(cur);
 }
+
+
+/* ================================================================ surface_follow: OpenSimplex heightfield
+ * base_surface_env.py:443-448 `OpenSimplex(seed=self.np_random.randint(1e8))`, :311-327 noise2 over the 64x64 grid.
+ * [EXT] opensimplex package (unpinned): _init / _noise2 restated from the published algorithm. */
+void or_opensimplex_init(long long seed_in, short perm[256])
+{
+    short source[256];
+    unsigned long long seed = (unsigned long long)seed_in; /* int64 wrap-around arithmetic */
+    for (int i = 0; i < 256; i++) source[i] = (short)i;
+    for (int k = 0; k < 3; k++) seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    for (int i = 255; i >= 0; i--) {
+        seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+        /* r = int((seed + 31) % (i + 1)) with Python's floor modulo on the signed 64-bit seed */
+        const long long sseed = (long long)seed;
+        const long long n = i + 1;
+        long long r = ((sseed % n) + n) % n;
+        r = (r + 31 % n) % n;
+        perm[i] = source[r];
+        source[r] = source[i];
+    }
+}
+
+static double os_extrapolate2(const short* perm, long long xsb, long long ysb, double dx, double dy)
+{
+    static const double G2[16] = {5, 2, 2, 5, -5, 2, -2, 5, 5, -2, 2, -5, -5, -2, -2, -5};
+    const int index = perm[(perm[xsb & 0xFF] + ysb) & 0xFF] & 0x0E;
+    return G2[index] * dx + G2[index + 1] * dy;
+}
+
+double or_opensimplex_noise2(const short perm[256], double x, double y)
+{
+    const double STRETCH = -0.211324865405187, SQUISH = 0.366025403784439, NORM = 47.0;
+    const double stretch_offset = (x + y) * STRETCH;
+    const double xs = x + stretch_offset, ys = y + stretch_offset;
+    long long xsb = (long long)floor(xs), ysb = (long long)floor(ys);
+    const double squish_offset = (double)(xsb + ysb) * SQUISH;
+    const double xb = (double)xsb + squish_offset, yb = (double)ysb + squish_offset;
+    const double xins = xs - (double)xsb, yins = ys - (double)ysb;
+    const double in_sum = xins + yins;
+    double dx0 = x - xb, dy0 = y - yb;
+    double value = 0.0;
+    double dx_ext, dy_ext;
+    long long xsv_ext, ysv_ext;
+
+    const double dx1 = dx0 - 1 - SQUISH, dy1 = dy0 - 0 - SQUISH;
+    double attn1 = 2 - dx1 * dx1 - dy1 * dy1;
+    if (attn1 > 0) { attn1 *= attn1; value += attn1 * attn1 * os_extrapolate2(perm, xsb + 1, ysb + 0, dx1, dy1); }
+    const double dx2 = dx0 - 0 - SQUISH, dy2 = dy0 - 1 - SQUISH;
+    double attn2 = 2 - dx2 * dx2 - dy2 * dy2;
+    if (attn2 > 0) { attn2 *= attn2; value += attn2 * attn2 * os_extrapolate2(perm, xsb + 0, ysb + 1, dx2, dy2); }
+
+    if (in_sum <= 1) {
+        const double zins = 1 - in_sum;
+        if (zins > xins || zins > yins) {
+            if (xins > yins) { xsv_ext = xsb + 1; ysv_ext = ysb - 1; dx_ext = dx0 - 1; dy_ext = dy0 + 1; }
+            else { xsv_ext = xsb - 1; ysv_ext = ysb + 1; dx_ext = dx0 + 1; dy_ext = dy0 - 1; }
+        } else { xsv_ext = xsb + 1; ysv_ext = ysb + 1; dx_ext = dx0 - 1 - 2 * SQUISH; dy_ext = dy0 - 1 - 2 * SQUISH; }
+    } else {
+        const double zins = 2 - in_sum;
+        if (zins < xins || zins < yins) {
+            if (xins > yins) { xsv_ext = xsb + 2; ysv_ext = ysb + 0; dx_ext = dx0 - 2 - 2 * SQUISH; dy_ext = dy0 + 0 - 2 * SQUISH; }
+            else { xsv_ext = xsb + 0; ysv_ext = ysb + 2; dx_ext = dx0 + 0 - 2 * SQUISH; dy_ext = dy0 - 2 - 2 * SQUISH; }
+        } else { dx_ext = dx0; dy_ext = dy0; xsv_ext = xsb; ysv_ext = ysb; }
+        xsb += 1; ysb += 1;
+        dx0 = dx0 - 1 - 2 * SQUISH; dy0 = dy0 - 1 - 2 * SQUISH;
+    }
+    double attn0 = 2 - dx0 * dx0 - dy0 * dy0;
+    if (attn0 > 0) { attn0 *= attn0; value += attn0 * attn0 * os_extrapolate2(perm, xsb, ysb, dx0, dy0); }
+    double attn_ext = 2 - dx_ext * dx_ext - dy_ext * dy_ext;
+    if (attn_ext > 0) { attn_ext *= attn_ext; value += attn_ext * attn_ext * os_extrapolate2(perm, xsv_ext, ysv_ext, dx_ext, dy_ext); }
+    return value / NORM;
+}
+
+void or_surface_heights(long long seed, int rows, int cols, double interp, double range, double* out)
+{
+    short perm[256];
+    or_opensimplex_init(seed, perm);
+    for (int x = 0; x < rows; x++)
+        for (int y = 0; y < cols; y++) out[x * cols + y] = or_opensimplex_noise2(perm, x * interp, y * interp) * range;
+}

@@ -132,6 +132,15 @@ void or_tactile_image(const OrModel* m, const double* q, int S, const double* tr
 void or_depth_image(const double eye[3], const double fwd[3], const double up[3], const double right[3],
                     double fov_deg, double near_, double far_, int S, const float* tris, int ntri, float* depth_out);
 
+/* ---- surface_follow: OpenSimplex heightfield (rl_envs/exploration/surface_follow/base_surface_env.py:311-334,443-458) ----
+ * PARITY UNPINNED: `opensimplex` (requirements.txt:4, unpinned, not vendored, not installed) - restated from the
+ * published algorithm (K. Spencer's OpenSimplex, 2D, as shipped in the opensimplex 0.4 Python package): LCG-shuffled
+ * permutation from the seed, stretch/squish constants (1/sqrt(3)-1)/2 and (sqrt(3)-1)/2, 8 gradients, norm 47. */
+void or_opensimplex_init(long long seed, short perm[256]);
+double or_opensimplex_noise2(const short perm[256], double x, double y);
+/* gen_heigtfield_simplex_2d (:311-327): out[x*cols + y] = noise2(x*interp, y*interp) * range */
+void or_surface_heights(long long seed, int rows, int cols, double interp, double range, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("TG_LIB_OVERRIDE") or os.path.join(HERE, "libtactile_g
 
 TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 8
 TG_TOPO_CHAIN6, TG_TOPO_MG400 = 0, 1
-TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE = 0, 1
+TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE, TG_TASK_SURFACE_FOLLOW = 0, 1, 2
 
 D3 = C.c_double * 3
 D9 = C.c_double * 9
@@ -49,6 +49,8 @@ class TgTask(C.Structure):
         ("obj_mass", C.c_double), ("obj_inertia", D3), ("obj_com_off", D3), ("obj_base_com", D3), ("obj_init_rpy", D3),
         ("obj_base_w", C.c_double), ("obj_base_h", C.c_double), ("obj_force", C.c_double),
         ("obj_term_deg", C.c_double), ("obj_term_pos", C.c_double), ("p2p_erp", C.c_double), ("p2p_max_impulse", C.c_double),
+        ("surf_pos", D3), ("surf_grid", C.c_double), ("surf_range", C.c_double), ("surf_interp", C.c_double),
+        ("surf_extent", C.c_double), ("surf_embed", C.c_double), ("surf_drive", C.c_double), ("surf_w_norm", C.c_double),
     ]
 
 

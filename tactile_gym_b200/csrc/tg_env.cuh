@@ -19,13 +19,14 @@
 // re-synchronised every RESET_CHUNK iterations on every path), so results do not depend on who ran which chunk.
 #pragma once
 #include "tg_dyn.cuh"
+#include "tg_surface.cuh"
 
 struct EnvBuffers {
     int n;
     int lanes;            // active lanes per warp in the step role
     int step_blocks;      // blocks [0, step_blocks) step envs, the rest recompute standbys
     int pipeline;         // 1: standby reset pipeline on
-    int ik_chunk, reset_chunk; // quantum sizes of the resumable reset (IK / blocking-move iterations per launch)
+    int ik_chunk, reset_chunk, surf_chunk; // quantum sizes of the resumable reset (IK / blocking-move iterations, heightfield points per launch)
     double* q;            // [NB][N]
     double* qd;           // [NB][N]
     double* embed;        // [N]
@@ -48,6 +49,13 @@ struct EnvBuffers {
     int* sb_ready;           // [N] slot state: SB_EMPTY / SB_READY / SB_PARTIAL / SB_BUSY
     int* sb_ik;              // [N] partial resets: IK iteration (ResetState::ik_it)
     double *sb_targ, *sb_cv, *sb_draw; // partial resets: IK target joints [NB][N], blocking-move step [N], draws [N][TG_MAXDRAW]
+    // surface_follow: heightfields [N][2][64*64] (one live, one being / been built for the next episode), hf_cur [N] = the
+    // live one, hf_meta [N][2][SURF_META]; partial resets: noise permutation [N][256], next grid point [N], float min/max [N][2]
+    double *height, *hf_meta;
+    int* hf_cur;
+    unsigned char* sb_perm;
+    int* sb_surf_it;
+    float* sb_hmm;
     // camera / stimulus of the state an env terminated in (for the terminal observation)
     double *term_cam, *term_stim;
     int* error_flag;         // sticky error flag (unused slots of the pipeline; kept for the C-ABI)
@@ -58,6 +66,7 @@ enum { SB_EMPTY = 0, SB_READY = 1, SB_PARTIAL = 2, SB_BUSY = 3 };
 #define RESET_CHUNK 6  // blocking-move iterations per quantum (a quarter of an env step's work: a standby warp may
                        // carry an IK quantum and a move quantum one after the other, plus cold code)
 #define IK_CHUNK 8     // IK iterations per quantum
+#define SURF_CHUNK 96  // heightfield points (OpenSimplex evaluations) per quantum
 
 // a reset in flight (between draws + IK and the end of the blocking move)
 template <int NB>
@@ -65,6 +74,8 @@ struct ResetState {
     double q[NB], qd[NB], targ_j[NB], cv, embed, edge_ang, draw[TG_MAXDRAW];
     int nsteps;
     int ik_it; // >= 0: the IK solve is at this iteration; -1: solved, the blocking move is running
+    int surf_it;       // surface_follow: next heightfield point to generate (SURF_PTS = done)
+    float hmin, hmax;  // running min / max of the float32 heights (the drawn mesh is centred on their middle)
 };
 
 // one env's start-of-episode state
@@ -227,7 +238,8 @@ TGD int ik_chunk(const TgArm& arm, double* q, const double* tpos, const double* 
 }
 
 // workframe_to_worldframe (base_robot_arm.py:47-60) of the init pose [0,0,embed], init_rpy
-TGD void reset_target(const TgTask& task, double embed, double* tpos, double* targ_orn)
+// (surface_follow: centre_h = the new surface's height at the grid centre, base_surface_env.py:549-573)
+TGD void reset_target(const TgTask& task, double embed, double centre_h, double* tpos, double* targ_orn)
 {
     const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
     double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
@@ -237,6 +249,7 @@ TGD void reset_target(const TgTask& task, double embed, double* tpos, double* ta
     mat_from_quat(wq, R);
     m3mulv(t, R, lp);
     tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
+    if (task.task == TG_TASK_SURFACE_FOLLOW) { tpos[0] = task.surf_pos[0]; tpos[1] = task.surf_pos[1]; tpos[2] = task.surf_pos[2] + centre_h - embed; }
     quat_mul(oq, wq, tq);
     euler_from_quat(oq, rpy);
     quat_from_euler(rpy, targ_orn);
@@ -260,9 +273,16 @@ __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, c
         b.reset_count[e] = cnt + 1;
     }
     const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
-    // edge_follow draws: embed_dist, edge_ang; object_balance draws: gravity_z, embed_dist, fx, fy
+    // edge_follow draws: embed_dist, edge_ang; object_balance draws: gravity_z, embed_dist, fx, fy;
+    // surface_follow draws: OpenSimplex seed, goal direction angle (kept in edge_ang)
     r.embed = balance ? r.draw[1] : r.draw[0];
     r.edge_ang = balance ? 0.0 : r.draw[1];
+    r.surf_it = SURF_PTS; r.hmin = 0.f; r.hmax = 0.f;
+    if (task.task == TG_TASK_SURFACE_FOLLOW) {
+        r.embed = task.surf_embed;
+        os_perm((long long)r.draw[0], b.sb_perm + (size_t)e * 256);
+        r.surf_it = 0; r.hmin = 3.0e38f; r.hmax = -3.0e38f;
+    }
 #pragma unroll
     for (int i = 0; i < NB; i++) { r.q[i] = b.rest_q[i]; r.qd[i] = 0.0; r.targ_j[i] = r.q[i]; }
     r.cv = 0.001;
@@ -274,11 +294,30 @@ __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, c
 // that is solved, up to RESET_CHUNK iterations of Robot.blocking_move(max_steps=1000, constant_vel=0.001)
 // (robot.py:188-260).  Returns true when the move has ended.
 template <class T>
-__device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, ResetState<T::NB>& r)
+__device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, ResetState<T::NB>& r)
 {
     constexpr int NB = T::NB;
+    double centre_h = 0.0;
+    if (task.task == TG_TASK_SURFACE_FOLLOW) {
+        // the next episode's heightfield goes into the buffer the live episode does not use
+        double* H = b.height + ((size_t)e * 2 + (size_t)(1 - b.hf_cur[e])) * SURF_PTS;
+        if (r.surf_it < SURF_PTS) {
+            // gen_heigtfield_simplex_2d (base_surface_env.py:311-327): h[x][y] = noise2(x * 0.05, y * 0.05) * 0.025
+            const unsigned char* perm = b.sb_perm + (size_t)e * 256;
+            const int end = min(r.surf_it + b.surf_chunk, SURF_PTS);
+#pragma unroll 1
+            for (int k = r.surf_it; k < end; k++) {
+                const double h = os_noise2(perm, (double)(k / SURF_N) * task.surf_interp, (double)(k % SURF_N) * task.surf_interp) * task.surf_range;
+                H[k] = h;
+                r.hmin = fminf(r.hmin, (float)h); r.hmax = fmaxf(r.hmax, (float)h);
+            }
+            r.surf_it = end;
+            return false;
+        }
+        centre_h = H[(SURF_N / 2) * SURF_N + SURF_N / 2];
+    }
     double tpos[3], targ_orn[4];
-    reset_target(task, r.embed, tpos, targ_orn);
+    reset_target(task, r.embed, centre_h, tpos, targ_orn);
     if (r.ik_it >= 0) {
         r.ik_it = ik_chunk<T>(arm, r.targ_j, tpos, targ_orn, r.ik_it, b.ik_chunk);
         return false;
@@ -323,7 +362,7 @@ __device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph
 
 // Reset, part 3: the start-of-episode state the step and raster kernels consume.
 template <class T>
-__device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, const ResetState<T::NB>& r, EpisodeStart<T::NB>& out)
+__device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, const EnvBuffers& b, int e, const ResetState<T::NB>& r, EpisodeStart<T::NB>& out)
 {
     constexpr int NB = T::NB;
     const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
@@ -342,7 +381,28 @@ __device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, 
 #pragma unroll
         for (int c = 0; c < 4; c++) out.tcp[3 + c] = tq[c];
     }
-    if (!balance) {
+    if (task.task == TG_TASK_SURFACE_FOLLOW) {
+        // make_goal (base_surface_env.py:501-537) on the new surface; the drawn mesh's height offset
+        const int sbuf = 1 - b.hf_cur[e];
+        const double* H = b.height + ((size_t)e * 2 + (size_t)sbuf) * SURF_PTS;
+        double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)sbuf) * SURF_META;
+        double sn, cs, wq[4], R[9];
+        sincos(r.edge_ang, &sn, &cs);
+        const double dirs[3] = {cs, sn, 0.0};
+        double wd[3];
+        quat_from_euler(task.workframe_rpy, wq);
+        mat_from_quat(wq, R);
+        m3mulv(wd, R, dirs);
+        const double gx = task.surf_pos[0] + task.surf_extent * wd[0], gy = task.surf_pos[1] + task.surf_extent * wd[1];
+        int gi, gj;
+        surf_index(task, gx, gy, gi, gj);
+        meta[0] = 0.5 * ((double)r.hmin + (double)r.hmax);
+        meta[1] = dirs[0]; meta[2] = dirs[1];
+        meta[3] = gx; meta[4] = gy; meta[5] = H[gi * SURF_N + gj] + task.surf_pos[2];
+        meta[6] = 0.0; meta[7] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) out.stim[i] = 0.0;
+    } else if (!balance) {
         double sn, cs;
         sincos(r.edge_ang * 0.5, &sn, &cs);
         double qz[4] = {0, 0, sn, cs}, R[9]; // getQuaternionFromEuler([0,0,ang]) (edge_follow_env.py:241)
@@ -377,8 +437,8 @@ TGD void reset_env(const TgArm& arm, const TgPhysics& ph, const TgTask& task, co
     ResetState<T::NB> r;
     reset_begin<T>(arm, task, b, e, r);
 #pragma unroll 1
-    while (!reset_advance<T>(arm, ph, task, b, r)) {}
-    reset_finish<T>(arm, task, r, out);
+    while (!reset_advance<T>(arm, ph, task, b, e, r)) {}
+    reset_finish<T>(arm, task, b, e, r, out);
 }
 
 template <int NB>
@@ -418,6 +478,7 @@ TGD void store_partial(const EnvBuffers& b, int e, const ResetState<NB>& r)
         b.sb_q[(size_t)i * b.n + e] = r.q[i]; b.sb_qd[(size_t)i * b.n + e] = r.qd[i]; b.sb_targ[(size_t)i * b.n + e] = r.targ_j[i];
     }
     b.sb_embed[e] = r.embed; b.sb_ang[e] = r.edge_ang; b.sb_substeps[e] = r.nsteps; b.sb_cv[e] = r.cv; b.sb_ik[e] = r.ik_it;
+    if (b.height) { b.sb_surf_it[e] = r.surf_it; b.sb_hmm[2 * e] = r.hmin; b.sb_hmm[2 * e + 1] = r.hmax; }
 #pragma unroll
     for (int d = 0; d < TG_MAXDRAW; d++) b.sb_draw[(size_t)e * TG_MAXDRAW + d] = r.draw[d];
     __threadfence();
@@ -431,6 +492,8 @@ TGD void load_partial(const EnvBuffers& b, int e, ResetState<NB>& r)
         r.q[i] = __ldcg(b.sb_q + (size_t)i * b.n + e); r.qd[i] = __ldcg(b.sb_qd + (size_t)i * b.n + e); r.targ_j[i] = __ldcg(b.sb_targ + (size_t)i * b.n + e);
     }
     r.embed = __ldcg(b.sb_embed + e); r.edge_ang = __ldcg(b.sb_ang + e); r.nsteps = __ldcg(b.sb_substeps + e); r.cv = __ldcg(b.sb_cv + e); r.ik_it = __ldcg(b.sb_ik + e);
+    r.surf_it = SURF_PTS; r.hmin = 0.f; r.hmax = 0.f;
+    if (b.height) { r.surf_it = __ldcg(b.sb_surf_it + e); r.hmin = __ldcg(b.sb_hmm + 2 * e); r.hmax = __ldcg(b.sb_hmm + 2 * e + 1); }
 #pragma unroll
     for (int d = 0; d < TG_MAXDRAW; d++) r.draw[d] = __ldcg(b.sb_draw + (size_t)e * TG_MAXDRAW + d);
 }
@@ -453,6 +516,7 @@ TGD void consume_standby(const EnvBuffers& b, int e)
         for (int c = 0; c < 4; c++) b.obj_ext[(size_t)e * 4 + c] = __ldcg(b.sb_obj_ext + (size_t)e * 4 + c);
         b.grav[e] = __ldcg(b.sb_grav + e);
     }
+    if (b.height) b.hf_cur[e] = 1 - b.hf_cur[e]; // the heightfield built for this episode becomes the live one
     __threadfence();
     atomicExch(&b.sb_ready[e], SB_EMPTY);
 }
@@ -470,14 +534,14 @@ TGD void standby_work(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
     bool fin = false;
     if (s == SB_EMPTY) reset_begin<T>(arm, task, b, e, r);
     else load_partial<T::NB>(b, e, r);
-    fin = reset_advance<T>(arm, ph, task, b, r);
+    fin = reset_advance<T>(arm, ph, task, b, e, r);
     if (complete) {
 #pragma unroll 1
-        while (!fin) fin = reset_advance<T>(arm, ph, task, b, r);
+        while (!fin) fin = reset_advance<T>(arm, ph, task, b, e, r);
     }
     if (fin) {
         EpisodeStart<T::NB> es;
-        reset_finish<T>(arm, task, r, es);
+        reset_finish<T>(arm, task, b, e, r, es);
         store_standby<T::NB>(b, e, es);
     } else store_partial<T::NB>(b, e, r);
 }
@@ -537,6 +601,11 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
                 for (int s = 0; s < 6; s++) if (task.act_index[kk] == s) enc[s] = a;
             }
+        if (task.task == TG_TASK_SURFACE_FOLLOW) {
+            // SurfaceFollowAutoEnv.encode_actions (surface_follow_auto_env.py:27-57): constant drive towards the goal
+            const double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)b.hf_cur[e]) * SURF_META;
+            enc[0] = meta[1] * task.surf_drive; enc[1] = meta[2] * task.surf_drive;
+        }
         const double in_range = task.act_max - task.act_min;
 #pragma unroll
         for (int s = 0; s < 6; s++) {
@@ -615,6 +684,9 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     if (balance) {
         balance_step_data(task, ob, b.embed[e], steps, &r, &d);
         obj_stim(task, ob, b.stim + (size_t)e * 12); // the pole moves: the raster needs its pose every step
+    } else if (task.task == TG_TASK_SURFACE_FOLLOW) {
+        const size_t hb = (size_t)e * 2 + (size_t)b.hf_cur[e];
+        surface_step_data(task, b.height + hb * SURF_PTS, b.hf_meta + hb * SURF_META, tp, tq, steps, &r, &d);
     } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
     reward[e] = r; done[e] = d;
     if (d && autoreset && b.pipeline) {

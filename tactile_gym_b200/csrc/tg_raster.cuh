@@ -71,6 +71,13 @@ struct RasterArgs {
     const uint8_t* mask;   // optional [N]
     uint8_t* obs;          // [N][S*S]
     float nd_ref;          // reference depth: the float path works on (nodef - nd_ref) to keep magnitudes (and errors) small
+    // heightfield stimulus (surface_follow, raster_hf_kernel): per-env 64 x 64 heights instead of a shared primitive list
+    const double* hf;      // [N][2][64*64] fp64 heights (row = y index)
+    const int* hf_cur;     // [N] which of the two is the live episode's
+    const double* hf_meta; // [N][2][SURF_META], [0] = the mesh's height offset (middle of the float32 range)
+    int hf_flip;           // 1: use the OTHER buffer (terminal observation of an env that has just been reset)
+    int hf_tile_rows, hf_tile_cols; // tile of the heightfield kernel: rows x cols pixels, rows * cols / 16 <= 32 spans
+    double surf_pos[3], surf_grid;
 };
 
 struct SpanEntry {
@@ -93,6 +100,8 @@ __device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gm
 }
 
 // vp[k] = (column, row, 1/z) of vertex k in pixel units, meaningful when the return value (all vertices in front) is true
+__device__ __forceinline__ bool prim_from_eye(const RasterArgs& a, const double (*ve)[3], int nv, PrimCoef& o, double (*vp)[3]);
+
 __device__ __forceinline__ bool prim_setup(const RasterArgs& a, const double* cam, const double* stim, const double* pl, int nv, PrimCoef& o, double (*vp)[3])
 {
     // stimulus frame -> world -> eye space (x right, y up, z forward)
@@ -107,6 +116,21 @@ __device__ __forceinline__ bool prim_setup(const RasterArgs& a, const double* ca
         ve[k][1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
         ve[k][2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
     }
+    return prim_from_eye(a, ve, nv, o, vp);
+}
+
+// world -> eye space
+__device__ __forceinline__ void world_to_eye(const double* cam, const double* v, double* e)
+{
+    const double w[3] = {v[0] - cam[0], v[1] - cam[1], v[2] - cam[2]};
+    e[0] = w[0] * cam[9] + w[1] * cam[10] + w[2] * cam[11];
+    e[1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
+    e[2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
+}
+
+// screen-space coefficient setup of one convex planar polygon given in eye space (ve[k], k >= nv repeat the last vertex)
+__device__ __forceinline__ bool prim_from_eye(const RasterArgs& a, const double (*ve)[3], int nv, PrimCoef& o, double (*vp)[3])
+{
     const double S = a.S;
     // plane: n . p = n . v0 ; along the pixel ray p = z d (d.z = 1):  1/z = (n . d) / (n . v0)
     double e1[3] = {ve[1][0] - ve[0][0], ve[1][1] - ve[0][1], ve[1][2] - ve[0][2]};
@@ -220,6 +244,128 @@ __device__ __forceinline__ uint32_t exact_pixel(const RasterArgs& a, const PrimC
     return quantize(fminf(nd, d), nd);
 }
 
+// what a warp's shading code needs (all shared-memory pointers are the warp's own)
+struct WarpCtx {
+    const PrimCoef* pc;
+    const float* s_nodef;
+    const uint8_t* s_base;
+    void* s_queue;  // exact-path queue: uint32 entries (mask << 16 | pixel offset, <= 16 primitives) or uint64 (mask << 32 | offset)
+    int* s_qcnt;
+    int S, sh_S, row0;
+};
+
+template <class QT> __device__ __forceinline__ QT queue_entry(uint32_t cand, uint32_t off);
+template <> __device__ __forceinline__ uint32_t queue_entry<uint32_t>(uint32_t cand, uint32_t off) { return (cand << 16) | off; }
+template <> __device__ __forceinline__ unsigned long long queue_entry<unsigned long long>(uint32_t cand, uint32_t off) { return ((unsigned long long)cand << 32) | off; }
+__device__ __forceinline__ void queue_decode(uint32_t q, uint32_t& cand, int& off) { cand = q >> 16; off = (int)(q & 0xffffu); }
+__device__ __forceinline__ void queue_decode(unsigned long long q, uint32_t& cand, int& off) { cand = (uint32_t)(q >> 32); off = (int)(uint32_t)q; }
+
+// shade one 16-pixel span (this lane's): float fast path; uncertain pixels go to the exact queue.
+// off = pixel offset inside the band; in_m / part_m = primitives covering the whole span / crossing it
+template <bool WITH_PART, class QT>
+__device__ __forceinline__ void shade_span(const RasterArgs& a, const WarpCtx& x, int off, uint32_t in_m, uint32_t part_m, bool clip, uint8_t* obs_e)
+{
+    const PrimCoef* pc = x.pc;
+    const int S = x.S;
+    const int lr = off >> x.sh_S, c0 = off & (S - 1), r = x.row0 + lr;
+    const float fr = (float)r, fc0 = (float)c0;
+    float vb[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) vb[k] = -1e30f;
+    uint32_t unc = 0; // pixels that need the exact path
+    uint32_t m = in_m;
+    while (m) {
+        const int t = __ffs(m) - 1;
+        m &= m - 1;
+        if (pc[t].steep) {
+            // grazing primitive: V is a small difference of large terms -> evaluate it in fp64, round the result
+            const double dA = pc[t].dvA, d0 = dA * c0 + (pc[t].dvB * r + pc[t].dvC);
+#pragma unroll
+            for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], (float)(dA * k + d0));
+            continue;
+        }
+        const float vA = pc[t].vA, v0 = fmaf(vA, fc0, fmaf(pc[t].vB, fr, pc[t].vC));
+#pragma unroll
+        for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], fmaf(vA, (float)k, v0));
+    }
+    if constexpr (WITH_PART) {
+        m = part_m;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            const PrimCoef& c = pc[t];
+            const float mg = c.margin, sc = c.margin / fmaxf(c.wmargin, 1e-30f); // w is compared on the edges' margin scale
+            const bool steep = c.steep;
+            float a0[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++) a0[i] = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i]));
+            const float vA = c.vA, v0 = fmaf(vA, fc0, fmaf(c.vB, fr, c.vC));
+            const double dA = c.dvA, d0 = steep ? dA * c0 + (c.dvB * r + c.dvC) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const float fk = (float)k;
+                const float lo = fminf(fminf(fmaf(c.fA[0], fk, a0[0]), fmaf(c.fA[1], fk, a0[1])),
+                                       fminf(fminf(fmaf(c.fA[2], fk, a0[2]), fmaf(c.fA[3], fk, a0[3])), fmaf(c.fA[4], fk, a0[4]) * sc));
+                if (lo > mg) vb[k] = fmaxf(vb[k], steep ? (float)(dA * k + d0) : fmaf(vA, fk, v0));
+                else if (lo >= -mg) unc |= 1u << k; // within the float margin of an edge
+            }
+            RSTAT(4, __popc(unc));
+        }
+    }
+    float nd[16];
+    {
+        const float4* p = reinterpret_cast<const float4*>(x.s_nodef + off);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 v = p[k];
+            nd[4 * k] = v.x; nd[4 * k + 1] = v.y; nd[4 * k + 2] = v.z; nd[4 * k + 3] = v.w;
+        }
+    }
+    const uint4 bres = *reinterpret_cast<const uint4*>(x.s_base + off);
+    uint32_t wds[4] = {bres.x, bres.y, bres.z, bres.w};
+    uint32_t nd_skin = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        // val = 5100 (nodef - d).  nodef - nd_ref is exact (Sterbenz); uncovered pixels have vb = -1e30 -> 0;
+        // border pixels (nd = -1) keep the baked byte
+        const bool skin = nd[k] >= 0.0f;
+        nd_skin |= (skin ? 1u : 0u) << k;
+        const float val = skin ? fmaf(nd[k] - a.nd_ref, VAL_SCALE, vb[k]) : -1e30f;
+        const uint32_t u = __float2uint_rz(fminf(fmaxf(val, 0.0f), 255.0f));
+        // quantisation step within the error bound?  (val in (-B, 255 + B) and |val - round(val)| < B)
+        if (fabsf(val - rintf(val)) < VAL_BOUND && val > -VAL_BOUND && val < 255.0f + VAL_BOUND) unc |= 1u << k;
+        wds[k >> 2] |= u << (8 * (k & 3));
+    }
+    *reinterpret_cast<uint4*>(obs_e + off) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    if (clip) unc = 0xffffu; // near/far clipping in play in this tile: every pixel of the span takes the exact path
+    unc &= nd_skin;
+    RSTAT(5, __popc(unc)); RSTAT(6, __popc(unc) * __popc(in_m | part_m)); RSTAT(7, 1);
+    RSTAT(8, __popc(part_m));
+    QT* queue = reinterpret_cast<QT*>(x.s_queue);
+    while (unc) {
+        const int k = __ffs(unc) - 1;
+        unc &= unc - 1;
+        queue[atomicAdd(x.s_qcnt, 1)] = queue_entry<QT>(in_m | part_m, (uint32_t)(off + k));
+    }
+}
+
+// EXACT PATCH-UP of the queued pixels (whole warp)
+template <class QT>
+__device__ __forceinline__ void flush_exact(const RasterArgs& a, const WarpCtx& x, uint8_t* obs_e, int lane)
+{
+    __syncwarp();
+    const int qn = *x.s_qcnt;
+    const QT* queue = reinterpret_cast<const QT*>(x.s_queue);
+    for (int i = lane; i < qn; i += 32) {
+        uint32_t cand; int off;
+        queue_decode(queue[i], cand, off);
+        obs_e[off] = (uint8_t)exact_pixel(a, x.pc, cand, off & (x.S - 1), x.row0 + (off >> x.sh_S), x.s_nodef[off], x.s_base[off]);
+    }
+    __syncwarp();
+    if (lane == 0) *x.s_qcnt = 0;
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS)
 raster_kernel(const RasterArgs a)
 {
@@ -281,104 +427,13 @@ raster_kernel(const RasterArgs a)
     SpanEntry* l_in = s_list;             // spans covered by whole primitives only
     SpanEntry* l_pt = s_list + SPAN_LIST; // spans some primitive edge crosses
 
-    // shade one listed span (this lane's): float fast path; uncertain pixels go to the exact queue
+    WarpCtx ctx;
+    ctx.pc = pc; ctx.s_nodef = s_nodef; ctx.s_base = s_base; ctx.s_queue = s_queue; ctx.s_qcnt = s_qcnt;
+    ctx.S = S; ctx.sh_S = sh_S; ctx.row0 = row0;
     auto shade = [&](const SpanEntry en, uint8_t* obs_e, auto with_part) {
-        const int off = (int)en.off16 * 16;
-        const int lr = off >> sh_S, c0 = off & (S - 1), r = row0 + lr;
-        const float fr = (float)r, fc0 = (float)c0;
-        float vb[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) vb[k] = -1e30f;
-        uint32_t unc = 0; // pixels that need the exact path
-        uint32_t m = en.in_m;
-        while (m) {
-            const int t = __ffs(m) - 1;
-            m &= m - 1;
-            if (pc[t].steep) {
-                // grazing primitive: V is a small difference of large terms -> evaluate it in fp64, round the result
-                const double dA = pc[t].dvA, d0 = dA * c0 + (pc[t].dvB * r + pc[t].dvC);
-#pragma unroll
-                for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], (float)(dA * k + d0));
-                continue;
-            }
-            const float vA = pc[t].vA, v0 = fmaf(vA, fc0, fmaf(pc[t].vB, fr, pc[t].vC));
-#pragma unroll
-            for (int k = 0; k < 16; k++) vb[k] = fmaxf(vb[k], fmaf(vA, (float)k, v0));
-        }
-        if constexpr (decltype(with_part)::value) {
-            m = en.part_m;
-            while (m) {
-                const int t = __ffs(m) - 1;
-                m &= m - 1;
-                const PrimCoef& c = pc[t];
-                const float mg = c.margin, sc = c.margin / fmaxf(c.wmargin, 1e-30f); // w is compared on the edges' margin scale
-                const bool steep = c.steep;
-                float a0[5];
-#pragma unroll
-                for (int i = 0; i < 5; i++) a0[i] = fmaf(c.fA[i], fc0, fmaf(c.fB[i], fr, c.fC[i]));
-                const float vA = c.vA, v0 = fmaf(vA, fc0, fmaf(c.vB, fr, c.vC));
-                const double dA = c.dvA, d0 = steep ? dA * c0 + (c.dvB * r + c.dvC) : 0.0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const float fk = (float)k;
-                    const float lo = fminf(fminf(fmaf(c.fA[0], fk, a0[0]), fmaf(c.fA[1], fk, a0[1])),
-                                           fminf(fminf(fmaf(c.fA[2], fk, a0[2]), fmaf(c.fA[3], fk, a0[3])), fmaf(c.fA[4], fk, a0[4]) * sc));
-                    if (lo > mg) vb[k] = fmaxf(vb[k], steep ? (float)(dA * k + d0) : fmaf(vA, fk, v0));
-                    else if (lo >= -mg) unc |= 1u << k; // within the float margin of an edge
-                }
-                RSTAT(4, __popc(unc));
-            }
-        }
-        float nd[16];
-        {
-            const float4* p = reinterpret_cast<const float4*>(s_nodef + off);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float4 v = p[k];
-                nd[4 * k] = v.x; nd[4 * k + 1] = v.y; nd[4 * k + 2] = v.z; nd[4 * k + 3] = v.w;
-            }
-        }
-        const uint4 bres = *reinterpret_cast<const uint4*>(s_base + off);
-        uint32_t wds[4] = {bres.x, bres.y, bres.z, bres.w};
-        uint32_t nd_skin = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            // val = 5100 (nodef - d).  nodef - nd_ref is exact (Sterbenz); uncovered pixels have vb = -1e30 -> 0;
-            // border pixels (nd = -1) keep the baked byte
-            const bool skin = nd[k] >= 0.0f;
-            nd_skin |= (skin ? 1u : 0u) << k;
-            const float val = skin ? fmaf(nd[k] - a.nd_ref, VAL_SCALE, vb[k]) : -1e30f;
-            const uint32_t u = __float2uint_rz(fminf(fmaxf(val, 0.0f), 255.0f));
-            // quantisation step within the error bound?  (val in (-B, 255 + B) and |val - round(val)| < B)
-            if (fabsf(val - rintf(val)) < VAL_BOUND && val > -VAL_BOUND && val < 255.0f + VAL_BOUND) unc |= 1u << k;
-            wds[k >> 2] |= u << (8 * (k & 3));
-        }
-        *reinterpret_cast<uint4*>(obs_e + off) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-        if (en.pad) unc = 0xffffu; // near/far clipping in play in this tile: every pixel of the span takes the exact path
-        unc &= nd_skin;
-        RSTAT(5, __popc(unc)); RSTAT(6, __popc(unc) * __popc((uint32_t)(en.in_m | en.part_m))); RSTAT(7, 1);
-        RSTAT(8, __popc((uint32_t)en.part_m));
-        const uint32_t cand = ((uint32_t)(en.in_m | en.part_m)) << 16;
-        while (unc) {
-            const int k = __ffs(unc) - 1;
-            unc &= unc - 1;
-            s_queue[atomicAdd(s_qcnt, 1)] = cand | (uint32_t)(off + k);
-        }
+        shade_span<decltype(with_part)::value, uint32_t>(a, ctx, (int)en.off16 * 16, en.in_m, en.part_m, en.pad != 0, obs_e);
     };
-
-    // EXACT PATCH-UP of the queued pixels (whole warp)
-    auto flush_queue = [&](uint8_t* obs_e) {
-        __syncwarp();
-        const int qn = *s_qcnt;
-        for (int i = lane; i < qn; i += 32) {
-            const uint32_t q = s_queue[i];
-            const int off = (int)(q & 0xffffu);
-            obs_e[off] = (uint8_t)exact_pixel(a, pc, q >> 16, off & (S - 1), row0 + (off >> sh_S), s_nodef[off], s_base[off]);
-        }
-        __syncwarp();
-        if (lane == 0) *s_qcnt = 0;
-        __syncwarp();
-    };
+    auto flush_queue = [&](uint8_t* obs_e) { flush_exact<uint32_t>(a, ctx, obs_e, lane); };
 
     // one env image (band slice) per warp iteration
     for (int e = lane_cta * RASTER_WARPS + warp; e < a.n; e += n_cta * RASTER_WARPS) {

@@ -11,6 +11,7 @@
 
 #include "tg_env.cuh"
 #include "tg_raster.cuh"
+#include "tg_raster_hf.cuh"
 
 static thread_local std::string g_err;
 
@@ -83,7 +84,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->arm.topo == TG_TOPO_CHAIN6 && cfg->arm.nb != 6) return fail(TG_EINVAL, "CHAIN6 topology needs nb == 6");
     if (cfg->arm.topo == TG_TOPO_MG400 && cfg->arm.nb != 8) return fail(TG_EINVAL, "MG400 topology needs nb == 8");
     if (cfg->arm.topo != TG_TOPO_CHAIN6 && cfg->arm.topo != TG_TOPO_MG400) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
-    if (cfg->task.task != TG_TASK_EDGE_FOLLOW && cfg->task.task != TG_TASK_OBJECT_BALANCE) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+    if (cfg->task.task != TG_TASK_EDGE_FOLLOW && cfg->task.task != TG_TASK_OBJECT_BALANCE && cfg->task.task != TG_TASK_SURFACE_FOLLOW) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
     if (cfg->task.task == TG_TASK_OBJECT_BALANCE && !(cfg->task.obj_mass > 0 && cfg->task.obj_inertia[0] > 0 && cfg->task.obj_inertia[1] > 0 && cfg->task.obj_inertia[2] > 0))
         return fail(TG_EINVAL, "object_balance needs a free object with positive mass and inertia");
     if (cfg->task.n_draws < 0 || cfg->task.n_draws > TG_MAXDRAW) return fail(TG_EINVAL, "n_draws must be in 0..%d", TG_MAXDRAW);
@@ -127,7 +128,8 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     b.draws = nullptr; b.draw_rounds = 0;
     // standby reset pipeline (tg_env.cuh): needs episodes of at least 2 steps
     b.pipeline = cfg->task.max_steps >= 2 ? 1 : 0;
-    b.ik_chunk = IK_CHUNK; b.reset_chunk = RESET_CHUNK;
+    b.ik_chunk = IK_CHUNK; b.reset_chunk = RESET_CHUNK; b.surf_chunk = SURF_CHUNK;
+    if (const char* ev = getenv("TG_SURF_CHUNK")) b.surf_chunk = std::max(1, atoi(ev));
     if (const char* ev = getenv("TG_IK_CHUNK")) b.ik_chunk = std::max(1, atoi(ev));       // tuning hooks
     if (const char* ev = getenv("TG_RESET_CHUNK")) b.reset_chunk = std::max(1, atoi(ev));
     b.step_blocks = (n + 4 * lanes - 1) / (4 * lanes);
@@ -141,6 +143,15 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         return rc;
     }
     w->standby_blocks = b.pipeline ? std::max(8, std::min(64, w->sm_count / 2)) : 0;
+    if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
+        if (!b.pipeline) { tg_destroy(w); return fail(TG_EINVAL, "surface_follow needs max_steps >= 2"); }
+        if ((rc = dalloc(w, &b.height, (size_t)2 * SURF_PTS * n)) || (rc = dalloc(w, &b.hf_meta, (size_t)2 * SURF_META * n)) ||
+            (rc = dalloc(w, &b.hf_cur, n)) || (rc = dalloc(w, &b.sb_perm, (size_t)256 * n)) || (rc = dalloc(w, &b.sb_surf_it, n)) ||
+            (rc = dalloc(w, &b.sb_hmm, (size_t)2 * n))) {
+            tg_destroy(w);
+            return rc;
+        }
+    }
     if (cfg->task.task == TG_TASK_OBJECT_BALANCE) {
         if ((rc = dalloc(w, &b.obj, (size_t)13 * n)) || (rc = dalloc(w, &b.obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.grav, n)) ||
             (rc = dalloc(w, &b.sb_obj, (size_t)13 * n)) || (rc = dalloc(w, &b.sb_obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.sb_grav, n))) {
@@ -163,11 +174,13 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         const int np = cfg->sensor.n_prim;
         for (int i = 0; i < np; i++)
             if (cfg->sensor.h_prim_nv[i] != 3 && cfg->sensor.h_prim_nv[i] != 4) { tg_destroy(w); return fail(TG_EINVAL, "primitive %d has %d vertices", i, cfg->sensor.h_prim_nv[i]); }
-        if ((rc = dalloc(w, &dn, px)) || (rc = dalloc(w, &db, px)) || (rc = dalloc(w, &dt, (size_t)np * 12)) || (rc = dalloc(w, &dnv, np))) { tg_destroy(w); return rc; }
+        if ((rc = dalloc(w, &dn, px)) || (rc = dalloc(w, &db, px)) || (rc = dalloc(w, &dt, (size_t)std::max(np, 1) * 12)) || (rc = dalloc(w, &dnv, std::max(np, 1)))) { tg_destroy(w); return rc; }
         CK(cudaMemcpy(dn, nd.data(), px * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(db, base.data(), px, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dt, cfg->sensor.h_prims, sizeof(double) * 12 * np, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dnv, cfg->sensor.h_prim_nv, sizeof(int) * np, cudaMemcpyHostToDevice));
+        if (np > 0) {
+            CK(cudaMemcpy(dt, cfg->sensor.h_prims, sizeof(double) * 12 * np, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(dnv, cfg->sensor.h_prim_nv, sizeof(int) * np, cudaMemcpyHostToDevice));
+        }
         float ndmin = 1e30f, ndmax = -1e30f;
         for (size_t i = 0; i < px; i++) if (nd[i] >= 0.0f) { ndmin = std::min(ndmin, nd[i]); ndmax = std::max(ndmax, nd[i]); }
         RasterArgs& r = w->ra;
@@ -189,6 +202,26 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         const int need = ((n + RASTER_WARPS - 1) / RASTER_WARPS) * r.bands;
         if (grid > need) grid = need;
         w->raster_grid = grid;
+        r.hf = nullptr; r.hf_cur = nullptr; r.hf_meta = nullptr; r.hf_flip = 0; r.hf_tile_rows = 16; r.hf_tile_cols = 32;
+        if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
+            // heightfield stimulus: per-tile primitive lists (tg_raster_hf.cuh).  Tile size: its footprint on the surface
+            // (at the deepest skin depth) should stay within ~1.5 grid cells so that a tile sees <= 32 triangles
+            r.hf = b.height; r.hf_cur = b.hf_cur; r.hf_meta = b.hf_meta;
+            for (int c = 0; c < 3; c++) r.surf_pos[c] = cfg->task.surf_pos[c];
+            r.surf_grid = cfg->task.surf_grid;
+            const double zmax = r.near_ * r.F / (r.F - (double)ndmax), pix = 2.0 * zmax * r.th / S, lim = 1.5 * r.surf_grid;
+            r.hf_tile_cols = 32 * pix <= lim ? 32 : 16;
+            r.hf_tile_rows = 16 * pix <= lim ? 16 : (8 * pix <= lim ? 8 : 4);
+            w->raster_smem = ((band_px * 5 + 15) & ~size_t(15)) + HF_PER_WARP_SMEM * HF_WARPS;
+            CK(cudaFuncSetAttribute(raster_hf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->raster_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_hf_kernel, HF_THREADS, w->raster_smem));
+            if (per_sm < 1) { tg_destroy(w); return fail(TG_ECUDA, "heightfield raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
+            grid = w->sm_count * per_sm;
+            grid -= grid % r.bands;
+            const int need_hf = ((n + HF_WARPS - 1) / HF_WARPS) * r.bands;
+            if (grid > need_hf) grid = need_hf;
+            w->raster_grid = grid;
+        }
     }
     *out = w;
     return TG_OK;
@@ -264,8 +297,9 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
 {
     RasterArgs r = w->ra;
     r.obs = d_obs; r.mask = mask;
-    if (terminal_state) { r.cam = w->eb.term_cam; r.stim = w->eb.term_stim; }
-    raster_kernel<<<w->raster_grid, RASTER_THREADS, w->raster_smem, st>>>(r);
+    if (terminal_state) { r.cam = w->eb.term_cam; r.stim = w->eb.term_stim; r.hf_flip = 1; }
+    if (r.hf) raster_hf_kernel<<<w->raster_grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
+    else raster_kernel<<<w->raster_grid, RASTER_THREADS, w->raster_smem, st>>>(r);
     w->launches++;
     CK(cudaGetLastError());
     return TG_OK;

@@ -217,6 +217,79 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     return cfg, (dep, gray, mask, tris, rest, prims, prim_nv), draw
 
 
+def surface_follow_draws():
+    """BaseSurfaceEnv.reset_task draws (base_surface_env.py:539-547): update_surface's `np_random.randint(1e8)` (the
+    OpenSimplex seed, :448) then make_goal's `uniform(-pi, pi)` (:508).  randint's rejection sampling consumes a
+    variable number of raw outputs, so the legacy RandomState calls themselves are used."""
+
+    def draw(rng, rounds):
+        out = np.empty((rounds, 2))
+        for r in range(rounds):
+            out[r, 0] = rng.randint(1e8)
+            out[r, 1] = rng.uniform(-np.pi, np.pi)
+        return out
+
+    return draw
+
+
+def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
+    """SurfaceFollowAutoEnv / BaseSurfaceEnv.__init__ (rl_envs/exploration/surface_follow/base_surface_env.py:14-150,
+    surface_follow_auto/surface_follow_auto_env.py) as a TgConfig.  Returns (cfg, keepalive, draw_fn)."""
+    arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
+    if env_modes.get("noise_mode", "simplex") != "simplex":
+        raise NotImplementedError("noise_mode %r: only 'simplex' is built" % env_modes.get("noise_mode"))
+    if env_modes["movement_mode"] not in ("xyz", "xyzRxRy"):
+        raise NotImplementedError("movement_mode %r: only 'xyz' and 'xyzRxRy' (2-d simplex surfaces) are built" % env_modes["movement_mode"])
+    if env_modes["control_mode"] != "TCP_velocity_control":
+        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
+    typ, S = "standard", int(image_size[0])
+    mj = scene.load_model_json(arm_type, sensor, typ)
+    sj = scene.load_sensor_json(sensor, typ)
+    cam = sj["types"][typ]
+    arm, control_links = scene.reduce_model(mj, sensor, cam["cam_pos"], cam["cam_rpy"])
+    cfg = L.TgConfig()
+    cfg.n_envs, cfg.lanes_per_warp, cfg.arm = n_envs, lanes_per_warp, arm
+    cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 10.0) / (1.0 / 240.0))))      # :26-28 -> 24
+    t = cfg.task
+    t.task, t.max_steps = L.TG_TASK_SURFACE_FOLLOW, int(max_steps)
+    idx = {"xyz": [2], "xyzRxRy": [2, 3, 4]}[env_modes["movement_mode"]]                          # surface_follow_auto_env.py:45-55
+    t.act_dim = len(idx)
+    for k in range(6):
+        t.act_index[k] = idx[k] if k < len(idx) else -1
+    t.act_min, t.act_max = -0.25, 0.25
+    mv, ma = 0.01, 5.0 * (np.pi / 180)                                                          # :197-206
+    hi = [mv, mv, mv, ma, ma, 0.0]
+    for k in range(6):
+        t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
+    wd = [0.33, 0.0, 0.0] if arm_type in ("mg400", "magician") else [0.65, 0.0, 0.0]              # :54-57
+    hrange, extent = 0.025, 0.15                                                                 # :240-246
+    wf_pos, wf_rpy = [wd[0], wd[1], hrange], [-np.pi, 0.0, np.pi / 2]                             # :111-114
+    lims = [(-extent, extent), (-extent, extent), (-hrange, hrange), (-np.pi / 4, np.pi / 4), (-np.pi / 4, np.pi / 4), (0.0, 0.0)]
+    for k in range(3):
+        t.workframe_pos[k], t.workframe_rpy[k], t.init_rpy[k] = wf_pos[k], wf_rpy[k], 0.0
+        t.surf_pos[k] = [wd[0], wd[1], hrange][k]                                                # :261
+    for k in range(6):
+        t.tcp_lims[k][0], t.tcp_lims[k][1] = lims[k]
+    t.termination_dist = 0.01                                                                    # :78
+    t.surf_grid, t.surf_range, t.surf_interp, t.surf_extent = 0.006, hrange, 0.05, extent
+    t.surf_embed = {"tactip": 0.0025, "digitac": 0.0015, "digit": 0.0015}[sensor]                 # :67-75
+    t.surf_drive = 0.25 * {"tactip": 1.0, "digitac": 0.9, "digit": 0.7}[sensor]                   # surface_follow_auto_env.py:35-43
+    t.surf_w_norm = 0.0 if env_modes["movement_mode"] == "xyz" else 1.0                           # :88-89
+    t.n_draws = 2
+    t.draw_default[0], t.draw_default[1] = 0.0, 0.0
+    dep, gray, mask = scene.load_refimg(sensor, typ, S)
+    rest = scene.load_rest_pose("surface_follow", arm_type, sensor, typ, control_links)
+    s = cfg.sensor
+    s.image_size, s.border_on = S, 1                                                             # turn_off_border=False :137
+    s.fov_deg, s.near_, s.far_ = sj["fov"], sj["near"], sj["far"]
+    s.h_nodef_dep = dep.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_nodef_gray = gray.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+    s.n_prim = 0                                                                                 # the stimulus is the per-env heightfield
+    cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
+    return cfg, (dep, gray, mask, rest), surface_follow_draws()
+
+
 class TactileWorld:
     """N envs of one task on one device."""
 

@@ -11,14 +11,15 @@ import time
 import numpy as np
 
 from . import spaces
-from .engine import TactileWorld, edge_follow_config, object_balance_config
+from .engine import TactileWorld, edge_follow_config, object_balance_config, surface_follow_config
 
 try:  # pragma: no cover
     from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
 except Exception:  # noqa: BLE001
     _VecEnvBase = object
 
-CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": object_balance_config}
+CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": object_balance_config,
+                   "surface_follow-v0": surface_follow_config}
 
 
 class TactileVecEnv(_VecEnvBase):

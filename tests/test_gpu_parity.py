@@ -436,3 +436,83 @@ def test_object_balance_matches_oracle(oracle, S, movement):
     assert ever_done.any()                # with no control for 25 steps some poles fall past 35 degrees
     assert not env.world.pipeline_error()
     env.close()
+
+
+SURFACE_MODES = {"movement_mode": "xyzRxRy", "control_mode": "TCP_velocity_control", "noise_mode": "simplex",
+                 "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "digit"}
+
+
+@pytest.mark.parametrize("sensor,S,movement", [("digit", 128, "xyzRxRy"), ("tactip", 128, "xyz"), ("tactip", 64, "xyzRxRy"), ("digitac", 256, "xyzRxRy")])
+def test_surface_follow_matches_oracle(oracle, sensor, S, movement):
+    """surface_follow-v0 (BASELINE config 3 = digit, 128): per-env OpenSimplex heightfield generated on the device,
+    heightfield raster with per-tile primitive lists, constant drive towards the goal, surface-distance + normal reward;
+    each step compared from an identical state.  (digitac 256 is one of the reference's stale fixtures: the garbage is
+    reproduced on both sides)"""
+    import tactile_gym_b200 as tg
+
+    modes = dict(SURFACE_MODES, movement_mode=movement, tactile_sensor_name=sensor)
+    n = 5
+    env = tg.make_vec("surface_follow-v0", n, env_kwargs={"env_modes": modes, "image_size": [S, S], "max_steps": 200})
+    rng = np.random.RandomState(S + len(sensor))
+    draws = np.stack([rng.randint(0, 10 ** 8, (n, 2)).astype(np.float64), rng.uniform(-np.pi, np.pi, (n, 2))], axis=2)
+    env.world.set_draws(draws)
+    obs = env.reset()["tactile"]
+    st = env.world.get_state()
+    refs = []
+    for i in range(n):
+        r = oracle.SurfaceFollowOracle(image_size=S, sensor=sensor, movement_mode=movement)
+        r.reset(draws=(draws[i, 0, 0], draws[i, 0, 1]))
+        refs.append(r)
+        assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=2e-6), i
+        assert st[i, 22] == r.last_reset_substeps
+        _sync_oracle(r, st[i])
+        mx, frac = _img_close(r.observation(), obs[i])
+        assert mx <= 1 and frac < 1e-3, (i, mx, frac)
+    act_dim = env.world.act_dim
+    touched = 0
+    for k in range(30):
+        act = rng.uniform(-0.25, 0.25, (n, act_dim)).astype(np.float32)
+        act[:, 0] = 0.25 if k < 12 else act[:, 0]          # push down (workframe z = world -z) so the skin meets the surface
+        o2, rew, done, infos = env.step(act)
+        st = env.world.get_state()
+        for i, r in enumerate(refs):
+            o, rr, dd, _ = r.step(act[i])
+            tol = 5e-6 if k == 0 else 1e-9
+            assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=tol), (k, i)
+            assert not dd and not done[i]
+            _sync_oracle(r, st[i])
+            rr, _ = r.step_data()
+            assert abs(rr - rew[i]) < 1e-6 * max(1.0, abs(rr)), (k, i, rr, rew[i])
+            img = r.observation()
+            mx, frac = _img_close(img, o2["tactile"][i])
+            assert mx <= 1 and frac < 1e-3, (k, i, mx, frac)
+            touched += int((img[..., 0][r.ref[2] == 0] > 0).sum() > 50)
+    assert touched > 10                                       # the comparison is not vacuous: the surface shows in the images
+    assert not env.world.pipeline_error()
+    env.close()
+
+
+def test_surface_follow_episode_turnover(oracle):
+    """short episodes: the next heightfield is built in the other buffer while the live one is rendered, then swapped"""
+    import tactile_gym_b200 as tg
+
+    n, S, L = 4, 64, 150
+    env = tg.make_vec("surface_follow-v0", n, env_kwargs={"env_modes": SURFACE_MODES, "image_size": [S, S], "max_steps": L})
+    rng = np.random.RandomState(9)
+    draws = np.stack([rng.randint(0, 10 ** 8, (n, 3)).astype(np.float64), rng.uniform(-np.pi, np.pi, (n, 3))], axis=2)
+    env.world.set_draws(draws)
+    env.reset()
+    act = np.zeros((n, 3), dtype=np.float32); act[:, 0] = 0.1
+    for k in range(L):
+        obs, rew, done, infos = env.step(act)
+    assert done.all()
+    st = env.world.get_state()
+    for i in range(n):
+        r = oracle.SurfaceFollowOracle(image_size=S, sensor="digit")
+        o = r.reset(draws=(draws[i, 1, 0], draws[i, 1, 1]))
+        assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=2e-6)
+        _sync_oracle(r, st[i])
+        assert _img_close(r.observation(), obs["tactile"][i])[0] <= 1
+        assert infos[i]["terminal_observation"]["tactile"].shape == (S, S, 1)
+    assert env.world.pipeline_stalls() == 0
+    env.close()

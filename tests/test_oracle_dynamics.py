@@ -53,3 +53,26 @@ def test_gym_seeding_is_deterministic(oracle):
     b = oracle.gym_np_random(7).uniform(size=3)
     c = oracle.gym_np_random(8).uniform(size=3)
     assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+def test_opensimplex_known_answer_and_surface_env(oracle):
+    """OpenSimplex restatement: the opensimplex package README's known answer (seed 1234: noise2(10, 10) =
+    0.580279369186297), permutation validity, and the surface_follow oracle env's basic invariants."""
+    import ctypes as C
+
+    lib = oracle.lib()
+    lib.or_opensimplex_noise2.restype = C.c_double
+    perm = (C.c_short * 256)()
+    lib.or_opensimplex_init(C.c_longlong(1234), perm)
+    assert sorted(perm) == list(range(256))
+    assert lib.or_opensimplex_noise2(perm, C.c_double(10.0), C.c_double(10.0)) == 0.580279369186297
+    h = oracle.surface_heights(1234)
+    assert h.shape == (64, 64) and np.abs(h).max() <= 0.025 and np.abs(np.diff(h, axis=0)).max() < 0.004   # coherent noise
+    e = oracle.SurfaceFollowOracle(image_size=64, sensor="digit", seed=5)
+    e.reset()
+    p, _ = e.tcp_world()
+    target_z = e.surface_pos[2] + e.h[32, 32] - e.embed_dist
+    assert abs(p[2] - target_z) < 3e-4 and abs(p[0] - 0.65) < 2e-4 and abs(p[1]) < 2e-4      # update_init_pose reached
+    assert abs(np.linalg.norm(e.goal_pos[:2] - e.surface_pos[:2]) - 0.15) < 1e-12
+    _, r, d, _ = e.step(np.array([0.25, 0.0, 0.0]))
+    assert r < 0 and not d
