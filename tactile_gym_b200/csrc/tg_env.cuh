@@ -399,7 +399,7 @@ __device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, 
         meta[0] = 0.5 * ((double)r.hmin + (double)r.hmax);
         meta[1] = dirs[0]; meta[2] = dirs[1];
         meta[3] = gx; meta[4] = gy; meta[5] = H[gi * SURF_N + gj] + task.surf_pos[2];
-        meta[6] = 0.0; meta[7] = 0.0;
+        meta[6] = (double)r.hmin; meta[7] = (double)r.hmax; // float32 height range (the raster's first slab bound)
 #pragma unroll
         for (int i = 0; i < 12; i++) out.stim[i] = 0.0;
     } else if (!balance) {

@@ -77,6 +77,7 @@ raster_hf_kernel(const RasterArgs a, int* __restrict__ error_flag)
         const int buf = a.hf_cur[e] ^ (a.hf_flip ? 1 : 0);
         const double* H = a.hf + ((size_t)e * 2 + (size_t)buf) * SURF_PTS;
         const double zc = a.hf_meta[((size_t)e * 2 + (size_t)buf) * SURF_META];
+        const double hmax_env = a.hf_meta[((size_t)e * 2 + (size_t)buf) * SURF_META + 7];
         uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
 
         // one rectangular pixel region (band-local rows): false = it needs more than HF_MAXPRIM triangles
@@ -94,29 +95,53 @@ raster_hf_kernel(const RasterArgs a, int* __restrict__ error_flag)
             if (__ballot_sync(0xffffffffu, skin) == 0u) return true; // border only
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-            // ---- 1. cells under the region's rays between the near plane and the deepest skin depth
-            double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-            if (lane < 8) {
-                const double z = (lane & 4) ? a.near_ * a.F / (a.F - (double)dmax) * (1.0 + 1e-6) : a.near_;
-                const double c = (lane & 1) ? (double)(cl0 + ncols) - 0.5 : (double)cl0 - 0.5;
-                const double r = (lane & 2) ? (double)(row0 + rl0 + nrows) - 0.5 : (double)(row0 + rl0) - 0.5;
-                const double ex = (kx * c + x0) * z, ey = (y0 - kx * r) * z;
-                xmin = xmax = cam[0] + cam[9] * ex + cam[6] * ey + cam[3] * z;
-                ymin = ymax = cam[1] + cam[10] * ex + cam[7] * ey + cam[4] * z;
-            }
+            // ---- 1. cells under the region's rays.  Only the ray segments below the terrain's top and in front of the
+            // deepest skin depth can meet visible terrain; the top starts as the env's highest point and is then
+            // tightened to the highest vertex of the cells found so far (sound: above that height, inside those cells,
+            // there is nothing to hit), which shrinks the segment - and the cell range - to the local relief.
+            const double zmax = a.near_ * a.F / (a.F - (double)dmax) * (1.0 + 1e-6);
+            const double cc = (lane & 1) ? (double)(cl0 + ncols) - 0.5 : (double)cl0 - 0.5;
+            const double rr = (lane & 2) ? (double)(row0 + rl0 + nrows) - 0.5 : (double)(row0 + rl0) - 0.5;
+            const double rdx = kx * cc + x0, rdy = y0 - kx * rr;
+            const double gz = cam[11] * rdx + cam[8] * rdy + cam[5]; // world-z change per unit eye depth along this corner ray
+            double zt = a.surf_pos[2] + hmax_env - zc + 1e-7;
+            int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+#pragma unroll 1
+            for (int it = 0; it < 4; it++) {
+                // eye depth from which the corner ray is below world height zt (looking up / already below: from the near plane)
+                double zlo = gz < 0.0 ? fmax((zt - cam[2]) / gz, a.near_) : a.near_;
+                zlo = fmin(zlo, __shfl_xor_sync(0xffffffffu, zlo, 1));
+                zlo = fmin(zlo, __shfl_xor_sync(0xffffffffu, zlo, 2));
+                zlo = __shfl_sync(0xffffffffu, zlo, 0) * (1.0 - 1e-9);
+                if (zlo > zmax) return true; // the terrain stays behind the skin everywhere in this region
+                const double z = (lane & 4) ? zmax : zlo;
+                const double ex = rdx * z, ey = rdy * z;
+                double xmin = cam[0] + cam[9] * ex + cam[6] * ey + cam[3] * z, xmax = xmin;
+                double ymin = cam[1] + cam[10] * ex + cam[7] * ey + cam[4] * z, ymax = ymin;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-                ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+                for (int o = 4; o > 0; o >>= 1) {
+                    xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+                    ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+                }
+                xmin = __shfl_sync(0xffffffffu, xmin, 0); xmax = __shfl_sync(0xffffffffu, xmax, 0);
+                ymin = __shfl_sync(0xffffffffu, ymin, 0); ymax = __shfl_sync(0xffffffffu, ymax, 0);
+                // vertex j sits at x = surf_pos.x + float32((j - 31.5) grid): widen by 1e-6 cells for that rounding
+                const double fj0 = floor((xmin - a.surf_pos[0]) / a.surf_grid + half - 1e-6), fj1 = floor((xmax - a.surf_pos[0]) / a.surf_grid + half + 1e-6);
+                const double fi0 = floor((ymin - a.surf_pos[1]) / a.surf_grid + half - 1e-6), fi1 = floor((ymax - a.surf_pos[1]) / a.surf_grid + half + 1e-6);
+                if (fj1 < 0.0 || fi1 < 0.0 || fj0 > (double)(SURF_N - 2) || fi0 > (double)(SURF_N - 2)) return true; // off the grid
+                j0 = (int)fmax(fj0, 0.0); j1 = (int)fmin(fj1, (double)(SURF_N - 2));
+                i0 = (int)fmax(fi0, 0.0); i1 = (int)fmin(fi1, (double)(SURF_N - 2));
+                if (2 * (j1 - j0 + 1) * (i1 - i0 + 1) <= HF_MAXPRIM / 2 || it == 3) break;
+                // highest vertex of these cells -> tighter top
+                const int nvj = j1 - j0 + 2, nvert = nvj * (i1 - i0 + 2);
+                float hm = -3.0e38f;
+                for (int v = lane; v < nvert; v += 32) hm = fmaxf(hm, (float)H[(i0 + v / nvj) * SURF_N + j0 + v % nvj]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) hm = fmaxf(hm, __shfl_xor_sync(0xffffffffu, hm, o));
+                const double zt_new = a.surf_pos[2] + (double)hm - zc + 1e-7;
+                if (!(zt_new < zt)) break;
+                zt = zt_new;
             }
-            xmin = __shfl_sync(0xffffffffu, xmin, 0); xmax = __shfl_sync(0xffffffffu, xmax, 0);
-            ymin = __shfl_sync(0xffffffffu, ymin, 0); ymax = __shfl_sync(0xffffffffu, ymax, 0);
-            // vertex j sits at x = surf_pos.x + float32((j - 31.5) grid): widen by 1e-6 cells for that rounding
-            const double fj0 = floor((xmin - a.surf_pos[0]) / a.surf_grid + half - 1e-6), fj1 = floor((xmax - a.surf_pos[0]) / a.surf_grid + half + 1e-6);
-            const double fi0 = floor((ymin - a.surf_pos[1]) / a.surf_grid + half - 1e-6), fi1 = floor((ymax - a.surf_pos[1]) / a.surf_grid + half + 1e-6);
-            if (fj1 < 0.0 || fi1 < 0.0 || fj0 > (double)(SURF_N - 2) || fi0 > (double)(SURF_N - 2)) return true; // off the grid
-            const int j0 = (int)fmax(fj0, 0.0), j1 = (int)fmin(fj1, (double)(SURF_N - 2));
-            const int i0 = (int)fmax(fi0, 0.0), i1 = (int)fmin(fi1, (double)(SURF_N - 2));
             const int ncj = j1 - j0 + 1, nprim = 2 * ncj * (i1 - i0 + 1);
             if (nprim > HF_MAXPRIM) return false;
             // ---- 2. lane = triangle

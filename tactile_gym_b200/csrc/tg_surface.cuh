@@ -15,7 +15,7 @@
 
 #define SURF_N TG_SURF_N
 #define SURF_PTS (SURF_N * SURF_N)
-#define SURF_META 8 // per episode: zc, dir x, dir y, goal x y z, (2 spare)
+#define SURF_META 8 // per episode: zc, dir x, dir y, goal x y z, float32 height min, max
 
 // permutation table of OpenSimplex(seed): LCG shuffle (int64 wrap-around; Python's floor modulo)
 TGD void os_perm(long long seed_in, unsigned char* perm /* [256], global */)

@@ -88,8 +88,11 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->task.task == TG_TASK_OBJECT_BALANCE && !(cfg->task.obj_mass > 0 && cfg->task.obj_inertia[0] > 0 && cfg->task.obj_inertia[1] > 0 && cfg->task.obj_inertia[2] > 0))
         return fail(TG_EINVAL, "object_balance needs a free object with positive mass and inertia");
     if (cfg->task.n_draws < 0 || cfg->task.n_draws > TG_MAXDRAW) return fail(TG_EINVAL, "n_draws must be in 0..%d", TG_MAXDRAW);
-    if (cfg->sensor.n_prim <= 0 || cfg->sensor.n_prim > RASTER_MAXPRIM) return fail(TG_EINVAL, "n_prim must be in 1..%d", RASTER_MAXPRIM);
-    if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->sensor.h_prims || !cfg->sensor.h_prim_nv || !cfg->h_rest_q)
+    if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
+        if (cfg->sensor.n_prim != 0) return fail(TG_EINVAL, "surface_follow draws the per-env heightfield: n_prim must be 0");
+    } else if (cfg->sensor.n_prim <= 0 || cfg->sensor.n_prim > RASTER_MAXPRIM) return fail(TG_EINVAL, "n_prim must be in 1..%d", RASTER_MAXPRIM);
+    if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->h_rest_q ||
+        (cfg->sensor.n_prim > 0 && (!cfg->sensor.h_prims || !cfg->sensor.h_prim_nv)))
         return fail(TG_EINVAL, "null table pointer in config");
     CK(cudaSetDevice(device));
 
