@@ -61,7 +61,16 @@ extern "C" {
 #define TG_TASK_EDGE_FOLLOW 0
 #define TG_TASK_OBJECT_BALANCE 1
 #define TG_TASK_SURFACE_FOLLOW 2
+#define TG_TASK_OBJECT_PUSH 3
 #define TG_SURF_N 64 /* heightfield rows = columns */
+#define TG_PUSH_NTRAJ 10 /* object_push: goals along the trajectory (object_push_env.py:233) */
+#define TG_PUSH_NFEAT 12 /* object_push: extended_feature length (object_push_env.py:611-629) */
+
+/* object_push action encodings (object_push_env.py:369-454) */
+#define TG_PUSH_WORK 0       /* xyRz: plain scatter of the policy action                                  */
+#define TG_PUSH_WORK_DRIVE 1 /* y, yRz: x slot driven with max_action                                     */
+#define TG_PUSH_TCP_TYRZ 2   /* TyRz: drive along the tip axis, action[0] across it, both in the TCP frame */
+#define TG_PUSH_TCP_TXTYRZ 3 /* TxTyRz                                                                    */
 
 /* Reduced arm model: fixed joints are merged into their moving parent at asset-compile time
  * (tactile_gym_b200/scene.py); `sub_*` keeps the original mass-carrying links for bullet's per-link
@@ -129,6 +138,19 @@ typedef struct {
     double surf_embed;               /* embed_dist: 0.0025 tactip, 0.0015 digit / digitac */
     double surf_drive;               /* constant drive along the goal direction: max_action x {1, 0.9, 0.7} */
     double surf_w_norm;              /* weight of the normal-alignment term (0 for yz / xyz movement) */
+    /* object_push (object_push_env.py, base_object_env.py): a free cube on the table pushed by the tip core; contact rows
+     * tip hull <-> cube and cube <-> table.  draws per reset: init_obj_ang, obj_mass, OpenSimplex seed | trajectory angle */
+    int32_t push_mode, push_traj_straight, push_sparse_reward, push_pad;
+    double push_half[3];             /* cube half extents (cube.urdf) */
+    double push_table_z;             /* table top (base_tactile_env.py:135-139 + table.urdf) */
+    double push_mu_table, push_mu_tip; /* products of the lateralFriction pairs (object_push_env.py:218, :61-66, table.urdf) */
+    double push_tip_k, push_tip_d;   /* combined contactStiffness / contactDamping of the tip <-> cube pair */
+    double push_erp, push_slop;      /* 0.2 [EXT]; contactBreakingThreshold 1e-4 (base_tactile_env.py:129) */
+    double push_lin_damping, push_ang_damping; /* cube: btMultiBody defaults 0.04 [EXT] */
+    double push_init_pos[3];         /* init_obj_pos (:193) */
+    double push_inertia_per_mass[3]; /* box inertia / mass: changeDynamics(mass=) keeps the shape's inertia [EXT] */
+    double push_term_dist;           /* 0.025 (:68) */
+    double push_traj_spacing, push_traj_perturb, push_traj_offset; /* 0.025, 0.1, obj_width / 2 + spacing (:233-235, :290) */
 } TgTask;
 
 typedef struct {
@@ -152,6 +174,10 @@ typedef struct {
     TgTask task;
     TgSensor sensor;
     const double* h_rest_q; /* [nb] */
+    /* contact envs: vertices of the tip core's convex hull, in the frame of arm.tcp_body (the body that carries the
+     * sensor); NULL / 0 otherwise */
+    const double* h_tip_hull; /* [n_tip_hull][3] */
+    int32_t n_tip_hull, pad1;
 } TgConfig;
 
 typedef struct TgWorld TgWorld;
@@ -185,13 +211,20 @@ int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream);
 int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float* d_reward, uint8_t* d_done,
             uint8_t* d_term_obs, void* stream);
 
+/* object_push, observation_mode "tactile_and_feature": bind caller-owned device buffers [N][TG_PUSH_NFEAT] f32 that every
+ * following tg_step / tg_reset / tg_physics_only fills with the extended_feature (object_push_env.py:611-629: TCP pos(3) +
+ * rpy(3) in the work frame, goal pos(3) + rpy(3) in the work frame).  d_term_feat (may be NULL) receives the features of the
+ * state a finished env terminated in.  NULL d_feat unbinds. */
+int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat);
+
 /* kernel-level entry points (tests, ncu) */
 int tg_physics_only(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, void* stream);
 int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream);
 int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream);
 
 /* state access (parity tests, checkpointing).  Layout: per env doubles
- * [q(nb) qd(nb) tcp_pos(3) tcp_quat(4) embed edge_ang steps reset_substeps | obj pos(3) quat(4) vel(3) omg(3) gravity_z] */
+ * [q(nb) qd(nb) tcp_pos(3) tcp_quat(4) embed edge_ang steps reset_substeps | obj pos(3) quat(4) vel(3) omg(3) scalar | goal]
+ * scalar = the episode's gravity_z (object_balance) or cube mass (object_push); goal = object_push's trajectory index */
 int tg_state_size(const TgWorld* w); /* doubles per env */
 int tg_get_state(TgWorld* w, double* h_state, void* stream);
 int tg_set_state(TgWorld* w, const double* h_state, void* stream);

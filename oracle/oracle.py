@@ -628,3 +628,219 @@ class SurfaceFollowOracle:
         lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
         self.reward, self.done = self.step_data()
         return self.observation(), self.reward, self.done, {}
+
+
+# ---------------------------------------------------------------- object_push task restatement
+OR_MAXC = 8
+
+
+class OrPush(C.Structure):
+    _fields_ = [
+        ("half", C.c_double * 3), ("table_z", C.c_double), ("mu_table", C.c_double), ("mu_tip", C.c_double),
+        ("tip_k", C.c_double), ("tip_d", C.c_double), ("erp", C.c_double), ("slop", C.c_double),
+        ("lin_damping", C.c_double), ("ang_damping", C.c_double), ("tip_link", C.c_int), ("n_hull", C.c_int),
+        ("hull", C.POINTER(C.c_double)), ("n_contacts", C.c_int), ("n_iters", C.c_int),
+        ("normal_impulse", C.c_double * OR_MAXC), ("contact_pos", (C.c_double * 3) * OR_MAXC),
+    ]
+
+
+def opensimplex_noise2(seed_int, x, y):
+    perm = (C.c_short * 256)()
+    lib().or_opensimplex_init(C.c_longlong(int(seed_int)), perm)
+    lib().or_opensimplex_noise2.restype = C.c_double
+    return lib().or_opensimplex_noise2(perm, C.c_double(x), C.c_double(y))
+
+
+def push_draws(rng, rand_init_orn=False, rand_obj_mass=False, traj_type="simplex"):
+    """Random draws of one ObjectPushEnv.reset in the reference's order: reset_object (init_obj_ang, obj_mass;
+    object_push_env.py:204-229) then make_goal -> update_trajectory (OpenSimplex seed :289 / traj_ang :310)."""
+    ang = rng.uniform(-np.pi / 32, np.pi / 32) if rand_init_orn else 0.0
+    mass = rng.uniform(0.4, 0.8) if rand_obj_mass else 0.491
+    third = float(rng.randint(1e8)) if traj_type == "simplex" else rng.uniform(-np.pi / 8, np.pi / 8)
+    return np.array([ang, mass, third])
+
+
+class ObjectPushOracle:
+    """Restates ObjectPushEnv (rl_envs/nonprehensile_manipulation/object_push/object_push_env.py) + BaseObjectEnv
+    (base_object_env.py) on top of the C oracle.  One env instance.  As for object_balance, Robot.reset() is run without
+    the cube in the world (the reference repositions the arm with the previous episode's cube still lying around)."""
+
+    def __init__(self, image_size=128, arm="mg400", sensor="digitac", max_steps=1000, movement_mode="TyRz", traj_type="simplex",
+                 rand_init_orn=False, rand_obj_mass=False, reward_mode="dense", seed=None):
+        self.S, self.arm, self.sensor, self.max_steps = image_size, arm, sensor, max_steps
+        self.movement_mode, self.traj_type, self.reward_mode = movement_mode, traj_type, reward_mode
+        self.rand_init_orn, self.rand_obj_mass = rand_init_orn, rand_obj_mass
+        self.typ = "right_angle"
+        self.obj_w = self.obj_h = 0.08
+        lims = np.zeros((6, 2))
+        a45 = 45 * np.pi / 180
+        if arm == "mg400":   # object_push_env.py:72-88
+            if sensor == "tactip":
+                raise NotImplementedError("mg400 + tactip uses the mini_right_angle sensor, which is not compiled")
+            lims[0], lims[1], lims[5] = (0.0, 0.3), (-0.1, 0.08), (-a45, a45)
+            wd = np.array([0.25, -0.1, self.obj_h / 2])
+        else:                # :89-101
+            lims[0], lims[1], lims[5] = (0.0, 0.3), (-0.1, 0.1), (-a45, a45)
+            wd = np.array([0.55, -0.20, self.obj_h / 2])
+        self.workframe_pos, self.workframe_rpy = wd, np.array([-np.pi, 0.0, np.pi / 2])
+        self.m = load_model(arm, sensor, self.typ, self.workframe_pos, self.workframe_rpy, lims)
+        self.rest = rest_pose("object_push", arm, sensor, self.typ, self.m)
+        self.ref = load_refimg(sensor, self.typ, image_size)
+        self.tris_local = np.load(os.path.join(ASSETS, "stimuli", "cube.npz"))["tris"]
+        with open(os.path.join(ASSETS, "objects", "cube.json")) as f:
+            self.cube = json.load(f)
+        self.hull = np.ascontiguousarray(np.load(os.path.join(ASSETS, "models", "%s_%s_%s_meshes.npz" % (arm, self.typ, sensor)))["tip_core_hull"], dtype=np.float64)
+        self.init_obj_pos = np.array([wd[0], wd[1] + self.obj_w / 2, self.obj_h / 2])       # :193
+        self.s, self.o, self.p = OrState(), OrObject(), OrPush()
+        p = self.p
+        dyn = {"tactip": (50, 100, 10.0), "digitac": (300, 100, 10.0), "digit": (50, 200, 10.0)}[sensor]   # :61-66
+        cube_mu, table_mu = 0.065, 1.0                                                       # :218, table.urdf
+        for c in range(3):
+            p.half[c] = 0.04
+        p.table_z = 0.0
+        p.mu_table, p.mu_tip = cube_mu * table_mu, min(cube_mu * dyn[2], 10.0)
+        # [EXT] combined stiffness 1/(1/kA + 1/kB) with the cube at bullet's default 1e18; combined damping dA + dB, default 0.1
+        p.tip_k, p.tip_d = 1.0 / (1.0 / dyn[0] + 1.0 / 1e18), dyn[1] + 0.1
+        p.erp, p.slop = 0.2, 1e-4
+        p.lin_damping, p.ang_damping = 0.04, 0.04
+        p.tip_link = self.m._names.index(sensor + "_tip_link")
+        p.n_hull = len(self.hull)
+        p.hull = self.hull.ctypes.data_as(C.POINTER(C.c_double))
+        self.repeat = int(np.floor((1.0 / 10.0) / (1.0 / 240.0)))
+        self.termination_pos_dist = 0.025
+        self.traj_n, self.traj_spacing, self.traj_max_perturb = 10, 0.025, 0.1
+        self.np_random = gym_np_random(seed)
+        self.steps = 0
+        R = np.zeros(9); lib().or_mat_from_quat(_dptr(quat_from_euler(self.workframe_rpy)), _dptr(R)); self.Rw = R.reshape(3, 3)
+
+    def seed(self, seed):
+        self.np_random = gym_np_random(seed)
+
+    def work_to_world(self, pos, rpy):   # base_robot_arm.py:47-60
+        po, qo = np.zeros(3), np.zeros(4)
+        lib().or_mul_transforms(_dptr(np.ascontiguousarray(self.workframe_pos)), _dptr(quat_from_euler(self.workframe_rpy)),
+                                _dptr(np.ascontiguousarray(pos, dtype=np.float64)), _dptr(quat_from_euler(rpy)), _dptr(po), _dptr(qo))
+        return po, euler_from_quat(qo)
+
+    def update_trajectory(self, third):   # :255-320
+        n = self.traj_n
+        self.traj_pos_work = np.zeros((n, 3)); self.traj_rpy_work = np.zeros((n, 3))
+        init_offset = self.obj_w / 2 + self.traj_spacing
+        if self.traj_type == "simplex":
+            first = None
+            for i in range(n):
+                noise = opensimplex_noise2(int(third), i * 0.1, 1) * self.traj_max_perturb
+                if first is None:
+                    first = -noise
+                self.traj_pos_work[i] = [init_offset + i * self.traj_spacing, first + noise, 0.0]
+        else:
+            for i in range(n):
+                dist = i * self.traj_spacing
+                self.traj_pos_work[i] = [init_offset + dist * np.cos(third), dist * np.sin(third), 0.0]
+        self.traj_rpy_work[:, 2] = np.gradient(self.traj_pos_work[:, 1], self.traj_spacing)
+        self.traj_pos_world = np.zeros((n, 3)); self.traj_orn_world = np.zeros((n, 4))
+        for i in range(n):
+            pw, rw = self.work_to_world(self.traj_pos_work[i], self.traj_rpy_work[i])
+            self.traj_pos_world[i] = pw; self.traj_orn_world[i] = quat_from_euler(rw)
+
+    def update_goal(self):   # :335-367
+        self.targ += 1
+        if self.targ >= self.traj_n:
+            return False
+        self.goal_pos_world, self.goal_orn_world = self.traj_pos_world[self.targ], self.traj_orn_world[self.targ]
+        self.goal_pos_work, self.goal_rpy_work = self.traj_pos_work[self.targ], self.traj_rpy_work[self.targ]
+        return True
+
+    def reset(self, draws=None):
+        self.steps = 0
+        d = push_draws(self.np_random, self.rand_init_orn, self.rand_obj_mass, self.traj_type) if draws is None else np.asarray(draws, dtype=np.float64)
+        ang, mass, third = d
+        pos = np.zeros(3); rpy = np.zeros(3)
+        self.last_reset_substeps = lib().or_robot_reset(C.byref(self.m), C.byref(self.s), _dptr(self.rest), _dptr(pos), _dptr(rpy))
+        o = self.o
+        o.enabled = 1; o.mass = mass; o.p2p_enabled = 0; o.ext_pending = 0
+        q0 = quat_from_euler([-np.pi, 0.0, np.pi / 2 + ang])                              # :210
+        # [EXT] changeDynamics(mass=) recomputes the box inertia from the collision shape
+        for c in range(3):
+            o.inertia[c] = self.cube["inertia_diag"][c] * (mass / self.cube["mass"]); o.com_off[c] = 0.0
+            o.pos[c] = self.init_obj_pos[c]; o.vel[c] = 0; o.omg[c] = 0
+        for c in range(4):
+            o.quat[c] = q0[c]
+        self.update_trajectory(third)
+        self.targ = -1
+        self.update_goal()
+        self.reward, self.done = self.step_data()
+        return self.observation()
+
+    def tcp_world(self):
+        P, Q = link_states(self.m, np.array(self.s.q[: self.m.ndof]))
+        return P[self.m.tcp_link], Q[self.m.tcp_link]
+
+    def stimulus_world(self):
+        R = np.zeros(9); q = np.array(self.o.quat[:])
+        lib().or_mat_from_quat(_dptr(q), _dptr(R)); R = R.reshape(3, 3)
+        return self.tris_local @ R.T + np.array(self.o.pos[:])
+
+    def features(self):   # get_extended_feature_array :611-629
+        p, r = tcp_pose_workframe(self.m, np.array(self.s.q[: self.m.ndof]))
+        return np.concatenate([p, r, self.goal_pos_work, self.goal_rpy_work])
+
+    def observation(self):
+        q = np.array(self.s.q[: self.m.ndof])
+        return {"tactile": tactile_image(self.m, q, self.S, self.stimulus_world(), self.ref, border_on=True)[..., None],
+                "extended_feature": self.features()}
+
+    def step_data(self):   # get_step_data :456-569
+        tp, tq = self.tcp_world()
+        op, oq = np.array(self.o.pos[:]), np.array(self.o.quat[:])
+        pos_dist = np.linalg.norm(op - self.goal_pos_world)
+        if self.reward_mode == "sparse":
+            reward = 1.0 if pos_dist < self.termination_pos_dist else 0.0
+        else:
+            orn_dist = np.arccos(np.clip(2 * (np.inner(self.goal_orn_world, oq) ** 2) - 1, -1, 1))
+            Ro, Rt = np.zeros(9), np.zeros(9)
+            lib().or_mat_from_quat(_dptr(np.ascontiguousarray(oq)), _dptr(Ro)); lib().or_mat_from_quat(_dptr(np.ascontiguousarray(tq)), _dptr(Rt))
+            ov, tv = Ro.reshape(3, 3)[:, 0], Rt.reshape(3, 3)[:, 0]
+            cos_dist = 1 - np.dot(ov, tv) / (np.linalg.norm(ov) * np.linalg.norm(tv))
+            reward = -(pos_dist + orn_dist + cos_dist)
+        done = False
+        if pos_dist < self.termination_pos_dist:
+            if not self.update_goal():
+                done = True
+        if self.steps >= self.max_steps:
+            done = True
+        return reward, done
+
+    def encode_scale(self, action):   # encode_actions :369-454, scale_actions base_tactile_env.py:141-164
+        a = np.asarray(action, dtype=np.float64)
+        enc = np.zeros(6)
+        mm = self.movement_mode
+        if mm == "y":
+            enc[0], enc[1] = 0.25, a[0]
+        elif mm == "yRz":
+            enc[0], enc[1], enc[5] = 0.25, a[0], a[1]
+        elif mm == "xyRz":
+            enc[0], enc[1], enc[5] = a[0], a[1], a[2]
+        else:
+            _, tq = self.tcp_world()
+            Rt = np.zeros(9); lib().or_mat_from_quat(_dptr(np.ascontiguousarray(tq)), _dptr(Rt)); Rt = Rt.reshape(3, 3)
+            par = self.Rw.T @ (Rt @ np.array([1.0, 0.0, 0.0])); perp = self.Rw.T @ (Rt @ np.array([0.0, -1.0, 0.0]))
+            if mm == "TyRz":
+                pa, pe = par * 0.25, perp * a[0]
+                enc[0] += pe[0] + pa[0]; enc[1] += pe[1] + pa[1]; enc[5] += a[1]
+            else:   # TxTyRz
+                pa, pe = par * a[0], perp * a[1]
+                enc[0] += pe[0] + pa[0]; enc[1] += pe[1] + pa[1]; enc[5] += a[2]
+        enc = np.clip(enc, -0.25, 0.25)
+        mv, ma = 0.01, 5.0 * (np.pi / 180)
+        amax = np.array([mv, mv, 0.0, 0.0, 0.0, ma]); amin = -amax
+        return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
+
+    def step(self, action):
+        v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
+        self.steps += 1
+        lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
+        for _ in range(self.repeat):
+            lib().or_step_sim_push(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p))
+        self.reward, self.done = self.step_data()
+        return self.observation(), self.reward, self.done, {}

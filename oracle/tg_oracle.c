@@ -544,7 +544,7 @@ static void quat_rotate(const double q[4], const double v[3], double o[3]) { m3 
 void or_step_sim_obj(const OrModel* m, OrState* s, OrObject* o)
 {
     int n = m->ndof;
-    double tau_gc[OR_MAXD], tau[OR_MAXD], qdd[OR_MAXD];
+    double tau_gc[OR_MAXD], tau[OR_MAXD] = {0}, qdd[OR_MAXD];
     or_inverse_dynamics(m, s->q, s->qd, NULL, tau_gc);
     for (int i = 0; i < n; i++) tau[i] = tau_gc[i] - m->joint_damping * s->qd[i];
     Aba A; aba_setup(m, s->q, s->qd, tau, 1, &A);
@@ -1056,4 +1056,278 @@ void or_surface_heights(long long seed, int rows, int cols, double interp, doubl
     or_opensimplex_init(seed, perm);
     for (int x = 0; x < rows; x++)
         for (int y = 0; y < cols; y++) out[x * cols + y] = or_opensimplex_noise2(perm, x * interp, y * interp) * range;
+}
+
+/* ================================================================ object_push: stepSimulation with contact rows
+ * See the block comment in tg_oracle.h for what is restated and what is simplified.  Call sites: robots/arms/robot.py:141
+ * (stepSimulation), object_push_env.py:204-229 (cube dynamics), sensors/tactile_sensor.py:314-332 (tip dynamics). */
+typedef struct {
+    int on_arm;          /* 1: tip core <-> cube, 0: cube <-> table */
+    double n[3];         /* unit normal: out of the cube face towards the tip / up from the table */
+    double pa[3], pb[3]; /* contact point on the arm (tip contacts only); contact point on the cube */
+    double dist, mu, cfm, erp;
+} PushContact;
+
+static long long qkey(double x) { return llrint(x * 1e9); } /* comparisons on a 1 nm grid: ties break by index */
+
+/* signed distance of a cube-local point to the cube surface (negative inside) and the face it belongs to */
+static double cube_sd(const double half[3], const double l[3], int* axis, int* sign)
+{
+    double best = -1e300; int a = 0;
+    for (int c = 0; c < 3; c++) { const double d = fabs(l[c]) - half[c]; if (d > best) { best = d; a = c; } }
+    *axis = a; *sign = l[a] >= 0 ? 1 : -1;
+    return best;
+}
+
+static void plane_space1(const double n[3], double p[3], double q[3]) /* [EXT] btPlaneSpace1 */
+{
+    if (fabs(n[2]) > 0.7071067811865475244008443621048490) {
+        const double a = n[1] * n[1] + n[2] * n[2], k = 1.0 / sqrt(a);
+        p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+        q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        const double a = n[0] * n[0] + n[1] * n[1], k = 1.0 / sqrt(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+        q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+    }
+}
+
+static int push_contacts(const OrModel* m, const Kin* k, const OrObject* o, const OrPush* P, const m3 Rb, PushContact* C)
+{
+    int nc = 0;
+    /* cube <-> table: cube vertices at or below the table top */
+    for (int v = 0; v < 8 && nc < 4; v++) {
+        v3 l = {(v & 1) ? P->half[0] : -P->half[0], (v & 2) ? P->half[1] : -P->half[1], (v & 4) ? P->half[2] : -P->half[2]}, w;
+        m3mulv(w, Rb, l); v3add(w, w, o->pos);
+        const double dist = w[2] - P->table_z;
+        if (dist > P->slop) continue;
+        PushContact* c = &C[nc++];
+        c->on_arm = 0; v3set(c->n, 0, 0, 1); v3cpy(c->pb, w); v3cpy(c->pa, w);
+        c->dist = dist; c->mu = P->mu_table; c->cfm = 0.0; c->erp = P->erp;
+    }
+    /* tip core hull <-> cube */
+    const int tl = P->tip_link;
+    m3 M; v3 t, d;
+    m3tmul(M, Rb, k->Rl[tl]);
+    v3sub(d, k->pl[tl], o->pos); m3tmulv(t, Rb, d);
+    long long deep_key = 0, ext_key[3][2]; int deep = -1, ext[3][2], ncand = 0;
+    for (int i = 0; i < P->n_hull; i++) {
+        v3 l; int ax, sg;
+        m3mulv(l, M, P->hull + 3 * i); v3add(l, l, t);
+        const double sd = cube_sd(P->half, l, &ax, &sg);
+        if (sd > P->slop) continue;
+        const long long key = qkey(sd);
+        if (ncand == 0 || key < deep_key) { deep_key = key; deep = i; }
+        for (int c = 0; c < 3; c++) {
+            const long long lk = qkey(l[c]);
+            if (ncand == 0 || lk < ext_key[c][0]) { ext_key[c][0] = lk; ext[c][0] = i; }
+            if (ncand == 0 || lk > ext_key[c][1]) { ext_key[c][1] = lk; ext[c][1] = i; }
+        }
+        ncand++;
+    }
+    if (ncand > 0) {
+        v3 l; int A, sg;
+        m3mulv(l, M, P->hull + 3 * deep); v3add(l, l, t);
+        cube_sd(P->half, l, &A, &sg);
+        const int U = (A + 1) % 3, V = (A + 2) % 3;
+        const long long dv = qkey(l[V]);
+        const long long a0 = llabs(ext_key[V][0] - dv), a1 = llabs(ext_key[V][1] - dv);
+        int sel[4] = {deep, ext[U][0], ext[U][1], a0 >= a1 ? ext[V][0] : ext[V][1]};
+        const double dtk = m->dt * P->tip_k + P->tip_d;
+        for (int j = 0; j < 4; j++) {
+            int dup = 0;
+            for (int i = 0; i < j; i++) if (sel[i] == sel[j]) dup = 1;
+            if (dup) continue;
+            int ax; v3 ln = {0, 0, 0}, w;
+            m3mulv(l, M, P->hull + 3 * sel[j]); v3add(l, l, t);
+            const double sd = cube_sd(P->half, l, &ax, &sg);
+            ln[ax] = sg;
+            PushContact* c = &C[nc++];
+            c->on_arm = 1;
+            m3mulv(c->n, Rb, ln);
+            m3mulv(w, k->Rl[tl], P->hull + 3 * sel[j]); v3add(c->pa, k->pl[tl], w);
+            for (int q = 0; q < 3; q++) c->pb[q] = c->pa[q] - sd * c->n[q];
+            c->dist = sd; c->mu = P->mu_tip;
+            c->cfm = (1.0 / (dtk < 2.2204460492503131e-16 ? 2.2204460492503131e-16 : dtk)) / m->dt;
+            c->erp = (m->dt * P->tip_k) / (dtk < 2.2204460492503131e-16 ? 2.2204460492503131e-16 : dtk);
+        }
+    }
+    return nc;
+}
+
+void or_step_sim_push(const OrModel* m, OrState* s, OrObject* o, OrPush* P)
+{
+    const int n = m->ndof;
+    double tau_gc[OR_MAXD], tau[OR_MAXD] = {0}, qdd[OR_MAXD];
+    or_inverse_dynamics(m, s->q, s->qd, NULL, tau_gc);
+    for (int i = 0; i < n; i++) tau[i] = tau_gc[i] - m->joint_damping * s->qd[i];
+    Aba A; aba_setup(m, s->q, s->qd, tau, 1, &A);
+    aba_accel(m, &A, qdd);
+    for (int i = 0; i < n; i++) s->qd[i] += m->dt * qdd[i];
+
+    /* narrow phase on the poses at the start of the step */
+    Kin k; kin_compute(m, s->q, &k);
+    m3 Rb; or_mat_from_quat(o->quat, Rb);
+    PushContact C[OR_MAXC];
+    const int nc = push_contacts(m, &k, o, P, Rb, C);
+
+    /* cube: unconstrained velocity update about its COM (gravity, [EXT] multibody base damping, gyroscopic term) */
+    double Iinv[3];
+    for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / o->inertia[c];
+    {
+        v3 wl, Iw, gy, al, aw;
+        m3tmulv(wl, Rb, o->omg);
+        for (int c = 0; c < 3; c++) Iw[c] = o->inertia[c] * wl[c];
+        v3cross(gy, wl, Iw);
+        const double ka = P->ang_damping * (1.0 + v3norm(o->omg)), kl = P->lin_damping * (1.0 + v3norm(o->vel));
+        for (int c = 0; c < 3; c++) al[c] = (-Iw[c] * ka - gy[c]) * Iinv[c];
+        m3mulv(aw, Rb, al);
+        for (int c = 0; c < 3; c++) {
+            const double f = m->gravity[c] * o->mass - o->mass * o->vel[c] * kl;
+            o->vel[c] += m->dt * f / o->mass; o->omg[c] += m->dt * aw[c];
+        }
+    }
+
+    /* rows: motors, then per contact (normal, friction 1, friction 2) */
+    enum { MAXR = 3 * OR_MAXC };
+    double jr[MAXR][OR_MAXD], ur[MAXR][OR_MAXD], jl[MAXR][3], ja[MAXR][3], ul[MAXR][3], ua[MAXR][3];
+    double diag[MAXR], dinv[MAXR], rhs[MAXR], cfmr[MAXR], applied[MAXR];
+    double mresp[OR_MAXD][OR_MAXD], mdinv[OR_MAXD], mrhs[OR_MAXD], mlim[OR_MAXD], mapplied[OR_MAXD];
+    int mrow[OR_MAXD], nm = 0;
+    for (int i = 0; i < n; i++) {
+        const double maximp = s->max_force[i] * m->dt;
+        if (maximp == 0) continue;
+        double f[OR_MAXD] = {0}; f[i] = 1.0;
+        aba_delta(m, &A, f, mresp[nm]);
+        const double denom = mresp[nm][i];
+        mdinv[nm] = denom > 2.2204460492503131e-16 ? 1.0 / denom : 0.0;
+        const double v = s->qd[i];
+        const double kp = s->motor_mode[i] == 1 ? s->kp[i] : 0.0, tp = s->motor_mode[i] == 1 ? s->target_pos[i] : 0.0;
+        const double rhs_v = kp * ((tp - s->q[i]) / m->dt) + v + s->kd[i] * (s->target_vel[i] - v);
+        mrhs[nm] = (rhs_v - v) * mdinv[nm];
+        mlim[nm] = maximp; mapplied[nm] = 0; mrow[nm] = i;
+        nm++;
+    }
+    for (int c = 0; c < nc; c++) {
+        const PushContact* ct = &C[c];
+        /* relative velocity of the two contact points (after the unconstrained update) */
+        v3 va = {0, 0, 0}, vb, rb, t, vrel;
+        v3sub(rb, ct->pb, o->pos);
+        v3cross(t, o->omg, rb); v3add(vb, o->vel, t);
+        if (ct->on_arm)
+            for (int i = P->tip_link; i >= 0; i = m->parent[i]) {
+                if (m->jtype[i] != 1) continue;
+                v3 r, lin; v3sub(r, ct->pa, k.pl[i]); v3cross(lin, k.aw[i], r);
+                v3axpy(va, s->qd[m->dof_of_link[i]], lin);
+            }
+        if (ct->on_arm) v3sub(vrel, va, vb); else v3cpy(vrel, vb);
+        /* friction directions: a fixed orthonormal basis of the contact plane ([EXT] btPlaneSpace1).  Bullet's default
+         * aligns the first direction with the lateral relative velocity; with two directions and an isotropic cone that
+         * does not change the converged solution, but it makes a solve truncated by the residual exit chaotic at
+         * resting contacts (a unit vector built from a ~1e-5 m/s velocity), so it is not restated. */
+        v3 dir[3];
+        v3cpy(dir[0], ct->n);
+        plane_space1(ct->n, dir[1], dir[2]);
+        const double sc = ct->on_arm ? -1.0 : 1.0; /* the cube is the second body of a tip contact */
+        for (int q = 0; q < 3; q++) {
+            const int r = 3 * c + q;
+            double f[OR_MAXD] = {0};
+            for (int d2 = 0; d2 < n; d2++) { jr[r][d2] = 0; ur[r][d2] = 0; }
+            if (ct->on_arm) {
+                for (int i = P->tip_link; i >= 0; i = m->parent[i]) {
+                    if (m->jtype[i] != 1) continue;
+                    v3 rr, lin; v3sub(rr, ct->pa, k.pl[i]); v3cross(lin, k.aw[i], rr);
+                    jr[r][m->dof_of_link[i]] = v3dot(dir[q], lin);
+                }
+                for (int d2 = 0; d2 < n; d2++) f[d2] = jr[r][d2];
+                aba_delta(m, &A, f, ur[r]);
+            }
+            v3scale(jl[r], dir[q], sc);
+            v3cross(ja[r], rb, dir[q]); v3scale(ja[r], ja[r], sc);
+            v3scale(ul[r], jl[r], 1.0 / o->mass);
+            { v3 a, b; m3tmulv(a, Rb, ja[r]); for (int c2 = 0; c2 < 3; c2++) b[c2] = a[c2] * Iinv[c2]; m3mulv(ua[r], Rb, b); }
+            double den = v3dot(jl[r], ul[r]) + v3dot(ja[r], ua[r]);
+            for (int d2 = 0; d2 < n; d2++) den += jr[r][d2] * ur[r][d2];
+            diag[r] = den;
+            const double rel = v3dot(dir[q], vrel);
+            if (q == 0) {
+                dinv[r] = 1.0 / (den + ct->cfm);
+                const double positional = ct->dist > 0 ? 0.0 : -ct->dist * ct->erp / m->dt;
+                const double velerr = -rel - (ct->dist > 0 ? ct->dist / m->dt : 0.0);
+                rhs[r] = (positional + velerr) * dinv[r];
+                cfmr[r] = ct->cfm * dinv[r];
+            } else {
+                dinv[r] = den > 2.2204460492503131e-16 ? 1.0 / den : 0.0;
+                rhs[r] = -rel * dinv[r];
+                cfmr[r] = 0.0;
+            }
+            applied[r] = 0.0;
+        }
+    }
+    double dv[OR_MAXD] = {0}, dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
+    int it = 0;
+    for (; it < m->solver_iters; it++) {
+        double resid = 0;
+        for (int jj = 0; jj < nm; jj++) {
+            const int r = (it & 1) ? jj : nm - 1 - jj, d = mrow[r];
+            double delta = mrhs[r] - dv[d] * mdinv[r];
+            const double sum = mapplied[r] + delta;
+            if (sum < -mlim[r]) { delta = -mlim[r] - mapplied[r]; mapplied[r] = -mlim[r]; }
+            else if (sum > mlim[r]) { delta = mlim[r] - mapplied[r]; mapplied[r] = mlim[r]; }
+            else mapplied[r] = sum;
+            for (int i = 0; i < n; i++) dv[i] += mresp[r][i] * delta;
+            const double dvel = mdinv[r] != 0 ? delta / mdinv[r] : 0.0;
+            if (dvel * dvel > resid) resid = dvel * dvel;
+        }
+        for (int c = 0; c < nc; c++) { /* normal rows: impulse >= 0 */
+            const int r = 3 * c;
+            double dot = v3dot(jl[r], dvl) + v3dot(ja[r], dva);
+            for (int d = 0; d < n; d++) dot += jr[r][d] * dv[d];
+            double delta = rhs[r] - applied[r] * cfmr[r] - dot * dinv[r];
+            const double sum = applied[r] + delta;
+            if (sum < 0.0) { delta = -applied[r]; applied[r] = 0.0; } else applied[r] = sum;
+            for (int d = 0; d < n; d++) dv[d] += ur[r][d] * delta;
+            for (int q = 0; q < 3; q++) { dvl[q] += ul[r][q] * delta; dva[q] += ua[r][q] * delta; }
+            const double dvel = delta * (diag[r] + C[c].cfm);
+            if (dvel * dvel > resid) resid = dvel * dvel;
+        }
+        for (int c = 0; c < nc; c++) { /* friction pairs inside the cone mu * normal impulse */
+            const double lim = C[c].mu * applied[3 * c];
+            if (!(applied[3 * c] > 0.0)) continue;
+            double sum[2], delta[2];
+            for (int q = 0; q < 2; q++) {
+                const int r = 3 * c + 1 + q;
+                double dot = v3dot(jl[r], dvl) + v3dot(ja[r], dva);
+                for (int d = 0; d < n; d++) dot += jr[r][d] * dv[d];
+                delta[q] = rhs[r] - dot * dinv[r];
+                sum[q] = applied[r] + delta[q];
+            }
+            const double nrm2 = sum[0] * sum[0] + sum[1] * sum[1];
+            if (nrm2 > lim * lim) { const double sc = lim / sqrt(nrm2); sum[0] *= sc; sum[1] *= sc; }
+            for (int q = 0; q < 2; q++) {
+                const int r = 3 * c + 1 + q;
+                delta[q] = sum[q] - applied[r]; applied[r] = sum[q];
+                for (int d = 0; d < n; d++) dv[d] += ur[r][d] * delta[q];
+                for (int q2 = 0; q2 < 3; q2++) { dvl[q2] += ul[r][q2] * delta[q]; dva[q2] += ua[r][q2] * delta[q]; }
+                const double dvel = delta[q] * diag[r];
+                if (dvel * dvel > resid) resid = dvel * dvel;
+            }
+        }
+        if (resid <= m->solver_residual_threshold) { it++; break; }
+    }
+    P->n_contacts = nc; P->n_iters = it;
+    for (int c = 0; c < OR_MAXC; c++) {
+        P->normal_impulse[c] = c < nc ? applied[3 * c] : 0.0;
+        for (int q = 0; q < 3; q++) P->contact_pos[c][q] = c < nc ? C[c].pb[q] : 0.0;
+    }
+    for (int i = 0; i < n; i++) { s->qd[i] += dv[i]; s->q[i] += m->dt * s->qd[i]; }
+    for (int c = 0; c < 3; c++) { o->vel[c] += dvl[c]; o->omg[c] += dva[c]; o->pos[c] += m->dt * o->vel[c]; }
+    {
+        const double wn = v3norm(o->omg), ang = wn * m->dt;
+        double dq[4] = {0, 0, 0, 1};
+        if (wn > 1e-300) { const double sn = sin(0.5 * ang) / wn; dq[0] = o->omg[0] * sn; dq[1] = o->omg[1] * sn; dq[2] = o->omg[2] * sn; dq[3] = cos(0.5 * ang); }
+        double qn[4]; quat_mul(qn, dq, o->quat);
+        const double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+        for (int c = 0; c < 4; c++) o->quat[c] = qn[c] / nn;
+    }
 }

@@ -141,6 +141,50 @@ double or_opensimplex_noise2(const short perm[256], double x, double y);
 /* gen_heigtfield_simplex_2d (:311-327): out[x*cols + y] = noise2(x*interp, y*interp) * range */
 void or_surface_heights(long long seed, int rows, int cols, double interp, double range, double* out);
 
+
+/* ---- object_push: contact rows (rl_envs/nonprehensile_manipulation/object_push/object_push_env.py) ----
+ * PARITY UNPINNED, and more loosely restated than the motor-only path: bullet's narrow phase for this pair is
+ * history dependent (GJK/EPA yields ONE point per frame, a persistent manifold caches up to four and drops the ones that
+ * drift), so its exact contact set cannot be reproduced without bullet itself.  What is restated:
+ *   geometry   memoryless manifolds rebuilt every stepSimulation from the poses at the start of the step:
+ *                cube <-> table (table top z = 0, base_tactile_env.py:135-139 + table.urdf): the cube vertices with
+ *                  z <= contactBreakingThreshold, normal +z, at most 4;
+ *                tip core hull <-> cube (the convex hull of the tip link's collision mesh, t_s_core "fixed",
+ *                  object_push_env.py:59): hull vertices inside the cube (per vertex: nearest face, signed distance),
+ *                  reduced to <= 4 like a persistent manifold (the deepest, the two extremes along the first tangent axis
+ *                  of the deepest point's face, the extreme along the second that is farther from the deepest);
+ *                  cube-vertex-in-hull and edge-edge contacts are not generated;
+ *   rows       [EXT] btMultiBodyConstraintSolver: per point one normal row (impulse >= 0; rhs = -rel_vel - dist/dt for
+ *              dist > 0, -rel_vel - dist*erp/dt otherwise) and two friction rows (fixed basis btPlaneSpace1(normal); bullet's
+ *              velocity-aligned first direction is deliberately not restated, see or_step_sim_push), implicit cone
+ *              |f| <= mu * normal impulse (enableConeFriction=1,
+ *              base_tactile_env.py:129); mu = product of the two lateralFriction values;
+ *   materials  contactStiffness / contactDamping of the tip (sensors/tactile_sensor.py:314-332, values
+ *              object_push_env.py:61-66) -> per-point erp = dt k / (dt k + d), cfm = 1 / (dt k + d) / dt [EXT];
+ *              table contacts: erp 0.2, cfm 0 [EXT defaults];
+ *   solver     motor rows (alternating order) then normal rows then friction pairs, <= 150 sweeps, residual exit as in
+ *              or_step_simulation; no warm starting (memoryless);
+ *   cube       floating base: gravity + [EXT] btMultiBody default damping 0.04 (1 + |v|) + gyroscopic term, explicit. */
+#define OR_MAXC 8
+typedef struct {
+    double half[3];          /* cube half extents (cube.urdf: 0.08 box) */
+    double table_z;          /* 0 */
+    double mu_table, mu_tip; /* 0.065 * 1.0, 0.065 * 10 (object_push_env.py:216-225, :61-66, table.urdf) */
+    double tip_k, tip_d;     /* combined contact stiffness / damping of the tip <-> cube pair */
+    double erp;              /* 0.2 */
+    double slop;             /* contactBreakingThreshold = 1e-4 (base_tactile_env.py:129) */
+    double lin_damping, ang_damping; /* cube: btMultiBody defaults 0.04 / 0.04 [EXT] */
+    int tip_link;            /* bullet link index owning the hull */
+    int n_hull;
+    const double* hull;      /* [n_hull][3], tip LINK frame */
+    /* diagnostics of the last substep */
+    int n_contacts, n_iters;
+    double normal_impulse[OR_MAXC];
+    double contact_pos[OR_MAXC][3];
+} OrPush;
+/* Robot.step_sim() with the cube in the world: gravity compensation + stepSimulation (motor + contact rows) */
+void or_step_sim_push(const OrModel* m, OrState* s, OrObject* cube, OrPush* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,9 @@ LIB_PATH = os.environ.get("TG_LIB_OVERRIDE") or os.path.join(HERE, "libtactile_g
 
 TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 8
 TG_TOPO_CHAIN6, TG_TOPO_MG400 = 0, 1
-TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE, TG_TASK_SURFACE_FOLLOW = 0, 1, 2
+TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE, TG_TASK_SURFACE_FOLLOW, TG_TASK_OBJECT_PUSH = 0, 1, 2, 3
+TG_PUSH_NTRAJ, TG_PUSH_NFEAT = 10, 12
+TG_PUSH_WORK, TG_PUSH_WORK_DRIVE, TG_PUSH_TCP_TYRZ, TG_PUSH_TCP_TXTYRZ = 0, 1, 2, 3
 
 D3 = C.c_double * 3
 D9 = C.c_double * 9
@@ -51,6 +53,11 @@ class TgTask(C.Structure):
         ("obj_term_deg", C.c_double), ("obj_term_pos", C.c_double), ("p2p_erp", C.c_double), ("p2p_max_impulse", C.c_double),
         ("surf_pos", D3), ("surf_grid", C.c_double), ("surf_range", C.c_double), ("surf_interp", C.c_double),
         ("surf_extent", C.c_double), ("surf_embed", C.c_double), ("surf_drive", C.c_double), ("surf_w_norm", C.c_double),
+        ("push_mode", C.c_int32), ("push_traj_straight", C.c_int32), ("push_sparse_reward", C.c_int32), ("push_pad", C.c_int32),
+        ("push_half", D3), ("push_table_z", C.c_double), ("push_mu_table", C.c_double), ("push_mu_tip", C.c_double),
+        ("push_tip_k", C.c_double), ("push_tip_d", C.c_double), ("push_erp", C.c_double), ("push_slop", C.c_double),
+        ("push_lin_damping", C.c_double), ("push_ang_damping", C.c_double), ("push_init_pos", D3), ("push_inertia_per_mass", D3),
+        ("push_term_dist", C.c_double), ("push_traj_spacing", C.c_double), ("push_traj_perturb", C.c_double), ("push_traj_offset", C.c_double),
     ]
 
 
@@ -68,11 +75,12 @@ class TgConfig(C.Structure):
         ("n_envs", C.c_int32), ("lanes_per_warp", C.c_int32),
         ("arm", TgArm), ("phys", TgPhysics), ("task", TgTask), ("sensor", TgSensor),
         ("h_rest_q", C.POINTER(C.c_double)),
+        ("h_tip_hull", C.POINTER(C.c_double)), ("n_tip_hull", C.c_int32), ("pad1", C.c_int32),
     ]
 
 
 EXPORTS = [
-    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_refill_draws", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step",
+    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_refill_draws", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_bind_features",
     "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
     "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_launch_count",
 ]
@@ -104,6 +112,7 @@ def load():
     lib.tg_get_reset_counts.argtypes = [vp, vp, vp]
     lib.tg_reset.argtypes = [vp, vp, vp, vp]
     lib.tg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.tg_bind_features.argtypes = [vp, vp, vp]
     lib.tg_physics_only.argtypes = [vp, vp, vp, vp, vp]
     lib.tg_raster_only.argtypes = [vp, vp, vp]
     lib.tg_reset_only.argtypes = [vp, vp, vp]

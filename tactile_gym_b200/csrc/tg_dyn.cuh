@@ -572,6 +572,7 @@ struct ObjState {
     double ext_pos[3]; // world point where the one-step external force applies
     int ext_pending;
     double grav_z, pivot_z; // per-episode gravity; constraint pivot z in the base-link COM frame
+    double mass;            // object_push: the cube's mass this episode (rand_obj_mass)
 };
 
 // Robot.step_sim() with the object in the world: 6 motor rows + 3 point-to-point rows

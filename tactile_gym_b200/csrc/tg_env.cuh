@@ -20,6 +20,9 @@
 #pragma once
 #include "tg_dyn.cuh"
 #include "tg_surface.cuh"
+#include "tg_push.cuh"
+
+#define PUSH_TRAJ_SZ (2 * PUSH_NTRAJ + 1) // y_i, Rz_i (work frame) and the episode's third draw (seed / direction)
 
 struct EnvBuffers {
     int n;
@@ -40,9 +43,17 @@ struct EnvBuffers {
     double* stim;         // [N][12] R(9) t(3) of the stimulus frame
     double* tcp;          // [N][7] tcp world pos + quat (state export)
     const double* rest_q; // [NB]
-    // free object (object_balance): [N][13] pos quat vel omg, [N][4] ext force point + pending flag, [N] gravity_z
+    // free object (object_balance pole / object_push cube): [N][13] pos quat vel omg, [N][4] ext force point + pending
+    // flag, [N] the episode's scalar (gravity_z for object_balance, the cube's mass for object_push)
     double *obj, *obj_ext, *grav;
     double *sb_obj, *sb_obj_ext, *sb_grav;
+    // object_push: trajectory of goals [N][PUSH_TRAJ_SZ], current goal index [N], tip hull (tcp body frame), and the
+    // caller's feature buffers [N][TG_PUSH_NFEAT] f32 (tg_bind_features; may be null)
+    double *traj, *sb_traj;
+    int *goal, *sb_goal;
+    const double* hull;
+    int n_hull;
+    float *feat, *term_feat;
     // standby start-of-episode state
     double *sb_q, *sb_qd, *sb_embed, *sb_ang, *sb_cam, *sb_stim, *sb_tcp;
     int* sb_substeps;
@@ -83,7 +94,9 @@ template <int NB>
 struct EpisodeStart {
     double q[NB], qd[NB], embed, edge_ang, cam[12], stim[12], tcp[7];
     int substeps;
-    ObjState obj; // object_balance only
+    ObjState obj; // object_balance, object_push
+    double traj[PUSH_TRAJ_SZ]; // object_push only
+    int goal;
 };
 
 TGD void obj_load(const double* o13, const double* e4, double g, double embed, const TgTask& task, ObjState& o)
@@ -94,6 +107,7 @@ TGD void obj_load(const double* o13, const double* e4, double g, double embed, c
     for (int c = 0; c < 4; c++) o.quat[c] = o13[3 + c];
     o.ext_pending = e4[3] != 0.0;
     o.grav_z = g;
+    o.mass = g; // object_push keeps the cube's mass in the episode scalar
     o.pivot_z = -task.obj_base_h * 0.5 + embed; // update_constraints (object_balance_env.py:285-293)
 }
 TGD void obj_store(double* o13, double* e4, const ObjState& o)
@@ -241,9 +255,9 @@ TGD int ik_chunk(const TgArm& arm, double* q, const double* tpos, const double* 
 // (surface_follow: centre_h = the new surface's height at the grid centre, base_surface_env.py:549-573)
 TGD void reset_target(const TgTask& task, double embed, double centre_h, double* tpos, double* targ_orn)
 {
-    const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
+    const bool balance = task.task == TG_TASK_OBJECT_BALANCE || task.task == TG_TASK_OBJECT_PUSH;
     double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
-    const double lp[3] = {0.0, 0.0, balance ? 0.0 : embed}; // update_init_pose: edge_follow_env.py:301-309 / base_object_env.py
+    const double lp[3] = {0.0, 0.0, balance ? 0.0 : embed}; // update_init_pose: edge_follow_env.py:301-309 / base_object_env.py:104-111
     quat_from_euler(task.workframe_rpy, wq);
     quat_from_euler(task.init_rpy, tq);
     mat_from_quat(wq, R);
@@ -275,8 +289,10 @@ __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, c
     const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
     // edge_follow draws: embed_dist, edge_ang; object_balance draws: gravity_z, embed_dist, fx, fy;
     // surface_follow draws: OpenSimplex seed, goal direction angle (kept in edge_ang)
+    // object_push draws: init_obj_ang, obj_mass, OpenSimplex seed | trajectory direction (consumed in reset_finish)
     r.embed = balance ? r.draw[1] : r.draw[0];
     r.edge_ang = balance ? 0.0 : r.draw[1];
+    if (task.task == TG_TASK_OBJECT_PUSH) { r.embed = 0.0; r.edge_ang = 0.0; }
     r.surf_it = SURF_PTS; r.hmin = 0.f; r.hmax = 0.f;
     if (task.task == TG_TASK_SURFACE_FOLLOW) {
         r.embed = task.surf_embed;
@@ -402,6 +418,25 @@ __device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, 
         meta[6] = (double)r.hmin; meta[7] = (double)r.hmax; // float32 height range (the raster's first slab bound)
 #pragma unroll
         for (int i = 0; i < 12; i++) out.stim[i] = 0.0;
+    } else if (task.task == TG_TASK_OBJECT_PUSH) {
+        // reset_object (object_push_env.py:204-229): cube back at init_obj_pos, yaw pi/2 + init_obj_ang, at rest;
+        // make_goal (:322-333): new trajectory, first goal; BaseObjectEnv.reset then calls get_step_data() once, whose
+        // termination() already advances the goal when the cube starts within termination_pos_dist of it
+        ObjState& o = out.obj;
+        const double rpy[3] = {task.obj_init_rpy[0], task.obj_init_rpy[1], task.obj_init_rpy[2] + r.draw[0]};
+        quat_from_euler(rpy, o.quat);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { o.pos[c] = task.push_init_pos[c]; o.vel[c] = 0.0; o.omg[c] = 0.0; o.ext_pos[c] = 0.0; }
+        o.ext_pending = 0; o.pivot_z = 0.0;
+        o.mass = r.draw[1]; o.grav_z = r.draw[1];
+        push_trajectory(task, r.draw[2], out.traj);
+        out.traj[2 * PUSH_NTRAJ] = r.draw[2];
+        out.goal = 0;
+        {
+            float rw; unsigned char dn;
+            push_step_data(task, o, out.tcp + 3, out.traj, r.draw[2], out.goal, 0, &rw, &dn);
+        }
+        obj_stim(task, o, out.stim);
     } else if (!balance) {
         double sn, cs;
         sincos(r.edge_ang * 0.5, &sn, &cs);
@@ -452,6 +487,11 @@ TGD void store_live(const EnvBuffers& b, int e, const EpisodeStart<NB>& s)
 #pragma unroll
     for (int c = 0; c < 7; c++) b.tcp[(size_t)e * 7 + c] = s.tcp[c];
     if (b.obj) { obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, s.obj); b.grav[e] = s.obj.grav_z; }
+    if (b.traj) {
+#pragma unroll 1
+        for (int c = 0; c < PUSH_TRAJ_SZ; c++) b.traj[(size_t)e * PUSH_TRAJ_SZ + c] = s.traj[c];
+        b.goal[e] = s.goal;
+    }
 }
 
 template <int NB>
@@ -465,6 +505,11 @@ TGD void store_standby(const EnvBuffers& b, int e, const EpisodeStart<NB>& s)
 #pragma unroll
     for (int c = 0; c < 7; c++) b.sb_tcp[(size_t)e * 7 + c] = s.tcp[c];
     if (b.obj) { obj_store(b.sb_obj + (size_t)e * 13, b.sb_obj_ext + (size_t)e * 4, s.obj); b.sb_grav[e] = s.obj.grav_z; }
+    if (b.traj) {
+#pragma unroll 1
+        for (int c = 0; c < PUSH_TRAJ_SZ; c++) b.sb_traj[(size_t)e * PUSH_TRAJ_SZ + c] = s.traj[c];
+        b.sb_goal[e] = s.goal;
+    }
     __threadfence();
     atomicExch(&b.sb_ready[e], SB_READY);
 }
@@ -516,9 +561,22 @@ TGD void consume_standby(const EnvBuffers& b, int e)
         for (int c = 0; c < 4; c++) b.obj_ext[(size_t)e * 4 + c] = __ldcg(b.sb_obj_ext + (size_t)e * 4 + c);
         b.grav[e] = __ldcg(b.sb_grav + e);
     }
+    if (b.traj) {
+#pragma unroll 1
+        for (int c = 0; c < PUSH_TRAJ_SZ; c++) b.traj[(size_t)e * PUSH_TRAJ_SZ + c] = __ldcg(b.sb_traj + (size_t)e * PUSH_TRAJ_SZ + c);
+        b.goal[e] = __ldcg(b.sb_goal + e);
+    }
     if (b.height) b.hf_cur[e] = 1 - b.hf_cur[e]; // the heightfield built for this episode becomes the live one
     __threadfence();
     atomicExch(&b.sb_ready[e], SB_EMPTY);
+}
+
+// object_push: the extended feature of env e's live state (after a reset / standby swap)
+TGD void write_live_features(const TgTask& task, const EnvBuffers& b, int e)
+{
+    if (!b.feat || !b.traj) return;
+    const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
+    push_features(task, b.tcp + (size_t)e * 7, b.tcp + (size_t)e * 7 + 3, tr, tr[2 * PUSH_NTRAJ], b.goal[e], b.feat + (size_t)e * TG_PUSH_NFEAT);
 }
 
 // Work on the standby slot of env e if it is free to take: EMPTY -> draws + IK, PARTIAL -> one chunk of the
@@ -592,7 +650,15 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 
     // encode_actions + scale_actions (edge_follow_env.py:345-369, base_tactile_env.py:141-164)
     double v[6];
+    Motors<NB> mot;
+    mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
     {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4], wq[4], Rw[9];
+        tcp_world<T>(arm, k, tp, tq);
+        quat_from_euler(task.workframe_rpy, wq);
+        mat_from_quat(wq, Rw);
         double enc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int kk = 0; kk < 6; kk++)
@@ -606,21 +672,34 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
             const double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)b.hf_cur[e]) * SURF_META;
             enc[0] = meta[1] * task.surf_drive; enc[1] = meta[2] * task.surf_drive;
         }
+        if (task.task == TG_TASK_OBJECT_PUSH) {
+            // ObjectPushEnv.encode_actions (object_push_env.py:369-454)
+            if (task.push_mode == TG_PUSH_WORK_DRIVE) enc[0] = task.act_max;
+            if (task.push_mode == TG_PUSH_TCP_TYRZ || task.push_mode == TG_PUSH_TCP_TXTYRZ) {
+                // directions along / across the tip in the TCP frame, brought to the work frame (worldvec_to_workvec)
+                double Rt[9], parw[3], perpw[3], par[3], perp[3];
+                mat_from_quat(tq, Rt);
+                const double ex[3] = {1.0, 0.0, 0.0}, ey[3] = {0.0, -1.0, 0.0};
+                m3mulv(parw, Rt, ex); m3mulv(perpw, Rt, ey);
+                m3tmulv(par, Rw, parw); m3tmulv(perp, Rw, perpw);
+                const bool ty = task.push_mode == TG_PUSH_TCP_TYRZ;
+                const double a0 = (double)actions[(size_t)e * task.act_dim], a1 = (double)actions[(size_t)e * task.act_dim + 1];
+                const double par_scale = ty ? 1.0 * task.act_max : a0, perp_scale = ty ? a0 : a1;
+                const double rz = ty ? a1 : (double)actions[(size_t)e * task.act_dim + (task.act_dim > 2 ? 2 : 1)];
+                enc[0] = 0.0; enc[1] = 0.0; enc[5] = 0.0;
+                enc[0] += perp[0] * perp_scale + par[0] * par_scale;
+                enc[1] += perp[1] * perp_scale + par[1] * par_scale;
+                enc[5] += rz;
+            }
+        }
         const double in_range = task.act_max - task.act_min;
 #pragma unroll
         for (int s = 0; s < 6; s++) {
             const double a = fmin(fmax(enc[s], task.act_min), task.act_max);
             v[s] = (((a - task.act_min) * (task.act_hi[s] - task.act_lo[s])) / in_range) + task.act_lo[s];
         }
-    }
-    Motors<NB> mot;
-    mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
-    {
         // tcp_velocity_control (base_robot_arm.py:281-332)
-        Kin<NB> k;
-        fk<T>(arm, q, k);
-        double tp[3], tq[4], wp[3], wr[3];
-        tcp_world<T>(arm, k, tp, tq);
+        double wp[3], wr[3];
         world_to_work(task, tp, tq, wp, wr);
 #pragma unroll
         for (int s = 0; s < 6; s++) {
@@ -628,10 +707,8 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
             const bool ex = (cur < task.tcp_lims[s][0] && v[s] < 0) || (cur > task.tcp_lims[s][1] && v[s] > 0);
             if (ex) v[s] = 0.0;
         }
-        double wq[4], R[9], vw[6];
-        quat_from_euler(task.workframe_rpy, wq);
-        mat_from_quat(wq, R);
-        m3mulv(vw, R, v); m3mulv(vw + 3, R, v + 3);
+        double vw[6];
+        m3mulv(vw, Rw, v); m3mulv(vw + 3, Rw, v + 3);
         double J[6][NB];
         tcp_jacobian<T>(arm, k, tp, J);
         bool use_pinv = NB != 6 || arm.topo == TG_TOPO_MG400;   // mg400.py:109 always uses the pseudo-inverse
@@ -656,12 +733,18 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;
     }
     const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
+    const bool push = task.task == TG_TASK_OBJECT_PUSH;
     ObjState ob;
     {
         double sc[NB][2]; // (sin q, cos q): exact here, then advanced by the trig identity after every substep
 #pragma unroll
         for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
-        if (balance) {
+        if (push) {
+            obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
+#pragma unroll 1
+            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob);
+            obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
+        } else if (balance) {
             obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);
 #pragma unroll 1
             for (int s = 0; s < ph.substeps; s++) substep_obj<T>(arm, ph, task, q, qd, sc, mot, ob);
@@ -681,7 +764,16 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     double tp[3], tq[4];
     tcp_world<T>(arm, k, tp, tq);
     float r; unsigned char d;
-    if (balance) {
+    if (push) {
+        const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
+        int goal = b.goal[e];
+        push_step_data(task, ob, tq, tr, tr[2 * PUSH_NTRAJ], goal, steps, &r, &d);
+        b.goal[e] = goal;
+        obj_stim(task, ob, b.stim + (size_t)e * 12);
+        // the observation is taken after get_step_data: the feature carries the (possibly advanced) goal
+        float* f = (d && autoreset && b.pipeline) ? b.term_feat : b.feat;
+        if (f) push_features(task, tp, tq, tr, tr[2 * PUSH_NTRAJ], goal, f + (size_t)e * TG_PUSH_NFEAT);
+    } else if (balance) {
         balance_step_data(task, ob, b.embed[e], steps, &r, &d);
         obj_stim(task, ob, b.stim + (size_t)e * 12); // the pole moves: the raster needs its pose every step
     } else if (task.task == TG_TASK_SURFACE_FOLLOW) {
@@ -695,6 +787,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
         for (int c = 0; c < 12; c++) b.term_stim[(size_t)e * 12 + c] = b.stim[(size_t)e * 12 + c];
         acquire_standby<T>(arm, ph, task, b, e);
+        write_live_features(task, b, e);
     } else {
         write_camera<T>(arm, k, b.cam + (size_t)e * 12);
 #pragma unroll
@@ -724,6 +817,7 @@ reset_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysic
         reset_env<T>(arm, ph, task, b, e, s);
         store_live<T::NB>(b, e, s);
     }
+    write_live_features(task, b, e);
 }
 
 // recompute every missing standby (after tg_set_draws invalidated them)

@@ -1,0 +1,503 @@
+// tg_push.cuh - object_push: one Robot.step_sim() with the cube in the world (motor rows + contact rows), the
+// trajectory of goals, reward / termination and the extended feature.
+//
+//   substep_push      <- pb.stepSimulation() (robots/arms/robot.py:141) for the scene of ObjectPushEnv
+//                        (rl_envs/nonprehensile_manipulation/object_push/object_push_env.py:204-229 cube dynamics,
+//                        sensors/tactile_sensor.py:314-332 tip contact stiffness / damping / friction)
+//   push_trajectory   <- update_trajectory_simplex / _straight + np.gradient (object_push_env.py:255-320)
+//   push_step_data    <- get_step_data / dense_reward / sparse_reward / termination (:456-569)
+//   push_features     <- get_extended_feature_array (:611-629)
+//
+// The contact model is the one oracle/tg_oracle.c:or_step_sim_push states (see oracle/tg_oracle.h for what is restated
+// from bullet and what is simplified): memoryless manifolds rebuilt every substep - cube vertices against the table
+// plane, tip-hull vertices inside the cube reduced to <= 4 points - one normal row (impulse >= 0, contact
+// stiffness / damping as per-point erp / cfm) and two friction rows per point inside the cone mu * normal impulse,
+// solved after the motor rows by the same projected Gauss-Seidel sweep, same residual exit.
+//
+// One thread per env.  The rows of a substep (<= 24 x (arm part NB + cube part 6)) live in per-thread local memory
+// (~4 KB, L1-resident at the env counts of the configs); the hull scan reads the same vertex in every lane (one
+// broadcast transaction per vertex per warp).
+#pragma once
+#include "tg_dyn.cuh"
+#include "tg_surface.cuh"
+
+#define PUSH_MAXC 8
+#define PUSH_NTRAJ TG_PUSH_NTRAJ
+
+TGD long long push_qkey(double x) { return __double2ll_rn(x * 1e9); } // comparisons on a 1 nm grid: ties break by index
+
+// signed distance of a cube-local point to the cube surface (negative inside) and the face it belongs to
+TGD double cube_sd(const double* half, const double* l, int& axis, int& sign)
+{
+    double best = -1e300;
+    int a = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double d = fabs(l[c]) - half[c];
+        if (d > best) { best = d; a = c; }
+    }
+    axis = a;
+    sign = (a == 0 ? l[0] : (a == 1 ? l[1] : l[2])) >= 0 ? 1 : -1;
+    return best;
+}
+
+TGD void plane_space1(const double* n, double* p, double* q) // [EXT] btPlaneSpace1
+{
+    if (fabs(n[2]) > 0.7071067811865475244008443621048490) {
+        const double a = n[1] * n[1] + n[2] * n[2], k = 1.0 / sqrt(a);
+        p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+        q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        const double a = n[0] * n[0] + n[1] * n[1], k = 1.0 / sqrt(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+        q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+    }
+}
+
+struct PushContact {
+    double n[3], pa[3], pb[3], dist;
+    int on_arm;
+};
+
+// is joint j an ancestor-or-self of the body that carries the tip?
+template <class T>
+TGD bool tip_ancestor(int tcp_body, int j)
+{
+    bool anc = false;
+    int a = tcp_body;
+#pragma unroll
+    for (int s = 0; s < T::NB; s++) {
+        if (a == j) anc = true;
+        if (a >= 0) {
+            int pa = -1;
+#pragma unroll
+            for (int b = 0; b < T::NB; b++) if (a == b) pa = T::parent(b);
+            a = pa;
+        }
+    }
+    return anc;
+}
+
+// narrow phase on the poses at the start of the substep; returns the number of contacts (table contacts first)
+template <class T>
+__device__ __noinline__ int push_contacts(const TgArm& arm, const TgTask& task, const double* __restrict__ hull, int n_hull,
+                                          const Kin<T::NB>& k, const ObjState& o, const double* Rb, PushContact* C)
+{
+    int nc = 0;
+#pragma unroll 1
+    for (int v = 0; v < 8 && nc < 4; v++) {
+        const double l[3] = {(v & 1) ? task.push_half[0] : -task.push_half[0], (v & 2) ? task.push_half[1] : -task.push_half[1],
+                             (v & 4) ? task.push_half[2] : -task.push_half[2]};
+        double w[3];
+        m3mulv(w, Rb, l);
+        w[0] += o.pos[0]; w[1] += o.pos[1]; w[2] += o.pos[2];
+        const double dist = w[2] - task.push_table_z;
+        if (dist > task.push_slop) continue;
+        PushContact& c = C[nc++];
+        c.on_arm = 0;
+        c.n[0] = 0; c.n[1] = 0; c.n[2] = 1;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { c.pb[q] = w[q]; c.pa[q] = w[q]; }
+        c.dist = dist;
+    }
+    // tip core hull <-> cube: cube-local coordinates of a hull vertex v (tip body frame) are M v + t
+    double Rt[9], pt[3], M[9], t[3];
+#pragma unroll
+    for (int b = 0; b < T::NB; b++)
+        if (arm.tcp_body == b) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) Rt[i] = k.R[b][i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) pt[i] = k.p[b][i];
+        }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) M[3 * i + j] = Rb[i] * Rt[j] + Rb[3 + i] * Rt[3 + j] + Rb[6 + i] * Rt[6 + j]; // Rb^T Rt
+    {
+        const double d[3] = {pt[0] - o.pos[0], pt[1] - o.pos[1], pt[2] - o.pos[2]};
+        m3tmulv(t, Rb, d);
+    }
+    long long deep_key = 0, ext_key[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    int deep = -1, ext[3][2] = {{0, 0}, {0, 0}, {0, 0}}, ncand = 0;
+#pragma unroll 2
+    for (int i = 0; i < n_hull; i++) {
+        const double v[3] = {__ldg(hull + 3 * i), __ldg(hull + 3 * i + 1), __ldg(hull + 3 * i + 2)};
+        double l[3];
+        m3mulv(l, M, v);
+        l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
+        int ax, sg;
+        const double sd = cube_sd(task.push_half, l, ax, sg);
+        if (sd > task.push_slop) continue;
+        const long long key = push_qkey(sd);
+        if (ncand == 0 || key < deep_key) { deep_key = key; deep = i; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const long long lk = push_qkey(l[c]);
+            if (ncand == 0 || lk < ext_key[c][0]) { ext_key[c][0] = lk; ext[c][0] = i; }
+            if (ncand == 0 || lk > ext_key[c][1]) { ext_key[c][1] = lk; ext[c][1] = i; }
+        }
+        ncand++;
+    }
+    if (ncand > 0) {
+        int A, sg;
+        double l[3];
+        {
+            const double v[3] = {__ldg(hull + 3 * deep), __ldg(hull + 3 * deep + 1), __ldg(hull + 3 * deep + 2)};
+            m3mulv(l, M, v);
+            l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
+            cube_sd(task.push_half, l, A, sg);
+        }
+        const int U = (A + 1) % 3, V = (A + 2) % 3;
+        const long long dv = push_qkey(V == 0 ? l[0] : (V == 1 ? l[1] : l[2]));
+        long long eU0 = 0, eU1 = 0, kV0 = 0, kV1 = 0, eV0 = 0, eV1 = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (c == U) { eU0 = ext[c][0]; eU1 = ext[c][1]; }
+            if (c == V) { kV0 = ext_key[c][0]; kV1 = ext_key[c][1]; eV0 = ext[c][0]; eV1 = ext[c][1]; }
+        }
+        const long long a0 = llabs(kV0 - dv), a1 = llabs(kV1 - dv);
+        const int sel[4] = {deep, (int)eU0, (int)eU1, a0 >= a1 ? (int)eV0 : (int)eV1};
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            bool dup = false;
+            for (int i = 0; i < j; i++) if (sel[i] == sel[j]) dup = true;
+            if (dup) continue;
+            const double v[3] = {__ldg(hull + 3 * sel[j]), __ldg(hull + 3 * sel[j] + 1), __ldg(hull + 3 * sel[j] + 2)};
+            m3mulv(l, M, v);
+            l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
+            int ax;
+            const double sd = cube_sd(task.push_half, l, ax, sg);
+            PushContact& c = C[nc++];
+            c.on_arm = 1;
+            // world normal = sign * column `ax` of Rb
+            c.n[0] = sg * (ax == 0 ? Rb[0] : (ax == 1 ? Rb[1] : Rb[2]));
+            c.n[1] = sg * (ax == 0 ? Rb[3] : (ax == 1 ? Rb[4] : Rb[5]));
+            c.n[2] = sg * (ax == 0 ? Rb[6] : (ax == 1 ? Rb[7] : Rb[8]));
+            double w[3];
+            m3mulv(w, Rt, v);
+#pragma unroll
+            for (int q = 0; q < 3; q++) { c.pa[q] = pt[q] + w[q]; c.pb[q] = c.pa[q] - sd * c.n[q]; }
+            c.dist = sd;
+        }
+    }
+    return nc;
+}
+
+// Robot.step_sim() with the cube in the world.  Returns the number of PGS sweeps.
+template <class T>
+__device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const double* __restrict__ hull, int n_hull,
+                                         double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot, ObjState& o)
+{
+    constexpr int NB = T::NB;
+    constexpr double EPS = 2.2204460492503131e-16;
+    double A[NB][NB];
+    robot_pre<T>(arm, ph, q, qd, sc, A);
+
+    Kin<NB> k;
+    fk_sc<T>(arm, sc, k);
+    double Rb[9];
+    mat_from_quat(o.quat, Rb);
+    PushContact C[PUSH_MAXC];
+    const int nc = push_contacts<T>(arm, task, hull, n_hull, k, o, Rb, C);
+
+    // cube: unconstrained velocity update about its COM (gravity, [EXT] multibody base damping, gyroscopic term)
+    double Iinv[3];
+    const double mass = o.mass, minv = 1.0 / mass;
+#pragma unroll
+    for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / (task.push_inertia_per_mass[c] * mass);
+    {
+        double wl[3], Iw[3], gy[3], al[3], aw[3];
+        m3tmulv(wl, Rb, o.omg);
+#pragma unroll
+        for (int c = 0; c < 3; c++) Iw[c] = task.push_inertia_per_mass[c] * mass * wl[c];
+        v3cross(gy, wl, Iw);
+        const double ka = task.push_ang_damping * (1.0 + sqrt(v3dot(o.omg, o.omg))), kl = task.push_lin_damping * (1.0 + sqrt(v3dot(o.vel, o.vel)));
+#pragma unroll
+        for (int c = 0; c < 3; c++) al[c] = (-Iw[c] * ka - gy[c]) * Iinv[c];
+        m3mulv(aw, Rb, al);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double f = ph.gravity[c] * mass - mass * o.vel[c] * kl;
+            o.vel[c] += ph.dt * f / mass;
+            o.omg[c] += ph.dt * aw[c];
+        }
+    }
+
+    // motor rows (registers), as in substep()
+    double mrhs[NB], mdinv[NB], mapplied[NB], dv[NB];
+    const double lim_m = mot.max_force * ph.dt;
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const double denom = A[i][i];
+        mdinv[i] = denom > EPS ? 1.0 / denom : 0.0;
+        const double v = qd[i];
+        const double pos_stab = mot.mode == 1 ? mot.kp * ((mot.target_pos[i] - q[i]) / ph.dt) : 0.0;
+        const double rhs_v = pos_stab + v + mot.kd * (mot.target_vel[i] - v);
+        mrhs[i] = (rhs_v - v) * mdinv[i];
+        mapplied[i] = 0; dv[i] = 0;
+    }
+
+    // contact rows (local memory): row 3c normal, 3c+1 / 3c+2 friction.  The arm part exists for tip contacts only.
+    double jr[3 * PUSH_MAXC][NB], ur[3 * PUSH_MAXC][NB];
+    double jl[3 * PUSH_MAXC][3], ja[3 * PUSH_MAXC][3], ua[3 * PUSH_MAXC][3];
+    double diag[3 * PUSH_MAXC], dinv[3 * PUSH_MAXC], rhs[3 * PUSH_MAXC], applied[3 * PUSH_MAXC], cfm[PUSH_MAXC], cfmr[PUSH_MAXC], mu[PUSH_MAXC];
+    const double dtk = fmax(ph.dt * task.push_tip_k + task.push_tip_d, EPS);
+#pragma unroll 1
+    for (int c = 0; c < nc; c++) {
+        const PushContact& ct = C[c];
+        const bool on_arm = ct.on_arm != 0;
+        const double erp = on_arm ? (ph.dt * task.push_tip_k) / dtk : task.push_erp;
+        cfm[c] = on_arm ? (1.0 / dtk) / ph.dt : 0.0;
+        mu[c] = on_arm ? task.push_mu_tip : task.push_mu_table;
+        double lin[NB][3]; // velocity of the arm's contact point per unit joint rate
+        double va[3] = {0, 0, 0}, vb[3], rb[3], vrel[3];
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const double r[3] = {ct.pa[0] - k.p[j][0], ct.pa[1] - k.p[j][1], ct.pa[2] - k.p[j][2]};
+            v3cross(lin[j], k.a[j], r);
+            const bool use = on_arm && tip_ancestor<T>(arm.tcp_body, j);
+#pragma unroll
+            for (int x = 0; x < 3; x++) { lin[j][x] = use ? lin[j][x] : 0.0; va[x] += qd[j] * lin[j][x]; }
+        }
+        {
+            double t[3];
+#pragma unroll
+            for (int x = 0; x < 3; x++) rb[x] = ct.pb[x] - o.pos[x];
+            v3cross(t, o.omg, rb);
+#pragma unroll
+            for (int x = 0; x < 3; x++) { vb[x] = o.vel[x] + t[x]; vrel[x] = on_arm ? va[x] - vb[x] : vb[x]; }
+        }
+        // friction basis: fixed per normal (see oracle/tg_oracle.c: the velocity-aligned first direction is not restated)
+        double dir[3][3];
+#pragma unroll
+        for (int x = 0; x < 3; x++) dir[0][x] = ct.n[x];
+        plane_space1(ct.n, dir[1], dir[2]);
+        const double scb = on_arm ? -1.0 : 1.0; // the cube is the second body of a tip contact
+#pragma unroll
+        for (int qq = 0; qq < 3; qq++) {
+            const int r = 3 * c + qq;
+            double den = 0;
+#pragma unroll
+            for (int j = 0; j < NB; j++) jr[r][j] = v3dot(dir[qq], lin[j]);
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                double u = 0;
+#pragma unroll
+                for (int e = 0; e < NB; e++) u += A[j][e] * jr[r][e];
+                ur[r][j] = u;
+                den += jr[r][j] * u;
+            }
+            double a[3], bq[3];
+            v3cross(ja[r], rb, dir[qq]);
+#pragma unroll
+            for (int x = 0; x < 3; x++) { jl[r][x] = scb * dir[qq][x]; ja[r][x] *= scb; }
+            m3tmulv(a, Rb, ja[r]);
+#pragma unroll
+            for (int x = 0; x < 3; x++) bq[x] = a[x] * Iinv[x];
+            m3mulv(ua[r], Rb, bq);
+            den += v3dot(jl[r], jl[r]) * minv + v3dot(ja[r], ua[r]);
+            diag[r] = den;
+            const double rel = v3dot(dir[qq], vrel);
+            if (qq == 0) {
+                dinv[r] = 1.0 / (den + cfm[c]);
+                const double positional = ct.dist > 0 ? 0.0 : -ct.dist * erp / ph.dt;
+                const double velerr = -rel - (ct.dist > 0 ? ct.dist / ph.dt : 0.0);
+                rhs[r] = (positional + velerr) * dinv[r];
+                cfmr[c] = cfm[c] * dinv[r];
+            } else {
+                dinv[r] = den > EPS ? 1.0 / den : 0.0;
+                rhs[r] = -rel * dinv[r];
+            }
+            applied[r] = 0.0;
+        }
+    }
+
+    double dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
+    auto row_m = [&](int r, double& resid) {
+        double delta = mrhs[r] - dv[r] * mdinv[r];
+        const double sum = mapplied[r] + delta;
+        const bool lo = sum < -lim_m, hi = sum > lim_m;
+        delta = lo ? (-lim_m - mapplied[r]) : (hi ? (lim_m - mapplied[r]) : delta);
+        mapplied[r] = lo ? -lim_m : (hi ? lim_m : sum);
+#pragma unroll
+        for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
+        const double dvel = delta * A[r][r];
+        resid = fmax(resid, dvel * dvel);
+    };
+    auto row_dot = [&](int r) {
+        double dot = v3dot(jl[r], dvl) + v3dot(ja[r], dva);
+#pragma unroll
+        for (int d = 0; d < NB; d++) dot += jr[r][d] * dv[d];
+        return dot;
+    };
+    auto row_apply = [&](int r, double delta) {
+#pragma unroll
+        for (int d = 0; d < NB; d++) dv[d] += ur[r][d] * delta;
+#pragma unroll
+        for (int x = 0; x < 3; x++) { dvl[x] += jl[r][x] * minv * delta; dva[x] += ua[r][x] * delta; }
+    };
+    int it = 0;
+#pragma unroll 1
+    for (; it < ph.solver_iters; it++) {
+        double resid = 0;
+        if (lim_m != 0.0) {
+            if (it & 1) {
+#pragma unroll
+                for (int r = 0; r < NB; r++) row_m(r, resid);
+            } else {
+#pragma unroll
+                for (int r = NB - 1; r >= 0; r--) row_m(r, resid);
+            }
+        }
+#pragma unroll 1
+        for (int c = 0; c < nc; c++) { // normal rows: impulse >= 0
+            const int r = 3 * c;
+            double delta = rhs[r] - applied[r] * cfmr[c] - row_dot(r) * dinv[r];
+            const double sum = applied[r] + delta;
+            const bool lo = sum < 0.0;
+            delta = lo ? -applied[r] : delta;
+            applied[r] = lo ? 0.0 : sum;
+            row_apply(r, delta);
+            const double dvel = delta * (diag[r] + cfm[c]);
+            resid = fmax(resid, dvel * dvel);
+        }
+#pragma unroll 1
+        for (int c = 0; c < nc; c++) { // friction pairs inside the cone mu * normal impulse
+            if (!(applied[3 * c] > 0.0)) continue;
+            const double lim = mu[c] * applied[3 * c];
+            const int r1 = 3 * c + 1, r2 = 3 * c + 2;
+            double s1 = applied[r1] + (rhs[r1] - row_dot(r1) * dinv[r1]);
+            double s2 = applied[r2] + (rhs[r2] - row_dot(r2) * dinv[r2]);
+            const double nrm2 = s1 * s1 + s2 * s2;
+            if (nrm2 > lim * lim) { const double scl = lim / sqrt(nrm2); s1 *= scl; s2 *= scl; }
+            const double d1 = s1 - applied[r1], d2 = s2 - applied[r2];
+            applied[r1] = s1; applied[r2] = s2;
+            row_apply(r1, d1);
+            row_apply(r2, d2);
+            const double e1 = d1 * diag[r1], e2 = d2 * diag[r2];
+            resid = fmax(resid, fmax(e1 * e1, e2 * e2));
+        }
+        if (resid <= ph.solver_residual_threshold) { it++; break; }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        qd[i] += dv[i];
+        const double d = ph.dt * qd[i];
+        q[i] += d;
+        sc_advance(sc[i], q[i], d);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { o.vel[c] += dvl[c]; o.omg[c] += dva[c]; o.pos[c] += ph.dt * o.vel[c]; }
+    {
+        const double wn = sqrt(v3dot(o.omg, o.omg)), ang = wn * ph.dt;
+        double dq[4] = {0, 0, 0, 1};
+        if (wn > 1e-300) {
+            double sn, cs;
+            sincos(0.5 * ang, &sn, &cs);
+            sn /= wn;
+            dq[0] = o.omg[0] * sn; dq[1] = o.omg[1] * sn; dq[2] = o.omg[2] * sn; dq[3] = cs;
+        }
+        double qn[4];
+        quat_mul(qn, dq, o.quat);
+        const double nn = 1.0 / sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) o.quat[c] = qn[c] * nn;
+    }
+    return it;
+}
+
+// ---------------------------------------------------------------- trajectory of goals
+// update_trajectory (object_push_env.py:255-320): traj[i] = y_i (work frame), traj[PUSH_NTRAJ + i] = Rz_i = np.gradient(y, spacing)
+__device__ __noinline__ void push_trajectory(const TgTask& task, double third, double* traj)
+{
+    if (task.push_traj_straight) {
+        double sn, cs;
+        sincos(third, &sn, &cs);
+#pragma unroll 1
+        for (int i = 0; i < PUSH_NTRAJ; i++) traj[i] = ((double)i * task.push_traj_spacing) * sn;
+    } else {
+        unsigned char perm[256];
+        os_perm((long long)third, perm);
+        double first = 0;
+#pragma unroll 1
+        for (int i = 0; i < PUSH_NTRAJ; i++) {
+            const double noise = os_noise2(perm, (double)i * 0.1, 1.0) * task.push_traj_perturb;
+            if (i == 0) first = -noise;
+            traj[i] = first + noise;
+        }
+    }
+    const double h = task.push_traj_spacing;
+#pragma unroll 1
+    for (int i = 0; i < PUSH_NTRAJ; i++) {
+        double g;
+        if (i == 0) g = (traj[1] - traj[0]) / h;
+        else if (i == PUSH_NTRAJ - 1) g = (traj[i] - traj[i - 1]) / h;
+        else g = (traj[i + 1] - traj[i - 1]) / (2.0 * h);
+        traj[PUSH_NTRAJ + i] = g;
+    }
+}
+
+// x of goal i in the work frame: straight trajectories advance along the trajectory direction (:312-320)
+TGD double push_goal_x(const TgTask& task, double third, int i)
+{
+    if (task.push_traj_straight) return task.push_traj_offset + ((double)i * task.push_traj_spacing) * cos(third);
+    return task.push_traj_offset + (double)i * task.push_traj_spacing;
+}
+
+// goal i in the world frame: workframe_to_worldframe (base_robot_arm.py:47-60), then getQuaternionFromEuler of the rpy
+TGD void push_goal_world(const TgTask& task, double gx, double gy, double grz, double* pos, double* quat)
+{
+    double wq[4], gq[4], R[9], t[3], oq[4], rpy[3];
+    const double lp[3] = {gx, gy, 0.0}, lr[3] = {0.0, 0.0, grz};
+    quat_from_euler(task.workframe_rpy, wq);
+    quat_from_euler(lr, gq);
+    mat_from_quat(wq, R);
+    m3mulv(t, R, lp);
+    pos[0] = task.workframe_pos[0] + t[0]; pos[1] = task.workframe_pos[1] + t[1]; pos[2] = task.workframe_pos[2] + t[2];
+    quat_mul(oq, wq, gq);
+    euler_from_quat(oq, rpy);
+    quat_from_euler(rpy, quat);
+}
+
+// get_step_data (:456-569): reward against the CURRENT goal, then termination() may advance the goal.
+// goal index is updated in place; returns done.
+TGD void push_step_data(const TgTask& task, const ObjState& o, const double* tcp_quat, const double* traj, double third, int& goal,
+                        int steps, float* reward, unsigned char* done)
+{
+    const int gi = goal < PUSH_NTRAJ ? goal : PUSH_NTRAJ - 1;
+    double gp[3], gq[4];
+    push_goal_world(task, push_goal_x(task, third, gi), traj[gi], traj[PUSH_NTRAJ + gi], gp, gq);
+    const double dx = o.pos[0] - gp[0], dy = o.pos[1] - gp[1], dz = o.pos[2] - gp[2];
+    const double pos_dist = sqrt(dx * dx + dy * dy + dz * dz);
+    if (task.push_sparse_reward) *reward = pos_dist < task.push_term_dist ? 1.0f : 0.0f;
+    else {
+        const double ip = gq[0] * o.quat[0] + gq[1] * o.quat[1] + gq[2] * o.quat[2] + gq[3] * o.quat[3];
+        const double orn_dist = acos(fmin(fmax(2.0 * (ip * ip) - 1.0, -1.0), 1.0));
+        double Ro[9], Rt[9];
+        mat_from_quat(o.quat, Ro);
+        mat_from_quat(tcp_quat, Rt);
+        const double ov[3] = {Ro[0], Ro[3], Ro[6]}, tv[3] = {Rt[0], Rt[3], Rt[6]};
+        const double cos_dist = 1.0 - v3dot(ov, tv) / (sqrt(v3dot(ov, ov)) * sqrt(v3dot(tv, tv)));
+        *reward = (float)(-((1.0 * pos_dist) + (1.0 * orn_dist) + (1.0 * cos_dist)));
+    }
+    bool d = false;
+    if (pos_dist < task.push_term_dist) {
+        goal++;
+        if (goal >= PUSH_NTRAJ) d = true;
+    }
+    if (steps >= task.max_steps) d = true;
+    *done = d ? 1 : 0;
+}
+
+// get_extended_feature_array (:611-629): TCP pose and current goal pose, both in the work frame
+TGD void push_features(const TgTask& task, const double* tcp_pos, const double* tcp_quat, const double* traj, double third, int goal, float* out)
+{
+    double wp[3], wr[3];
+    world_to_work(task, tcp_pos, tcp_quat, wp, wr);
+    const int gi = goal < PUSH_NTRAJ ? (goal < 0 ? 0 : goal) : PUSH_NTRAJ - 1;
+    out[0] = (float)wp[0]; out[1] = (float)wp[1]; out[2] = (float)wp[2];
+    out[3] = (float)wr[0]; out[4] = (float)wr[1]; out[5] = (float)wr[2];
+    out[6] = (float)push_goal_x(task, third, gi); out[7] = (float)traj[gi]; out[8] = 0.0f;
+    out[9] = 0.0f; out[10] = 0.0f; out[11] = (float)traj[PUSH_NTRAJ + gi];
+}

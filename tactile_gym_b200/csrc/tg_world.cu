@@ -84,7 +84,16 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->arm.topo == TG_TOPO_CHAIN6 && cfg->arm.nb != 6) return fail(TG_EINVAL, "CHAIN6 topology needs nb == 6");
     if (cfg->arm.topo == TG_TOPO_MG400 && cfg->arm.nb != 8) return fail(TG_EINVAL, "MG400 topology needs nb == 8");
     if (cfg->arm.topo != TG_TOPO_CHAIN6 && cfg->arm.topo != TG_TOPO_MG400) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
-    if (cfg->task.task != TG_TASK_EDGE_FOLLOW && cfg->task.task != TG_TASK_OBJECT_BALANCE && cfg->task.task != TG_TASK_SURFACE_FOLLOW) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+    if (cfg->task.task != TG_TASK_EDGE_FOLLOW && cfg->task.task != TG_TASK_OBJECT_BALANCE && cfg->task.task != TG_TASK_SURFACE_FOLLOW &&
+        cfg->task.task != TG_TASK_OBJECT_PUSH) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+    if (cfg->task.task == TG_TASK_OBJECT_PUSH) {
+        if (!cfg->h_tip_hull || cfg->n_tip_hull <= 0) return fail(TG_EINVAL, "object_push needs the tip core hull (h_tip_hull)");
+        if (!(cfg->task.push_half[0] > 0 && cfg->task.push_half[1] > 0 && cfg->task.push_half[2] > 0 && cfg->task.push_inertia_per_mass[0] > 0 &&
+              cfg->task.push_inertia_per_mass[1] > 0 && cfg->task.push_inertia_per_mass[2] > 0))
+            return fail(TG_EINVAL, "object_push needs a cube with positive extents and inertia");
+        if (cfg->task.push_mode < TG_PUSH_WORK || cfg->task.push_mode > TG_PUSH_TCP_TXTYRZ) return fail(TG_EINVAL, "unknown push_mode %d", cfg->task.push_mode);
+        if (cfg->task.n_draws != 3) return fail(TG_EINVAL, "object_push consumes 3 draws per reset (init_obj_ang, obj_mass, seed | direction)");
+    }
     if (cfg->task.task == TG_TASK_OBJECT_BALANCE && !(cfg->task.obj_mass > 0 && cfg->task.obj_inertia[0] > 0 && cfg->task.obj_inertia[1] > 0 && cfg->task.obj_inertia[2] > 0))
         return fail(TG_EINVAL, "object_balance needs a free object with positive mass and inertia");
     if (cfg->task.n_draws < 0 || cfg->task.n_draws > TG_MAXDRAW) return fail(TG_EINVAL, "n_draws must be in 0..%d", TG_MAXDRAW);
@@ -155,7 +164,17 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             return rc;
         }
     }
-    if (cfg->task.task == TG_TASK_OBJECT_BALANCE) {
+    if (cfg->task.task == TG_TASK_OBJECT_PUSH) {
+        double* hull = nullptr;
+        if ((rc = dalloc(w, &b.traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.sb_traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.goal, n)) ||
+            (rc = dalloc(w, &b.sb_goal, n)) || (rc = dalloc(w, &hull, (size_t)3 * cfg->n_tip_hull))) {
+            tg_destroy(w);
+            return rc;
+        }
+        CK(cudaMemcpy(hull, cfg->h_tip_hull, sizeof(double) * 3 * cfg->n_tip_hull, cudaMemcpyHostToDevice));
+        b.hull = hull; b.n_hull = cfg->n_tip_hull;
+    }
+    if (cfg->task.task == TG_TASK_OBJECT_BALANCE || cfg->task.task == TG_TASK_OBJECT_PUSH) {
         if ((rc = dalloc(w, &b.obj, (size_t)13 * n)) || (rc = dalloc(w, &b.obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.grav, n)) ||
             (rc = dalloc(w, &b.sb_obj, (size_t)13 * n)) || (rc = dalloc(w, &b.sb_obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.sb_grav, n))) {
             tg_destroy(w);
@@ -325,6 +344,15 @@ static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint
     return TG_OK;
 }
 
+extern "C" int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat)
+{
+    if (!w) return fail(TG_EINVAL, "bad arguments");
+    if (d_feat && w->cfg.task.task != TG_TASK_OBJECT_PUSH) return fail(TG_EUNSUPPORTED, "only object_push has an extended feature");
+    w->eb.feat = d_feat;
+    w->eb.term_feat = d_feat ? d_term_feat : nullptr;
+    return TG_OK;
+}
+
 extern "C" int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream)
 {
     if (!w || !d_obs) return fail(TG_EINVAL, "bad arguments");
@@ -375,7 +403,7 @@ extern "C" int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream)
     return launch_raster(w, d_obs, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int tg_state_size(const TgWorld* w) { return w ? 2 * w->nb + 7 + 4 + 14 : 0; }
+extern "C" int tg_state_size(const TgWorld* w) { return w ? 2 * w->nb + 7 + 4 + 14 + 1 : 0; }
 
 extern "C" int tg_get_state(TgWorld* w, double* h, void* stream)
 {
@@ -398,7 +426,12 @@ extern "C" int tg_get_state(TgWorld* w, double* h, void* stream)
         for (int i = 0; i < nb; i++) { o[i] = q[(size_t)i * n + e]; o[nb + i] = qd[(size_t)i * n + e]; }
         for (int c = 0; c < 7; c++) o[2 * nb + c] = tcp[(size_t)e * 7 + c];
         o[2 * nb + 7] = emb[e]; o[2 * nb + 8] = ang[e]; o[2 * nb + 9] = steps[e]; o[2 * nb + 10] = rs[e];
-        for (int c = 0; c < 14; c++) o[2 * nb + 11 + c] = 0.0;
+        for (int c = 0; c < 15; c++) o[2 * nb + 11 + c] = 0.0;
+    }
+    if (w->eb.goal) {
+        std::vector<int> gl(n);
+        CK(cudaMemcpy(gl.data(), w->eb.goal, sizeof(int) * n, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < n; e++) h[(size_t)e * sz + 2 * nb + 25] = gl[e];
     }
     if (w->eb.obj) {
         std::vector<double> ob((size_t)13 * n), gr(n);
@@ -441,6 +474,11 @@ extern "C" int tg_set_state(TgWorld* w, const double* h, void* stream)
         }
         CK(cudaMemcpy(w->eb.obj, ob.data(), sizeof(double) * 13 * n, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(w->eb.grav, gr.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    if (w->eb.goal) {
+        std::vector<int> gl(n);
+        for (int e = 0; e < n; e++) gl[e] = (int)h[(size_t)e * sz + 2 * nb + 25];
+        CK(cudaMemcpy(w->eb.goal, gl.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     }
     return TG_OK;
 }

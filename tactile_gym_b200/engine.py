@@ -290,6 +290,118 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     return cfg, (dep, gray, mask, rest), surface_follow_draws()
 
 
+def object_push_draws(rand_init_orn, rand_obj_mass, traj_type, default_mass):
+    """ObjectPushEnv draws per reset in the reference's call order: reset_object's `uniform(-pi/32, pi/32)` (if
+    rand_init_orn) and `uniform(0.4, 0.8)` (if rand_obj_mass) (object_push_env.py:204-229), then make_goal ->
+    update_trajectory's `randint(1e8)` (simplex, :289) or `uniform(-pi/8, pi/8)` (straight, :310)."""
+
+    def draw(rng, rounds):
+        out = np.empty((rounds, 3))
+        for r in range(rounds):
+            out[r, 0] = rng.uniform(-np.pi / 32, np.pi / 32) if rand_init_orn else 0.0
+            out[r, 1] = rng.uniform(0.4, 0.8) if rand_obj_mass else default_mass
+            out[r, 2] = rng.randint(1e8) if traj_type == "simplex" else rng.uniform(-np.pi / 8, np.pi / 8)
+        return out
+
+    return draw
+
+
+def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
+    """ObjectPushEnv.__init__ (rl_envs/nonprehensile_manipulation/object_push/object_push_env.py:24-125) + BaseObjectEnv
+    as a TgConfig.  Returns (cfg, keepalive, draw_fn)."""
+    arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
+    movement_mode, traj_type = env_modes["movement_mode"], env_modes.get("traj_type", "simplex")
+    if env_modes["control_mode"] != "TCP_velocity_control":
+        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
+    if arm_type not in ("ur5", "mg400"):
+        raise ValueError("Incorrect arm type specified {}".format(arm_type))
+    if traj_type not in ("simplex", "straight"):
+        raise ValueError("Incorrect traj_type specified: {}".format(traj_type))          # :272
+    if movement_mode not in ("y", "yRz", "xyRz", "TyRz", "TxTyRz"):
+        raise ValueError("Incorrect movement_mode specified: {}".format(movement_mode))
+    typ = "right_angle"                                                                    # :58
+    if arm_type == "mg400" and sensor == "tactip":
+        raise NotImplementedError("mg400 + tactip pushes with the mini_right_angle TacTip (:84-86), which is not compiled")
+    S = int(image_size[0])
+    mj = scene.load_model_json(arm_type, sensor, typ)
+    sj = scene.load_sensor_json(sensor, typ)
+    cam = sj["types"][typ]
+    arm, control_links = scene.reduce_model(mj, sensor, cam["cam_pos"], cam["cam_rpy"])
+    cfg = L.TgConfig()
+    cfg.n_envs, cfg.lanes_per_warp, cfg.arm = n_envs, lanes_per_warp, arm
+    cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 10.0) / (1.0 / 240.0))))      # :36-38 -> 24
+    t = cfg.task
+    t.task, t.max_steps = L.TG_TASK_OBJECT_PUSH, int(max_steps)
+    idx = {"y": [1], "yRz": [1, 5], "xyRz": [0, 1, 5], "TyRz": [-1, -1], "TxTyRz": [-1, -1, -1]}[movement_mode]   # :369-454
+    t.push_mode = {"y": L.TG_PUSH_WORK_DRIVE, "yRz": L.TG_PUSH_WORK_DRIVE, "xyRz": L.TG_PUSH_WORK, "TyRz": L.TG_PUSH_TCP_TYRZ,
+                   "TxTyRz": L.TG_PUSH_TCP_TXTYRZ}[movement_mode]
+    t.act_dim = len(idx)
+    for k in range(6):
+        t.act_index[k] = idx[k] if k < len(idx) else -1
+    t.act_min, t.act_max = -0.25, 0.25
+    mv, ma = 0.01, 5.0 * (np.pi / 180)                                                          # :150-160
+    hi = [mv, mv, 0.0, 0.0, 0.0, ma]
+    for k in range(6):
+        t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
+    obj_w = obj_h = 0.08                                                                         # :54-55
+    a45 = 45 * np.pi / 180
+    if arm_type == "mg400":                                                                      # :72-88
+        lims = [(0.0, 0.3), (-0.1, 0.08), (0.0, 0.0), (0.0, 0.0), (0.0, 0.0), (-a45, a45)]
+        wd = [0.25, -0.1, obj_h / 2]
+    else:                                                                                        # :89-101
+        lims = [(0.0, 0.3), (-0.1, 0.1), (0.0, 0.0), (0.0, 0.0), (0.0, 0.0), (-a45, a45)]
+        wd = [0.55, -0.20, obj_h / 2]
+    wf_rpy = [-np.pi, 0.0, np.pi / 2]                                                            # :105
+    for k in range(3):
+        t.workframe_pos[k], t.workframe_rpy[k], t.init_rpy[k] = wd[k], wf_rpy[k], 0.0
+        t.obj_init_rpy[k] = [-np.pi, 0.0, np.pi / 2][k]                                          # :196, :210
+        t.obj_base_com[k] = 0.0
+        t.push_init_pos[k] = [wd[0], wd[1] + obj_w / 2, obj_h / 2][k]                            # :193
+    for k in range(6):
+        t.tcp_lims[k][0], t.tcp_lims[k][1] = lims[k]
+    cube = scene.load_object_json("cube")
+    box = [0.08, 0.08, 0.08]
+    stiff, damp, fric = {"tactip": (50, 100, 10.0), "digitac": (300, 100, 10.0), "digit": (50, 200, 10.0)}[sensor]   # :61-66
+    cube_mu, table_mu = 0.065, 1.0                                                               # :218, table.urdf
+    for k in range(3):
+        t.push_half[k] = box[k] / 2
+        t.push_inertia_per_mass[k] = cube["inertia_diag"][k] / cube["mass"]
+    t.push_table_z = 0.0
+    t.push_mu_table, t.push_mu_tip = cube_mu * table_mu, min(cube_mu * fric, 10.0)               # [EXT] product, clamped at 10
+    t.push_tip_k, t.push_tip_d = 1.0 / (1.0 / stiff + 1.0 / 1e18), damp + 0.1                    # [EXT] combined with bullet's defaults
+    t.push_erp, t.push_slop = 0.2, 1e-4
+    t.push_lin_damping, t.push_ang_damping = 0.04, 0.04
+    t.push_term_dist = 0.025                                                                     # :68
+    t.push_traj_spacing, t.push_traj_perturb = 0.025, 0.1                                        # :234-235
+    t.push_traj_offset = obj_w / 2 + 0.025                                                       # :290
+    t.push_traj_straight = 1 if traj_type == "straight" else 0
+    t.push_sparse_reward = 1 if env_modes.get("reward_mode", "dense") == "sparse" else 0
+    t.n_draws = 3
+    t.draw_default[0], t.draw_default[1], t.draw_default[2] = 0.0, cube["mass"], 0.0
+    dep, gray, mask = scene.load_refimg(sensor, typ, S)
+    tris = scene.load_stimulus("cube")
+    rest = scene.load_rest_pose("object_push", arm_type, sensor, typ, control_links)
+    hull_link = scene.load_tip_hull(arm_type, sensor, typ)
+    hb, hull = scene.link_points_in_body(arm, sensor + "_tip_link", hull_link)
+    if hb != arm.tcp_body:
+        raise ValueError("the tip link and the TCP must ride on the same body")
+    s = cfg.sensor
+    s.image_size, s.border_on = S, 1
+    s.fov_deg, s.near_, s.far_ = sj["fov"], sj["near"], sj["far"]
+    s.h_nodef_dep = dep.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_nodef_gray = gray.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+    prims, prim_nv = scene.merge_coplanar(tris)
+    s.n_prim = len(prims)
+    s.h_prims = prims.ctypes.data_as(C.POINTER(C.c_double))
+    s.h_prim_nv = prim_nv.ctypes.data_as(C.POINTER(C.c_int32))
+    cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
+    cfg.h_tip_hull = hull.ctypes.data_as(C.POINTER(C.c_double))
+    cfg.n_tip_hull = len(hull)
+    draw = object_push_draws(bool(env_modes.get("rand_init_orn", False)), bool(env_modes.get("rand_obj_mass", False)), traj_type, cube["mass"])
+    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv, hull), draw
+
+
 class TactileWorld:
     """N envs of one task on one device."""
 
@@ -312,6 +424,12 @@ class TactileWorld:
             self.term_obs = torch.zeros_like(self.obs)
             self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+            self.feat = self.term_feat = None
+            if cfg.task.task == L.TG_TASK_OBJECT_PUSH:
+                # extended_feature (object_push_env.py:611-629), filled by every step / reset
+                self.feat = torch.zeros((self.n, L.TG_PUSH_NFEAT), dtype=torch.float32, device=self.device)
+                self.term_feat = torch.zeros_like(self.feat)
+                L.check(self.lib.tg_bind_features(self.h, self.feat.data_ptr(), self.term_feat.data_ptr()))
         self._draw = draw_fn if draw_fn is not None else edge_follow_draws(cfg.task)
         self._rngs = [seeding.np_random(None)[0] for _ in range(self.n)]
         self._host_draws = None

@@ -232,8 +232,28 @@ def reduce_model(mj, sensor, cam_pos, cam_rpy):
         arm.cam_pos[k] = tc[k]
     for k in range(9):
         arm.cam_rot[k] = Rc.reshape(-1)[k]
-    _align_body_frames(arm)
+    A = _align_body_frames(arm)
+    # kept for link_points_in_body(): URDF link frames in their (world-aligned) body frame
+    arm._link_frames = {names[i]: (body_of_link[i], A[body_of_link[i]] @ T_body_link[i][0], A[body_of_link[i]] @ T_body_link[i][1])
+                        for i in range(n) if body_of_link[i] >= 0}
     return arm, moving
+
+
+def link_points_in_body(arm, link_name, pts):
+    """Points given in a URDF link frame (e.g. the tip core hull, assets/models/*_meshes.npz) -> the frame of the reduced
+    body that carries the link.  Returns (body index, points [K,3])."""
+    b, R, t = arm._link_frames[link_name]
+    return b, np.ascontiguousarray(np.asarray(pts, dtype=np.float64) @ R.T + t)
+
+
+def load_tip_hull(arm_type, sensor, typ):
+    d = np.load(os.path.join(ASSETS, "models", "%s_%s_%s_meshes.npz" % (arm_type, typ, sensor)))
+    return np.ascontiguousarray(d["tip_core_hull"], dtype=np.float64)
+
+
+def load_object_json(name):
+    with open(os.path.join(ASSETS, "objects", name + ".json")) as f:
+        return json.load(f)
 
 
 def _align_body_frames(arm):
@@ -269,6 +289,7 @@ def _align_body_frames(arm):
     setv(arm.tcp_rot, (A[arm.tcp_body] @ np.array(arm.tcp_rot[:]).reshape(3, 3)).reshape(-1))
     setv(arm.cam_pos, A[arm.cam_body] @ np.array(arm.cam_pos[:]))
     setv(arm.cam_rot, (A[arm.cam_body] @ np.array(arm.cam_rot[:]).reshape(3, 3)).reshape(-1))
+    return A
 
 
 def default_physics(substeps=24, gravity=(0.0, 0.0, -9.81)):

@@ -11,7 +11,7 @@ import time
 import numpy as np
 
 from . import spaces
-from .engine import TactileWorld, edge_follow_config, object_balance_config, surface_follow_config
+from .engine import TactileWorld, edge_follow_config, object_balance_config, object_push_config, surface_follow_config
 
 try:  # pragma: no cover
     from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
@@ -19,7 +19,7 @@ except Exception:  # noqa: BLE001
     _VecEnvBase = object
 
 CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": object_balance_config,
-                   "surface_follow-v0": surface_follow_config}
+                   "surface_follow-v0": surface_follow_config, "object_push-v0": object_push_config}
 
 
 class TactileVecEnv(_VecEnvBase):
@@ -32,8 +32,9 @@ class TactileVecEnv(_VecEnvBase):
             raise ValueError("env_kwargs['env_modes'] is required")
         if kw.get("show_gui") or kw.get("show_tactile"):
             raise ValueError("show_gui / show_tactile are not available in the batched engine")
-        if env_modes.get("observation_mode", "tactile") != "tactile":
-            raise NotImplementedError("only observation_mode='tactile' is built")
+        self.observation_mode = env_modes.get("observation_mode", "tactile")
+        if self.observation_mode != "tactile" and not (self.observation_mode == "tactile_and_feature" and env_id == "object_push-v0"):
+            raise NotImplementedError("observation_mode %r is not built for %s" % (self.observation_mode, env_id))
         image_size = kw.get("image_size", [64, 64])
         max_steps = kw.get("max_steps", 250)
         built = CONFIG_BUILDERS[env_id](env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp)
@@ -41,7 +42,11 @@ class TactileVecEnv(_VecEnvBase):
         self.world = TactileWorld(cfg, keep, device=device, draw_fn=draw)
         self.num_envs = n_envs
         S = int(image_size[0])
-        self.observation_space = spaces.Dict({"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)})
+        sp = {"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)}
+        self._with_feat = self.observation_mode == "tactile_and_feature"
+        if self._with_feat:
+            sp["extended_feature"] = spaces.Box(low=-np.inf, high=np.inf, shape=(12,), dtype=np.float32)
+        self.observation_space = spaces.Dict(sp)
         self.action_space = spaces.Box(low=-0.25, high=0.25, shape=(self.world.act_dim,), dtype=np.float32)
         self.metadata = {"render.modes": ["rgb_array"]}
         self._actions = None
@@ -57,10 +62,11 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_obs = self._pin_obs2[0]
         self._pin_rew = torch.zeros(n_envs, dtype=torch.float32).pin_memory()
         self._pin_done = torch.zeros(n_envs, dtype=torch.uint8).pin_memory()
+        self._pin_feat = torch.zeros((n_envs, 12), dtype=torch.float32).pin_memory() if self._with_feat else None
         if seed is not None:
             self.seed(seed)
         self.h2d_bytes_per_step = self._pin_actions.numel() * 4
-        self.d2h_bytes_per_step = self._pin_obs.numel() + self._pin_rew.numel() * 4 + self._pin_done.numel()
+        self.d2h_bytes_per_step = self._pin_obs.numel() + self._pin_rew.numel() * 4 + self._pin_done.numel() + (self._pin_feat.numel() * 4 if self._with_feat else 0)
 
     # ---------------------------------------------------------------- VecEnv API (host numpy)
     def seed(self, seed=None):
@@ -71,13 +77,21 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_obs = self._pin_obs2[self._flip]
         return self._pin_obs
 
+    def _obs_dict(self):
+        o = {"tactile": self._pin_obs.numpy()}
+        if self._with_feat:
+            o["extended_feature"] = self._pin_feat.numpy().copy()
+        return o
+
     def reset(self):
         self.world.reset()
         self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
+        if self._with_feat:
+            self._pin_feat.copy_(self.world.feat, non_blocking=True)
         self.world.torch.cuda.synchronize(self.world.device)
         self._ep_ret[:] = 0
         self._ep_len[:] = 0
-        return {"tactile": self._pin_obs.numpy()}
+        return self._obs_dict()
 
     def step_async(self, actions):
         torch = self.world.torch
@@ -87,6 +101,8 @@ class TactileVecEnv(_VecEnvBase):
         self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
         self._pin_rew.copy_(self.world.reward, non_blocking=True)
         self._pin_done.copy_(self.world.done, non_blocking=True)
+        if self._with_feat:
+            self._pin_feat.copy_(self.world.feat, non_blocking=True)
 
     def step_wait(self):
         torch = self.world.torch
@@ -98,13 +114,17 @@ class TactileVecEnv(_VecEnvBase):
         infos = [{} for _ in range(self.num_envs)]
         if done.any():
             idx = np.nonzero(done)[0]
-            term = self.world.term_obs[torch.as_tensor(idx, device=self.world.device)].cpu().numpy()
+            didx = torch.as_tensor(idx, device=self.world.device)
+            term = self.world.term_obs[didx].cpu().numpy()
+            tfeat = self.world.term_feat[didx].cpu().numpy() if self._with_feat else None
             for k, i in enumerate(idx):
                 infos[i]["terminal_observation"] = {"tactile": term[k]}
+                if self._with_feat:
+                    infos[i]["terminal_observation"]["extended_feature"] = tfeat[k]
                 infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
                 self._ep_ret[i] = 0
                 self._ep_len[i] = 0
-        return {"tactile": self._pin_obs.numpy()}, rew, done, infos
+        return self._obs_dict(), rew, done, infos
 
     def step(self, actions):
         self.step_async(actions)

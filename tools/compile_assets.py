@@ -389,6 +389,7 @@ SENSOR_CAMERAS = {
 
 OBJECTS = {
     "pole": "rl_env_assets/nonprehensile_manipulation/object_balance/pole/pole.urdf",
+    "cube": "rl_env_assets/nonprehensile_manipulation/object_push/cube/cube.urdf",
 }
 
 STIMULI = {
