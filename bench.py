@@ -38,9 +38,24 @@ WORKLOAD = "edge_follow-v0 ur5+tactip %dx%d, %d envs/GPU, max_steps %d, actions 
 
 
 def select_workload(name):
-    """default: BASELINE config 2 (the one the metric is quoted on).  'balance': config 5 per GPU
-    (object_balance-v0 ur5+tactip 256x256, 16384 envs over 8 GPUs = 2048 envs/GPU) - for the profiles, not the driver."""
+    """default: BASELINE config 2 (the one the metric is quoted on).  The others are for the profiles, not the driver:
+    'balance': config 5 per GPU (object_balance-v0 ur5+tactip 256x256, 16384 envs over 8 GPUs = 2048 envs/GPU);
+    'surface': config 3 per GPU (surface_follow-v0 ur5+digit 128x128, 8192 envs over 8 GPUs = 1024 envs/GPU);
+    'push': config 4 (object_push-v0 mg400+digitac 128x128, 8192 envs)."""
     global MODES, ENV_ID, N_ENVS, IMG, MAX_STEPS, ALG_BYTES, WORKLOAD
+    if name == "surface":
+        MODES = {"movement_mode": "xyzRxRy", "control_mode": "TCP_velocity_control", "noise_mode": "simplex", "observation_mode": "tactile",
+                 "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "digit"}
+        ENV_ID, N_ENVS, IMG, MAX_STEPS = "surface_follow-v0", 1024, 128, 200
+        ALG_BYTES = IMG * IMG + 64 + 64 * 64 * 4      # SURVEY.md 8(d), config 3: + the env's 64x64 f32 heights
+        WORKLOAD = "surface_follow-v0 ur5+digit %dx%d, %d envs/GPU, max_steps %d, actions iid U(-0.25,0.25) seed 0" % (IMG, IMG, N_ENVS, MAX_STEPS)
+    if name == "push":
+        MODES = {"movement_mode": "TyRz", "control_mode": "TCP_velocity_control", "rand_init_orn": False, "rand_obj_mass": False,
+                 "traj_type": "simplex", "observation_mode": "tactile_and_feature", "reward_mode": "dense", "arm_type": "mg400",
+                 "tactile_sensor_name": "digitac"}
+        ENV_ID, N_ENVS, IMG, MAX_STEPS = "object_push-v0", 8192, 128, 1000
+        ALG_BYTES = IMG * IMG + 92 + 48               # SURVEY.md 8(d), config 4: + 12 f32 features
+        WORKLOAD = "object_push-v0 mg400+digitac %dx%d, %d envs/GPU, max_steps %d, actions iid U(-0.25,0.25) seed 0" % (IMG, IMG, N_ENVS, MAX_STEPS)
     if name == "balance":
         MODES = {"movement_mode": "xy", "control_mode": "TCP_velocity_control", "object_mode": "pole", "rand_gravity": True,
                  "rand_embed_dist": True, "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5",
@@ -95,7 +110,14 @@ def make_oracle_env(seed):
 
     if ENV_ID == "object_balance-v0":
         return O.ObjectBalanceOracle(image_size=IMG, max_steps=MAX_STEPS, seed=seed)
+    if ENV_ID == "surface_follow-v0":
+        return O.SurfaceFollowOracle(image_size=IMG, max_steps=MAX_STEPS, seed=seed)
+    if ENV_ID == "object_push-v0":
+        return O.ObjectPushOracle(image_size=IMG, max_steps=MAX_STEPS, seed=seed)
     return O.EdgeFollowOracle(image_size=IMG, max_steps=MAX_STEPS, seed=seed)
+
+
+ACT_DIM = {"edge_follow-v0": 2, "object_balance-v0": 2, "surface_follow-v0": 3, "object_push-v0": 2}
 
 
 def cpu_port_rate(seconds, seed=0):
@@ -107,7 +129,7 @@ def cpu_port_rate(seconds, seed=0):
     rng = np.random.RandomState(seed)
     n, t0 = 0, time.perf_counter()
     while True:
-        _, _, done, _ = env.step(rng.uniform(-0.25, 0.25, 2).astype(np.float32))
+        _, _, done, _ = env.step(rng.uniform(-0.25, 0.25, ACT_DIM[ENV_ID]).astype(np.float32))
         n += 1
         if done:
             env.reset()
@@ -137,7 +159,7 @@ def _cpu_worker(seconds):
     env, rng = _WORKER_ENV
     n, t0 = 0, time.perf_counter()
     while True:
-        _, _, done, _ = env.step(rng.uniform(-0.25, 0.25, 2).astype(np.float32))
+        _, _, done, _ = env.step(rng.uniform(-0.25, 0.25, ACT_DIM[ENV_ID]).astype(np.float32))
         n += 1
         if done:
             env.reset()
@@ -186,7 +208,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="edge", choices=["edge", "balance"])
+    ap.add_argument("--workload", default="edge", choices=["edge", "balance", "surface", "push"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (0: the workload's)")
     ap.add_argument("--phases", default="staggered", choices=["staggered", "sync"],
                     help="staggered: episode phases uniform in [0, max_steps) as in a long-running job, so every timed "
@@ -226,7 +248,7 @@ def main():
     dev = w.device
     if args.phases == "staggered":
         st = w.get_state()
-        st[:, st.shape[1] - 14 - 2] = np.random.RandomState(1000 + rank).randint(0, MAX_STEPS, size=n)   # the `steps` field
+        st[:, 2 * w.nb + 9] = np.random.RandomState(1000 + rank).randint(0, MAX_STEPS, size=n)   # the `steps` field
         w.set_state(st)
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
     acts = (torch.rand((W + K, n, w.act_dim), device=dev, generator=gen) - 0.5) * 0.5
@@ -311,7 +333,7 @@ def main():
             "e2e": {"value": n * world * Ke / (t_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step,
                     "d2h_bytes_per_step": env.d2h_bytes_per_step, "steps": Ke},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "raster_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"kernel": "raster_hf_kernel" if ENV_ID.startswith("surface") else "raster_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * ALG_BYTES, "launch_ms": t_raster},
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -639,7 +639,8 @@ class OrPush(C.Structure):
         ("half", C.c_double * 3), ("table_z", C.c_double), ("mu_table", C.c_double), ("mu_tip", C.c_double),
         ("tip_k", C.c_double), ("tip_d", C.c_double), ("erp", C.c_double), ("slop", C.c_double),
         ("lin_damping", C.c_double), ("ang_damping", C.c_double), ("tip_link", C.c_int), ("n_hull", C.c_int),
-        ("hull", C.POINTER(C.c_double)), ("n_contacts", C.c_int), ("n_iters", C.c_int),
+        ("hull", C.POINTER(C.c_double)), ("warmstart", C.c_double), ("ws_n", C.c_int), ("ws_feature", C.c_int * OR_MAXC),
+        ("ws_impulse", (C.c_double * 3) * OR_MAXC), ("n_contacts", C.c_int), ("n_iters", C.c_int),
         ("normal_impulse", C.c_double * OR_MAXC), ("contact_pos", (C.c_double * 3) * OR_MAXC),
     ]
 
@@ -703,6 +704,7 @@ class ObjectPushOracle:
         p.tip_k, p.tip_d = 1.0 / (1.0 / dyn[0] + 1.0 / 1e18), dyn[1] + 0.1
         p.erp, p.slop = 0.2, 1e-4
         p.lin_damping, p.ang_damping = 0.04, 0.04
+        p.warmstart, p.ws_n = 0.0, 0   # warm starting off (the device path has none yet)
         p.tip_link = self.m._names.index(sensor + "_tip_link")
         p.n_hull = len(self.hull)
         p.hull = self.hull.ctypes.data_as(C.POINTER(C.c_double))
@@ -766,6 +768,7 @@ class ObjectPushOracle:
             o.pos[c] = self.init_obj_pos[c]; o.vel[c] = 0; o.omg[c] = 0
         for c in range(4):
             o.quat[c] = q0[c]
+        self.p.ws_n = 0            # resetBasePositionAndOrientation: the manifolds start empty
         self.update_trajectory(third)
         self.targ = -1
         self.update_goal()

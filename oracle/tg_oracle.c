@@ -1066,6 +1066,7 @@ typedef struct {
     double n[3];         /* unit normal: out of the cube face towards the tip / up from the table */
     double pa[3], pb[3]; /* contact point on the arm (tip contacts only); contact point on the cube */
     double dist, mu, cfm, erp;
+    int feature;         /* identity across substeps: cube vertex v -> v, hull vertex i -> 8 + i (warm starting) */
 } PushContact;
 
 static long long qkey(double x) { return llrint(x * 1e9); } /* comparisons on a 1 nm grid: ties break by index */
@@ -1103,7 +1104,7 @@ static int push_contacts(const OrModel* m, const Kin* k, const OrObject* o, cons
         if (dist > P->slop) continue;
         PushContact* c = &C[nc++];
         c->on_arm = 0; v3set(c->n, 0, 0, 1); v3cpy(c->pb, w); v3cpy(c->pa, w);
-        c->dist = dist; c->mu = P->mu_table; c->cfm = 0.0; c->erp = P->erp;
+        c->dist = dist; c->mu = P->mu_table; c->cfm = 0.0; c->erp = P->erp; c->feature = v;
     }
     /* tip core hull <-> cube */
     const int tl = P->tip_link;
@@ -1147,7 +1148,7 @@ static int push_contacts(const OrModel* m, const Kin* k, const OrObject* o, cons
             m3mulv(c->n, Rb, ln);
             m3mulv(w, k->Rl[tl], P->hull + 3 * sel[j]); v3add(c->pa, k->pl[tl], w);
             for (int q = 0; q < 3; q++) c->pb[q] = c->pa[q] - sd * c->n[q];
-            c->dist = sd; c->mu = P->mu_tip;
+            c->dist = sd; c->mu = P->mu_tip; c->feature = 8 + sel[j];
             c->cfm = (1.0 / (dtk < 2.2204460492503131e-16 ? 2.2204460492503131e-16 : dtk)) / m->dt;
             c->erp = (m->dt * P->tip_k) / (dtk < 2.2204460492503131e-16 ? 2.2204460492503131e-16 : dtk);
         }
@@ -1261,10 +1262,18 @@ void or_step_sim_push(const OrModel* m, OrState* s, OrObject* o, OrPush* P)
                 rhs[r] = -rel * dinv[r];
                 cfmr[r] = 0.0;
             }
+            /* [EXT] warm starting: the impulse the same feature ended the previous stepSimulation with, times
+             * m_warmstartingFactor (0.85) */
             applied[r] = 0.0;
+            for (int w = 0; w < P->ws_n; w++) if (P->ws_feature[w] == ct->feature) applied[r] = P->warmstart * P->ws_impulse[w][q];
         }
     }
     double dv[OR_MAXD] = {0}, dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
+    for (int r = 0; r < 3 * nc; r++) {
+        if (applied[r] == 0.0) continue;
+        for (int d = 0; d < n; d++) dv[d] += ur[r][d] * applied[r];
+        for (int q = 0; q < 3; q++) { dvl[q] += ul[r][q] * applied[r]; dva[q] += ua[r][q] * applied[r]; }
+    }
     int it = 0;
     for (; it < m->solver_iters; it++) {
         double resid = 0;
@@ -1315,6 +1324,8 @@ void or_step_sim_push(const OrModel* m, OrState* s, OrObject* o, OrPush* P)
         }
         if (resid <= m->solver_residual_threshold) { it++; break; }
     }
+    P->ws_n = nc;
+    for (int c = 0; c < nc; c++) { P->ws_feature[c] = C[c].feature; for (int q = 0; q < 3; q++) P->ws_impulse[c][q] = applied[3 * c + q]; }
     P->n_contacts = nc; P->n_iters = it;
     for (int c = 0; c < OR_MAXC; c++) {
         P->normal_impulse[c] = c < nc ? applied[3 * c] : 0.0;

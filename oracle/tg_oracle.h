@@ -177,6 +177,11 @@ typedef struct {
     int tip_link;            /* bullet link index owning the hull */
     int n_hull;
     const double* hull;      /* [n_hull][3], tip LINK frame */
+    /* warm starting [EXT]: impulses (normal, friction 1, friction 2) the contact features ended the previous
+     * stepSimulation with; part of the env state */
+    double warmstart;        /* m_warmstartingFactor 0.85; 0 = off */
+    int ws_n, ws_feature[OR_MAXC];
+    double ws_impulse[OR_MAXC][3];
     /* diagnostics of the last substep */
     int n_contacts, n_iters;
     double normal_impulse[OR_MAXC];

@@ -632,18 +632,30 @@ TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
 }
 
 // autoreset: 1 = finished envs start their next episode inside this launch (VecEnv semantics)
-template <class T>
+// TASK is a template parameter so that each task's step is its own lean kernel (with all four tasks behind run-time
+// branches the edge_follow step was 45 % slower than alone: registers, instruction cache).
+// object_push runs PUSH_BLOCK envs per block, all lanes active, its constraint rows staged in dynamic shared memory, and
+// has no standby blocks: its episodes are long and its reset short, so each step thread advances its own env's standby
+// slot by one quantum after the step.
+template <class T, int TASK>
 __global__ void __launch_bounds__(128)
 step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
             EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
 {
     constexpr int NB = T::NB;
-    if ((int)blockIdx.x >= b.step_blocks) {
-        standby_role<T>(arm, ph, task, b, b.step_blocks, false);
-        return;
+    constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, push = TASK == TG_TASK_OBJECT_PUSH, surface = TASK == TG_TASK_SURFACE_FOLLOW;
+    int e;
+    if (push) {
+        e = blockIdx.x * blockDim.x + threadIdx.x;
+        if (e >= b.n) return;
+    } else {
+        if ((int)blockIdx.x >= b.step_blocks) {
+            standby_role<T>(arm, ph, task, b, b.step_blocks, false);
+            return;
+        }
+        e = env_index(b);
+        if (e < 0) return;
     }
-    const int e = env_index(b);
-    if (e < 0) return;
     double q[NB], qd[NB];
 #pragma unroll
     for (int i = 0; i < NB; i++) { q[i] = b.q[(size_t)i * b.n + e]; qd[i] = b.qd[(size_t)i * b.n + e]; }
@@ -667,12 +679,12 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
                 for (int s = 0; s < 6; s++) if (task.act_index[kk] == s) enc[s] = a;
             }
-        if (task.task == TG_TASK_SURFACE_FOLLOW) {
+        if (surface) {
             // SurfaceFollowAutoEnv.encode_actions (surface_follow_auto_env.py:27-57): constant drive towards the goal
             const double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)b.hf_cur[e]) * SURF_META;
             enc[0] = meta[1] * task.surf_drive; enc[1] = meta[2] * task.surf_drive;
         }
-        if (task.task == TG_TASK_OBJECT_PUSH) {
+        if (push) {
             // ObjectPushEnv.encode_actions (object_push_env.py:369-454)
             if (task.push_mode == TG_PUSH_WORK_DRIVE) enc[0] = task.act_max;
             if (task.push_mode == TG_PUSH_TCP_TYRZ || task.push_mode == TG_PUSH_TCP_TXTYRZ) {
@@ -732,8 +744,6 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
         for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;
     }
-    const bool balance = task.task == TG_TASK_OBJECT_BALANCE;
-    const bool push = task.task == TG_TASK_OBJECT_PUSH;
     ObjState ob;
     {
         double sc[NB][2]; // (sin q, cos q): exact here, then advanced by the trig identity after every substep
@@ -741,8 +751,9 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
         if (push) {
             obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
+            extern __shared__ double push_rows[]; // [PushLayout<T>::SLOTS][blockDim.x]
 #pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob);
+            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, push_rows + threadIdx.x, blockDim.x);
             obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
         } else if (balance) {
             obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);
@@ -776,7 +787,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     } else if (balance) {
         balance_step_data(task, ob, b.embed[e], steps, &r, &d);
         obj_stim(task, ob, b.stim + (size_t)e * 12); // the pole moves: the raster needs its pose every step
-    } else if (task.task == TG_TASK_SURFACE_FOLLOW) {
+    } else if (surface) {
         const size_t hb = (size_t)e * 2 + (size_t)b.hf_cur[e];
         surface_step_data(task, b.height + hb * SURF_PTS, b.hf_meta + hb * SURF_META, tp, tq, steps, &r, &d);
     } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
@@ -795,6 +806,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
         for (int c = 0; c < 4; c++) b.tcp[(size_t)e * 7 + 3 + c] = tq[c];
     }
+    if (push && b.pipeline) standby_work<T>(arm, ph, task, b, e, false); // one quantum of this env's next-episode rebuild, if due
 }
 
 // explicit reset of the masked envs.  With the pipeline on, an env's standby IS its next episode: take it and

@@ -184,158 +184,216 @@ __device__ __noinline__ int push_contacts(const TgArm& arm, const TgTask& task, 
     return nc;
 }
 
-// Robot.step_sim() with the cube in the world.  Returns the number of PGS sweeps.
+// ---- shared-memory staging of one env's constraint rows -------------------------------------------------------------
+// A substep's rows are read ~55 times (PGS sweeps) each: they live in shared memory, one COLUMN per env
+// (slot s of thread t at sm[s * stride + t]: consecutive threads touch consecutive doubles, no bank conflicts).
+// ncu of the first version, which kept them in per-thread local memory: 74 % of the stall samples on local loads, L1 hit
+// rate 18 %, 15.6 GB of DRAM reads per launch (profiles/r01_push_step_v0.md).
+//   motors      : A = M^-1 upper triangle NB (NB + 1) / 2, then rhs / dinv / applied per joint
+//   table rows  : 3 per contact x 4 contacts: ja(3) ua(3) rhs dinv diagc applied  (normal +z, fixed friction basis)
+//   tip rows    : 3 per contact x 4 contacts: dir(3) ja(3) ua(3) jr(NA) ur(NB) rhs dinv diagc applied
+// with NA = joints between the base and the tip (the MG400's three slaved joints are not among them).
+template <class T>
+struct PushLayout {
+    static constexpr int NB = T::NB;
+    static constexpr int NA = NB == 8 ? 5 : NB;   // TopoMG400: chain 0-1-2-3-4 carries the tip; TopoChain6: all six
+    static constexpr int TRI = NB * (NB + 1) / 2;
+    static constexpr int MOT = TRI;               // + 3 * NB
+    static constexpr int TAB = MOT + 3 * NB;      // 12 rows x 10
+    static constexpr int TAB_ROW = 10;
+    static constexpr int TIP = TAB + 12 * TAB_ROW;
+    static constexpr int TIP_ROW = 13 + NA + NB;
+    static constexpr int SLOTS = TIP + 12 * TIP_ROW;
+    __host__ __device__ static constexpr int tri(int i, int j) { return i <= j ? i * NB - i * (i - 1) / 2 + (j - i) : j * NB - j * (j - 1) / 2 + (i - j); }
+};
+#define PUSH_BLOCK 56 // envs (threads) per block: 56 x 492 slots x 8 B = 220 KB of the 227 KB a block may have, one block per SM
+
+// Robot.step_sim() with the cube in the world.  `sm` = this thread's column of the block's row store, `ss` its stride.
+// Returns the number of PGS sweeps.
 template <class T>
 __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const double* __restrict__ hull, int n_hull,
-                                         double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot, ObjState& o)
+                                         double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot, ObjState& o,
+                                         double* __restrict__ sm, const int ss)
 {
-    constexpr int NB = T::NB;
+    using LY = PushLayout<T>;
+    constexpr int NB = T::NB, NA = LY::NA;
     constexpr double EPS = 2.2204460492503131e-16;
-    double A[NB][NB];
-    robot_pre<T>(arm, ph, q, qd, sc, A);
-
-    Kin<NB> k;
-    fk_sc<T>(arm, sc, k);
-    double Rb[9];
-    mat_from_quat(o.quat, Rb);
+#define SM(slot) sm[(slot) * ss]
     PushContact C[PUSH_MAXC];
-    const int nc = push_contacts<T>(arm, task, hull, n_hull, k, o, Rb, C);
-
-    // cube: unconstrained velocity update about its COM (gravity, [EXT] multibody base damping, gyroscopic term)
-    double Iinv[3];
+    int nc, ntab = 0;
+    double Rb[9], Iinv[3];
     const double mass = o.mass, minv = 1.0 / mass;
-#pragma unroll
-    for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / (task.push_inertia_per_mass[c] * mass);
-    {
-        double wl[3], Iw[3], gy[3], al[3], aw[3];
-        m3tmulv(wl, Rb, o.omg);
-#pragma unroll
-        for (int c = 0; c < 3; c++) Iw[c] = task.push_inertia_per_mass[c] * mass * wl[c];
-        v3cross(gy, wl, Iw);
-        const double ka = task.push_ang_damping * (1.0 + sqrt(v3dot(o.omg, o.omg))), kl = task.push_lin_damping * (1.0 + sqrt(v3dot(o.vel, o.vel)));
-#pragma unroll
-        for (int c = 0; c < 3; c++) al[c] = (-Iw[c] * ka - gy[c]) * Iinv[c];
-        m3mulv(aw, Rb, al);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const double f = ph.gravity[c] * mass - mass * o.vel[c] * kl;
-            o.vel[c] += ph.dt * f / mass;
-            o.omg[c] += ph.dt * aw[c];
-        }
-    }
-
-    // motor rows (registers), as in substep()
-    double mrhs[NB], mdinv[NB], mapplied[NB], dv[NB];
     const double lim_m = mot.max_force * ph.dt;
+    {
+        double A[NB][NB];
+        robot_pre<T>(arm, ph, q, qd, sc, A);
+        // motor rows, as in substep(): J = e_i, response column A[:, i]
 #pragma unroll
-    for (int i = 0; i < NB; i++) {
-        const double denom = A[i][i];
-        mdinv[i] = denom > EPS ? 1.0 / denom : 0.0;
-        const double v = qd[i];
-        const double pos_stab = mot.mode == 1 ? mot.kp * ((mot.target_pos[i] - q[i]) / ph.dt) : 0.0;
-        const double rhs_v = pos_stab + v + mot.kd * (mot.target_vel[i] - v);
-        mrhs[i] = (rhs_v - v) * mdinv[i];
-        mapplied[i] = 0; dv[i] = 0;
-    }
-
-    // contact rows (local memory): row 3c normal, 3c+1 / 3c+2 friction.  The arm part exists for tip contacts only.
-    double jr[3 * PUSH_MAXC][NB], ur[3 * PUSH_MAXC][NB];
-    double jl[3 * PUSH_MAXC][3], ja[3 * PUSH_MAXC][3], ua[3 * PUSH_MAXC][3];
-    double diag[3 * PUSH_MAXC], dinv[3 * PUSH_MAXC], rhs[3 * PUSH_MAXC], applied[3 * PUSH_MAXC], cfm[PUSH_MAXC], cfmr[PUSH_MAXC], mu[PUSH_MAXC];
-    const double dtk = fmax(ph.dt * task.push_tip_k + task.push_tip_d, EPS);
-#pragma unroll 1
-    for (int c = 0; c < nc; c++) {
-        const PushContact& ct = C[c];
-        const bool on_arm = ct.on_arm != 0;
-        const double erp = on_arm ? (ph.dt * task.push_tip_k) / dtk : task.push_erp;
-        cfm[c] = on_arm ? (1.0 / dtk) / ph.dt : 0.0;
-        mu[c] = on_arm ? task.push_mu_tip : task.push_mu_table;
-        double lin[NB][3]; // velocity of the arm's contact point per unit joint rate
-        double va[3] = {0, 0, 0}, vb[3], rb[3], vrel[3];
+        for (int i = 0; i < NB; i++) {
 #pragma unroll
-        for (int j = 0; j < NB; j++) {
-            const double r[3] = {ct.pa[0] - k.p[j][0], ct.pa[1] - k.p[j][1], ct.pa[2] - k.p[j][2]};
-            v3cross(lin[j], k.a[j], r);
-            const bool use = on_arm && tip_ancestor<T>(arm.tcp_body, j);
-#pragma unroll
-            for (int x = 0; x < 3; x++) { lin[j][x] = use ? lin[j][x] : 0.0; va[x] += qd[j] * lin[j][x]; }
+            for (int j = i; j < NB; j++) SM(LY::tri(i, j)) = A[i][j];
+            const double denom = A[i][i];
+            const double mdinv = denom > EPS ? 1.0 / denom : 0.0;
+            const double v = qd[i];
+            const double pos_stab = mot.mode == 1 ? mot.kp * ((mot.target_pos[i] - q[i]) / ph.dt) : 0.0;
+            const double rhs_v = pos_stab + v + mot.kd * (mot.target_vel[i] - v);
+            SM(LY::MOT + 3 * i) = (rhs_v - v) * mdinv;
+            SM(LY::MOT + 3 * i + 1) = mdinv;
+            SM(LY::MOT + 3 * i + 2) = 0.0;
         }
+
+        Kin<NB> k;
+        fk_sc<T>(arm, sc, k);
+        mat_from_quat(o.quat, Rb);
+        nc = push_contacts<T>(arm, task, hull, n_hull, k, o, Rb, C);
+
+        // cube: unconstrained velocity update about its COM (gravity, [EXT] multibody base damping, gyroscopic term)
+#pragma unroll
+        for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / (task.push_inertia_per_mass[c] * mass);
         {
-            double t[3];
+            double wl[3], Iw[3], gy[3], al[3], aw[3];
+            m3tmulv(wl, Rb, o.omg);
 #pragma unroll
-            for (int x = 0; x < 3; x++) rb[x] = ct.pb[x] - o.pos[x];
-            v3cross(t, o.omg, rb);
+            for (int c = 0; c < 3; c++) Iw[c] = task.push_inertia_per_mass[c] * mass * wl[c];
+            v3cross(gy, wl, Iw);
+            const double ka = task.push_ang_damping * (1.0 + sqrt(v3dot(o.omg, o.omg))), kl = task.push_lin_damping * (1.0 + sqrt(v3dot(o.vel, o.vel)));
 #pragma unroll
-            for (int x = 0; x < 3; x++) { vb[x] = o.vel[x] + t[x]; vrel[x] = on_arm ? va[x] - vb[x] : vb[x]; }
+            for (int c = 0; c < 3; c++) al[c] = (-Iw[c] * ka - gy[c]) * Iinv[c];
+            m3mulv(aw, Rb, al);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double f = ph.gravity[c] * mass - mass * o.vel[c] * kl;
+                o.vel[c] += ph.dt * f / mass;
+                o.omg[c] += ph.dt * aw[c];
+            }
         }
-        // friction basis: fixed per normal (see oracle/tg_oracle.c: the velocity-aligned first direction is not restated)
-        double dir[3][3];
+
+        // contact rows: row 3c normal, 3c+1 / 3c+2 friction; table contacts come first
+        const double dtk = fmax(ph.dt * task.push_tip_k + task.push_tip_d, EPS);
+#pragma unroll 1
+        for (int c = 0; c < nc; c++) {
+            const PushContact& ct = C[c];
+            const bool on_arm = ct.on_arm != 0;
+            if (!on_arm) ntab = c + 1;
+            const double erp = on_arm ? (ph.dt * task.push_tip_k) / dtk : task.push_erp;
+            const double cfm = on_arm ? (1.0 / dtk) / ph.dt : 0.0;
+            double lin[NA][3]; // velocity of the arm's contact point per unit rate of the joints that carry the tip
+            double va[3] = {0, 0, 0}, vb[3], rb[3], vrel[3];
+            if (on_arm) {
 #pragma unroll
-        for (int x = 0; x < 3; x++) dir[0][x] = ct.n[x];
-        plane_space1(ct.n, dir[1], dir[2]);
-        const double scb = on_arm ? -1.0 : 1.0; // the cube is the second body of a tip contact
+                for (int j = 0; j < NA; j++) {
+                    const double r[3] = {ct.pa[0] - k.p[j][0], ct.pa[1] - k.p[j][1], ct.pa[2] - k.p[j][2]};
+                    v3cross(lin[j], k.a[j], r);
 #pragma unroll
-        for (int qq = 0; qq < 3; qq++) {
-            const int r = 3 * c + qq;
-            double den = 0;
-#pragma unroll
-            for (int j = 0; j < NB; j++) jr[r][j] = v3dot(dir[qq], lin[j]);
-#pragma unroll
-            for (int j = 0; j < NB; j++) {
-                double u = 0;
-#pragma unroll
-                for (int e = 0; e < NB; e++) u += A[j][e] * jr[r][e];
-                ur[r][j] = u;
-                den += jr[r][j] * u;
+                    for (int x = 0; x < 3; x++) va[x] += qd[j] * lin[j][x];
+                }
             }
-            double a[3], bq[3];
-            v3cross(ja[r], rb, dir[qq]);
+            {
+                double t[3];
 #pragma unroll
-            for (int x = 0; x < 3; x++) { jl[r][x] = scb * dir[qq][x]; ja[r][x] *= scb; }
-            m3tmulv(a, Rb, ja[r]);
+                for (int x = 0; x < 3; x++) rb[x] = ct.pb[x] - o.pos[x];
+                v3cross(t, o.omg, rb);
 #pragma unroll
-            for (int x = 0; x < 3; x++) bq[x] = a[x] * Iinv[x];
-            m3mulv(ua[r], Rb, bq);
-            den += v3dot(jl[r], jl[r]) * minv + v3dot(ja[r], ua[r]);
-            diag[r] = den;
-            const double rel = v3dot(dir[qq], vrel);
-            if (qq == 0) {
-                dinv[r] = 1.0 / (den + cfm[c]);
-                const double positional = ct.dist > 0 ? 0.0 : -ct.dist * erp / ph.dt;
-                const double velerr = -rel - (ct.dist > 0 ? ct.dist / ph.dt : 0.0);
-                rhs[r] = (positional + velerr) * dinv[r];
-                cfmr[c] = cfm[c] * dinv[r];
-            } else {
-                dinv[r] = den > EPS ? 1.0 / den : 0.0;
-                rhs[r] = -rel * dinv[r];
+                for (int x = 0; x < 3; x++) { vb[x] = o.vel[x] + t[x]; vrel[x] = on_arm ? va[x] - vb[x] : vb[x]; }
             }
-            applied[r] = 0.0;
+            // friction basis: fixed per normal (see oracle/tg_oracle.c: the velocity-aligned first direction is not restated)
+            double dir[3][3];
+#pragma unroll
+            for (int x = 0; x < 3; x++) dir[0][x] = ct.n[x];
+            plane_space1(ct.n, dir[1], dir[2]);
+            const double scb = on_arm ? -1.0 : 1.0; // the cube is the second body of a tip contact
+#pragma unroll
+            for (int qq = 0; qq < 3; qq++) {
+                const int base = on_arm ? LY::TIP + (3 * (c - ntab) + qq) * LY::TIP_ROW : LY::TAB + (3 * c + qq) * LY::TAB_ROW;
+                const int o_ja = on_arm ? 3 : 0, o_sc = on_arm ? 9 + NA + NB : 6;
+                double den = 0, ja[3], ua[3], a[3], bq[3];
+                if (on_arm) {
+                    double jr[NA];
+#pragma unroll
+                    for (int j = 0; j < NA; j++) { jr[j] = v3dot(dir[qq], lin[j]); SM(base + 9 + j) = jr[j]; }
+#pragma unroll
+                    for (int j = 0; j < NB; j++) {
+                        double u = 0;
+#pragma unroll
+                        for (int e = 0; e < NA; e++) u += A[j][e] * jr[e];
+                        SM(base + 9 + NA + j) = u;
+                        if (j < NA) den += jr[j < NA ? j : 0] * u;
+                    }
+#pragma unroll
+                    for (int x = 0; x < 3; x++) SM(base + x) = dir[qq][x];
+                }
+                v3cross(ja, rb, dir[qq]);
+#pragma unroll
+                for (int x = 0; x < 3; x++) ja[x] *= scb;
+                m3tmulv(a, Rb, ja);
+#pragma unroll
+                for (int x = 0; x < 3; x++) bq[x] = a[x] * Iinv[x];
+                m3mulv(ua, Rb, bq);
+#pragma unroll
+                for (int x = 0; x < 3; x++) { SM(base + o_ja + x) = ja[x]; SM(base + o_ja + 3 + x) = ua[x]; }
+                den += v3dot(dir[qq], dir[qq]) * minv + v3dot(ja, ua);
+                const double rel = v3dot(dir[qq], vrel);
+                double dinv, rhs, diagc;
+                if (qq == 0) {
+                    dinv = 1.0 / (den + cfm);
+                    const double positional = ct.dist > 0 ? 0.0 : -ct.dist * erp / ph.dt;
+                    const double velerr = -rel - (ct.dist > 0 ? ct.dist / ph.dt : 0.0);
+                    rhs = (positional + velerr) * dinv;
+                    diagc = den + cfm;
+                } else {
+                    dinv = den > EPS ? 1.0 / den : 0.0;
+                    rhs = -rel * dinv;
+                    diagc = den;
+                }
+                SM(base + o_sc) = rhs; SM(base + o_sc + 1) = dinv; SM(base + o_sc + 2) = diagc; SM(base + o_sc + 3) = 0.0;
+            }
         }
     }
+    const int ntip = nc - ntab;
+    const double cfm_tip = (1.0 / fmax(ph.dt * task.push_tip_k + task.push_tip_d, EPS)) / ph.dt;
 
-    double dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
-    auto row_m = [&](int r, double& resid) {
-        double delta = mrhs[r] - dv[r] * mdinv[r];
-        const double sum = mapplied[r] + delta;
-        const bool lo = sum < -lim_m, hi = sum > lim_m;
-        delta = lo ? (-lim_m - mapplied[r]) : (hi ? (lim_m - mapplied[r]) : delta);
-        mapplied[r] = lo ? -lim_m : (hi ? lim_m : sum);
+    double dv[NB], dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < NB; i++) dv[i] += A[r][i] * delta;
-        const double dvel = delta * A[r][r];
+    for (int i = 0; i < NB; i++) dv[i] = 0;
+    auto row_m = [&](int r, double& resid) {
+        double Ar[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) Ar[i] = SM(LY::tri(r, i));
+        const double mrhs = SM(LY::MOT + 3 * r), mdinv = SM(LY::MOT + 3 * r + 1), mapp = SM(LY::MOT + 3 * r + 2);
+        double delta = mrhs - dv[r] * mdinv;
+        const double sum = mapp + delta;
+        const bool lo = sum < -lim_m, hi = sum > lim_m;
+        delta = lo ? (-lim_m - mapp) : (hi ? (lim_m - mapp) : delta);
+        SM(LY::MOT + 3 * r + 2) = lo ? -lim_m : (hi ? lim_m : sum);
+#pragma unroll
+        for (int i = 0; i < NB; i++) dv[i] += Ar[i] * delta;
+        const double dvel = delta * Ar[r];
         resid = fmax(resid, dvel * dvel);
     };
-    auto row_dot = [&](int r) {
-        double dot = v3dot(jl[r], dvl) + v3dot(ja[r], dva);
-#pragma unroll
-        for (int d = 0; d < NB; d++) dot += jr[r][d] * dv[d];
-        return dot;
+    // table rows: directions are (0,0,1), (0,-1,0), (1,0,0) = btPlaneSpace1 of +z; the cube is the first body
+    auto tab_dot = [&](int base, int qq) {
+        const double lin = qq == 0 ? dvl[2] : (qq == 1 ? -dvl[1] : dvl[0]);
+        return lin + SM(base) * dva[0] + SM(base + 1) * dva[1] + SM(base + 2) * dva[2];
     };
-    auto row_apply = [&](int r, double delta) {
+    auto tab_apply = [&](int base, int qq, double delta) {
+        const double d = delta * minv;
+        if (qq == 0) dvl[2] += d; else if (qq == 1) dvl[1] -= d; else dvl[0] += d;
+        dva[0] += SM(base + 3) * delta; dva[1] += SM(base + 4) * delta; dva[2] += SM(base + 5) * delta;
+    };
+    auto tip_dot = [&](int base) {
+        double dot = -(SM(base) * dvl[0] + SM(base + 1) * dvl[1] + SM(base + 2) * dvl[2]);
+        dot += SM(base + 3) * dva[0] + SM(base + 4) * dva[1] + SM(base + 5) * dva[2];
+        double da = 0;
 #pragma unroll
-        for (int d = 0; d < NB; d++) dv[d] += ur[r][d] * delta;
+        for (int j = 0; j < NA; j++) da += SM(base + 9 + j) * dv[j];
+        return dot + da;
+    };
+    auto tip_apply = [&](int base, double delta) {
+        const double d = -delta * minv;
 #pragma unroll
-        for (int x = 0; x < 3; x++) { dvl[x] += jl[r][x] * minv * delta; dva[x] += ua[r][x] * delta; }
+        for (int x = 0; x < 3; x++) { dvl[x] += SM(base + x) * d; dva[x] += SM(base + 6 + x) * delta; }
+#pragma unroll
+        for (int j = 0; j < NB; j++) dv[j] += SM(base + 9 + NA + j) * delta;
     };
     int it = 0;
 #pragma unroll 1
@@ -350,36 +408,73 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
                 for (int r = NB - 1; r >= 0; r--) row_m(r, resid);
             }
         }
+        // normal rows: impulse >= 0
 #pragma unroll 1
-        for (int c = 0; c < nc; c++) { // normal rows: impulse >= 0
-            const int r = 3 * c;
-            double delta = rhs[r] - applied[r] * cfmr[c] - row_dot(r) * dinv[r];
-            const double sum = applied[r] + delta;
+        for (int c = 0; c < ntab; c++) {
+            const int base = LY::TAB + 3 * c * LY::TAB_ROW;
+            const double rhs = SM(base + 6), dinv = SM(base + 7), diagc = SM(base + 8), app = SM(base + 9);
+            double delta = rhs - tab_dot(base, 0) * dinv; // cfm = 0 on the table
+            const double sum = app + delta;
             const bool lo = sum < 0.0;
-            delta = lo ? -applied[r] : delta;
-            applied[r] = lo ? 0.0 : sum;
-            row_apply(r, delta);
-            const double dvel = delta * (diag[r] + cfm[c]);
+            delta = lo ? -app : delta;
+            SM(base + 9) = lo ? 0.0 : sum;
+            tab_apply(base, 0, delta);
+            const double dvel = delta * diagc;
             resid = fmax(resid, dvel * dvel);
         }
 #pragma unroll 1
-        for (int c = 0; c < nc; c++) { // friction pairs inside the cone mu * normal impulse
-            if (!(applied[3 * c] > 0.0)) continue;
-            const double lim = mu[c] * applied[3 * c];
-            const int r1 = 3 * c + 1, r2 = 3 * c + 2;
-            double s1 = applied[r1] + (rhs[r1] - row_dot(r1) * dinv[r1]);
-            double s2 = applied[r2] + (rhs[r2] - row_dot(r2) * dinv[r2]);
+        for (int c = 0; c < ntip; c++) {
+            const int base = LY::TIP + 3 * c * LY::TIP_ROW, sc0 = base + 9 + NA + NB;
+            const double rhs = SM(sc0), dinv = SM(sc0 + 1), diagc = SM(sc0 + 2), app = SM(sc0 + 3);
+            double delta = rhs - app * (cfm_tip * dinv) - tip_dot(base) * dinv;
+            const double sum = app + delta;
+            const bool lo = sum < 0.0;
+            delta = lo ? -app : delta;
+            SM(sc0 + 3) = lo ? 0.0 : sum;
+            tip_apply(base, delta);
+            const double dvel = delta * diagc;
+            resid = fmax(resid, dvel * dvel);
+        }
+        // friction pairs inside the cone mu * normal impulse
+#pragma unroll 1
+        for (int c = 0; c < ntab; c++) {
+            const int b0 = LY::TAB + 3 * c * LY::TAB_ROW, b1 = b0 + LY::TAB_ROW, b2 = b1 + LY::TAB_ROW;
+            const double napp = SM(b0 + 9);
+            if (!(napp > 0.0)) continue;
+            const double lim = task.push_mu_table * napp;
+            const double a1 = SM(b1 + 9), a2 = SM(b2 + 9);
+            double s1 = a1 + (SM(b1 + 6) - tab_dot(b1, 1) * SM(b1 + 7));
+            double s2 = a2 + (SM(b2 + 6) - tab_dot(b2, 2) * SM(b2 + 7));
             const double nrm2 = s1 * s1 + s2 * s2;
             if (nrm2 > lim * lim) { const double scl = lim / sqrt(nrm2); s1 *= scl; s2 *= scl; }
-            const double d1 = s1 - applied[r1], d2 = s2 - applied[r2];
-            applied[r1] = s1; applied[r2] = s2;
-            row_apply(r1, d1);
-            row_apply(r2, d2);
-            const double e1 = d1 * diag[r1], e2 = d2 * diag[r2];
+            const double d1 = s1 - a1, d2 = s2 - a2;
+            SM(b1 + 9) = s1; SM(b2 + 9) = s2;
+            tab_apply(b1, 1, d1);
+            tab_apply(b2, 2, d2);
+            const double e1 = d1 * SM(b1 + 8), e2 = d2 * SM(b2 + 8);
+            resid = fmax(resid, fmax(e1 * e1, e2 * e2));
+        }
+#pragma unroll 1
+        for (int c = 0; c < ntip; c++) {
+            const int b0 = LY::TIP + 3 * c * LY::TIP_ROW, b1 = b0 + LY::TIP_ROW, b2 = b1 + LY::TIP_ROW, so = 9 + NA + NB;
+            const double napp = SM(b0 + so + 3);
+            if (!(napp > 0.0)) continue;
+            const double lim = task.push_mu_tip * napp;
+            const double a1 = SM(b1 + so + 3), a2 = SM(b2 + so + 3);
+            double s1 = a1 + (SM(b1 + so) - tip_dot(b1) * SM(b1 + so + 1));
+            double s2 = a2 + (SM(b2 + so) - tip_dot(b2) * SM(b2 + so + 1));
+            const double nrm2 = s1 * s1 + s2 * s2;
+            if (nrm2 > lim * lim) { const double scl = lim / sqrt(nrm2); s1 *= scl; s2 *= scl; }
+            const double d1 = s1 - a1, d2 = s2 - a2;
+            SM(b1 + so + 3) = s1; SM(b2 + so + 3) = s2;
+            tip_apply(b1, d1);
+            tip_apply(b2, d2);
+            const double e1 = d1 * SM(b1 + so + 2), e2 = d2 * SM(b2 + so + 2);
             resid = fmax(resid, fmax(e1 * e1, e2 * e2));
         }
         if (resid <= ph.solver_residual_threshold) { it++; break; }
     }
+#undef SM
 #pragma unroll
     for (int i = 0; i < NB; i++) {
         qd[i] += dv[i];

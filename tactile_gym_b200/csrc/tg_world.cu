@@ -51,6 +51,7 @@ struct TgWorld {
     unsigned char* d_done_internal = nullptr;
     float* d_reward_internal = nullptr;
     size_t raster_smem = 0;
+    size_t push_smem = 0;
     int raster_grid = 0;
     int standby_blocks = 0;
     long long launches = 0;
@@ -155,6 +156,18 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         return rc;
     }
     w->standby_blocks = b.pipeline ? std::max(8, std::min(64, w->sm_count / 2)) : 0;
+    if (cfg->task.task == TG_TASK_OBJECT_PUSH) {
+        // object_push steps PUSH_BLOCK envs per block with its constraint rows in dynamic shared memory (tg_push.cuh);
+        // standby rebuilds ride in the step threads, not in extra blocks
+        w->standby_blocks = 0;
+        if (cfg->arm.topo == TG_TOPO_MG400) {
+            w->push_smem = sizeof(double) * PushLayout<TopoMG400>::SLOTS * PUSH_BLOCK;
+            CK(cudaFuncSetAttribute(step_kernel<TopoMG400, TG_TASK_OBJECT_PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
+        } else {
+            w->push_smem = sizeof(double) * PushLayout<TopoChain6>::SLOTS * PUSH_BLOCK;
+            CK(cudaFuncSetAttribute(step_kernel<TopoChain6, TG_TASK_OBJECT_PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
+        }
+    }
     if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
         if (!b.pipeline) { tg_destroy(w); return fail(TG_EINVAL, "surface_follow needs max_steps >= 2"); }
         if ((rc = dalloc(w, &b.height, (size_t)2 * SURF_PTS * n)) || (rc = dalloc(w, &b.hf_meta, (size_t)2 * SURF_META * n)) ||
@@ -335,10 +348,22 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
     return TG_OK;
 }
 
+// step kernels are specialised per (topology, task)
+#define STEP_LAUNCH(Topo, TASK, grid, block, smem) \
+    step_kernel<Topo, TASK><<<grid, block, smem, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done, autoreset)
+#define STEP_DISPATCH(Topo)                                                                               \
+    switch (w->cfg.task.task) {                                                                           \
+    case TG_TASK_OBJECT_BALANCE: STEP_LAUNCH(Topo, TG_TASK_OBJECT_BALANCE, grid, 128, 0); break;          \
+    case TG_TASK_SURFACE_FOLLOW: STEP_LAUNCH(Topo, TG_TASK_SURFACE_FOLLOW, grid, 128, 0); break;          \
+    case TG_TASK_OBJECT_PUSH: STEP_LAUNCH(Topo, TG_TASK_OBJECT_PUSH, pgrid, PUSH_BLOCK, w->push_smem); break; \
+    default: STEP_LAUNCH(Topo, TG_TASK_EDGE_FOLLOW, grid, 128, 0); break;                                 \
+    }
+
 static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, int autoreset, cudaStream_t st)
 {
     const dim3 grid(w->eb.step_blocks + w->standby_blocks); // the extra blocks recompute consumed standbys meanwhile
-    TOPO_DISPATCH(w, (step_kernel<Topo><<<grid, 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done, autoreset)));
+    const dim3 pgrid((w->n + PUSH_BLOCK - 1) / PUSH_BLOCK);  // object_push: PUSH_BLOCK envs per block, rows in shared memory
+    if (w->cfg.arm.topo == TG_TOPO_MG400) { STEP_DISPATCH(TopoMG400) } else { STEP_DISPATCH(TopoChain6) }
     w->launches++;
     CK(cudaGetLastError());
     return TG_OK;

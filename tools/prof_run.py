@@ -1,6 +1,6 @@
 """Short workload for ncu: BASELINE config 2 (edge_follow-v0, UR5+TacTip 128x128, 4096 envs) or config 5
 (object_balance-v0, 256x256, 2048 envs), a few steps, then optionally 3 raster-only launches.
-usage: prof_run.py [n] [S] [steps] [raster|-] [edge|balance]"""
+usage: prof_run.py [n] [S] [steps] [raster|-] [edge|balance|surface|push]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,6 +12,15 @@ if task == "balance":
     modes = {"movement_mode": "xy", "control_mode": "TCP_velocity_control", "object_mode": "pole", "rand_gravity": True,
              "rand_embed_dist": True, "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5",
              "tactile_sensor_name": "tactip"}
+elif task == "surface":
+    env_id, act_dim = "surface_follow-v0", 3
+    modes = {"movement_mode": "xyzRxRy", "control_mode": "TCP_velocity_control", "noise_mode": "simplex", "observation_mode": "tactile",
+             "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "digit"}
+elif task == "push":
+    env_id, act_dim = "object_push-v0", 2
+    modes = {"movement_mode": "TyRz", "control_mode": "TCP_velocity_control", "rand_init_orn": False, "rand_obj_mass": False,
+             "traj_type": "simplex", "observation_mode": "tactile_and_feature", "reward_mode": "dense", "arm_type": "mg400",
+             "tactile_sensor_name": "digitac"}
 else:
     env_id, act_dim = "edge_follow-v0", 2
     modes = {"movement_mode": "xy", "control_mode": "TCP_velocity_control", "noise_mode": "rand_height",
