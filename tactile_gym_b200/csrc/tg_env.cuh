@@ -638,15 +638,19 @@ TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
 // has no standby blocks: its episodes are long and its reset short, so each step thread advances its own env's standby
 // slot by one quantum after the step.
 template <class T, int TASK>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TASK == TG_TASK_OBJECT_PUSH ? PUSH_THREADS : 128)
 step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
             EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
 {
     constexpr int NB = T::NB;
     constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, push = TASK == TG_TASK_OBJECT_PUSH, surface = TASK == TG_TASK_SURFACE_FOLLOW;
     int e;
+    int col = 0; // object_push: this env's column in the block's shared-memory row store
     if (push) {
-        e = blockIdx.x * blockDim.x + threadIdx.x;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane >= PUSH_LANES) return;
+        col = warp * PUSH_LANES + lane;
+        e = blockIdx.x * PUSH_BLOCK + col;
         if (e >= b.n) return;
     } else {
         if ((int)blockIdx.x >= b.step_blocks) {
@@ -751,9 +755,8 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
         if (push) {
             obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
-            extern __shared__ double push_rows[]; // [PushLayout<T>::SLOTS][blockDim.x]
 #pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, push_rows + threadIdx.x, blockDim.x);
+            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col);
             obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
         } else if (balance) {
             obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);

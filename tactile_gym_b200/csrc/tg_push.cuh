@@ -191,7 +191,7 @@ __device__ __noinline__ int push_contacts(const TgArm& arm, const TgTask& task, 
 // rate 18 %, 15.6 GB of DRAM reads per launch (profiles/r01_push_step_v0.md).
 //   motors      : A = M^-1 upper triangle NB (NB + 1) / 2, then rhs / dinv / applied per joint
 //   table rows  : 3 per contact x 4 contacts: ja(3) ua(3) rhs dinv diagc applied  (normal +z, fixed friction basis)
-//   tip rows    : 3 per contact x 4 contacts: dir(3) ja(3) ua(3) jr(NA) ur(NB) rhs dinv diagc applied
+//   tip rows    : 3 per contact x 4 contacts: jl(3) ja(3) ua(3) jr(NA) ur(NB) rhs dinv diagc applied
 // with NA = joints between the base and the tip (the MG400's three slaved joints are not among them).
 template <class T>
 struct PushLayout {
@@ -206,19 +206,25 @@ struct PushLayout {
     static constexpr int SLOTS = TIP + 12 * TIP_ROW;
     __host__ __device__ static constexpr int tri(int i, int j) { return i <= j ? i * NB - i * (i - 1) / 2 + (j - i) : j * NB - j * (j - 1) / 2 + (i - j); }
 };
-#define PUSH_BLOCK 56 // envs (threads) per block: 56 x 492 slots x 8 B = 220 KB of the 227 KB a block may have, one block per SM
+#define PUSH_BLOCK 56 // envs per block: 56 x 492 slots x 8 B = 220 KB of the 227 KB a block may have, one block per SM
+// The PGS sweep count differs from env to env (median ~55, 2 % of the substeps run into the cap of 150) and a warp sweeps
+// until its slowest lane is done, so the 56 envs of a block are spread over 7 warps of PUSH_LANES = 8 active lanes:
+// the expected slowest-of-8 is much shorter than the slowest-of-28, and 7 warps keep all four schedulers of the SM busy
+// where 2 left half of them idle (ncu, 2 warps: issue slots 24 % busy, 48 % of the stall samples fixed-latency waits).
+#define PUSH_LANES 8
+#define PUSH_THREADS (32 * (PUSH_BLOCK / PUSH_LANES))
 
-// Robot.step_sim() with the cube in the world.  `sm` = this thread's column of the block's row store, `ss` its stride.
+// Robot.step_sim() with the cube in the world.  `col` = this env's column of the block's row store.
 // Returns the number of PGS sweeps.
 template <class T>
 __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const double* __restrict__ hull, int n_hull,
-                                         double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot, ObjState& o,
-                                         double* __restrict__ sm, const int ss)
+                                         double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot, ObjState& o, const int col)
 {
+    extern __shared__ double push_rows[]; // [PushLayout<T>::SLOTS][PUSH_BLOCK]; indexed directly so that the accesses are LDS / STS
     using LY = PushLayout<T>;
     constexpr int NB = T::NB, NA = LY::NA;
     constexpr double EPS = 2.2204460492503131e-16;
-#define SM(slot) sm[(slot) * ss]
+#define SM(slot) push_rows[(slot) * PUSH_BLOCK + col]
     PushContact C[PUSH_MAXC];
     int nc, ntab = 0;
     double Rb[9], Iinv[3];
@@ -320,7 +326,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
                         if (j < NA) den += jr[j < NA ? j : 0] * u;
                     }
 #pragma unroll
-                    for (int x = 0; x < 3; x++) SM(base + x) = dir[qq][x];
+                    for (int x = 0; x < 3; x++) SM(base + x) = scb * dir[qq][x];
                 }
                 v3cross(ja, rb, dir[qq]);
 #pragma unroll
@@ -352,6 +358,10 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
     const int ntip = nc - ntab;
     const double cfm_tip = (1.0 / fmax(ph.dt * task.push_tip_k + task.push_tip_d, EPS)) / ph.dt;
 
+    // ---- projected Gauss-Seidel ------------------------------------------------------------------------------------
+    // The sweep is one long dependent chain (each row reads the velocities the previous row wrote), so a row update is
+    // written for latency: all of its operands are loaded first, dot products are summed as trees (depth 5 instead of
+    // 11-14 dependent FMAs), the cone clamp uses rsqrt instead of sqrt + divide.
     double dv[NB], dvl[3] = {0, 0, 0}, dva[3] = {0, 0, 0};
 #pragma unroll
     for (int i = 0; i < NB; i++) dv[i] = 0;
@@ -370,30 +380,49 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
         const double dvel = delta * Ar[r];
         resid = fmax(resid, dvel * dvel);
     };
-    // table rows: directions are (0,0,1), (0,-1,0), (1,0,0) = btPlaneSpace1 of +z; the cube is the first body
-    auto tab_dot = [&](int base, int qq) {
-        const double lin = qq == 0 ? dvl[2] : (qq == 1 ? -dvl[1] : dvl[0]);
-        return lin + SM(base) * dva[0] + SM(base + 1) * dva[1] + SM(base + 2) * dva[2];
+    // one row's operands, in registers
+    struct TabRow { double ja[3], ua[3], rhs, dinv, diagc, app; };
+    struct TipRow { double jl[3], ja[3], ua[3], jr[NA], ur[NB], rhs, dinv, diagc, app; };
+    auto tab_load = [&](int base, TabRow& R) {
+#pragma unroll
+        for (int x = 0; x < 3; x++) { R.ja[x] = SM(base + x); R.ua[x] = SM(base + 3 + x); }
+        R.rhs = SM(base + 6); R.dinv = SM(base + 7); R.diagc = SM(base + 8); R.app = SM(base + 9);
     };
-    auto tab_apply = [&](int base, int qq, double delta) {
+    auto tip_load = [&](int base, TipRow& R) {
+#pragma unroll
+        for (int x = 0; x < 3; x++) { R.jl[x] = SM(base + x); R.ja[x] = SM(base + 3 + x); R.ua[x] = SM(base + 6 + x); }
+#pragma unroll
+        for (int j = 0; j < NA; j++) R.jr[j] = SM(base + 9 + j);
+#pragma unroll
+        for (int j = 0; j < NB; j++) R.ur[j] = SM(base + 9 + NA + j);
+        R.rhs = SM(base + 9 + NA + NB); R.dinv = SM(base + 10 + NA + NB); R.diagc = SM(base + 11 + NA + NB); R.app = SM(base + 12 + NA + NB);
+    };
+    // table rows: directions are (0,0,1), (0,-1,0), (1,0,0) = btPlaneSpace1 of +z; the cube is the first body
+    auto tab_dot = [&](const TabRow& R, int qq) {
+        const double lin = qq == 0 ? dvl[2] : (qq == 1 ? -dvl[1] : dvl[0]);
+        return (lin + R.ja[0] * dva[0]) + (R.ja[1] * dva[1] + R.ja[2] * dva[2]);
+    };
+    auto tab_apply = [&](const TabRow& R, int qq, double delta) {
         const double d = delta * minv;
         if (qq == 0) dvl[2] += d; else if (qq == 1) dvl[1] -= d; else dvl[0] += d;
-        dva[0] += SM(base + 3) * delta; dva[1] += SM(base + 4) * delta; dva[2] += SM(base + 5) * delta;
+#pragma unroll
+        for (int x = 0; x < 3; x++) dva[x] += R.ua[x] * delta;
     };
-    auto tip_dot = [&](int base) {
-        double dot = -(SM(base) * dvl[0] + SM(base + 1) * dvl[1] + SM(base + 2) * dvl[2]);
-        dot += SM(base + 3) * dva[0] + SM(base + 4) * dva[1] + SM(base + 5) * dva[2];
-        double da = 0;
+    auto tip_dot = [&](const TipRow& R) {
+        const double p0 = R.jl[0] * dvl[0] + R.jl[1] * dvl[1], p1 = R.jl[2] * dvl[2] + R.ja[0] * dva[0], p2 = R.ja[1] * dva[1] + R.ja[2] * dva[2];
+        double pa[(NA + 1) / 2];
 #pragma unroll
-        for (int j = 0; j < NA; j++) da += SM(base + 9 + j) * dv[j];
-        return dot + da;
+        for (int j = 0; j + 1 < NA; j += 2) pa[j / 2] = R.jr[j] * dv[j] + R.jr[j + 1] * dv[j + 1];
+        if (NA & 1) pa[NA / 2] = R.jr[NA - 1] * dv[NA - 1];
+        double sa = (pa[0] + pa[1]) + pa[2];                   // NA = 5 or 6: three partial sums
+        return ((p0 + p1) + p2) + sa;
     };
-    auto tip_apply = [&](int base, double delta) {
-        const double d = -delta * minv;
+    auto tip_apply = [&](const TipRow& R, double delta) {
+        const double d = delta * minv;
 #pragma unroll
-        for (int x = 0; x < 3; x++) { dvl[x] += SM(base + x) * d; dva[x] += SM(base + 6 + x) * delta; }
+        for (int x = 0; x < 3; x++) { dvl[x] += R.jl[x] * d; dva[x] += R.ua[x] * delta; }
 #pragma unroll
-        for (int j = 0; j < NB; j++) dv[j] += SM(base + 9 + NA + j) * delta;
+        for (int j = 0; j < NB; j++) dv[j] += R.ur[j] * delta;
     };
     int it = 0;
 #pragma unroll 1
@@ -412,27 +441,30 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
 #pragma unroll 1
         for (int c = 0; c < ntab; c++) {
             const int base = LY::TAB + 3 * c * LY::TAB_ROW;
-            const double rhs = SM(base + 6), dinv = SM(base + 7), diagc = SM(base + 8), app = SM(base + 9);
-            double delta = rhs - tab_dot(base, 0) * dinv; // cfm = 0 on the table
-            const double sum = app + delta;
+            TabRow R;
+            tab_load(base, R);
+            double delta = R.rhs - tab_dot(R, 0) * R.dinv; // cfm = 0 on the table
+            const double sum = R.app + delta;
             const bool lo = sum < 0.0;
-            delta = lo ? -app : delta;
+            delta = lo ? -R.app : delta;
             SM(base + 9) = lo ? 0.0 : sum;
-            tab_apply(base, 0, delta);
-            const double dvel = delta * diagc;
+            tab_apply(R, 0, delta);
+            const double dvel = delta * R.diagc;
             resid = fmax(resid, dvel * dvel);
         }
 #pragma unroll 1
         for (int c = 0; c < ntip; c++) {
-            const int base = LY::TIP + 3 * c * LY::TIP_ROW, sc0 = base + 9 + NA + NB;
-            const double rhs = SM(sc0), dinv = SM(sc0 + 1), diagc = SM(sc0 + 2), app = SM(sc0 + 3);
-            double delta = rhs - app * (cfm_tip * dinv) - tip_dot(base) * dinv;
-            const double sum = app + delta;
+            const int base = LY::TIP + 3 * c * LY::TIP_ROW;
+            TipRow R;
+            tip_load(base, R);
+            const double pre = R.rhs - R.app * (cfm_tip * R.dinv);
+            double delta = pre - tip_dot(R) * R.dinv;
+            const double sum = R.app + delta;
             const bool lo = sum < 0.0;
-            delta = lo ? -app : delta;
-            SM(sc0 + 3) = lo ? 0.0 : sum;
-            tip_apply(base, delta);
-            const double dvel = delta * diagc;
+            delta = lo ? -R.app : delta;
+            SM(base + 12 + NA + NB) = lo ? 0.0 : sum;
+            tip_apply(R, delta);
+            const double dvel = delta * R.diagc;
             resid = fmax(resid, dvel * dvel);
         }
         // friction pairs inside the cone mu * normal impulse
@@ -441,17 +473,18 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
             const int b0 = LY::TAB + 3 * c * LY::TAB_ROW, b1 = b0 + LY::TAB_ROW, b2 = b1 + LY::TAB_ROW;
             const double napp = SM(b0 + 9);
             if (!(napp > 0.0)) continue;
+            TabRow R1, R2;
+            tab_load(b1, R1); tab_load(b2, R2);
             const double lim = task.push_mu_table * napp;
-            const double a1 = SM(b1 + 9), a2 = SM(b2 + 9);
-            double s1 = a1 + (SM(b1 + 6) - tab_dot(b1, 1) * SM(b1 + 7));
-            double s2 = a2 + (SM(b2 + 6) - tab_dot(b2, 2) * SM(b2 + 7));
+            double s1 = R1.app + (R1.rhs - tab_dot(R1, 1) * R1.dinv);
+            double s2 = R2.app + (R2.rhs - tab_dot(R2, 2) * R2.dinv);
             const double nrm2 = s1 * s1 + s2 * s2;
-            if (nrm2 > lim * lim) { const double scl = lim / sqrt(nrm2); s1 *= scl; s2 *= scl; }
-            const double d1 = s1 - a1, d2 = s2 - a2;
+            if (nrm2 > lim * lim) { const double scl = lim * rsqrt(nrm2); s1 *= scl; s2 *= scl; }
+            const double d1 = s1 - R1.app, d2 = s2 - R2.app;
             SM(b1 + 9) = s1; SM(b2 + 9) = s2;
-            tab_apply(b1, 1, d1);
-            tab_apply(b2, 2, d2);
-            const double e1 = d1 * SM(b1 + 8), e2 = d2 * SM(b2 + 8);
+            tab_apply(R1, 1, d1);
+            tab_apply(R2, 2, d2);
+            const double e1 = d1 * R1.diagc, e2 = d2 * R2.diagc;
             resid = fmax(resid, fmax(e1 * e1, e2 * e2));
         }
 #pragma unroll 1
@@ -459,17 +492,18 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
             const int b0 = LY::TIP + 3 * c * LY::TIP_ROW, b1 = b0 + LY::TIP_ROW, b2 = b1 + LY::TIP_ROW, so = 9 + NA + NB;
             const double napp = SM(b0 + so + 3);
             if (!(napp > 0.0)) continue;
+            TipRow R1, R2;
+            tip_load(b1, R1); tip_load(b2, R2);
             const double lim = task.push_mu_tip * napp;
-            const double a1 = SM(b1 + so + 3), a2 = SM(b2 + so + 3);
-            double s1 = a1 + (SM(b1 + so) - tip_dot(b1) * SM(b1 + so + 1));
-            double s2 = a2 + (SM(b2 + so) - tip_dot(b2) * SM(b2 + so + 1));
+            double s1 = R1.app + (R1.rhs - tip_dot(R1) * R1.dinv);
+            double s2 = R2.app + (R2.rhs - tip_dot(R2) * R2.dinv);
             const double nrm2 = s1 * s1 + s2 * s2;
-            if (nrm2 > lim * lim) { const double scl = lim / sqrt(nrm2); s1 *= scl; s2 *= scl; }
-            const double d1 = s1 - a1, d2 = s2 - a2;
+            if (nrm2 > lim * lim) { const double scl = lim * rsqrt(nrm2); s1 *= scl; s2 *= scl; }
+            const double d1 = s1 - R1.app, d2 = s2 - R2.app;
             SM(b1 + so + 3) = s1; SM(b2 + so + 3) = s2;
-            tip_apply(b1, d1);
-            tip_apply(b2, d2);
-            const double e1 = d1 * SM(b1 + so + 2), e2 = d2 * SM(b2 + so + 2);
+            tip_apply(R1, d1);
+            tip_apply(R2, d2);
+            const double e1 = d1 * R1.diagc, e2 = d2 * R2.diagc;
             resid = fmax(resid, fmax(e1 * e1, e2 * e2));
         }
         if (resid <= ph.solver_residual_threshold) { it++; break; }

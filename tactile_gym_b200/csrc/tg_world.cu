@@ -355,7 +355,7 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
     switch (w->cfg.task.task) {                                                                           \
     case TG_TASK_OBJECT_BALANCE: STEP_LAUNCH(Topo, TG_TASK_OBJECT_BALANCE, grid, 128, 0); break;          \
     case TG_TASK_SURFACE_FOLLOW: STEP_LAUNCH(Topo, TG_TASK_SURFACE_FOLLOW, grid, 128, 0); break;          \
-    case TG_TASK_OBJECT_PUSH: STEP_LAUNCH(Topo, TG_TASK_OBJECT_PUSH, pgrid, PUSH_BLOCK, w->push_smem); break; \
+    case TG_TASK_OBJECT_PUSH: STEP_LAUNCH(Topo, TG_TASK_OBJECT_PUSH, pgrid, PUSH_THREADS, w->push_smem); break; \
     default: STEP_LAUNCH(Topo, TG_TASK_EDGE_FOLLOW, grid, 128, 0); break;                                 \
     }
 
