@@ -645,13 +645,13 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     constexpr int NB = T::NB;
     constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, push = TASK == TG_TASK_OBJECT_PUSH, surface = TASK == TG_TASK_SURFACE_FOLLOW;
     int e;
-    int col = 0; // object_push: this env's column in the block's shared-memory row store
+    int col = 0;       // object_push: this env's column in the block's shared-memory row store
+    bool owner = true; // object_push: lanes 0..PUSH_LANES-1 of a warp each step an env; the others only help in the hull scan
     if (push) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane >= PUSH_LANES) return;
-        col = warp * PUSH_LANES + lane;
+        col = warp * PUSH_LANES + (lane & (PUSH_LANES - 1));
         e = blockIdx.x * PUSH_BLOCK + col;
-        if (e >= b.n) return;
+        owner = lane < PUSH_LANES && e < b.n;
     } else {
         if ((int)blockIdx.x >= b.step_blocks) {
             standby_role<T>(arm, ph, task, b, b.step_blocks, false);
@@ -662,13 +662,17 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     }
     double q[NB], qd[NB];
 #pragma unroll
-    for (int i = 0; i < NB; i++) { q[i] = b.q[(size_t)i * b.n + e]; qd[i] = b.qd[(size_t)i * b.n + e]; }
+    for (int i = 0; i < NB; i++) { q[i] = 0.0; qd[i] = 0.0; }
+    if (owner) {
+#pragma unroll
+        for (int i = 0; i < NB; i++) { q[i] = b.q[(size_t)i * b.n + e]; qd[i] = b.qd[(size_t)i * b.n + e]; }
+    }
 
     // encode_actions + scale_actions (edge_follow_env.py:345-369, base_tactile_env.py:141-164)
     double v[6];
     Motors<NB> mot;
     mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
-    {
+    if (owner) {
         Kin<NB> k;
         fk<T>(arm, q, k);
         double tp[3], tq[4], wq[4], Rw[9];
@@ -754,10 +758,10 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
         for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
         if (push) {
-            obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
+            if (owner) obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
 #pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col);
-            obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
+            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col, owner); // whole warp
+            if (owner) obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
         } else if (balance) {
             obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);
 #pragma unroll 1
@@ -769,6 +773,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         }
     }
 
+    if (!owner) return;
     const int steps = b.steps[e] + 1;
     b.steps[e] = steps;
 #pragma unroll

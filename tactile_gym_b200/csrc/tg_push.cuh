@@ -23,6 +23,13 @@
 
 #define PUSH_MAXC 8
 #define PUSH_NTRAJ TG_PUSH_NTRAJ
+#define PUSH_BLOCK 56 // envs per block: 56 x 492 slots x 8 B = 220 KB of the 227 KB a block may have, one block per SM
+// The PGS sweep count differs from env to env (median ~55, 2 % of the substeps run into the cap of 150) and a warp sweeps
+// until its slowest lane is done, so the 56 envs of a block are spread over 7 warps of PUSH_LANES = 8 active lanes:
+// the expected slowest-of-8 is much shorter than the slowest-of-28, and 7 warps keep all four schedulers of the SM busy
+// where 2 left half of them idle (ncu, 2 warps: issue slots 24 % busy, 48 % of the stall samples fixed-latency waits).
+#define PUSH_LANES 8
+#define PUSH_THREADS (32 * (PUSH_BLOCK / PUSH_LANES))
 
 TGD long long push_qkey(double x) { return __double2ll_rn(x * 1e9); } // comparisons on a 1 nm grid: ties break by index
 
@@ -78,10 +85,77 @@ TGD bool tip_ancestor(int tcp_body, int j)
     return anc;
 }
 
-// narrow phase on the poses at the start of the substep; returns the number of contacts (table contacts first)
-template <class T>
-__device__ __noinline__ int push_contacts(const TgArm& arm, const TgTask& task, const double* __restrict__ hull, int n_hull,
-                                          const Kin<T::NB>& k, const ObjState& o, const double* Rb, PushContact* C)
+// ---- narrow phase on the poses at the start of the substep ---------------------------------------------------------
+// An env is stepped by ONE lane (its owner, lanes 0..PUSH_LANES-1 of a warp), but the scan of the tip hull's ~600
+// vertices against the cube is shared with the warp's otherwise idle lanes: env slot s is served by the PUSH_PARTS lanes
+// s, s + 8, s + 16, s + 24, each testing every fourth vertex; the partial results are merged with shuffles.
+#define PUSH_PARTS (32 / PUSH_LANES)
+
+struct HullScan {
+    long long deep_key, ext_key[3][2]; // 1 nm keys of the deepest signed distance / of the extreme cube-local coordinates
+    int deep, ext[3][2], ncand;        // and the hull vertices that attain them (lowest index on ties)
+};
+
+// all 32 lanes of the warp call this together.  M, t: cube-local coordinates of hull vertex v are M v + t (valid in the
+// owner lane only; broadcast here).
+__device__ __noinline__ void push_scan(const double* __restrict__ hull, int n_hull, const double* Mo, const double* to, const double* half,
+                                       double slop, HullScan& h)
+{
+    const int lane = threadIdx.x & 31, slot = lane & (PUSH_LANES - 1), part = lane / PUSH_LANES;
+    double M[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = __shfl_sync(0xffffffffu, Mo[i], slot);
+#pragma unroll
+    for (int i = 0; i < 3; i++) t[i] = __shfl_sync(0xffffffffu, to[i], slot);
+    h.deep_key = 0x7fffffffffffffffLL; h.deep = 0x7fffffff; h.ncand = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        h.ext_key[c][0] = 0x7fffffffffffffffLL; h.ext_key[c][1] = -0x7fffffffffffffffLL - 1;
+        h.ext[c][0] = 0x7fffffff; h.ext[c][1] = 0x7fffffff;
+    }
+#pragma unroll 4
+    for (int i = part; i < n_hull; i += PUSH_PARTS) {
+        const double v[3] = {__ldg(hull + 3 * i), __ldg(hull + 3 * i + 1), __ldg(hull + 3 * i + 2)};
+        double l[3];
+        m3mulv(l, M, v);
+        l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
+        int ax, sg;
+        const double sd = cube_sd(half, l, ax, sg);
+        if (sd > slop) continue;
+        const long long key = push_qkey(sd);
+        if (key < h.deep_key) { h.deep_key = key; h.deep = i; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const long long lk = push_qkey(l[c]);
+            if (lk < h.ext_key[c][0]) { h.ext_key[c][0] = lk; h.ext[c][0] = i; }
+            if (lk > h.ext_key[c][1]) { h.ext_key[c][1] = lk; h.ext[c][1] = i; }
+        }
+        h.ncand++;
+    }
+    // merge the parts (xor over the lane bits above the slot bits); ties go to the lower vertex index, as in a
+    // sequential scan in index order
+#pragma unroll
+    for (int m = PUSH_LANES; m < 32; m <<= 1) {
+        {
+            const long long ok = __shfl_xor_sync(0xffffffffu, h.deep_key, m);
+            const int oi = __shfl_xor_sync(0xffffffffu, h.deep, m);
+            if (ok < h.deep_key || (ok == h.deep_key && oi < h.deep)) { h.deep_key = ok; h.deep = oi; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            long long ok = __shfl_xor_sync(0xffffffffu, h.ext_key[c][0], m);
+            int oi = __shfl_xor_sync(0xffffffffu, h.ext[c][0], m);
+            if (ok < h.ext_key[c][0] || (ok == h.ext_key[c][0] && oi < h.ext[c][0])) { h.ext_key[c][0] = ok; h.ext[c][0] = oi; }
+            ok = __shfl_xor_sync(0xffffffffu, h.ext_key[c][1], m);
+            oi = __shfl_xor_sync(0xffffffffu, h.ext[c][1], m);
+            if (ok > h.ext_key[c][1] || (ok == h.ext_key[c][1] && oi < h.ext[c][1])) { h.ext_key[c][1] = ok; h.ext[c][1] = oi; }
+        }
+        h.ncand += __shfl_xor_sync(0xffffffffu, h.ncand, m);
+    }
+}
+
+// cube <-> table: cube vertices at or below the table top (owner lane)
+TGD int push_table_contacts(const TgTask& task, const ObjState& o, const double* Rb, PushContact* C)
 {
     int nc = 0;
 #pragma unroll 1
@@ -100,86 +174,55 @@ __device__ __noinline__ int push_contacts(const TgArm& arm, const TgTask& task, 
         for (int q = 0; q < 3; q++) { c.pb[q] = w[q]; c.pa[q] = w[q]; }
         c.dist = dist;
     }
-    // tip core hull <-> cube: cube-local coordinates of a hull vertex v (tip body frame) are M v + t
-    double Rt[9], pt[3], M[9], t[3];
-#pragma unroll
-    for (int b = 0; b < T::NB; b++)
-        if (arm.tcp_body == b) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) Rt[i] = k.R[b][i];
-#pragma unroll
-            for (int i = 0; i < 3; i++) pt[i] = k.p[b][i];
-        }
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) M[3 * i + j] = Rb[i] * Rt[j] + Rb[3 + i] * Rt[3 + j] + Rb[6 + i] * Rt[6 + j]; // Rb^T Rt
+    return nc;
+}
+
+// tip core hull <-> cube: reduce the penetrating vertices to <= 4 contacts (owner lane): the deepest, the two extremes
+// along the first tangent axis of its face, the extreme along the second that is farther from the deepest
+__device__ __noinline__ int push_tip_contacts(const TgTask& task, const double* __restrict__ hull, const HullScan& h, const double* M, const double* t,
+                                              const double* Rb, const double* Rt, const double* pt, PushContact* C, int nc)
+{
+    if (h.ncand <= 0) return nc;
+    int A, sg;
+    double l[3];
     {
-        const double d[3] = {pt[0] - o.pos[0], pt[1] - o.pos[1], pt[2] - o.pos[2]};
-        m3tmulv(t, Rb, d);
-    }
-    long long deep_key = 0, ext_key[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    int deep = -1, ext[3][2] = {{0, 0}, {0, 0}, {0, 0}}, ncand = 0;
-#pragma unroll 2
-    for (int i = 0; i < n_hull; i++) {
-        const double v[3] = {__ldg(hull + 3 * i), __ldg(hull + 3 * i + 1), __ldg(hull + 3 * i + 2)};
-        double l[3];
+        const double v[3] = {__ldg(hull + 3 * h.deep), __ldg(hull + 3 * h.deep + 1), __ldg(hull + 3 * h.deep + 2)};
         m3mulv(l, M, v);
         l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
-        int ax, sg;
-        const double sd = cube_sd(task.push_half, l, ax, sg);
-        if (sd > task.push_slop) continue;
-        const long long key = push_qkey(sd);
-        if (ncand == 0 || key < deep_key) { deep_key = key; deep = i; }
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const long long lk = push_qkey(l[c]);
-            if (ncand == 0 || lk < ext_key[c][0]) { ext_key[c][0] = lk; ext[c][0] = i; }
-            if (ncand == 0 || lk > ext_key[c][1]) { ext_key[c][1] = lk; ext[c][1] = i; }
-        }
-        ncand++;
+        cube_sd(task.push_half, l, A, sg);
     }
-    if (ncand > 0) {
-        int A, sg;
-        double l[3];
-        {
-            const double v[3] = {__ldg(hull + 3 * deep), __ldg(hull + 3 * deep + 1), __ldg(hull + 3 * deep + 2)};
-            m3mulv(l, M, v);
-            l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
-            cube_sd(task.push_half, l, A, sg);
-        }
-        const int U = (A + 1) % 3, V = (A + 2) % 3;
-        const long long dv = push_qkey(V == 0 ? l[0] : (V == 1 ? l[1] : l[2]));
-        long long eU0 = 0, eU1 = 0, kV0 = 0, kV1 = 0, eV0 = 0, eV1 = 0;
+    const int U = (A + 1) % 3, V = (A + 2) % 3;
+    const long long dv = push_qkey(V == 0 ? l[0] : (V == 1 ? l[1] : l[2]));
+    long long kV0 = 0, kV1 = 0;
+    int eU0 = 0, eU1 = 0, eV0 = 0, eV1 = 0;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            if (c == U) { eU0 = ext[c][0]; eU1 = ext[c][1]; }
-            if (c == V) { kV0 = ext_key[c][0]; kV1 = ext_key[c][1]; eV0 = ext[c][0]; eV1 = ext[c][1]; }
-        }
-        const long long a0 = llabs(kV0 - dv), a1 = llabs(kV1 - dv);
-        const int sel[4] = {deep, (int)eU0, (int)eU1, a0 >= a1 ? (int)eV0 : (int)eV1};
+    for (int c = 0; c < 3; c++) {
+        if (c == U) { eU0 = h.ext[c][0]; eU1 = h.ext[c][1]; }
+        if (c == V) { kV0 = h.ext_key[c][0]; kV1 = h.ext_key[c][1]; eV0 = h.ext[c][0]; eV1 = h.ext[c][1]; }
+    }
+    const long long a0 = llabs(kV0 - dv), a1 = llabs(kV1 - dv);
+    const int sel[4] = {h.deep, eU0, eU1, a0 >= a1 ? eV0 : eV1};
 #pragma unroll 1
-        for (int j = 0; j < 4; j++) {
-            bool dup = false;
-            for (int i = 0; i < j; i++) if (sel[i] == sel[j]) dup = true;
-            if (dup) continue;
-            const double v[3] = {__ldg(hull + 3 * sel[j]), __ldg(hull + 3 * sel[j] + 1), __ldg(hull + 3 * sel[j] + 2)};
-            m3mulv(l, M, v);
-            l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
-            int ax;
-            const double sd = cube_sd(task.push_half, l, ax, sg);
-            PushContact& c = C[nc++];
-            c.on_arm = 1;
-            // world normal = sign * column `ax` of Rb
-            c.n[0] = sg * (ax == 0 ? Rb[0] : (ax == 1 ? Rb[1] : Rb[2]));
-            c.n[1] = sg * (ax == 0 ? Rb[3] : (ax == 1 ? Rb[4] : Rb[5]));
-            c.n[2] = sg * (ax == 0 ? Rb[6] : (ax == 1 ? Rb[7] : Rb[8]));
-            double w[3];
-            m3mulv(w, Rt, v);
+    for (int j = 0; j < 4; j++) {
+        bool dup = false;
+        for (int i = 0; i < j; i++) if (sel[i] == sel[j]) dup = true;
+        if (dup) continue;
+        const double v[3] = {__ldg(hull + 3 * sel[j]), __ldg(hull + 3 * sel[j] + 1), __ldg(hull + 3 * sel[j] + 2)};
+        m3mulv(l, M, v);
+        l[0] += t[0]; l[1] += t[1]; l[2] += t[2];
+        int ax;
+        const double sd = cube_sd(task.push_half, l, ax, sg);
+        PushContact& c = C[nc++];
+        c.on_arm = 1;
+        // world normal = sign * column `ax` of Rb
+        c.n[0] = sg * (ax == 0 ? Rb[0] : (ax == 1 ? Rb[1] : Rb[2]));
+        c.n[1] = sg * (ax == 0 ? Rb[3] : (ax == 1 ? Rb[4] : Rb[5]));
+        c.n[2] = sg * (ax == 0 ? Rb[6] : (ax == 1 ? Rb[7] : Rb[8]));
+        double w[3];
+        m3mulv(w, Rt, v);
 #pragma unroll
-            for (int q = 0; q < 3; q++) { c.pa[q] = pt[q] + w[q]; c.pb[q] = c.pa[q] - sd * c.n[q]; }
-            c.dist = sd;
-        }
+        for (int q = 0; q < 3; q++) { c.pa[q] = pt[q] + w[q]; c.pb[q] = c.pa[q] - sd * c.n[q]; }
+        c.dist = sd;
     }
     return nc;
 }
@@ -198,39 +241,42 @@ struct PushLayout {
     static constexpr int NB = T::NB;
     static constexpr int NA = NB == 8 ? 5 : NB;   // TopoMG400: chain 0-1-2-3-4 carries the tip; TopoChain6: all six
     static constexpr int TRI = NB * (NB + 1) / 2;
-    static constexpr int MOT = TRI;               // + 3 * NB
-    static constexpr int TAB = MOT + 3 * NB;      // 12 rows x 10
+    // every section starts on an even slot and rows have even lengths: slots are stored in PAIRS (slot 2k and 2k+1 of
+    // an env are adjacent), so that the loads of a row pair up into 16-byte LDS (half as many load instructions)
+    static constexpr int MOT = (TRI + 1) & ~1;               // + 3 * NB
+    static constexpr int TAB = MOT + ((3 * NB + 1) & ~1);    // 12 rows x 10
     static constexpr int TAB_ROW = 10;
     static constexpr int TIP = TAB + 12 * TAB_ROW;
-    static constexpr int TIP_ROW = 13 + NA + NB;
+    static constexpr int TIP_ROW = (13 + NA + NB + 1) & ~1;
     static constexpr int SLOTS = TIP + 12 * TIP_ROW;
     __host__ __device__ static constexpr int tri(int i, int j) { return i <= j ? i * NB - i * (i - 1) / 2 + (j - i) : j * NB - j * (j - 1) / 2 + (i - j); }
 };
-#define PUSH_BLOCK 56 // envs per block: 56 x 492 slots x 8 B = 220 KB of the 227 KB a block may have, one block per SM
-// The PGS sweep count differs from env to env (median ~55, 2 % of the substeps run into the cap of 150) and a warp sweeps
-// until its slowest lane is done, so the 56 envs of a block are spread over 7 warps of PUSH_LANES = 8 active lanes:
-// the expected slowest-of-8 is much shorter than the slowest-of-28, and 7 warps keep all four schedulers of the SM busy
-// where 2 left half of them idle (ncu, 2 warps: issue slots 24 % busy, 48 % of the stall samples fixed-latency waits).
-#define PUSH_LANES 8
-#define PUSH_THREADS (32 * (PUSH_BLOCK / PUSH_LANES))
 
-// Robot.step_sim() with the cube in the world.  `col` = this env's column of the block's row store.
+
+// Robot.step_sim() with the cube in the world.  `col` = this env's column of the block's row store.  All 32 lanes of the
+// warp call it together; only the owner lanes (`owner`) carry an env, the others just lend a hand in the hull scan.
 // Returns the number of PGS sweeps.
 template <class T>
 __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const double* __restrict__ hull, int n_hull,
-                                         double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot, ObjState& o, const int col)
+                                         double* q, double* qd, double (&sc)[T::NB][2], const Motors<T::NB>& mot, ObjState& o, const int col, const bool owner)
 {
-    extern __shared__ double push_rows[]; // [PushLayout<T>::SLOTS][PUSH_BLOCK]; indexed directly so that the accesses are LDS / STS
+    extern __shared__ __align__(16) double push_rows[]; // [PushLayout<T>::SLOTS / 2][PUSH_BLOCK][2]; indexed directly so that the accesses are LDS / STS
     using LY = PushLayout<T>;
     constexpr int NB = T::NB, NA = LY::NA;
     constexpr double EPS = 2.2204460492503131e-16;
-#define SM(slot) push_rows[(slot) * PUSH_BLOCK + col]
+#define SM(slot) push_rows[(((slot) >> 1) * PUSH_BLOCK + col) * 2 + ((slot) & 1)]
+// same for an EVEN run-time base b and a compile-time offset k: the pair index and the parity are then constants
+#define SMB(b, k) push_rows[((((b) >> 1) + ((k) >> 1)) * PUSH_BLOCK + col) * 2 + ((k) & 1)]
     PushContact C[PUSH_MAXC];
-    int nc, ntab = 0;
-    double Rb[9], Iinv[3];
+    int nc = 0, ntab = 0;
+    double Rb[9], Iinv[3], Rt[9], pt[3], Mc[9], tc[3];
+    Kin<NB> k;
     const double mass = o.mass, minv = 1.0 / mass;
     const double lim_m = mot.max_force * ph.dt;
-    {
+#pragma unroll
+    for (int i = 0; i < 9; i++) { Mc[i] = 0.0; Rb[i] = 0.0; }
+    tc[0] = tc[1] = tc[2] = 0.0;
+    if (owner) {
         double A[NB][NB];
         robot_pre<T>(arm, ph, q, qd, sc, A);
         // motor rows, as in substep(): J = e_i, response column A[:, i]
@@ -247,12 +293,30 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
             SM(LY::MOT + 3 * i + 1) = mdinv;
             SM(LY::MOT + 3 * i + 2) = 0.0;
         }
-
-        Kin<NB> k;
         fk_sc<T>(arm, sc, k);
         mat_from_quat(o.quat, Rb);
-        nc = push_contacts<T>(arm, task, hull, n_hull, k, o, Rb, C);
-
+        nc = push_table_contacts(task, o, Rb, C);
+        // cube-local coordinates of a hull vertex v (tip body frame) are Mc v + tc
+#pragma unroll
+        for (int b2 = 0; b2 < NB; b2++)
+            if (arm.tcp_body == b2) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) Rt[i] = k.R[b2][i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) pt[i] = k.p[b2][i];
+            }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) Mc[3 * i + j] = Rb[i] * Rt[j] + Rb[3 + i] * Rt[3 + j] + Rb[6 + i] * Rt[6 + j]; // Rb^T Rt
+        const double d[3] = {pt[0] - o.pos[0], pt[1] - o.pos[1], pt[2] - o.pos[2]};
+        m3tmulv(tc, Rb, d);
+    }
+    HullScan hs;
+    push_scan(hull, n_hull, Mc, tc, task.push_half, task.push_slop, hs); // the whole warp
+    if (!owner) return 0;
+    nc = push_tip_contacts(task, hull, hs, Mc, tc, Rb, Rt, pt, C, nc);
+    {
         // cube: unconstrained velocity update about its COM (gravity, [EXT] multibody base damping, gyroscopic term)
 #pragma unroll
         for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / (task.push_inertia_per_mass[c] * mass);
@@ -321,7 +385,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
                     for (int j = 0; j < NB; j++) {
                         double u = 0;
 #pragma unroll
-                        for (int e = 0; e < NA; e++) u += A[j][e] * jr[e];
+                        for (int e = 0; e < NA; e++) u += SM(LY::tri(j, e)) * jr[e];
                         SM(base + 9 + NA + j) = u;
                         if (j < NA) den += jr[j < NA ? j : 0] * u;
                     }
@@ -385,17 +449,17 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
     struct TipRow { double jl[3], ja[3], ua[3], jr[NA], ur[NB], rhs, dinv, diagc, app; };
     auto tab_load = [&](int base, TabRow& R) {
 #pragma unroll
-        for (int x = 0; x < 3; x++) { R.ja[x] = SM(base + x); R.ua[x] = SM(base + 3 + x); }
-        R.rhs = SM(base + 6); R.dinv = SM(base + 7); R.diagc = SM(base + 8); R.app = SM(base + 9);
+        for (int x = 0; x < 3; x++) { R.ja[x] = SMB(base, x); R.ua[x] = SMB(base, 3 + x); }
+        R.rhs = SMB(base, 6); R.dinv = SMB(base, 7); R.diagc = SMB(base, 8); R.app = SMB(base, 9);
     };
     auto tip_load = [&](int base, TipRow& R) {
 #pragma unroll
-        for (int x = 0; x < 3; x++) { R.jl[x] = SM(base + x); R.ja[x] = SM(base + 3 + x); R.ua[x] = SM(base + 6 + x); }
+        for (int x = 0; x < 3; x++) { R.jl[x] = SMB(base, x); R.ja[x] = SMB(base, 3 + x); R.ua[x] = SMB(base, 6 + x); }
 #pragma unroll
-        for (int j = 0; j < NA; j++) R.jr[j] = SM(base + 9 + j);
+        for (int j = 0; j < NA; j++) R.jr[j] = SMB(base, 9 + j);
 #pragma unroll
-        for (int j = 0; j < NB; j++) R.ur[j] = SM(base + 9 + NA + j);
-        R.rhs = SM(base + 9 + NA + NB); R.dinv = SM(base + 10 + NA + NB); R.diagc = SM(base + 11 + NA + NB); R.app = SM(base + 12 + NA + NB);
+        for (int j = 0; j < NB; j++) R.ur[j] = SMB(base, 9 + NA + j);
+        R.rhs = SMB(base, 9 + NA + NB); R.dinv = SMB(base, 10 + NA + NB); R.diagc = SMB(base, 11 + NA + NB); R.app = SMB(base, 12 + NA + NB);
     };
     // table rows: directions are (0,0,1), (0,-1,0), (1,0,0) = btPlaneSpace1 of +z; the cube is the first body
     auto tab_dot = [&](const TabRow& R, int qq) {
@@ -447,7 +511,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
             const double sum = R.app + delta;
             const bool lo = sum < 0.0;
             delta = lo ? -R.app : delta;
-            SM(base + 9) = lo ? 0.0 : sum;
+            SMB(base, 9) = lo ? 0.0 : sum;
             tab_apply(R, 0, delta);
             const double dvel = delta * R.diagc;
             resid = fmax(resid, dvel * dvel);
@@ -462,7 +526,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
             const double sum = R.app + delta;
             const bool lo = sum < 0.0;
             delta = lo ? -R.app : delta;
-            SM(base + 12 + NA + NB) = lo ? 0.0 : sum;
+            SMB(base, 12 + NA + NB) = lo ? 0.0 : sum;
             tip_apply(R, delta);
             const double dvel = delta * R.diagc;
             resid = fmax(resid, dvel * dvel);
@@ -471,7 +535,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
 #pragma unroll 1
         for (int c = 0; c < ntab; c++) {
             const int b0 = LY::TAB + 3 * c * LY::TAB_ROW, b1 = b0 + LY::TAB_ROW, b2 = b1 + LY::TAB_ROW;
-            const double napp = SM(b0 + 9);
+            const double napp = SMB(b0, 9);
             if (!(napp > 0.0)) continue;
             TabRow R1, R2;
             tab_load(b1, R1); tab_load(b2, R2);
@@ -481,7 +545,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
             const double nrm2 = s1 * s1 + s2 * s2;
             if (nrm2 > lim * lim) { const double scl = lim * rsqrt(nrm2); s1 *= scl; s2 *= scl; }
             const double d1 = s1 - R1.app, d2 = s2 - R2.app;
-            SM(b1 + 9) = s1; SM(b2 + 9) = s2;
+            SMB(b1, 9) = s1; SMB(b2, 9) = s2;
             tab_apply(R1, 1, d1);
             tab_apply(R2, 2, d2);
             const double e1 = d1 * R1.diagc, e2 = d2 * R2.diagc;
@@ -490,7 +554,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
 #pragma unroll 1
         for (int c = 0; c < ntip; c++) {
             const int b0 = LY::TIP + 3 * c * LY::TIP_ROW, b1 = b0 + LY::TIP_ROW, b2 = b1 + LY::TIP_ROW, so = 9 + NA + NB;
-            const double napp = SM(b0 + so + 3);
+            const double napp = SMB(b0, so + 3);
             if (!(napp > 0.0)) continue;
             TipRow R1, R2;
             tip_load(b1, R1); tip_load(b2, R2);
@@ -500,7 +564,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
             const double nrm2 = s1 * s1 + s2 * s2;
             if (nrm2 > lim * lim) { const double scl = lim * rsqrt(nrm2); s1 *= scl; s2 *= scl; }
             const double d1 = s1 - R1.app, d2 = s2 - R2.app;
-            SM(b1 + so + 3) = s1; SM(b2 + so + 3) = s2;
+            SMB(b1, so + 3) = s1; SMB(b2, so + 3) = s2;
             tip_apply(R1, d1);
             tip_apply(R2, d2);
             const double e1 = d1 * R1.diagc, e2 = d2 * R2.diagc;
@@ -508,6 +572,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
         }
         if (resid <= ph.solver_residual_threshold) { it++; break; }
     }
+#undef SMB
 #undef SM
 #pragma unroll
     for (int i = 0; i < NB; i++) {
