@@ -250,6 +250,12 @@ def main():
         st = w.get_state()
         st[:, 2 * w.nb + 9] = np.random.RandomState(1000 + rank).randint(0, MAX_STEPS, size=n)   # the `steps` field
         w.set_state(st)
+        # the artificial phase shift makes many envs finish before their pre-computed next episode exists (they complete
+        # it inline, tg_pipeline_stalls counts them): let the reset pipeline reach its steady state before warm-up
+        g0 = torch.Generator(device=dev); g0.manual_seed(12345 + rank)
+        for _ in range(40):
+            w.step((torch.rand((n, w.act_dim), device=dev, generator=g0) - 0.5) * 0.5)
+        torch.cuda.synchronize(dev)
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
     acts = (torch.rand((W + K, n, w.act_dim), device=dev, generator=gen) - 0.5) * 0.5
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
