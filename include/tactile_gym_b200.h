@@ -62,6 +62,7 @@ extern "C" {
 #define TG_TASK_OBJECT_BALANCE 1
 #define TG_TASK_SURFACE_FOLLOW 2
 #define TG_TASK_OBJECT_PUSH 3
+#define TG_TASK_OBJECT_ROLL 4
 #define TG_SURF_N 64 /* heightfield rows = columns */
 #define TG_PUSH_NTRAJ 10 /* object_push: goals along the trajectory (object_push_env.py:233) */
 #define TG_PUSH_NFEAT 12 /* object_push: extended_feature length (object_push_env.py:611-629) */
@@ -140,7 +141,8 @@ typedef struct {
     double surf_w_norm;              /* weight of the normal-alignment term (0 for yz / xyz movement) */
     /* object_push (object_push_env.py, base_object_env.py): a free cube on the table pushed by the tip core; contact rows
      * tip hull <-> cube and cube <-> table.  draws per reset: init_obj_ang, obj_mass, OpenSimplex seed | trajectory angle */
-    int32_t push_mode, push_traj_straight, push_sparse_reward, push_pad;
+    int32_t push_mode, push_traj_straight, push_sparse_reward;
+    int32_t push_shape;              /* 0: cube vs tip hull (object_push); 1: sphere vs cylinder cap (object_roll) */
     double push_half[3];             /* cube half extents (cube.urdf) */
     double push_table_z;             /* table top (base_tactile_env.py:135-139 + table.urdf) */
     double push_mu_table, push_mu_tip; /* products of the lateralFriction pairs (object_push_env.py:218, :61-66, table.urdf) */
@@ -151,6 +153,14 @@ typedef struct {
     double push_inertia_per_mass[3]; /* box inertia / mass: changeDynamics(mass=) keeps the shape's inertia [EXT] */
     double push_term_dist;           /* 0.025 (:68) */
     double push_traj_spacing, push_traj_perturb, push_traj_offset; /* 0.025, 0.1, obj_width / 2 + spacing (:233-235, :290) */
+    /* object_roll (object_roll_env.py): a marble (sphere.urdf, radius roll_radius x the episode's scaling factor) between the
+     * table and the flat TacTip, whose core is a cylinder (ur5_with_flat_tactip.urdf:320-325).  It shares object_push's
+     * contact solve (push_* materials, push_init_pos = marble x / y, obj_mass) with push_shape = 1.  The workframe height
+     * changes per episode (2 r - embed_dist, :197-202); the goal is fixed in the TCP frame (:244-286).
+     * draws per reset: scaling_factor, embed_dist, dx, dy, goal_ang, goal_dist */
+    double roll_radius;              /* default_obj_radius 0.0025 (:166) */
+    double roll_cyl_pos[3], roll_cyl_axis[3]; /* cylinder centre / unit axis in the frame of arm.tcp_body */
+    double roll_cyl_half_len, roll_cyl_radius; /* 0.00325, 0.02 */
 } TgTask;
 
 typedef struct {
@@ -211,9 +221,10 @@ int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream);
 int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float* d_reward, uint8_t* d_done,
             uint8_t* d_term_obs, void* stream);
 
-/* object_push, observation_mode "tactile_and_feature": bind caller-owned device buffers [N][TG_PUSH_NFEAT] f32 that every
- * following tg_step / tg_reset / tg_physics_only fills with the extended_feature (object_push_env.py:611-629: TCP pos(3) +
- * rpy(3) in the work frame, goal pos(3) + rpy(3) in the work frame).  d_term_feat (may be NULL) receives the features of the
+/* object_push / object_roll, observation_mode "tactile_and_feature": bind caller-owned device buffers [N][TG_PUSH_NFEAT] f32
+ * that every following tg_step / tg_reset / tg_physics_only fills with the extended_feature (object_push_env.py:611-629: TCP
+ * pos(3) + rpy(3) in the work frame, goal pos(3) + rpy(3) in the work frame; object_roll_env.py:402-408: the goal position in
+ * the TCP frame in the first 3 entries).  d_term_feat (may be NULL) receives the features of the
  * state a finished env terminated in.  NULL d_feat unbinds. */
 int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat);
 
@@ -224,7 +235,8 @@ int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream);
 
 /* state access (parity tests, checkpointing).  Layout: per env doubles
  * [q(nb) qd(nb) tcp_pos(3) tcp_quat(4) embed edge_ang steps reset_substeps | obj pos(3) quat(4) vel(3) omg(3) scalar | goal]
- * scalar = the episode's gravity_z (object_balance) or cube mass (object_push); goal = object_push's trajectory index */
+ * scalar = the episode's gravity_z (object_balance), cube mass (object_push) or marble radius (object_roll);
+ * goal = object_push's trajectory index */
 int tg_state_size(const TgWorld* w); /* doubles per env */
 int tg_get_state(TgWorld* w, double* h_state, void* stream);
 int tg_set_state(TgWorld* w, const double* h_state, void* stream);

@@ -639,7 +639,8 @@ class OrPush(C.Structure):
         ("half", C.c_double * 3), ("table_z", C.c_double), ("mu_table", C.c_double), ("mu_tip", C.c_double),
         ("tip_k", C.c_double), ("tip_d", C.c_double), ("erp", C.c_double), ("slop", C.c_double),
         ("lin_damping", C.c_double), ("ang_damping", C.c_double), ("tip_link", C.c_int), ("n_hull", C.c_int),
-        ("hull", C.POINTER(C.c_double)), ("warmstart", C.c_double), ("ws_n", C.c_int), ("ws_feature", C.c_int * OR_MAXC),
+        ("hull", C.POINTER(C.c_double)), ("shape", C.c_int), ("radius", C.c_double), ("cyl_pos", C.c_double * 3),
+        ("cyl_axis", C.c_double * 3), ("cyl_half_len", C.c_double), ("cyl_radius", C.c_double), ("warmstart", C.c_double), ("ws_n", C.c_int), ("ws_feature", C.c_int * OR_MAXC),
         ("ws_impulse", (C.c_double * 3) * OR_MAXC), ("n_contacts", C.c_int), ("n_iters", C.c_int),
         ("normal_impulse", C.c_double * OR_MAXC), ("contact_pos", (C.c_double * 3) * OR_MAXC),
     ]
@@ -837,6 +838,142 @@ class ObjectPushOracle:
         enc = np.clip(enc, -0.25, 0.25)
         mv, ma = 0.01, 5.0 * (np.pi / 180)
         amax = np.array([mv, mv, 0.0, 0.0, 0.0, ma]); amin = -amax
+        return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
+
+    def step(self, action):
+        v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
+        self.steps += 1
+        lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
+        for _ in range(self.repeat):
+            lib().or_step_sim_push(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p))
+        self.reward, self.done = self.step_data()
+        return self.observation(), self.reward, self.done, {}
+
+
+# ---------------------------------------------------------------- object_roll task restatement
+def roll_draws(rng, rand_obj_size=False, rand_embed_dist=False, rand_init_obj_pos=False):
+    """Random draws of one ObjectRollEnv.reset in the reference's order: reset_task (scaling_factor, embed_dist;
+    object_roll_env.py:182-195), reset_object (x, y; :209-216), make_goal (goal_ang, goal_dist; :244-250)."""
+    scale = rng.uniform(1.0, 2.0) if rand_obj_size else 1.0
+    embed = rng.uniform(0.0015, 0.003) if rand_embed_dist else 0.0015
+    dx = rng.uniform(-0.009, 0.009) if rand_init_obj_pos else 0.0
+    dy = rng.uniform(-0.009, 0.009) if rand_init_obj_pos else 0.0
+    ang = rng.uniform(-np.pi, np.pi)
+    dist = rng.uniform(0.0, 0.015) if rand_init_obj_pos else rng.uniform(0.005, 0.015)
+    return np.array([scale, embed, dx, dy, ang, dist])
+
+
+def sphere_tactile_image(m, q, S, centre, radius, refimg, border_on=True):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    dep, gray, mask = refimg
+    img = np.zeros((S, S), dtype=np.uint8)
+    lib().or_tactile_image_sphere(C.byref(m), _dptr(q), C.c_int(S), _dptr(np.ascontiguousarray(centre, dtype=np.float64)), C.c_double(radius),
+                                  dep.ctypes.data_as(C.POINTER(C.c_float)), gray.ctypes.data_as(C.POINTER(C.c_float)),
+                                  mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(int(border_on)), img.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return img
+
+
+class ObjectRollOracle:
+    """Restates ObjectRollEnv (rl_envs/nonprehensile_manipulation/object_roll/object_roll_env.py) + BaseObjectEnv on top of
+    the C oracle: a marble between the table and the flat TacTip.  One env instance.  Robot.reset() runs without the
+    marble in the world; the semi-transparent goal indicator is not drawn (as for the other tasks)."""
+
+    def __init__(self, image_size=128, sensor="tactip", max_steps=250, movement_mode="xy", rand_obj_size=False, rand_embed_dist=False,
+                 rand_init_obj_pos=False, reward_mode="dense", seed=None):
+        self.S, self.sensor, self.max_steps, self.movement_mode, self.reward_mode = image_size, sensor, max_steps, movement_mode, reward_mode
+        self.rand_obj_size, self.rand_embed_dist, self.rand_init_obj_pos = rand_obj_size, rand_embed_dist, rand_init_obj_pos
+        self.typ = "flat"
+        self.default_obj_radius = 0.0025
+        self.workframe_rpy = np.array([-np.pi, 0.0, np.pi / 2])
+        lims = np.zeros((6, 2))
+        lims[0], lims[1], lims[2] = (-0.05, 0.05), (-0.05, 0.05), (-0.01, 0.01)      # :74-81
+        self.m = load_model("ur5", sensor, self.typ, [0.65, 0.0, 2 * 0.0025 - 0.0015], self.workframe_rpy, lims)
+        self.rest = rest_pose("object_roll", "ur5", sensor, self.typ, self.m)
+        self.ref = load_refimg(sensor, self.typ, image_size)
+        with open(os.path.join(ASSETS, "models", "ur5_flat_%s.json" % sensor)) as f:
+            cyl = json.load(f)["tip_collision"]
+        self.s, self.o, self.p = OrState(), OrObject(), OrPush()
+        p = self.p
+        p.shape = 1
+        p.table_z = 0.0
+        # sphere lateralFriction 10 (:226) x table 1.0, x tip 10 (:62); [EXT] products, clamped at MAX_FRICTION 10
+        p.mu_table, p.mu_tip = min(10.0 * 1.0, 10.0), min(10.0 * 10.0, 10.0)
+        p.tip_k, p.tip_d = 1.0 / (1.0 / 10.0 + 1.0 / 1e18), 100 + 0.1                # t_s_dynamics :62
+        p.erp, p.slop = 0.2, 1e-4
+        p.lin_damping, p.ang_damping = 0.04, 0.04
+        p.warmstart, p.ws_n = 0.0, 0
+        p.tip_link = self.m._names.index(sensor + "_tip_link")
+        p.n_hull = 0
+        R = np.zeros(9); lib().or_mat_from_quat(_dptr(quat_from_euler(cyl["rpy"])), _dptr(R)); R = R.reshape(3, 3)
+        ax = R @ np.array([0.0, 0.0, 1.0])
+        for c in range(3):
+            p.cyl_pos[c] = cyl["xyz"][c]; p.cyl_axis[c] = ax[c]
+        p.cyl_half_len, p.cyl_radius = cyl["length"] / 2, cyl["radius"]
+        self.mass = 0.05                                                            # sphere.urdf
+        self.repeat = int(np.floor((1.0 / 10.0) / (1.0 / 240.0)))
+        self.termination_pos_dist = 0.001
+        self.np_random = gym_np_random(seed)
+        self.steps = 0
+
+    def seed(self, seed):
+        self.np_random = gym_np_random(seed)
+
+    def reset(self, draws=None):
+        self.steps = 0
+        d = roll_draws(self.np_random, self.rand_obj_size, self.rand_embed_dist, self.rand_init_obj_pos) if draws is None else np.asarray(draws, dtype=np.float64)
+        scale, self.embed_dist, dx, dy, ang, dist = d
+        self.radius = self.default_obj_radius * scale
+        # update_workframe (:197-202)
+        self.workframe_pos = np.array([0.65, 0.0, 2 * self.radius - self.embed_dist])
+        for c in range(3):
+            self.m.workframe_pos[c] = self.workframe_pos[c]
+        pos = np.zeros(3); rpy = np.zeros(3)
+        self.last_reset_substeps = lib().or_robot_reset(C.byref(self.m), C.byref(self.s), _dptr(self.rest), _dptr(pos), _dptr(rpy))
+        o = self.o
+        o.enabled = 1; o.mass = self.mass; o.p2p_enabled = 0; o.ext_pending = 0
+        init = [0.65 + dx, 0.0 + dy, self.radius]                                    # :209-216
+        for c in range(3):
+            o.inertia[c] = 0.4 * self.mass * self.radius ** 2                         # [EXT] btSphereShape::calculateLocalInertia
+            o.com_off[c] = 0.0; o.pos[c] = init[c]; o.vel[c] = 0; o.omg[c] = 0
+        o.quat[0] = o.quat[1] = o.quat[2] = 0.0; o.quat[3] = 1.0
+        self.p.radius = self.radius
+        self.p.ws_n = 0
+        self.goal_pos_tcp = np.array([dist * np.cos(ang), dist * np.sin(ang), 0.0])   # make_goal :244-256
+        self.reward, self.done = self.step_data()
+        return self.observation()
+
+    def tcp_world(self):
+        P, Q = link_states(self.m, np.array(self.s.q[: self.m.ndof]))
+        return P[self.m.tcp_link], Q[self.m.tcp_link]
+
+    def update_goal(self):   # :258-286: the goal is fixed in the TCP frame
+        tp, tq = self.tcp_world()
+        po, qo = np.zeros(3), np.zeros(4)
+        lib().or_mul_transforms(_dptr(np.ascontiguousarray(tp)), _dptr(np.ascontiguousarray(tq)), _dptr(np.ascontiguousarray(self.goal_pos_tcp)),
+                                _dptr(np.array([0.0, 0.0, 0.0, 1.0])), _dptr(po), _dptr(qo))
+        self.goal_pos_world = po
+
+    def step_data(self):     # get_step_data :299-322, termination :324-336, rewards :338-360
+        self.update_goal()
+        d = np.linalg.norm(np.array(self.o.pos[:2]) - self.goal_pos_world[:2])
+        done = bool(d < self.termination_pos_dist or self.steps >= self.max_steps)
+        reward = (1.0 if d < self.termination_pos_dist else 0.0) if self.reward_mode == "sparse" else -d
+        return reward, done
+
+    def features(self):      # get_extended_feature_array :402-408
+        return self.goal_pos_tcp.copy()
+
+    def observation(self):
+        q = np.array(self.s.q[: self.m.ndof])
+        return {"tactile": sphere_tactile_image(self.m, q, self.S, np.array(self.o.pos[:]), self.radius, self.ref)[..., None],
+                "extended_feature": self.features()}
+
+    def encode_scale(self, action):
+        enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
+        enc[0], enc[1] = a[0], a[1]
+        enc = np.clip(enc, -0.25, 0.25)
+        mv = 0.01
+        amax = np.array([mv, mv, 0.0, 0.0, 0.0, 0.0]); amin = -amax
         return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
 
     def step(self, action):

@@ -1096,6 +1096,35 @@ static void plane_space1(const double n[3], double p[3], double q[3]) /* [EXT] b
 static int push_contacts(const OrModel* m, const Kin* k, const OrObject* o, const OrPush* P, const m3 Rb, PushContact* C)
 {
     int nc = 0;
+    if (P->shape == 1) {
+        /* object_roll: sphere <-> table, sphere <-> cap of the tip core's cylinder */
+        const double dtk0 = m->dt * P->tip_k + P->tip_d, dtk = dtk0 < 2.2204460492503131e-16 ? 2.2204460492503131e-16 : dtk0;
+        const double dist = o->pos[2] - P->radius - P->table_z;
+        if (dist <= P->slop) {
+            PushContact* c = &C[nc++];
+            c->on_arm = 0; v3set(c->n, 0, 0, 1);
+            v3set(c->pb, o->pos[0], o->pos[1], o->pos[2] - P->radius); v3cpy(c->pa, c->pb);
+            c->dist = dist; c->mu = P->mu_table; c->cfm = 0.0; c->erp = P->erp; c->feature = 0;
+        }
+        const int tl = P->tip_link;
+        v3 cc, ax, d, t;
+        m3mulv(t, k->Rl[tl], P->cyl_pos); v3add(cc, k->pl[tl], t);
+        m3mulv(ax, k->Rl[tl], P->cyl_axis);
+        v3sub(d, o->pos, cc);
+        double h = v3dot(d, ax);
+        if (h < 0) { v3scale(ax, ax, -1.0); h = -h; }            /* the cap that faces the sphere */
+        const v3 lat = {d[0] - h * ax[0], d[1] - h * ax[1], d[2] - h * ax[2]};
+        const double sd = h - P->cyl_half_len - P->radius;
+        if (sd <= P->slop && v3dot(lat, lat) <= P->cyl_radius * P->cyl_radius) {
+            PushContact* c = &C[nc++];
+            c->on_arm = 1;
+            v3scale(c->n, ax, -1.0);                               /* out of the sphere, towards the tip */
+            for (int q = 0; q < 3; q++) { c->pb[q] = o->pos[q] - P->radius * ax[q]; c->pa[q] = c->pb[q] - sd * ax[q]; }
+            c->dist = sd; c->mu = P->mu_tip; c->feature = 8;
+            c->cfm = (1.0 / dtk) / m->dt; c->erp = (m->dt * P->tip_k) / dtk;
+        }
+        return nc;
+    }
     /* cube <-> table: cube vertices at or below the table top */
     for (int v = 0; v < 8 && nc < 4; v++) {
         v3 l = {(v & 1) ? P->half[0] : -P->half[0], (v & 2) ? P->half[1] : -P->half[1], (v & 4) ? P->half[2] : -P->half[2]}, w;
@@ -1341,4 +1370,44 @@ void or_step_sim_push(const OrModel* m, OrState* s, OrObject* o, OrPush* P)
         const double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
         for (int c = 0; c < 4; c++) o->quat[c] = qn[c] / nn;
     }
+}
+
+/* ---- object_roll tactile image: the stimulus is a sphere.  [EXT] pybullet draws a <sphere> visual as a tessellated
+ * mesh whose resolution is not recoverable here; the analytic sphere is rendered instead (a 32-segment tessellation
+ * differs from it by < 0.5 % of the radius = 0.2 output LSB at the flat TacTip).  Depth per pixel = nearest ray / sphere
+ * intersection, then TactileSensor.t_s_camera (tactile_sensor.py:261-294) as in or_tactile_image. */
+void or_tactile_image_sphere(const OrModel* m, const double* q, int S, const double centre[3], double radius,
+                             const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
+                             int border_on, unsigned char* img_out)
+{
+    double eye[3], fwd[3], up[3], right[3];
+    or_camera_frame(m, q, eye, fwd, up, right);
+    const double th = tan(m->fov_deg * (M_PI / 180.0) / 2.0);
+    v3 d0; v3sub(d0, centre, eye);
+    const double s[3] = {v3dot(d0, right), v3dot(d0, up), v3dot(d0, fwd)};
+    const double ss = v3dot(s, s) - radius * radius;
+    const float eps = (float)1e-4, maxpen = (float)0.05;
+    for (int r = 0; r < S; r++)
+        for (int c = 0; c < S; c++) {
+            const int i = r * S + c;
+            float cur = nodef_dep[i];
+            const double xn = (c + 0.5) / S * 2 - 1, yn = 1 - (r + 0.5) / S * 2;
+            const double d[3] = {xn * th, yn * th, 1.0};
+            const double dd = v3dot(d, d), ds = v3dot(d, s), disc = ds * ds - dd * ss;
+            if (disc >= 0) {
+                const double z = (ds - sqrt(disc)) / dd;
+                if (z >= m->near_ && z <= m->far_) {
+                    const float dep = (float)(m->far_ / (m->far_ - m->near_) * (1.0 - m->near_ / z));
+                    if (dep < cur) cur = dep;
+                }
+            }
+            float diff = cur - nodef_dep[i];
+            if (diff >= -eps && diff <= eps) diff = 0.0f;
+            const float pen = fabsf(diff);
+            const float cl = pen < 0.0f ? 0.0f : (pen > maxpen ? maxpen : pen);
+            const float val = (cl / maxpen) * 255.0f;
+            unsigned char o = (unsigned char)val;
+            if (border_on && border_mask[i] == 1) o = (unsigned char)nodef_gray[i];
+            img_out[i] = o;
+        }
 }

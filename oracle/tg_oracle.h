@@ -177,6 +177,13 @@ typedef struct {
     int tip_link;            /* bullet link index owning the hull */
     int n_hull;
     const double* hull;      /* [n_hull][3], tip LINK frame */
+    /* object_roll (rl_envs/nonprehensile_manipulation/object_roll/object_roll_env.py): the object is a SPHERE (sphere.urdf,
+     * radius 0.0025 x globalScaling) between the table and the flat TacTip's core, a CYLINDER (ur5_with_flat_tactip.urdf:
+     * length 0.0065, radius 0.02).  shape 1 selects: sphere <-> table = one point below the centre; sphere <-> cylinder =
+     * one point on the cap facing the sphere while the centre projects inside the cap (rim / side contacts not generated) */
+    int shape;               /* 0 cube vs hull (object_push), 1 sphere vs cylinder cap (object_roll) */
+    double radius;           /* sphere radius this episode */
+    double cyl_pos[3], cyl_axis[3], cyl_half_len, cyl_radius; /* cylinder centre / unit axis in the tip LINK frame */
     /* warm starting [EXT]: impulses (normal, friction 1, friction 2) the contact features ended the previous
      * stepSimulation with; part of the env state */
     double warmstart;        /* m_warmstartingFactor 0.85; 0 = off */
@@ -189,6 +196,10 @@ typedef struct {
 } OrPush;
 /* Robot.step_sim() with the cube in the world: gravity compensation + stepSimulation (motor + contact rows) */
 void or_step_sim_push(const OrModel* m, OrState* s, OrObject* cube, OrPush* p);
+/* object_roll tactile image: analytic sphere composited over nodef_dep, then the t_s_camera post-process */
+void or_tactile_image_sphere(const OrModel* m, const double* q, int S, const double centre[3], double radius,
+                             const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
+                             int border_on, unsigned char* img_out);
 
 #ifdef __cplusplus
 }

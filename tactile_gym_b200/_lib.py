@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("TG_LIB_OVERRIDE") or os.path.join(HERE, "libtactile_g
 
 TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 8
 TG_TOPO_CHAIN6, TG_TOPO_MG400 = 0, 1
-TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE, TG_TASK_SURFACE_FOLLOW, TG_TASK_OBJECT_PUSH = 0, 1, 2, 3
+TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE, TG_TASK_SURFACE_FOLLOW, TG_TASK_OBJECT_PUSH, TG_TASK_OBJECT_ROLL = 0, 1, 2, 3, 4
 TG_PUSH_NTRAJ, TG_PUSH_NFEAT = 10, 12
 TG_PUSH_WORK, TG_PUSH_WORK_DRIVE, TG_PUSH_TCP_TYRZ, TG_PUSH_TCP_TXTYRZ = 0, 1, 2, 3
 
@@ -53,11 +53,12 @@ class TgTask(C.Structure):
         ("obj_term_deg", C.c_double), ("obj_term_pos", C.c_double), ("p2p_erp", C.c_double), ("p2p_max_impulse", C.c_double),
         ("surf_pos", D3), ("surf_grid", C.c_double), ("surf_range", C.c_double), ("surf_interp", C.c_double),
         ("surf_extent", C.c_double), ("surf_embed", C.c_double), ("surf_drive", C.c_double), ("surf_w_norm", C.c_double),
-        ("push_mode", C.c_int32), ("push_traj_straight", C.c_int32), ("push_sparse_reward", C.c_int32), ("push_pad", C.c_int32),
+        ("push_mode", C.c_int32), ("push_traj_straight", C.c_int32), ("push_sparse_reward", C.c_int32), ("push_shape", C.c_int32),
         ("push_half", D3), ("push_table_z", C.c_double), ("push_mu_table", C.c_double), ("push_mu_tip", C.c_double),
         ("push_tip_k", C.c_double), ("push_tip_d", C.c_double), ("push_erp", C.c_double), ("push_slop", C.c_double),
         ("push_lin_damping", C.c_double), ("push_ang_damping", C.c_double), ("push_init_pos", D3), ("push_inertia_per_mass", D3),
         ("push_term_dist", C.c_double), ("push_traj_spacing", C.c_double), ("push_traj_perturb", C.c_double), ("push_traj_offset", C.c_double),
+        ("roll_radius", C.c_double), ("roll_cyl_pos", D3), ("roll_cyl_axis", D3), ("roll_cyl_half_len", C.c_double), ("roll_cyl_radius", C.c_double),
     ]
 
 

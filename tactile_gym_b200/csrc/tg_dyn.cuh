@@ -777,7 +777,13 @@ TGD void tcp_world(const TgArm& arm, const Kin<T::NB>& k, double* pos, double* q
     quat_from_mat(quat, R);
 }
 
+TGD void world_to_work_at(const TgTask& task, const double* wf_pos, const double* pos, const double* quat, double* wpos, double* wrpy);
 TGD void world_to_work(const TgTask& task, const double* pos, const double* quat, double* wpos, double* wrpy)
+{
+    world_to_work_at(task, task.workframe_pos, pos, quat, wpos, wrpy);
+}
+// same with an explicit workframe origin (object_roll moves it every episode, object_roll_env.py:197-202)
+TGD void world_to_work_at(const TgTask& task, const double* wf_pos, const double* pos, const double* quat, double* wpos, double* wrpy)
 {
     // worldframe_to_workframe (base_robot_arm.py:62-74): rpy -> quat -> inverse workframe -> rpy
     double rpy_w[3], qw[4], wq[4], wqi[4], R[9], d[3], oq[4];
@@ -788,7 +794,7 @@ TGD void world_to_work(const TgTask& task, const double* pos, const double* quat
     mat_from_quat(wqi, R);
     // inverse transform: p' = R^-1 (p - t) computed as bullet does: inv_pos = -(R^-1 t); out = inv_pos + R^-1 p
     double it[3], ip[3];
-    m3mulv(it, R, task.workframe_pos);
+    m3mulv(it, R, wf_pos);
     m3mulv(ip, R, pos);
     d[0] = -it[0] + ip[0]; d[1] = -it[1] + ip[1]; d[2] = -it[2] + ip[2];
     wpos[0] = d[0]; wpos[1] = d[1]; wpos[2] = d[2];

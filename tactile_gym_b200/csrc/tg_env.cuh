@@ -255,7 +255,7 @@ TGD int ik_chunk(const TgArm& arm, double* q, const double* tpos, const double* 
 // (surface_follow: centre_h = the new surface's height at the grid centre, base_surface_env.py:549-573)
 TGD void reset_target(const TgTask& task, double embed, double centre_h, double* tpos, double* targ_orn)
 {
-    const bool balance = task.task == TG_TASK_OBJECT_BALANCE || task.task == TG_TASK_OBJECT_PUSH;
+    const bool balance = task.task == TG_TASK_OBJECT_BALANCE || task.task == TG_TASK_OBJECT_PUSH || task.task == TG_TASK_OBJECT_ROLL;
     double wq[4], tq[4], R[9], t[3], oq[4], rpy[3];
     const double lp[3] = {0.0, 0.0, balance ? 0.0 : embed}; // update_init_pose: edge_follow_env.py:301-309 / base_object_env.py:104-111
     quat_from_euler(task.workframe_rpy, wq);
@@ -264,6 +264,7 @@ TGD void reset_target(const TgTask& task, double embed, double centre_h, double*
     m3mulv(t, R, lp);
     tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
     if (task.task == TG_TASK_SURFACE_FOLLOW) { tpos[0] = task.surf_pos[0]; tpos[1] = task.surf_pos[1]; tpos[2] = task.surf_pos[2] + centre_h - embed; }
+    if (task.task == TG_TASK_OBJECT_ROLL) tpos[2] = centre_h; // update_workframe (object_roll_env.py:197-202): the caller passes 2 r - embed_dist
     quat_mul(oq, wq, tq);
     euler_from_quat(oq, rpy);
     quat_from_euler(rpy, targ_orn);
@@ -293,6 +294,8 @@ __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, c
     r.embed = balance ? r.draw[1] : r.draw[0];
     r.edge_ang = balance ? 0.0 : r.draw[1];
     if (task.task == TG_TASK_OBJECT_PUSH) { r.embed = 0.0; r.edge_ang = 0.0; }
+    // object_roll draws: scaling_factor, embed_dist, dx, dy, goal_ang, goal_dist
+    if (task.task == TG_TASK_OBJECT_ROLL) { r.embed = r.draw[1]; r.edge_ang = 0.0; }
     r.surf_it = SURF_PTS; r.hmin = 0.f; r.hmax = 0.f;
     if (task.task == TG_TASK_SURFACE_FOLLOW) {
         r.embed = task.surf_embed;
@@ -332,6 +335,7 @@ __device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph
         }
         centre_h = H[(SURF_N / 2) * SURF_N + SURF_N / 2];
     }
+    if (task.task == TG_TASK_OBJECT_ROLL) centre_h = 2.0 * (task.roll_radius * r.draw[0]) - r.embed; // this episode's workframe height
     double tpos[3], targ_orn[4];
     reset_target(task, r.embed, centre_h, tpos, targ_orn);
     if (r.ik_it >= 0) {
@@ -418,6 +422,30 @@ __device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, 
         meta[6] = (double)r.hmin; meta[7] = (double)r.hmax; // float32 height range (the raster's first slab bound)
 #pragma unroll
         for (int i = 0; i < 12; i++) out.stim[i] = 0.0;
+    } else if (task.task == TG_TASK_OBJECT_ROLL) {
+        // reset_object (object_roll_env.py:204-236): the marble back on the table under the tip (+ random offset), at rest;
+        // make_goal (:238-256): goal at (dist, ang) in the TCP frame.  The episode's radius and workframe height ride in
+        // the object's spare slots (ext_pos[0], ext_pos[1]); the goal in traj[0..1].
+        ObjState& o = out.obj;
+        const double rad = task.roll_radius * r.draw[0];
+        o.pos[0] = task.push_init_pos[0] + r.draw[2]; o.pos[1] = task.push_init_pos[1] + r.draw[3]; o.pos[2] = rad;
+        o.quat[0] = 0.0; o.quat[1] = 0.0; o.quat[2] = 0.0; o.quat[3] = 1.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { o.vel[c] = 0.0; o.omg[c] = 0.0; }
+        o.ext_pos[0] = rad; o.ext_pos[1] = 2.0 * rad - r.embed; o.ext_pos[2] = 0.0;
+        o.ext_pending = 0; o.pivot_z = 0.0;
+        o.mass = task.obj_mass; o.grav_z = task.obj_mass;
+#pragma unroll 1
+        for (int c = 0; c < PUSH_TRAJ_SZ; c++) out.traj[c] = 0.0;
+        double sn, cs;
+        sincos(r.draw[4], &sn, &cs);
+        out.traj[0] = r.draw[5] * cs; out.traj[1] = r.draw[5] * sn;
+        out.goal = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) out.stim[i] = 0.0;
+        out.stim[0] = rad;
+#pragma unroll
+        for (int i = 0; i < 3; i++) out.stim[9 + i] = o.pos[i];
     } else if (task.task == TG_TASK_OBJECT_PUSH) {
         // reset_object (object_push_env.py:204-229): cube back at init_obj_pos, yaw pi/2 + init_obj_ang, at rest;
         // make_goal (:322-333): new trajectory, first goal; BaseObjectEnv.reset then calls get_step_data() once, whose
@@ -571,11 +599,20 @@ TGD void consume_standby(const EnvBuffers& b, int e)
     atomicExch(&b.sb_ready[e], SB_EMPTY);
 }
 
-// object_push: the extended feature of env e's live state (after a reset / standby swap)
+// get_extended_feature_array (object_roll_env.py:402-408): the goal position in the TCP frame
+TGD void roll_features(const double* traj, float* out)
+{
+    out[0] = (float)traj[0]; out[1] = (float)traj[1]; out[2] = 0.0f;
+#pragma unroll
+    for (int i = 3; i < TG_PUSH_NFEAT; i++) out[i] = 0.0f;
+}
+
+// object_push / object_roll: the extended feature of env e's live state (after a reset / standby swap)
 TGD void write_live_features(const TgTask& task, const EnvBuffers& b, int e)
 {
     if (!b.feat || !b.traj) return;
     const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
+    if (task.task == TG_TASK_OBJECT_ROLL) { roll_features(tr, b.feat + (size_t)e * TG_PUSH_NFEAT); return; }
     push_features(task, b.tcp + (size_t)e * 7, b.tcp + (size_t)e * 7 + 3, tr, tr[2 * PUSH_NTRAJ], b.goal[e], b.feat + (size_t)e * TG_PUSH_NFEAT);
 }
 
@@ -638,12 +675,13 @@ TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
 // has no standby blocks: its episodes are long and its reset short, so each step thread advances its own env's standby
 // slot by one quantum after the step.
 template <class T, int TASK>
-__global__ void __launch_bounds__(TASK == TG_TASK_OBJECT_PUSH ? PUSH_THREADS : 128)
+__global__ void __launch_bounds__((TASK == TG_TASK_OBJECT_PUSH || TASK == TG_TASK_OBJECT_ROLL) ? PUSH_THREADS : 128)
 step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
             EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
 {
     constexpr int NB = T::NB;
-    constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, push = TASK == TG_TASK_OBJECT_PUSH, surface = TASK == TG_TASK_SURFACE_FOLLOW;
+    constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, roll = TASK == TG_TASK_OBJECT_ROLL, surface = TASK == TG_TASK_SURFACE_FOLLOW;
+    constexpr bool push = TASK == TG_TASK_OBJECT_PUSH || roll; // object_roll runs on object_push's contact machinery
     int e;
     int col = 0;       // object_push: this env's column in the block's shared-memory row store
     bool owner = true; // object_push: lanes 0..PUSH_LANES-1 of a warp each step an env; the others only help in the hull scan
@@ -692,7 +730,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
             const double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)b.hf_cur[e]) * SURF_META;
             enc[0] = meta[1] * task.surf_drive; enc[1] = meta[2] * task.surf_drive;
         }
-        if (push) {
+        if (push && !roll) {
             // ObjectPushEnv.encode_actions (object_push_env.py:369-454)
             if (task.push_mode == TG_PUSH_WORK_DRIVE) enc[0] = task.act_max;
             if (task.push_mode == TG_PUSH_TCP_TYRZ || task.push_mode == TG_PUSH_TCP_TXTYRZ) {
@@ -720,7 +758,10 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         }
         // tcp_velocity_control (base_robot_arm.py:281-332)
         double wp[3], wr[3];
-        world_to_work(task, tp, tq, wp, wr);
+        if (roll) {
+            const double wf[3] = {task.workframe_pos[0], task.workframe_pos[1], b.obj_ext[(size_t)e * 4 + 1]}; // this episode's workframe
+            world_to_work_at(task, wf, tp, tq, wp, wr);
+        } else world_to_work(task, tp, tq, wp, wr);
 #pragma unroll
         for (int s = 0; s < 6; s++) {
             const double cur = s < 3 ? wp[s] : wr[s - 3];
@@ -783,7 +824,14 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     double tp[3], tq[4];
     tcp_world<T>(arm, k, tp, tq);
     float r; unsigned char d;
-    if (push) {
+    if (roll) {
+        const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
+        roll_step_data(task, ob, tp, tq, tr[0], tr[1], steps, &r, &d);
+        double* st = b.stim + (size_t)e * 12;
+        st[0] = ob.ext_pos[0]; st[9] = ob.pos[0]; st[10] = ob.pos[1]; st[11] = ob.pos[2];
+        float* f = (d && autoreset && b.pipeline) ? b.term_feat : b.feat;
+        if (f) roll_features(tr, f + (size_t)e * TG_PUSH_NFEAT);
+    } else if (push) {
         const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
         int goal = b.goal[e];
         push_step_data(task, ob, tq, tr, tr[2 * PUSH_NTRAJ], goal, steps, &r, &d);

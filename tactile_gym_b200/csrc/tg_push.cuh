@@ -227,6 +227,42 @@ __device__ __noinline__ int push_tip_contacts(const TgTask& task, const double* 
     return nc;
 }
 
+// object_roll narrow phase (owner lane): sphere <-> table = one point below the centre; sphere <-> the cap of the tip
+// core's cylinder that faces it, while the centre projects inside the cap (rim / side contacts not generated)
+// (oracle/tg_oracle.c:push_contacts, shape 1)
+TGD int roll_contacts(const TgTask& task, const ObjState& o, double radius, const double* Rt, const double* pt, PushContact* C)
+{
+    int nc = 0;
+    const double dist = o.pos[2] - radius - task.push_table_z;
+    if (dist <= task.push_slop) {
+        PushContact& c = C[nc++];
+        c.on_arm = 0;
+        c.n[0] = 0; c.n[1] = 0; c.n[2] = 1;
+        c.pb[0] = o.pos[0]; c.pb[1] = o.pos[1]; c.pb[2] = o.pos[2] - radius;
+#pragma unroll
+        for (int q = 0; q < 3; q++) c.pa[q] = c.pb[q];
+        c.dist = dist;
+    }
+    double cc[3], ax[3], t[3];
+    m3mulv(t, Rt, task.roll_cyl_pos);
+    m3mulv(ax, Rt, task.roll_cyl_axis);
+#pragma unroll
+    for (int q = 0; q < 3; q++) cc[q] = pt[q] + t[q];
+    const double d[3] = {o.pos[0] - cc[0], o.pos[1] - cc[1], o.pos[2] - cc[2]};
+    double h = v3dot(d, ax);
+    if (h < 0) { ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; h = -h; } // the cap that faces the sphere
+    const double lat[3] = {d[0] - h * ax[0], d[1] - h * ax[1], d[2] - h * ax[2]};
+    const double sd = h - task.roll_cyl_half_len - radius;
+    if (sd <= task.push_slop && v3dot(lat, lat) <= task.roll_cyl_radius * task.roll_cyl_radius) {
+        PushContact& c = C[nc++];
+        c.on_arm = 1;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { c.n[q] = -ax[q]; c.pb[q] = o.pos[q] - radius * ax[q]; c.pa[q] = c.pb[q] - sd * ax[q]; }
+        c.dist = sd;
+    }
+    return nc;
+}
+
 // ---- shared-memory staging of one env's constraint rows -------------------------------------------------------------
 // A substep's rows are read ~55 times (PGS sweeps) each: they live in shared memory, one COLUMN per env
 // (slot s of thread t at sm[s * stride + t]: consecutive threads touch consecutive doubles, no bank conflicts).
@@ -269,7 +305,10 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
 #define SMB(b, k) push_rows[((((b) >> 1) + ((k) >> 1)) * PUSH_BLOCK + col) * 2 + ((k) & 1)]
     PushContact C[PUSH_MAXC];
     int nc = 0, ntab = 0;
-    double Rb[9], Iinv[3], Rt[9], pt[3], Mc[9], tc[3];
+    const bool sphere = task.push_shape == 1; // object_roll: the episode's marble radius rides in o.ext_pos[0]
+    double Rb[9], Iinv[3], Rt[9], pt[3], Mc[9], tc[3], ipm[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) ipm[c] = sphere ? 0.4 * o.ext_pos[0] * o.ext_pos[0] : task.push_inertia_per_mass[c]; // [EXT] btSphereShape: 2/5 m r^2
     Kin<NB> k;
     const double mass = o.mass, minv = 1.0 / mass;
     const double lim_m = mot.max_force * ph.dt;
@@ -295,7 +334,7 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
         }
         fk_sc<T>(arm, sc, k);
         mat_from_quat(o.quat, Rb);
-        nc = push_table_contacts(task, o, Rb, C);
+        if (!sphere) nc = push_table_contacts(task, o, Rb, C);
         // cube-local coordinates of a hull vertex v (tip body frame) are Mc v + tc
 #pragma unroll
         for (int b2 = 0; b2 < NB; b2++)
@@ -313,18 +352,19 @@ __device__ __noinline__ int substep_push(const TgArm& arm, const TgPhysics& ph, 
         m3tmulv(tc, Rb, d);
     }
     HullScan hs;
-    push_scan(hull, n_hull, Mc, tc, task.push_half, task.push_slop, hs); // the whole warp
+    if (!sphere) push_scan(hull, n_hull, Mc, tc, task.push_half, task.push_slop, hs); // the whole warp
     if (!owner) return 0;
-    nc = push_tip_contacts(task, hull, hs, Mc, tc, Rb, Rt, pt, C, nc);
+    if (sphere) nc = roll_contacts(task, o, o.ext_pos[0], Rt, pt, C);
+    else nc = push_tip_contacts(task, hull, hs, Mc, tc, Rb, Rt, pt, C, nc);
     {
         // cube: unconstrained velocity update about its COM (gravity, [EXT] multibody base damping, gyroscopic term)
 #pragma unroll
-        for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / (task.push_inertia_per_mass[c] * mass);
+        for (int c = 0; c < 3; c++) Iinv[c] = 1.0 / (ipm[c] * mass);
         {
             double wl[3], Iw[3], gy[3], al[3], aw[3];
             m3tmulv(wl, Rb, o.omg);
 #pragma unroll
-            for (int c = 0; c < 3; c++) Iw[c] = task.push_inertia_per_mass[c] * mass * wl[c];
+            for (int c = 0; c < 3; c++) Iw[c] = ipm[c] * mass * wl[c];
             v3cross(gy, wl, Iw);
             const double ka = task.push_ang_damping * (1.0 + sqrt(v3dot(o.omg, o.omg))), kl = task.push_lin_damping * (1.0 + sqrt(v3dot(o.vel, o.vel)));
 #pragma unroll
@@ -694,4 +734,21 @@ TGD void push_features(const TgTask& task, const double* tcp_pos, const double* 
     out[3] = (float)wr[0]; out[4] = (float)wr[1]; out[5] = (float)wr[2];
     out[6] = (float)push_goal_x(task, third, gi); out[7] = (float)traj[gi]; out[8] = 0.0f;
     out[9] = 0.0f; out[10] = 0.0f; out[11] = (float)traj[PUSH_NTRAJ + gi];
+}
+
+// ---------------------------------------------------------------- object_roll task level
+// update_goal (object_roll_env.py:258-286): the goal is fixed in the TCP frame -> world; get_step_data / termination /
+// rewards (:299-360): xy distance marble <-> goal, done below 1 mm
+TGD void roll_step_data(const TgTask& task, const ObjState& o, const double* tcp_pos, const double* tcp_quat, double gx, double gy,
+                        int steps, float* reward, unsigned char* done)
+{
+    double R[9], t[3];
+    const double g[3] = {gx, gy, 0.0};
+    mat_from_quat(tcp_quat, R);
+    m3mulv(t, R, g);
+    const double dx = o.pos[0] - (tcp_pos[0] + t[0]), dy = o.pos[1] - (tcp_pos[1] + t[1]);
+    const double d = sqrt(dx * dx + dy * dy);
+    const bool near_ = d < task.push_term_dist;
+    *reward = task.push_sparse_reward ? (near_ ? 1.0f : 0.0f) : (float)(-(1.0 * d));
+    *done = (near_ || steps >= task.max_steps) ? 1 : 0;
 }

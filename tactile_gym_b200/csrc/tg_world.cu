@@ -12,6 +12,7 @@
 #include "tg_env.cuh"
 #include "tg_raster.cuh"
 #include "tg_raster_hf.cuh"
+#include "tg_raster_sphere.cuh"
 
 static thread_local std::string g_err;
 
@@ -86,7 +87,13 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->arm.topo == TG_TOPO_MG400 && cfg->arm.nb != 8) return fail(TG_EINVAL, "MG400 topology needs nb == 8");
     if (cfg->arm.topo != TG_TOPO_CHAIN6 && cfg->arm.topo != TG_TOPO_MG400) return fail(TG_EINVAL, "unknown topology %d", cfg->arm.topo);
     if (cfg->task.task != TG_TASK_EDGE_FOLLOW && cfg->task.task != TG_TASK_OBJECT_BALANCE && cfg->task.task != TG_TASK_SURFACE_FOLLOW &&
-        cfg->task.task != TG_TASK_OBJECT_PUSH) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+        cfg->task.task != TG_TASK_OBJECT_PUSH && cfg->task.task != TG_TASK_OBJECT_ROLL) return fail(TG_EUNSUPPORTED, "task %d not built yet", cfg->task.task);
+    if (cfg->task.task == TG_TASK_OBJECT_ROLL) {
+        if (cfg->task.push_shape != 1 || !(cfg->task.roll_radius > 0 && cfg->task.obj_mass > 0 && cfg->task.roll_cyl_radius > 0))
+            return fail(TG_EINVAL, "object_roll needs push_shape = 1, a marble radius / mass and the tip cylinder");
+        if (cfg->task.n_draws != 6) return fail(TG_EINVAL, "object_roll consumes 6 draws per reset");
+        if (cfg->arm.topo != TG_TOPO_CHAIN6) return fail(TG_EUNSUPPORTED, "object_roll is built for the UR5 (the reference has no MG400 rest pose for it)");
+    }
     if (cfg->task.task == TG_TASK_OBJECT_PUSH) {
         if (!cfg->h_tip_hull || cfg->n_tip_hull <= 0) return fail(TG_EINVAL, "object_push needs the tip core hull (h_tip_hull)");
         if (!(cfg->task.push_half[0] > 0 && cfg->task.push_half[1] > 0 && cfg->task.push_half[2] > 0 && cfg->task.push_inertia_per_mass[0] > 0 &&
@@ -98,8 +105,8 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->task.task == TG_TASK_OBJECT_BALANCE && !(cfg->task.obj_mass > 0 && cfg->task.obj_inertia[0] > 0 && cfg->task.obj_inertia[1] > 0 && cfg->task.obj_inertia[2] > 0))
         return fail(TG_EINVAL, "object_balance needs a free object with positive mass and inertia");
     if (cfg->task.n_draws < 0 || cfg->task.n_draws > TG_MAXDRAW) return fail(TG_EINVAL, "n_draws must be in 0..%d", TG_MAXDRAW);
-    if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
-        if (cfg->sensor.n_prim != 0) return fail(TG_EINVAL, "surface_follow draws the per-env heightfield: n_prim must be 0");
+    if (cfg->task.task == TG_TASK_SURFACE_FOLLOW || cfg->task.task == TG_TASK_OBJECT_ROLL) {
+        if (cfg->sensor.n_prim != 0) return fail(TG_EINVAL, "surface_follow / object_roll draw a per-env heightfield / sphere: n_prim must be 0");
     } else if (cfg->sensor.n_prim <= 0 || cfg->sensor.n_prim > RASTER_MAXPRIM) return fail(TG_EINVAL, "n_prim must be in 1..%d", RASTER_MAXPRIM);
     if (!cfg->sensor.h_nodef_dep || !cfg->sensor.h_nodef_gray || !cfg->sensor.h_border_mask || !cfg->h_rest_q ||
         (cfg->sensor.n_prim > 0 && (!cfg->sensor.h_prims || !cfg->sensor.h_prim_nv)))
@@ -156,6 +163,11 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         return rc;
     }
     w->standby_blocks = b.pipeline ? std::max(8, std::min(64, w->sm_count / 2)) : 0;
+    if (cfg->task.task == TG_TASK_OBJECT_ROLL) {
+        w->standby_blocks = 0;
+        w->push_smem = sizeof(double) * PushLayout<TopoChain6>::SLOTS * PUSH_BLOCK;
+        CK(cudaFuncSetAttribute(step_kernel<TopoChain6, TG_TASK_OBJECT_ROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
+    }
     if (cfg->task.task == TG_TASK_OBJECT_PUSH) {
         // object_push steps PUSH_BLOCK envs per block with its constraint rows in dynamic shared memory (tg_push.cuh);
         // standby rebuilds ride in the step threads, not in extra blocks
@@ -177,6 +189,14 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             return rc;
         }
     }
+    if (cfg->task.task == TG_TASK_OBJECT_ROLL) {
+        if ((rc = dalloc(w, &b.traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.sb_traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.goal, n)) ||
+            (rc = dalloc(w, &b.sb_goal, n))) {
+            tg_destroy(w);
+            return rc;
+        }
+        b.hull = nullptr; b.n_hull = 0;
+    }
     if (cfg->task.task == TG_TASK_OBJECT_PUSH) {
         double* hull = nullptr;
         if ((rc = dalloc(w, &b.traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.sb_traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.goal, n)) ||
@@ -187,7 +207,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         CK(cudaMemcpy(hull, cfg->h_tip_hull, sizeof(double) * 3 * cfg->n_tip_hull, cudaMemcpyHostToDevice));
         b.hull = hull; b.n_hull = cfg->n_tip_hull;
     }
-    if (cfg->task.task == TG_TASK_OBJECT_BALANCE || cfg->task.task == TG_TASK_OBJECT_PUSH) {
+    if (cfg->task.task == TG_TASK_OBJECT_BALANCE || cfg->task.task == TG_TASK_OBJECT_PUSH || cfg->task.task == TG_TASK_OBJECT_ROLL) {
         if ((rc = dalloc(w, &b.obj, (size_t)13 * n)) || (rc = dalloc(w, &b.obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.grav, n)) ||
             (rc = dalloc(w, &b.sb_obj, (size_t)13 * n)) || (rc = dalloc(w, &b.sb_obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.sb_grav, n))) {
             tg_destroy(w);
@@ -333,7 +353,8 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
     RasterArgs r = w->ra;
     r.obs = d_obs; r.mask = mask;
     if (terminal_state) { r.cam = w->eb.term_cam; r.stim = w->eb.term_stim; r.hf_flip = 1; }
-    if (r.hf) raster_hf_kernel<<<w->raster_grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
+    if (w->cfg.task.task == TG_TASK_OBJECT_ROLL) raster_sphere_kernel<<<std::min((w->n + 7) / 8, 8 * w->sm_count), SPH_THREADS, 0, st>>>(r);
+    else if (r.hf) raster_hf_kernel<<<w->raster_grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
     else raster_kernel<<<w->raster_grid, RASTER_THREADS, w->raster_smem, st>>>(r);
     w->launches++;
     CK(cudaGetLastError());
@@ -356,6 +377,7 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
     case TG_TASK_OBJECT_BALANCE: STEP_LAUNCH(Topo, TG_TASK_OBJECT_BALANCE, grid, 128, 0); break;          \
     case TG_TASK_SURFACE_FOLLOW: STEP_LAUNCH(Topo, TG_TASK_SURFACE_FOLLOW, grid, 128, 0); break;          \
     case TG_TASK_OBJECT_PUSH: STEP_LAUNCH(Topo, TG_TASK_OBJECT_PUSH, pgrid, PUSH_THREADS, w->push_smem); break; \
+    case TG_TASK_OBJECT_ROLL: STEP_LAUNCH(Topo, TG_TASK_OBJECT_ROLL, pgrid, PUSH_THREADS, w->push_smem); break; \
     default: STEP_LAUNCH(Topo, TG_TASK_EDGE_FOLLOW, grid, 128, 0); break;                                 \
     }
 
@@ -372,7 +394,8 @@ static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint
 extern "C" int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat)
 {
     if (!w) return fail(TG_EINVAL, "bad arguments");
-    if (d_feat && w->cfg.task.task != TG_TASK_OBJECT_PUSH) return fail(TG_EUNSUPPORTED, "only object_push has an extended feature");
+    if (d_feat && w->cfg.task.task != TG_TASK_OBJECT_PUSH && w->cfg.task.task != TG_TASK_OBJECT_ROLL)
+        return fail(TG_EUNSUPPORTED, "only object_push and object_roll have an extended feature");
     w->eb.feat = d_feat;
     w->eb.term_feat = d_feat ? d_term_feat : nullptr;
     return TG_OK;

@@ -402,6 +402,106 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     return cfg, (dep, gray, mask, tris, rest, prims, prim_nv, hull), draw
 
 
+def object_roll_draws(rand_obj_size, rand_embed_dist, rand_init_obj_pos):
+    """ObjectRollEnv draws per reset in the reference's call order: reset_task's `uniform(1, 2)` (if rand_obj_size) and
+    `uniform(0.0015, 0.003)` (if rand_embed_dist) (object_roll_env.py:182-195), reset_object's two `uniform(-0.009, 0.009)`
+    (if rand_init_obj_pos, :209-216), make_goal's `uniform(-pi, pi)` and `uniform(0 | 0.005, 0.015)` (:244-250)."""
+
+    def draw(rng, rounds):
+        out = np.empty((rounds, 6))
+        for r in range(rounds):
+            out[r, 0] = rng.uniform(1.0, 2.0) if rand_obj_size else 1.0
+            out[r, 1] = rng.uniform(0.0015, 0.003) if rand_embed_dist else 0.0015
+            out[r, 2] = rng.uniform(-0.009, 0.009) if rand_init_obj_pos else 0.0
+            out[r, 3] = rng.uniform(-0.009, 0.009) if rand_init_obj_pos else 0.0
+            out[r, 4] = rng.uniform(-np.pi, np.pi)
+            out[r, 5] = rng.uniform(0.0, 0.015) if rand_init_obj_pos else rng.uniform(0.005, 0.015)
+        return out
+
+    return draw
+
+
+def object_roll_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
+    """ObjectRollEnv.__init__ (rl_envs/nonprehensile_manipulation/object_roll/object_roll_env.py:23-104) + BaseObjectEnv as a
+    TgConfig.  Returns (cfg, keepalive, draw_fn)."""
+    arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
+    if env_modes["control_mode"] != "TCP_velocity_control":
+        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
+    if env_modes["movement_mode"] != "xy":
+        raise ValueError("Incorrect movement_mode specified: {}".format(env_modes["movement_mode"]))      # :288-297 knows "xy" only
+    if arm_type != "ur5":
+        raise ValueError("object_roll has rest poses for the ur5 only among the built arms (rest_poses.py)")
+    if sensor != "tactip":
+        raise NotImplementedError("object_roll uses the flat TacTip (t_s_type 'flat', :58); %r has no flat variant" % sensor)
+    typ, S = "flat", int(image_size[0])                                                          # :58
+    mj = scene.load_model_json(arm_type, sensor, typ)
+    sj = scene.load_sensor_json(sensor, typ)
+    cam = sj["types"][typ]
+    arm, control_links = scene.reduce_model(mj, sensor, cam["cam_pos"], cam["cam_rpy"])
+    cfg = L.TgConfig()
+    cfg.n_envs, cfg.lanes_per_warp, cfg.arm = n_envs, lanes_per_warp, arm
+    cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 10.0) / (1.0 / 240.0))))      # :34-36 -> 24
+    t = cfg.task
+    t.task, t.max_steps = L.TG_TASK_OBJECT_ROLL, int(max_steps)
+    t.act_dim = 2
+    for k in range(6):
+        t.act_index[k] = [0, 1][k] if k < 2 else -1                                              # :288-297
+    t.act_min, t.act_max = -0.25, 0.25
+    mv = 0.01                                                                                    # :129-139
+    hi = [mv, mv, 0.0, 0.0, 0.0, 0.0]
+    for k in range(6):
+        t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
+    radius, embed = 0.0025, 0.0015                                                               # :166, :67
+    wf = [0.65, 0.0, 2 * radius - embed]                                                         # :72 (z is per episode on the device)
+    lims = [(-0.05, 0.05), (-0.05, 0.05), (-0.01, 0.01), (0.0, 0.0), (0.0, 0.0), (0.0, 0.0)]     # :75-81
+    for k in range(3):
+        t.workframe_pos[k], t.workframe_rpy[k], t.init_rpy[k] = wf[k], [-np.pi, 0.0, np.pi / 2][k], 0.0
+        t.push_init_pos[k] = [0.65, 0.0, radius][k]                                              # :167
+        t.obj_init_rpy[k], t.obj_base_com[k] = 0.0, 0.0
+        t.push_half[k], t.push_inertia_per_mass[k] = radius, 0.4 * radius * radius               # unused by the sphere narrow phase
+    for k in range(6):
+        t.tcp_lims[k][0], t.tcp_lims[k][1] = lims[k]
+    t.push_shape = 1
+    t.roll_radius = radius
+    t.obj_mass = 0.05                                                                            # sphere.urdf
+    cyl = mj.get("tip_collision")
+    if not cyl or cyl["type"] != "cylinder":
+        raise ValueError("the flat tip's collision primitive is missing from the compiled model")
+    ax_link = scene.rpy_to_mat(cyl["rpy"]) @ np.array([0.0, 0.0, 1.0])
+    pts_link = np.array([cyl["xyz"], np.array(cyl["xyz"]) + ax_link])
+    hb, pts = scene.link_points_in_body(arm, sensor + "_tip_link", pts_link)
+    if hb != arm.tcp_body:
+        raise ValueError("the tip link and the TCP must ride on the same body")
+    for k in range(3):
+        t.roll_cyl_pos[k], t.roll_cyl_axis[k] = pts[0][k], (pts[1] - pts[0])[k]
+    t.roll_cyl_half_len, t.roll_cyl_radius = cyl["length"] / 2, cyl["radius"]
+    stiff, damp, fric = 10.0, 100, 10.0                                                          # t_s_dynamics :62
+    sphere_mu, table_mu = 10.0, 1.0                                                              # :226, table.urdf
+    t.push_table_z = 0.0
+    t.push_mu_table, t.push_mu_tip = min(sphere_mu * table_mu, 10.0), min(sphere_mu * fric, 10.0)  # [EXT] product, clamped at 10
+    t.push_tip_k, t.push_tip_d = 1.0 / (1.0 / stiff + 1.0 / 1e18), damp + 0.1
+    t.push_erp, t.push_slop = 0.2, 1e-4
+    t.push_lin_damping, t.push_ang_damping = 0.04, 0.04
+    t.push_term_dist = 0.001                                                                     # :64
+    t.push_sparse_reward = 1 if env_modes.get("reward_mode", "dense") == "sparse" else 0
+    t.n_draws = 6
+    for k, v in enumerate([1.0, embed, 0.0, 0.0, 0.0, 0.01]):
+        t.draw_default[k] = v
+    dep, gray, mask = scene.load_refimg(sensor, typ, S)
+    rest = scene.load_rest_pose("object_roll", arm_type, sensor, typ, control_links)
+    s = cfg.sensor
+    s.image_size, s.border_on = S, 1
+    s.fov_deg, s.near_, s.far_ = sj["fov"], sj["near"], sj["far"]
+    s.h_nodef_dep = dep.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_nodef_gray = gray.ctypes.data_as(C.POINTER(C.c_float))
+    s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+    s.n_prim = 0                                                                                 # the stimulus is the per-env sphere
+    cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
+    draw = object_roll_draws(bool(env_modes.get("rand_obj_size", False)), bool(env_modes.get("rand_embed_dist", False)),
+                             bool(env_modes.get("rand_init_obj_pos", False)))
+    return cfg, (dep, gray, mask, rest), draw
+
+
 class TactileWorld:
     """N envs of one task on one device."""
 
@@ -425,8 +525,10 @@ class TactileWorld:
             self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
             self.feat = self.term_feat = None
-            if cfg.task.task == L.TG_TASK_OBJECT_PUSH:
-                # extended_feature (object_push_env.py:611-629), filled by every step / reset
+            self.nfeat = {L.TG_TASK_OBJECT_PUSH: 12, L.TG_TASK_OBJECT_ROLL: 3}.get(cfg.task.task, 0)
+            if self.nfeat:
+                # extended_feature (object_push_env.py:611-629, object_roll_env.py:402-408), filled by every step / reset;
+                # the first `nfeat` columns are meaningful
                 self.feat = torch.zeros((self.n, L.TG_PUSH_NFEAT), dtype=torch.float32, device=self.device)
                 self.term_feat = torch.zeros_like(self.feat)
                 L.check(self.lib.tg_bind_features(self.h, self.feat.data_ptr(), self.term_feat.data_ptr()))

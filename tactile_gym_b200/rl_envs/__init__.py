@@ -6,6 +6,7 @@ ids are also registered there so `gym.make("edge_follow-v0", ...)` resolves to t
 from .edge_follow_env import EdgeFollowEnv
 from .object_balance_env import ObjectBalanceEnv
 from .object_push_env import ObjectPushEnv
+from .object_roll_env import ObjectRollEnv
 from .surface_follow_env import SurfaceFollowAutoEnv
 
 REGISTRY = {
@@ -13,10 +14,11 @@ REGISTRY = {
     "object_balance-v0": ObjectBalanceEnv,
     "surface_follow-v0": SurfaceFollowAutoEnv,
     "object_push-v0": ObjectPushEnv,
+    "object_roll-v0": ObjectRollEnv,
 }
 
 # ids the reference registers that are not built yet (SURVEY.md 8, rows "next")
-NOT_BUILT = ["surface_follow-v1", "surface_follow-v2", "object_roll-v0"]
+NOT_BUILT = ["surface_follow-v1", "surface_follow-v2"]
 
 
 def make(env_id, **kwargs):

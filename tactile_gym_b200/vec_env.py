@@ -11,7 +11,7 @@ import time
 import numpy as np
 
 from . import spaces
-from .engine import TactileWorld, edge_follow_config, object_balance_config, object_push_config, surface_follow_config
+from .engine import TactileWorld, edge_follow_config, object_balance_config, object_push_config, object_roll_config, surface_follow_config
 
 try:  # pragma: no cover
     from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
@@ -19,7 +19,7 @@ except Exception:  # noqa: BLE001
     _VecEnvBase = object
 
 CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": object_balance_config,
-                   "surface_follow-v0": surface_follow_config, "object_push-v0": object_push_config}
+                   "surface_follow-v0": surface_follow_config, "object_push-v0": object_push_config, "object_roll-v0": object_roll_config}
 
 
 class TactileVecEnv(_VecEnvBase):
@@ -33,7 +33,7 @@ class TactileVecEnv(_VecEnvBase):
         if kw.get("show_gui") or kw.get("show_tactile"):
             raise ValueError("show_gui / show_tactile are not available in the batched engine")
         self.observation_mode = env_modes.get("observation_mode", "tactile")
-        if self.observation_mode != "tactile" and not (self.observation_mode == "tactile_and_feature" and env_id == "object_push-v0"):
+        if self.observation_mode != "tactile" and not (self.observation_mode == "tactile_and_feature" and env_id in ("object_push-v0", "object_roll-v0")):
             raise NotImplementedError("observation_mode %r is not built for %s" % (self.observation_mode, env_id))
         image_size = kw.get("image_size", [64, 64])
         max_steps = kw.get("max_steps", 250)
@@ -44,8 +44,9 @@ class TactileVecEnv(_VecEnvBase):
         S = int(image_size[0])
         sp = {"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)}
         self._with_feat = self.observation_mode == "tactile_and_feature"
+        self._nfeat = self.world.nfeat
         if self._with_feat:
-            sp["extended_feature"] = spaces.Box(low=-np.inf, high=np.inf, shape=(12,), dtype=np.float32)
+            sp["extended_feature"] = spaces.Box(low=-np.inf, high=np.inf, shape=(self._nfeat,), dtype=np.float32)
         self.observation_space = spaces.Dict(sp)
         self.action_space = spaces.Box(low=-0.25, high=0.25, shape=(self.world.act_dim,), dtype=np.float32)
         self.metadata = {"render.modes": ["rgb_array"]}
@@ -80,7 +81,7 @@ class TactileVecEnv(_VecEnvBase):
     def _obs_dict(self):
         o = {"tactile": self._pin_obs.numpy()}
         if self._with_feat:
-            o["extended_feature"] = self._pin_feat.numpy().copy()
+            o["extended_feature"] = self._pin_feat.numpy()[:, : self._nfeat].copy()
         return o
 
     def reset(self):
@@ -120,7 +121,7 @@ class TactileVecEnv(_VecEnvBase):
             for k, i in enumerate(idx):
                 infos[i]["terminal_observation"] = {"tactile": term[k]}
                 if self._with_feat:
-                    infos[i]["terminal_observation"]["extended_feature"] = tfeat[k]
+                    infos[i]["terminal_observation"]["extended_feature"] = tfeat[k][: self._nfeat]
                 infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
                 self._ep_ret[i] = 0
                 self._ep_len[i] = 0

@@ -412,6 +412,14 @@ def main():
         wv = [body, tip] + (["tactip_adapter_link"] if (sensor == "tactip" and typ in ("right_angle", "forward")) else [])
         model, meshes = parse_urdf(urdf, want_visual=wv, want_collision=[tip])
         model.update({"arm": arm, "sensor": sensor, "type": typ, "source": os.path.relpath(urdf, REF)})
+        # the tip core's collision primitive when it is not a mesh (the flat TacTip's core is a cylinder)
+        tip_elem = [l for l in ET.parse(urdf).getroot().findall("link") if l.get("name") == tip][0]
+        col = tip_elem.find("collision")
+        cyl = col.find("geometry").find("cylinder") if col is not None else None
+        if cyl is not None:
+            co = col.find("origin")
+            model["tip_collision"] = {"type": "cylinder", "length": atof(cyl.get("length")), "radius": atof(cyl.get("radius")),
+                                      "xyz": vec(co.get("xyz") if co is not None else None), "rpy": vec(co.get("rpy") if co is not None else None)}
         name = "%s_%s_%s" % (arm, typ, sensor)
         with open(os.path.join(OUT, "models", name + ".json"), "w") as f:
             json.dump(model, f, indent=1)
