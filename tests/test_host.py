@@ -54,11 +54,13 @@ def test_config_rejects_bad_modes(edge_modes):
 def test_registry_ids():
     import tactile_gym_b200 as tg
 
-    assert "edge_follow-v0" in tg.REGISTRY
+    # the reference's ids (tactile_gym/rl_envs/__init__.py:3-41)
+    for env_id in ("edge_follow-v0", "surface_follow-v0", "object_roll-v0", "object_push-v0", "object_balance-v0"):
+        assert env_id in tg.REGISTRY
     with pytest.raises(KeyError):
         tg.make("no_such_env-v0")
     with pytest.raises(NotImplementedError):
-        tg.make("object_roll-v0")
+        tg.make("surface_follow-v1")
 
 
 def test_seeding_matches_oracle_restatement(oracle):
