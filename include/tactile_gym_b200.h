@@ -139,6 +139,8 @@ typedef struct {
     double surf_embed;               /* embed_dist: 0.0025 tactip, 0.0015 digit / digitac */
     double surf_drive;               /* constant drive along the goal direction: max_action x {1, 0.9, 0.7} */
     double surf_w_norm;              /* weight of the normal-alignment term (0 for yz / xyz movement) */
+    double surf_w_goal, surf_w_surf; /* weights of the xy goal distance / surface distance: 0, 1 surface_follow-v0
+                                        (surface_follow_auto_env.py:76-94); 1, 10 surface_follow-v1 (surface_follow_goal_env.py:62-81) */
     /* object_push (object_push_env.py, base_object_env.py): a free cube on the table pushed by the tip core; contact rows
      * tip hull <-> cube and cube <-> table.  draws per reset: init_obj_ang, obj_mass, OpenSimplex seed | trajectory angle */
     int32_t push_mode, push_traj_straight, push_sparse_reward;
@@ -221,10 +223,10 @@ int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream);
 int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float* d_reward, uint8_t* d_done,
             uint8_t* d_term_obs, void* stream);
 
-/* object_push / object_roll, observation_mode "tactile_and_feature": bind caller-owned device buffers [N][TG_PUSH_NFEAT] f32
+/* object_push / object_roll / surface_follow-v1, observation_mode "tactile_and_feature": bind caller-owned device buffers [N][TG_PUSH_NFEAT] f32
  * that every following tg_step / tg_reset / tg_physics_only fills with the extended_feature (object_push_env.py:611-629: TCP
  * pos(3) + rpy(3) in the work frame, goal pos(3) + rpy(3) in the work frame; object_roll_env.py:402-408: the goal position in
- * the TCP frame in the first 3 entries).  d_term_feat (may be NULL) receives the features of the
+ * the TCP frame in the first 3 entries; surface_follow_goal_env.py:83-97: TCP pos(3) + goal pos(3) in the work frame).  d_term_feat (may be NULL) receives the features of the
  * state a finished env terminated in.  NULL d_feat unbinds. */
 int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat);
 

@@ -511,9 +511,11 @@ class SurfaceFollowOracle:
     "xyz" / "xyzRxRy".  One env instance.  The tip core <-> table contact (only reachable in the deepest valleys,
     SURVEY.md 8a R5) is not modelled."""
 
-    def __init__(self, image_size=128, arm="ur5", sensor="digit", max_steps=200, movement_mode="xyzRxRy", seed=None):
+    def __init__(self, image_size=128, arm="ur5", sensor="digit", max_steps=200, movement_mode="xyzRxRy", seed=None, variant="auto"):
+        """variant "auto": SurfaceFollowAutoEnv (surface_follow-v0); "goal": SurfaceFollowGoalEnv (surface_follow-v1,
+        surface_follow_goal/surface_follow_goal_env.py: the policy steers x / y, the reward adds the goal distance)"""
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
-        self.max_steps, self.movement_mode = max_steps, movement_mode
+        self.max_steps, self.movement_mode, self.variant = max_steps, movement_mode, variant
         self.grid, self.hrange, self.rows, self.cols, self.interp, self.extent = 0.006, 0.025, 64, 64, 0.05, 0.15
         wd = [0.33, 0.0, 0.0] if arm == "mg400" else [0.65, 0.0, 0.0]                  # base_surface_env.py:54-57
         self.embed_dist = {"tactip": 0.0025, "digitac": 0.0015, "digit": 0.0015}[sensor]  # :67-75
@@ -607,16 +609,27 @@ class SurfaceFollowOracle:
         v = R @ np.array([0.0, 0.0, -1.0])
         cos_dist = 1 - np.dot(n, v) / (np.linalg.norm(n) * np.linalg.norm(v))
         w_norm = 0.0 if self.movement_mode in ("yz", "xyz") else 1.0
+        if self.variant == "goal":   # surface_follow_goal_env.py:62-81
+            goal_xy = np.linalg.norm(p[:2] - self.goal_pos[:2])
+            return -(1.0 * goal_xy + 10.0 * surf_dist + w_norm * cos_dist), done
         return -(1.0 * surf_dist + w_norm * cos_dist), done
+
+    def features(self):   # SurfaceFollowGoalEnv.get_extended_feature_array (surface_follow_goal_env.py:83-97)
+        tp, _ = tcp_pose_workframe(self.m, np.array(self.s.q[: self.m.ndof]))
+        gp = self.Rw.T @ (self.goal_pos - self.workframe_pos)
+        return np.concatenate([tp, gp])
 
     def encode_scale(self, action):   # surface_follow_auto_env.py:27-57, base_tactile_env.py:141-164
         enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
         k = {"tactip": 1.0, "digitac": 0.9, "digit": 0.7}[self.sensor]
-        enc[0] = self.dirs[0] * 0.25 * k; enc[1] = self.dirs[1] * 0.25 * k
-        if self.movement_mode == "xyz":
-            enc[2] = a[0]
+        if self.variant == "goal":   # surface_follow_goal_env.py:27-52
+            enc[: len(a)] = a
         else:
-            enc[2], enc[3], enc[4] = a[0], a[1], a[2]
+            enc[0] = self.dirs[0] * 0.25 * k; enc[1] = self.dirs[1] * 0.25 * k
+            if self.movement_mode == "xyz":
+                enc[2] = a[0]
+            else:
+                enc[2], enc[3], enc[4] = a[0], a[1], a[2]
         enc = np.clip(enc, -0.25, 0.25)
         mv, ma = 0.01, 5.0 * (np.pi / 180)
         amax = np.array([mv, mv, mv, ma, ma, 0.0]); amin = -amax

@@ -53,6 +53,7 @@ class TgTask(C.Structure):
         ("obj_term_deg", C.c_double), ("obj_term_pos", C.c_double), ("p2p_erp", C.c_double), ("p2p_max_impulse", C.c_double),
         ("surf_pos", D3), ("surf_grid", C.c_double), ("surf_range", C.c_double), ("surf_interp", C.c_double),
         ("surf_extent", C.c_double), ("surf_embed", C.c_double), ("surf_drive", C.c_double), ("surf_w_norm", C.c_double),
+        ("surf_w_goal", C.c_double), ("surf_w_surf", C.c_double),
         ("push_mode", C.c_int32), ("push_traj_straight", C.c_int32), ("push_sparse_reward", C.c_int32), ("push_shape", C.c_int32),
         ("push_half", D3), ("push_table_z", C.c_double), ("push_mu_table", C.c_double), ("push_mu_tip", C.c_double),
         ("push_tip_k", C.c_double), ("push_tip_d", C.c_double), ("push_erp", C.c_double), ("push_slop", C.c_double),

@@ -610,7 +610,13 @@ TGD void roll_features(const double* traj, float* out)
 // object_push / object_roll: the extended feature of env e's live state (after a reset / standby swap)
 TGD void write_live_features(const TgTask& task, const EnvBuffers& b, int e)
 {
-    if (!b.feat || !b.traj) return;
+    if (!b.feat) return;
+    if (task.task == TG_TASK_SURFACE_FOLLOW) {
+        const double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)b.hf_cur[e]) * SURF_META;
+        surface_features(task, meta, b.tcp + (size_t)e * 7, b.tcp + (size_t)e * 7 + 3, b.feat + (size_t)e * TG_PUSH_NFEAT);
+        return;
+    }
+    if (!b.traj) return;
     const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
     if (task.task == TG_TASK_OBJECT_ROLL) { roll_features(tr, b.feat + (size_t)e * TG_PUSH_NFEAT); return; }
     push_features(task, b.tcp + (size_t)e * 7, b.tcp + (size_t)e * 7 + 3, tr, tr[2 * PUSH_NTRAJ], b.goal[e], b.feat + (size_t)e * TG_PUSH_NFEAT);
@@ -725,8 +731,9 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll
                 for (int s = 0; s < 6; s++) if (task.act_index[kk] == s) enc[s] = a;
             }
-        if (surface) {
+        if (surface && task.surf_drive != 0.0) {
             // SurfaceFollowAutoEnv.encode_actions (surface_follow_auto_env.py:27-57): constant drive towards the goal
+            // (surface_follow-v1 has none: the policy's own x / y stay)
             const double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)b.hf_cur[e]) * SURF_META;
             enc[0] = meta[1] * task.surf_drive; enc[1] = meta[2] * task.surf_drive;
         }
@@ -846,6 +853,8 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
     } else if (surface) {
         const size_t hb = (size_t)e * 2 + (size_t)b.hf_cur[e];
         surface_step_data(task, b.height + hb * SURF_PTS, b.hf_meta + hb * SURF_META, tp, tq, steps, &r, &d);
+        float* f = (d && autoreset && b.pipeline) ? b.term_feat : b.feat;
+        if (f) surface_features(task, b.hf_meta + hb * SURF_META, tp, tq, f + (size_t)e * TG_PUSH_NFEAT);
     } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
     reward[e] = r; done[e] = d;
     if (d && autoreset && b.pipeline) {

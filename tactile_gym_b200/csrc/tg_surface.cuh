@@ -142,8 +142,23 @@ TGD void surface_step_data(const TgTask& task, const double* H, const double* me
     n[0] /= nn; n[1] /= nn; n[2] /= nn;
     const double v[3] = {-R[2], -R[5], -R[8]};
     const double cs = (n[0] * v[0] + n[1] * v[1] + n[2] * v[2]) / (sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
-    *reward = (float)(-((1.0 * surf_dist) + (task.surf_w_norm * (1.0 - cs))));
+    // SurfaceFollowAutoEnv.dense_reward (W_goal = 0, W_surf = 1) / SurfaceFollowGoalEnv.dense_reward (W_goal = 1, W_surf = 10)
+    const double goal_xy = sqrt(gx * gx + gy * gy);
+    *reward = (float)(-((task.surf_w_goal * goal_xy) + (task.surf_w_surf * surf_dist) + (task.surf_w_norm * (1.0 - cs))));
     *done = (goal_dist < task.termination_dist || steps >= task.max_steps) ? 1 : 0;
+}
+
+// SurfaceFollowGoalEnv.get_extended_feature_array (surface_follow_goal_env.py:83-97): TCP and goal position, work frame
+TGD void surface_features(const TgTask& task, const double* meta, const double* tp, const double* tq, float* out)
+{
+    double wp[3], wr[3], gp[3], gr[3];
+    const double ident[4] = {0.0, 0.0, 0.0, 1.0}, g[3] = {meta[3], meta[4], meta[5]};
+    world_to_work(task, tp, tq, wp, wr);
+    world_to_work(task, g, ident, gp, gr);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { out[i] = (float)wp[i]; out[3 + i] = (float)gp[i]; }
+#pragma unroll
+    for (int i = 6; i < TG_PUSH_NFEAT; i++) out[i] = 0.0f;
 }
 
 // world-space mesh vertex (column j = x index, row i = y index); zc = middle of the float32 height range

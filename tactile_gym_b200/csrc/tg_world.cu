@@ -394,8 +394,8 @@ static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint
 extern "C" int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat)
 {
     if (!w) return fail(TG_EINVAL, "bad arguments");
-    if (d_feat && w->cfg.task.task != TG_TASK_OBJECT_PUSH && w->cfg.task.task != TG_TASK_OBJECT_ROLL)
-        return fail(TG_EUNSUPPORTED, "only object_push and object_roll have an extended feature");
+    if (d_feat && w->cfg.task.task != TG_TASK_OBJECT_PUSH && w->cfg.task.task != TG_TASK_OBJECT_ROLL && w->cfg.task.task != TG_TASK_SURFACE_FOLLOW)
+        return fail(TG_EUNSUPPORTED, "only object_push, object_roll and surface_follow have an extended feature");
     w->eb.feat = d_feat;
     w->eb.term_feat = d_feat ? d_term_feat : nullptr;
     return TG_OK;

@@ -232,9 +232,16 @@ def surface_follow_draws():
     return draw
 
 
-def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
-    """SurfaceFollowAutoEnv / BaseSurfaceEnv.__init__ (rl_envs/exploration/surface_follow/base_surface_env.py:14-150,
-    surface_follow_auto/surface_follow_auto_env.py) as a TgConfig.  Returns (cfg, keepalive, draw_fn)."""
+def surface_follow_goal_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
+    """surface_follow-v1: SurfaceFollowGoalEnv (surface_follow_goal/surface_follow_goal_env.py) - the policy steers x / y itself
+    towards the goal instead of being driven there."""
+    return surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp, variant="goal")
+
+
+def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0, variant="auto"):
+    """SurfaceFollowAutoEnv (variant "auto", surface_follow-v0) / SurfaceFollowGoalEnv (variant "goal", surface_follow-v1) on
+    BaseSurfaceEnv.__init__ (rl_envs/exploration/surface_follow/base_surface_env.py:14-150) as a TgConfig.
+    Returns (cfg, keepalive, draw_fn)."""
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
     if env_modes.get("noise_mode", "simplex") != "simplex":
         raise NotImplementedError("noise_mode %r: only 'simplex' is built" % env_modes.get("noise_mode"))
@@ -252,7 +259,10 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 10.0) / (1.0 / 240.0))))      # :26-28 -> 24
     t = cfg.task
     t.task, t.max_steps = L.TG_TASK_SURFACE_FOLLOW, int(max_steps)
-    idx = {"xyz": [2], "xyzRxRy": [2, 3, 4]}[env_modes["movement_mode"]]                          # surface_follow_auto_env.py:45-55
+    if variant == "goal":
+        idx = {"xyz": [0, 1, 2], "xyzRxRy": [0, 1, 2, 3, 4]}[env_modes["movement_mode"]]          # surface_follow_goal_env.py:27-52
+    else:
+        idx = {"xyz": [2], "xyzRxRy": [2, 3, 4]}[env_modes["movement_mode"]]                      # surface_follow_auto_env.py:45-55
     t.act_dim = len(idx)
     for k in range(6):
         t.act_index[k] = idx[k] if k < len(idx) else -1
@@ -275,6 +285,9 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     t.surf_embed = {"tactip": 0.0025, "digitac": 0.0015, "digit": 0.0015}[sensor]                 # :67-75
     t.surf_drive = 0.25 * {"tactip": 1.0, "digitac": 0.9, "digit": 0.7}[sensor]                   # surface_follow_auto_env.py:35-43
     t.surf_w_norm = 0.0 if env_modes["movement_mode"] == "xyz" else 1.0                           # :88-89
+    t.surf_w_goal, t.surf_w_surf = 0.0, 1.0                                                      # :79-80, :92
+    if variant == "goal":                                                                        # surface_follow_goal_env.py:62-81
+        t.surf_drive, t.surf_w_goal, t.surf_w_surf = 0.0, 1.0, 10.0
     t.n_draws = 2
     t.draw_default[0], t.draw_default[1] = 0.0, 0.0
     dep, gray, mask = scene.load_refimg(sensor, typ, S)
@@ -526,6 +539,8 @@ class TactileWorld:
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
             self.feat = self.term_feat = None
             self.nfeat = {L.TG_TASK_OBJECT_PUSH: 12, L.TG_TASK_OBJECT_ROLL: 3}.get(cfg.task.task, 0)
+            if cfg.task.task == L.TG_TASK_SURFACE_FOLLOW and cfg.task.surf_w_goal != 0.0:
+                self.nfeat = 6                   # surface_follow-v1: TCP + goal position (surface_follow_goal_env.py:83-97)
             if self.nfeat:
                 # extended_feature (object_push_env.py:611-629, object_roll_env.py:402-408), filled by every step / reset;
                 # the first `nfeat` columns are meaningful

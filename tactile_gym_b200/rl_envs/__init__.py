@@ -7,18 +7,19 @@ from .edge_follow_env import EdgeFollowEnv
 from .object_balance_env import ObjectBalanceEnv
 from .object_push_env import ObjectPushEnv
 from .object_roll_env import ObjectRollEnv
-from .surface_follow_env import SurfaceFollowAutoEnv
+from .surface_follow_env import SurfaceFollowAutoEnv, SurfaceFollowGoalEnv
 
 REGISTRY = {
     "edge_follow-v0": EdgeFollowEnv,
     "object_balance-v0": ObjectBalanceEnv,
     "surface_follow-v0": SurfaceFollowAutoEnv,
+    "surface_follow-v1": SurfaceFollowGoalEnv,
     "object_push-v0": ObjectPushEnv,
     "object_roll-v0": ObjectRollEnv,
 }
 
 # ids the reference registers that are not built yet (SURVEY.md 8, rows "next")
-NOT_BUILT = ["surface_follow-v1", "surface_follow-v2"]
+NOT_BUILT = ["surface_follow-v2", "edge_follow_aotu-v0"]
 
 
 def make(env_id, **kwargs):

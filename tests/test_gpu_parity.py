@@ -516,3 +516,48 @@ def test_surface_follow_episode_turnover(oracle):
         assert infos[i]["terminal_observation"]["tactile"].shape == (S, S, 1)
     assert env.world.pipeline_stalls() == 0
     env.close()
+
+
+@pytest.mark.parametrize("sensor,S,movement", [("tactip", 64, "xyzRxRy"), ("digit", 128, "xyz")])
+def test_surface_follow_goal_matches_oracle(oracle, sensor, S, movement):
+    """surface_follow-v1 (SurfaceFollowGoalEnv): the policy steers x / y itself, reward = goal distance + 10 x surface distance
+    + normal alignment, extended_feature = TCP and goal position in the work frame; each step from an identical state."""
+    import tactile_gym_b200 as tg
+
+    modes = dict(SURFACE_MODES, movement_mode=movement, tactile_sensor_name=sensor, observation_mode="tactile_and_feature")
+    n = 4
+    env = tg.make_vec("surface_follow-v1", n, env_kwargs={"env_modes": modes, "image_size": [S, S], "max_steps": 200})
+    rng = np.random.RandomState(S)
+    draws = np.stack([rng.randint(0, 10 ** 8, (n, 2)).astype(np.float64), rng.uniform(-np.pi, np.pi, (n, 2))], axis=2)
+    env.world.set_draws(draws)
+    ob = env.reset()
+    st = env.world.get_state()
+    refs = []
+    for i in range(n):
+        r = oracle.SurfaceFollowOracle(image_size=S, sensor=sensor, movement_mode=movement, variant="goal")
+        r.reset(draws=(draws[i, 0, 0], draws[i, 0, 1]))
+        refs.append(r)
+        _sync_oracle(r, st[i])
+        assert ob["extended_feature"].shape == (n, 6)
+        assert np.allclose(r.features(), ob["extended_feature"][i], atol=1e-6)
+        assert abs(np.linalg.norm(ob["extended_feature"][i][3:5]) - 0.15) < 1e-6      # the goal is 0.15 m from the work origin
+    act_dim = env.world.act_dim
+    assert act_dim == (5 if movement == "xyzRxRy" else 3)
+    for k in range(12):
+        act = rng.uniform(-0.25, 0.25, (n, act_dim)).astype(np.float32)
+        act[:, 2] = 0.25                                       # push down so the skin meets the surface
+        o2, rew, done, infos = env.step(act)
+        st = env.world.get_state()
+        for i, r in enumerate(refs):
+            o, rr, dd, _ = r.step(act[i])
+            tol = 5e-6 if k == 0 else 1e-9
+            assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=tol), (k, i)
+            assert not dd and not done[i]
+            _sync_oracle(r, st[i])
+            rr, _ = r.step_data()
+            assert abs(rr - rew[i]) < 1e-6 * max(1.0, abs(rr)), (k, i, rr, rew[i])
+            assert np.allclose(r.features(), o2["extended_feature"][i], atol=1e-6), (k, i)
+            mx, frac = _img_close(r.observation(), o2["tactile"][i])
+            assert mx <= 1 and frac < 1e-3, (k, i, mx, frac)
+    assert not env.world.pipeline_error()
+    env.close()

@@ -60,7 +60,7 @@ def test_registry_ids():
     with pytest.raises(KeyError):
         tg.make("no_such_env-v0")
     with pytest.raises(NotImplementedError):
-        tg.make("surface_follow-v1")
+        tg.make("surface_follow-v2")
 
 
 def test_seeding_matches_oracle_restatement(oracle):
