@@ -329,7 +329,9 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "raster_traffic.json")
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            rec = json.load(open(tp)).get(args.workload)
+            if rec and rec.get("n_envs") == n and rec.get("image") == IMG:     # only for the launch shape that was captured
+                traffic = rec.get("dram_bytes_per_launch")
         line = {
             "metric": "env steps/sec (tactile frames/sec)", "value": n * world * K / (t_ms * 1e-3), "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -338,7 +340,8 @@ def main():
                        "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events",
                        "physics_ms": t_phys, "raster_ms": t_raster, "lanes_per_warp": int(w.cfg.lanes_per_warp), "episode_phases": args.phases},
             "e2e": {"value": n * world * Ke / (t_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": env.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": env.d2h_bytes_per_step, "steps": Ke},
+                    "d2h_bytes_per_step": env.d2h_bytes_per_step, "steps": Ke,
+                    "path": "TactileVecEnv.step (numpy in/out) -> tg_step_host: obs rendered + copied out in chunks, D2H overlapped" if env._host_step else "TactileVecEnv.step (numpy in/out) -> tg_step + torch copies"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "raster_hf_kernel" if ENV_ID.startswith("surface") else "raster_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * ALG_BYTES, "launch_ms": t_raster},

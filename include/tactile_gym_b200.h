@@ -65,6 +65,7 @@ extern "C" {
 #define TG_TASK_OBJECT_ROLL 4
 #define TG_SURF_N 64 /* heightfield rows = columns */
 #define TG_PUSH_NTRAJ 10 /* object_push: goals along the trajectory (object_push_env.py:233) */
+#define TG_ORACLE_NOBS 36 /* observation_mode "oracle": floats per env (10 edge, 20 surface, 26 balance, 30 push, 34 roll; rest 0) */
 #define TG_PUSH_NFEAT 12 /* object_push: extended_feature length (object_push_env.py:611-629) */
 
 /* object_push action encodings (object_push_env.py:369-454) */
@@ -223,12 +224,43 @@ int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream);
 int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float* d_reward, uint8_t* d_done,
             uint8_t* d_term_obs, void* stream);
 
+/* One env step with HOST buffers, the call behind the numpy VecEnv (replaces SubprocVecEnv.step_async/step_wait's pipes,
+ * stable_baselines3 via tactile_gym/sb3_helpers/rl_utils.py:17-35, around BaseTactileEnv.step base_tactile_env.py:166-185).
+ * h_* must be page-locked host memory for the copies to overlap; d_* are the caller-owned device tensors tg_step takes
+ * (they hold the same results afterwards).  The observation is rendered and copied out in `chunks` env ranges: the
+ * device->host copy of one range runs (on an internal copy stream) while the next range and the terminal observations
+ * are rendered.  Everything is ordered into `stream`: synchronising it makes the host buffers valid.  d_term_obs / d_feat /
+ * h_feat may be NULL (d_feat is the buffer bound with tg_bind_features). */
+#define TG_HOST_MAX_CHUNKS 16
+typedef struct TgHostStep {
+    const float* h_actions; /* [N][act_dim] */
+    uint8_t* d_obs;         /* [N][S][S][1]; NULL together with h_obs: no image is rendered (observation_mode "oracle") */
+    float* d_reward;        /* [N] */
+    uint8_t* d_done;        /* [N] */
+    uint8_t* d_term_obs;    /* [N][S][S][1] or NULL */
+    const float* d_feat;    /* [N][TG_PUSH_NFEAT] or NULL */
+    uint8_t* h_obs;
+    float* h_reward;
+    uint8_t* h_done;
+    float* h_feat;          /* or NULL */
+    float* h_oracle;        /* [N][TG_ORACLE_NOBS] or NULL: the buffer bound with tg_bind_oracle_obs, copied out */
+    int chunks;             /* <= 0: 4 */
+} TgHostStep;
+int tg_step_host(TgWorld* w, const TgHostStep* hs, void* stream);
+
 /* object_push / object_roll / surface_follow-v1, observation_mode "tactile_and_feature": bind caller-owned device buffers [N][TG_PUSH_NFEAT] f32
  * that every following tg_step / tg_reset / tg_physics_only fills with the extended_feature (object_push_env.py:611-629: TCP
  * pos(3) + rpy(3) in the work frame, goal pos(3) + rpy(3) in the work frame; object_roll_env.py:402-408: the goal position in
  * the TCP frame in the first 3 entries; surface_follow_goal_env.py:83-97: TCP pos(3) + goal pos(3) in the work frame).  d_term_feat (may be NULL) receives the features of the
  * state a finished env terminated in.  NULL d_feat unbinds. */
 int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat);
+
+/* observation_mode "oracle" (get_oracle_obs: edge_follow_env.py:454-476, base_surface_env.py:789-819, object_balance_env.py:528-563,
+ * object_push_env.py:571-609, object_roll_env.py:371-409; the "oracle" entry of get_observation, base_tactile_env.py:258-262):
+ * bind caller-owned device buffers [N][TG_ORACLE_NOBS] f32 that every following tg_step / tg_step_host / tg_reset /
+ * tg_physics_only fills with the state vector of each env (the task's first k entries are meaningful).  d_term_oracle (may be
+ * NULL) receives the vector of the state a finished env terminated in.  NULL d_oracle unbinds. */
+int tg_bind_oracle_obs(TgWorld* w, float* d_oracle, float* d_term_oracle);
 
 /* kernel-level entry points (tests, ncu) */
 int tg_physics_only(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, void* stream);

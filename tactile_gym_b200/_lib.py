@@ -81,8 +81,16 @@ class TgConfig(C.Structure):
     ]
 
 
+class TgHostStep(C.Structure):
+    _fields_ = [
+        ("h_actions", C.c_void_p), ("d_obs", C.c_void_p), ("d_reward", C.c_void_p), ("d_done", C.c_void_p), ("d_term_obs", C.c_void_p),
+        ("d_feat", C.c_void_p), ("h_obs", C.c_void_p), ("h_reward", C.c_void_p), ("h_done", C.c_void_p), ("h_feat", C.c_void_p), ("h_oracle", C.c_void_p),
+        ("chunks", C.c_int32),
+    ]
+
+
 EXPORTS = [
-    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_refill_draws", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_bind_features",
+    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_refill_draws", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
     "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
     "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_launch_count",
 ]
@@ -114,7 +122,9 @@ def load():
     lib.tg_get_reset_counts.argtypes = [vp, vp, vp]
     lib.tg_reset.argtypes = [vp, vp, vp, vp]
     lib.tg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.tg_step_host.argtypes = [vp, C.POINTER(TgHostStep), vp]
     lib.tg_bind_features.argtypes = [vp, vp, vp]
+    lib.tg_bind_oracle_obs.argtypes = [vp, vp, vp]
     lib.tg_physics_only.argtypes = [vp, vp, vp, vp, vp]
     lib.tg_raster_only.argtypes = [vp, vp, vp]
     lib.tg_reset_only.argtypes = [vp, vp, vp]

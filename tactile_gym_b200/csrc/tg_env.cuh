@@ -54,6 +54,8 @@ struct EnvBuffers {
     const double* hull;
     int n_hull;
     float *feat, *term_feat;
+    // observation_mode "oracle": caller's buffers [N][TG_ORACLE_NOBS] f32 (tg_bind_oracle_obs; may be null)
+    float *oracle, *term_oracle;
     // standby start-of-episode state
     double *sb_q, *sb_qd, *sb_embed, *sb_ang, *sb_cam, *sb_stim, *sb_tcp;
     int* sb_substeps;
@@ -622,6 +624,94 @@ TGD void write_live_features(const TgTask& task, const EnvBuffers& b, int e)
     push_features(task, b.tcp + (size_t)e * 7, b.tcp + (size_t)e * 7 + 3, tr, tr[2 * PUSH_NTRAJ], b.goal[e], b.feat + (size_t)e * TG_PUSH_NFEAT);
 }
 
+// get_oracle_obs of env e's CURRENT state in the buffers (observation_mode "oracle": the state vector that replaces the
+// tactile image).  edge_follow_env.py:454-476 (10 values), base_surface_env.py:789-819 (20), object_balance_env.py:528-563 (26),
+// object_push_env.py:571-609 (30), object_roll_env.py:371-409 (34).  TCP pose / velocity in the work frame as
+// get_current_TCP_pos_vel_workframe builds them (base_robot_arm.py:136-172): getLinkState's inertial-frame pose and the
+// velocity of that point, J(q) qd.  Kept out of line: it runs once per env step and only when the buffer is bound.
+template <class T>
+__device__ __noinline__ void oracle_obs_env(const TgArm& arm, const TgTask& task, const EnvBuffers& b, int e, float* out)
+{
+    constexpr int NB = T::NB;
+    double q[NB], qd[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) { q[i] = b.q[(size_t)i * b.n + e]; qd[i] = b.qd[(size_t)i * b.n + e]; }
+    Kin<NB> k;
+    fk<T>(arm, q, k);
+    double tp[3], tq[4], J[6][NB], vw[6];
+    tcp_world<T>(arm, k, tp, tq);
+    tcp_jacobian<T>(arm, k, tp, J);
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB; i++) a += J[r][i] * qd[i];
+        vw[r] = a;
+    }
+    const bool roll = task.task == TG_TASK_OBJECT_ROLL;
+    // object_roll moves the workframe every episode (object_roll_env.py:197-202)
+    const double wf[3] = {task.workframe_pos[0], task.workframe_pos[1], roll ? b.obj_ext[(size_t)e * 4 + 1] : task.workframe_pos[2]};
+    double wp[3], wr[3], wo[4], wq[4], wqi[4], Ri[9], vl[3], va[3];
+    world_to_work_at(task, wf, tp, tq, wp, wr);
+    quat_from_euler(wr, wo);
+    // worldvel_to_workvel (base_robot_arm.py:107-118): the matrix of the inverted workframe quaternion
+    quat_from_euler(task.workframe_rpy, wq);
+    wqi[0] = -wq[0]; wqi[1] = -wq[1]; wqi[2] = -wq[2]; wqi[3] = wq[3];
+    mat_from_quat(wqi, Ri);
+    m3mulv(vl, Ri, vw); m3mulv(va, Ri, vw + 3);
+    const double ident[4] = {0.0, 0.0, 0.0, 1.0};
+    int n = 0;
+    auto put3 = [&](const double* v) { out[n++] = (float)v[0]; out[n++] = (float)v[1]; out[n++] = (float)v[2]; };
+    auto put4 = [&](const double* v) { out[n++] = (float)v[0]; out[n++] = (float)v[1]; out[n++] = (float)v[2]; out[n++] = (float)v[3]; };
+    if (task.task == TG_TASK_EDGE_FOLLOW) {
+        double s, c, gp[3], gr[3];
+        sincos(b.edge_ang[e], &s, &c);
+        const double g[3] = {task.edge_pos[0] + task.edge_len * c, task.edge_pos[1] + task.edge_len * s, task.edge_pos[2] + task.edge_height};
+        world_to_work_at(task, wf, g, ident, gp, gr);
+        put3(wp); put3(vl); put3(gp);
+        out[n++] = (float)b.edge_ang[e];
+    } else if (task.task == TG_TASK_SURFACE_FOLLOW) {
+        const size_t hb = (size_t)e * 2 + (size_t)b.hf_cur[e];
+        const double* H = b.height + hb * SURF_PTS;
+        const double* meta = b.hf_meta + hb * SURF_META;
+        int ti, tj;
+        surf_index(task, tp[0], tp[1], ti, tj);
+        double g0, g1, gp[3], gr[3], nw[3];
+        surf_gradient(H, task.surf_grid, ti, tj, g0, g1);
+        double nrm[3] = {-g1, -g0, 1.0};
+        const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+        nrm[0] /= nn; nrm[1] /= nn; nrm[2] /= nn;
+        m3mulv(nw, Ri, nrm);
+        const double g[3] = {meta[3], meta[4], meta[5]};
+        world_to_work_at(task, wf, g, ident, gp, gr);
+        put3(wp); put4(wo); put3(vl); put3(va); put3(gp);
+        out[n++] = (float)(H[ti * SURF_N + tj] + task.surf_pos[2]);
+        put3(nw);
+    } else {
+        // the free object: getBasePositionAndOrientation / getBaseVelocity brought to the work frame (base_object_env.py:118-139)
+        const double* o13 = b.obj + (size_t)e * 13;
+        double op[3], orr[3], oq[4], ol[3], oa[3];
+        world_to_work_at(task, wf, o13, o13 + 3, op, orr);
+        quat_from_euler(orr, oq);
+        m3mulv(ol, Ri, o13 + 7); m3mulv(oa, Ri, o13 + 10);
+        if (task.task == TG_TASK_OBJECT_PUSH) {
+            const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
+            const int goal = b.goal[e], gi = goal < PUSH_NTRAJ ? (goal < 0 ? 0 : goal) : PUSH_NTRAJ - 1;
+            const double gp[3] = {push_goal_x(task, tr[2 * PUSH_NTRAJ], gi), tr[gi], 0.0}, gr[3] = {0.0, 0.0, tr[PUSH_NTRAJ + gi]};
+            put3(wp); put3(wr); put3(vl); put3(va); put3(op); put3(orr); put3(ol); put3(oa); put3(gp); put3(gr);
+        } else {
+            put3(wp); put4(wo); put3(vl); put3(va); put3(op); put4(oq); put3(ol); put3(oa);
+            if (roll) {
+                const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
+                const double gp[3] = {tr[0], tr[1], 0.0};
+                put3(gp); put4(ident);
+                out[n++] = (float)b.obj_ext[(size_t)e * 4];   // scaled_obj_radius
+            }
+        }
+    }
+    for (; n < TG_ORACLE_NOBS; n++) out[n] = 0.0f;
+}
+
 // Work on the standby slot of env e if it is free to take: EMPTY -> draws + IK, PARTIAL -> one chunk of the
 // blocking move (complete: everything, to READY).
 template <class T>
@@ -857,6 +947,10 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         if (f) surface_features(task, b.hf_meta + hb * SURF_META, tp, tq, f + (size_t)e * TG_PUSH_NFEAT);
     } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
     reward[e] = r; done[e] = d;
+    if (b.oracle) {
+        float* oo = (d && autoreset) ? b.term_oracle : b.oracle;   // a finished env's last state goes to the terminal buffer
+        if (oo) oracle_obs_env<T>(arm, task, b, e, oo + (size_t)e * TG_ORACLE_NOBS);
+    }
     if (d && autoreset && b.pipeline) {
         // terminal camera for the terminal observation, then the standby becomes the live state
         write_camera<T>(arm, k, b.term_cam + (size_t)e * 12);
@@ -864,6 +958,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int c = 0; c < 12; c++) b.term_stim[(size_t)e * 12 + c] = b.stim[(size_t)e * 12 + c];
         acquire_standby<T>(arm, ph, task, b, e);
         write_live_features(task, b, e);
+        if (b.oracle) oracle_obs_env<T>(arm, task, b, e, b.oracle + (size_t)e * TG_ORACLE_NOBS);
     } else {
         write_camera<T>(arm, k, b.cam + (size_t)e * 12);
 #pragma unroll
@@ -895,6 +990,7 @@ reset_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysic
         store_live<T::NB>(b, e, s);
     }
     write_live_features(task, b, e);
+    if (b.oracle) oracle_obs_env<T>(arm, task, b, e, b.oracle + (size_t)e * TG_ORACLE_NOBS);
 }
 
 // recompute every missing standby (after tg_set_draws invalidated them)

@@ -56,6 +56,11 @@ struct TgWorld {
     int raster_grid = 0;
     int standby_blocks = 0;
     long long launches = 0;
+    // tg_step_host: device staging for the actions, a copy stream and one event per observation chunk
+    float* d_actions_stage = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[TG_HOST_MAX_CHUNKS] = {};
+    cudaEvent_t step_ev = nullptr, copy_done_ev = nullptr;
 };
 
 template <class Tp>
@@ -241,7 +246,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         RasterArgs& r = w->ra;
         r.nd_ref = ndmin <= ndmax ? 0.5f * (ndmin + ndmax) : 0.5f;
         if (ndmin <= ndmax && !(ndmin >= 0.5f * r.nd_ref && ndmax <= 2.0f * r.nd_ref)) { tg_destroy(w); return fail(TG_EUNSUPPORTED, "nodef_dep range [%g, %g] too wide for the float path", ndmin, ndmax); }
-        r.n = n; r.S = S; r.bands = S == 256 ? 4 : 1; r.nprim = np; r.prim_nv = dnv;
+        r.n = n; r.e0 = 0; r.S = S; r.bands = S == 256 ? 4 : 1; r.nprim = np; r.prim_nv = dnv;
         r.th = tan(cfg->sensor.fov_deg * (M_PI / 180.0) / 2.0);
         r.near_ = cfg->sensor.near_; r.far_ = cfg->sensor.far_;
         r.F = cfg->sensor.far_ / (cfg->sensor.far_ - cfg->sensor.near_);
@@ -288,6 +293,10 @@ extern "C" int tg_destroy(TgWorld* w)
     cudaSetDevice(w->device);
     for (void* p : w->allocs) cudaFree(p);
     if (w->d_draws) cudaFree(w->d_draws);
+    if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
+    for (cudaEvent_t ev : w->chunk_ev) if (ev) cudaEventDestroy(ev);
+    if (w->step_ev) cudaEventDestroy(w->step_ev);
+    if (w->copy_done_ev) cudaEventDestroy(w->copy_done_ev);
     delete w;
     return TG_OK;
 }
@@ -348,14 +357,22 @@ extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)
 
 static dim3 env_grid(const TgWorld* w) { return dim3(w->eb.step_blocks); } // 128 threads = 4 warps = 4 * lanes envs
 
-static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaStream_t st, bool terminal_state = false)
+static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaStream_t st, bool terminal_state = false, int e0 = 0, int e1 = -1)
 {
     RasterArgs r = w->ra;
     r.obs = d_obs; r.mask = mask;
+    if (e1 < 0) e1 = w->n;
+    r.e0 = e0; r.n = e1;   // envs [e0, e1)
+    const int cnt = e1 - e0;
+    if (cnt <= 0) return TG_OK;
     if (terminal_state) { r.cam = w->eb.term_cam; r.stim = w->eb.term_stim; r.hf_flip = 1; }
-    if (w->cfg.task.task == TG_TASK_OBJECT_ROLL) raster_sphere_kernel<<<std::min((w->n + 7) / 8, 8 * w->sm_count), SPH_THREADS, 0, st>>>(r);
-    else if (r.hf) raster_hf_kernel<<<w->raster_grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
-    else raster_kernel<<<w->raster_grid, RASTER_THREADS, w->raster_smem, st>>>(r);
+    if (w->cfg.task.task == TG_TASK_OBJECT_ROLL) raster_sphere_kernel<<<std::min((cnt + 7) / 8, 8 * w->sm_count), SPH_THREADS, 0, st>>>(r);
+    else {
+        const int wp = r.hf ? HF_WARPS : RASTER_WARPS;
+        const int grid = std::min(w->raster_grid, ((cnt + wp - 1) / wp) * r.bands);
+        if (r.hf) raster_hf_kernel<<<grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
+        else raster_kernel<<<grid, RASTER_THREADS, w->raster_smem, st>>>(r);
+    }
     w->launches++;
     CK(cudaGetLastError());
     return TG_OK;
@@ -401,6 +418,14 @@ extern "C" int tg_bind_features(TgWorld* w, float* d_feat, float* d_term_feat)
     return TG_OK;
 }
 
+extern "C" int tg_bind_oracle_obs(TgWorld* w, float* d_oracle, float* d_term_oracle)
+{
+    if (!w) return fail(TG_EINVAL, "bad arguments");
+    w->eb.oracle = d_oracle;
+    w->eb.term_oracle = d_oracle ? d_term_oracle : nullptr;
+    return TG_OK;
+}
+
 extern "C" int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream)
 {
     if (!w || !d_obs) return fail(TG_EINVAL, "bad arguments");
@@ -435,6 +460,52 @@ extern "C" int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float
     if (d_term_obs && (rc = launch_raster(w, d_term_obs, d_done, st))) return rc;
     if ((rc = launch_reset(w, d_done, st))) return rc;
     return launch_raster(w, d_obs, nullptr, st);
+}
+
+// One env step with HOST buffers (the call a numpy VecEnv makes): the observation leaves in chunks, each chunk's
+// device->host copy (copy stream) overlapping the next chunk's raster and the terminal-observation raster (caller's stream).
+extern "C" int tg_step_host(TgWorld* w, const TgHostStep* hs, void* stream)
+{
+    if (!w || !hs || !hs->h_actions || !hs->d_reward || !hs->d_done || !hs->h_reward || !hs->h_done) return fail(TG_EINVAL, "bad arguments");
+    if ((hs->h_obs != nullptr) != (hs->d_obs != nullptr)) return fail(TG_EINVAL, "h_obs and d_obs go together");
+    if (!hs->h_obs && !hs->h_oracle) return fail(TG_EINVAL, "no observation requested (h_obs and h_oracle are both NULL)");
+    if ((hs->h_feat != nullptr) != (hs->d_feat != nullptr)) return fail(TG_EINVAL, "h_feat and d_feat go together");
+    if (!w->eb.pipeline) return fail(TG_EUNSUPPORTED, "tg_step_host needs the standby reset pipeline (max_steps >= 2)");
+    CK(cudaSetDevice(w->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = w->n;
+    if (!w->copy_stream) {
+        int rc;
+        if ((rc = dalloc(w, &w->d_actions_stage, (size_t)n * w->cfg.task.act_dim))) return rc;
+        CK(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t& ev : w->chunk_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&w->step_ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&w->copy_done_ev, cudaEventDisableTiming));
+    }
+    int chunks = hs->chunks <= 0 ? 4 : hs->chunks;
+    if (chunks > TG_HOST_MAX_CHUNKS) chunks = TG_HOST_MAX_CHUNKS;
+    if (chunks > n) chunks = n;
+    const size_t img = (size_t)w->S * w->S;
+    int rc;
+    CK(cudaMemcpyAsync(w->d_actions_stage, hs->h_actions, sizeof(float) * n * w->cfg.task.act_dim, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_step(w, w->d_actions_stage, hs->d_reward, hs->d_done, 1, st))) return rc;
+    CK(cudaEventRecord(w->step_ev, st));
+    CK(cudaStreamWaitEvent(w->copy_stream, w->step_ev, 0));
+    CK(cudaMemcpyAsync(hs->h_reward, hs->d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, w->copy_stream));
+    CK(cudaMemcpyAsync(hs->h_done, hs->d_done, n, cudaMemcpyDeviceToHost, w->copy_stream));
+    if (hs->h_feat) CK(cudaMemcpyAsync(hs->h_feat, hs->d_feat, sizeof(float) * TG_PUSH_NFEAT * n, cudaMemcpyDeviceToHost, w->copy_stream));
+    if (hs->h_oracle && w->eb.oracle) CK(cudaMemcpyAsync(hs->h_oracle, w->eb.oracle, sizeof(float) * TG_ORACLE_NOBS * n, cudaMemcpyDeviceToHost, w->copy_stream));
+    for (int c = 0; hs->d_obs && c < chunks; c++) {   // observation_mode "oracle" renders nothing
+        const int e0 = (int)((long long)n * c / chunks), e1 = (int)((long long)n * (c + 1) / chunks);
+        if ((rc = launch_raster(w, hs->d_obs, nullptr, st, false, e0, e1))) return rc;
+        CK(cudaEventRecord(w->chunk_ev[c], st));
+        CK(cudaStreamWaitEvent(w->copy_stream, w->chunk_ev[c], 0));
+        CK(cudaMemcpyAsync(hs->h_obs + img * e0, hs->d_obs + img * e0, img * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, w->copy_stream));
+    }
+    if (hs->d_obs && hs->d_term_obs && (rc = launch_raster(w, hs->d_term_obs, hs->d_done, st, true))) return rc;
+    CK(cudaEventRecord(w->copy_done_ev, w->copy_stream));
+    CK(cudaStreamWaitEvent(st, w->copy_done_ev, 0));   // the caller's stream is complete only when the host buffers are
+    return TG_OK;
 }
 
 extern "C" int tg_physics_only(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, void* stream)

@@ -616,6 +616,21 @@ class TactileWorld:
             self._upload_draws()
         return self.obs, self.reward, self.done
 
+    def step_host(self, h_actions, h_obs, h_reward, h_done, h_feat=None, want_terminal_obs=True, chunks=0):
+        """One env step with pinned HOST tensors in and out (tg_step_host): the observation is rendered and copied out in
+        chunks so the PCIe transfer overlaps the raster.  Valid after synchronising the current stream."""
+        hs = L.TgHostStep()
+        hs.h_actions, hs.h_obs, hs.h_reward, hs.h_done = h_actions.data_ptr(), h_obs.data_ptr(), h_reward.data_ptr(), h_done.data_ptr()
+        hs.d_obs, hs.d_reward, hs.d_done = self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr()
+        hs.d_term_obs = self.term_obs.data_ptr() if want_terminal_obs else None
+        if h_feat is not None:
+            hs.d_feat, hs.h_feat = self.feat.data_ptr(), h_feat.data_ptr()
+        hs.chunks = chunks
+        L.check(self.lib.tg_step_host(self.h, C.byref(hs), self._stream()))
+        self._steps_since_check += 1
+        if self._steps_since_check >= DRAW_CHECK_EVERY:
+            self._upload_draws()
+
     def physics_only(self, actions):
         L.check(self.lib.tg_physics_only(self.h, actions.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
 

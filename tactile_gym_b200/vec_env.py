@@ -23,7 +23,7 @@ CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": ob
 
 
 class TactileVecEnv(_VecEnvBase):
-    def __init__(self, env_id, n_envs, seed=None, env_kwargs=None, device=0, lanes_per_warp=0):
+    def __init__(self, env_id, n_envs, seed=None, env_kwargs=None, device=0, lanes_per_warp=0, copy_chunks=0):
         kw = dict(env_kwargs or {})
         if env_id not in CONFIG_BUILDERS:
             raise NotImplementedError("%s is not built yet in tactile_gym_b200" % env_id)
@@ -41,6 +41,9 @@ class TactileVecEnv(_VecEnvBase):
         cfg, keep, draw = built if len(built) == 3 else (built[0], built[1], None)
         self.world = TactileWorld(cfg, keep, device=device, draw_fn=draw)
         self.num_envs = n_envs
+        # tg_step_host needs the standby reset pipeline (episodes of >= 2 steps); copy_chunks < 0 forces the torch copy path
+        self.copy_chunks = copy_chunks
+        self._host_step = copy_chunks >= 0 and max_steps >= 2
         S = int(image_size[0])
         sp = {"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)}
         self._with_feat = self.observation_mode == "tactile_and_feature"
@@ -64,6 +67,12 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_rew = torch.zeros(n_envs, dtype=torch.float32).pin_memory()
         self._pin_done = torch.zeros(n_envs, dtype=torch.uint8).pin_memory()
         self._pin_feat = torch.zeros((n_envs, 12), dtype=torch.float32).pin_memory() if self._with_feat else None
+        self._blank_infos = [{} for _ in range(n_envs)]
+        # terminal observations of the envs that finish in a step: gathered on the device, copied out through a pinned stage
+        # that grows (geometrically) to the largest number of simultaneous episode ends seen
+        self._pin_idx = torch.zeros(n_envs, dtype=torch.int64).pin_memory()
+        self._term_dev = self._term_stage = None
+        self._grow_term_stage(min(n_envs, 64))
         if seed is not None:
             self.seed(seed)
         self.h2d_bytes_per_step = self._pin_actions.numel() * 4
@@ -97,6 +106,11 @@ class TactileVecEnv(_VecEnvBase):
     def step_async(self, actions):
         torch = self.world.torch
         self._pin_actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, -1)))
+        if self._host_step:
+            # one C-ABI call with the pinned host buffers: chunked raster, D2H overlapped on the library's copy stream
+            self.world.step_host(self._pin_actions, self._next_obs_buffer(), self._pin_rew, self._pin_done,
+                                 h_feat=self._pin_feat, want_terminal_obs=True, chunks=self.copy_chunks)
+            return
         a = self._pin_actions.to(self.world.device, non_blocking=True)
         self.world.step(a, want_terminal_obs=True)
         self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
@@ -105,26 +119,50 @@ class TactileVecEnv(_VecEnvBase):
         if self._with_feat:
             self._pin_feat.copy_(self.world.feat, non_blocking=True)
 
+    def _grow_term_stage(self, k):
+        torch = self.world.torch
+        if self._term_stage is not None and self._term_stage.shape[0] >= k:
+            return
+        cap = min(self.num_envs, max(64, 1 << int(k - 1).bit_length()))
+        S = self.world.S
+        self._term_dev = torch.zeros((cap, S, S, 1), dtype=torch.uint8, device=self.world.device)
+        self._term_stage = torch.zeros((cap, S, S, 1), dtype=torch.uint8).pin_memory()
+
     def step_wait(self):
         torch = self.world.torch
-        torch.cuda.synchronize(self.world.device)
+        torch.cuda.current_stream(self.world.device).synchronize()
         rew = self._pin_rew.numpy().copy()
-        done = self._pin_done.numpy().astype(bool)
+        done = self._pin_done.numpy().view(np.bool_).copy()
         self._ep_ret += rew
         self._ep_len += 1
-        infos = [{} for _ in range(self.num_envs)]
-        if done.any():
-            idx = np.nonzero(done)[0]
-            didx = torch.as_tensor(idx, device=self.world.device)
-            term = self.world.term_obs[didx].cpu().numpy()
-            tfeat = self.world.term_feat[didx].cpu().numpy() if self._with_feat else None
-            for k, i in enumerate(idx):
-                infos[i]["terminal_observation"] = {"tactile": term[k]}
+        # envs that did not finish share their (empty) info dict from step to step: 4096 fresh dicts per step cost more
+        # host time than the kernels; finished envs get a fresh dict
+        infos = list(self._blank_infos)
+        idx = np.flatnonzero(done)
+        if idx.size:
+            k = idx.size
+            self._grow_term_stage(k)
+            didx = self._pin_idx[:k]
+            didx.copy_(torch.from_numpy(idx))
+            didx = didx.to(self.world.device, non_blocking=True)
+            # gather the finished envs' terminal observations on the device, one small pinned copy out
+            term = self._term_stage[:k]
+            torch.index_select(self.world.term_obs, 0, didx, out=self._term_dev[:k])
+            term.copy_(self._term_dev[:k], non_blocking=True)
+            tfeat = None
+            if self._with_feat:
+                tfeat = self.world.term_feat[didx].cpu().numpy()
+            torch.cuda.current_stream(self.world.device).synchronize()
+            term = term.numpy().copy()
+            now = round(time.time() - self._t0, 6)
+            for j, i in enumerate(idx):
+                info = {"terminal_observation": {"tactile": term[j]},
+                        "episode": {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": now}}
                 if self._with_feat:
-                    infos[i]["terminal_observation"]["extended_feature"] = tfeat[k][: self._nfeat]
-                infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
-                self._ep_ret[i] = 0
-                self._ep_len[i] = 0
+                    info["terminal_observation"]["extended_feature"] = tfeat[j][: self._nfeat]
+                infos[i] = info
+            self._ep_ret[idx] = 0
+            self._ep_len[idx] = 0
         return self._obs_dict(), rew, done, infos
 
     def step(self, actions):
