@@ -233,6 +233,52 @@ def tactile_image(m, q, S, tris_world, refimg, border_on=True, want_depth=False)
     return (img, dout) if want_depth else img
 
 
+def mul_transforms(pa, qa, pb, qb):
+    po, qo = np.zeros(3), np.zeros(4)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (pa, qa, pb, qb)]
+    lib().or_mul_transforms(_dptr(a[0]), _dptr(a[1]), _dptr(a[2]), _dptr(a[3]), _dptr(po), _dptr(qo))
+    return po, qo
+
+
+def mat_from_quat(q):
+    R = np.zeros(9)
+    lib().or_mat_from_quat(_dptr(np.ascontiguousarray(q, dtype=np.float64)), _dptr(R))
+    return R.reshape(3, 3)
+
+
+def world_to_work(m, pos, quat):
+    """worldframe_to_workframe (robots/arms/base_robot_arm.py:62-74): pose -> rpy -> quaternion -> inverse workframe -> rpy"""
+    wq = quat_from_euler(np.array(m.workframe_rpy[:]))
+    iq = np.array([-wq[0], -wq[1], -wq[2], wq[3]])                 # invertTransform
+    ip = -(mat_from_quat(iq) @ np.array(m.workframe_pos[:]))
+    q2 = quat_from_euler(euler_from_quat(quat))
+    po, qo = mul_transforms(ip, iq, pos, q2)
+    return po, euler_from_quat(qo)
+
+
+def world_to_work_vec(m, v):
+    """worldvec_to_workvec / worldvel_to_workvel (base_robot_arm.py:88-118): the matrix of the inverted workframe quaternion"""
+    wq = quat_from_euler(np.array(m.workframe_rpy[:]))
+    return mat_from_quat(np.array([-wq[0], -wq[1], -wq[2], wq[3]])) @ np.asarray(v, dtype=np.float64)
+
+
+def tcp_state_workframe(m, s):
+    """get_current_TCP_pos_vel_workframe (base_robot_arm.py:136-172): pos, rpy, orn, lin vel, ang vel of the TCP link's
+    inertial frame (getLinkState(computeLinkVelocity=True) items 0, 1, 6, 7) in the work frame"""
+    q = np.array(s.q[: m.ndof]); qd = np.array(s.qd[: m.ndof])
+    P, Q = link_states(m, q)
+    lin, ang = np.zeros(3), np.zeros(3)
+    lib().or_link_velocity(C.byref(m), _dptr(np.ascontiguousarray(q)), _dptr(np.ascontiguousarray(qd)), C.c_int(m.tcp_link), _dptr(lin), _dptr(ang))
+    pos, rpy = world_to_work(m, P[m.tcp_link], Q[m.tcp_link])
+    return pos, rpy, quat_from_euler(rpy), world_to_work_vec(m, lin), world_to_work_vec(m, ang)
+
+
+def object_state_workframe(m, o):
+    """get_obj_pos_workframe / get_obj_vel_workframe (rl_envs/nonprehensile_manipulation/base_object_env.py:118-139)"""
+    pos, rpy = world_to_work(m, np.array(o.pos[:]), np.array(o.quat[:]))
+    return pos, rpy, quat_from_euler(rpy), world_to_work_vec(m, np.array(o.vel[:])), world_to_work_vec(m, np.array(o.omg[:]))
+
+
 # ---------------------------------------------------------------- gym <= 0.21 seeding
 def gym_np_random(seed):
     """gym.utils.seeding.np_random of gym <= 0.21 (base_tactile_env.py:61-64): a numpy RandomState seeded
@@ -334,6 +380,11 @@ class EdgeFollowOracle:
         edge_dist = np.abs(a_[0] * b_[1] - a_[1] * b_[0]) / np.linalg.norm(p2 - p1)
         done = bool(goal_dist < self.termination_dist or self.steps >= self.max_steps)
         return -(1.0 * goal_dist + 10.0 * edge_dist), done
+
+    def oracle_obs(self):   # get_oracle_obs, edge_follow_env.py:454-476
+        pos, _, _, lin, _ = tcp_state_workframe(self.m, self.s)
+        goal, _ = world_to_work(self.m, self.goal_pos, np.array([0.0, 0.0, 0.0, 1.0]))
+        return np.hstack([pos, lin, goal, self.edge_ang])
 
     def encode_scale(self, action):
         enc = np.zeros(6)
@@ -451,6 +502,11 @@ class ObjectBalanceOracle:
         rpy_dist = np.abs(((rpy_deg - init_deg) + 180) % 360 - 180)
         fall = bool(rpy_dist[0] > 35 or rpy_dist[1] > 35 or np.linalg.norm(np.array(self.o.pos[:]) - self.init_obj_pos) > 0.1)
         return 1.0, bool(fall or self.steps >= self.max_steps)
+
+    def oracle_obs(self):   # get_oracle_obs, object_balance_env.py:528-563
+        pos, _, orn, lin, ang = tcp_state_workframe(self.m, self.s)
+        op, _, oo, ol, oa = object_state_workframe(self.m, self.o)
+        return np.hstack([pos, orn, lin, ang, op, oo, ol, oa])
 
     def encode_scale(self, action):
         enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
@@ -613,6 +669,12 @@ class SurfaceFollowOracle:
             goal_xy = np.linalg.norm(p[:2] - self.goal_pos[:2])
             return -(1.0 * goal_xy + 10.0 * surf_dist + w_norm * cos_dist), done
         return -(1.0 * surf_dist + w_norm * cos_dist), done
+
+    def oracle_obs(self):   # get_oracle_obs, base_surface_env.py:789-819 (tip_i / tip_j from the last get_step_data)
+        pos, _, orn, lin, ang = tcp_state_workframe(self.m, self.s)
+        goal, _ = world_to_work(self.m, self.goal_pos, np.array([0.0, 0.0, 0.0, 1.0]))
+        n = world_to_work_vec(self.m, self.surface_normals[self.tip_i, self.tip_j])
+        return np.hstack([pos, orn, lin, ang, goal, self.surface_array[self.tip_i, self.tip_j, 2], n])
 
     def features(self):   # SurfaceFollowGoalEnv.get_extended_feature_array (surface_follow_goal_env.py:83-97)
         tp, _ = tcp_pose_workframe(self.m, np.array(self.s.q[: self.m.ndof]))
@@ -798,6 +860,11 @@ class ObjectPushOracle:
         lib().or_mat_from_quat(_dptr(q), _dptr(R)); R = R.reshape(3, 3)
         return self.tris_local @ R.T + np.array(self.o.pos[:])
 
+    def oracle_obs(self):   # get_oracle_obs :571-609
+        pos, rpy, _, lin, ang = tcp_state_workframe(self.m, self.s)
+        op, orpy, _, ol, oa = object_state_workframe(self.m, self.o)
+        return np.hstack([pos, rpy, lin, ang, op, orpy, ol, oa, self.goal_pos_work, self.goal_rpy_work])
+
     def features(self):   # get_extended_feature_array :611-629
         p, r = tcp_pose_workframe(self.m, np.array(self.s.q[: self.m.ndof]))
         return np.concatenate([p, r, self.goal_pos_work, self.goal_rpy_work])
@@ -972,6 +1039,11 @@ class ObjectRollOracle:
         done = bool(d < self.termination_pos_dist or self.steps >= self.max_steps)
         reward = (1.0 if d < self.termination_pos_dist else 0.0) if self.reward_mode == "sparse" else -d
         return reward, done
+
+    def oracle_obs(self):    # get_oracle_obs :371-409
+        pos, _, orn, lin, ang = tcp_state_workframe(self.m, self.s)
+        op, _, oo, ol, oa = object_state_workframe(self.m, self.o)
+        return np.hstack([pos, orn, lin, ang, op, oo, ol, oa, self.goal_pos_tcp, [0.0, 0.0, 0.0, 1.0], self.radius])
 
     def features(self):      # get_extended_feature_array :402-408
         return self.goal_pos_tcp.copy()

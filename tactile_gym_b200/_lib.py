@@ -12,6 +12,7 @@ TG_MAXB, TG_MAXSUB, TG_MAXTRI, TG_MAXDRAW = 8, 16, 64, 8
 TG_TOPO_CHAIN6, TG_TOPO_MG400 = 0, 1
 TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE, TG_TASK_SURFACE_FOLLOW, TG_TASK_OBJECT_PUSH, TG_TASK_OBJECT_ROLL = 0, 1, 2, 3, 4
 TG_PUSH_NTRAJ, TG_PUSH_NFEAT = 10, 12
+TG_ORACLE_NOBS = 36
 TG_PUSH_WORK, TG_PUSH_WORK_DRIVE, TG_PUSH_TCP_TYRZ, TG_PUSH_TCP_TXTYRZ = 0, 1, 2, 3
 
 D3 = C.c_double * 3

@@ -547,11 +547,25 @@ class TactileWorld:
                 self.feat = torch.zeros((self.n, L.TG_PUSH_NFEAT), dtype=torch.float32, device=self.device)
                 self.term_feat = torch.zeros_like(self.feat)
                 L.check(self.lib.tg_bind_features(self.h, self.feat.data_ptr(), self.term_feat.data_ptr()))
+        # observation_mode "oracle" (get_oracle_obs): length of the task's state vector; buffers bound on demand
+        self.n_oracle = {L.TG_TASK_EDGE_FOLLOW: 10, L.TG_TASK_SURFACE_FOLLOW: 20, L.TG_TASK_OBJECT_BALANCE: 26,
+                         L.TG_TASK_OBJECT_PUSH: 30, L.TG_TASK_OBJECT_ROLL: 34}[cfg.task.task]
+        self.oracle_obs = self.term_oracle_obs = None
         self._draw = draw_fn if draw_fn is not None else edge_follow_draws(cfg.task)
         self._rngs = [seeding.np_random(None)[0] for _ in range(self.n)]
         self._host_draws = None
         self._steps_since_check = 0
         self._upload_draws(fresh=True)
+
+    def bind_oracle_obs(self):
+        """observation_mode "oracle": every following step / reset fills self.oracle_obs [N, TG_ORACLE_NOBS] (first
+        n_oracle columns meaningful) and, for finished envs, self.term_oracle_obs."""
+        if self.oracle_obs is None:
+            torch = self.torch
+            self.oracle_obs = torch.zeros((self.n, L.TG_ORACLE_NOBS), dtype=torch.float32, device=self.device)
+            self.term_oracle_obs = torch.zeros_like(self.oracle_obs)
+            L.check(self.lib.tg_bind_oracle_obs(self.h, self.oracle_obs.data_ptr(), self.term_oracle_obs.data_ptr()))
+        return self.oracle_obs
 
     # ------------------------------------------------------------------ seeding / draws
     def seed(self, seeds):
@@ -616,15 +630,21 @@ class TactileWorld:
             self._upload_draws()
         return self.obs, self.reward, self.done
 
-    def step_host(self, h_actions, h_obs, h_reward, h_done, h_feat=None, want_terminal_obs=True, chunks=0):
+    def step_host(self, h_actions, h_obs, h_reward, h_done, h_feat=None, h_oracle=None, want_terminal_obs=True, chunks=0):
         """One env step with pinned HOST tensors in and out (tg_step_host): the observation is rendered and copied out in
-        chunks so the PCIe transfer overlaps the raster.  Valid after synchronising the current stream."""
+        chunks so the PCIe transfer overlaps the raster.  h_obs None (observation_mode "oracle"): nothing is rendered.
+        Valid after synchronising the current stream."""
         hs = L.TgHostStep()
-        hs.h_actions, hs.h_obs, hs.h_reward, hs.h_done = h_actions.data_ptr(), h_obs.data_ptr(), h_reward.data_ptr(), h_done.data_ptr()
-        hs.d_obs, hs.d_reward, hs.d_done = self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr()
-        hs.d_term_obs = self.term_obs.data_ptr() if want_terminal_obs else None
+        hs.h_actions, hs.h_reward, hs.h_done = h_actions.data_ptr(), h_reward.data_ptr(), h_done.data_ptr()
+        hs.d_reward, hs.d_done = self.reward.data_ptr(), self.done.data_ptr()
+        if h_obs is not None:
+            hs.h_obs, hs.d_obs = h_obs.data_ptr(), self.obs.data_ptr()
+            hs.d_term_obs = self.term_obs.data_ptr() if want_terminal_obs else None
         if h_feat is not None:
             hs.d_feat, hs.h_feat = self.feat.data_ptr(), h_feat.data_ptr()
+        if h_oracle is not None:
+            self.bind_oracle_obs()
+            hs.h_oracle = h_oracle.data_ptr()
         hs.chunks = chunks
         L.check(self.lib.tg_step_host(self.h, C.byref(hs), self._stream()))
         self._steps_since_check += 1

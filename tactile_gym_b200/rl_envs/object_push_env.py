@@ -1,7 +1,4 @@
 """object_push-v0 (tactile_gym/rl_envs/nonprehensile_manipulation/object_push/object_push_env.py) on the batched engine."""
-import numpy as np
-
-from .. import spaces
 from ..engine import TactileWorld, object_push_config
 from .base_tactile_env import BaseTactileEnv
 
@@ -37,25 +34,3 @@ class ObjectPushEnv(BaseTactileEnv):
         cfg, keep, draw = object_push_config(env_modes, image_size, max_steps, n_envs=1)
         self.world = TactileWorld(cfg, keep, device=device, draw_fn=draw)
         self._finish_init()
-
-    def _finish_init(self):
-        self.min_action, self.max_action = -0.25, 0.25
-        self.act_dim = self.world.act_dim
-        self.action_space = spaces.Box(low=self.min_action, high=self.max_action, shape=(self.act_dim,), dtype=np.float32)
-        if self.observation_mode not in ("tactile", "tactile_and_feature"):
-            raise NotImplementedError("observation_mode %r: only 'tactile' and 'tactile_and_feature' are built" % self.observation_mode)
-        S = self._image_size[0]
-        sp = {"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)}
-        if self.observation_mode == "tactile_and_feature":
-            sp["extended_feature"] = spaces.Box(low=-np.inf, high=np.inf, shape=(12,), dtype=np.float32)
-        self.observation_space = spaces.Dict(sp)
-        self.reset()
-
-    def _obs(self):
-        o = {"tactile": self.world.obs[0].cpu().numpy()}
-        if self.observation_mode == "tactile_and_feature":
-            o["extended_feature"] = self.world.feat[0].cpu().numpy()
-        return o
-
-    def get_extended_feature_array(self):
-        return self.world.feat[0].cpu().numpy()

@@ -1,8 +1,5 @@
 """surface_follow-v0 (tactile_gym/rl_envs/exploration/surface_follow/surface_follow_auto/surface_follow_auto_env.py on
 base_surface_env.py, noise_mode "simplex") on the batched engine."""
-import numpy as np
-
-from .. import spaces
 from ..engine import TactileWorld, surface_follow_config, surface_follow_goal_config
 from .base_tactile_env import BaseTactileEnv
 
@@ -49,23 +46,4 @@ class SurfaceFollowGoalEnv(BaseTactileEnv):
         self.t_s_name = env_modes["tactile_sensor_name"]
         cfg, keep, draw = surface_follow_goal_config(env_modes, image_size, max_steps, n_envs=1)
         self.world = TactileWorld(cfg, keep, device=device, draw_fn=draw)
-        self.min_action, self.max_action = -0.25, 0.25
-        self.act_dim = self.world.act_dim
-        self.action_space = spaces.Box(low=self.min_action, high=self.max_action, shape=(self.act_dim,), dtype=np.float32)
-        if self.observation_mode not in ("tactile", "tactile_and_feature"):
-            raise NotImplementedError("observation_mode %r: only 'tactile' and 'tactile_and_feature' are built" % self.observation_mode)
-        S = self._image_size[0]
-        sp = {"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)}
-        if self.observation_mode == "tactile_and_feature":
-            sp["extended_feature"] = spaces.Box(low=-np.inf, high=np.inf, shape=(6,), dtype=np.float32)
-        self.observation_space = spaces.Dict(sp)
-        self.reset()
-
-    def _obs(self):
-        o = {"tactile": self.world.obs[0].cpu().numpy()}
-        if self.observation_mode == "tactile_and_feature":
-            o["extended_feature"] = self.world.feat[0, :6].cpu().numpy()
-        return o
-
-    def get_extended_feature_array(self):
-        return self.world.feat[0, :6].cpu().numpy()
+        self._finish_init()

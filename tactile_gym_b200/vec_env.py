@@ -33,7 +33,7 @@ class TactileVecEnv(_VecEnvBase):
         if kw.get("show_gui") or kw.get("show_tactile"):
             raise ValueError("show_gui / show_tactile are not available in the batched engine")
         self.observation_mode = env_modes.get("observation_mode", "tactile")
-        if self.observation_mode != "tactile" and not (self.observation_mode == "tactile_and_feature" and env_id in ("object_push-v0", "object_roll-v0", "surface_follow-v1")):
+        if self.observation_mode not in ("oracle", "tactile") and not (self.observation_mode == "tactile_and_feature" and env_id in ("object_push-v0", "object_roll-v0", "surface_follow-v1")):
             raise NotImplementedError("observation_mode %r is not built for %s" % (self.observation_mode, env_id))
         image_size = kw.get("image_size", [64, 64])
         max_steps = kw.get("max_steps", 250)
@@ -45,7 +45,15 @@ class TactileVecEnv(_VecEnvBase):
         self.copy_chunks = copy_chunks
         self._host_step = copy_chunks >= 0 and max_steps >= 2
         S = int(image_size[0])
-        sp = {"tactile": spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)}
+        # "oracle": the task's state vector instead of the image (get_oracle_obs); nothing is rendered in that mode
+        self._oracle = self.observation_mode == "oracle"
+        sp = {}
+        if self._oracle:
+            self.world.bind_oracle_obs()
+            self._noracle = self.world.n_oracle
+            sp["oracle"] = spaces.Box(low=-np.inf, high=np.inf, shape=(self._noracle,), dtype=np.float32)
+        else:
+            sp["tactile"] = spaces.Box(low=0, high=255, shape=(S, S, 1), dtype=np.uint8)
         self._with_feat = self.observation_mode == "tactile_and_feature"
         self._nfeat = self.world.nfeat
         if self._with_feat:
@@ -61,7 +69,8 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_actions = torch.zeros((n_envs, self.world.act_dim), dtype=torch.float32).pin_memory()
         # two pinned observation buffers, used alternately: the arrays handed out are views (no 64 MB host copy);
         # an observation stays valid until the step after next
-        self._pin_obs2 = [torch.zeros((n_envs, S, S, 1), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._pin_obs2 = [torch.zeros((1 if self._oracle else n_envs, S, S, 1), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._pin_oracle = torch.zeros((n_envs, self.world.oracle_obs.shape[1]), dtype=torch.float32).pin_memory() if self._oracle else None
         self._flip = 0
         self._pin_obs = self._pin_obs2[0]
         self._pin_rew = torch.zeros(n_envs, dtype=torch.float32).pin_memory()
@@ -76,7 +85,7 @@ class TactileVecEnv(_VecEnvBase):
         if seed is not None:
             self.seed(seed)
         self.h2d_bytes_per_step = self._pin_actions.numel() * 4
-        self.d2h_bytes_per_step = self._pin_obs.numel() + self._pin_rew.numel() * 4 + self._pin_done.numel() + (self._pin_feat.numel() * 4 if self._with_feat else 0)
+        self.d2h_bytes_per_step = (self._pin_oracle.numel() * 4 if self._oracle else self._pin_obs.numel()) + self._pin_rew.numel() * 4 + self._pin_done.numel() + (self._pin_feat.numel() * 4 if self._with_feat else 0)
 
     # ---------------------------------------------------------------- VecEnv API (host numpy)
     def seed(self, seed=None):
@@ -88,6 +97,8 @@ class TactileVecEnv(_VecEnvBase):
         return self._pin_obs
 
     def _obs_dict(self):
+        if self._oracle:
+            return {"oracle": self._pin_oracle.numpy()[:, : self._noracle].copy()}
         o = {"tactile": self._pin_obs.numpy()}
         if self._with_feat:
             o["extended_feature"] = self._pin_feat.numpy()[:, : self._nfeat].copy()
@@ -95,7 +106,10 @@ class TactileVecEnv(_VecEnvBase):
 
     def reset(self):
         self.world.reset()
-        self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
+        if self._oracle:
+            self._pin_oracle.copy_(self.world.oracle_obs, non_blocking=True)
+        else:
+            self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
         if self._with_feat:
             self._pin_feat.copy_(self.world.feat, non_blocking=True)
         self.world.torch.cuda.synchronize(self.world.device)
@@ -108,12 +122,15 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, -1)))
         if self._host_step:
             # one C-ABI call with the pinned host buffers: chunked raster, D2H overlapped on the library's copy stream
-            self.world.step_host(self._pin_actions, self._next_obs_buffer(), self._pin_rew, self._pin_done,
-                                 h_feat=self._pin_feat, want_terminal_obs=True, chunks=self.copy_chunks)
+            self.world.step_host(self._pin_actions, None if self._oracle else self._next_obs_buffer(), self._pin_rew, self._pin_done,
+                                 h_feat=self._pin_feat, h_oracle=self._pin_oracle, want_terminal_obs=True, chunks=self.copy_chunks)
             return
         a = self._pin_actions.to(self.world.device, non_blocking=True)
         self.world.step(a, want_terminal_obs=True)
-        self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
+        if self._oracle:
+            self._pin_oracle.copy_(self.world.oracle_obs, non_blocking=True)
+        else:
+            self._next_obs_buffer().copy_(self.world.obs, non_blocking=True)
         self._pin_rew.copy_(self.world.reward, non_blocking=True)
         self._pin_done.copy_(self.world.done, non_blocking=True)
         if self._with_feat:
@@ -121,6 +138,8 @@ class TactileVecEnv(_VecEnvBase):
 
     def _grow_term_stage(self, k):
         torch = self.world.torch
+        if self._oracle:
+            return
         if self._term_stage is not None and self._term_stage.shape[0] >= k:
             return
         cap = min(self.num_envs, max(64, 1 << int(k - 1).bit_length()))
@@ -145,22 +164,28 @@ class TactileVecEnv(_VecEnvBase):
             didx = self._pin_idx[:k]
             didx.copy_(torch.from_numpy(idx))
             didx = didx.to(self.world.device, non_blocking=True)
-            # gather the finished envs' terminal observations on the device, one small pinned copy out
-            term = self._term_stage[:k]
-            torch.index_select(self.world.term_obs, 0, didx, out=self._term_dev[:k])
-            term.copy_(self._term_dev[:k], non_blocking=True)
-            tfeat = None
-            if self._with_feat:
-                tfeat = self.world.term_feat[didx].cpu().numpy()
-            torch.cuda.current_stream(self.world.device).synchronize()
-            term = term.numpy().copy()
             now = round(time.time() - self._t0, 6)
-            for j, i in enumerate(idx):
-                info = {"terminal_observation": {"tactile": term[j]},
-                        "episode": {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": now}}
+            if self._oracle:
+                term = self.world.term_oracle_obs[didx].cpu().numpy()[:, : self._noracle]
+                for j, i in enumerate(idx):
+                    infos[i] = {"terminal_observation": {"oracle": term[j]},
+                                "episode": {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": now}}
+            else:
+                # gather the finished envs' terminal observations on the device, one small pinned copy out
+                term = self._term_stage[:k]
+                torch.index_select(self.world.term_obs, 0, didx, out=self._term_dev[:k])
+                term.copy_(self._term_dev[:k], non_blocking=True)
+                tfeat = None
                 if self._with_feat:
-                    info["terminal_observation"]["extended_feature"] = tfeat[j][: self._nfeat]
-                infos[i] = info
+                    tfeat = self.world.term_feat[didx].cpu().numpy()
+                torch.cuda.current_stream(self.world.device).synchronize()
+                term = term.numpy().copy()
+                for j, i in enumerate(idx):
+                    info = {"terminal_observation": {"tactile": term[j]},
+                            "episode": {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": now}}
+                    if self._with_feat:
+                        info["terminal_observation"]["extended_feature"] = tfeat[j][: self._nfeat]
+                    infos[i] = info
             self._ep_ret[idx] = 0
             self._ep_len[idx] = 0
         return self._obs_dict(), rew, done, infos
