@@ -146,6 +146,14 @@ typedef struct {
      * tip hull <-> cube and cube <-> table.  draws per reset: init_obj_ang, obj_mass, OpenSimplex seed | trajectory angle */
     int32_t push_mode, push_traj_straight, push_sparse_reward;
     int32_t push_shape;              /* 0: cube vs tip hull (object_push); 1: sphere vs cylinder cap (object_roll) */
+    /* reward_mode "sparse" of edge_follow (1 at the goal else 0, edge_follow_env.py:430-438), object_balance (-1 once fallen else
+     * 0, object_balance_env.py:508-518) and surface_follow (the dense reward accumulated over the episode, reset included, paid
+     * out at the goal, surface_follow_auto_env.py:59-73 / surface_follow_goal_env.py:53-67); object_push / object_roll keep
+     * push_sparse_reward */
+    int32_t sparse_reward;
+    int32_t surf_mode;               /* heights: 0 simplex 2-d (xyz, xyzRxRy), 1 simplex 1-d along y (yz, yzRx; :339-357), 2 flat (noise_mode "none") */
+    int32_t surf_dir_mode;           /* goal direction: 0 (cos, sin) of the drawn angle; 1 (0, +-1) = the drawn choice([-1, 1]) (:512-514) */
+    int32_t pad_modes;
     double push_half[3];             /* cube half extents (cube.urdf) */
     double push_table_z;             /* table top (base_tactile_env.py:135-139 + table.urdf) */
     double push_mu_table, push_mu_tip; /* products of the lateralFriction pairs (object_push_env.py:218, :61-66, table.urdf) */

@@ -305,7 +305,8 @@ class EdgeFollowOracle:
     (rl_envs/base_tactile_env.py:166-185) on top of the C oracle.  One env instance."""
 
     def __init__(self, image_size=128, arm="ur5", sensor="tactip", max_steps=200, movement_mode="xy",
-                 noise_mode="rand_height", seed=None):
+                 noise_mode="rand_height", seed=None, reward_mode="dense"):
+        self.reward_mode = reward_mode
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
         self.max_steps, self.movement_mode, self.noise_mode = max_steps, movement_mode, noise_mode
         lims = np.zeros((6, 2))
@@ -379,6 +380,8 @@ class EdgeFollowOracle:
         a_, b_ = p2 - p1, p1 - p[:2]
         edge_dist = np.abs(a_[0] * b_[1] - a_[1] * b_[0]) / np.linalg.norm(p2 - p1)
         done = bool(goal_dist < self.termination_dist or self.steps >= self.max_steps)
+        if self.reward_mode == "sparse":   # sparse_reward :430-438
+            return (1.0 if goal_dist < self.termination_dist else 0.0), done
         return -(1.0 * goal_dist + 10.0 * edge_dist), done
 
     def oracle_obs(self):   # get_oracle_obs, edge_follow_env.py:454-476
@@ -501,7 +504,8 @@ class ObjectBalanceOracle:
         init_deg = self.init_rpy * 180 / np.pi
         rpy_dist = np.abs(((rpy_deg - init_deg) + 180) % 360 - 180)
         fall = bool(rpy_dist[0] > 35 or rpy_dist[1] > 35 or np.linalg.norm(np.array(self.o.pos[:]) - self.init_obj_pos) > 0.1)
-        return 1.0, bool(fall or self.steps >= self.max_steps)
+        reward = (-1.0 if fall else 0.0) if getattr(self, "reward_mode", "dense") == "sparse" else 1.0   # :508-526
+        return reward, bool(fall or self.steps >= self.max_steps)
 
     def oracle_obs(self):   # get_oracle_obs, object_balance_env.py:528-563
         pos, _, orn, lin, ang = tcp_state_workframe(self.m, self.s)
@@ -567,11 +571,14 @@ class SurfaceFollowOracle:
     "xyz" / "xyzRxRy".  One env instance.  The tip core <-> table contact (only reachable in the deepest valleys,
     SURVEY.md 8a R5) is not modelled."""
 
-    def __init__(self, image_size=128, arm="ur5", sensor="digit", max_steps=200, movement_mode="xyzRxRy", seed=None, variant="auto"):
+    def __init__(self, image_size=128, arm="ur5", sensor="digit", max_steps=200, movement_mode="xyzRxRy", seed=None, variant="auto",
+                 noise_mode="simplex", reward_mode="dense", render=True):
         """variant "auto": SurfaceFollowAutoEnv (surface_follow-v0); "goal": SurfaceFollowGoalEnv (surface_follow-v1,
         surface_follow_goal/surface_follow_goal_env.py: the policy steers x / y, the reward adds the goal distance)"""
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
         self.max_steps, self.movement_mode, self.variant = max_steps, movement_mode, variant
+        self.noise_mode, self.reward_mode, self.render = noise_mode, reward_mode, render
+        self.one_d = movement_mode in ("yz", "yzRx")
         self.grid, self.hrange, self.rows, self.cols, self.interp, self.extent = 0.006, 0.025, 64, 64, 0.05, 0.15
         wd = [0.33, 0.0, 0.0] if arm == "mg400" else [0.65, 0.0, 0.0]                  # base_surface_env.py:54-57
         self.embed_dist = {"tactip": 0.0025, "digitac": 0.0015, "digit": 0.0015}[sensor]  # :67-75
@@ -599,8 +606,8 @@ class SurfaceFollowOracle:
 
     def draw(self):
         """reset_task order (:539-547): update_surface's randint(1e8) (:448), then make_goal's uniform(-pi, pi) (:508)"""
-        seed_int = self.np_random.randint(1e8)
-        ang = self.np_random.uniform(-np.pi, np.pi)
+        seed_int = self.np_random.randint(1e8) if self.noise_mode == "simplex" else 0      # :436-458
+        ang = float(self.np_random.choice([-1, 1])) if self.one_d else self.np_random.uniform(-np.pi, np.pi)   # :512-520
         return float(seed_int), ang
 
     def xy_to_surface_idx(self, x, y):   # :273-288
@@ -612,7 +619,14 @@ class SurfaceFollowOracle:
     def reset(self, draws=None):
         self.steps = 0
         seed_int, ang = self.draw() if draws is None else draws
-        self.h = surface_heights(int(seed_int), self.rows, self.cols, self.interp, self.hrange)
+        if self.noise_mode == "none":                                                  # :436-437
+            self.h = np.zeros((self.rows, self.cols))
+        elif self.one_d:                                                                # gen_heigtfield_simplex_1d :339-357
+            row = np.array([opensimplex_noise2(int(seed_int), 1 * self.interp, y * self.interp) * self.hrange for y in range(self.cols)])
+            self.h = np.tile(row, (self.rows, 1))
+        else:
+            self.h = surface_heights(int(seed_int), self.rows, self.cols, self.interp, self.hrange)
+        self.accum_rew = 0.0                                                           # reset_task :590-591
         # update_surface :480-499: surface_array / normals
         X, Y = np.meshgrid(self.x_bins, self.y_bins)
         self.surface_array = np.dstack((X, Y, self.h + self.surface_pos[2]))
@@ -621,7 +635,7 @@ class SurfaceFollowOracle:
         self.surface_normals = nrm / np.linalg.norm(nrm, axis=2)[..., None]
         self.V = heightfield_local_vertices(self.h, self.grid) + self.surface_pos
         # make_goal :501-537
-        self.dirs = np.array([np.cos(ang), np.sin(ang), 0.0])
+        self.dirs = np.array([0.0, ang, 0.0]) if self.one_d else np.array([np.cos(ang), np.sin(ang), 0.0])
         wdir = self.Rw @ self.dirs
         g = [self.surface_pos[0] + self.extent * wdir[0], self.surface_pos[1] + self.extent * wdir[1]]
         gi, gj = self.xy_to_surface_idx(g[0], g[1])
@@ -632,7 +646,7 @@ class SurfaceFollowOracle:
         pos = self.Rw.T @ (init_world - self.workframe_pos); rpy = np.zeros(3)
         self.last_reset_substeps = lib().or_robot_reset(C.byref(self.m), C.byref(self.s), _dptr(self.rest), _dptr(np.ascontiguousarray(pos)), _dptr(rpy))
         self.reward, self.done = self.step_data()
-        return self.observation()
+        return self.observation() if self.render else None
 
     def tcp_world(self):
         P, Q = link_states(self.m, np.array(self.s.q[: self.m.ndof]))
@@ -667,8 +681,13 @@ class SurfaceFollowOracle:
         w_norm = 0.0 if self.movement_mode in ("yz", "xyz") else 1.0
         if self.variant == "goal":   # surface_follow_goal_env.py:62-81
             goal_xy = np.linalg.norm(p[:2] - self.goal_pos[:2])
-            return -(1.0 * goal_xy + 10.0 * surf_dist + w_norm * cos_dist), done
-        return -(1.0 * surf_dist + w_norm * cos_dist), done
+            dense = -(1.0 * goal_xy + 10.0 * surf_dist + w_norm * cos_dist)
+        else:
+            dense = -(1.0 * surf_dist + w_norm * cos_dist)
+        if self.reward_mode == "sparse":   # sparse_reward (surface_follow_auto_env.py:59-73, surface_follow_goal_env.py:53-67)
+            self.accum_rew += dense
+            return (self.accum_rew if np.linalg.norm(p - self.goal_pos) < self.termination_dist else 0.0), done
+        return dense, done
 
     def oracle_obs(self):   # get_oracle_obs, base_surface_env.py:789-819 (tip_i / tip_j from the last get_step_data)
         pos, _, orn, lin, ang = tcp_state_workframe(self.m, self.s)
@@ -685,13 +704,10 @@ class SurfaceFollowOracle:
         enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
         k = {"tactip": 1.0, "digitac": 0.9, "digit": 0.7}[self.sensor]
         if self.variant == "goal":   # surface_follow_goal_env.py:27-52
-            enc[: len(a)] = a
+            enc[{"yz": [1, 2], "xyz": [0, 1, 2], "yzRx": [1, 2, 3], "xyzRxRy": [0, 1, 2, 3, 4]}[self.movement_mode]] = a
         else:
             enc[0] = self.dirs[0] * 0.25 * k; enc[1] = self.dirs[1] * 0.25 * k
-            if self.movement_mode == "xyz":
-                enc[2] = a[0]
-            else:
-                enc[2], enc[3], enc[4] = a[0], a[1], a[2]
+            enc[{"yz": [2], "xyz": [2], "yzRx": [2, 3], "xyzRxRy": [2, 3, 4]}[self.movement_mode]] = a
         enc = np.clip(enc, -0.25, 0.25)
         mv, ma = 0.01, 5.0 * (np.pi / 180)
         amax = np.array([mv, mv, mv, ma, ma, 0.0]); amin = -amax
@@ -702,7 +718,7 @@ class SurfaceFollowOracle:
         self.steps += 1
         lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
         self.reward, self.done = self.step_data()
-        return self.observation(), self.reward, self.done, {}
+        return (self.observation() if self.render else None), self.reward, self.done, {}
 
 
 # ---------------------------------------------------------------- object_push task restatement

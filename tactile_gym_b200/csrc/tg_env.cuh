@@ -65,6 +65,7 @@ struct EnvBuffers {
     // surface_follow: heightfields [N][2][64*64] (one live, one being / been built for the next episode), hf_cur [N] = the
     // live one, hf_meta [N][2][SURF_META]; partial resets: noise permutation [N][256], next grid point [N], float min/max [N][2]
     double *height, *hf_meta;
+    double* accum;           // [N] surface_follow, reward_mode "sparse": the episode's accumulated dense reward (accum_rew)
     int* hf_cur;
     unsigned char* sb_perm;
     int* sb_surf_it;
@@ -148,7 +149,7 @@ TGD void balance_step_data(const TgTask& task, const ObjState& o, double embed, 
     const double ip[3] = {task.workframe_pos[0], task.workframe_pos[1], task.workframe_pos[2] + task.obj_base_h * 0.5 - embed};
     const double dx = o.pos[0] - ip[0], dy = o.pos[1] - ip[1], dz = o.pos[2] - ip[2];
     if (sqrt(dx * dx + dy * dy + dz * dz) > task.obj_term_pos) fall = true;
-    *reward = 1.0f;
+    *reward = task.sparse_reward ? (fall ? -1.0f : 0.0f) : 1.0f; // sparse_reward (:508-518) / dense_reward (:520-526)
     *done = (fall || steps >= task.max_steps) ? 1 : 0;
 }
 
@@ -194,6 +195,7 @@ TGD void edge_step_data(const TgTask& task, const double* tcp_pos, double edge_a
     const double fx = p1x - tcp_pos[0], fy = p1y - tcp_pos[1];
     const double edge_dist = fabs(ex * fy - ey * fx) / sqrt(ex * ex + ey * ey);
     *reward = (float)(-((1.0 * goal_dist) + (10.0 * edge_dist) + (1.0 * 0.0)));
+    if (task.sparse_reward) *reward = goal_dist < task.termination_dist ? 1.0f : 0.0f; // sparse_reward (:430-438)
     *done = (goal_dist < task.termination_dist || steps >= task.max_steps) ? 1 : 0;
 }
 
@@ -328,7 +330,9 @@ __device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph
             const int end = min(r.surf_it + b.surf_chunk, SURF_PTS);
 #pragma unroll 1
             for (int k = r.surf_it; k < end; k++) {
-                const double h = os_noise2(perm, (double)(k / SURF_N) * task.surf_interp, (double)(k % SURF_N) * task.surf_interp) * task.surf_range;
+                // surf_mode 1: gen_heigtfield_simplex_1d (:339-357), noise along y only; 2: noise_mode "none" (:436-437)
+                const double nx = task.surf_mode == 1 ? 1.0 * task.surf_interp : (double)(k / SURF_N) * task.surf_interp;
+                const double h = task.surf_mode == 2 ? 0.0 : os_noise2(perm, nx, (double)(k % SURF_N) * task.surf_interp) * task.surf_range;
                 H[k] = h;
                 r.hmin = fminf(r.hmin, (float)h); r.hmax = fmaxf(r.hmax, (float)h);
             }
@@ -410,7 +414,8 @@ __device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, 
         double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)sbuf) * SURF_META;
         double sn, cs, wq[4], R[9];
         sincos(r.edge_ang, &sn, &cs);
-        const double dirs[3] = {cs, sn, 0.0};
+        // yz / yzRx: workframe_directions = (0, choice([-1, 1]), 0) (:512-514), the draw itself
+        const double dirs[3] = {task.surf_dir_mode ? 0.0 : cs, task.surf_dir_mode ? r.edge_ang : sn, 0.0};
         double wd[3];
         quat_from_euler(task.workframe_rpy, wq);
         mat_from_quat(wq, R);
@@ -607,6 +612,16 @@ TGD void roll_features(const double* traj, float* out)
     out[0] = (float)traj[0]; out[1] = (float)traj[1]; out[2] = 0.0f;
 #pragma unroll
     for (int i = 3; i < TG_PUSH_NFEAT; i++) out[i] = 0.0f;
+}
+
+// surface_follow, reward_mode "sparse": reset() runs get_step_data once (base_surface_env.py:638), so the episode's accumulator
+// starts at the dense reward of the start pose (reset_task zeroes it just before, :590-591)
+TGD void surface_accum_start(const TgTask& task, const EnvBuffers& b, int e)
+{
+    const size_t hb = (size_t)e * 2 + (size_t)b.hf_cur[e];
+    float r; unsigned char d; double dense;
+    surface_step_data(task, b.height + hb * SURF_PTS, b.hf_meta + hb * SURF_META, b.tcp + (size_t)e * 7, b.tcp + (size_t)e * 7 + 3, 0, &r, &d, &dense);
+    b.accum[e] = dense;
 }
 
 // object_push / object_roll: the extended feature of env e's live state (after a reset / standby swap)
@@ -942,7 +957,16 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         obj_stim(task, ob, b.stim + (size_t)e * 12); // the pole moves: the raster needs its pose every step
     } else if (surface) {
         const size_t hb = (size_t)e * 2 + (size_t)b.hf_cur[e];
-        surface_step_data(task, b.height + hb * SURF_PTS, b.hf_meta + hb * SURF_META, tp, tq, steps, &r, &d);
+        double dense;
+        surface_step_data(task, b.height + hb * SURF_PTS, b.hf_meta + hb * SURF_META, tp, tq, steps, &r, &d, &dense);
+        if (task.sparse_reward) {
+            // sparse_reward (surface_follow_auto_env.py:59-73): accum_rew += dense; paid out inside termination_dist of the goal
+            const double acc = b.accum[e] + dense;
+            b.accum[e] = acc;
+            const double* meta = b.hf_meta + hb * SURF_META;
+            const double gx = tp[0] - meta[3], gy = tp[1] - meta[4], gz = tp[2] - meta[5];
+            r = sqrt(gx * gx + gy * gy + gz * gz) < task.termination_dist ? (float)acc : 0.0f;
+        }
         float* f = (d && autoreset && b.pipeline) ? b.term_feat : b.feat;
         if (f) surface_features(task, b.hf_meta + hb * SURF_META, tp, tq, f + (size_t)e * TG_PUSH_NFEAT);
     } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
@@ -958,6 +982,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int c = 0; c < 12; c++) b.term_stim[(size_t)e * 12 + c] = b.stim[(size_t)e * 12 + c];
         acquire_standby<T>(arm, ph, task, b, e);
         write_live_features(task, b, e);
+        if (surface && task.sparse_reward) surface_accum_start(task, b, e);
         if (b.oracle) oracle_obs_env<T>(arm, task, b, e, b.oracle + (size_t)e * TG_ORACLE_NOBS);
     } else {
         write_camera<T>(arm, k, b.cam + (size_t)e * 12);
@@ -990,6 +1015,7 @@ reset_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysic
         store_live<T::NB>(b, e, s);
     }
     write_live_features(task, b, e);
+    if (task.task == TG_TASK_SURFACE_FOLLOW && task.sparse_reward) surface_accum_start(task, b, e);
     if (b.oracle) oracle_obs_env<T>(arm, task, b, e, b.oracle + (size_t)e * TG_ORACLE_NOBS);
 }
 

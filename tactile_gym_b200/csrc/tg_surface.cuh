@@ -122,7 +122,7 @@ TGD void surf_gradient(const double* H, double grid, int i, int j, double& d_axi
 
 // reward / termination.  H: the live heightfield [64][64] (row = y index), meta: zc, dir, goal
 TGD void surface_step_data(const TgTask& task, const double* H, const double* meta, const double* tp, const double* tq, int steps,
-                           float* reward, unsigned char* done)
+                           float* reward, unsigned char* done, double* dense = nullptr)
 {
     int ti, tj;
     surf_index(task, tp[0], tp[1], ti, tj);
@@ -144,7 +144,9 @@ TGD void surface_step_data(const TgTask& task, const double* H, const double* me
     const double cs = (n[0] * v[0] + n[1] * v[1] + n[2] * v[2]) / (sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
     // SurfaceFollowAutoEnv.dense_reward (W_goal = 0, W_surf = 1) / SurfaceFollowGoalEnv.dense_reward (W_goal = 1, W_surf = 10)
     const double goal_xy = sqrt(gx * gx + gy * gy);
-    *reward = (float)(-((task.surf_w_goal * goal_xy) + (task.surf_w_surf * surf_dist) + (task.surf_w_norm * (1.0 - cs))));
+    const double rw = -((task.surf_w_goal * goal_xy) + (task.surf_w_surf * surf_dist) + (task.surf_w_norm * (1.0 - cs)));
+    if (dense) *dense = rw;
+    *reward = (float)rw;
     *done = (goal_dist < task.termination_dist || steps >= task.max_steps) ? 1 : 0;
 }
 

@@ -189,7 +189,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         if (!b.pipeline) { tg_destroy(w); return fail(TG_EINVAL, "surface_follow needs max_steps >= 2"); }
         if ((rc = dalloc(w, &b.height, (size_t)2 * SURF_PTS * n)) || (rc = dalloc(w, &b.hf_meta, (size_t)2 * SURF_META * n)) ||
             (rc = dalloc(w, &b.hf_cur, n)) || (rc = dalloc(w, &b.sb_perm, (size_t)256 * n)) || (rc = dalloc(w, &b.sb_surf_it, n)) ||
-            (rc = dalloc(w, &b.sb_hmm, (size_t)2 * n))) {
+            (rc = dalloc(w, &b.sb_hmm, (size_t)2 * n)) || (rc = dalloc(w, &b.accum, n))) {
             tg_destroy(w);
             return rc;
         }

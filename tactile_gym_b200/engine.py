@@ -16,6 +16,14 @@ DRAW_ROUNDS = 64        # resets per env covered by one upload
 DRAW_CHECK_EVERY = 32   # steps between (synchronising) checks of how many draws were consumed
 
 
+def _sparse_flag(env_modes):
+    """reward_mode -> TgTask.sparse_reward; anything but 'dense' / 'sparse' is the reference's sys.exit (ValueError here)"""
+    mode = env_modes.get("reward_mode", "dense")
+    if mode not in ("dense", "sparse"):
+        raise ValueError("Incorrect reward_mode specified: {}".format(mode))
+    return 1 if mode == "sparse" else 0
+
+
 def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
     """EdgeFollowEnv.__init__ (rl_envs/exploration/edge_follow/edge_follow_env.py:23-134) as a TgConfig.
     Returns (cfg, keepalive) - keepalive holds the numpy arrays the config points into."""
@@ -45,6 +53,7 @@ def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
 
     t = cfg.task
     t.task = L.TG_TASK_EDGE_FOLLOW
+    t.sparse_reward = _sparse_flag(env_modes)                                                 # edge_follow_env.py:430-438
     t.max_steps = int(max_steps)
     idx = {"xy": [0, 1], "xyz": [0, 1, 2], "xyRz": [0, 1, 5], "xyzRz": [0, 1, 2, 5]}[movement_mode]
     t.act_dim = len(idx)
@@ -171,6 +180,7 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 20.0) / (1.0 / 240.0))))   # :33-35 -> 12
     t = cfg.task
     t.task, t.max_steps = L.TG_TASK_OBJECT_BALANCE, int(max_steps)
+    t.sparse_reward = _sparse_flag(env_modes)                                                 # object_balance_env.py:508-518
     idx = {"xy": [0, 1], "xyz": [0, 1, 2], "RxRy": [3, 4], "xyRxRy": [0, 1, 3, 4]}[env_modes["movement_mode"]]   # :416-442
     t.act_dim = len(idx)
     for k in range(6):
@@ -217,16 +227,17 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     return cfg, (dep, gray, mask, tris, rest, prims, prim_nv), draw
 
 
-def surface_follow_draws():
+def surface_follow_draws(noise_mode="simplex", one_d=False):
     """BaseSurfaceEnv.reset_task draws (base_surface_env.py:539-547): update_surface's `np_random.randint(1e8)` (the
-    OpenSimplex seed, :448) then make_goal's `uniform(-pi, pi)` (:508).  randint's rejection sampling consumes a
-    variable number of raw outputs, so the legacy RandomState calls themselves are used."""
+    OpenSimplex seed, :448; not drawn for noise_mode "none") then make_goal's `uniform(-pi, pi)` (:508) or, for the yz / yzRx
+    movement modes, `choice([-1, 1])` (:513).  randint's rejection sampling consumes a variable number of raw outputs, so the
+    legacy RandomState calls themselves are used."""
 
     def draw(rng, rounds):
         out = np.empty((rounds, 2))
         for r in range(rounds):
-            out[r, 0] = rng.randint(1e8)
-            out[r, 1] = rng.uniform(-np.pi, np.pi)
+            out[r, 0] = rng.randint(1e8) if noise_mode == "simplex" else 0
+            out[r, 1] = rng.choice([-1, 1]) if one_d else rng.uniform(-np.pi, np.pi)
         return out
 
     return draw
@@ -243,10 +254,14 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     BaseSurfaceEnv.__init__ (rl_envs/exploration/surface_follow/base_surface_env.py:14-150) as a TgConfig.
     Returns (cfg, keepalive, draw_fn)."""
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
-    if env_modes.get("noise_mode", "simplex") != "simplex":
-        raise NotImplementedError("noise_mode %r: only 'simplex' is built" % env_modes.get("noise_mode"))
-    if env_modes["movement_mode"] not in ("xyz", "xyzRxRy"):
-        raise NotImplementedError("movement_mode %r: only 'xyz' and 'xyzRxRy' (2-d simplex surfaces) are built" % env_modes["movement_mode"])
+    noise_mode, movement_mode = env_modes.get("noise_mode", "simplex"), env_modes["movement_mode"]
+    if noise_mode == "random":
+        raise NotImplementedError("noise_mode 'random' (1,024 uniform draws per reset, base_surface_env.py:290-309) is not built")
+    if noise_mode not in ("simplex", "none"):
+        raise ValueError("Incorrect noise mode specified")                                       # :461, :463 (vertical_simplex: surface_follow-v2)
+    if movement_mode not in ("yz", "xyz", "yzRx", "xyzRxRy"):
+        raise ValueError("Incorrect movement mode specified: %r" % movement_mode)
+    one_d = movement_mode in ("yz", "yzRx")
     if env_modes["control_mode"] != "TCP_velocity_control":
         raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
     typ, S = "standard", int(image_size[0])
@@ -260,9 +275,14 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     t = cfg.task
     t.task, t.max_steps = L.TG_TASK_SURFACE_FOLLOW, int(max_steps)
     if variant == "goal":
-        idx = {"xyz": [0, 1, 2], "xyzRxRy": [0, 1, 2, 3, 4]}[env_modes["movement_mode"]]          # surface_follow_goal_env.py:27-52
+        idx = {"yz": [1, 2], "xyz": [0, 1, 2], "yzRx": [1, 2, 3], "xyzRxRy": [0, 1, 2, 3, 4]}[movement_mode]   # surface_follow_goal_env.py:27-52
     else:
-        idx = {"xyz": [2], "xyzRxRy": [2, 3, 4]}[env_modes["movement_mode"]]                      # surface_follow_auto_env.py:45-55
+        idx = {"yz": [2], "xyz": [2], "yzRx": [2, 3], "xyzRxRy": [2, 3, 4]}[movement_mode]        # surface_follow_auto_env.py:45-55
+    t.sparse_reward = _sparse_flag(env_modes)                                                    # surface_follow_auto_env.py:59-73
+    # heights (update_surface :434-463): 2-d simplex for xyz / xyzRxRy, 1-d (along y) for yz / yzRx, flat for "none";
+    # goal direction (make_goal :501-520): an angle, or choice([-1, 1]) along y
+    t.surf_mode = 2 if noise_mode == "none" else (1 if one_d else 0)
+    t.surf_dir_mode = 1 if one_d else 0
     t.act_dim = len(idx)
     for k in range(6):
         t.act_index[k] = idx[k] if k < len(idx) else -1
@@ -284,7 +304,7 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     t.surf_grid, t.surf_range, t.surf_interp, t.surf_extent = 0.006, hrange, 0.05, extent
     t.surf_embed = {"tactip": 0.0025, "digitac": 0.0015, "digit": 0.0015}[sensor]                 # :67-75
     t.surf_drive = 0.25 * {"tactip": 1.0, "digitac": 0.9, "digit": 0.7}[sensor]                   # surface_follow_auto_env.py:35-43
-    t.surf_w_norm = 0.0 if env_modes["movement_mode"] == "xyz" else 1.0                           # :88-89
+    t.surf_w_norm = 0.0 if movement_mode in ("yz", "xyz") else 1.0                                # :88-89
     t.surf_w_goal, t.surf_w_surf = 0.0, 1.0                                                      # :79-80, :92
     if variant == "goal":                                                                        # surface_follow_goal_env.py:62-81
         t.surf_drive, t.surf_w_goal, t.surf_w_surf = 0.0, 1.0, 10.0
@@ -300,7 +320,7 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
     s.n_prim = 0                                                                                 # the stimulus is the per-env heightfield
     cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
-    return cfg, (dep, gray, mask, rest), surface_follow_draws()
+    return cfg, (dep, gray, mask, rest), surface_follow_draws(noise_mode, one_d)
 
 
 def object_push_draws(rand_init_orn, rand_obj_mass, traj_type, default_mass):

@@ -21,8 +21,8 @@ class EdgeFollowEnv(BaseTactileEnv):
         self.noise_mode = env_modes["noise_mode"]
         self.observation_mode = env_modes["observation_mode"]
         self.reward_mode = env_modes["reward_mode"]
-        if self.reward_mode != "dense":
-            raise NotImplementedError("reward_mode %r: only 'dense' is built" % self.reward_mode)
+        if self.reward_mode not in ("dense", "sparse"):
+            raise ValueError("Incorrect reward_mode specified: {}".format(self.reward_mode))
         self.t_s_name = env_modes["tactile_sensor_name"]
         cfg, keep = edge_follow_config(env_modes, image_size, max_steps, n_envs=1)
         self.world = TactileWorld(cfg, keep, device=device)
