@@ -578,7 +578,7 @@ class SurfaceFollowOracle:
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
         self.max_steps, self.movement_mode, self.variant = max_steps, movement_mode, variant
         self.noise_mode, self.reward_mode, self.render = noise_mode, reward_mode, render
-        self.one_d = movement_mode in ("yz", "yzRx")
+        self.one_d = movement_mode in ("yz", "yzRx", "xRz")
         self.grid, self.hrange, self.rows, self.cols, self.interp, self.extent = 0.006, 0.025, 64, 64, 0.05, 0.15
         wd = [0.33, 0.0, 0.0] if arm == "mg400" else [0.65, 0.0, 0.0]                  # base_surface_env.py:54-57
         self.embed_dist = {"tactip": 0.0025, "digitac": 0.0015, "digit": 0.0015}[sensor]  # :67-75
@@ -619,7 +619,7 @@ class SurfaceFollowOracle:
     def reset(self, draws=None):
         self.steps = 0
         seed_int, ang = self.draw() if draws is None else draws
-        if self.noise_mode == "none":                                                  # :436-437
+        if self.noise_mode == "none" or self.movement_mode == "xRz":                   # :436-437; "xRz" is in neither list of :450-455
             self.h = np.zeros((self.rows, self.cols))
         elif self.one_d:                                                                # gen_heigtfield_simplex_1d :339-357
             row = np.array([opensimplex_noise2(int(seed_int), 1 * self.interp, y * self.interp) * self.hrange for y in range(self.cols)])
@@ -679,7 +679,9 @@ class SurfaceFollowOracle:
         v = R @ np.array([0.0, 0.0, -1.0])
         cos_dist = 1 - np.dot(n, v) / (np.linalg.norm(n) * np.linalg.norm(v))
         w_norm = 0.0 if self.movement_mode in ("yz", "xyz") else 1.0
-        if self.variant == "goal":   # surface_follow_goal_env.py:62-81
+        if self.variant == "vert":   # surface_follow_vert_env.py:63-79
+            dense = -(10.0 * surf_dist + 3.0 * cos_dist)
+        elif self.variant == "goal":   # surface_follow_goal_env.py:62-81
             goal_xy = np.linalg.norm(p[:2] - self.goal_pos[:2])
             dense = -(1.0 * goal_xy + 10.0 * surf_dist + w_norm * cos_dist)
         else:
@@ -703,7 +705,10 @@ class SurfaceFollowOracle:
     def encode_scale(self, action):   # surface_follow_auto_env.py:27-57, base_tactile_env.py:141-164
         enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
         k = {"tactip": 1.0, "digitac": 0.9, "digit": 0.7}[self.sensor]
-        if self.variant == "goal":   # surface_follow_goal_env.py:27-52
+        if self.variant == "vert":   # surface_follow_vert_env.py:30-45
+            enc[1] = self.dirs[1] * 0.25 * k
+            enc[0], enc[5] = a[0], a[1]
+        elif self.variant == "goal":   # surface_follow_goal_env.py:27-52
             enc[{"yz": [1, 2], "xyz": [0, 1, 2], "yzRx": [1, 2, 3], "xyzRxRy": [0, 1, 2, 3, 4]}[self.movement_mode]] = a
         else:
             enc[0] = self.dirs[0] * 0.25 * k; enc[1] = self.dirs[1] * 0.25 * k

@@ -840,7 +840,8 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
             // SurfaceFollowAutoEnv.encode_actions (surface_follow_auto_env.py:27-57): constant drive towards the goal
             // (surface_follow-v1 has none: the policy's own x / y stay)
             const double* meta = b.hf_meta + ((size_t)e * 2 + (size_t)b.hf_cur[e]) * SURF_META;
-            enc[0] = meta[1] * task.surf_drive; enc[1] = meta[2] * task.surf_drive;
+            if (!task.surf_drive_y_only) enc[0] = meta[1] * task.surf_drive;   // -v2 (SurfaceFollowVertEnv): x is the policy's
+            enc[1] = meta[2] * task.surf_drive;
         }
         if (push && !roll) {
             // ObjectPushEnv.encode_actions (object_push_env.py:369-454)

@@ -249,6 +249,13 @@ def surface_follow_goal_config(env_modes, image_size, max_steps, n_envs, lanes_p
     return surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp, variant="goal")
 
 
+def surface_follow_vert_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
+    """surface_follow-v2: SurfaceFollowVertEnv (surface_follow_vert/surface_follow_vert_env.py) on the horizontal surfaces
+    (noise_mode 'simplex' - which leaves the surface flat for its 'xRz' movement mode, base_surface_env.py:443-452 - or 'none').
+    noise_mode 'vertical_simplex' (the `forward` sensor type on a vertical heightfield) is not built."""
+    return surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp, variant="vert")
+
+
 def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0, variant="auto"):
     """SurfaceFollowAutoEnv (variant "auto", surface_follow-v0) / SurfaceFollowGoalEnv (variant "goal", surface_follow-v1) on
     BaseSurfaceEnv.__init__ (rl_envs/exploration/surface_follow/base_surface_env.py:14-150) as a TgConfig.
@@ -257,11 +264,16 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     noise_mode, movement_mode = env_modes.get("noise_mode", "simplex"), env_modes["movement_mode"]
     if noise_mode == "random":
         raise NotImplementedError("noise_mode 'random' (1,024 uniform draws per reset, base_surface_env.py:290-309) is not built")
+    if noise_mode == "vertical_simplex":
+        raise NotImplementedError("noise_mode 'vertical_simplex' (vertical heightfield, `forward` sensor type, base_surface_env.py:60-63,83-107) is not built")
     if noise_mode not in ("simplex", "none"):
-        raise ValueError("Incorrect noise mode specified")                                       # :461, :463 (vertical_simplex: surface_follow-v2)
-    if movement_mode not in ("yz", "xyz", "yzRx", "xyzRxRy"):
+        raise ValueError("Incorrect noise mode specified")                                       # :461, :463
+    if variant == "vert":
+        if movement_mode != "xRz":
+            raise NotImplementedError("surface_follow-v2 encodes actions for movement_mode 'xRz' only (surface_follow_vert_env.py:43-45)")
+    elif movement_mode not in ("yz", "xyz", "yzRx", "xyzRxRy"):
         raise ValueError("Incorrect movement mode specified: %r" % movement_mode)
-    one_d = movement_mode in ("yz", "yzRx")
+    one_d = movement_mode in ("yz", "yzRx", "xRz")
     if env_modes["control_mode"] != "TCP_velocity_control":
         raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
     typ, S = "standard", int(image_size[0])
@@ -274,14 +286,17 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 10.0) / (1.0 / 240.0))))      # :26-28 -> 24
     t = cfg.task
     t.task, t.max_steps = L.TG_TASK_SURFACE_FOLLOW, int(max_steps)
-    if variant == "goal":
+    if variant == "vert":
+        idx = [0, 5]                                                                             # surface_follow_vert_env.py:43-45
+    elif variant == "goal":
         idx = {"yz": [1, 2], "xyz": [0, 1, 2], "yzRx": [1, 2, 3], "xyzRxRy": [0, 1, 2, 3, 4]}[movement_mode]   # surface_follow_goal_env.py:27-52
     else:
         idx = {"yz": [2], "xyz": [2], "yzRx": [2, 3], "xyzRxRy": [2, 3, 4]}[movement_mode]        # surface_follow_auto_env.py:45-55
     t.sparse_reward = _sparse_flag(env_modes)                                                    # surface_follow_auto_env.py:59-73
     # heights (update_surface :434-463): 2-d simplex for xyz / xyzRxRy, 1-d (along y) for yz / yzRx, flat for "none";
     # goal direction (make_goal :501-520): an angle, or choice([-1, 1]) along y
-    t.surf_mode = 2 if noise_mode == "none" else (1 if one_d else 0)
+    # ("xRz" is in neither of update_surface's lists, so -v2's simplex surface keeps its zeros: flat; the seed is still drawn)
+    t.surf_mode = 2 if noise_mode == "none" or movement_mode == "xRz" else (1 if one_d else 0)
     t.surf_dir_mode = 1 if one_d else 0
     t.act_dim = len(idx)
     for k in range(6):
@@ -308,6 +323,8 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     t.surf_w_goal, t.surf_w_surf = 0.0, 1.0                                                      # :79-80, :92
     if variant == "goal":                                                                        # surface_follow_goal_env.py:62-81
         t.surf_drive, t.surf_w_goal, t.surf_w_surf = 0.0, 1.0, 10.0
+    if variant == "vert":                                                                        # surface_follow_vert_env.py:63-79
+        t.surf_drive_y_only, t.surf_w_goal, t.surf_w_surf, t.surf_w_norm = 1, 0.0, 10.0, 3.0
     t.n_draws = 2
     t.draw_default[0], t.draw_default[1] = 0.0, 0.0
     dep, gray, mask = scene.load_refimg(sensor, typ, S)
@@ -559,8 +576,8 @@ class TactileWorld:
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
             self.feat = self.term_feat = None
             self.nfeat = {L.TG_TASK_OBJECT_PUSH: 12, L.TG_TASK_OBJECT_ROLL: 3}.get(cfg.task.task, 0)
-            if cfg.task.task == L.TG_TASK_SURFACE_FOLLOW and cfg.task.surf_w_goal != 0.0:
-                self.nfeat = 6                   # surface_follow-v1: TCP + goal position (surface_follow_goal_env.py:83-97)
+            if cfg.task.task == L.TG_TASK_SURFACE_FOLLOW and (cfg.task.surf_w_goal != 0.0 or cfg.task.surf_drive_y_only):
+                self.nfeat = 6                   # surface_follow-v1 / -v2: TCP + goal position (surface_follow_goal_env.py:83-97)
             if self.nfeat:
                 # extended_feature (object_push_env.py:611-629, object_roll_env.py:402-408), filled by every step / reset;
                 # the first `nfeat` columns are meaningful

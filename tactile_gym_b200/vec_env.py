@@ -11,7 +11,8 @@ import time
 import numpy as np
 
 from . import spaces
-from .engine import TactileWorld, edge_follow_config, object_balance_config, object_push_config, object_roll_config, surface_follow_config, surface_follow_goal_config
+from .engine import (TactileWorld, edge_follow_config, object_balance_config, object_push_config, object_roll_config, surface_follow_config,
+                     surface_follow_goal_config, surface_follow_vert_config)
 
 try:  # pragma: no cover
     from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
@@ -19,7 +20,7 @@ except Exception:  # noqa: BLE001
     _VecEnvBase = object
 
 CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": object_balance_config,
-                   "surface_follow-v0": surface_follow_config, "surface_follow-v1": surface_follow_goal_config, "object_push-v0": object_push_config, "object_roll-v0": object_roll_config}
+                   "surface_follow-v0": surface_follow_config, "surface_follow-v1": surface_follow_goal_config, "surface_follow-v2": surface_follow_vert_config, "object_push-v0": object_push_config, "object_roll-v0": object_roll_config}
 
 
 class TactileVecEnv(_VecEnvBase):
@@ -33,7 +34,7 @@ class TactileVecEnv(_VecEnvBase):
         if kw.get("show_gui") or kw.get("show_tactile"):
             raise ValueError("show_gui / show_tactile are not available in the batched engine")
         self.observation_mode = env_modes.get("observation_mode", "tactile")
-        if self.observation_mode not in ("oracle", "tactile") and not (self.observation_mode == "tactile_and_feature" and env_id in ("object_push-v0", "object_roll-v0", "surface_follow-v1")):
+        if self.observation_mode not in ("oracle", "tactile") and not (self.observation_mode == "tactile_and_feature" and env_id in ("object_push-v0", "object_roll-v0", "surface_follow-v1", "surface_follow-v2")):
             raise NotImplementedError("observation_mode %r is not built for %s" % (self.observation_mode, env_id))
         image_size = kw.get("image_size", [64, 64])
         max_steps = kw.get("max_steps", 250)

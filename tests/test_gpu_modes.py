@@ -103,18 +103,19 @@ def test_object_balance_sparse_reward(oracle):
 
 
 @pytest.mark.parametrize("env_id,movement,noise", [("surface_follow-v0", "xyzRxRy", "simplex"), ("surface_follow-v0", "yzRx", "simplex"),
-                                                   ("surface_follow-v1", "yz", "simplex"), ("surface_follow-v0", "xyz", "none")])
+                                                   ("surface_follow-v1", "yz", "simplex"), ("surface_follow-v0", "xyz", "none"),
+                                                   ("surface_follow-v2", "xRz", "simplex")])
 def test_surface_follow_modes_and_sparse_reward(oracle, env_id, movement, noise):
     """1-d / flat surfaces and the (0, +-1) goal direction show in the reset pose, the goal and the per-step reward terms; the
     sparse reward is 0 on the way and the accumulated dense reward (reset's own get_step_data included) at the goal"""
     import tactile_gym_b200 as tg
 
     n = 4
-    variant = "goal" if env_id.endswith("v1") else "auto"
+    variant = {"v0": "auto", "v1": "goal", "v2": "vert"}[env_id[-2:]]
     modes = dict(BASE, movement_mode=movement, noise_mode=noise)
     env = tg.make_vec(env_id, n, env_kwargs={"env_modes": modes, "image_size": [64, 64], "max_steps": 400})
     rng = np.random.RandomState(len(movement) + len(noise))
-    one_d = movement in ("yz", "yzRx")
+    one_d = movement in ("yz", "yzRx", "xRz")
     second = rng.choice([-1.0, 1.0], (n, 2)) if one_d else rng.uniform(-np.pi, np.pi, (n, 2))
     first = rng.randint(0, 10 ** 8, (n, 2)).astype(np.float64) if noise == "simplex" else np.zeros((n, 2))
     draws = np.stack([first, second], axis=2)
@@ -129,7 +130,7 @@ def test_surface_follow_modes_and_sparse_reward(oracle, env_id, movement, noise)
         refs.append(r)
         assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=2e-6), i          # start pose = centre height of the new surface
         assert st[i, 22] == r.last_reset_substeps
-        if noise == "none":
+        if noise == "none" or movement == "xRz":
             assert np.all(r.h == 0)
         elif one_d:
             assert np.ptp(r.h, axis=0).max() == 0 and np.ptp(r.h) > 1e-3          # constant along x, varying along y
@@ -137,12 +138,15 @@ def test_surface_follow_modes_and_sparse_reward(oracle, env_id, movement, noise)
         assert np.allclose(obs[i], r.oracle_obs(), atol=2e-5), (i, np.abs(obs[i] - r.oracle_obs()).max())
     act_dim = env.world.act_dim
     paid = np.zeros(n, bool)
-    zi = {"auto": 0, "goal": 1 if one_d else 2}[variant]      # which policy action is z
+    zi = {"auto": 0, "goal": 1 if one_d else 2, "vert": None}[variant]      # which policy action is z (-v2 has none)
     for k in range(330):
         # steer: z towards the goal's height (oracle obs: tcp pos [0:3], goal pos [13:16], work frame); v1 also steers x / y
         act = np.zeros((n, act_dim), np.float32)
         dz = obs[:, 15] - obs[:, 2]
-        act[:, zi] = np.clip(250.0 * dz * 0.1, -0.25, 0.25)
+        if zi is not None:
+            act[:, zi] = np.clip(250.0 * dz * 0.1, -0.25, 0.25)
+        else:
+            act[:, 0] = np.clip(25.0 * (obs[:, 13] - obs[:, 0]), -0.25, 0.25)      # -v2: keep x on the goal's, Rz has no range
         if variant == "goal":
             d = obs[:, 13:15] - obs[:, 0:2]
             a = 0.25 * d / np.maximum(np.abs(d).max(axis=1, keepdims=True), 1e-9)

@@ -55,12 +55,42 @@ def test_registry_ids():
     import tactile_gym_b200 as tg
 
     # the reference's ids (tactile_gym/rl_envs/__init__.py:3-41)
-    for env_id in ("edge_follow-v0", "surface_follow-v0", "object_roll-v0", "object_push-v0", "object_balance-v0"):
+    for env_id in ("edge_follow-v0", "surface_follow-v0", "surface_follow-v1", "surface_follow-v2", "object_roll-v0", "object_push-v0", "object_balance-v0"):
         assert env_id in tg.REGISTRY
     with pytest.raises(KeyError):
         tg.make("no_such_env-v0")
     with pytest.raises(NotImplementedError):
-        tg.make("surface_follow-v2")
+        tg.make("edge_follow_aotu-v0")      # registered by the reference for a class that its sources do not define
+
+
+def test_surface_config_modes():
+    """host-side mapping of the surface_follow variants / modes to the task description (no GPU needed)"""
+    from tactile_gym_b200.engine import surface_follow_config, surface_follow_goal_config, surface_follow_vert_config
+
+    m = {"movement_mode": "xRz", "control_mode": "TCP_velocity_control", "noise_mode": "simplex", "observation_mode": "oracle",
+         "reward_mode": "sparse", "arm_type": "ur5", "tactile_sensor_name": "digit"}
+    cfg, _, draw = surface_follow_vert_config(m, [64, 64], 200, 2)
+    t = cfg.task
+    assert (t.act_dim, list(t.act_index[:2]), t.surf_mode, t.surf_dir_mode, t.surf_drive_y_only, t.sparse_reward) == (2, [0, 5], 2, 1, 1, 1)
+    assert (t.surf_w_goal, t.surf_w_surf, t.surf_w_norm) == (0.0, 10.0, 3.0) and abs(t.surf_drive - 0.25 * 0.7) < 1e-15
+    assert t.act_hi[5] == 0.0                      # horizontal surface: no yaw range (base_surface_env.py:197-206)
+    with pytest.raises(NotImplementedError):
+        surface_follow_vert_config(dict(m, noise_mode="vertical_simplex"), [64, 64], 200, 2)
+    cfg, _, _ = surface_follow_config(dict(m, movement_mode="yzRx", reward_mode="dense"), [64, 64], 200, 2)
+    assert (cfg.task.act_dim, cfg.task.surf_mode, cfg.task.surf_dir_mode, cfg.task.sparse_reward) == (2, 1, 1, 0)
+    cfg, _, _ = surface_follow_goal_config(dict(m, movement_mode="yz", noise_mode="none"), [64, 64], 200, 2)
+    assert (cfg.task.act_dim, list(cfg.task.act_index[:2]), cfg.task.surf_mode) == (2, [1, 2], 2)
+    with pytest.raises(NotImplementedError):
+        surface_follow_config(dict(m, movement_mode="xyz", noise_mode="random"), [64, 64], 200, 2)
+    with pytest.raises(ValueError):
+        surface_follow_config(dict(m, movement_mode="xyz", reward_mode="shaped"), [64, 64], 200, 2)
+    # draws follow the reference's RNG call order: randint(1e8) only for simplex, choice([-1, 1]) for the 1-d modes
+    from tactile_gym_b200 import seeding
+
+    a, b = seeding.np_random(7)[0], seeding.np_random(7)[0]
+    d = draw(a, 3)
+    for r in range(3):
+        assert d[r, 0] == b.randint(1e8) and d[r, 1] == b.choice([-1, 1])
 
 
 def test_seeding_matches_oracle_restatement(oracle):
