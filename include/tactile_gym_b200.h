@@ -154,6 +154,11 @@ typedef struct {
     int32_t surf_mode;               /* heights: 0 simplex 2-d (xyz, xyzRxRy), 1 simplex 1-d along y (yz, yzRx; :339-357), 2 flat (noise_mode "none") */
     int32_t surf_dir_mode;           /* goal direction: 0 (cos, sin) of the drawn angle; 1 (0, +-1) = the drawn choice([-1, 1]) (:512-514) */
     int32_t surf_drive_y_only;       /* 1: surface_follow-v2 drives along y only, x stays the policy's (surface_follow_vert_env.py:30-45) */
+    /* control_mode (robots/arms/robot.py:156-186): 0 TCP_velocity_control (Jacobian inverse, velocity motors, `substeps` steps);
+     * 1 TCP_position_control (base_robot_arm.py:228-279: the scaled action is a pose DELTA in the work frame, clipped to
+     * tcp_lims, IK from the current joints, position motors, then blocking_move(max_steps = pos_max_steps, robot.py:188-260):
+     * step until the pose error / joint speed test passes).  Built for the motor-only tasks (edge_follow, surface_follow), UR5. */
+    int32_t control_mode, pos_max_steps;
     double push_half[3];             /* cube half extents (cube.urdf) */
     double push_table_z;             /* table top (base_tactile_env.py:135-139 + table.urdf) */
     double push_mu_table, push_mu_tip; /* products of the lateralFriction pairs (object_push_env.py:218, :61-66, table.urdf) */

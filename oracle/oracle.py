@@ -305,8 +305,8 @@ class EdgeFollowOracle:
     (rl_envs/base_tactile_env.py:166-185) on top of the C oracle.  One env instance."""
 
     def __init__(self, image_size=128, arm="ur5", sensor="tactip", max_steps=200, movement_mode="xy",
-                 noise_mode="rand_height", seed=None, reward_mode="dense"):
-        self.reward_mode = reward_mode
+                 noise_mode="rand_height", seed=None, reward_mode="dense", control_mode="TCP_velocity_control"):
+        self.reward_mode, self.control_mode = reward_mode, control_mode
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
         self.max_steps, self.movement_mode, self.noise_mode = max_steps, movement_mode, noise_mode
         lims = np.zeros((6, 2))
@@ -396,13 +396,18 @@ class EdgeFollowOracle:
         enc[idx] = a
         enc = np.clip(enc, -0.25, 0.25)
         amax = np.array([self.max_pos_vel] * 3 + [0.0, 0.0, self.max_ang_vel])
+        if self.control_mode == "TCP_position_control":   # edge_follow_env.py:143-153
+            amax = np.array([0.001] * 3 + [0.0, 0.0, 1 * (np.pi / 180)])
         amin = -amax
         return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
 
     def step(self, action):
         v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
         self.steps += 1
-        lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
+        if self.control_mode == "TCP_position_control":   # robot.py:156-186, _max_blocking_pos_move_steps = 10 (edge_follow_env.py:38)
+            self.last_move_substeps = lib().or_tcp_position_control(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(10))
+        else:
+            lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
         self.reward, self.done = self.step_data()
         return self.observation(), self.reward, self.done, {}
 
@@ -572,7 +577,8 @@ class SurfaceFollowOracle:
     SURVEY.md 8a R5) is not modelled."""
 
     def __init__(self, image_size=128, arm="ur5", sensor="digit", max_steps=200, movement_mode="xyzRxRy", seed=None, variant="auto",
-                 noise_mode="simplex", reward_mode="dense", render=True):
+                 noise_mode="simplex", reward_mode="dense", render=True, control_mode="TCP_velocity_control"):
+        self.control_mode = control_mode
         """variant "auto": SurfaceFollowAutoEnv (surface_follow-v0); "goal": SurfaceFollowGoalEnv (surface_follow-v1,
         surface_follow_goal/surface_follow_goal_env.py: the policy steers x / y, the reward adds the goal distance)"""
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
@@ -715,13 +721,18 @@ class SurfaceFollowOracle:
             enc[{"yz": [2], "xyz": [2], "yzRx": [2, 3], "xyzRxRy": [2, 3, 4]}[self.movement_mode]] = a
         enc = np.clip(enc, -0.25, 0.25)
         mv, ma = 0.01, 5.0 * (np.pi / 180)
+        if self.control_mode == "TCP_position_control":   # base_surface_env.py:172-181
+            mv, ma = 0.001, 1 * (np.pi / 180)
         amax = np.array([mv, mv, mv, ma, ma, 0.0]); amin = -amax
         return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
 
     def step(self, action):
         v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
         self.steps += 1
-        lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
+        if self.control_mode == "TCP_position_control":   # robot.py:156-186, _max_blocking_pos_move_steps = 10 (base_surface_env.py:28)
+            self.last_move_substeps = lib().or_tcp_position_control(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(10))
+        else:
+            lib().or_apply_action(C.byref(self.m), C.byref(self.s), _dptr(v), C.c_int(self.repeat))
         self.reward, self.done = self.step_data()
         return (self.observation() if self.render else None), self.reward, self.done, {}
 

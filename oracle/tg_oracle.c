@@ -874,6 +874,46 @@ int or_robot_reset(const OrModel* m, OrState* s, const double* rest_q, const dou
     return steps;
 }
 
+/* Robot.apply_action(control_mode="TCP_position_control") (robot.py:156-186): tcp_position_control (base_robot_arm.py:228-279) -
+ * pose delta in the work frame, check_TCP_pos_lims (:349-355), workframe_to_worldframe (:47-60), IK from the current joints,
+ * position motors with forces = max_force - then blocking_move(max_steps, constant_vel=None) (robot.py:188-260): the pose
+ * error and the joint speeds are read before each step.  Returns the number of simulation steps taken. */
+int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_work[6], int max_steps)
+{
+    int n = m->ndof;
+    double pos[3], rpy[3], tp[3], tr[3];
+    or_tcp_pose_workframe(m, s->q, pos, rpy);
+    for (int c = 0; c < 3; c++) {
+        tp[c] = pos[c] + delta_work[c]; tr[c] = rpy[c] + delta_work[3 + c];
+        tp[c] = tp[c] < m->tcp_lims[c][0] ? m->tcp_lims[c][0] : (tp[c] > m->tcp_lims[c][1] ? m->tcp_lims[c][1] : tp[c]);
+        tr[c] = tr[c] < m->tcp_lims[3 + c][0] ? m->tcp_lims[3 + c][0] : (tr[c] > m->tcp_lims[3 + c][1] ? m->tcp_lims[3 + c][1] : tr[c]);
+    }
+    double wq[4], tq[4], tpos[3], tquat[4], trpy[3], targ_orn[4], targ_j[OR_MAXD];
+    workframe_quat(m, wq);
+    or_quat_from_euler(tr, tq);
+    or_mul_transforms(m->workframe_pos, wq, tp, tq, tpos, tquat);
+    or_euler_from_quat(tquat, trpy);
+    or_quat_from_euler(trpy, targ_orn);
+    or_inverse_kinematics(m, s->q, tpos, targ_orn, targ_j);
+    for (int i = 0; i < n; i++) {
+        s->motor_mode[i] = 1; s->target_pos[i] = targ_j[i]; s->target_vel[i] = 0;
+        s->kp[i] = m->pos_gain; s->kd[i] = m->vel_gain; s->max_force[i] = m->max_force;
+    }
+    int steps = 0;
+    for (int it = 0; it < max_steps; it++) {
+        double P[OR_MAXL][3], Q[OR_MAXL][4], tot = 0, pe = 0, ip = 0;
+        or_link_states(m, s->q, P, Q);
+        for (int i = 0; i < n; i++) tot += fabs(s->qd[i]);
+        or_step_sim(m, s);
+        steps++;
+        for (int c = 0; c < 3; c++) pe += fabs(tpos[c] - P[m->tcp_link][c]);
+        for (int c = 0; c < 4; c++) ip += targ_orn[c] * Q[m->tcp_link][c];
+        double ca = 2 * ip * ip - 1; ca = ca < -1 ? -1 : (ca > 1 ? 1 : ca);
+        if (pe < 2e-4 && acos(ca) < 1e-3 && tot < 0.1) break;
+    }
+    return steps;
+}
+
 /* ------------------------------------------------------------------ tactile raster */
 /* TactileSensor.update_cam_frame + get_imgs camera vectors (tactile_sensor.py:150-229) */
 void or_camera_frame(const OrModel* m, const double* q, double eye[3], double fwd[3], double up[3], double right[3])

@@ -274,6 +274,20 @@ TGD void reset_target(const TgTask& task, double embed, double centre_h, double*
     quat_from_euler(rpy, targ_orn);
 }
 
+// workframe_to_worldframe (base_robot_arm.py:47-60) + getQuaternionFromEuler of the resulting rpy
+TGD void work_to_world(const TgTask& task, const double* pos, const double* rpy, double* wpos, double* wquat)
+{
+    double wq[4], tq[4], R[9], t[3], oq[4], r2[3];
+    quat_from_euler(task.workframe_rpy, wq);
+    quat_from_euler(rpy, tq);
+    mat_from_quat(wq, R);
+    m3mulv(t, R, pos);
+    wpos[0] = task.workframe_pos[0] + t[0]; wpos[1] = task.workframe_pos[1] + t[1]; wpos[2] = task.workframe_pos[2] + t[2];
+    quat_mul(oq, wq, tq);
+    euler_from_quat(oq, r2);
+    quat_from_euler(r2, wquat);
+}
+
 // Reset, part 1: consume the env's next draws, rest pose; the IK of the start pose starts in reset_advance.
 template <class T>
 __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, const EnvBuffers& b, int e, ResetState<T::NB>& r)
@@ -785,6 +799,55 @@ TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
 // object_push runs PUSH_BLOCK envs per block, all lanes active, its constraint rows staged in dynamic shared memory, and
 // has no standby blocks: its episodes are long and its reset short, so each step thread advances its own env's standby
 // slot by one quantum after the step.
+// control_mode TCP_position_control, one env step (robot.py:156-186): tcp_position_control (base_robot_arm.py:228-279) -
+// the scaled action is a pose delta in the work frame, clipped to tcp_lims (check_TCP_pos_lims :349-355), brought to the world
+// frame, solved by IK from the current joints, held by position motors - then blocking_move(max_steps, constant_vel=None)
+// (robot.py:188-260): step until pose error and joint speed, both read BEFORE the step, pass.  Out of line: the velocity
+// mode's registers stay what they were.
+template <class T>
+__device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhysics& ph, const TgTask& task, double* q, double* qd, const double* delta)
+{
+    constexpr int NB = T::NB;
+    double tpos[3], torn[4];
+    Motors<NB> mot;
+    mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
+    {
+        Kin<NB> k;
+        fk<T>(arm, q, k);
+        double tp[3], tq[4], wp[3], wr[3], np_[3], nr[3];
+        tcp_world<T>(arm, k, tp, tq);
+        world_to_work(task, tp, tq, wp, wr);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            np_[c] = fmin(fmax(wp[c] + delta[c], task.tcp_lims[c][0]), task.tcp_lims[c][1]);
+            nr[c] = fmin(fmax(wr[c] + delta[3 + c], task.tcp_lims[3 + c][0]), task.tcp_lims[3 + c][1]);
+        }
+        work_to_world(task, np_, nr, tpos, torn);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) { mot.target_pos[i] = q[i]; mot.target_vel[i] = 0.0; }
+    for (int it = 0; it >= 0;) it = ik_chunk<T>(arm, mot.target_pos, tpos, torn, it, 100);
+    double sc[NB][2];
+#pragma unroll
+    for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
+#pragma unroll 1
+    for (int s = 0; s < task.pos_max_steps; s++) {
+        double tp[3], tq[4], tot = 0.0;
+        {
+            Kin<NB> k;
+            fk_sc<T>(arm, sc, k);
+            tcp_world<T>(arm, k, tp, tq);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; i++) tot += fabs(qd[i]);
+        substep<T>(arm, ph, q, qd, sc, mot);
+        const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
+        const double ip = torn[0] * tq[0] + torn[1] * tq[1] + torn[2] * tq[2] + torn[3] * tq[3];
+        const double oe = acos(fmin(fmax(2 * ip * ip - 1, -1.0), 1.0));
+        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
+    }
+}
+
 template <class T, int TASK>
 __global__ void __launch_bounds__((TASK == TG_TASK_OBJECT_PUSH || TASK == TG_TASK_OBJECT_ROLL) ? PUSH_THREADS : 128)
 step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
@@ -869,7 +932,8 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
             const double a = fmin(fmax(enc[s], task.act_min), task.act_max);
             v[s] = (((a - task.act_min) * (task.act_hi[s] - task.act_lo[s])) / in_range) + task.act_lo[s];
         }
-        // tcp_velocity_control (base_robot_arm.py:281-332)
+        // tcp_velocity_control (base_robot_arm.py:281-332); TCP_position_control is handled by position_control_move below
+        if (task.control_mode != 1) {
         double wp[3], wr[3];
         if (roll) {
             const double wf[3] = {task.workframe_pos[0], task.workframe_pos[1], b.obj_ext[(size_t)e * 4 + 1]}; // this episode's workframe
@@ -905,6 +969,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         }
 #pragma unroll
         for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;
+        }
     }
     ObjState ob;
     {
@@ -921,6 +986,8 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
 #pragma unroll 1
             for (int s = 0; s < ph.substeps; s++) substep_obj<T>(arm, ph, task, q, qd, sc, mot, ob);
             obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
+        } else if (task.control_mode == 1) {
+            position_control_move<T>(arm, ph, task, q, qd, v);
         } else {
 #pragma unroll 1
             for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, sc, mot);

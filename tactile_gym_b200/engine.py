@@ -24,6 +24,18 @@ def _sparse_flag(env_modes):
     return 1 if mode == "sparse" else 0
 
 
+def _control_mode(env_modes, arm_type):
+    """control_mode -> (TgTask.control_mode, pos_max_steps).  robot.py:156-186; _max_blocking_pos_move_steps = 10 in every env."""
+    mode = env_modes["control_mode"]
+    if mode == "TCP_velocity_control":
+        return 0, 10
+    if mode == "TCP_position_control":
+        if arm_type != "ur5":
+            raise NotImplementedError("TCP_position_control is built for the ur5 (the mg400's joint slaving of IK targets, mg400.py:167-172, is not)")
+        return 1, 10
+    raise ValueError("Incorrect control mode specified: {}".format(mode))
+
+
 def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
     """EdgeFollowEnv.__init__ (rl_envs/exploration/edge_follow/edge_follow_env.py:23-134) as a TgConfig.
     Returns (cfg, keepalive) - keepalive holds the numpy arrays the config points into."""
@@ -34,8 +46,6 @@ def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     movement_mode = env_modes["movement_mode"]
     control_mode = env_modes["control_mode"]
     noise_mode = env_modes["noise_mode"]
-    if control_mode != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built (SURVEY 8(f) item 4)" % control_mode)
     if arm_type not in ("ur5", "mg400"):
         raise ValueError("Incorrect arm type specified {}".format(arm_type))
     typ = "standard"
@@ -60,7 +70,10 @@ def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     for k in range(6):
         t.act_index[k] = idx[k] if k < len(idx) else -1
     t.act_min, t.act_max = -0.25, 0.25
+    t.control_mode, t.pos_max_steps = _control_mode(env_modes, arm_type)
     max_pos_vel, max_ang_vel = 0.01, 5.0 * (np.pi / 180)          # edge_follow_env.py:155-165
+    if t.control_mode == 1:                                        # :143-153: m / rad per step
+        max_pos_vel, max_ang_vel = 0.001, 1 * (np.pi / 180)
     hi = [max_pos_vel] * 3 + [0.0, 0.0, max_ang_vel]
     for k in range(6):
         t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
@@ -167,7 +180,7 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     if env_modes.get("object_mode", "pole") != "pole":
         raise NotImplementedError("object_mode %r: only 'pole' is built" % env_modes.get("object_mode"))
     if env_modes["control_mode"] != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
+        raise NotImplementedError("control_mode %r: TCP_position_control is built for edge_follow / surface_follow only (SURVEY 8(f) item 4)" % env_modes["control_mode"])
     if arm_type != "ur5":
         raise ValueError("object_balance has rest poses for the ur5 only among the built arms (rest_poses.py)")
     typ, S = "standard", int(image_size[0])
@@ -274,8 +287,6 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     elif movement_mode not in ("yz", "xyz", "yzRx", "xyzRxRy"):
         raise ValueError("Incorrect movement mode specified: %r" % movement_mode)
     one_d = movement_mode in ("yz", "yzRx", "xRz")
-    if env_modes["control_mode"] != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
     typ, S = "standard", int(image_size[0])
     mj = scene.load_model_json(arm_type, sensor, typ)
     sj = scene.load_sensor_json(sensor, typ)
@@ -286,6 +297,7 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     cfg.phys = scene.default_physics(substeps=int(np.floor((1.0 / 10.0) / (1.0 / 240.0))))      # :26-28 -> 24
     t = cfg.task
     t.task, t.max_steps = L.TG_TASK_SURFACE_FOLLOW, int(max_steps)
+    t.control_mode, t.pos_max_steps = _control_mode(env_modes, arm_type)
     if variant == "vert":
         idx = [0, 5]                                                                             # surface_follow_vert_env.py:43-45
     elif variant == "goal":
@@ -303,6 +315,8 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
         t.act_index[k] = idx[k] if k < len(idx) else -1
     t.act_min, t.act_max = -0.25, 0.25
     mv, ma = 0.01, 5.0 * (np.pi / 180)                                                          # :197-206
+    if t.control_mode == 1:                                                                      # :172-181: m / rad per step
+        mv, ma = 0.001, 1 * (np.pi / 180)
     hi = [mv, mv, mv, ma, ma, 0.0]
     for k in range(6):
         t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
@@ -362,7 +376,7 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
     movement_mode, traj_type = env_modes["movement_mode"], env_modes.get("traj_type", "simplex")
     if env_modes["control_mode"] != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
+        raise NotImplementedError("control_mode %r: TCP_position_control is built for edge_follow / surface_follow only (SURVEY 8(f) item 4)" % env_modes["control_mode"])
     if arm_type not in ("ur5", "mg400"):
         raise ValueError("Incorrect arm type specified {}".format(arm_type))
     if traj_type not in ("simplex", "straight"):
@@ -476,7 +490,7 @@ def object_roll_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     TgConfig.  Returns (cfg, keepalive, draw_fn)."""
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
     if env_modes["control_mode"] != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: only TCP_velocity_control is built" % env_modes["control_mode"])
+        raise NotImplementedError("control_mode %r: TCP_position_control is built for edge_follow / surface_follow only (SURVEY 8(f) item 4)" % env_modes["control_mode"])
     if env_modes["movement_mode"] != "xy":
         raise ValueError("Incorrect movement_mode specified: {}".format(env_modes["movement_mode"]))      # :288-297 knows "xy" only
     if arm_type != "ur5":

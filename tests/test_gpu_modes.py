@@ -174,3 +174,54 @@ def test_surface_follow_modes_and_sparse_reward(oracle, env_id, movement, noise)
     assert paid.all()
     assert not env.world.pipeline_error()
     env.close()
+
+
+@pytest.mark.parametrize("task", ["edge", "surface"])
+def test_tcp_position_control(oracle, task):
+    """control_mode "TCP_position_control" (robot.py:156-186, base_robot_arm.py:228-279): pose-delta actions, IK from the current
+    joints, position motors, blocking move of <= 10 substeps with the pose / speed exit - each step from an identical state"""
+    import tactile_gym_b200 as tg
+
+    n = 5
+    rng = np.random.RandomState(17)
+    if task == "edge":
+        modes = dict(BASE, movement_mode="xyzRz", noise_mode="rand_height", control_mode="TCP_position_control", reward_mode="dense")
+        env_id = "edge_follow-v0"
+        draws = np.stack([rng.uniform(0.0015, 0.0065, (n, 2)), rng.uniform(-np.pi, np.pi, (n, 2))], axis=2)
+        mk = lambda: oracle.EdgeFollowOracle(image_size=64, movement_mode="xyzRz", control_mode="TCP_position_control")
+    else:
+        modes = dict(BASE, movement_mode="xyzRxRy", noise_mode="simplex", control_mode="TCP_position_control", reward_mode="dense")
+        env_id = "surface_follow-v0"
+        draws = np.stack([rng.randint(0, 10 ** 8, (n, 2)).astype(np.float64), rng.uniform(-np.pi, np.pi, (n, 2))], axis=2)
+        mk = lambda: oracle.SurfaceFollowOracle(image_size=64, sensor="tactip", control_mode="TCP_position_control", render=False)
+    env = tg.make_vec(env_id, n, env_kwargs={"env_modes": modes, "image_size": [64, 64], "max_steps": 200})
+    env.world.set_draws(draws)
+    obs = env.reset()["oracle"]
+    st = env.world.get_state()
+    refs = []
+    for i in range(n):
+        r = mk()
+        r.reset(draws=tuple(draws[i, 0]))
+        refs.append(r)
+    p0 = obs[:, 0:3].copy()
+    moved = 0.0
+    for k in range(12):
+        act = rng.uniform(-0.25, 0.25, (n, env.world.act_dim)).astype(np.float32)
+        if k < 6:
+            act[:, 0] = 0.25                       # a steady 1 mm per step along the first action axis
+        for i, r in enumerate(refs):
+            _sync(r, st[i])
+            r.step(act[i])
+        o, rew, done, infos = env.step(act)
+        st = env.world.get_state()
+        for i, r in enumerate(refs):
+            assert np.allclose(st[i, :6], np.array(r.s.q[:6]), atol=1e-9), (k, i, np.abs(st[i, :6] - np.array(r.s.q[:6])).max())
+            assert np.allclose(st[i, 6:12], np.array(r.s.qd[:6]), atol=1e-7), (k, i)
+            assert 1 <= r.last_move_substeps <= 10
+            assert abs(rew[i] - r.reward) < 1e-6 and bool(done[i]) == r.done
+            assert np.allclose(o["oracle"][i], r.oracle_obs(), atol=2e-5)
+        if k == 5:
+            axis = 0 if task == "edge" else 2      # edge xyzRz: x; surface-auto xyzRxRy: the first policy action is z
+            moved = np.abs(o["oracle"][:, axis] - p0[:, axis])
+    assert np.all(moved > 0.004) and np.all(moved < 0.0065), moved      # ~6 mm after six full-scale position steps
+    env.close()

@@ -46,9 +46,13 @@ def test_config_rejects_bad_modes(edge_modes):
     bad = dict(edge_modes, arm_type="pr2")
     with pytest.raises(ValueError):
         edge_follow_config(bad, [128, 128], 200, 1)
-    bad = dict(edge_modes, control_mode="TCP_position_control")
+    bad = dict(edge_modes, control_mode="TCP_position_control", arm_type="mg400")     # position control: ur5 only
     with pytest.raises(NotImplementedError):
         edge_follow_config(bad, [128, 128], 200, 1)
+    with pytest.raises(ValueError):
+        edge_follow_config(dict(edge_modes, control_mode="joint_torque_control"), [128, 128], 200, 1)
+    cfg, _ = edge_follow_config(dict(edge_modes, control_mode="TCP_position_control"), [128, 128], 200, 1)
+    assert (cfg.task.control_mode, cfg.task.pos_max_steps, cfg.task.act_hi[0]) == (1, 10, 0.001)     # edge_follow_env.py:143-153
 
 
 def test_registry_ids():
