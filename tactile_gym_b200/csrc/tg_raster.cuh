@@ -60,7 +60,6 @@ struct PrimCoef {
 
 struct RasterArgs {
     int n, S, bands, nprim;
-    int e0;                // first env of this launch (envs [e0, n) are rendered; tg_step_host renders in chunks)
     double th;             // tan(fov/2)
     double F, near_, far_; // F = far/(far-near)
     const float* nodef;    // [S*S], border pixels = -1
@@ -437,7 +436,7 @@ raster_kernel(const RasterArgs a)
     auto flush_queue = [&](uint8_t* obs_e) { flush_exact<uint32_t>(a, ctx, obs_e, lane); };
 
     // one env image (band slice) per warp iteration
-    for (int e = a.e0 + lane_cta * RASTER_WARPS + warp; e < a.n; e += n_cta * RASTER_WARPS) {
+    for (int e = lane_cta * RASTER_WARPS + warp; e < a.n; e += n_cta * RASTER_WARPS) {
         if (a.mask && !a.mask[e]) continue;
         __syncwarp();
         if (lane == 0) *s_qcnt = 0;

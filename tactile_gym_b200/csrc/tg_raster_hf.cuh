@@ -71,7 +71,7 @@ raster_hf_kernel(const RasterArgs a, int* __restrict__ error_flag)
     const int tr = a.hf_tile_rows, tc = a.hf_tile_cols;
     const int tiles_x = S / tc, n_tiles = tiles_x * (band_rows / tr);
 
-    for (int e = a.e0 + lane_cta * HF_WARPS + warp; e < a.n; e += n_cta * HF_WARPS) {
+    for (int e = lane_cta * HF_WARPS + warp; e < a.n; e += n_cta * HF_WARPS) {
         if (a.mask && !a.mask[e]) continue;
         const double* cam = a.cam + (size_t)e * 12;
         const int buf = a.hf_cur[e] ^ (a.hf_flip ? 1 : 0);

@@ -18,7 +18,7 @@ raster_sphere_kernel(const RasterArgs a)
 {
     const int S = a.S, px = S * S, spans = px >> 4;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
-    for (int e = a.e0 + warp; e < a.n; e += nwarp) {
+    for (int e = warp; e < a.n; e += nwarp) {
         if (a.mask && !a.mask[e]) continue;
         const double* cam = a.cam + (size_t)e * 12;
         const double* st = a.stim + (size_t)e * 12;

@@ -246,7 +246,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         RasterArgs& r = w->ra;
         r.nd_ref = ndmin <= ndmax ? 0.5f * (ndmin + ndmax) : 0.5f;
         if (ndmin <= ndmax && !(ndmin >= 0.5f * r.nd_ref && ndmax <= 2.0f * r.nd_ref)) { tg_destroy(w); return fail(TG_EUNSUPPORTED, "nodef_dep range [%g, %g] too wide for the float path", ndmin, ndmax); }
-        r.n = n; r.e0 = 0; r.S = S; r.bands = S == 256 ? 4 : 1; r.nprim = np; r.prim_nv = dnv;
+        r.n = n; r.S = S; r.bands = S == 256 ? 4 : 1; r.nprim = np; r.prim_nv = dnv;
         r.th = tan(cfg->sensor.fov_deg * (M_PI / 180.0) / 2.0);
         r.near_ = cfg->sensor.near_; r.far_ = cfg->sensor.far_;
         r.F = cfg->sensor.far_ / (cfg->sensor.far_ - cfg->sensor.near_);
@@ -362,10 +362,14 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
     RasterArgs r = w->ra;
     r.obs = d_obs; r.mask = mask;
     if (e1 < 0) e1 = w->n;
-    r.e0 = e0; r.n = e1;   // envs [e0, e1)
     const int cnt = e1 - e0;
     if (cnt <= 0) return TG_OK;
     if (terminal_state) { r.cam = w->eb.term_cam; r.stim = w->eb.term_stim; r.hf_flip = 1; }
+    // envs [e0, e1): the kernels index their per-env arrays from 0, so the range is a shift of the base pointers
+    r.n = cnt;
+    r.obs += (size_t)e0 * w->S * w->S; r.cam += (size_t)e0 * 12; r.stim += (size_t)e0 * 12;
+    if (r.mask) r.mask += e0;
+    if (r.hf) { r.hf += (size_t)e0 * 2 * SURF_PTS; r.hf_cur += e0; r.hf_meta += (size_t)e0 * 2 * SURF_META; }
     if (w->cfg.task.task == TG_TASK_OBJECT_ROLL) raster_sphere_kernel<<<std::min((cnt + 7) / 8, 8 * w->sm_count), SPH_THREADS, 0, st>>>(r);
     else {
         const int wp = r.hf ? HF_WARPS : RASTER_WARPS;
