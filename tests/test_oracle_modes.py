@@ -1,0 +1,113 @@
+"""CPU known answers for the oracle's restatement of the modes beyond the BASELINE configs (no GPU): get_oracle_obs vectors,
+sparse rewards, 1-d / flat surfaces, surface_follow-v2's action encoding, TCP_position_control.  The GPU parity tests compare
+the CUDA path with these functions; here the functions themselves are checked against what the reference's code implies."""
+import ctypes as C
+
+import numpy as np
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def test_edge_oracle_obs_known_answers(oracle):
+    """edge_follow_env.py:454-476: [tcp pos (3), tcp lin vel (3), goal pos (3), edge_ang], all in the work frame
+    (rpy (-pi, 0, pi/2): x_work = world y, y_work = world x, z_work = -world z)"""
+    e = oracle.EdgeFollowOracle(image_size=64)
+    e.reset(draws=(0.003, 0.0))
+    o = e.oracle_obs()
+    assert o.shape == (10,)
+    p, _ = oracle.tcp_pose_workframe(e.m, np.array(e.s.q[:6]))
+    assert np.allclose(o[0:3], p, atol=1e-12) and abs(p[2] - 0.003) < 2e-4          # embedded 3 mm below the edge top
+    assert np.allclose(o[6:9], [0.0, 0.175, 0.0], atol=1e-12)                        # goal at the +x end of the edge (edge_ang 0)
+    assert o[9] == 0.0
+    e.step(np.array([0.25, -0.125], np.float32))
+    o = e.oracle_obs()
+    assert np.allclose(o[3:6], [0.01, -0.005, 0.0], atol=2e-4)                      # the velocity motors hold the commanded twist
+    e.reset(draws=(0.003, np.pi / 2))
+    assert np.allclose(e.oracle_obs()[6:9], [0.175, 0.0, 0.0], atol=1e-12)
+
+
+def test_object_oracle_obs_shapes_and_frames(oracle):
+    b = oracle.ObjectBalanceOracle(image_size=64, seed=1); b.reset()
+    o = b.oracle_obs()
+    assert o.shape == (26,)
+    assert abs(np.linalg.norm(o[3:7]) - 1) < 1e-9 and abs(np.linalg.norm(o[16:20]) - 1) < 1e-9      # two unit quaternions
+    # object_balance's work frame is not flipped (rpy 0, object_balance_env.py:73-74): the pole's base COM sits
+    # base_h / 2 - embed_dist above its origin (:214-219)
+    assert abs(o[15] - (b.base_h / 2 - b.embed_dist)) < 1e-12 and abs(o[13]) < 1e-12 and abs(o[14]) < 1e-12
+    p = oracle.ObjectPushOracle(image_size=64, seed=1); p.reset()
+    o = p.oracle_obs()
+    assert o.shape == (30,) and np.allclose(o[24:27], p.goal_pos_work) and np.allclose(o[27:30], p.goal_rpy_work)
+    r = oracle.ObjectRollOracle(image_size=64, seed=1); r.reset()
+    o = r.oracle_obs()
+    assert o.shape == (34,) and np.allclose(o[26:29], r.goal_pos_tcp) and np.allclose(o[29:33], [0, 0, 0, 1]) and o[33] == r.radius
+
+
+def test_sparse_rewards(oracle):
+    # edge_follow_env.py:430-438: 1 inside termination_dist of the goal, else 0
+    e = oracle.EdgeFollowOracle(image_size=64, reward_mode="sparse")
+    e.reset(draws=(0.003, 0.0))
+    assert e.step_data() == (0.0, False)
+    pos, rpy = np.array([0.0, 0.17, 0.003]), np.zeros(3)                              # 5 mm from the goal (work frame y = world x)
+    oracle.lib().or_robot_reset(C.byref(e.m), C.byref(e.s), _dptr(e.rest), _dptr(pos), _dptr(rpy))
+    assert e.step_data() == (1.0, True)
+    # object_balance_env.py:508-518: -1 once fallen, else 0
+    b = oracle.ObjectBalanceOracle(image_size=64, seed=1); b.reward_mode = "sparse"; b.reset()
+    assert b.step_data() == (0.0, False)
+    q = oracle.quat_from_euler([0.7, 0.0, -np.pi / 2])                               # 40 degrees of roll
+    for c in range(4):
+        b.o.quat[c] = q[c]
+    assert b.step_data() == (-1.0, True)
+
+
+def test_surface_modes(oracle):
+    # yz / yzRx: gen_heigtfield_simplex_1d (base_surface_env.py:339-357) and the (0, +-1) goal direction (:512-514)
+    s = oracle.SurfaceFollowOracle(image_size=64, sensor="tactip", movement_mode="yzRx", reward_mode="sparse", render=False)
+    s.reset(draws=(1234.0, -1.0))
+    assert np.ptp(s.h, axis=0).max() == 0 and np.ptp(s.h) > 1e-3
+    assert abs(s.h[5, 10] - oracle.opensimplex_noise2(1234, 1 * 0.05, 10 * 0.05) * 0.025) < 1e-15
+    assert np.allclose(s.dirs, [0.0, -1.0, 0.0])
+    assert abs(s.goal_pos[0] - (0.65 - 0.15)) < 1e-12 and abs(s.goal_pos[1]) < 1e-12    # y_work = world x
+    # sparse: reset's own get_step_data already accumulates (:590-591, :638); nothing is paid away from the goal
+    first = s.accum_rew
+    assert first < 0 and s.reward == 0.0
+    _, rew, done, _ = s.step(np.zeros(2, np.float32))
+    assert rew == 0.0 and not done and s.accum_rew < first
+    enc = s.encode_scale(np.array([0.1, -0.2], np.float32))                          # auto env: y driven, z / Rx the policy's
+    assert abs(enc[1] + 0.01) < 1e-15 and enc[0] == 0 and abs(enc[2] - 0.004) < 1e-9 and enc[3] < 0 and enc[4] == 0
+    # noise_mode "none": flat, no seed drawn
+    f = oracle.SurfaceFollowOracle(image_size=64, sensor="digit", movement_mode="xyz", noise_mode="none", render=False, seed=3)
+    a = oracle.gym_np_random(3)
+    f.reset()
+    assert np.all(f.h == 0) and abs(np.arctan2(f.dirs[1], f.dirs[0]) - a.uniform(-np.pi, np.pi)) < 1e-12
+    # surface_follow-v2 (surface_follow_vert_env.py): flat for xRz, y driven, x the policy's, Rz without range, 10 / 3 weights
+    v = oracle.SurfaceFollowOracle(image_size=64, sensor="digit", movement_mode="xRz", variant="vert", render=False)
+    v.reset(draws=(99.0, 1.0))
+    assert np.all(v.h == 0)
+    enc = v.encode_scale(np.array([0.25, 0.25], np.float32))
+    assert abs(enc[0] - 0.01) < 1e-15 and abs(enc[1] - 0.01 * 0.7) < 1e-15 and enc[5] == 0.0
+    p, qt = v.tcp_world()
+    # flat surface at z = 0.025; the reference point is the TCP moved embed_dist along the tip's own -z, which points up in the
+    # world's z here (base_surface_env.py:727-757); tip level: no normal term
+    assert abs(v.reward + 10.0 * abs((p[2] + v.embed_dist) - 0.025)) < 1e-6
+
+
+def test_tcp_position_control(oracle):
+    """base_robot_arm.py:228-279 + robot.py:188-260: 1 mm per full-scale step, the blocking move exits after a few substeps,
+    targets are clipped to the TCP limits (check_TCP_pos_lims)"""
+    e = oracle.EdgeFollowOracle(image_size=64, movement_mode="xyzRz", control_mode="TCP_position_control")
+    e.reset(draws=(0.003, 0.3))
+    p0 = e.oracle_obs()[:3].copy()
+    for k in range(5):
+        e.step(np.array([0.25, 0.0, 0.0, 0.0], np.float32))
+        assert 1 <= e.last_move_substeps <= 10
+    p1 = e.oracle_obs()[:3]
+    assert abs((p1[0] - p0[0]) - 0.005) < 1e-4 and abs(p1[1] - p0[1]) < 1e-4 and abs(p1[2] - p0[2]) < 1e-4
+    s = oracle.SurfaceFollowOracle(image_size=64, sensor="tactip", movement_mode="xyz", noise_mode="none", render=False,
+                                   control_mode="TCP_position_control")
+    s.reset(draws=(0.0, 0.0))
+    for k in range(30):
+        s.step(np.array([0.25], np.float32))                                          # z + 1 mm per step, limit + 25 mm
+    z = s.oracle_obs()[2]
+    assert 0.0245 < z < 0.0252
