@@ -19,8 +19,10 @@ STALLS = "smsp__pcsamp_warps_issue_stalled_"
 
 
 def main(rep, out, title):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    # a .csv is the raw page already exported on the GPU box (`ncu -i X.ncu-rep --page raw --csv`: the reports themselves are
+    # tens of MB and do not fit gpurun_out's copy-back limit)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
     hdr, units = rows[0], rows[1]
     lines = ["# %s" % title, "", "source: `%s` (ncu --set full --clock-control none --import-source on; times under ncu are serialised/cold - use shares, not absolutes)" % rep, ""]
     for vals in rows[2:]:
