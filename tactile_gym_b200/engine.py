@@ -584,8 +584,9 @@ class TactileWorld:
         L.check(self.lib.tg_create(C.byref(cfg), device, C.byref(h)))
         self.h = h
         with torch.cuda.device(self.device):
-            self.obs = torch.zeros((self.n, self.S, self.S, 1), dtype=torch.uint8, device=self.device)
-            self.term_obs = torch.zeros_like(self.obs)
+            # the observation tensors [N, S, S, 1] u8 are allocated on first use: observation_mode "oracle" never renders,
+            # and at 16,384 envs x 256 x 256 they are 1 GiB each
+            self._obs = self._term_obs = None
             self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
             self.feat = self.term_feat = None
@@ -607,6 +608,20 @@ class TactileWorld:
         self._host_draws = None
         self._steps_since_check = 0
         self._upload_draws(fresh=True)
+
+    @property
+    def obs(self):
+        if self._obs is None:
+            with self.torch.cuda.device(self.device):
+                self._obs = self.torch.zeros((self.n, self.S, self.S, 1), dtype=self.torch.uint8, device=self.device)
+        return self._obs
+
+    @property
+    def term_obs(self):
+        if self._term_obs is None:
+            with self.torch.cuda.device(self.device):
+                self._term_obs = self.torch.zeros((self.n, self.S, self.S, 1), dtype=self.torch.uint8, device=self.device)
+        return self._term_obs
 
     def bind_oracle_obs(self):
         """observation_mode "oracle": every following step / reset fills self.oracle_obs [N, TG_ORACLE_NOBS] (first
@@ -659,11 +674,15 @@ class TactileWorld:
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
-    def reset(self, mask=None):
+    def reset(self, mask=None, render=True):
+        """Reset the masked envs (None: all).  render=False (observation_mode "oracle") skips their first image."""
         mp = None
         if mask is not None:
             mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
             mp = mask.data_ptr()
+        if not render:
+            L.check(self.lib.tg_reset_only(self.h, mp, self._stream()))
+            return None
         L.check(self.lib.tg_reset(self.h, mp, self.obs.data_ptr(), self._stream()))
         return self.obs
 

@@ -73,7 +73,7 @@ class BaseTactileEnv(_Base):
         return self.world.feat[0, : self.world.nfeat].cpu().numpy()
 
     def reset(self):
-        self.world.reset()
+        self.world.reset(render="tactile" in self.observation_mode)
         return self._obs()
 
     def step(self, action):
@@ -87,6 +87,8 @@ class BaseTactileEnv(_Base):
         return self._obs(), float(self.world.reward[0].item()), bool(self.world.done[0].item()), {}
 
     def get_tactile_obs(self):
+        if "tactile" not in self.observation_mode:      # the reference renders on demand (base_tactile_env.py:200-210)
+            self.world.raster_only()
         return self.world.obs[0].cpu().numpy()
 
     def render(self, mode="rgb_array"):

@@ -106,7 +106,7 @@ class TactileVecEnv(_VecEnvBase):
         return o
 
     def reset(self):
-        self.world.reset()
+        self.world.reset(render=not self._oracle)
         if self._oracle:
             self._pin_oracle.copy_(self.world.oracle_obs, non_blocking=True)
         else:
