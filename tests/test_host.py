@@ -179,3 +179,30 @@ def test_pole_asset_composite():
     assert abs(pole["com_off"][2] - ((0.01 * 0.00125 + 0.1 * 0.05) / 0.11 - 0.00125)) < 1e-15
     prims, nv = scene.merge_coplanar(scene.load_stimulus("pole"))
     assert prims.shape == (12, 4, 3) and (nv == 4).all()
+
+
+def test_ctypes_structs_mirror_the_header(tmp_path):
+    """Every field of the ctypes Structures in _lib.py sits at the offset the C compiler gives the header's struct (a drifted
+    mirror would corrupt the task description silently): sizeof + offsetof of all fields, compiled from include/*.h."""
+    from tactile_gym_b200 import _lib
+
+    structs = ["TgArm", "TgPhysics", "TgTask", "TgSensor", "TgConfig", "TgHostStep"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tactile_gym_b200.h"', "int main(void) {"]
+    for sn in structs:
+        lines.append('printf("%s . %%zu\\n", sizeof(%s));' % (sn, sn))
+        for fname, *_ in getattr(_lib, sn)._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (sn, fname, sn, fname))
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    n = 0
+    for line in out.splitlines():
+        sn, fname, val = line.split()
+        cls = getattr(_lib, sn)
+        want = C.sizeof(cls) if fname == "." else getattr(cls, fname).offset
+        assert int(val) == want, (sn, fname, int(val), want)
+        n += 1
+    assert n >= 150
