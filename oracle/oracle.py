@@ -704,7 +704,7 @@ class SurfaceFollowOracle:
         return np.hstack([pos, orn, lin, ang, goal, self.surface_array[self.tip_i, self.tip_j, 2], n])
 
     def features(self):   # SurfaceFollowGoalEnv.get_extended_feature_array (surface_follow_goal_env.py:83-97)
-        tp, _ = tcp_pose_workframe(self.m, np.array(self.s.q[: self.m.ndof]))
+        tp = tcp_state_workframe(self.m, self.s)[0]
         gp = self.Rw.T @ (self.goal_pos - self.workframe_pos)
         return np.concatenate([tp, gp])
 
@@ -898,7 +898,7 @@ class ObjectPushOracle:
         return np.hstack([pos, rpy, lin, ang, op, orpy, ol, oa, self.goal_pos_work, self.goal_rpy_work])
 
     def features(self):   # get_extended_feature_array :611-629
-        p, r = tcp_pose_workframe(self.m, np.array(self.s.q[: self.m.ndof]))
+        p, r = tcp_state_workframe(self.m, self.s)[:2]
         return np.concatenate([p, r, self.goal_pos_work, self.goal_rpy_work])
 
     def observation(self):

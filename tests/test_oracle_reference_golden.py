@@ -1,8 +1,10 @@
 """CPU: the oracle against golden vectors computed by the REFERENCE'S OWN SOURCE (tests/golden/reference_numpy.npz, written by
 tools/make_reference_golden.py, which compiles the reference's class bodies from /root/reference and runs their pure-numpy
-methods): action encoding + scaling of every env / movement mode / control mode, the work-frame transforms, the edge reward and
-termination geometry, the surface index lookup, distances and the three surface envs' dense rewards.  This pins the parts of
-the oracle that restate reference Python (as opposed to pybullet's C++) to the reference itself."""
+methods): action encoding + scaling of every env / movement mode / control mode (object_push's TCP-frame encodings included),
+the work-frame transforms, the edge reward and termination geometry, the surface index lookup, distances and the three surface
+envs' dense rewards, object_push's trajectory of goals (around a stand-in noise function), its rewards, goal advancing and
+extended feature, object_balance's fall test, object_roll's TCP-frame goal, and get_oracle_obs of all five tasks.  This pins the
+parts of the oracle that restate reference Python (as opposed to pybullet's C++) to the reference itself."""
 import os
 
 import numpy as np
@@ -123,3 +125,131 @@ def test_surface_lookup_and_rewards(oracle, monkeypatch):
         z, cs, xy = rows[k, 0], rows[k, 1], rows[k, 13]
         assert abs(rows[k, 2] + (z + cs)) < 1e-12 and abs(rows[k, 5] + z) < 1e-12
         assert abs(rows[k, 8] + (xy + 10 * z + cs)) < 1e-12 and abs(rows[k, 11] + (10 * z + 3 * cs)) < 1e-12
+
+
+# ---------------------------------------------------------------- object tasks and the oracle observations
+def _fake_noise(seed, x, y):       # the stand-in noise function of tools/make_reference_golden.py (section E)
+    return 0.6 * np.sin(2.3 * x + 0.4) * np.cos(0.7 * y) + 0.2 * np.sin(5.1 * x)
+
+
+def _inject_tcp(oracle, monkeypatch, env, tcp):
+    """make the oracle env see a given world TCP state [pos, rpy, lin vel, ang vel] instead of its joints'"""
+    pos, quat, lin, ang = tcp[0:3], oracle.quat_from_euler(tcp[3:6]), tcp[6:9], tcp[9:12]
+    env.tcp_world = lambda: (pos, quat)
+
+    def state(m, s):
+        p, r = oracle.world_to_work(m, pos, quat)
+        return p, r, oracle.quat_from_euler(r), oracle.world_to_work_vec(m, lin), oracle.world_to_work_vec(m, ang)
+
+    monkeypatch.setattr(oracle, "tcp_state_workframe", state)
+
+
+def _set_obj(env, o13):
+    for c in range(3):
+        env.o.pos[c] = o13[c]
+    for c in range(4):
+        env.o.quat[c] = o13[3 + c]
+    if len(o13) >= 13:
+        for c in range(3):
+            env.o.vel[c] = o13[7 + c]; env.o.omg[c] = o13[10 + c]
+
+
+def test_push_actions_trajectory_rewards_and_observations(oracle, monkeypatch):
+    monkeypatch.setattr(oracle, "opensimplex_noise2", _fake_noise)
+    assert np.allclose(GOLD["push_wpos"], oracle.ObjectPushOracle(image_size=64, arm="ur5", sensor="tactip").workframe_pos)
+    rpy = GOLD["push_tcp_rpy_for_actions"]
+    for mode in ("y", "yRz", "xyRz", "TyRz", "TxTyRz"):
+        e = oracle.ObjectPushOracle(image_size=64, arm="ur5", sensor="tactip", movement_mode=mode)
+        e.tcp_world = lambda: (GOLD["push_wpos"], oracle.quat_from_euler(rpy))
+        _check_actions("push_%s" % mode, e)
+    for traj_type, third in (("simplex", 4242.0), ("straight", 0.23)):
+        g = lambda n: GOLD["push_%s_%s" % (traj_type, n)]
+        e = oracle.ObjectPushOracle(image_size=64, arm="ur5", sensor="tactip", movement_mode="TyRz", traj_type=traj_type, max_steps=1000)
+        e.reset(draws=np.array([0.0, 0.491, third]))
+        assert np.allclose(e.traj_pos_work, g("traj_pos_work"), atol=TOL) and np.allclose(e.traj_rpy_work, g("traj_rpy_work"), atol=TOL)
+        assert np.allclose(e.traj_pos_world, g("traj_pos_world"), atol=TOL)
+        assert np.allclose(np.abs(np.sum(e.traj_orn_world * g("traj_orn_world"), axis=1)), 1.0, atol=1e-12)     # same rotation (q ~ -q)
+        tcp = np.concatenate([GOLD["push_wpos"] + np.array([0.01, 0.02, 0.0]), rpy, [0.004, -0.003, 0.001], [0.01, 0.02, -0.2]])
+        _inject_tcp(oracle, monkeypatch, e, tcp)
+        e.targ = -1
+        e.update_goal()
+        e.steps = 5
+        rows = g("rows")
+        for k, row in enumerate(rows):
+            _set_obj(e, g("obj")[k])
+            e.reward_mode = "sparse"
+            targ = e.targ
+            assert e.step_data()[0] == row[1], (traj_type, k)
+            e.targ = targ                                   # (step_data advances the goal: rewind for the dense evaluation)
+            e.goal_pos_world, e.goal_orn_world = e.traj_pos_world[min(targ, 9)], e.traj_orn_world[min(targ, 9)]
+            e.goal_pos_work, e.goal_rpy_work = e.traj_pos_work[min(targ, 9)], e.traj_rpy_work[min(targ, 9)]
+            e.reward_mode = "dense"
+            rew, done = e.step_data()
+            assert abs(rew - row[0]) < 1e-12 and abs(rew - row[2]) < 1e-12 and done == bool(row[3]), (traj_type, k, rew, row[:4])
+            assert e.targ == int(row[4]), (traj_type, k, e.targ, row[4])
+            assert np.allclose(e.features(), row[5:17], atol=1e-12), (traj_type, k)
+        assert rows[-1][3] == 1.0 and rows[-1][4] == 10            # walked the whole trajectory: done when the last goal is reached
+        if traj_type == "simplex":
+            e.targ = int(GOLD["push_oracle_goal_index"][0]) - 1
+            e.update_goal()
+            _set_obj(e, GOLD["push_oracle_obj"])
+            assert np.allclose(e.oracle_obs(), GOLD["push_oracle_obs"], atol=1e-12)
+
+
+def test_balance_fall_rewards_and_observation(oracle, monkeypatch):
+    b = oracle.ObjectBalanceOracle(image_size=64, rand_gravity=False, rand_embed_dist=False)
+    b.reset(draws=np.array([-0.1, 0.0035, 0.0, 0.0]))
+    assert np.allclose(b.init_obj_pos, GOLD["balance_init_pos"], atol=1e-15)
+    for o7, row in zip(GOLD["balance_obj"], GOLD["balance_rows"]):
+        _set_obj(b, o7)
+        b.steps = int(row[4])
+        b.reward_mode = "dense"
+        rew, done = b.step_data()
+        assert rew == row[3] and done == bool(row[1])
+        b.reward_mode = "sparse"
+        assert b.step_data()[0] == row[2]
+    assert 0 < GOLD["balance_rows"][:, 0].sum() < len(GOLD["balance_rows"])      # both fallen and standing poses are covered
+    _inject_tcp(oracle, monkeypatch, b, GOLD["balance_oracle_tcp"])
+    _set_obj(b, GOLD["balance_oracle_obj"])
+    got, want = b.oracle_obs(), GOLD["balance_oracle_obs"]
+    assert got.shape == want.shape == (26,) and np.allclose(got, want, atol=1e-12), np.abs(got - want).max()
+
+
+def test_roll_goal_rewards_and_observation(oracle, monkeypatch):
+    radius, embed = GOLD["roll_radius"]
+    r = oracle.ObjectRollOracle(image_size=64, rand_obj_size=True, rand_embed_dist=True, rand_init_obj_pos=True, max_steps=250)
+    r.reset(draws=np.array([radius / 0.0025, embed, 0.0, 0.0, 0.0, 0.01]))
+    assert np.allclose(r.workframe_pos, GOLD["roll_wpos"], atol=1e-15)
+    _inject_tcp(oracle, monkeypatch, r, np.concatenate([GOLD["roll_tcp"], [0.004, -0.003, 0.0], [0.0, 0.0, 0.0]]))
+    for row in GOLD["roll_rows"]:
+        r.goal_pos_tcp = row[0:3].copy()
+        _set_obj(r, np.concatenate([row[3:6], [0.0, 0.0, 0.0, 1.0]]))
+        r.steps = int(row[12])
+        r.reward_mode = "dense"
+        rew, done = r.step_data()
+        assert np.allclose(r.goal_pos_world, row[6:9], atol=1e-12)
+        assert abs(rew - row[9]) < 1e-12 and done == bool(row[11])
+        r.reward_mode = "sparse"
+        assert r.step_data()[0] == row[10]
+        assert np.allclose(r.features(), row[13:16], atol=0)
+    assert GOLD["roll_rows"][:, 10].max() == 1.0 and GOLD["roll_rows"][:, 10].min() == 0.0
+    _set_obj(r, GOLD["roll_oracle_obj"])
+    got, want = r.oracle_obs(), GOLD["roll_oracle_obs"]
+    assert got.shape == want.shape == (34,) and np.allclose(got, want, atol=1e-12), np.abs(got - want).max()
+
+
+def test_edge_and_surface_oracle_observations(oracle, monkeypatch):
+    e = oracle.EdgeFollowOracle(image_size=64)
+    e.reset(draws=(0.003, 1.1))
+    _inject_tcp(oracle, monkeypatch, e, GOLD["edge_oracle_tcp"])
+    got, want = e.oracle_obs(), GOLD["edge_oracle_obs"]
+    assert got.shape == want.shape == (10,) and np.allclose(got, want, atol=1e-12), np.abs(got - want).max()
+    h = GOLD["surf_h"]
+    monkeypatch.setattr(oracle, "surface_heights", lambda *a, **k: h.copy())
+    s = oracle.SurfaceFollowOracle(image_size=64, sensor="tactip", render=False)
+    s.reset(draws=(1.0, 0.3))
+    s.goal_pos = GOLD["surf_goal"]
+    _inject_tcp(oracle, monkeypatch, s, GOLD["surf_oracle_tcp"])
+    s.step_data()
+    got, want = s.oracle_obs(), GOLD["surf_oracle_obs"]
+    assert got.shape == want.shape == (20,) and np.allclose(got, want, atol=1e-12), np.abs(got - want).max()

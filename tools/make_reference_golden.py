@@ -68,7 +68,16 @@ class PB:
         R = np.array(cls.getMatrixFromQuaternion(qi)).reshape(3, 3)
         return tuple(-(R @ np.asarray(p, float))), qi
 
-    def __getattr__(self, name):   # resetBasePositionAndOrientation, addUserDebugLine ...: scene bookkeeping, no arithmetic
+    def __init__(self):
+        self.bodies = {}
+
+    def resetBasePositionAndOrientation(self, uid, pos, orn):
+        self.bodies[uid] = (tuple(float(v) for v in pos), tuple(float(v) for v in orn))
+
+    def getBasePositionAndOrientation(self, uid):
+        return self.bodies[uid]
+
+    def __getattr__(self, name):   # changeVisualShape, addUserDebugLine ...: scene bookkeeping, no arithmetic
         return lambda *a, **k: None
 
 
@@ -120,6 +129,9 @@ def main():
     BaseObjectEnv = ref_class(os.path.join(obj, "base_object_env.py"), "BaseObjectEnv", (BaseTactileEnv,))
     Balance = ref_class(os.path.join(obj, "object_balance", "object_balance_env.py"), "ObjectBalanceEnv", (BaseObjectEnv,))
     Roll = ref_class(os.path.join(obj, "object_roll", "object_roll_env.py"), "ObjectRollEnv", (BaseObjectEnv,))
+    noise = lambda x, y: 0.6 * np.sin(2.3 * x + 0.4) * np.cos(0.7 * y) + 0.2 * np.sin(5.1 * x)   # stand-in for OpenSimplex.noise2
+    FakeSimplex = type("OpenSimplex", (), {"__init__": lambda self, seed: None, "noise2": lambda self, x, y: noise(x, y)})
+    Push = ref_class(os.path.join(obj, "object_push", "object_push_env.py"), "ObjectPushEnv", (BaseObjectEnv,), extra={"OpenSimplex": FakeSimplex, "os": os})
 
     # ---- A. encode_actions + scale_actions (R2): every movement mode, both control modes where the env defines them
     def actions_case(key, cls, act_dim, **attrs):
@@ -226,6 +238,124 @@ def main():
             vals += [e.z_dist_to_surface(), e.cos_dist_to_surface_normal(), e.dense_reward()]
         rows.append(vals + [e.xyz_dist_to_goal(), e.xy_dist_to_goal(), float(e.termination())])
     out["surf_tcp_pos"], out["surf_tcp_rpy"], out["surf_goal"], out["surf_rows"] = tcp_pos, tcp_rpy, goal, np.array(rows)
+
+    # ---- E. object_push (R2, R7, R10): TCP-frame / work-frame action encodings, the trajectory of goals around a stand-in noise
+    # function (the replay injects the same one into the oracle), rewards, goal advancing, extended feature, oracle observation
+    def arm_with_state(wpos, wrpy, tcp_pos, push_rpy, lin, ang):
+        arm = bare(BaseRobotArm, _pb=PB())
+        arm.set_workframe(wpos, wrpy)
+        q = PB.getQuaternionFromEuler(push_rpy)
+        arm.get_current_TCP_pos_vel_worldframe = lambda: (np.array(tcp_pos), np.array(PB.getEulerFromQuaternion(q)), np.array(q), np.array(lin), np.array(ang))
+        return arm
+
+    wpos, wrpy = np.array([0.55, -0.20, 0.04]), np.array([-np.pi, 0.0, np.pi / 2])      # ur5: well_designed_pos, obj_height / 2 (:96-101)
+    out["push_wpos"], out["push_wrpy"] = wpos, wrpy
+    push_rpy = np.array([-np.pi, 0.0, np.pi / 2 + 0.31])
+    out["push_tcp_rpy_for_actions"] = push_rpy
+    for mode, nd in (("y", 1), ("yRz", 2), ("xyRz", 3), ("TyRz", 2), ("TxTyRz", 3)):
+        arm = arm_with_state(wpos, wrpy, wpos, push_rpy, np.zeros(3), np.zeros(3))
+        actions_case("push_%s" % mode, Push, nd, movement_mode=mode, control_mode="TCP_velocity_control", _pb=PB(),
+                     robot=types.SimpleNamespace(arm=arm), cur_tcp_orn_worldframe=PB.getQuaternionFromEuler(push_rpy))
+    for traj_type, third in (("simplex", 4242.0), ("straight", 0.23)):
+        pb = PB()
+        arm = arm_with_state(wpos, wrpy, wpos + np.array([0.01, 0.02, 0.0]), push_rpy, [0.004, -0.003, 0.001], [0.01, 0.02, -0.2])
+        env = bare(Push, _pb=pb, robot=types.SimpleNamespace(arm=arm), traj_type=traj_type, traj_n_points=10, traj_spacing=0.025, traj_max_perturb=0.1,
+                   traj_ids=list(range(100, 110)), obj_width=0.08, termination_pos_dist=0.025, _max_steps=1000, _env_step_counter=5, reward_mode="dense",
+                   obj_id=7, np_random=types.SimpleNamespace(randint=lambda hi: int(third), uniform=lambda lo, hi: third))
+        env.make_goal()
+        out["push_%s_traj_pos_work" % traj_type], out["push_%s_traj_rpy_work" % traj_type] = env.traj_pos_workframe.copy(), env.traj_rpy_workframe.copy()
+        out["push_%s_traj_pos_world" % traj_type] = np.array([pb.bodies[i][0] for i in env.traj_ids])
+        out["push_%s_traj_orn_world" % traj_type] = np.array([pb.bodies[i][1] for i in env.traj_ids])
+        # the cube walks along the trajectory: rewards before the goal advances, goal index after
+        rows, objs = [], []
+        for k in range(24):
+            g = min(env.targ_traj_list_id, 9)
+            near = k % 3 != 1
+            op = np.array(pb.bodies[env.traj_ids[g]][0]) + (np.array([0.004, -0.006, 0.0]) if near else np.array([0.05, 0.03, 0.0]))
+            oq = PB.getQuaternionFromEuler([-np.pi, 0.0, np.pi / 2 + 0.1 * k - 0.4])
+            pb.bodies[7] = (tuple(op), oq)
+            objs.append(np.concatenate([op, oq]))
+            env.reward_mode = "dense"
+            (env.cur_tcp_pos_worldframe, env.cur_push_rpy_worldframe, env.cur_tcp_orn_worldframe, _, _) = arm.get_current_TCP_pos_vel_worldframe()
+            env.cur_obj_pos_worldframe, env.cur_obj_orn_worldframe = env.get_obj_pos_worldframe()
+            dense, sparse = env.dense_reward(), env.sparse_reward()
+            rew, done = env.get_step_data()
+            feat = env.get_extended_feature_array()
+            rows.append([dense, sparse, rew, float(done), env.targ_traj_list_id, *feat])
+            if done:
+                break
+        out["push_%s_obj" % traj_type], out["push_%s_rows" % traj_type] = np.array(objs), np.array(rows, dtype=np.float64)
+        if traj_type == "simplex":
+            pb.bodies[7] = (tuple(wpos + np.array([0.05, 0.01, 0.0])), PB.getQuaternionFromEuler([-np.pi, 0.0, np.pi / 2 + 0.2]))
+            pb.getBaseVelocity = lambda uid: ((0.01, -0.02, 0.003), (0.1, 0.2, -0.3))
+            out["push_oracle_obj"] = np.concatenate([pb.bodies[7][0], pb.bodies[7][1], [0.01, -0.02, 0.003], [0.1, 0.2, -0.3]])
+            out["push_oracle_tcp"] = np.concatenate([wpos + np.array([0.01, 0.02, 0.0]), push_rpy, [0.004, -0.003, 0.001], [0.01, 0.02, -0.2]])
+            out["push_oracle_goal_index"] = np.array([env.targ_traj_list_id])
+            out["push_oracle_obs"] = np.array(env.get_oracle_obs(), dtype=np.float64)
+
+    # ---- F. object_balance: check_obj_fall / rewards (R7) and its oracle observation (R10)
+    bw, brpy = np.array([0.55, 0.0, 0.35]), np.zeros(3)
+    init_pos, init_rpy = bw + np.array([0.0, 0.0, 0.00125 - 0.0035]), np.array([0.0, 0.0, -np.pi / 2])
+    rows, objs = [], []
+    for k in range(12):
+        pb = PB()
+        rpy = init_rpy + np.array([0.25, -0.2, 0.4]) * rng.uniform(-3.5, 3.5, 3)
+        pos = init_pos + rng.uniform(-0.09, 0.09, 3) * (1.0 if k % 2 else 0.3)
+        pb.bodies[3] = (tuple(pos), PB.getQuaternionFromEuler(rpy))
+        e = bare(Balance, _pb=pb, obj_id=3, init_obj_rpy=init_rpy, init_obj_pos=init_pos, termination_dist_deg=35, termination_dist_pos=0.1,
+                 _max_steps=250, _env_step_counter=int(rng.randint(0, 260)))
+        objs.append(np.concatenate([pos, pb.bodies[3][1]]))
+        rows.append([float(e.check_obj_fall()), float(e.termination()), e.sparse_reward(), e.dense_reward(), e._env_step_counter])
+    out["balance_obj"], out["balance_rows"], out["balance_init_pos"] = np.array(objs), np.array(rows), init_pos
+    pb = PB()
+    pb.bodies[3] = (tuple(init_pos + np.array([0.01, -0.02, 0.003])), PB.getQuaternionFromEuler(init_rpy + np.array([0.1, -0.05, 0.2])))
+    pb.getBaseVelocity = lambda uid: ((0.01, -0.02, 0.003), (0.1, 0.2, -0.3))
+    arm = arm_with_state(bw, brpy, bw + np.array([0.002, 0.001, -0.0003]), [0.05, -0.02, 0.01], [0.004, -0.003, 0.001], [0.01, 0.02, -0.2])
+    arm._pb = pb
+    e = bare(Balance, _pb=pb, obj_id=3, robot=types.SimpleNamespace(arm=arm))
+    out["balance_oracle_obj"] = np.concatenate([pb.bodies[3][0], pb.bodies[3][1], [0.01, -0.02, 0.003], [0.1, 0.2, -0.3]])
+    out["balance_oracle_tcp"] = np.concatenate([bw + np.array([0.002, 0.001, -0.0003]), [0.05, -0.02, 0.01], [0.004, -0.003, 0.001], [0.01, 0.02, -0.2]])
+    out["balance_oracle_obs"] = np.array(e.get_oracle_obs(), dtype=np.float64)
+
+    # ---- G. object_roll: the goal fixed in the TCP frame, rewards / termination, feature and oracle observation
+    radius, embed = 0.0025 * 1.4, 0.0025
+    rw_, rrpy = np.array([0.65, 0.0, 2 * radius - embed]), np.array([-np.pi, 0.0, np.pi / 2])
+    rows = []
+    tcp_p, tcp_r = rw_ + np.array([0.003, -0.002, 0.0002]), np.array([-np.pi, 0.0, np.pi / 2])
+    for k in range(8):
+        pb = PB()
+        arm = arm_with_state(rw_, rrpy, tcp_p, tcp_r, [0.004, -0.003, 0.0], [0.0, 0.0, 0.0])
+        goal_tcp = np.array([0.008 * np.cos(0.9 * k), 0.008 * np.sin(0.9 * k), 0.0])
+        e = bare(Roll, _pb=pb, obj_id=5, robot=types.SimpleNamespace(arm=arm), goal_pos_tcp=goal_tcp, goal_rpy_tcp=[0.0, 0.0, 0.0],
+                 goal_orn_tcp=PB.getQuaternionFromEuler([0.0, 0.0, 0.0]), visualise_goal=False, termination_pos_dist=0.001, _max_steps=250,
+                 _env_step_counter=3 if k < 7 else 250, reward_mode="dense", scaled_obj_radius=radius)
+        e.update_goal()
+        obj_p = np.array(e.goal_pos_worldframe) + (np.array([0.0004, -0.0003, 0.0]) if k % 2 == 0 else np.array([0.004, 0.003, 0.0]))
+        obj_p[2] = radius
+        pb.bodies[5] = (tuple(obj_p), (0.0, 0.0, 0.0, 1.0))
+        rew_d, done = e.get_step_data()
+        e.reward_mode = "sparse"
+        rew_s, _ = e.get_step_data()
+        rows.append([*goal_tcp, *obj_p, *e.goal_pos_worldframe, rew_d, rew_s, float(done), e._env_step_counter, *e.get_extended_feature_array()])
+    out["roll_rows"], out["roll_tcp"], out["roll_wpos"], out["roll_radius"] = np.array(rows), np.concatenate([tcp_p, tcp_r]), rw_, np.array([radius, embed])
+    pb.getBaseVelocity = lambda uid: ((0.01, -0.02, 0.0), (0.1, 0.2, -0.3))
+    arm._pb = pb
+    out["roll_oracle_obj"] = np.concatenate([pb.bodies[5][0], pb.bodies[5][1], [0.01, -0.02, 0.0], [0.1, 0.2, -0.3]])
+    out["roll_oracle_obs"] = np.array(e.get_oracle_obs(), dtype=np.float64)
+
+    # ---- H. edge / surface oracle observations (R10) from a given world TCP state
+    arm = arm_with_state([0.65, 0.0, 0.035], [-np.pi, 0.0, np.pi / 2], [0.66, 0.01, 0.032], [-np.pi + 0.02, 0.03, np.pi / 2 - 0.4], [0.004, -0.003, 0.001], [0.01, 0.02, -0.2])
+    e = bare(EdgeFollowEnv, _pb=PB(), robot=types.SimpleNamespace(arm=arm), edge_pos=[0.65, 0.0, 0.0], edge_len=0.175, edge_height=0.035, edge_stim_id=0,
+             goal_indicator=1, np_random=types.SimpleNamespace(uniform=lambda lo, hi: 1.1))
+    e.update_edge()
+    out["edge_oracle_tcp"] = np.concatenate([[0.66, 0.01, 0.032], [-np.pi + 0.02, 0.03, np.pi / 2 - 0.4], [0.004, -0.003, 0.001], [0.01, 0.02, -0.2]])
+    out["edge_oracle_obs"] = np.array(e.get_oracle_obs(), dtype=np.float64)
+    arm = arm_with_state([0.65, 0.0, 0.025], [-np.pi, 0.0, np.pi / 2], out["surf_tcp_pos"][0], out["surf_tcp_rpy"][0], [0.004, -0.003, 0.001], [0.01, 0.02, -0.2])
+    e = bare(SurfAuto, _pb=PB(), robot=types.SimpleNamespace(arm=arm), surface_array=surface_array, surface_normals=nrm, x_bins=sv.x_bins, y_bins=sv.y_bins,
+             num_heightfield_rows=64, num_heightfield_cols=64, goal_pos_workframe=arm.worldframe_to_workframe(goal, [0, 0, 0])[0])
+    e.tip_i, e.tip_j = e.xy_to_surface_idx(out["surf_tcp_pos"][0][0], out["surf_tcp_pos"][0][1])
+    out["surf_oracle_tcp"] = np.concatenate([out["surf_tcp_pos"][0], out["surf_tcp_rpy"][0], [0.004, -0.003, 0.001], [0.01, 0.02, -0.2]])
+    out["surf_oracle_obs"] = np.array(e.get_oracle_obs(), dtype=np.float64)
 
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
