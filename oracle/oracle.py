@@ -220,6 +220,18 @@ def depth_image(eye, fwd, up, right, fov, near, far, S, tris):
     return out
 
 
+def postprocess(cur_depth, refimg, border_on=True):
+    """t_s_camera's arithmetic (tactile_sensor.py:268-292) on a given float32 depth image"""
+    dep, gray, mask = refimg
+    S = dep.shape[0]
+    cur = np.ascontiguousarray(cur_depth, dtype=np.float32)
+    img = np.zeros((S, S), dtype=np.uint8)
+    lib().or_postprocess(C.c_int(S), cur.ctypes.data_as(C.POINTER(C.c_float)), dep.ctypes.data_as(C.POINTER(C.c_float)),
+                         gray.ctypes.data_as(C.POINTER(C.c_float)), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(int(border_on)),
+                         img.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return img
+
+
 def tactile_image(m, q, S, tris_world, refimg, border_on=True, want_depth=False):
     q = np.ascontiguousarray(q, dtype=np.float64)
     tris = np.ascontiguousarray(tris_world, dtype=np.float64).reshape(-1, 9)

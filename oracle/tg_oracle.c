@@ -993,15 +993,11 @@ void or_depth_image(const double eye[3], const double fwd[3], const double up[3]
 }
 
 /* TactileSensor.t_s_camera (tactile_sensor.py:261-294), float32 arithmetic like numpy */
-void or_tactile_image(const OrModel* m, const double* q, int S, const double* tris_world, int ntri,
-                      const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
-                      int border_on, unsigned char* img_out, float* depth_out)
+/* TactileSensor.t_s_camera's arithmetic (tactile_sensor.py:268-292) on a given depth image, float32 as numpy does it:
+ * diff = cur - nodef; |diff| <= 1e-4 -> 0; uint8(clip(|diff|, 0, 0.05) / 0.05 * 255); border pixels take the baked grey. */
+void or_postprocess(int S, const float* cur, const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
+                    int border_on, unsigned char* img_out)
 {
-    double eye[3], fwd[3], up[3], right[3];
-    or_camera_frame(m, q, eye, fwd, up, right);
-    float* cur = (float*)malloc(sizeof(float) * (size_t)S * S);
-    memcpy(cur, nodef_dep, sizeof(float) * (size_t)S * S);
-    raster_tris_d(eye, fwd, up, right, m->fov_deg, m->near_, m->far_, S, tris_world, ntri, cur);
     const float eps = (float)1e-4, maxpen = (float)0.05;
     for (int i = 0; i < S * S; i++) {
         float diff = cur[i] - nodef_dep[i];
@@ -1012,8 +1008,20 @@ void or_tactile_image(const OrModel* m, const double* q, int S, const double* tr
         unsigned char o = (unsigned char)val;
         if (border_on && border_mask[i] == 1) o = (unsigned char)nodef_gray[i];
         img_out[i] = o;
-        if (depth_out) depth_out[i] = cur[i];
     }
+}
+
+void or_tactile_image(const OrModel* m, const double* q, int S, const double* tris_world, int ntri,
+                      const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
+                      int border_on, unsigned char* img_out, float* depth_out)
+{
+    double eye[3], fwd[3], up[3], right[3];
+    or_camera_frame(m, q, eye, fwd, up, right);
+    float* cur = (float*)malloc(sizeof(float) * (size_t)S * S);
+    memcpy(cur, nodef_dep, sizeof(float) * (size_t)S * S);
+    raster_tris_d(eye, fwd, up, right, m->fov_deg, m->near_, m->far_, S, tris_world, ntri, cur);
+    or_postprocess(S, cur, nodef_dep, nodef_gray, border_mask, border_on, img_out);
+    if (depth_out) memcpy(depth_out, cur, sizeof(float) * (size_t)S * S);
     free(cur);
 }
 

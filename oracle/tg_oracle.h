@@ -130,6 +130,8 @@ void or_tactile_image(const OrModel* m, const double* q, int S, const double* tr
                       const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
                       int border_on, unsigned char* img_out, float* depth_out);
 /* depth image only (no nodef composite): background = 1.0 (far plane).  Used by the fixture KAT. */
+void or_postprocess(int S, const float* cur, const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
+                    int border_on, unsigned char* img_out);
 void or_depth_image(const double eye[3], const double fwd[3], const double up[3], const double right[3],
                     double fov_deg, double near_, double far_, int S, const float* tris, int ntri, float* depth_out);
 

@@ -253,3 +253,39 @@ def test_edge_and_surface_oracle_observations(oracle, monkeypatch):
     s.step_data()
     got, want = s.oracle_obs(), GOLD["surf_oracle_obs"]
     assert got.shape == want.shape == (20,) and np.allclose(got, want, atol=1e-12), np.abs(got - want).max()
+
+
+SENSOR_CASES = [("tactip", "standard", 64, False), ("tactip", "standard", 128, False), ("tactip", "flat", 128, False),
+                ("digit", "standard", 128, False), ("digitac", "right_angle", 128, True), ("tactip", "standard", 256, False)]
+
+
+@pytest.mark.parametrize("name,typ,S,border_off", SENSOR_CASES)
+def test_sensor_camera_rig_and_postprocess(oracle, name, typ, S, border_off):
+    """TactileSensor.setup_camera_info / update_cam_frame / get_imgs / t_s_camera (sensors/tactile_sensor.py:127-294) run from
+    the reference's source: the camera pose relative to the sensor body, and the depth -> uint8 arithmetic on a synthetic depth"""
+    key = "sensor_%s_%s_%d" % (name, typ, S)
+    cam = GOLD[key + "_cam"]
+    eye0, target0, up0, (fov, focal, near, far) = cam[0:3], cam[3:6], cam[6:9], cam[9:13]
+    m = oracle.load_model("ur5", name, typ, [0.65, 0.0, 0.035], [-np.pi, 0.0, np.pi / 2], np.zeros((6, 2)))
+    assert (m.fov_deg, m.near_, m.far_) == (fov, near, far) and abs(m.focal_dist - focal) < 1e-15
+    fwd0 = (target0 - eye0) / np.linalg.norm(target0 - eye0)
+    assert abs(np.linalg.norm(target0 - eye0) - focal) < 1e-12 and abs(np.dot(fwd0, up0)) < 1e-12
+    rng = np.random.RandomState(S)
+    for k in range(3):
+        q = rng.uniform(-1.0, 1.0, m.ndof)
+        P, Q = oracle.link_states(m, q)           # getLinkState()[0:2]: the body link's INERTIAL frame (tactile_sensor.py:153-155)
+        Pb, Rb = P[m.body_link], oracle.mat_from_quat(Q[m.body_link])
+        e, f, u, r = oracle.camera_frame(m, q)
+        assert np.allclose(e, Pb + Rb @ eye0, atol=1e-12) and np.allclose(f, Rb @ fwd0, atol=1e-12) and np.allclose(u, Rb @ up0, atol=1e-12)
+        assert np.allclose(r, np.cross(f, u), atol=1e-12)
+    # t_s_camera on the synthetic depth, with OUR copy of the fixture images: equal bytes wherever the segmentation mask did not
+    # flag the sensor body; flagged pixels are zeroed by the reference and then take the border grey where the border is on
+    ref = oracle.load_refimg(name, typ, S)
+    got = oracle.postprocess(GOLD[key + "_cur"], ref, border_on=not border_off)
+    want, body = GOLD[key + "_img"], GOLD[key + "_seg_body"]
+    assert np.array_equal(got[~body], want[~body])
+    dep, gray, mask = ref
+    expect_body = np.where((mask == 1) & (not border_off), gray.astype(np.uint8), 0)
+    assert np.array_equal(want[body], expect_body[body])
+    free = (~body) & ((mask == 0) | border_off)
+    assert (want[free] == 255).sum() > 10 and (want[free] == 0).sum() > 10 and len(np.unique(want[free])) > 50     # clip, dead band, ramp

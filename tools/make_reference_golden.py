@@ -357,6 +357,39 @@ def main():
     out["surf_oracle_tcp"] = np.concatenate([out["surf_tcp_pos"][0], out["surf_tcp_rpy"][0], [0.004, -0.003, 0.001], [0.01, 0.02, -0.2]])
     out["surf_oracle_obs"] = np.array(e.get_oracle_obs(), dtype=np.float64)
 
+    # ---- I. TactileSensor (R8, R9): the camera rig relative to the sensor body (update_cam_frame + get_imgs's vectors, with the
+    # body at the identity pose) and t_s_camera on a synthetic depth image: the reference's own fixture images, load_reference_images
+    # as written, a depth = nodef_dep with dents / noise that exercise the 1e-4 dead band, the 0.05 clip and the uint8 truncation
+    assets = os.path.join(REF, "tactile_gym", "assets")
+    TactileSensor = ref_class(os.path.join(REF, "tactile_gym", "sensors", "tactile_sensor.py"), "TactileSensor",
+                              extra={"os": os, "add_assets_path": lambda p: os.path.join(assets, p)})
+    for name, typ, S, border_off in (("tactip", "standard", 64, False), ("tactip", "standard", 128, False), ("tactip", "flat", 128, False),
+                                     ("digit", "standard", 128, False), ("digitac", "right_angle", 128, True), ("tactip", "standard", 256, False)):
+        pb = PB()
+        captured = {}
+        pb.getLinkState = lambda *a, **k: ((0.0, 0.0, 0.0), (0.0, 0.0, 0.0, 1.0), None, None, None, None)
+        pb.computeProjectionMatrixFOV = lambda fov, aspect, near, far: (fov, aspect, near, far)
+        pb.computeViewMatrix = lambda eye, target, up: captured.update(eye=np.array(eye), target=np.array(target), up=np.array(up)) or "view"
+        pb.ER_SEGMENTATION_MASK_OBJECT_AND_LINKINDEX, pb.ER_BULLET_HARDWARE_OPENGL = 1, 2
+        ts = bare(TactileSensor, _pb=pb, robot_id=4, tactile_link_ids={"body": 9, "tip": 10}, t_s_name=name, t_s_type=typ, image_size=[S, S],
+                  turn_off_border=border_off)
+        ts.load_reference_images()
+        ts.setup_camera_info()
+        nd = ts.no_deformation_dep.astype(np.float32)
+        cur = nd.copy()
+        yy, xx = np.mgrid[0:S, 0:S]
+        cur -= (0.06 * np.exp(-((xx - 0.4 * S) ** 2 + (yy - 0.55 * S) ** 2) / (0.02 * S * S))).astype(np.float32)     # a dent deeper than the clip
+        cur += rng.uniform(-2.5e-4, 2.5e-4, (S, S)).astype(np.float32)                                               # around the 1e-4 dead band
+        cur[: S // 8] += np.float32(0.013)                                                                           # behind the skin: |diff| counts too
+        seg = np.full((S, S), -1, dtype=np.int64)
+        seg[-(S // 16):, :] = 4 + ((9 + 1) << 24)                                                                     # rows where the sensor body is seen
+        pb.getCameraImage = lambda w, h, view, proj, renderer=None, flags=None: (w, h, np.zeros((h, w, 4), np.uint8), cur.copy(), seg.copy())
+        img = ts.t_s_camera()
+        key = "sensor_%s_%s_%d" % (name, typ, S)
+        out[key + "_cam"] = np.concatenate([captured["eye"], captured["target"], captured["up"], [ts.fov, ts.focal_dist, ts.nearplane, ts.farplane]])
+        out[key + "_cur"], out[key + "_seg_body"], out[key + "_img"] = cur, (seg >= 0), img
+        assert img.dtype == np.uint8 and img.shape == (S, S)
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
