@@ -289,3 +289,32 @@ def test_sensor_camera_rig_and_postprocess(oracle, name, typ, S, border_off):
     assert np.array_equal(want[body], expect_body[body])
     free = (~body) & ((mask == 0) | border_off)
     assert (want[free] == 255).sum() > 10 and (want[free] == 0).sum() > 10 and len(np.unique(want[free])) > 50     # clip, dead band, ramp
+
+
+@pytest.mark.parametrize("arm,sensor", [("ur5", "tactip"), ("mg400", "digitac")])
+def test_tcp_velocity_control_targets(oracle, arm, sensor):
+    """tcp_velocity_control (base_robot_arm.py:281-332; mg400.py:77-129) run from the reference source on stored kinematic inputs:
+    limit handling, work -> world twist, Jacobian stacking, inverse / pseudo-inverse, MG400 slaving -> joint velocity targets"""
+    import ctypes as C
+
+    g = lambda n: GOLD["velctl_%s_%s" % (arm, n)]
+    wpos = [0.33, 0.0, 0.035] if arm == "mg400" else [0.65, 0.0, 0.035]
+    m = oracle.load_model(arm, sensor, "standard", wpos, [-np.pi, 0.0, np.pi / 2], g("lims"))
+    n = m.ndof
+    capped = 0
+    for q, v, J, pose, want in zip(g("q"), g("v"), g("J"), g("pose"), g("target")):
+        P, Q = oracle.link_states(m, q)                     # the stored inputs still are the oracle's kinematics
+        assert np.allclose(np.concatenate([P[m.tcp_link], Q[m.tcp_link]]), pose, atol=1e-12)
+        assert np.allclose(oracle.jacobian(m, q, m.tcp_link), J, atol=1e-12)
+        s = oracle.OrState()
+        for i in range(n):
+            s.q[i] = q[i]
+        vv = np.ascontiguousarray(v, dtype=np.float64)
+        oracle.lib().or_tcp_velocity_control(C.byref(m), C.byref(s), vv.ctypes.data_as(C.POINTER(C.c_double)))
+        got = np.array(s.target_vel[:n])
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-12), (np.abs(got - want).max(), got, want)
+        assert all(s.motor_mode[i] == 0 and s.max_force[i] == 1000.0 and s.kd[i] == 1.0 for i in range(n))
+        p, r = oracle.tcp_pose_workframe(m, q)
+        cur = np.concatenate([p, r])
+        capped += int(np.any(((cur < g("lims")[:, 0]) & (v < 0)) | ((cur > g("lims")[:, 1]) & (v > 0))))
+    assert capped >= 2          # the vectors do exercise check_TCP_vel_lims

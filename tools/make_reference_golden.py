@@ -390,6 +390,46 @@ def main():
         out[key + "_cur"], out[key + "_seg_body"], out[key + "_img"] = cur, (seg >= 0), img
         assert img.dtype == np.uint8 and img.shape == (S, S)
 
+    # ---- J. tcp_velocity_control (R3) run from the reference source (BaseRobotArm for the ur5, MG400's override): check_TCP_vel_lims,
+    # work -> world twist, [jac_t; jac_r] stacking, matrix_rank -> inv / pinv, the MG400's slaved joints.  The kinematic INPUTS
+    # (TCP pose, Jacobian at the TCP link's inertial frame) come from the oracle for the arm at hand and are stored, so the replay
+    # first checks that they still are what the oracle computes, then compares the joint-velocity targets.
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import oracle as O
+    O.build()
+    MG400 = ref_class(os.path.join(REF, "tactile_gym", "robots", "arms", "mg400", "mg400.py"), "MG400", (BaseRobotArm,))
+    for arm_name, sensor, typ, cls in (("ur5", "tactip", "standard", BaseRobotArm), ("mg400", "digitac", "standard", MG400)):
+        wpos_, wrpy_ = ([0.33, 0.0, 0.035] if arm_name == "mg400" else [0.65, 0.0, 0.035]), [-np.pi, 0.0, np.pi / 2]
+        lims = np.array([[-0.01, 0.01], [-0.02, 0.02], [-0.1, 0.1], [0.0, 0.0], [0.0, 0.0], [-0.5, 0.5]])
+        m = O.load_model(arm_name, sensor, typ, wpos_, wrpy_, lims)
+        rest = O.rest_pose("edge_follow", arm_name, sensor, typ, m)
+        n = m.ndof
+        qs, vels, Js, poses, targets = [], [], [], [], []
+        for k in range(8):
+            q = np.array(rest[:n]) + rng.uniform(-0.15, 0.15, n) * (1.0 if arm_name == "ur5" else 0.3)
+            if arm_name == "mg400":      # keep the parallelogram closed (mg400.py:111-120)
+                q[n - 3], q[n - 2], q[n - 1] = q[1], -q[1], q[1] + q[2]
+            P, Q = O.link_states(m, q)
+            J = O.jacobian(m, q, m.tcp_link)
+            v = rng.uniform(-0.01, 0.01, 6) * np.array([1, 1, 1, 5, 5, 5])
+            pb = PB()
+            sent = {}
+            pb.calculateJacobian = lambda *a, J=J: (J[:3].tolist(), J[3:].tolist())
+            pb.setJointMotorControlArray = lambda *a, **kw: sent.update(kw)
+            pb.VELOCITY_CONTROL = 0
+            arm = bare(cls, _pb=pb, robot_id=0, TCP_link_id=0, num_control_dofs=n, control_joint_ids=list(range(n)), vel_gain=1.0, max_force=1000.0,
+                       robot_type="MG400")
+            arm.set_workframe(wpos_, wrpy_)
+            arm.set_TCP_lims(lims)
+            arm.get_current_TCP_pos_vel_worldframe = lambda P=P, Q=Q: (P[m.tcp_link], np.array(PB.getEulerFromQuaternion(Q[m.tcp_link])), Q[m.tcp_link], np.zeros(3), np.zeros(3))
+            arm.get_current_joint_pos_vel = lambda q=q: (list(q), [0.0] * n)
+            arm.tcp_velocity_control(v)
+            qs.append(q); vels.append(v); Js.append(J); poses.append(np.concatenate([P[m.tcp_link], Q[m.tcp_link]])); targets.append(np.array(sent["targetVelocities"], dtype=np.float64))
+            assert sent["forces"] == [1000.0] * n and sent["velocityGains"] == [1.0] * n
+        out["velctl_%s_lims" % arm_name] = lims
+        out["velctl_%s_q" % arm_name], out["velctl_%s_v" % arm_name], out["velctl_%s_J" % arm_name] = np.array(qs), np.array(vels), np.array(Js)
+        out["velctl_%s_pose" % arm_name], out["velctl_%s_target" % arm_name] = np.array(poses), np.array(targets)
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
