@@ -878,22 +878,30 @@ int or_robot_reset(const OrModel* m, OrState* s, const double* rest_q, const dou
  * pose delta in the work frame, check_TCP_pos_lims (:349-355), workframe_to_worldframe (:47-60), IK from the current joints,
  * position motors with forces = max_force - then blocking_move(max_steps, constant_vel=None) (robot.py:188-260): the pose
  * error and the joint speeds are read before each step.  Returns the number of simulation steps taken. */
-int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_work[6], int max_steps)
+/* the IK target of tcp_position_control (base_robot_arm.py:233-252): current work-frame pose + delta, check_TCP_pos_lims,
+ * workframe_to_worldframe, getQuaternionFromEuler of the world rpy */
+void or_tcp_position_target(const OrModel* m, const double* q, const double delta_work[6], double tpos[3], double targ_orn[4])
 {
-    int n = m->ndof;
     double pos[3], rpy[3], tp[3], tr[3];
-    or_tcp_pose_workframe(m, s->q, pos, rpy);
+    or_tcp_pose_workframe(m, q, pos, rpy);
     for (int c = 0; c < 3; c++) {
         tp[c] = pos[c] + delta_work[c]; tr[c] = rpy[c] + delta_work[3 + c];
         tp[c] = tp[c] < m->tcp_lims[c][0] ? m->tcp_lims[c][0] : (tp[c] > m->tcp_lims[c][1] ? m->tcp_lims[c][1] : tp[c]);
         tr[c] = tr[c] < m->tcp_lims[3 + c][0] ? m->tcp_lims[3 + c][0] : (tr[c] > m->tcp_lims[3 + c][1] ? m->tcp_lims[3 + c][1] : tr[c]);
     }
-    double wq[4], tq[4], tpos[3], tquat[4], trpy[3], targ_orn[4], targ_j[OR_MAXD];
+    double wq[4], tq[4], tquat[4], trpy[3];
     workframe_quat(m, wq);
     or_quat_from_euler(tr, tq);
     or_mul_transforms(m->workframe_pos, wq, tp, tq, tpos, tquat);
     or_euler_from_quat(tquat, trpy);
     or_quat_from_euler(trpy, targ_orn);
+}
+
+int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_work[6], int max_steps)
+{
+    int n = m->ndof;
+    double tpos[3], targ_orn[4], targ_j[OR_MAXD];
+    or_tcp_position_target(m, s->q, delta_work, tpos, targ_orn);
     or_inverse_kinematics(m, s->q, tpos, targ_orn, targ_j);
     for (int i = 0; i < n; i++) {
         s->motor_mode[i] = 1; s->target_pos[i] = targ_j[i]; s->target_vel[i] = 0;

@@ -117,6 +117,7 @@ void or_apply_action(const OrModel* m, OrState* s, const double vels_work[6], in
  * returns number of substeps used */
 int or_robot_reset(const OrModel* m, OrState* s, const double* rest_q, const double tcp_pos_work[3], const double tcp_rpy_work[3]);
 /* pb.calculateInverseKinematics(..., maxNumIterations=100, residualThreshold=1e-8) (base_robot_arm.py:201-209) */
+void or_tcp_position_target(const OrModel* m, const double* q, const double delta_work[6], double tpos[3], double targ_orn[4]);
 int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_work[6], int max_steps);
 void or_inverse_kinematics(const OrModel* m, const double* q0, const double target_pos[3], const double target_quat[4], double* q_out);
 void or_tcp_pose_workframe(const OrModel* m, const double* q, double pos[3], double rpy[3]);

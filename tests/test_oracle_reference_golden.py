@@ -318,3 +318,21 @@ def test_tcp_velocity_control_targets(oracle, arm, sensor):
         cur = np.concatenate([p, r])
         capped += int(np.any(((cur < g("lims")[:, 0]) & (v < 0)) | ((cur > g("lims")[:, 1]) & (v > 0))))
     assert capped >= 2          # the vectors do exercise check_TCP_vel_lims
+
+
+def test_tcp_position_control_target(oracle):
+    """tcp_position_control (base_robot_arm.py:228-279) run from the reference source: the pose handed to the IK"""
+    import ctypes as C
+
+    m = oracle.load_model("ur5", "tactip", "standard", [0.65, 0.0, 0.035], [-np.pi, 0.0, np.pi / 2], GOLD["posctl_lims"])
+    clipped = 0
+    for q, d, want in zip(GOLD["posctl_q"], GOLD["posctl_delta"], GOLD["posctl_ik_target"]):
+        tpos, torn = np.zeros(3), np.zeros(4)
+        dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+        oracle.lib().or_tcp_position_target(C.byref(m), dp(q), dp(d), tpos.ctypes.data_as(C.POINTER(C.c_double)), torn.ctypes.data_as(C.POINTER(C.c_double)))
+        assert np.allclose(tpos, want[:3], atol=1e-12)
+        assert abs(abs(np.dot(torn, want[3:7])) - 1.0) < 1e-12           # the same rotation (q ~ -q)
+        p, r = oracle.tcp_pose_workframe(m, q)
+        t = np.concatenate([p, r]) + d
+        clipped += int(np.any((t < GOLD["posctl_lims"][:, 0]) | (t > GOLD["posctl_lims"][:, 1])))
+    assert clipped >= 4         # check_TCP_pos_lims is exercised

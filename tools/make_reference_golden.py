@@ -430,6 +430,33 @@ def main():
         out["velctl_%s_q" % arm_name], out["velctl_%s_v" % arm_name], out["velctl_%s_J" % arm_name] = np.array(qs), np.array(vels), np.array(Js)
         out["velctl_%s_pose" % arm_name], out["velctl_%s_target" % arm_name] = np.array(poses), np.array(targets)
 
+    # ---- K. tcp_position_control (base_robot_arm.py:228-279) from the reference source, ur5: pose delta + check_TCP_pos_lims +
+    # workframe_to_worldframe -> the IK target pose (calculateInverseKinematics itself is pybullet's: the stub records its
+    # arguments and returns the current joints), position-motor settings
+    lims = np.array([[-0.004, 0.004], [-0.02, 0.02], [0.002, 0.1], [0.0, 0.0], [0.0, 0.0], [-0.05, 0.05]])
+    m = O.load_model("ur5", "tactip", "standard", [0.65, 0.0, 0.035], [-np.pi, 0.0, np.pi / 2], lims)
+    rest = O.rest_pose("edge_follow", "ur5", "tactip", "standard", m)
+    qs, deltas, ik_targets = [], [], []
+    for k in range(8):
+        q = np.array(rest[:6]) + rng.uniform(-0.02, 0.02, 6)
+        P, Q = O.link_states(m, q)
+        d = rng.uniform(-0.001, 0.001, 6) * np.array([1, 1, 1, 17, 17, 17])
+        pb = PB()
+        got = {}
+        pb.calculateInverseKinematics = lambda rid, link, pos, orn, **kw: got.update(pos=np.array(pos), orn=np.array(orn), kw=kw) or tuple(q)
+        pb.setJointMotorControlArray = lambda *a, **kw: got.update(motor=kw)
+        pb.POSITION_CONTROL = 2
+        arm = bare(BaseRobotArm, _pb=pb, robot_id=0, TCP_link_id=0, num_control_dofs=6, control_joint_ids=list(range(6)), vel_gain=1.0, pos_gain=1.0,
+                   max_force=1000.0, rest_poses=rest)
+        arm.set_workframe([0.65, 0.0, 0.035], [-np.pi, 0.0, np.pi / 2])
+        arm.set_TCP_lims(lims)
+        arm.get_current_TCP_pos_vel_worldframe = lambda P=P, Q=Q: (P[m.tcp_link], np.array(PB.getEulerFromQuaternion(Q[m.tcp_link])), Q[m.tcp_link], np.zeros(3), np.zeros(3))
+        arm.tcp_position_control(d)
+        assert got["kw"]["maxNumIterations"] == 100 and got["kw"]["residualThreshold"] == 1e-8
+        assert got["motor"]["forces"] == [1000.0] * 6 and got["motor"]["positionGains"] == [1.0] * 6 and got["motor"]["targetVelocities"] == [0] * 6
+        qs.append(q); deltas.append(d); ik_targets.append(np.concatenate([got["pos"], got["orn"]]))
+    out["posctl_lims"], out["posctl_q"], out["posctl_delta"], out["posctl_ik_target"] = lims, np.array(qs), np.array(deltas), np.array(ik_targets)
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
