@@ -336,3 +336,79 @@ def test_tcp_position_control_target(oracle):
         t = np.concatenate([p, r]) + d
         clipped += int(np.any((t < GOLD["posctl_lims"][:, 0]) | (t > GOLD["posctl_lims"][:, 1])))
     assert clipped >= 4         # check_TCP_pos_lims is exercised
+
+
+# ---------------------------------------------------------------- the RNG call order of reset()
+def _draw_rows(draw_fn, seed, rounds=3):
+    from tactile_gym_b200 import seeding
+
+    return draw_fn(seeding.np_random(int(seed))[0], rounds)
+
+
+def test_reset_draw_order_matches_the_reference(oracle):
+    """Each env's reset() run from the reference source with a recording RandomState (tools/make_reference_golden.py, section L)
+    against the engine's host-side draw functions and the oracle envs' own draws: same stream, same order, same ranges."""
+    from tactile_gym_b200 import engine as E
+
+    base = {"control_mode": "TCP_velocity_control", "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5"}
+    g = lambda k: (GOLD["draws_" + k], int(GOLD["draws_%s_seed" % k][0]))
+    # edge_follow: [embed_dist,] edge_ang
+    for sensor in ("tactip", "digit", "digitac"):
+        want, seed = g("edge_" + sensor)
+        cfg, _ = E.edge_follow_config(dict(base, movement_mode="xy", noise_mode="rand_height", tactile_sensor_name=sensor), [64, 64], 200, 1)
+        assert np.allclose(_draw_rows(E.edge_follow_draws(cfg.task), seed), want, rtol=0, atol=1e-15)
+        o = oracle.EdgeFollowOracle(image_size=64, sensor=sensor, seed=seed)
+        assert np.allclose([o.draw() for _ in range(3)], want, rtol=0, atol=1e-15)
+    want, seed = g("edge_fixed")
+    cfg, _ = E.edge_follow_config(dict(base, movement_mode="xy", noise_mode="fixed_height", tactile_sensor_name="tactip"), [64, 64], 200, 1)
+    rows = _draw_rows(E.edge_follow_draws(cfg.task), seed)
+    assert np.allclose(rows[:, 1:], want, rtol=0, atol=1e-15) and np.all(rows[:, 0] == 0.0035)
+    # surface_follow: [OpenSimplex seed,] goal angle | +-1
+    for key, fn, mode, noise in (("surface_xyzRxRy", E.surface_follow_config, "xyzRxRy", "simplex"), ("surface_yzRx", E.surface_follow_config, "yzRx", "simplex"),
+                                 ("surface_xyz_none", E.surface_follow_config, "xyz", "none"), ("surface_vert_xRz", E.surface_follow_vert_config, "xRz", "simplex")):
+        want, seed = g(key)
+        _, _, draw = fn(dict(base, movement_mode=mode, noise_mode=noise, tactile_sensor_name="tactip"), [64, 64], 200, 1)
+        rows = _draw_rows(draw, seed)
+        assert np.allclose(rows if noise == "simplex" else rows[:, 1:], want, rtol=0, atol=1e-15), key
+        variant = "vert" if "vert" in key else "auto"
+        o = oracle.SurfaceFollowOracle(image_size=64, sensor="tactip", movement_mode=mode, variant=variant, noise_mode=noise, seed=seed, render=False)
+        got = np.array([o.draw() for _ in range(3)])
+        assert np.allclose(got if noise == "simplex" else got[:, 1:], want, rtol=0, atol=1e-15), key
+    # object_balance: [gravity] [embed] choice rand choice rand -> gravity, embed, fx, fy
+    for key, rg, re_ in (("balance_rand", True, True), ("balance_fixed", False, False), ("balance_gravity_only", True, False)):
+        want, seed = g(key)
+        _, _, draw = E.object_balance_config(dict(base, movement_mode="xy", object_mode="pole", rand_gravity=rg, rand_embed_dist=re_, tactile_sensor_name="tactip"),
+                                             [64, 64], 250, 1)
+        rows = _draw_rows(draw, seed)
+        k = 0
+        if rg:
+            assert np.allclose(rows[:, 0], want[:, k], rtol=0, atol=1e-15); k += 1
+        else:
+            assert np.all(rows[:, 0] == -0.1)
+        if re_:
+            assert np.allclose(rows[:, 1], want[:, k], rtol=0, atol=1e-15); k += 1
+        assert np.allclose(rows[:, 2], want[:, k] * want[:, k + 1], rtol=0, atol=1e-15) and np.allclose(rows[:, 3], want[:, k + 2] * want[:, k + 3], rtol=0, atol=1e-15)
+        o = oracle.ObjectBalanceOracle(image_size=64, rand_gravity=rg, rand_embed_dist=re_, seed=seed)
+        got = np.array([oracle.balance_draws(o.np_random, "tactip", rg, re_) for _ in range(3)])
+        assert np.allclose(got[:, 2], rows[:, 2], rtol=0, atol=1e-15) and np.allclose(got[:, 0], rows[:, 0], rtol=0, atol=1e-15)
+    # object_push: [init angle] [mass] OpenSimplex seed | trajectory angle
+    for key, ro, rm, tt in (("push_rand_simplex", True, True, "simplex"), ("push_fixed_simplex", False, False, "simplex"), ("push_rand_straight", True, True, "straight")):
+        want, seed = g(key)
+        _, _, draw = E.object_push_config(dict(base, movement_mode="TyRz", rand_init_orn=ro, rand_obj_mass=rm, traj_type=tt, tactile_sensor_name="tactip"),
+                                          [64, 64], 1000, 1)
+        rows = _draw_rows(draw, seed)
+        assert np.allclose(rows if ro else rows[:, 2:], want, rtol=0, atol=1e-15), key
+        o = oracle.ObjectPushOracle(image_size=64, arm="ur5", sensor="tactip", rand_init_orn=ro, rand_obj_mass=rm, traj_type=tt, seed=seed)
+        got = np.array([oracle.push_draws(o.np_random, ro, rm, tt) for _ in range(3)])
+        assert np.allclose(got, rows, rtol=0, atol=1e-15), key
+    # object_roll: [scale] [embed] [dx dy] goal angle, goal distance
+    for key, a_, b_, c_ in (("roll_rand", True, True, True), ("roll_fixed", False, False, False), ("roll_pos_only", False, False, True)):
+        want, seed = g(key)
+        _, _, draw = E.object_roll_config(dict(base, movement_mode="xy", rand_obj_size=a_, rand_embed_dist=b_, rand_init_obj_pos=c_, tactile_sensor_name="tactip"),
+                                          [64, 64], 250, 1)
+        rows = _draw_rows(draw, seed)
+        cols = ([0] if a_ else []) + ([1] if b_ else []) + ([2, 3] if c_ else []) + [4, 5]
+        assert np.allclose(rows[:, cols], want, rtol=0, atol=1e-15), key
+        o = oracle.ObjectRollOracle(image_size=64, rand_obj_size=a_, rand_embed_dist=b_, rand_init_obj_pos=c_, seed=seed)
+        got = np.array([oracle.roll_draws(o.np_random, a_, b_, c_) for _ in range(3)])
+        assert np.allclose(got, rows, rtol=0, atol=1e-15), key

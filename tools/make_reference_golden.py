@@ -457,6 +457,87 @@ def main():
         qs.append(q); deltas.append(d); ik_targets.append(np.concatenate([got["pos"], got["orn"]]))
     out["posctl_lims"], out["posctl_q"], out["posctl_delta"], out["posctl_ik_target"] = lims, np.array(qs), np.array(deltas), np.array(ik_targets)
 
+    # ---- L. the random draws of reset() (R11), in the reference's own call order: each env's reset() run from its source with a
+    # recording proxy around a gym <= 0.21 RandomState (tactile_gym_b200.seeding: RandomState seeded from sha512(str(seed)));
+    # arm, scene and observation calls are no-ops.  The replay compares the engine's host-side draw functions, which must consume
+    # the same stream in the same order for seeded runs to match the reference's.
+    from tactile_gym_b200 import seeding
+
+    class RecRNG:
+        def __init__(self, seed):
+            self.rs, self.log = seeding.np_random(seed)[0], []
+
+        def __getattr__(self, name):
+            f = getattr(self.rs, name)
+
+            def call(*a, **k):
+                r = f(*a, **k)
+                self.log.append(float(r))
+                return r
+            return call
+
+    class ScenePB(PB):
+        def getNumJoints(self, uid):
+            return 1
+
+        def loadURDF(self, *a, **k):
+            return 11
+
+        def createCollisionShape(self, **k):
+            return 12
+
+        def createMultiBody(self, **k):
+            return 13
+
+    def run_resets(key, cls, seed, n_resets=3, extra_globals=None, **attrs):
+        arm = bare(BaseRobotArm, _pb=PB())
+        arm.set_workframe(attrs.get("workframe_pos", [0.65, 0.0, 0.035]), attrs.get("workframe_rpy", [-np.pi, 0.0, np.pi / 2]))
+        arm.get_current_TCP_pos_vel_worldframe = lambda: (np.zeros(3), np.zeros(3), np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3), np.zeros(3))
+        robot = types.SimpleNamespace(arm=arm, reset=lambda **k: None)
+        rec = RecRNG(seed)
+        env = bare(cls, _pb=ScenePB(), robot=robot, np_random=rec, reset_counter=0, reset_limit=10 ** 9, _env_step_counter=0, **attrs)
+        env.get_step_data = lambda: (0.0, False)
+        env.get_observation = lambda: None
+        rows = []
+        for k in range(n_resets):
+            rec.log = []
+            env.reset()
+            rows.append(list(rec.log))
+        assert len({len(r) for r in rows}) == 1
+        out["draws_%s" % key], out["draws_%s_seed" % key] = np.array(rows, dtype=np.float64), np.array([seed])
+
+    for sensor in ("tactip", "digit", "digitac"):
+        run_resets("edge_%s" % sensor, EdgeFollowEnv, 101, noise_mode="rand_height", t_s_name=sensor, edge_pos=[0.65, 0.0, 0.0], edge_len=0.175,
+                   edge_height=0.035, edge_stim_id=0, goal_indicator=1, embed_dist=0.0035)
+    run_resets("edge_fixed", EdgeFollowEnv, 102, noise_mode="fixed_height", t_s_name="tactip", edge_pos=[0.65, 0.0, 0.0], edge_len=0.175,
+               edge_height=0.035, edge_stim_id=0, goal_indicator=1, embed_dist=0.0035)
+    surf_ns = {"OpenSimplex": FakeSimplex}
+    BaseSurfaceEnvR = ref_class(os.path.join(surf, "base_surface_env.py"), "BaseSurfaceEnv", (BaseTactileEnv,), extra=surf_ns)
+    SurfAutoR = ref_class(os.path.join(surf, "surface_follow_auto", "surface_follow_auto_env.py"), "SurfaceFollowAutoEnv", (BaseSurfaceEnvR,))
+    SurfVertR = ref_class(os.path.join(surf, "surface_follow_vert", "surface_follow_vert_env.py"), "SurfaceFollowVertEnv", (BaseSurfaceEnvR,))
+    for key, cls, mode, nmode in (("surface_xyzRxRy", SurfAutoR, "xyzRxRy", "simplex"), ("surface_yzRx", SurfAutoR, "yzRx", "simplex"),
+                                  ("surface_xyz_none", SurfAutoR, "xyz", "none"), ("surface_vert_xRz", SurfVertR, "xRz", "simplex")):
+        e0 = bare(cls, _pb=PB(), noise_mode=nmode, movement_mode=mode, well_designed_pos=[0.65, 0.0, 0.0])
+        e0.setup_surface()
+        run_resets(key, cls, 103, noise_mode=nmode, movement_mode=mode, reward_mode="dense", embed_dist=0.0025, surface_id=1, goal_indicator=2,
+                   workframe_pos=[0.65, 0.0, 0.025], heightfield_data=np.zeros((64, 64)),      # init_surface_and_goal's zeros (:381)
+                   **{k: v for k, v in e0.__dict__.items() if k not in ("_pb", "noise_mode", "movement_mode")})
+    BalanceR = ref_class(os.path.join(obj, "object_balance", "object_balance_env.py"), "ObjectBalanceEnv", (BaseObjectEnv,),
+                         extra={"plot_vector": lambda *a, **k: None})
+    for key, rg, re_ in (("balance_rand", True, True), ("balance_fixed", False, False), ("balance_gravity_only", True, False)):
+        run_resets(key, BalanceR, 104, rand_gravity=rg, rand_embed_dist=re_, t_s_name="tactip", object_mode="pole", obj_id=3, obj_base_width=0.1,
+                   obj_base_height=0.0025, embed_dist=0.0035, init_obj_pos=[0.55, 0.0, 0.35], init_obj_orn=(0, 0, 0, 1), workframe_pos=np.array([0.55, 0.0, 0.35]),
+                   workframe_rpy=np.array([0.0, 0.0, 0.0]), obj_tip_constraint_id=1, update_constraints=lambda: None)
+    PushR = ref_class(os.path.join(obj, "object_push", "object_push_env.py"), "ObjectPushEnv", (BaseObjectEnv,),
+                      extra={"OpenSimplex": FakeSimplex, "os": os})
+    for key, ro, rm, tt in (("push_rand_simplex", True, True, "simplex"), ("push_fixed_simplex", False, False, "simplex"), ("push_rand_straight", True, True, "straight")):
+        run_resets(key, PushR, 105, rand_init_orn=ro, rand_obj_mass=rm, traj_type=tt, obj_id=7, init_obj_pos=[0.55, -0.16, 0.04], traj_n_points=10,
+                   traj_spacing=0.025, traj_max_perturb=0.1, traj_ids=list(range(100, 110)), obj_width=0.08, workframe_pos=np.array([0.55, -0.2, 0.04]))
+    RollR = ref_class(os.path.join(obj, "object_roll", "object_roll_env.py"), "ObjectRollEnv", (BaseObjectEnv,), extra={"add_assets_path": lambda p_: p_})
+    for key, a_, b_, c_ in (("roll_rand", True, True, True), ("roll_fixed", False, False, False), ("roll_pos_only", False, False, True)):
+        run_resets(key, RollR, 106, rand_obj_size=a_, rand_embed_dist=b_, rand_init_obj_pos=c_, default_obj_radius=0.0025, embed_dist=0.0015, obj_id=5,
+                   object_path="sphere.urdf", workframe_rpy=np.array([-np.pi, 0.0, np.pi / 2]), visualise_goal=False)
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
