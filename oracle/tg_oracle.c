@@ -827,6 +827,34 @@ void or_inverse_kinematics(const OrModel* m, const double* q0, const double targ
     }
 }
 
+/* blocking_move's constant-velocity retargeting (robot.py:221-246, from google-ravens): step_j = cur + unit(targ - cur) * cv,
+ * and cv halves (after it was used) once every joint is closer than cv to its target */
+void or_blocking_retarget(int n, const double* q, const double* targ_j, double* cv, double* step_j)
+{
+    double diff[OR_MAXD], nrm = 0;
+    int all_small = 1;
+    for (int i = 0; i < n; i++) { diff[i] = targ_j[i] - q[i]; nrm += diff[i] * diff[i]; }
+    nrm = sqrt(nrm);
+    for (int i = 0; i < n; i++) {
+        double vdir = nrm > 0 ? diff[i] / nrm : 0.0;
+        step_j[i] = q[i] + vdir * *cv;
+        if (!(fabs(diff[i]) < *cv)) all_small = 0;
+    }
+    if (all_small) *cv /= 2;
+}
+
+/* blocking_move's exit test (robot.py:248-259) on the TCP pose and joint speeds read BEFORE the step:
+ * sum |pos error| < 2e-4, quaternion angle < 1e-3, sum |qd| < 0.1 */
+int or_blocking_reached(const double tpos[3], const double targ_orn[4], const double tcp_pos[3], const double tcp_quat[4], const double* qd, int n)
+{
+    double tot = 0, pe = 0, ip = 0;
+    for (int i = 0; i < n; i++) tot += fabs(qd[i]);
+    for (int c = 0; c < 3; c++) pe += fabs(tpos[c] - tcp_pos[c]);
+    for (int c = 0; c < 4; c++) ip += targ_orn[c] * tcp_quat[c];
+    double ca = 2 * ip * ip - 1; ca = ca < -1 ? -1 : (ca > 1 ? 1 : ca);
+    return pe < 2e-4 && acos(ca) < 1e-3 && tot < 0.1;
+}
+
 /* Robot.reset (robot.py:114-125): arm.reset (base_robot_arm.py:17-37) -> tcp_direct_workframe_move (:191-226)
  * -> blocking_move(max_steps=1000, constant_vel=0.001) (robot.py:188-260).  Position motors set inside
  * blocking_move pass no `forces`, so pybullet's default (1e5) applies [EXT]. */
@@ -849,35 +877,21 @@ int or_robot_reset(const OrModel* m, OrState* s, const double* rest_q, const dou
     double cv = 0.001;
     int steps = 0;
     for (int it = 0; it < 1000; it++) {
-        double P[OR_MAXL][3], Q[OR_MAXL][4], diff[OR_MAXD], nrm = 0, curq[OR_MAXD], curqd[OR_MAXD];
+        double P[OR_MAXL][3], Q[OR_MAXL][4], curqd[OR_MAXD], step_j[OR_MAXD];
         or_link_states(m, s->q, P, Q);
-        int all_small = 1;
-        for (int i = 0; i < n; i++) { curq[i] = s->q[i]; curqd[i] = s->qd[i]; diff[i] = targ_j[i] - s->q[i]; nrm += diff[i] * diff[i]; }
-        nrm = sqrt(nrm);
+        for (int i = 0; i < n; i++) curqd[i] = s->qd[i];
+        or_blocking_retarget(n, s->q, targ_j, &cv, step_j);
         for (int i = 0; i < n; i++) {
-            double vdir = nrm > 0 ? diff[i] / nrm : 0.0;
-            s->motor_mode[i] = 1; s->target_pos[i] = curq[i] + vdir * cv; s->target_vel[i] = 0;
+            s->motor_mode[i] = 1; s->target_pos[i] = step_j[i]; s->target_vel[i] = 0;
             s->kp[i] = m->pos_gain; s->kd[i] = m->vel_gain; s->max_force[i] = 100000.0;
-            if (!(fabs(diff[i]) < cv)) all_small = 0;
         }
-        if (all_small) cv /= 2;
         or_step_sim(m, s);
         steps++;
-        double tot = 0, pe = 0, ip = 0;
-        for (int i = 0; i < n; i++) tot += fabs(curqd[i]);
-        for (int c = 0; c < 3; c++) pe += fabs(tpos[c] - P[m->tcp_link][c]);
-        for (int c = 0; c < 4; c++) ip += targ_orn[c] * Q[m->tcp_link][c];
-        double ca = 2 * ip * ip - 1; ca = ca < -1 ? -1 : (ca > 1 ? 1 : ca);
-        double oe = acos(ca);
-        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
+        if (or_blocking_reached(tpos, targ_orn, P[m->tcp_link], Q[m->tcp_link], curqd, n)) break;
     }
     return steps;
 }
 
-/* Robot.apply_action(control_mode="TCP_position_control") (robot.py:156-186): tcp_position_control (base_robot_arm.py:228-279) -
- * pose delta in the work frame, check_TCP_pos_lims (:349-355), workframe_to_worldframe (:47-60), IK from the current joints,
- * position motors with forces = max_force - then blocking_move(max_steps, constant_vel=None) (robot.py:188-260): the pose
- * error and the joint speeds are read before each step.  Returns the number of simulation steps taken. */
 /* the IK target of tcp_position_control (base_robot_arm.py:233-252): current work-frame pose + delta, check_TCP_pos_lims,
  * workframe_to_worldframe, getQuaternionFromEuler of the world rpy */
 void or_tcp_position_target(const OrModel* m, const double* q, const double delta_work[6], double tpos[3], double targ_orn[4])
@@ -909,15 +923,12 @@ int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_wor
     }
     int steps = 0;
     for (int it = 0; it < max_steps; it++) {
-        double P[OR_MAXL][3], Q[OR_MAXL][4], tot = 0, pe = 0, ip = 0;
+        double P[OR_MAXL][3], Q[OR_MAXL][4], curqd[OR_MAXD];
         or_link_states(m, s->q, P, Q);
-        for (int i = 0; i < n; i++) tot += fabs(s->qd[i]);
+        for (int i = 0; i < n; i++) curqd[i] = s->qd[i];
         or_step_sim(m, s);
         steps++;
-        for (int c = 0; c < 3; c++) pe += fabs(tpos[c] - P[m->tcp_link][c]);
-        for (int c = 0; c < 4; c++) ip += targ_orn[c] * Q[m->tcp_link][c];
-        double ca = 2 * ip * ip - 1; ca = ca < -1 ? -1 : (ca > 1 ? 1 : ca);
-        if (pe < 2e-4 && acos(ca) < 1e-3 && tot < 0.1) break;
+        if (or_blocking_reached(tpos, targ_orn, P[m->tcp_link], Q[m->tcp_link], curqd, n)) break;
     }
     return steps;
 }

@@ -115,6 +115,8 @@ void or_tcp_velocity_control(const OrModel* m, OrState* s, const double vels_wor
 void or_apply_action(const OrModel* m, OrState* s, const double vels_work[6], int repeat);
 /* BaseRobotArm.reset + tcp_direct_workframe_move + Robot.blocking_move (robot.py:114-125,188-260).
  * returns number of substeps used */
+void or_blocking_retarget(int n, const double* q, const double* targ_j, double* cv, double* step_j);
+int or_blocking_reached(const double tpos[3], const double targ_orn[4], const double tcp_pos[3], const double tcp_quat[4], const double* qd, int n);
 int or_robot_reset(const OrModel* m, OrState* s, const double* rest_q, const double tcp_pos_work[3], const double tcp_rpy_work[3]);
 /* pb.calculateInverseKinematics(..., maxNumIterations=100, residualThreshold=1e-8) (base_robot_arm.py:201-209) */
 void or_tcp_position_target(const OrModel* m, const double* q, const double delta_work[6], double tpos[3], double targ_orn[4]);

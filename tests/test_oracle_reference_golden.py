@@ -412,3 +412,34 @@ def test_reset_draw_order_matches_the_reference(oracle):
         o = oracle.ObjectRollOracle(image_size=64, rand_obj_size=a_, rand_embed_dist=b_, rand_init_obj_pos=c_, seed=seed)
         got = np.array([oracle.roll_draws(o.np_random, a_, b_, c_) for _ in range(3)])
         assert np.allclose(got, rows, rtol=0, atol=1e-15), key
+
+
+def test_blocking_move_retargeting_and_exit(oracle):
+    """Robot.blocking_move (robot.py:188-260) run from the reference source on an ideal position servo: the commanded joint
+    target of every iteration (constant-velocity retargeting with the halving rule) and the iteration the move ends on (the
+    test reads the pose and joint speeds from BEFORE the step) against the oracle's or_blocking_retarget / or_blocking_reached,
+    the two functions its reset and its position control are built from"""
+    import ctypes as C
+
+    dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+    L = oracle.lib()
+    L.or_blocking_reached.restype = C.c_int
+    m = oracle.load_model("ur5", "tactip", "standard", [0.65, 0.0, 0.035], [-np.pi, 0.0, np.pi / 2], np.zeros((6, 2)))
+    for case in (0, 1):
+        hist, t = GOLD["blocking_%d_hist" % case], GOLD["blocking_%d_target" % case]
+        targ_j, tpos, torn, cv0, max_steps = t[0:6], t[6:9], t[9:13], t[13], int(t[14])
+        cv = C.c_double(cv0)
+        assert len(hist) < max_steps                      # ended on the exit test, not on the step budget
+        for k, row in enumerate(hist):
+            q, qd, cmd = row[0:6].copy(), row[6:12].copy(), row[12:18]
+            if cv0 > 0:
+                step = np.zeros(6)
+                L.or_blocking_retarget(C.c_int(6), dp(q), dp(targ_j), C.byref(cv), step.ctypes.data_as(C.POINTER(C.c_double)))
+                assert np.allclose(step, cmd, rtol=0, atol=1e-15), (case, k)
+            else:
+                assert np.array_equal(cmd, targ_j)          # constant_vel=None: the target set by tcp_position_control stays
+            P, Q = oracle.link_states(m, q)
+            done = L.or_blocking_reached(dp(tpos), dp(torn), dp(P[m.tcp_link]), dp(Q[m.tcp_link]), dp(qd), C.c_int(6))
+            assert bool(done) == (k == len(hist) - 1), (case, k)
+        if cv0 > 0:
+            assert cv.value < cv0                          # the halving rule fired on the way in

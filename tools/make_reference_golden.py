@@ -538,6 +538,41 @@ def main():
         run_resets(key, RollR, 106, rand_obj_size=a_, rand_embed_dist=b_, rand_init_obj_pos=c_, default_obj_radius=0.0025, embed_dist=0.0015, obj_id=5,
                    object_path="sphere.urdf", workframe_rpy=np.array([-np.pi, 0.0, np.pi / 2]), visualise_goal=False)
 
+    # ---- M. Robot.blocking_move (robot.py:188-260, R11) from the reference source, driven by an ideal position servo instead of
+    # pybullet (step_sim: every joint lands on its commanded target): the constant-velocity retargeting, the halving rule and the
+    # exit test on the PRE-step pose / speeds.  Kinematics (TCP pose of a joint vector) from the oracle, as in section J.
+    Robot = ref_class(os.path.join(REF, "tactile_gym", "robots", "arms", "robot.py"), "Robot")
+    m = O.load_model("ur5", "tactip", "standard", [0.65, 0.0, 0.035], [-np.pi, 0.0, np.pi / 2], np.zeros((6, 2)))
+    rest = np.array(O.rest_pose("edge_follow", "ur5", "tactip", "standard", m)[:6])
+    for case, (cv, max_steps, dq) in enumerate(((0.001, 1000, np.array([0.004, -0.003, 0.0025, 0.001, -0.0015, 0.002])),
+                                               (None, 10, np.array([0.0004, -0.0003, 0.00025, 0.0001, -0.00015, 0.0002])))):
+        targ_j = rest + dq
+        Pt, Qt = O.link_states(m, targ_j)
+        state = {"q": rest.copy(), "qd": np.zeros(6), "cmd": targ_j.copy()}
+        hist = []
+
+        def tcp_world():
+            P, Q = O.link_states(m, state["q"])
+            return P[m.tcp_link], np.array(PB.getEulerFromQuaternion(Q[m.tcp_link])), Q[m.tcp_link], np.zeros(3), np.zeros(3)
+
+        def set_motors(rid, ids, mode, targetPositions=None, **kw):
+            state["cmd"] = np.array(targetPositions, dtype=np.float64)
+
+        def step_sim():
+            hist.append(np.concatenate([state["q"], state["qd"], state["cmd"]]))
+            new = state["cmd"].copy()
+            state["qd"], state["q"] = (new - state["q"]) * 240.0, new
+
+        pb = PB(); pb.setJointMotorControlArray = set_motors; pb.POSITION_CONTROL = 2
+        arm = types.SimpleNamespace(target_pos_worldframe=Pt[m.tcp_link], target_orn_worldframe=Qt[m.tcp_link], target_joints=targ_j,
+                                    get_current_TCP_pos_vel_worldframe=tcp_world, get_current_joint_pos_vel=lambda: (state["q"].copy(), state["qd"].copy()),
+                                    control_joint_ids=list(range(6)), num_control_dofs=6, pos_gain=1.0, vel_gain=1.0, robot_id=0)
+        rb = bare(Robot, _pb=pb, arm=arm, robot_id=0)
+        rb.step_sim = step_sim
+        rb.blocking_move(max_steps=max_steps, constant_vel=cv)
+        out["blocking_%d_hist" % case] = np.array(hist)               # per iteration: q, qd before the step, commanded joint target
+        out["blocking_%d_target" % case] = np.concatenate([targ_j, Pt[m.tcp_link], Qt[m.tcp_link], [cv if cv is not None else -1.0, max_steps]])
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
