@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  The product package never imports this module.
 
-Parity status: raster + kinematics pinned by the reference's fixtures; dynamics PARITY UNPINNED
+Parity status: raster + kinematics pinned by the reference's fixtures; the reference's own Python around its native calls pinned
+by vectors computed by running its source (tests/golden/reference_numpy.npz); pybullet's dynamics / IK / contacts PARITY UNPINNED
 (pybullet not available) - see oracle/tg_oracle.h.
 """
 import ctypes as C

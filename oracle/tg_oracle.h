@@ -9,6 +9,12 @@
  *                                   (tests/test_oracle_raster.py).
  *   kinematics                    : pinned by the reference's rest_poses <-> workframe design
  *                                   identities (tests/test_oracle_kinematics.py).
+ *   the reference's own Python    : pinned by vectors computed by RUNNING THE REFERENCE'S SOURCE (tools/make_reference_golden.py
+ *   around the native calls         compiles its class bodies; tests/golden/reference_numpy.npz; tests/test_oracle_reference_golden.py):
+ *                                   action encoding / scaling, work-frame transforms, tcp_velocity_control (UR5, MG400),
+ *                                   tcp_position_control's IK target, blocking_move's retargeting / exit test, rewards and
+ *                                   terminations of all tasks, surface lookups, push trajectories, sensor camera rig and
+ *                                   t_s_camera, get_oracle_obs, the RNG call order of reset().
  *   dynamics (stepSimulation, IK) : PARITY UNPINNED.  The arithmetic lives in `pybullet`
  *                                   (requirements.txt:6, ">=3.1.0", not vendored, not installed).
  *                                   Restated from the published Bullet3 btMultiBody algorithm
