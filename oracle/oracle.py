@@ -798,9 +798,9 @@ class ObjectPushOracle:
         a45 = 45 * np.pi / 180
         if arm == "mg400":   # object_push_env.py:72-88
             if sensor == "tactip":
-                raise NotImplementedError("mg400 + tactip uses the mini_right_angle sensor, which is not compiled")
+                self.typ = "mini_right_angle"                                          # :84-86
             lims[0], lims[1], lims[5] = (0.0, 0.3), (-0.1, 0.08), (-a45, a45)
-            wd = np.array([0.25, -0.1, self.obj_h / 2])
+            wd = np.array([0.30 if sensor == "tactip" else 0.25, -0.1, self.obj_h / 2])   # :82-88
         else:                # :89-101
             lims[0], lims[1], lims[5] = (0.0, 0.3), (-0.1, 0.1), (-a45, a45)
             wd = np.array([0.55, -0.20, self.obj_h / 2])

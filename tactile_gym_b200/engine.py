@@ -385,7 +385,7 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
         raise ValueError("Incorrect movement_mode specified: {}".format(movement_mode))
     typ = "right_angle"                                                                    # :58
     if arm_type == "mg400" and sensor == "tactip":
-        raise NotImplementedError("mg400 + tactip pushes with the mini_right_angle TacTip (:84-86), which is not compiled")
+        typ = "mini_right_angle"                                                           # :84-86 (the reference's own PPO set-up)
     S = int(image_size[0])
     mj = scene.load_model_json(arm_type, sensor, typ)
     sj = scene.load_sensor_json(sensor, typ)
@@ -411,7 +411,7 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     a45 = 45 * np.pi / 180
     if arm_type == "mg400":                                                                      # :72-88
         lims = [(0.0, 0.3), (-0.1, 0.08), (0.0, 0.0), (0.0, 0.0), (0.0, 0.0), (-a45, a45)]
-        wd = [0.25, -0.1, obj_h / 2]
+        wd = [0.30 if sensor == "tactip" else 0.25, -0.1, obj_h / 2]                             # :82-88
     else:                                                                                        # :89-101
         lims = [(0.0, 0.3), (-0.1, 0.1), (0.0, 0.0), (0.0, 0.0), (0.0, 0.0), (-a45, a45)]
         wd = [0.55, -0.20, obj_h / 2]

@@ -160,5 +160,29 @@ def test_push_config_tables():
 
     with pytest.raises(ValueError):
         object_push_config(dict(modes, traj_type="zigzag"), [64, 64], 10, 1)
-    with pytest.raises(NotImplementedError):
-        object_push_config(dict(modes, tactile_sensor_name="tactip"), [64, 64], 10, 1)
+    # MG400 + TacTip = the mini_right_angle sensor, workframe 5 cm further out (object_push_env.py:82-86)
+    cfg2, keep2, _ = object_push_config(dict(modes, tactile_sensor_name="tactip"), [128, 128], 10, 1)
+    assert abs(cfg2.task.workframe_pos[0] - 0.30) < 1e-15 and cfg2.n_tip_hull == 1089 and cfg2.sensor.fov_deg == 60
+    assert abs(cfg2.task.push_tip_k - 50) < 1e-9 and abs(cfg2.task.push_tip_d - 100.1) < 1e-12
+
+
+def test_mg400_mini_tactip_push(oracle):
+    """object_push's MG400 + TacTip pairing (object_push_env.py:82-86: the mini_right_angle sensor, workframe x = 0.30) - the
+    reference's own PPO set-up (sb3_helpers/params/object_push_params.py).  The 4-dof arm cannot reach the commanded
+    orientation to blocking_move's 1e-3 rad (0.0014 rad is left), so the reset runs its full 1000 substeps (robot.py:188-260
+    has no other exit); then the tip pushes the cube along the trajectory and the goals advance."""
+    # (image size 128 as in the reference's set-up: its 64 / 256 fixtures for this sensor type were captured with the
+    # right_angle camera - nodef depths 0.51+ instead of 0.0003+ - and show nothing)
+    e = oracle.ObjectPushOracle(image_size=128, arm="mg400", sensor="tactip", seed=3)
+    e.reset()
+    assert e.typ == "mini_right_angle" and abs(e.workframe_pos[0] - 0.30) < 1e-15
+    assert e.last_reset_substeps == 1000
+    p, r = oracle.tcp_pose_workframe(e.m, np.array(e.s.q[: e.m.ndof]))
+    assert np.abs(p).max() < 2e-4 and 1e-3 < np.linalg.norm(r) < 2e-3
+    y0 = e.o.pos[1]
+    touched = 0
+    for k in range(32):
+        o, rew, done, _ = e.step(np.array([0.0, 0.0], np.float32))
+        touched = max(touched, int((o["tactile"][..., 0][e.ref[2] == 0] > 0).sum()))
+    assert e.o.pos[1] - y0 > 0.02 and abs(e.o.pos[2] - 0.04) < 1e-3      # pushed 2+ cm along the work frame's x, still flat on the table
+    assert touched > 100 and e.targ >= 1 and not done

@@ -339,6 +339,7 @@ ROBOTS = [
     ("mg400", "digit", "standard"),
     ("mg400", "digitac", "standard"),
     ("mg400", "tactip", "right_angle"),
+    ("mg400", "tactip", "mini_right_angle"),   # object_push's MG400 + TacTip (object_push_env.py:84-86): the reference's own PPO set-up
     ("mg400", "digit", "right_angle"),
     ("mg400", "digitac", "right_angle"),
 ]
