@@ -42,12 +42,7 @@ def _set_goal(ref, g):
     ("mg400", "digitac", 128, "TyRz", "simplex", False, "dense"),      # BASELINE config 4
     ("ur5", "tactip", 64, "yRz", "straight", True, "dense"),
     ("ur5", "digit", 128, "TxTyRz", "simplex", True, "sparse"),
-    # the reference's own PPO set-up (sb3_helpers/params/object_push_params.py): MG400 + the mini_right_angle TacTip.  The model was
-    # compiled after the round's GPU budget was spent: the oracle side is tested on the CPU (tests/test_oracle_push.py), the
-    # kernels are the MG400 / push instantiation verified by the first case, but this case itself has not run on a GPU yet -
-    # hence a non-strict xfail, to be dropped after its first green run.
-    pytest.param("mg400", "tactip", 128, "TyRz", "simplex", False, "dense",
-                 marks=pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent; not yet run on a GPU")),
+    ("mg400", "tactip", 128, "TyRz", "simplex", False, "dense"),      # the reference's own PPO set-up: MG400 + mini_right_angle TacTip
 ])
 def test_object_push_matches_oracle(oracle, arm, sensor, S, movement, traj, rand, reward):
     import tactile_gym_b200 as tg
