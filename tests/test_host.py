@@ -217,7 +217,7 @@ def test_reference_training_params_are_accepted():
     from tactile_gym_b200.vec_env import CONFIG_BUILDERS
 
     sets = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_params.json")))
-    assert len(sets) == 14
+    assert len(sets) == 21      # 14 training parameter sets + the 7 demo scripts' (examples/demo_*_env.py)
     built = 0
     for p in sets:
         modes, env_id = p["env_modes"], p["env_name"]
@@ -236,4 +236,6 @@ def test_reference_training_params_are_accepted():
         cfg = out[0]
         assert cfg.n_envs == 2 and cfg.task.max_steps == p["max_ep_len"] and cfg.sensor.image_size == p["image_size"][0]
         built += 1
-    assert built == 6      # edge, balance, push (MG400 + mini_right_angle TacTip), roll, surface -v0, -v1: every complete PPO set-up but -v2's
+    # every complete PPO set-up but -v2's vertical one (edge, balance, push on the MG400 + mini TacTip, roll, surface -v0, -v1)
+    # and every demo script but demo_surf_vert_env.py
+    assert built == 12
