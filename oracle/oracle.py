@@ -606,12 +606,25 @@ class SurfaceFollowOracle:
         lims = np.zeros((6, 2))
         lims[0], lims[1], lims[2] = (-self.extent, self.extent), (-self.extent, self.extent), (-self.hrange, self.hrange)
         lims[3], lims[4] = (-np.pi / 4, np.pi / 4), (-np.pi / 4, np.pi / 4)
+        # noise_mode "vertical_simplex" (surface_follow-v2's own surface; CPU oracle only so far, the CUDA path does not build it):
+        # the heightfield stands upright 0.15 m above the table, the `forward` sensor type faces it (:60-63, :83-107, :248-259)
+        self.vertical = noise_mode == "vertical_simplex"
+        self.R_flip = np.eye(3)
+        self.original_surface_pos = self.surface_pos.copy()
+        if self.vertical:
+            self.typ = "forward"
+            self.surface_pos = np.array([wd[0], wd[1], 0.15 + self.hrange])
+            self.R_flip = mat_from_quat(quat_from_euler([0.0, -np.pi / 2, 0.0]))
+            self.workframe_pos, self.workframe_rpy = self.surface_pos.copy(), np.array([-np.pi, 0.0, 0.0])
+            lims = np.zeros((6, 2))
+            lims[0], lims[1], lims[5] = (-self.hrange, self.hrange), (-self.extent, self.extent), (-np.pi / 4, np.pi / 4)
         self.m = load_model(arm, sensor, self.typ, self.workframe_pos, self.workframe_rpy, lims)
         self.rest = rest_pose("surface_follow", arm, sensor, self.typ, self.m)
         self.ref = load_refimg(sensor, self.typ, image_size)
         # :264-271 x/y bins
-        self.x_bins = np.linspace(self.surface_pos[0] - (self.rows / 2) * self.grid, self.surface_pos[0] + (self.rows / 2) * self.grid, self.rows)
-        self.y_bins = np.linspace(self.surface_pos[1] - (self.cols / 2) * self.grid, self.surface_pos[1] + (self.cols / 2) * self.grid, self.cols)
+        sp = self.original_surface_pos      # (the vertical set-up builds the bins around the un-flipped surface position, :248-259)
+        self.x_bins = np.linspace(sp[0] - (self.rows / 2) * self.grid, sp[0] + (self.rows / 2) * self.grid, self.rows)
+        self.y_bins = np.linspace(sp[1] - (self.cols / 2) * self.grid, sp[1] + (self.cols / 2) * self.grid, self.cols)
         self.s = OrState()
         self.repeat = int(np.floor((1.0 / 10.0) / (1.0 / 240.0)))
         self.termination_dist = 0.01
@@ -625,7 +638,7 @@ class SurfaceFollowOracle:
 
     def draw(self):
         """reset_task order (:539-547): update_surface's randint(1e8) (:448), then make_goal's uniform(-pi, pi) (:508)"""
-        seed_int = self.np_random.randint(1e8) if self.noise_mode == "simplex" else 0      # :436-458
+        seed_int = self.np_random.randint(1e8) if self.noise_mode in ("simplex", "vertical_simplex") else 0      # :436-458
         ang = float(self.np_random.choice([-1, 1])) if self.one_d else self.np_random.uniform(-np.pi, np.pi)   # :512-520
         return float(seed_int), ang
 
@@ -638,7 +651,10 @@ class SurfaceFollowOracle:
     def reset(self, draws=None):
         self.steps = 0
         seed_int, ang = self.draw() if draws is None else draws
-        if self.noise_mode == "none" or self.movement_mode == "xRz":                   # :436-437; "xRz" is in neither list of :450-455
+        if self.vertical:                                                               # gen_heigtfield_simplex_1d_vertical :359-379
+            col = np.array([opensimplex_noise2(int(seed_int), x * self.interp, 1 * self.interp) * self.hrange for x in range(self.rows)])
+            self.h = np.tile(col[:, None], (1, self.cols))
+        elif self.noise_mode == "none" or self.movement_mode == "xRz":                 # :436-437; "xRz" is in neither list of :450-455
             self.h = np.zeros((self.rows, self.cols))
         elif self.one_d:                                                                # gen_heigtfield_simplex_1d :339-357
             row = np.array([opensimplex_noise2(int(seed_int), 1 * self.interp, y * self.interp) * self.hrange for y in range(self.cols)])
@@ -653,15 +669,23 @@ class SurfaceFollowOracle:
         nrm = np.dstack((-gx, -gy, np.ones_like(self.h)))
         self.surface_normals = nrm / np.linalg.norm(nrm, axis=2)[..., None]
         self.V = heightfield_local_vertices(self.h, self.grid) + self.surface_pos
+        if self.vertical:
+            # :472-489 every surface point goes world -> surface frame (translation only), is turned by the surface's orientation
+            # and comes back; :499-506 the normals are turned the same way.  The drawn mesh is the body at surface_pos / surface_orn.
+            self.surface_array = (self.surface_array - self.surface_pos) @ self.R_flip.T + self.surface_pos
+            self.surface_normals = self.surface_normals @ self.R_flip.T
+            self.V = heightfield_local_vertices(self.h, self.grid) @ self.R_flip.T + self.surface_pos
         # make_goal :501-537
         self.dirs = np.array([0.0, ang, 0.0]) if self.one_d else np.array([np.cos(ang), np.sin(ang), 0.0])
         wdir = self.Rw @ self.dirs
-        g = [self.surface_pos[0] + self.extent * wdir[0], self.surface_pos[1] + self.extent * wdir[1]]
+        g = [self.original_surface_pos[0] + self.extent * wdir[0], self.original_surface_pos[1] + self.extent * wdir[1]]
         gi, gj = self.xy_to_surface_idx(g[0], g[1])
-        self.goal_pos = np.array([g[0], g[1], self.surface_array[gi, gj, 2]])
+        self.goal_pos = self.surface_array[gi, gj].copy() if self.vertical else np.array([g[0], g[1], self.surface_array[gi, gj, 2]])   # :523-537
         # update_init_pose :549-573 + Robot.reset
         ch = self.h[self.rows // 2, self.cols // 2]
         init_world = np.array([self.surface_pos[0], self.surface_pos[1], self.surface_pos[2] + ch - self.embed_dist])
+        if self.vertical:
+            init_world = np.array([self.surface_pos[0] - (ch - self.embed_dist), self.surface_pos[1], self.surface_pos[2]])
         pos = self.Rw.T @ (init_world - self.workframe_pos); rpy = np.zeros(3)
         self.last_reset_substeps = lib().or_robot_reset(C.byref(self.m), C.byref(self.s), _dptr(self.rest), _dptr(np.ascontiguousarray(pos)), _dptr(rpy))
         self.reward, self.done = self.step_data()
@@ -674,8 +698,13 @@ class SurfaceFollowOracle:
     def stimulus_world(self, radius=0.06):
         """the heightfield cells within `radius` (m) of the TCP in x/y (everything the tactile camera can see)"""
         p, _ = self.tcp_world()
-        cx = (p[0] - self.surface_pos[0]) / self.grid + (self.cols - 1) / 2.0
-        cy = (p[1] - self.surface_pos[1]) / self.grid + (self.rows - 1) / 2.0
+        if self.vertical:
+            # the upright surface: grid columns (local x) run along world z, rows (local y) along world y
+            local = (p - self.surface_pos) @ self.R_flip          # = R_flip^T (p - surface_pos): the TCP in the heightfield's own frame
+            cx, cy = local[0] / self.grid + (self.cols - 1) / 2.0, local[1] / self.grid + (self.rows - 1) / 2.0
+        else:
+            cx = (p[0] - self.surface_pos[0]) / self.grid + (self.cols - 1) / 2.0
+            cy = (p[1] - self.surface_pos[1]) / self.grid + (self.rows - 1) / 2.0
         r = radius / self.grid
         j0, j1 = int(max(0, np.floor(cx - r))), int(min(self.cols - 1, np.ceil(cx + r)))
         i0, i1 = int(max(0, np.floor(cy - r))), int(min(self.rows - 1, np.ceil(cy + r)))
@@ -696,6 +725,10 @@ class SurfaceFollowOracle:
         surf_dist = abs(emb[2] - self.surface_array[self.tip_i, self.tip_j, 2])
         n = self.surface_normals[self.tip_i, self.tip_j]
         v = R @ np.array([0.0, 0.0, -1.0])
+        if self.vertical:   # :708-711, :733-735, :752-754: the forward sensor's axis is its -x, the distance is measured along world x
+            emb = p + R @ np.array([-self.embed_dist, 0.0, 0.0])
+            surf_dist = abs(emb[0] - self.surface_array[self.tip_i, self.tip_j, 0])
+            v = R @ np.array([-1.0, 0.0, 0.0])
         cos_dist = 1 - np.dot(n, v) / (np.linalg.norm(n) * np.linalg.norm(v))
         w_norm = 0.0 if self.movement_mode in ("yz", "xyz") else 1.0
         if self.variant == "vert":   # surface_follow_vert_env.py:63-79
@@ -737,6 +770,8 @@ class SurfaceFollowOracle:
         if self.control_mode == "TCP_position_control":   # base_surface_env.py:172-181
             mv, ma = 0.001, 1 * (np.pi / 180)
         amax = np.array([mv, mv, mv, ma, ma, 0.0]); amin = -amax
+        if self.vertical:   # :183-194
+            amax = np.array([mv, mv, 0.0, 0.0, 0.0, ma]); amin = -amax
         return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
 
     def step(self, action):

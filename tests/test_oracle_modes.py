@@ -111,3 +111,25 @@ def test_tcp_position_control(oracle):
         s.step(np.array([0.25], np.float32))                                          # z + 1 mm per step, limit + 25 mm
     z = s.oracle_obs()[2]
     assert 0.0245 < z < 0.0252
+
+
+def test_vertical_surface_env(oracle):
+    """surface_follow-v2 on its own (vertical) surface, oracle side: MG400 + forward TacTip facing an upright 1-d simplex
+    heightfield 0.15 m above the table; the start pose embeds the tip 2.5 mm, the drive runs along y, the skin sees the surface"""
+    e = oracle.SurfaceFollowOracle(image_size=128, arm="mg400", sensor="tactip", movement_mode="xRz", variant="vert",
+                                   noise_mode="vertical_simplex", seed=5)
+    o = e.reset()
+    p, qt = e.tcp_world()
+    ch = e.h[32, 32]
+    assert abs(p[0] - (0.33 - ch + 0.0025)) < 3e-4 and abs(p[1]) < 3e-4 and abs(p[2] - 0.175) < 3e-4
+    R = oracle.mat_from_quat(qt)
+    assert np.allclose(R[:, 0], [1, 0, 0], atol=1e-3)                  # the forward sensor's axis points at the surface (+x)
+    dep, gray, mask = e.ref
+    assert (o[..., 0][mask == 0] > 0).sum() > 500                        # embedded: the surface shows on the skin
+    y0 = p[1]
+    for k in range(20):
+        o, r, d, _ = e.step(np.array([0.0, 0.0], np.float32))
+    p1, _ = e.tcp_world()
+    # 1 mm per step along the drawn direction (work frame rpy (-pi, 0, 0): its y is the world's -y)
+    assert abs(abs(p1[1] - y0) - 0.02) < 1e-3 and np.sign(p1[1] - y0) == -e.dirs[1]
+    assert abs(p1[0] - p[0]) < 5e-4 and abs(p1[2] - p[2]) < 5e-4 and -1.0 < r < 0.0 and not d

@@ -443,3 +443,41 @@ def test_blocking_move_retargeting_and_exit(oracle):
             assert bool(done) == (k == len(hist) - 1), (case, k)
         if cv0 > 0:
             assert cv.value < cv0                          # the halving rule fired on the way in
+
+
+@pytest.mark.parametrize("arm,sign", [("mg400", 1), ("mg400", -1), ("ur5", 1), ("ur5", -1)])
+def test_vertical_surface_geometry_and_rewards(oracle, monkeypatch, arm, sign):
+    """surface_follow-v2's own surface (noise_mode "vertical_simplex", `forward` sensors) run from the reference source: the
+    upright heightfield's surface_array / normals, goal, start pose and the reward terms - against the oracle's restatement
+    (the CUDA path does not build this mode yet; this pins the checker it will be compared with)."""
+    monkeypatch.setattr(oracle, "opensimplex_noise2", _fake_noise)
+    key = "vert_%s_%s" % (arm, "p" if sign > 0 else "m")
+    g = lambda n: GOLD[key + "_" + n]
+    e = oracle.SurfaceFollowOracle(image_size=64, arm=arm, sensor="tactip", movement_mode="xRz", variant="vert", noise_mode="vertical_simplex",
+                                   render=False, max_steps=200)
+    assert e.typ == "forward"
+    e.reset(draws=(77.0, float(sign)))
+    assert np.allclose(np.stack([e.x_bins, e.y_bins]), g("bins"), atol=0) and np.allclose(e.surface_pos, g("surface_pos"), atol=0)
+    assert np.allclose(e.h, g("h"), atol=1e-15) and np.ptp(e.h, axis=1).max() == 0 and np.ptp(e.h) > 1e-3       # varies along the rows only
+    assert np.allclose(e.surface_array, g("array"), atol=1e-12)
+    assert np.allclose(e.surface_normals, g("normals"), atol=1e-12)
+    assert np.allclose(e.goal_pos, g("goal")[:3], atol=1e-12)
+    gw, _ = oracle.world_to_work(e.m, e.goal_pos, np.array([0.0, 0.0, 0.0, 1.0]))
+    assert np.allclose(gw, g("goal")[3:6], atol=1e-12)
+    # update_init_pose (:556-563): the start pose handed to Robot.reset, in the work frame
+    ch = e.h[32, 32]
+    init_world = np.array([e.surface_pos[0] - (ch - e.embed_dist), e.surface_pos[1], e.surface_pos[2]])
+    assert np.allclose(e.Rw.T @ (init_world - e.workframe_pos), g("init")[:3], atol=1e-12) and np.all(g("init")[3:] == 0)
+    ended = 0
+    for pose, row in zip(g("poses"), g("rows")):
+        q = oracle.quat_from_euler(pose[3:6])
+        e.tcp_world = lambda p=pose[:3], q=q: (p, q)
+        e.steps = 7
+        rew, done = e.step_data()
+        assert (e.tip_i, e.tip_j) == (int(row[4]), int(row[5]))
+        assert abs(rew - row[2]) < 1e-12 and done == bool(row[3])
+        assert abs(rew + (10.0 * row[0] + 3.0 * row[1])) < 1e-12
+        ended += int(done)
+    assert ended == 1
+    if arm == "ur5" and sign == -1:
+        _check_actions("surfvert_vertical", e)        # x, y +-0.01 m/s, yaw +-5 deg/s (:183-194); e.dirs = (0, -1, 0) from the reset

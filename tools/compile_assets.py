@@ -342,6 +342,13 @@ ROBOTS = [
     ("mg400", "tactip", "mini_right_angle"),   # object_push's MG400 + TacTip (object_push_env.py:84-86): the reference's own PPO set-up
     ("mg400", "digit", "right_angle"),
     ("mg400", "digitac", "right_angle"),
+    # the `forward` sensor type of surface_follow's vertical surface (noise_mode "vertical_simplex", base_surface_env.py:60-63)
+    ("ur5", "tactip", "forward"),
+    ("ur5", "digit", "forward"),
+    ("ur5", "digitac", "forward"),
+    ("mg400", "tactip", "forward"),
+    ("mg400", "digit", "forward"),
+    ("mg400", "digitac", "forward"),
 ]
 
 KAT_COMBOS = {("ur5", "tactip", "standard"), ("ur5", "digit", "standard"), ("mg400", "digitac", "right_angle")}

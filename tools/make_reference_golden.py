@@ -573,6 +573,46 @@ def main():
         out["blocking_%d_hist" % case] = np.array(hist)               # per iteration: q, qd before the step, commanded joint target
         out["blocking_%d_target" % case] = np.concatenate([targ_j, Pt[m.tcp_link], Qt[m.tcp_link], [cv if cv is not None else -1.0, max_steps]])
 
+    # ---- N. surface_follow-v2's own surface: noise_mode "vertical_simplex" (base_surface_env.py:60-63, 83-107, 183-194, 248-259,
+    # 359-379, 459-506, 523-537, 556-563, 708-754) - the upright heightfield and everything derived from it, from the reference
+    # source: setup_surface, reset_task (update_surface with the stand-in noise, make_goal), update_init_pose, the action ranges,
+    # and the reward terms at given TCP poses.  (CPU oracle only so far: the CUDA path does not build this mode yet.)
+    for arm_name, wd in (("mg400", [0.33, 0.0, 0.0]), ("ur5", [0.65, 0.0, 0.0])):
+        for dirsign in (1, -1):
+            arm = bare(BaseRobotArm, _pb=PB())
+            wp = [wd[0], wd[1], 0.15 + 0.025]
+            arm.set_workframe(wp, [-np.pi, 0.0, 0.0])
+            ev = bare(SurfVertR, _pb=ScenePB(), noise_mode="vertical_simplex", movement_mode="xRz", reward_mode="dense", well_designed_pos=wd,
+                      embed_dist=0.0025, robot=types.SimpleNamespace(arm=arm), surface_id=1, goal_indicator=2, termination_dist=0.01,
+                      _max_steps=200, _env_step_counter=7, t_s_name="tactip", control_mode="TCP_velocity_control",
+                      np_random=types.SimpleNamespace(randint=lambda hi: 77, choice=lambda opts, dirsign=dirsign: dirsign))
+            ev.setup_surface()
+            ev.heightfield_data = np.zeros((64, 64))
+            ev.reset_task()
+            init_pos, init_rpy = ev.update_init_pose()
+            key = "vert_%s_%s" % (arm_name, "p" if dirsign > 0 else "m")
+            out[key + "_h"], out[key + "_array"], out[key + "_normals"] = ev.heightfield_data.copy(), ev.surface_array.copy(), ev.surface_normals.copy()
+            out[key + "_goal"] = np.concatenate([ev.goal_pos_worldframe, ev.goal_pos_workframe])
+            out[key + "_init"] = np.concatenate([init_pos, init_rpy])
+            out[key + "_bins"] = np.stack([ev.x_bins, ev.y_bins])
+            out[key + "_surface_pos"] = np.array(ev.surface_pos, dtype=np.float64)
+            poses, rows = [], []
+            for k in range(8):
+                p_ = np.array([wd[0] + rng.uniform(-0.01, 0.02), rng.uniform(-0.12, 0.12), 0.175 + rng.uniform(-0.002, 0.002)])
+                r_ = np.array([-np.pi + rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), rng.uniform(-0.5, 0.5)])
+                if k == 0:
+                    p_ = np.array(ev.goal_pos_worldframe) + np.array([0.002, -0.003, 0.001])      # inside the termination radius
+                ev.cur_tcp_pos_worldframe, ev.cur_tcp_orn_worldframe = p_, PB.getQuaternionFromEuler(r_)
+                ev.tip_i, ev.tip_j = ev.xy_to_surface_idx(p_[0], p_[1])
+                rows.append([ev.z_dist_to_surface(), ev.cos_dist_to_surface_normal(), ev.dense_reward(), float(ev.termination()), ev.tip_i, ev.tip_j])
+                poses.append(np.concatenate([p_, r_]))
+            out[key + "_poses"], out[key + "_rows"] = np.array(poses), np.array(rows, dtype=np.float64)
+    ev.get_act_dim = lambda: 2
+    ev.workframe_directions = [0, -1, 0]
+    ev.setup_action_space()
+    acts = rng.uniform(-0.3, 0.3, (12, 2))
+    out["act_surfvert_vertical_in"], out["act_surfvert_vertical_out"] = acts, np.array([ev.scale_actions(ev.encode_actions(a)) for a in acts])
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
