@@ -76,3 +76,48 @@ def test_opensimplex_known_answer_and_surface_env(oracle):
     assert abs(np.linalg.norm(e.goal_pos[:2] - e.surface_pos[:2]) - 0.15) < 1e-12
     _, r, d, _ = e.step(np.array([0.25, 0.0, 0.0]))
     assert r < 0 and not d
+
+
+def test_free_body_known_answers(oracle):
+    """SURVEY 8(c) self-consistency checks for the free rigid body of object_balance (or_step_sim_obj with the point-to-point
+    rows switched off): semi-implicit free fall z_n = z_0 + g dt^2 n (n + 1) / 2 with the episode's gravity, a spin about a
+    principal axis stays what it is, and a torque-free tumble keeps its angular momentum R I R^T w"""
+    import ctypes as C
+
+    b = oracle.ObjectBalanceOracle(image_size=64, rand_gravity=False, rand_embed_dist=False)
+    b.reset(draws=np.array([-0.5, 0.0035, 0.0, 0.0]))
+    o = b.o
+    o.p2p_enabled, o.ext_pending = 0, 0
+    dt, g = 1.0 / 240.0, -0.5
+    z0 = o.pos[2]
+    com0 = np.array(o.pos[:]) + oracle.mat_from_quat(np.array(o.quat[:])) @ np.array(o.com_off[:])
+    n = 48
+    for _ in range(n):
+        oracle.lib().or_step_sim_obj(C.byref(b.m), C.byref(b.s), C.byref(o))
+    assert abs((o.pos[2] - z0) - g * dt * dt * n * (n + 1) / 2) < 1e-12
+    assert abs(o.vel[2] - g * dt * n) < 1e-12 and abs(o.vel[0]) < 1e-15 and abs(o.omg[0]) < 1e-15
+    com1 = np.array(o.pos[:]) + oracle.mat_from_quat(np.array(o.quat[:])) @ np.array(o.com_off[:])
+    assert np.allclose(com1[:2], com0[:2], atol=1e-15)
+    # spin about the body's z axis (a principal axis of the pole): constant
+    b.m.gravity[2] = 0.0
+    R = oracle.mat_from_quat(np.array(o.quat[:]))
+    for c in range(3):
+        o.vel[c] = 0.0; o.omg[c] = 3.0 * R[c, 2]
+    for _ in range(240):
+        oracle.lib().or_step_sim_obj(C.byref(b.m), C.byref(b.s), C.byref(o))
+    R1 = oracle.mat_from_quat(np.array(o.quat[:]))
+    assert np.allclose(np.array(o.omg[:]), 3.0 * R1[:, 2], atol=1e-9) and np.allclose(R1[:, 2], R[:, 2], atol=1e-9)
+    # torque-free tumble: angular momentum is conserved to the integrator's order, kinetic energy too
+    I = np.array(o.inertia[:])
+    w0 = R1 @ np.array([1.0, 0.7, 2.0])
+    for c in range(3):
+        o.omg[c] = w0[c]
+    L0 = R1 @ (I * (R1.T @ w0))
+    E0 = 0.5 * np.dot(w0, L0)
+    for _ in range(240):
+        oracle.lib().or_step_sim_obj(C.byref(b.m), C.byref(b.s), C.byref(o))
+    R2, w2 = oracle.mat_from_quat(np.array(o.quat[:])), np.array(o.omg[:])
+    L2 = R2 @ (I * (R2.T @ w2))
+    assert np.linalg.norm(L2 - L0) < 2e-2 * np.linalg.norm(L0)
+    assert abs(0.5 * np.dot(w2, L2) - E0) < 2e-2 * E0
+    assert np.linalg.norm(R2 - R1) > 0.5          # it did tumble
