@@ -151,7 +151,7 @@ typedef struct {
      * out at the goal, surface_follow_auto_env.py:59-73 / surface_follow_goal_env.py:53-67); object_push / object_roll keep
      * push_sparse_reward */
     int32_t sparse_reward;
-    int32_t surf_mode;               /* heights: 0 simplex 2-d (xyz, xyzRxRy), 1 simplex 1-d along y (yz, yzRx; :339-357), 2 flat (noise_mode "none") */
+    int32_t surf_mode;               /* heights: 0 simplex 2-d (xyz, xyzRxRy), 1 simplex 1-d along y (yz, yzRx; :339-357), 2 flat (noise_mode "none"), 3 simplex 1-d along the rows (vertical) */
     int32_t surf_dir_mode;           /* goal direction: 0 (cos, sin) of the drawn angle; 1 (0, +-1) = the drawn choice([-1, 1]) (:512-514) */
     int32_t surf_drive_y_only;       /* 1: surface_follow-v2 drives along y only, x stays the policy's (surface_follow_vert_env.py:30-45) */
     /* control_mode (robots/arms/robot.py:156-186): 0 TCP_velocity_control (Jacobian inverse, velocity motors, `substeps` steps);
@@ -159,6 +159,11 @@ typedef struct {
      * tcp_lims, IK from the current joints, position motors, then blocking_move(max_steps = pos_max_steps, robot.py:188-260):
      * step until the pose error / joint speed test passes).  Built for the motor-only tasks (edge_follow, surface_follow), UR5. */
     int32_t control_mode, pos_max_steps;
+    /* surface_follow-v2's own surface (noise_mode "vertical_simplex", base_surface_env.py:60-63,83-107,248-259): the heightfield
+     * body stands upright, turned by euler (0, -pi/2, 0) about surf_pos (a local point (x, y, z) sits at surf_pos + (-z, y, x)),
+     * the `forward` sensor type faces it; heights vary along the rows only (surf_mode 3, gen_heigtfield_simplex_1d_vertical
+     * :359-379); surface distance and tip axis are taken along x (:708-754) */
+    int32_t surf_vertical, pad_vertical;
     double push_half[3];             /* cube half extents (cube.urdf) */
     double push_table_z;             /* table top (base_tactile_env.py:135-139 + table.urdf) */
     double push_mu_table, push_mu_tip; /* products of the lateralFriction pairs (object_push_env.py:218, :61-66, table.urdf) */

@@ -58,6 +58,7 @@ class TgTask(C.Structure):
         ("push_mode", C.c_int32), ("push_traj_straight", C.c_int32), ("push_sparse_reward", C.c_int32), ("push_shape", C.c_int32),
         ("sparse_reward", C.c_int32), ("surf_mode", C.c_int32), ("surf_dir_mode", C.c_int32), ("surf_drive_y_only", C.c_int32),
         ("control_mode", C.c_int32), ("pos_max_steps", C.c_int32),
+        ("surf_vertical", C.c_int32), ("pad_vertical", C.c_int32),
         ("push_half", D3), ("push_table_z", C.c_double), ("push_mu_table", C.c_double), ("push_mu_tip", C.c_double),
         ("push_tip_k", C.c_double), ("push_tip_d", C.c_double), ("push_erp", C.c_double), ("push_slop", C.c_double),
         ("push_lin_damping", C.c_double), ("push_ang_damping", C.c_double), ("push_init_pos", D3), ("push_inertia_per_mass", D3),

@@ -268,6 +268,7 @@ TGD void reset_target(const TgTask& task, double embed, double centre_h, double*
     m3mulv(t, R, lp);
     tpos[0] = task.workframe_pos[0] + t[0]; tpos[1] = task.workframe_pos[1] + t[1]; tpos[2] = task.workframe_pos[2] + t[2];
     if (task.task == TG_TASK_SURFACE_FOLLOW) { tpos[0] = task.surf_pos[0]; tpos[1] = task.surf_pos[1]; tpos[2] = task.surf_pos[2] + centre_h - embed; }
+    if (task.task == TG_TASK_SURFACE_FOLLOW && task.surf_vertical) { tpos[0] = task.surf_pos[0] - (centre_h - embed); tpos[2] = task.surf_pos[2]; } // :556-563
     if (task.task == TG_TASK_OBJECT_ROLL) tpos[2] = centre_h; // update_workframe (object_roll_env.py:197-202): the caller passes 2 r - embed_dist
     quat_mul(oq, wq, tq);
     euler_from_quat(oq, rpy);
@@ -345,8 +346,10 @@ __device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph
 #pragma unroll 1
             for (int k = r.surf_it; k < end; k++) {
                 // surf_mode 1: gen_heigtfield_simplex_1d (:339-357), noise along y only; 2: noise_mode "none" (:436-437)
+                // 3: gen_heigtfield_simplex_1d_vertical (:359-379), noise along the rows only
                 const double nx = task.surf_mode == 1 ? 1.0 * task.surf_interp : (double)(k / SURF_N) * task.surf_interp;
-                const double h = task.surf_mode == 2 ? 0.0 : os_noise2(perm, nx, (double)(k % SURF_N) * task.surf_interp) * task.surf_range;
+                const double ny = task.surf_mode == 3 ? 1.0 * task.surf_interp : (double)(k % SURF_N) * task.surf_interp;
+                const double h = task.surf_mode == 2 ? 0.0 : os_noise2(perm, nx, ny) * task.surf_range;
                 H[k] = h;
                 r.hmin = fminf(r.hmin, (float)h); r.hmax = fmaxf(r.hmax, (float)h);
             }
@@ -440,6 +443,12 @@ __device__ __noinline__ void reset_finish(const TgArm& arm, const TgTask& task, 
         meta[0] = 0.5 * ((double)r.hmin + (double)r.hmax);
         meta[1] = dirs[0]; meta[2] = dirs[1];
         meta[3] = gx; meta[4] = gy; meta[5] = H[gi * SURF_N + gj] + task.surf_pos[2];
+        if (task.surf_vertical) {
+            // :523-527 the goal is the (flipped) surface point itself: local (X - sx, Y - sy, h) -> surf_pos + (-h, Y - sy, X - sx)
+            meta[3] = task.surf_pos[0] - H[gi * SURF_N + gj];
+            meta[4] = surf_bin(task.surf_pos[1], task.surf_grid, gi);
+            meta[5] = task.surf_pos[2] + (surf_bin(task.surf_pos[0], task.surf_grid, gj) - task.surf_pos[0]);
+        }
         meta[6] = (double)r.hmin; meta[7] = (double)r.hmax; // float32 height range (the raster's first slab bound)
 #pragma unroll
         for (int i = 0; i < 12; i++) out.stim[i] = 0.0;
@@ -710,11 +719,17 @@ __device__ __noinline__ void oracle_obs_env(const TgArm& arm, const TgTask& task
         double nrm[3] = {-g1, -g0, 1.0};
         const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
         nrm[0] /= nn; nrm[1] /= nn; nrm[2] /= nn;
+        double surf_h = H[ti * SURF_N + tj] + task.surf_pos[2];
+        if (task.surf_vertical) {   // the flipped surface_array / surface_normals (:472-506)
+            const double fl[3] = {-nrm[2], nrm[1], nrm[0]};
+            nrm[0] = fl[0]; nrm[1] = fl[1]; nrm[2] = fl[2];
+            surf_h = task.surf_pos[2] + (surf_bin(task.surf_pos[0], task.surf_grid, tj) - task.surf_pos[0]);
+        }
         m3mulv(nw, Ri, nrm);
         const double g[3] = {meta[3], meta[4], meta[5]};
         world_to_work_at(task, wf, g, ident, gp, gr);
         put3(wp); put4(wo); put3(vl); put3(va); put3(gp);
-        out[n++] = (float)(H[ti * SURF_N + tj] + task.surf_pos[2]);
+        out[n++] = (float)surf_h;
         put3(nw);
     } else {
         // the free object: getBasePositionAndOrientation / getBaseVelocity brought to the work frame (base_object_env.py:118-139)

@@ -133,14 +133,22 @@ TGD void surface_step_data(const TgTask& task, const double* H, const double* me
     // z_dist_to_surface (:727-757): tip pushed embed_dist along its own -z
     const double emb_z = tp[2] + R[8] * (-task.surf_embed);
     const double surf_z = H[ti * SURF_N + tj] + task.surf_pos[2];
-    const double surf_dist = fabs(emb_z - surf_z);
+    double surf_dist = fabs(emb_z - surf_z);
+    if (task.surf_vertical) surf_dist = fabs((tp[0] + R[0] * (-task.surf_embed)) - (task.surf_pos[0] - H[ti * SURF_N + tj]));
     // cos_dist_to_surface_normal (:701-725)
     double g0, g1;
     surf_gradient(H, task.surf_grid, ti, tj, g0, g1); // g0 = "surface_grad_y", g1 = "surface_grad_x"
     double n[3] = {-g1, -g0, 1.0};
     const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
     n[0] /= nn; n[1] /= nn; n[2] /= nn;
-    const double v[3] = {-R[2], -R[5], -R[8]};
+    double v[3] = {-R[2], -R[5], -R[8]};
+    if (task.surf_vertical) {
+        // the upright surface (:708-711, :733-735, :752-754): the forward sensor's axis is its -x, the surface distance is taken
+        // along world x, the normal is the flipped one (local (x, y, z) -> (-z, y, x))
+        const double fl[3] = {-n[2], n[1], n[0]};
+        n[0] = fl[0]; n[1] = fl[1]; n[2] = fl[2];
+        v[0] = -R[0]; v[1] = -R[3]; v[2] = -R[6];
+    }
     const double cs = (n[0] * v[0] + n[1] * v[1] + n[2] * v[2]) / (sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
     // SurfaceFollowAutoEnv.dense_reward (W_goal = 0, W_surf = 1) / SurfaceFollowGoalEnv.dense_reward (W_goal = 1, W_surf = 10)
     const double goal_xy = sqrt(gx * gx + gy * gy);

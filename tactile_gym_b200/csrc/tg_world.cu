@@ -57,6 +57,7 @@ struct TgWorld {
     int standby_blocks = 0;
     long long launches = 0;
     // tg_step_host: device staging for the actions, a copy stream and one event per observation chunk
+    double* cam_local = nullptr;      // surface_follow-v2 (vertical): the cameras in the heightfield's frame, [N][12]
     float* d_actions_stage = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[TG_HOST_MAX_CHUNKS] = {};
@@ -189,7 +190,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         if (!b.pipeline) { tg_destroy(w); return fail(TG_EINVAL, "surface_follow needs max_steps >= 2"); }
         if ((rc = dalloc(w, &b.height, (size_t)2 * SURF_PTS * n)) || (rc = dalloc(w, &b.hf_meta, (size_t)2 * SURF_META * n)) ||
             (rc = dalloc(w, &b.hf_cur, n)) || (rc = dalloc(w, &b.sb_perm, (size_t)256 * n)) || (rc = dalloc(w, &b.sb_surf_it, n)) ||
-            (rc = dalloc(w, &b.sb_hmm, (size_t)2 * n)) || (rc = dalloc(w, &b.accum, n))) {
+            (rc = dalloc(w, &b.sb_hmm, (size_t)2 * n)) || (rc = dalloc(w, &b.accum, n)) || (rc = dalloc(w, &w->cam_local, (size_t)12 * n))) {
             tg_destroy(w);
             return rc;
         }
@@ -357,6 +358,21 @@ extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)
 
 static dim3 env_grid(const TgWorld* w) { return dim3(w->eb.step_blocks); } // 128 threads = 4 warps = 4 * lanes envs
 
+// surface_follow-v2's upright heightfield: depth along a camera ray does not change under a rigid motion, so instead of rotating the
+// 7,938-triangle surface the camera is brought into the heightfield's own frame (about surf_pos; world (a, b, c) -> local (c, b, -a),
+// the inverse of euler (0, -pi/2, 0)) and raster_hf_kernel runs unchanged
+__global__ void surf_cam_local_kernel(int n, const double* __restrict__ cam, double* __restrict__ out, double sx, double sy, double sz)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double* c = cam + (size_t)e * 12;
+    double* o = out + (size_t)e * 12;
+    const double ex = c[0] - sx, ey = c[1] - sy, ez = c[2] - sz;
+    o[0] = sx + ez; o[1] = sy + ey; o[2] = sz - ex;
+#pragma unroll
+    for (int k = 1; k < 4; k++) { o[3 * k] = c[3 * k + 2]; o[3 * k + 1] = c[3 * k + 1]; o[3 * k + 2] = -c[3 * k]; }
+}
+
 static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaStream_t st, bool terminal_state = false, int e0 = 0, int e1 = -1)
 {
     RasterArgs r = w->ra;
@@ -370,6 +386,13 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
     r.obs += (size_t)e0 * w->S * w->S; r.cam += (size_t)e0 * 12; r.stim += (size_t)e0 * 12;
     if (r.mask) r.mask += e0;
     if (r.hf) { r.hf += (size_t)e0 * 2 * SURF_PTS; r.hf_cur += e0; r.hf_meta += (size_t)e0 * 2 * SURF_META; }
+    if (r.hf && w->cfg.task.surf_vertical) {
+        double* local = w->cam_local + (size_t)e0 * 12;
+        surf_cam_local_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(cnt, r.cam, local, w->cfg.task.surf_pos[0], w->cfg.task.surf_pos[1], w->cfg.task.surf_pos[2]);
+        w->launches++;
+        CK(cudaGetLastError());
+        r.cam = local;
+    }
     if (w->cfg.task.task == TG_TASK_OBJECT_ROLL) raster_sphere_kernel<<<std::min((cnt + 7) / 8, 8 * w->sm_count), SPH_THREADS, 0, st>>>(r);
     else {
         const int wp = r.hf ? HF_WARPS : RASTER_WARPS;
