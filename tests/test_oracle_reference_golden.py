@@ -481,3 +481,23 @@ def test_vertical_surface_geometry_and_rewards(oracle, monkeypatch, arm, sign):
     assert ended == 1
     if arm == "ur5" and sign == -1:
         _check_actions("surfvert_vertical", e)        # x, y +-0.01 m/s, yaw +-5 deg/s (:183-194); e.dirs = (0, -1, 0) from the reset
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tactile_gym"), reason="needs the reference checkout (build container only)")
+def test_committed_golden_is_what_the_reference_source_produces(tmp_path):
+    """Where the reference is present, re-run it: the committed vectors must be exactly what tools/make_reference_golden.py and
+    tools/make_reference_params.py produce from /root/reference today (no hand-edited or stale golden files)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "ref.npz")
+    subprocess.run([sys.executable, os.path.join(root, "tools", "make_reference_golden.py"), "/root/reference", out], check=True, capture_output=True)
+    new = np.load(out)
+    assert sorted(new.files) == sorted(GOLD.files)
+    for k in new.files:
+        assert new[k].shape == GOLD[k].shape and np.array_equal(new[k], GOLD[k]), k
+    outj = str(tmp_path / "params.json")
+    subprocess.run([sys.executable, os.path.join(root, "tools", "make_reference_params.py"), "/root/reference", outj], check=True, capture_output=True)
+    assert json.load(open(outj)) == json.load(open(os.path.join(root, "tests", "golden", "reference_params.json")))
