@@ -57,8 +57,12 @@ def load_sensor_json(sensor, typ):
 def load_rest_pose(env, arm, sensor, typ, control_links):
     with open(os.path.join(ASSETS, "rest_poses.json")) as f:
         rp = json.load(f)[env][arm]
-    rp = rp[sensor][typ] if sensor in rp else rp[typ]
-    return np.asarray(rp, dtype=np.float64)[control_links].copy()
+    rp = rp[sensor] if sensor in rp else rp
+    if typ not in rp:
+        # the reference's tables decide which pairings exist (e.g. surface_follow has MG400 rest poses for `forward` only):
+        # its own constructor dies with the same KeyError (rest_poses_dict[arm][sensor][type])
+        raise KeyError("the reference has no %s rest pose for %s + %s / %s" % (env, arm, sensor, typ))
+    return np.asarray(rp[typ], dtype=np.float64)[control_links].copy()
 
 
 def load_refimg(sensor, typ, S):
