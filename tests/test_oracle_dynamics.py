@@ -3,6 +3,7 @@ RNEA(q, qd, ABA(q, qd, tau)) == tau, M^-1 symmetric positive definite, motor-onl
 import ctypes as C
 
 import numpy as np
+import pytest
 
 
 def _model(oracle):
@@ -121,3 +122,27 @@ def test_free_body_known_answers(oracle):
     assert np.linalg.norm(L2 - L0) < 2e-2 * np.linalg.norm(L0)
     assert abs(0.5 * np.dot(w2, L2) - E0) < 2e-2 * E0
     assert np.linalg.norm(R2 - R1) > 0.5          # it did tumble
+
+
+@pytest.mark.parametrize("arm,sensor", [("ur5", "tactip"), ("mg400", "digitac")])
+def test_mass_matrix_from_link_jacobians(oracle, arm, sensor):
+    """A third, independent route to the joint-space inertia: M = sum_links J_v^T m J_v + J_w^T (R I R^T) J_w from the
+    (finite-difference-checked) link Jacobians at the inertial frames, against the inverse of the oracle's ABA-built M^-1.
+    Ties the dynamics restatement to the kinematics one without going through either dynamics algorithm."""
+    typ = "standard"
+    m = oracle.load_model(arm, sensor, typ, [0.65, 0, 0.035], [-np.pi, 0, np.pi / 2], np.zeros((6, 2)))
+    rest = np.array(oracle.rest_pose("edge_follow", arm, sensor, typ, m)[: m.ndof])
+    rng = np.random.RandomState(4)
+    for k in range(3):
+        q = rest + rng.uniform(-0.3, 0.3, m.ndof) * (1.0 if arm == "ur5" else 0.2)
+        P, Q = oracle.link_states(m, q)
+        M = np.zeros((m.ndof, m.ndof))
+        for i in range(m.nlinks):
+            if m.mass[i] <= 0:
+                continue
+            J = oracle.jacobian(m, q, i)
+            R = oracle.mat_from_quat(Q[i])
+            Iw = R @ np.diag(np.array(m.inertia[i][:])) @ R.T
+            M += m.mass[i] * J[:3].T @ J[:3] + J[3:].T @ Iw @ J[3:]
+        Minv = oracle.mass_matrix_inverse(m, q)
+        assert np.allclose(Minv @ M, np.eye(m.ndof), atol=1e-8), np.abs(Minv @ M - np.eye(m.ndof)).max()
