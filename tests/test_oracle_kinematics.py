@@ -52,3 +52,29 @@ def test_euler_quat_roundtrip(oracle):
     for _ in range(100):
         rpy = rng.uniform([-np.pi, -1.5, -np.pi], [np.pi, 1.5, np.pi])
         assert np.allclose(oracle.euler_from_quat(oracle.quat_from_euler(rpy)), rpy, atol=1e-9)
+
+
+def test_inverse_kinematics_reaches_the_target(oracle):
+    """or_inverse_kinematics (the damped-least-squares restatement of pb.calculateInverseKinematics, base_robot_arm.py:201-209):
+    from the rest pose, targets a few centimetres / degrees away are met by forward kinematics to the solver's residual, and a
+    target at the current pose leaves the joints where they are."""
+    import ctypes as C
+
+    m = oracle.load_model("ur5", "tactip", "standard", [0.65, 0, 0.035], [-np.pi, 0, np.pi / 2], np.zeros((6, 2)))
+    rest = np.array(oracle.rest_pose("edge_follow", "ur5", "tactip", "standard", m)[:6])
+    dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+    P0, Q0 = oracle.link_states(m, rest)
+    rng = np.random.RandomState(8)
+    for k in range(5):
+        dpos = rng.uniform(-0.03, 0.03, 3) if k else np.zeros(3)
+        drpy = rng.uniform(-0.2, 0.2, 3) if k else np.zeros(3)
+        tpos = P0[m.tcp_link] + dpos
+        _, tq = oracle.mul_transforms(np.zeros(3), oracle.quat_from_euler(drpy), np.zeros(3), Q0[m.tcp_link])
+        q = np.zeros(8)
+        oracle.lib().or_inverse_kinematics(C.byref(m), dp(rest), dp(tpos), dp(tq), q.ctypes.data_as(C.POINTER(C.c_double)))
+        P, Q = oracle.link_states(m, q[:6])
+        # the damping (0.5 on the diagonal of J^T J) makes the last approach slow: 100 iterations leave ~1e-5 m / rad
+        assert np.linalg.norm(P[m.tcp_link] - tpos) < 5e-5, (k, np.linalg.norm(P[m.tcp_link] - tpos))
+        assert 1.0 - abs(np.dot(Q[m.tcp_link], tq)) < 1e-8, k
+        if k == 0:
+            assert np.allclose(q[:6], rest, atol=1e-12)
