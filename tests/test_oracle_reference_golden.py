@@ -501,3 +501,18 @@ def test_committed_golden_is_what_the_reference_source_produces(tmp_path):
     outj = str(tmp_path / "params.json")
     subprocess.run([sys.executable, os.path.join(root, "tools", "make_reference_params.py"), "/root/reference", outj], check=True, capture_output=True)
     assert json.load(open(outj)) == json.load(open(os.path.join(root, "tests", "golden", "reference_params.json")))
+
+
+def test_balance_reset_scene(oracle):
+    """object_balance's reset_task + reset_object (object_balance_env.py:295-381) run from the reference source: gravity, the
+    constraint pivot, the pole's start position and the one-off 0.1 N push (where and which way), for three seeds"""
+    for row in GOLD["balance_reset_rows"]:
+        seed, log = int(row[0]), row[1:7]                       # draws: gravity, embed, choice, rand, choice, rand
+        g, pivot, init_pos, force, fpos = row[7], row[8:11], row[11:14], row[14:17], row[17:20]
+        b = oracle.ObjectBalanceOracle(image_size=64, seed=seed)
+        b.reset()
+        assert b.m.gravity[2] == g == log[0] and b.embed_dist == log[1]
+        assert np.allclose(np.array(b.o.pivot_b[:]), pivot, atol=1e-15)
+        assert np.allclose(b.init_obj_pos, init_pos, atol=1e-15) and np.allclose(np.array(b.o.pos[:]), init_pos, atol=1e-15)
+        assert np.allclose(np.array(b.o.ext_force[:]), force, atol=0) and np.allclose(np.array(b.o.ext_pos[:]), fpos, atol=1e-15)
+        assert b.o.ext_pending == 1

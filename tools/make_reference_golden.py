@@ -613,6 +613,25 @@ def main():
     acts = rng.uniform(-0.3, 0.3, (12, 2))
     out["act_surfvert_vertical_in"], out["act_surfvert_vertical_out"] = acts, np.array([ev.scale_actions(ev.encode_actions(a)) for a in acts])
 
+    # ---- O. object_balance's reset as the reference runs it (reset_task + reset_object, object_balance_env.py:295-381): the episode's
+    # gravity, the constraint pivot handed to changeConstraint, the pole's start pose and the one-off external force (point, vector)
+    rows = []
+    for seed in (201, 202, 203):
+        pb = ScenePB()
+        rec = {}
+        pb.setGravity = lambda x, y, z: rec.update(gravity=(x, y, z))
+        pb.changeConstraint = lambda cid, **kw: rec.update(pivot=tuple(kw["jointChildPivot"]))
+        pb.applyExternalForce = lambda uid, link, force, pos, flags=None: rec.update(force=tuple(float(v) for v in force), fpos=tuple(float(v) for v in pos))
+        pb.WORLD_FRAME = 1
+        rng_ = RecRNG(seed)
+        e = bare(BalanceR, _pb=pb, np_random=rng_, rand_gravity=True, rand_embed_dist=True, t_s_name="tactip", object_mode="pole", obj_id=3,
+                 obj_base_width=0.1, obj_base_height=0.0025, embed_dist=0.0035, init_obj_pos=[0.55, 0.0, 0.35], init_obj_orn=(0, 0, 0, 1),
+                 workframe_pos=np.array([0.55, 0.0, 0.35]), obj_tip_constraint_id=1)
+        e.reset_task()
+        e.reset_object()
+        rows.append([seed, *rng_.log, rec["gravity"][2], *rec["pivot"], *e.init_obj_pos, *rec["force"], *rec["fpos"]])
+    out["balance_reset_rows"] = np.array(rows, dtype=np.float64)
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
