@@ -516,3 +516,27 @@ def test_balance_reset_scene(oracle):
         assert np.allclose(b.init_obj_pos, init_pos, atol=1e-15) and np.allclose(np.array(b.o.pos[:]), init_pos, atol=1e-15)
         assert np.allclose(np.array(b.o.ext_force[:]), force, atol=0) and np.allclose(np.array(b.o.ext_pos[:]), fpos, atol=1e-15)
         assert b.o.ext_pending == 1
+
+
+def test_push_and_roll_reset_scenes(oracle):
+    """reset_object of object_push (object_push_env.py:196-229) and reset_task / update_workframe / reset_object / make_goal of
+    object_roll (object_roll_env.py:176-256) run from the reference source: start poses, mass, radius, work frame, TCP-frame goal"""
+    for row in GOLD["push_reset_rows"]:
+        seed, ang, mass = int(row[0]), row[1], row[2]
+        pos, orn, mass_set = row[3:6], row[6:10], row[10]
+        p = oracle.ObjectPushOracle(image_size=64, arm="ur5", sensor="tactip", rand_init_orn=True, rand_obj_mass=True, seed=seed)
+        p.reset()
+        assert np.allclose(np.array(p.o.pos[:]), pos, atol=1e-15) and p.o.mass == mass == mass_set
+        assert abs(abs(np.dot(np.array(p.o.quat[:]), orn)) - 1.0) < 1e-15
+    for row in GOLD["roll_reset_rows"]:
+        seed, (scale, embed, dx, dy, gang, gdist) = int(row[0]), row[1:7]
+        radius, wpos, obj_pos, scaling, goal_tcp = row[7], row[8:11], row[11:14], row[14], row[15:18]
+        r = oracle.ObjectRollOracle(image_size=64, rand_obj_size=True, rand_embed_dist=True, rand_init_obj_pos=True, seed=seed)
+        r.reset()
+        assert r.radius == radius and scaling == scale and r.embed_dist == embed
+        assert np.allclose(r.workframe_pos, wpos, atol=1e-15) and np.allclose(np.array(r.o.pos[:]), obj_pos, atol=1e-15)
+        assert np.allclose(r.goal_pos_tcp, goal_tcp, atol=1e-15)
+        # the goal in the world for the TCP pose the generator injected (:258-286)
+        r.tcp_world = lambda: (np.array([0.65, 0.0, 0.004]), oracle.quat_from_euler([-np.pi, 0.0, np.pi / 2]))
+        r.update_goal()
+        assert np.allclose(r.goal_pos_world, row[18:21], atol=1e-12)

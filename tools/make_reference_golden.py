@@ -632,6 +632,33 @@ def main():
         rows.append([seed, *rng_.log, rec["gravity"][2], *rec["pivot"], *e.init_obj_pos, *rec["force"], *rec["fpos"]])
     out["balance_reset_rows"] = np.array(rows, dtype=np.float64)
 
+    # ---- P. object_push / object_roll reset scenes from the reference source: the cube's start pose and mass (reset_object,
+    # object_push_env.py:196-229), the marble's radius, start position, work frame and TCP-frame goal (object_roll_env.py:176-256)
+    rows = []
+    for seed in (301, 302):
+        pb = ScenePB(); rec = {}
+        pb.changeDynamics = lambda uid, link, **kw: rec.update({k: v for k, v in kw.items() if k == "mass"})
+        rng_ = RecRNG(seed)
+        e = bare(PushR, _pb=pb, np_random=rng_, rand_init_orn=True, rand_obj_mass=True, obj_id=7, init_obj_pos=[0.55, -0.16, 0.04])
+        e.reset_object()
+        rows.append([seed, *rng_.log, *pb.bodies[7][0], *pb.bodies[7][1], rec["mass"]])
+    out["push_reset_rows"] = np.array(rows, dtype=np.float64)
+    rows = []
+    for seed in (303, 304):
+        pb = ScenePB()
+        arm = bare(BaseRobotArm, _pb=PB())
+        arm.set_workframe([0.65, 0.0, 0.0035], [-np.pi, 0.0, np.pi / 2])
+        arm.get_current_TCP_pos_vel_worldframe = lambda: (np.array([0.65, 0.0, 0.004]), np.zeros(3), np.array(PB.getQuaternionFromEuler([-np.pi, 0.0, np.pi / 2])), np.zeros(3), np.zeros(3))
+        rng_ = RecRNG(seed)
+        e = bare(RollR, _pb=pb, np_random=rng_, robot=types.SimpleNamespace(arm=arm), rand_obj_size=True, rand_embed_dist=True, rand_init_obj_pos=True,
+                 default_obj_radius=0.0025, embed_dist=0.0015, obj_id=5, object_path="sphere.urdf", workframe_rpy=np.array([-np.pi, 0.0, np.pi / 2]),
+                 visualise_goal=False)
+        pb.loadURDF = lambda path, pos, orn, **kw: rec2.update(pos=tuple(pos), scaling=kw.get("globalScaling")) or 5
+        rec2 = {}
+        e.reset_task(); e.update_workframe(); e.reset_object(); e.make_goal()
+        rows.append([seed, *rng_.log, e.scaled_obj_radius, *e.workframe_pos, *rec2["pos"], rec2["scaling"], *e.goal_pos_tcp, *e.goal_pos_worldframe])
+    out["roll_reset_rows"] = np.array(rows, dtype=np.float64)
+
     np.savez_compressed(OUT, **out)
     print("wrote %s: %d arrays" % (OUT, len(out)))
 
