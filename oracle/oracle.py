@@ -584,16 +584,18 @@ def heightfield_tris(V, i0, i1, j0, j1):
 
 
 class SurfaceFollowOracle:
-    """Restates SurfaceFollowAutoEnv (rl_envs/exploration/surface_follow/surface_follow_auto/surface_follow_auto_env.py)
-    on BaseSurfaceEnv (rl_envs/exploration/surface_follow/base_surface_env.py), noise_mode "simplex", movement modes
-    "xyz" / "xyzRxRy".  One env instance.  The tip core <-> table contact (only reachable in the deepest valleys,
+    """Restates the three surface envs (rl_envs/exploration/surface_follow/surface_follow_{auto,goal,vert}/*_env.py) on
+    BaseSurfaceEnv (rl_envs/exploration/surface_follow/base_surface_env.py).  One env instance.  The tip core <-> table contact (only reachable in the deepest valleys,
     SURVEY.md 8a R5) is not modelled."""
 
     def __init__(self, image_size=128, arm="ur5", sensor="digit", max_steps=200, movement_mode="xyzRxRy", seed=None, variant="auto",
                  noise_mode="simplex", reward_mode="dense", render=True, control_mode="TCP_velocity_control"):
-        self.control_mode = control_mode
         """variant "auto": SurfaceFollowAutoEnv (surface_follow-v0); "goal": SurfaceFollowGoalEnv (surface_follow-v1,
-        surface_follow_goal/surface_follow_goal_env.py: the policy steers x / y, the reward adds the goal distance)"""
+        surface_follow_goal/surface_follow_goal_env.py: the policy steers x / y, the reward adds the goal distance); "vert":
+        SurfaceFollowVertEnv (surface_follow-v2, surface_follow_vert/surface_follow_vert_env.py: x steered, y driven, 10 / 3 weights).
+        noise_mode "simplex" | "none" | "vertical_simplex" (the upright surface of -v2, `forward` sensors); movement modes
+        yz / xyz / yzRx / xyzRxRy (+ xRz for "vert"); reward_mode dense | sparse; render=False skips the images."""
+        self.control_mode = control_mode
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
         self.max_steps, self.movement_mode, self.variant = max_steps, movement_mode, variant
         self.noise_mode, self.reward_mode, self.render = noise_mode, reward_mode, render
