@@ -917,6 +917,9 @@ int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_wor
     double tpos[3], targ_orn[4], targ_j[OR_MAXD];
     or_tcp_position_target(m, s->q, delta_work, tpos, targ_orn);
     or_inverse_kinematics(m, s->q, tpos, targ_orn, targ_j);
+    if (m->mg400_slave) { /* MG400.tcp_position_control (mg400.py:167-172) */
+        targ_j[n - 3] = targ_j[1]; targ_j[n - 2] = -targ_j[1]; targ_j[n - 1] = targ_j[1] + targ_j[2];
+    }
     for (int i = 0; i < n; i++) {
         s->motor_mode[i] = 1; s->target_pos[i] = targ_j[i]; s->target_vel[i] = 0;
         s->kp[i] = m->pos_gain; s->kd[i] = m->vel_gain; s->max_force[i] = m->max_force;

@@ -842,6 +842,13 @@ __device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhy
 #pragma unroll
     for (int i = 0; i < NB; i++) { mot.target_pos[i] = q[i]; mot.target_vel[i] = 0.0; }
     for (int it = 0; it >= 0;) it = ik_chunk<T>(arm, mot.target_pos, tpos, torn, it, 100);
+    if (arm.topo == TG_TOPO_MG400 && NB == 8) {
+        // MG400.tcp_position_control (mg400.py:167-172): the parallelogram's slaved joints follow j2_1 / j3_1 in the IK result too
+        // (not yet run on a GPU: the host config refuses MG400 position control unless TG_UNVERIFIED_MG400_POSCTL is set)
+        mot.target_pos[NB - 3] = mot.target_pos[1];
+        mot.target_pos[NB - 2] = -mot.target_pos[1];
+        mot.target_pos[NB - 1] = mot.target_pos[1] + mot.target_pos[2];
+    }
     double sc[NB][2];
 #pragma unroll
     for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);

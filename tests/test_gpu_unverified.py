@@ -1,11 +1,12 @@
-"""surface_follow-v2 on its own surface (noise_mode "vertical_simplex": upright heightfield, `forward` sensor type), CUDA path
-against the CPU oracle - NOT YET RUN ON A GPU.
+"""Device code written after round 1's GPU budget was spent - NOT YET RUN ON A GPU: (1) surface_follow-v2 on its own surface
+(noise_mode "vertical_simplex": upright heightfield, `forward` sensor type), (2) TCP_position_control on the MG400 (slaved joints
+in the IK result, mg400.py:167-172).  CUDA path against the CPU oracle, each case in its own subprocess.
 
 The device code for this mode (TgTask.surf_vertical: row-wise 1-d heights, flipped goal / normals / surface distance, the camera
 brought into the heightfield's frame for raster_hf_kernel) was written after round 1's GPU budget was spent.  The oracle side is
 pinned to the reference's source on the CPU (tests/test_oracle_reference_golden.py::test_vertical_surface_geometry_and_rewards),
 but the kernels themselves have never executed, so:
-  * the product keeps refusing the mode (NotImplementedError) unless TG_UNVERIFIED_VERTICAL is set;
+  * the product keeps refusing the mode (NotImplementedError) unless TG_UNVERIFIED_VERTICAL (TG_UNVERIFIED_MG400_POSCTL for the second) is set;
   * this test runs in a SUBPROCESS with that variable set - a fault in the new code cannot poison the CUDA context of the rest
     of the suite - and is a non-strict xfail: an XPASS on the first GPU run is the signal to drop both the gate and the mark.
 """
@@ -97,3 +98,56 @@ def test_vertical_surface_matches_oracle(arm, sensor, S, obs_mode):
     env = dict(os.environ, TG_UNVERIFIED_VERTICAL="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "VERTICAL-OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+
+
+CHILD_POSCTL = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import tactile_gym_b200 as tg
+from oracle import oracle as O
+
+O.build()
+n, nb = 5, 8
+modes = {"movement_mode": "xyzRz", "control_mode": "TCP_position_control", "noise_mode": "rand_height", "observation_mode": "oracle",
+         "reward_mode": "dense", "arm_type": "mg400", "tactile_sensor_name": "digitac"}
+env = tg.make_vec("edge_follow-v0", n, env_kwargs={"env_modes": modes, "image_size": [64, 64], "max_steps": 200})
+rng = np.random.RandomState(17)
+draws = np.stack([rng.uniform(0.0015, 0.0045, (n, 2)), rng.uniform(-np.pi, np.pi, (n, 2))], axis=2)
+env.world.set_draws(draws)
+obs = env.reset()["oracle"]
+st = env.world.get_state()
+refs = []
+for i in range(n):
+    r = O.EdgeFollowOracle(image_size=64, arm="mg400", sensor="digitac", movement_mode="xyzRz", control_mode="TCP_position_control")
+    r.reset(draws=tuple(draws[i, 0]))
+    refs.append(r)
+p0 = obs[:, 0:3].copy()
+for k in range(8):
+    act = rng.uniform(-0.25, 0.25, (n, 4)).astype(np.float32)
+    if k < 5:
+        act[:, 0] = 0.25
+    for i, r in enumerate(refs):
+        for j in range(nb):
+            r.s.q[j] = st[i, j]; r.s.qd[j] = st[i, nb + j]
+        r.steps = int(st[i, 2 * nb + 9])
+        r.step(act[i])
+    o, rew, done, infos = env.step(act)
+    st = env.world.get_state()
+    for i, r in enumerate(refs):
+        assert np.allclose(st[i, :nb], np.array(r.s.q[:nb]), atol=1e-9), ("joints", k, i, np.abs(st[i, :nb] - np.array(r.s.q[:nb])).max())
+        assert abs(rew[i] - r.reward) < 1e-6 and bool(done[i]) == r.done, ("reward", k, i)
+        assert np.allclose(o["oracle"][i], r.oracle_obs(), atol=2e-5), ("oracle obs", k, i)
+    if k == 4:
+        moved = np.abs(o["oracle"][:, 0] - p0[:, 0])
+        assert np.all(moved > 0.004) and np.all(moved < 0.0055), moved
+env.close()
+print("POSCTL-OK")
+'''
+
+
+@pytest.mark.xfail(strict=False, reason="MG400 position control written after the round-1 GPU budget was spent; never run on a GPU")
+def test_mg400_position_control_matches_oracle():
+    env = dict(os.environ, TG_UNVERIFIED_MG400_POSCTL="1")
+    out = subprocess.run([sys.executable, "-c", CHILD_POSCTL % {"root": ROOT}], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "POSCTL-OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])

@@ -133,3 +133,18 @@ def test_vertical_surface_env(oracle):
     # 1 mm per step along the drawn direction (work frame rpy (-pi, 0, 0): its y is the world's -y)
     assert abs(abs(p1[1] - y0) - 0.02) < 1e-3 and np.sign(p1[1] - y0) == -e.dirs[1]
     assert abs(p1[0] - p[0]) < 5e-4 and abs(p1[2] - p[2]) < 5e-4 and -1.0 < r < 0.0 and not d
+
+
+def test_mg400_position_control(oracle):
+    """MG400.tcp_position_control (mg400.py:131-190): the IK result's slaved joints follow j2_1 / j3_1; the 4-dof arm never meets
+    blocking_move's orientation tolerance exactly, so every move runs its 10 substeps; 1 mm per full-scale step all the same"""
+    e = oracle.EdgeFollowOracle(image_size=64, arm="mg400", sensor="digitac", movement_mode="xyzRz", control_mode="TCP_position_control", seed=1)
+    e.reset()
+    p0 = e.oracle_obs()[:3].copy()
+    for k in range(5):
+        e.step(np.array([0.25, 0.0, 0.0, 0.0], np.float32))
+        assert e.last_move_substeps == 10
+        q = np.array(e.s.q[:8])
+        assert abs(q[5] - q[1]) + abs(q[6] + q[1]) + abs(q[7] - (q[1] + q[2])) < 5e-6
+    d = e.oracle_obs()[:3] - p0
+    assert abs(d[0] - 0.005) < 1e-4 and abs(d[1]) < 1e-4 and abs(d[2]) < 1e-4
