@@ -96,7 +96,7 @@ def test_vertical_surface_matches_oracle(arm, sensor, S, obs_mode):
     code = CHILD % {"root": ROOT, "arm": arm, "sensor": sensor, "S": S, "obs": obs_mode, "render": "True" if obs_mode == "tactile" else "False",
                     "steps": 8}
     env = dict(os.environ, TG_UNVERIFIED_VERTICAL="1")
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=150, env=env)
     assert out.returncode == 0 and "VERTICAL-OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
 
 
@@ -149,5 +149,5 @@ print("POSCTL-OK")
 @pytest.mark.xfail(strict=False, reason="MG400 position control written after the round-1 GPU budget was spent; never run on a GPU")
 def test_mg400_position_control_matches_oracle():
     env = dict(os.environ, TG_UNVERIFIED_MG400_POSCTL="1")
-    out = subprocess.run([sys.executable, "-c", CHILD_POSCTL % {"root": ROOT}], capture_output=True, text=True, timeout=300, env=env)
+    out = subprocess.run([sys.executable, "-c", CHILD_POSCTL % {"root": ROOT}], capture_output=True, text=True, timeout=150, env=env)
     assert out.returncode == 0 and "POSCTL-OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
