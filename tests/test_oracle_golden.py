@@ -13,7 +13,8 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "oracle_trajectories.npz")
 
 
-@pytest.mark.parametrize("case", ["edge", "edge_mg400_digitac", "balance", "surface", "surface_goal", "push", "roll"])
+@pytest.mark.parametrize("case", ["edge", "edge_mg400_digitac", "balance", "surface", "surface_goal", "push", "roll", "edge_posctl", "edge_sparse",
+                                  "surface_yzRx_sparse", "surface_vert_flat", "surface_vertical", "surface_posctl", "push_mg400_mini_tactip"])
 def test_oracle_replays_golden_trajectory(oracle, case):
     import make_oracle_golden as G
 
@@ -29,5 +30,5 @@ def test_oracle_replays_golden_trajectory(oracle, case):
     assert np.all(np.abs(dig[:, 1] - g[:, 1]) <= 8) and np.all(np.abs(dig[:, 2] - g[:, 2]) <= 4), (dig[:, 1:], g[:, 1:])
     same = (dig[:, 1] == g[:, 1]) & (dig[:, 2] == g[:, 2])
     assert np.mean(dig[same, 0] == g[same, 0]) > 0.8
-    if case not in ("edge_mg400_digitac", "push"):      # (those two start clear of the stimulus: DIGIT-type images stay blank)
+    if case not in ("edge_mg400_digitac", "push", "push_mg400_mini_tactip"):      # (those two start clear of the stimulus: DIGIT-type images stay blank)
         assert g[:, 2].max() > 20      # the trajectories do touch the stimulus: the images are not blank
