@@ -219,13 +219,20 @@ const char* tg_last_error(void);
 int tg_create(const TgConfig* cfg, int device, TgWorld** out);
 int tg_destroy(TgWorld* w);
 
-/* Upload random draws for future resets: h_draws[n_envs][rounds][n_draws] (double).  The r-th reset of
- * env i after this call consumes h_draws[i][r].  Synchronous host->device copy. */
+/* Start a sequence of random draws for future resets: h_draws[n_envs][rounds][n_draws] (double).  The r-th reset of env i after
+ * this call consumes h_draws[i][r] (r < rounds).  Synchronous host->device copy; pre-computed next episodes are recomputed. */
 int tg_set_draws(TgWorld* w, const double* h_draws, int rounds);
-/* Same upload, but the sequence CONTINUES: pre-computed standby episodes (which already consumed their draws) stay
- * valid.  h_draws[i][0] must be env i's first unconsumed draw (see tg_get_reset_counts). */
-int tg_refill_draws(TgWorld* w, const double* h_draws, int rounds);
-/* Sticky error flag of the reset pipeline (0: none; nothing raises it since the slots became resumable); synchronises */
+/* Keeping the sequence fed without synchronising.  The device buffer is a RING: the r-th reset of env i reads slot r % rounds
+ * and needs r < avail[i] (tg_set_draws: avail = rounds).
+ *   tg_draws_poll:   enqueue on `stream` the device->host copy of resets consumed per env [N] followed by the error flags [1]
+ *                    into h_counts (page-locked, N + 1 ints); the caller waits for it with its own event.
+ *   tg_draws_upload: enqueue the host->device copy of the whole ring h_ring[N][rounds][n_draws] and of h_avail[N] (both
+ *                    page-locked, untouched until the copy has run).  The caller may only have changed slots whose draws were
+ *                    consumed (r < counts[i]); every other slot must hold what the device already has. */
+int tg_draws_poll(TgWorld* w, int32_t* h_counts, void* stream);
+int tg_draws_upload(TgWorld* w, const double* h_ring, const int32_t* h_avail, void* stream);
+/* Sticky error flags (0: none).  bit 0: reset pipeline / heightfield raster overflow; bit 1: a reset found no draw left in the
+ * ring (it used TgTask.draw_default): the host fell behind with tg_draws_upload.  Synchronises. */
 int tg_pipeline_error(TgWorld* w, void* stream);
 /* Number of episode ends so far that found their pre-computed next episode unfinished and completed it inline
  * (exact either way; a performance counter: episodes shorter than the ~8 launches a rebuild takes).  Synchronises. */

@@ -1017,6 +1017,11 @@ void or_depth_image(const double eye[3], const double fwd[3], const double up[3]
 /* TactileSensor.t_s_camera (tactile_sensor.py:261-294), float32 arithmetic like numpy */
 /* TactileSensor.t_s_camera's arithmetic (tactile_sensor.py:268-292) on a given depth image, float32 as numpy does it:
  * diff = cur - nodef; |diff| <= 1e-4 -> 0; uint8(clip(|diff|, 0, 0.05) / 0.05 * 255); border pixels take the baked grey. */
+/* `pen_img[full_mask] = 0` (tactile_sensor.py:283-288: pixels whose segmentation id is the sensor body) has no line here on
+ * purpose: `cur` is nodef_dep with the stimulus composited in, so a pixel where the body is the nearest surface has
+ * cur == nodef_dep -> diff 0 -> already 0, and where the stimulus is nearer the segmentation id is the stimulus' and the
+ * reference keeps the value as well.  tests/test_oracle_raster.py::test_body_mask_zeroing_is_an_identity_for_the_composited_depth
+ * applies the reference's line with a segmentation built from the sensor meshes and finds no pixel changed. */
 void or_postprocess(int S, const float* cur, const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,
                     int border_on, unsigned char* img_out)
 {

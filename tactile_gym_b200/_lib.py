@@ -94,7 +94,7 @@ class TgHostStep(C.Structure):
 
 
 EXPORTS = [
-    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_refill_draws", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
+    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
     "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
     "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_launch_count",
 ]
@@ -120,7 +120,8 @@ def load():
     lib.tg_create.argtypes = [C.POINTER(TgConfig), C.c_int, C.POINTER(vp)]
     lib.tg_destroy.argtypes = [vp]
     lib.tg_set_draws.argtypes = [vp, vp, C.c_int]
-    lib.tg_refill_draws.argtypes = [vp, vp, C.c_int]
+    lib.tg_draws_poll.argtypes = [vp, vp, vp]
+    lib.tg_draws_upload.argtypes = [vp, vp, vp, vp]
     lib.tg_pipeline_error.argtypes = [vp, vp]
     lib.tg_pipeline_stalls.argtypes = [vp, vp]
     lib.tg_get_reset_counts.argtypes = [vp, vp, vp]

@@ -37,8 +37,10 @@ struct EnvBuffers {
     int* steps;           // [N]
     int* reset_substeps;  // [N]
     int* reset_count;     // [N] draws consumed since tg_set_draws
-    const double* draws;  // [N][rounds][n_draws] or null
+    const double* draws;  // [N][rounds][n_draws] or null: a ring, the k-th reset of env e reads slot k % rounds
     int draw_rounds;
+    const int* draw_avail; // [N] draws uploaded so far per env (reset_count[e] < draw_avail[e] or the draw is missing)
+    int epoch;            // launch counter: tags the slots consumed in THIS launch (SB_CONSUMED + epoch)
     double* cam;          // [N][12] eye fwd up right
     double* stim;         // [N][12] R(9) t(3) of the stimulus frame
     double* tcp;          // [N][7] tcp world pos + quat (state export)
@@ -76,7 +78,11 @@ struct EnvBuffers {
     int* stall_count;        // episode ends that had to complete their standby inline
 };
 
-enum { SB_EMPTY = 0, SB_READY = 1, SB_PARTIAL = 2, SB_BUSY = 3 };
+// SB_CONSUMED + epoch: swapped in during launch `epoch`.  It is EMPTY for every later launch, but the launch that consumed it
+// must not start the rebuild: for surface_follow the rebuild overwrites the heightfield of the episode that just ended, which
+// the terminal-observation raster still reads after this launch.
+enum { SB_EMPTY = 0, SB_READY = 1, SB_PARTIAL = 2, SB_BUSY = 3, SB_CONSUMED = 16 };
+#define SB_EPOCH_MASK 0x0fffffff
 #define RESET_CHUNK 6  // blocking-move iterations per quantum (a quarter of an env step's work: a standby warp may
                        // carry an IK quantum and a move quantum one after the other, plus cold code)
 #define IK_CHUNK 8     // IK iterations per quantum
@@ -299,10 +305,13 @@ __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, c
     for (int d = 0; d < TG_MAXDRAW; d++) r.draw[d] = task.draw_default[d];
     {
         const int cnt = b.reset_count[e];
-        if (b.draws && cnt < b.draw_rounds) {
+        if (b.draws) {
+            if (cnt < b.draw_avail[e]) {
+                const int slot = cnt % b.draw_rounds;
 #pragma unroll
-            for (int d = 0; d < TG_MAXDRAW; d++)
-                if (d < task.n_draws) r.draw[d] = b.draws[((size_t)e * b.draw_rounds + cnt) * task.n_draws + d];
+                for (int d = 0; d < TG_MAXDRAW; d++)
+                    if (d < task.n_draws) r.draw[d] = b.draws[((size_t)e * b.draw_rounds + slot) * task.n_draws + d];
+            } else atomicOr(b.error_flag, 2); // draws exhausted: the defaults are used and the host is told (tg_draws_poll)
         }
         b.reset_count[e] = cnt + 1;
     }
@@ -626,7 +635,7 @@ TGD void consume_standby(const EnvBuffers& b, int e)
     }
     if (b.height) b.hf_cur[e] = 1 - b.hf_cur[e]; // the heightfield built for this episode becomes the live one
     __threadfence();
-    atomicExch(&b.sb_ready[e], SB_EMPTY);
+    atomicExch(&b.sb_ready[e], SB_CONSUMED + (b.epoch & SB_EPOCH_MASK));
 }
 
 // get_extended_feature_array (object_roll_env.py:402-408): the goal position in the TCP frame
@@ -763,11 +772,12 @@ TGD void standby_work(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
 {
     const int s = atomicAdd(&b.sb_ready[e], 0);
     if (s == SB_READY || s == SB_BUSY) return;
+    if (!complete && s == SB_CONSUMED + (b.epoch & SB_EPOCH_MASK)) return; // consumed in this launch: the next one starts the rebuild
     if (atomicCAS(&b.sb_ready[e], s, SB_BUSY) != s) return;
     __threadfence();
     ResetState<T::NB> r;
     bool fin = false;
-    if (s == SB_EMPTY) reset_begin<T>(arm, task, b, e, r);
+    if (s == SB_EMPTY || s >= SB_CONSUMED) reset_begin<T>(arm, task, b, e, r);
     else load_partial<T::NB>(b, e, r);
     fin = reset_advance<T>(arm, ph, task, b, e, r);
     if (complete) {
@@ -844,7 +854,6 @@ __device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhy
     for (int it = 0; it >= 0;) it = ik_chunk<T>(arm, mot.target_pos, tpos, torn, it, 100);
     if (arm.topo == TG_TOPO_MG400 && NB == 8) {
         // MG400.tcp_position_control (mg400.py:167-172): the parallelogram's slaved joints follow j2_1 / j3_1 in the IK result too
-        // (not yet run on a GPU: the host config refuses MG400 position control unless TG_UNVERIFIED_MG400_POSCTL is set)
         mot.target_pos[NB - 3] = mot.target_pos[1];
         mot.target_pos[NB - 2] = -mot.target_pos[1];
         mot.target_pos[NB - 1] = mot.target_pos[1] + mot.target_pos[2];
@@ -1031,7 +1040,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         roll_step_data(task, ob, tp, tq, tr[0], tr[1], steps, &r, &d);
         double* st = b.stim + (size_t)e * 12;
         st[0] = ob.ext_pos[0]; st[9] = ob.pos[0]; st[10] = ob.pos[1]; st[11] = ob.pos[2];
-        float* f = (d && autoreset && b.pipeline) ? b.term_feat : b.feat;
+        float* f = (d && autoreset && b.term_feat) ? b.term_feat : b.feat;
         if (f) roll_features(tr, f + (size_t)e * TG_PUSH_NFEAT);
     } else if (push) {
         const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
@@ -1040,7 +1049,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         b.goal[e] = goal;
         obj_stim(task, ob, b.stim + (size_t)e * 12);
         // the observation is taken after get_step_data: the feature carries the (possibly advanced) goal
-        float* f = (d && autoreset && b.pipeline) ? b.term_feat : b.feat;
+        float* f = (d && autoreset && b.term_feat) ? b.term_feat : b.feat;
         if (f) push_features(task, tp, tq, tr, tr[2 * PUSH_NTRAJ], goal, f + (size_t)e * TG_PUSH_NFEAT);
     } else if (balance) {
         balance_step_data(task, ob, b.embed[e], steps, &r, &d);
@@ -1057,7 +1066,7 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
             const double gx = tp[0] - meta[3], gy = tp[1] - meta[4], gz = tp[2] - meta[5];
             r = sqrt(gx * gx + gy * gy + gz * gz) < task.termination_dist ? (float)acc : 0.0f;
         }
-        float* f = (d && autoreset && b.pipeline) ? b.term_feat : b.feat;
+        float* f = (d && autoreset && b.term_feat) ? b.term_feat : b.feat;
         if (f) surface_features(task, b.hf_meta + hb * SURF_META, tp, tq, f + (size_t)e * TG_PUSH_NFEAT);
     } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
     reward[e] = r; done[e] = d;

@@ -49,6 +49,9 @@ struct TgWorld {
     RasterArgs ra{};
     std::vector<void*> allocs;
     double* d_draws = nullptr;
+    int* d_draw_avail = nullptr;
+    int draw_capacity = 0;            // doubles allocated behind d_draws
+    int epoch = 0;                    // bumped by every launch that may touch the standby slots
     unsigned char* d_done_internal = nullptr;
     float* d_reward_internal = nullptr;
     size_t raster_smem = 0;
@@ -120,6 +123,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     CK(cudaSetDevice(device));
 
     TgWorld* w = new TgWorld();
+    struct Guard { TgWorld* w; ~Guard() { if (w) tg_destroy(w); } } guard{w};   // every early return below frees the partial world
     w->cfg = *cfg;
     w->device = device;
     w->n = cfg->n_envs; w->nb = cfg->arm.nb; w->S = S;
@@ -146,7 +150,6 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         (rc = dalloc(w, &b.reset_count, n)) || (rc = dalloc(w, &b.cam, (size_t)12 * n)) || (rc = dalloc(w, &b.stim, (size_t)12 * n)) ||
         (rc = dalloc(w, &b.tcp, (size_t)7 * n)) || (rc = dalloc(w, &rest, nb)) || (rc = dalloc(w, &w->d_done_internal, n)) ||
         (rc = dalloc(w, &w->d_reward_internal, n))) {
-        tg_destroy(w);
         return rc;
     }
     CK(cudaMemcpy(rest, cfg->h_rest_q, sizeof(double) * nb, cudaMemcpyHostToDevice));
@@ -165,7 +168,6 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         (rc = dalloc(w, &b.term_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.term_stim, (size_t)12 * n)) || (rc = dalloc(w, &b.error_flag, 1)) ||
         (rc = dalloc(w, &b.stall_count, 1)) || (rc = dalloc(w, &b.sb_targ, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_cv, n)) || (rc = dalloc(w, &b.sb_ik, n)) ||
         (rc = dalloc(w, &b.sb_draw, (size_t)TG_MAXDRAW * n))) {
-        tg_destroy(w);
         return rc;
     }
     w->standby_blocks = b.pipeline ? std::max(8, std::min(64, w->sm_count / 2)) : 0;
@@ -187,18 +189,16 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         }
     }
     if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
-        if (!b.pipeline) { tg_destroy(w); return fail(TG_EINVAL, "surface_follow needs max_steps >= 2"); }
+        if (!b.pipeline) { return fail(TG_EINVAL, "surface_follow needs max_steps >= 2"); }
         if ((rc = dalloc(w, &b.height, (size_t)2 * SURF_PTS * n)) || (rc = dalloc(w, &b.hf_meta, (size_t)2 * SURF_META * n)) ||
             (rc = dalloc(w, &b.hf_cur, n)) || (rc = dalloc(w, &b.sb_perm, (size_t)256 * n)) || (rc = dalloc(w, &b.sb_surf_it, n)) ||
             (rc = dalloc(w, &b.sb_hmm, (size_t)2 * n)) || (rc = dalloc(w, &b.accum, n)) || (rc = dalloc(w, &w->cam_local, (size_t)12 * n))) {
-            tg_destroy(w);
             return rc;
         }
     }
     if (cfg->task.task == TG_TASK_OBJECT_ROLL) {
         if ((rc = dalloc(w, &b.traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.sb_traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.goal, n)) ||
             (rc = dalloc(w, &b.sb_goal, n))) {
-            tg_destroy(w);
             return rc;
         }
         b.hull = nullptr; b.n_hull = 0;
@@ -207,7 +207,6 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         double* hull = nullptr;
         if ((rc = dalloc(w, &b.traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.sb_traj, (size_t)PUSH_TRAJ_SZ * n)) || (rc = dalloc(w, &b.goal, n)) ||
             (rc = dalloc(w, &b.sb_goal, n)) || (rc = dalloc(w, &hull, (size_t)3 * cfg->n_tip_hull))) {
-            tg_destroy(w);
             return rc;
         }
         CK(cudaMemcpy(hull, cfg->h_tip_hull, sizeof(double) * 3 * cfg->n_tip_hull, cudaMemcpyHostToDevice));
@@ -216,7 +215,6 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     if (cfg->task.task == TG_TASK_OBJECT_BALANCE || cfg->task.task == TG_TASK_OBJECT_PUSH || cfg->task.task == TG_TASK_OBJECT_ROLL) {
         if ((rc = dalloc(w, &b.obj, (size_t)13 * n)) || (rc = dalloc(w, &b.obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.grav, n)) ||
             (rc = dalloc(w, &b.sb_obj, (size_t)13 * n)) || (rc = dalloc(w, &b.sb_obj_ext, (size_t)4 * n)) || (rc = dalloc(w, &b.sb_grav, n))) {
-            tg_destroy(w);
             return rc;
         }
     }
@@ -234,8 +232,8 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         float* dn; uint8_t* db; double* dt; int* dnv;
         const int np = cfg->sensor.n_prim;
         for (int i = 0; i < np; i++)
-            if (cfg->sensor.h_prim_nv[i] != 3 && cfg->sensor.h_prim_nv[i] != 4) { tg_destroy(w); return fail(TG_EINVAL, "primitive %d has %d vertices", i, cfg->sensor.h_prim_nv[i]); }
-        if ((rc = dalloc(w, &dn, px)) || (rc = dalloc(w, &db, px)) || (rc = dalloc(w, &dt, (size_t)std::max(np, 1) * 12)) || (rc = dalloc(w, &dnv, std::max(np, 1)))) { tg_destroy(w); return rc; }
+            if (cfg->sensor.h_prim_nv[i] != 3 && cfg->sensor.h_prim_nv[i] != 4) { return fail(TG_EINVAL, "primitive %d has %d vertices", i, cfg->sensor.h_prim_nv[i]); }
+        if ((rc = dalloc(w, &dn, px)) || (rc = dalloc(w, &db, px)) || (rc = dalloc(w, &dt, (size_t)std::max(np, 1) * 12)) || (rc = dalloc(w, &dnv, std::max(np, 1)))) { return rc; }
         CK(cudaMemcpy(dn, nd.data(), px * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(db, base.data(), px, cudaMemcpyHostToDevice));
         if (np > 0) {
@@ -246,7 +244,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         for (size_t i = 0; i < px; i++) if (nd[i] >= 0.0f) { ndmin = std::min(ndmin, nd[i]); ndmax = std::max(ndmax, nd[i]); }
         RasterArgs& r = w->ra;
         r.nd_ref = ndmin <= ndmax ? 0.5f * (ndmin + ndmax) : 0.5f;
-        if (ndmin <= ndmax && !(ndmin >= 0.5f * r.nd_ref && ndmax <= 2.0f * r.nd_ref)) { tg_destroy(w); return fail(TG_EUNSUPPORTED, "nodef_dep range [%g, %g] too wide for the float path", ndmin, ndmax); }
+        if (ndmin <= ndmax && !(ndmin >= 0.5f * r.nd_ref && ndmax <= 2.0f * r.nd_ref)) { return fail(TG_EUNSUPPORTED, "nodef_dep range [%g, %g] too wide for the float path", ndmin, ndmax); }
         r.n = n; r.S = S; r.bands = S == 256 ? 4 : 1; r.nprim = np; r.prim_nv = dnv;
         r.th = tan(cfg->sensor.fov_deg * (M_PI / 180.0) / 2.0);
         r.near_ = cfg->sensor.near_; r.far_ = cfg->sensor.far_;
@@ -257,7 +255,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         CK(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->raster_smem));
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel, RASTER_THREADS, w->raster_smem));
-        if (per_sm < 1) { tg_destroy(w); return fail(TG_ECUDA, "raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
+        if (per_sm < 1) { return fail(TG_ECUDA, "raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
         int grid = w->sm_count * per_sm;
         grid -= grid % r.bands;
         const int need = ((n + RASTER_WARPS - 1) / RASTER_WARPS) * r.bands;
@@ -276,7 +274,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             w->raster_smem = ((band_px * 5 + 15) & ~size_t(15)) + HF_PER_WARP_SMEM * HF_WARPS;
             CK(cudaFuncSetAttribute(raster_hf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->raster_smem));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_hf_kernel, HF_THREADS, w->raster_smem));
-            if (per_sm < 1) { tg_destroy(w); return fail(TG_ECUDA, "heightfield raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
+            if (per_sm < 1) { return fail(TG_ECUDA, "heightfield raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
             grid = w->sm_count * per_sm;
             grid -= grid % r.bands;
             const int need_hf = ((n + HF_WARPS - 1) / HF_WARPS) * r.bands;
@@ -284,6 +282,9 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             w->raster_grid = grid;
         }
     }
+    if ((rc = dalloc(w, &w->d_draw_avail, n))) return rc;
+    b.draw_avail = w->d_draw_avail;
+    guard.w = nullptr;
     *out = w;
     return TG_OK;
 }
@@ -302,20 +303,35 @@ extern "C" int tg_destroy(TgWorld* w)
     return TG_OK;
 }
 
-static int set_draws_impl(TgWorld* w, const double* h_draws, int rounds, int invalidate)
+// Reset draws live in a device ring [N][rounds][n_draws]: the k-th reset of env e since tg_set_draws reads slot k % rounds and
+// needs k < draw_avail[e].  tg_set_draws starts a sequence (synchronous); tg_draws_poll / tg_draws_upload keep it fed without
+// ever synchronising (the host overwrites only slots whose draws were consumed).
+extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds)
 {
     if (!w || !h_draws || rounds <= 0) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
     CK(cudaDeviceSynchronize());
-    if (w->d_draws) { cudaFree(w->d_draws); w->d_draws = nullptr; }
     const size_t cnt = (size_t)w->n * rounds * w->cfg.task.n_draws;
-    CK(cudaMalloc(&w->d_draws, cnt * sizeof(double)));
+    if ((size_t)w->draw_capacity < cnt) {
+        if (w->d_draws) { cudaFree(w->d_draws); w->d_draws = nullptr; w->draw_capacity = 0; }
+        CK(cudaMalloc(&w->d_draws, cnt * sizeof(double)));
+        w->draw_capacity = (int)cnt;
+    }
     CK(cudaMemcpy(w->d_draws, h_draws, cnt * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemset(w->eb.reset_count, 0, sizeof(int) * w->n));
+    std::vector<int> avail(w->n, rounds);
+    CK(cudaMemcpy(w->d_draw_avail, avail.data(), sizeof(int) * w->n, cudaMemcpyHostToDevice));
     w->eb.draws = w->d_draws; w->eb.draw_rounds = rounds;
-    if (invalidate && w->eb.pipeline) {
+    {
+        int flag = 0;   // a new sequence: forget that the old one ran dry
+        CK(cudaMemcpy(&flag, w->eb.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        flag &= ~2;
+        CK(cudaMemcpy(w->eb.error_flag, &flag, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (w->eb.pipeline) {
         // a new draw sequence starts: standbys computed from the old one are recomputed now
         CK(cudaMemset(w->eb.sb_ready, 0, sizeof(int) * w->n));
+        w->eb.epoch = ++w->epoch;
         TOPO_DISPATCH(w, (standby_kernel<Topo><<<(w->n + 127) / 128, 128>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb)));
         w->launches++;
         CK(cudaGetLastError());
@@ -324,8 +340,27 @@ static int set_draws_impl(TgWorld* w, const double* h_draws, int rounds, int inv
     return TG_OK;
 }
 
-extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds) { return set_draws_impl(w, h_draws, rounds, 1); }
-extern "C" int tg_refill_draws(TgWorld* w, const double* h_draws, int rounds) { return set_draws_impl(w, h_draws, rounds, 0); }
+extern "C" int tg_draws_poll(TgWorld* w, int32_t* h_counts, void* stream)
+{
+    if (!w || !h_counts) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    CK(cudaMemcpyAsync(h_counts, w->eb.reset_count, sizeof(int) * w->n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(h_counts + w->n, w->eb.error_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return TG_OK;
+}
+
+extern "C" int tg_draws_upload(TgWorld* w, const double* h_ring, const int32_t* h_avail, void* stream)
+{
+    if (!w || !h_ring || !h_avail) return fail(TG_EINVAL, "bad arguments");
+    if (!w->d_draws || w->eb.draw_rounds <= 0) return fail(TG_EINVAL, "tg_draws_upload needs a ring started by tg_set_draws");
+    CK(cudaSetDevice(w->device));
+    const size_t cnt = (size_t)w->n * w->eb.draw_rounds * w->cfg.task.n_draws;
+    // ring first, counters second: a reset that sees the new draw_avail finds the new draws (same stream, in order; slots
+    // already valid are rewritten with identical values)
+    CK(cudaMemcpyAsync(w->d_draws, h_ring, cnt * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(w->d_draw_avail, h_avail, sizeof(int) * w->n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return TG_OK;
+}
 
 extern "C" int tg_pipeline_error(TgWorld* w, void* stream)
 {
@@ -334,7 +369,7 @@ extern "C" int tg_pipeline_error(TgWorld* w, void* stream)
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, w->eb.error_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
-    return flag;
+    return flag;   // bit 0: reset pipeline / raster; bit 1: a reset found its draws exhausted
 }
 
 extern "C" int tg_pipeline_stalls(TgWorld* w, void* stream)
@@ -407,6 +442,7 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
 
 static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
 {
+    w->eb.epoch = ++w->epoch;
     TOPO_DISPATCH(w, (reset_kernel<Topo><<<env_grid(w), 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, mask)));
     w->launches++;
     CK(cudaGetLastError());
@@ -427,6 +463,7 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
 
 static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, int autoreset, cudaStream_t st)
 {
+    w->eb.epoch = ++w->epoch;
     const dim3 grid(w->eb.step_blocks + w->standby_blocks); // the extra blocks recompute consumed standbys meanwhile
     const dim3 pgrid((w->n + PUSH_BLOCK - 1) / PUSH_BLOCK);  // object_push: PUSH_BLOCK envs per block, rows in shared memory
     if (w->cfg.arm.topo == TG_TOPO_MG400) { STEP_DISPATCH(TopoMG400) } else { STEP_DISPATCH(TopoChain6) }

@@ -13,8 +13,8 @@ import numpy as np
 from . import _lib as L
 from . import scene, seeding
 
-DRAW_ROUNDS = 64        # resets per env covered by one upload
-DRAW_CHECK_EVERY = 32   # steps between (synchronising) checks of how many draws were consumed
+DRAW_ROUNDS = 64        # slots of the per-env draw ring on the device
+DRAW_CHECK_EVERY = 32   # steps / resets between (asynchronous) read-backs of how many draws were consumed
 
 
 def _sparse_flag(env_modes):
@@ -31,10 +31,7 @@ def _control_mode(env_modes, arm_type):
     if mode == "TCP_velocity_control":
         return 0, 10
     if mode == "TCP_position_control":
-        if arm_type != "ur5" and not os.environ.get("TG_UNVERIFIED_MG400_POSCTL"):
-            # the MG400 variant (slaved joints in the IK result, mg400.py:167-172) is written on both sides but has not run on a GPU
-            raise NotImplementedError("TCP_position_control is built for the ur5 (the mg400's joint slaving of IK targets, mg400.py:167-172, is not)")
-        return 1, 10
+        return 1, 10    # ur5 and mg400 (the latter slaves joints 5..7 in the IK result too, mg400.py:167-172)
     raise ValueError("Incorrect control mode specified: {}".format(mode))
 
 
@@ -281,11 +278,7 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
         raise NotImplementedError("noise_mode 'random' (1,024 uniform draws per reset, base_surface_env.py:290-309) is not built")
     vertical = noise_mode == "vertical_simplex"
     if vertical:
-        # The CUDA side of the upright surface (TgTask.surf_vertical) was written after the round's GPU budget was spent and has
-        # not run on a GPU yet: the mode stays refused unless the caller opts in (tests/test_gpu_vertical.py does, in a
-        # subprocess); drop the gate once that test has been green on a B200.
-        if not os.environ.get("TG_UNVERIFIED_VERTICAL"):
-            raise NotImplementedError("noise_mode 'vertical_simplex' (vertical heightfield, `forward` sensor type, base_surface_env.py:60-63,83-107) is not built")
+        # upright heightfield + `forward` sensor type (base_surface_env.py:60-63, 83-107): TgTask.surf_vertical
         if variant != "vert" or movement_mode != "xRz":
             raise ValueError("Incorrect movement mode specified")                                # update_surface :459-463 knows "xRz" only
     elif noise_mode not in ("simplex", "none"):
@@ -621,9 +614,10 @@ class TactileWorld:
         self.oracle_obs = self.term_oracle_obs = None
         self._draw = draw_fn if draw_fn is not None else edge_follow_draws(cfg.task)
         self._rngs = [seeding.np_random(None)[0] for _ in range(self.n)]
-        self._host_draws = None
-        self._steps_since_check = 0
-        self._upload_draws(fresh=True)
+        self._pin_ring = self._pin_avail = self._pin_counts = None
+        self._poll_ev = self._upload_ev = None
+        self._managed, self._since_poll = True, 0
+        self._start_draws()
 
     @property
     def obs(self):
@@ -658,33 +652,76 @@ class TactileWorld:
         for i, s in enumerate(seeds):
             self._rngs[i], sd = seeding.np_random(s)
             out.append(sd)
-        self._upload_draws(fresh=True)
+        self._start_draws()
         return out
 
-    def _upload_draws(self, fresh=False):
-        if fresh or self._host_draws is None:
-            self._host_draws = np.stack([self._draw(r, DRAW_ROUNDS) for r in self._rngs])
-        else:
-            counts = np.zeros(self.n, dtype=np.int32)
-            L.check(self.lib.tg_get_reset_counts(self.h, counts.ctypes.data, self._stream()))
-            self._steps_since_check = 0
-            if counts.max() < DRAW_ROUNDS // 2:
-                return      # plenty left on the device; a refill costs ~1 us per env on the host, so do it rarely
-            for i in np.nonzero(counts)[0]:
-                c = min(int(counts[i]), DRAW_ROUNDS)
-                self._host_draws[i] = np.concatenate([self._host_draws[i, c:], self._draw(self._rngs[i], c)])
-        arr = np.ascontiguousarray(self._host_draws, dtype=np.float64)
-        # fresh sequence (seed()): pre-computed standby episodes are recomputed; refill: they stay valid
-        L.check((self.lib.tg_set_draws if fresh else self.lib.tg_refill_draws)(self.h, arr.ctypes.data, DRAW_ROUNDS))
-        self._steps_since_check = 0
+    def _start_draws(self):
+        """A fresh draw sequence (construction, seed()): DRAW_ROUNDS draws per env go up synchronously and the pre-computed next
+        episodes are recomputed.  The host copy is a pinned RING [N, DRAW_ROUNDS, n_draws]: the k-th reset of env i reads slot
+        k % DRAW_ROUNDS, `_avail[i]` counts the draws produced so far."""
+        torch = self.torch
+        nd = self.cfg.task.n_draws
+        if self._pin_ring is None:
+            self._pin_ring = torch.zeros((self.n, DRAW_ROUNDS, nd), dtype=torch.float64).pin_memory()
+            self._pin_avail = torch.zeros(self.n, dtype=torch.int32).pin_memory()
+            self._pin_counts = torch.zeros(self.n + 1, dtype=torch.int32).pin_memory()
+        if self._upload_ev is not None:
+            self._upload_ev.synchronize()
+        ring = self._pin_ring.numpy()
+        for i, r in enumerate(self._rngs):
+            ring[i] = self._draw(r, DRAW_ROUNDS)
+        self._pin_avail.fill_(DRAW_ROUNDS)
+        L.check(self.lib.tg_set_draws(self.h, self._pin_ring.data_ptr(), DRAW_ROUNDS))
+        self._managed, self._poll_ev, self._since_poll = True, None, 0
+
+    def _feed_draws(self, wait=False):
+        """Called once per step / reset; never synchronises in steady state.  Every DRAW_CHECK_EVERY calls the per-env reset
+        counters are copied out asynchronously; when that copy has landed, the slots of consumed draws are refilled from the
+        envs' own RandomStates (episode order is kept: draw k of env i is always the k-th output of its stream) and the ring
+        goes back up, asynchronously too.  Only if the device ran so far ahead of the host that the ring could run dry before
+        the counters arrive does this wait for them."""
+        if not self._managed:
+            return
+        torch = self.torch
+        self._since_poll += 1
+        if self._poll_ev is None:
+            if self._since_poll < DRAW_CHECK_EVERY and not wait:
+                return
+            L.check(self.lib.tg_draws_poll(self.h, self._pin_counts.data_ptr(), self._stream()))
+            self._poll_ev = torch.cuda.Event()
+            self._poll_ev.record(torch.cuda.current_stream(self.device))
+            if not wait:
+                return
+        if not self._poll_ev.query():
+            if not wait and self._since_poll < DRAW_CHECK_EVERY + DRAW_ROUNDS // 8:
+                return
+            self._poll_ev.synchronize()
+        self._poll_ev, self._since_poll = None, 0
+        counts = self._pin_counts.numpy()
+        if int(counts[self.n]) & 2:
+            raise L.TgError("reset draws ran out on the device (an env reset with TgTask.draw_default): the host fell behind refilling the ring")
+        consumed = counts[: self.n].astype(np.int64)
+        avail = self._pin_avail.numpy()
+        free = consumed + DRAW_ROUNDS - avail            # slots whose draw has been consumed
+        if free.max() < DRAW_ROUNDS // 4:
+            return                                       # plenty left; a refill costs a few us per env on the host
+        if self._upload_ev is not None:
+            self._upload_ev.synchronize()                # the previous upload read the pinned ring (long done)
+        ring = self._pin_ring.numpy()
+        for i in np.nonzero(free > 0)[0]:
+            c, a = int(free[i]), int(avail[i])
+            ring[i, (a + np.arange(c)) % DRAW_ROUNDS] = self._draw(self._rngs[i], c)
+            avail[i] = a + c
+        L.check(self.lib.tg_draws_upload(self.h, self._pin_ring.data_ptr(), self._pin_avail.data_ptr(), self._stream()))
+        self._upload_ev = torch.cuda.Event()
+        self._upload_ev.record(torch.cuda.current_stream(self.device))
 
     def set_draws(self, draws):
-        """Explicit draws [N, rounds, 2] (parity tests)."""
+        """Explicit draws [N, rounds, n_draws] (parity tests): the r-th reset of env i uses draws[i, r]; nothing is refilled."""
         arr = np.ascontiguousarray(draws, dtype=np.float64)
         assert arr.shape[0] == self.n and arr.shape[2] == self.cfg.task.n_draws, arr.shape
         L.check(self.lib.tg_set_draws(self.h, arr.ctypes.data, arr.shape[1]))
-        self._host_draws = None
-        self._steps_since_check = -(10 ** 9)
+        self._managed = False
 
     # ------------------------------------------------------------------ stepping
     def _stream(self):
@@ -698,23 +735,32 @@ class TactileWorld:
             mp = mask.data_ptr()
         if not render:
             L.check(self.lib.tg_reset_only(self.h, mp, self._stream()))
-            return None
-        L.check(self.lib.tg_reset(self.h, mp, self.obs.data_ptr(), self._stream()))
-        return self.obs
+        else:
+            L.check(self.lib.tg_reset(self.h, mp, self.obs.data_ptr(), self._stream()))
+        self._feed_draws()
+        return self.obs if render else None
 
-    def step(self, actions, want_terminal_obs=False):
-        """actions: float32 cuda tensor [N, act_dim].  Returns (obs, reward, done) tensors (no sync)."""
+    def step(self, actions, want_terminal_obs=False, out=None):
+        """actions: float32 cuda tensor [N, act_dim].  Returns (obs, reward, done) tensors (no sync).
+        out = (obs u8 [N,S,S,1], reward f32 [N], done u8 [N], feat f32 [N,TG_PUSH_NFEAT] | None): write this step's results
+        into the caller's tensors instead of the world's own (distributed.CollatedBatch hands out views of its packed
+        all-gather buffer, so the kernels write straight into the send slot)."""
         a = actions
         if a.device != self.device or a.dtype != self.torch.float32 or not a.is_contiguous():
             a = a.to(device=self.device, dtype=self.torch.float32).contiguous()
         if a.shape != (self.n, self.act_dim):
             raise ValueError("actions must have shape (%d, %d), got %s" % (self.n, self.act_dim, tuple(a.shape)))
-        L.check(self.lib.tg_step(self.h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+        obs, reward, done = (self.obs, self.reward, self.done) if out is None else out[:3]
+        if out is not None and self.nfeat:
+            if out[3] is None or tuple(out[3].shape) != (self.n, L.TG_PUSH_NFEAT):
+                raise ValueError("this task writes an extended feature: out[3] must be float32 [N, %d]" % L.TG_PUSH_NFEAT)
+            L.check(self.lib.tg_bind_features(self.h, out[3].data_ptr(), self.term_feat.data_ptr()))
+        L.check(self.lib.tg_step(self.h, a.data_ptr(), obs.data_ptr(), reward.data_ptr(), done.data_ptr(),
                                  self.term_obs.data_ptr() if want_terminal_obs else None, self._stream()))
-        self._steps_since_check += 1
-        if self._steps_since_check >= DRAW_CHECK_EVERY:
-            self._upload_draws()
-        return self.obs, self.reward, self.done
+        if out is not None and self.nfeat:
+            L.check(self.lib.tg_bind_features(self.h, self.feat.data_ptr(), self.term_feat.data_ptr()))
+        self._feed_draws()
+        return obs, reward, done
 
     def step_host(self, h_actions, h_obs, h_reward, h_done, h_feat=None, h_oracle=None, want_terminal_obs=True, chunks=0):
         """One env step with pinned HOST tensors in and out (tg_step_host): the observation is rendered and copied out in
@@ -733,12 +779,11 @@ class TactileWorld:
             hs.h_oracle = h_oracle.data_ptr()
         hs.chunks = chunks
         L.check(self.lib.tg_step_host(self.h, C.byref(hs), self._stream()))
-        self._steps_since_check += 1
-        if self._steps_since_check >= DRAW_CHECK_EVERY:
-            self._upload_draws()
+        self._feed_draws()
 
     def physics_only(self, actions):
         L.check(self.lib.tg_physics_only(self.h, actions.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
+        self._feed_draws()
 
     def raster_only(self):
         L.check(self.lib.tg_raster_only(self.h, self.obs.data_ptr(), self._stream()))
@@ -763,8 +808,13 @@ class TactileWorld:
         return cam
 
     def pipeline_error(self):
-        """sticky error flag of the reset pipeline (always False since the standby slots became resumable)"""
-        return bool(self.lib.tg_pipeline_error(self.h, self._stream()))
+        """sticky error flag of the reset pipeline / heightfield raster (bit 0 of tg_pipeline_error)"""
+        return bool(self.lib.tg_pipeline_error(self.h, self._stream()) & 1)
+
+    def draws_exhausted(self):
+        """a reset found the draw ring empty and used the task's default draws (bit 1 of tg_pipeline_error).  Expected with
+        explicit set_draws() once its rounds are used up (the pipeline pre-computes one episode ahead); an error otherwise."""
+        return bool(self.lib.tg_pipeline_error(self.h, self._stream()) & 2)
 
     def pipeline_stalls(self):
         """episode ends that had to finish their pre-computed next episode inline (exact, just slower)"""

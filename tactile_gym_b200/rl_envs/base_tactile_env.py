@@ -8,12 +8,13 @@ import numpy as np
 
 from .. import spaces
 
-try:  # pragma: no cover
-    import gym
-
-    _Base = gym.Env
-except Exception:  # noqa: BLE001
-    _Base = object
+_Base = object
+for _mod in ("gym", "gymnasium"):   # the reference's envs are old-gym Envs (4-tuple step); either base class will do
+    try:  # pragma: no cover
+        _Base = __import__(_mod).Env
+        break
+    except Exception:  # noqa: BLE001
+        pass
 
 
 class BaseTactileEnv(_Base):

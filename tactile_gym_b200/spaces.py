@@ -5,13 +5,17 @@ rl_envs/exploration/edge_follow/edge_follow_env.py:167-174).  gym is not a hard 
 """
 import numpy as np
 
-try:  # pragma: no cover - depends on the environment
-    from gym import spaces as _spaces  # type: ignore
-
+_spaces = None
+for _mod in ("gymnasium", "gym"):   # SB3 >= 2.0 checks isinstance against gymnasium's spaces; the reference itself is on old gym
+    try:  # pragma: no cover - depends on the environment
+        _spaces = __import__(_mod, fromlist=["spaces"]).spaces
+        break
+    except Exception:  # noqa: BLE001
+        _spaces = None
+HAVE_GYM = _spaces is not None
+if HAVE_GYM:  # pragma: no cover
     Box, Dict = _spaces.Box, _spaces.Dict
-    HAVE_GYM = True
-except Exception:  # noqa: BLE001
-    HAVE_GYM = False
+else:
 
     class Box:
         def __init__(self, low, high, shape=None, dtype=np.float32):

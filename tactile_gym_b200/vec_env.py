@@ -23,6 +23,40 @@ CONFIG_BUILDERS = {"edge_follow-v0": edge_follow_config, "object_balance-v0": ob
                    "surface_follow-v0": surface_follow_config, "surface_follow-v1": surface_follow_goal_config, "surface_follow-v2": surface_follow_vert_config, "object_push-v0": object_push_config, "object_roll-v0": object_roll_config}
 
 
+class _Info(dict):
+    """info dict of an env that did not finish.  They are reused from step to step (4,096 fresh dicts per step cost more host
+    time than the kernels); one that a wrapper or callback wrote into registers itself and is emptied before the next step, so
+    nothing leaks from one step into the next."""
+    __slots__ = ("_dirty",)
+
+    def _touch(self):
+        self._dirty.append(self)
+
+    def __setitem__(self, k, v):
+        self._touch(); dict.__setitem__(self, k, v)
+
+    def __delitem__(self, k):
+        self._touch(); dict.__delitem__(self, k)
+
+    def update(self, *a, **kw):
+        self._touch(); dict.update(self, *a, **kw)
+
+    def setdefault(self, k, d=None):
+        self._touch(); return dict.setdefault(self, k, d)
+
+    def pop(self, *a):
+        self._touch(); return dict.pop(self, *a)
+
+    def popitem(self):
+        self._touch(); return dict.popitem(self)
+
+    def clear(self):
+        dict.clear(self)
+
+    def __ior__(self, other):
+        self._touch(); dict.update(self, other); return self
+
+
 class TactileVecEnv(_VecEnvBase):
     def __init__(self, env_id, n_envs, seed=None, env_kwargs=None, device=0, lanes_per_warp=0, copy_chunks=0):
         kw = dict(env_kwargs or {})
@@ -62,6 +96,7 @@ class TactileVecEnv(_VecEnvBase):
         self.observation_space = spaces.Dict(sp)
         self.action_space = spaces.Box(low=-0.25, high=0.25, shape=(self.world.act_dim,), dtype=np.float32)
         self.metadata = {"render.modes": ["rgb_array"]}
+        self.render_mode = "rgb_array"
         self._actions = None
         self._ep_ret = np.zeros(n_envs, dtype=np.float64)
         self._ep_len = np.zeros(n_envs, dtype=np.int64)
@@ -77,16 +112,33 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_rew = torch.zeros(n_envs, dtype=torch.float32).pin_memory()
         self._pin_done = torch.zeros(n_envs, dtype=torch.uint8).pin_memory()
         self._pin_feat = torch.zeros((n_envs, 12), dtype=torch.float32).pin_memory() if self._with_feat else None
-        self._blank_infos = [{} for _ in range(n_envs)]
+        self._dirty_infos = []
+        self._blank_infos = [_Info() for _ in range(n_envs)]
+        for d in self._blank_infos:
+            d._dirty = self._dirty_infos
         # terminal observations of the envs that finish in a step: gathered on the device, copied out through a pinned stage
         # that grows (geometrically) to the largest number of simultaneous episode ends seen
         self._pin_idx = torch.zeros(n_envs, dtype=torch.int64).pin_memory()
         self._term_dev = self._term_stage = None
         self._grow_term_stage(min(n_envs, 64))
+        if _VecEnvBase is not object:  # pragma: no cover - needs stable_baselines3
+            # SB3's wrappers read reset_infos / _seeds / _options / render_mode off the base class
+            self._sb3_init()
         if seed is not None:
             self.seed(seed)
         self.h2d_bytes_per_step = self._pin_actions.numel() * 4
         self.d2h_bytes_per_step = (self._pin_oracle.numel() * 4 if self._oracle else self._pin_obs.numel()) + self._pin_rew.numel() * 4 + self._pin_done.numel() + (self._pin_feat.numel() * 4 if self._with_feat else 0)
+
+    def _sb3_init(self):  # pragma: no cover - needs stable_baselines3
+        import inspect
+
+        kw = {}
+        if "render_mode" in inspect.signature(_VecEnvBase.__init__).parameters:
+            kw["render_mode"] = self.render_mode
+        try:
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space, **kw)
+        except TypeError:
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
 
     # ---------------------------------------------------------------- VecEnv API (host numpy)
     def seed(self, seed=None):
@@ -105,7 +157,10 @@ class TactileVecEnv(_VecEnvBase):
             o["extended_feature"] = self._pin_feat.numpy()[:, : self._nfeat].copy()
         return o
 
-    def reset(self):
+    def reset(self, seed=None, options=None):
+        """seed / options: accepted for gymnasium-era callers (seed re-seeds env i with seed + i first)"""
+        if seed is not None:
+            self.seed(seed)
         self.world.reset(render=not self._oracle)
         if self._oracle:
             self._pin_oracle.copy_(self.world.oracle_obs, non_blocking=True)
@@ -157,6 +212,8 @@ class TactileVecEnv(_VecEnvBase):
         self._ep_len += 1
         # envs that did not finish share their (empty) info dict from step to step: 4096 fresh dicts per step cost more
         # host time than the kernels; finished envs get a fresh dict
+        while self._dirty_infos:
+            self._dirty_infos.pop().clear()
         infos = list(self._blank_infos)
         idx = np.flatnonzero(done)
         if idx.size:
@@ -199,6 +256,23 @@ class TactileVecEnv(_VecEnvBase):
     def step_tensor(self, actions):
         """actions: cuda float32 [N, act_dim] -> (obs, reward, done) cuda tensors; nothing synchronises."""
         return self.world.step(actions)
+
+    def step_collated(self, actions, group=None):
+        """Device-resident step whose results are all-gathered over the process group into ONE collated batch (the job
+        SubprocVecEnv's pipes do in the reference, sb3_helpers/rl_utils.py:17-30): the kernels write into this rank's slot of
+        a packed buffer, one in-place NCCL all_gather_into_tensor runs on a side stream, and the call returns at once with a
+        handle; `collated_wait(handle)` gives (obs [G, N, S, S, 1], reward [G, N], done [G, N], feat [G, N, 12] | None) in
+        global env order, valid until the step after next (two buffers alternate, so the gather overlaps the next step)."""
+        from .distributed import CollatedBatch
+        from . import _lib as L
+
+        if getattr(self, "_cb", None) is None:
+            self._cb = CollatedBatch(self.num_envs, self.world.S, L.TG_PUSH_NFEAT if self.world.nfeat else 0, self.world.device, group=group)
+        self.world.step(actions, out=self._cb.local_views())
+        return self._cb.gather()
+
+    def collated_wait(self, handle):
+        return self._cb.wait(handle)
 
     def close(self):
         self.world.close()

@@ -1,18 +1,11 @@
-"""Device code written after round 1's GPU budget was spent - NOT YET RUN ON A GPU: (1) surface_follow-v2 on its own surface
-(noise_mode "vertical_simplex": upright heightfield, `forward` sensor type), (2) TCP_position_control on the MG400 (slaved joints
-in the IK result, mg400.py:167-172).  CUDA path against the CPU oracle, each case in its own subprocess.
+"""surface_follow-v2 on its own surface (noise_mode "vertical_simplex": upright heightfield, `forward` sensor type) and
+TCP_position_control on the MG400 (slaved joints in the IK result, mg400.py:167-172): CUDA path against the CPU oracle.
 
-The device code for this mode (TgTask.surf_vertical: row-wise 1-d heights, flipped goal / normals / surface distance, the camera
-brought into the heightfield's frame for raster_hf_kernel) was written after round 1's GPU budget was spent.  The oracle side is
-pinned to the reference's source on the CPU (tests/test_oracle_reference_golden.py::test_vertical_surface_geometry_and_rewards),
-but the kernels themselves have never executed, so:
-  * the product keeps refusing the mode (NotImplementedError) unless TG_UNVERIFIED_VERTICAL (TG_UNVERIFIED_MG400_POSCTL for the second) is set;
-  * this test runs in a SUBPROCESS with that variable set - a fault in the new code cannot poison the CUDA context of the rest
-    of the suite - and is a non-strict xfail: an XPASS on the first GPU run is the signal to drop both the gate and the mark.
-"""
+Both were written after round 1's GPU budget was spent, gated off, and passed on the first B200 they ever saw (4 XPASS in
+GPUTEST_r01.json); the gates are gone and these are plain tests now.  The oracle side is pinned to the reference's source on the
+CPU (tests/test_oracle_reference_golden.py::test_vertical_surface_geometry_and_rewards).  The bodies stay scripts so that
+tests/test_vertical_posctl_scripts_dryrun.py can run them on the CPU against an oracle-backed stand-in."""
 import os
-import subprocess
-import sys
 
 import pytest
 
@@ -90,14 +83,12 @@ print("VERTICAL-OK")
 '''
 
 
-@pytest.mark.xfail(strict=False, reason="device code for vertical_simplex written after the round-1 GPU budget was spent; never run on a GPU")
 @pytest.mark.parametrize("arm,sensor,S,obs_mode", [("mg400", "tactip", 128, "tactile"), ("ur5", "digit", 128, "tactile"), ("mg400", "tactip", 64, "oracle")])
-def test_vertical_surface_matches_oracle(arm, sensor, S, obs_mode):
+def test_vertical_surface_matches_oracle(capsys, arm, sensor, S, obs_mode):
     code = CHILD % {"root": ROOT, "arm": arm, "sensor": sensor, "S": S, "obs": obs_mode, "render": "True" if obs_mode == "tactile" else "False",
                     "steps": 8}
-    env = dict(os.environ, TG_UNVERIFIED_VERTICAL="1")
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=150, env=env)
-    assert out.returncode == 0 and "VERTICAL-OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+    exec(compile(code, "vertical-child", "exec"), {"__name__": "child"})
+    assert "VERTICAL-OK" in capsys.readouterr().out
 
 
 CHILD_POSCTL = r'''
@@ -146,8 +137,6 @@ print("POSCTL-OK")
 '''
 
 
-@pytest.mark.xfail(strict=False, reason="MG400 position control written after the round-1 GPU budget was spent; never run on a GPU")
-def test_mg400_position_control_matches_oracle():
-    env = dict(os.environ, TG_UNVERIFIED_MG400_POSCTL="1")
-    out = subprocess.run([sys.executable, "-c", CHILD_POSCTL % {"root": ROOT}], capture_output=True, text=True, timeout=150, env=env)
-    assert out.returncode == 0 and "POSCTL-OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+def test_mg400_position_control_matches_oracle(capsys):
+    exec(compile(CHILD_POSCTL % {"root": ROOT}, "posctl-child", "exec"), {"__name__": "child"})
+    assert "POSCTL-OK" in capsys.readouterr().out

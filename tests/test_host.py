@@ -46,9 +46,8 @@ def test_config_rejects_bad_modes(edge_modes):
     bad = dict(edge_modes, arm_type="pr2")
     with pytest.raises(ValueError):
         edge_follow_config(bad, [128, 128], 200, 1)
-    bad = dict(edge_modes, control_mode="TCP_position_control", arm_type="mg400")     # position control: ur5 only
-    with pytest.raises(NotImplementedError):
-        edge_follow_config(bad, [128, 128], 200, 1)
+    cfg, _ = edge_follow_config(dict(edge_modes, control_mode="TCP_position_control", arm_type="mg400"), [128, 128], 200, 1)
+    assert (cfg.task.control_mode, cfg.arm.nb) == (1, 8)                             # mg400.py:131-175
     with pytest.raises(ValueError):
         edge_follow_config(dict(edge_modes, control_mode="joint_torque_control"), [128, 128], 200, 1)
     cfg, _ = edge_follow_config(dict(edge_modes, control_mode="TCP_position_control"), [128, 128], 200, 1)
@@ -78,8 +77,8 @@ def test_surface_config_modes():
     assert (t.act_dim, list(t.act_index[:2]), t.surf_mode, t.surf_dir_mode, t.surf_drive_y_only, t.sparse_reward) == (2, [0, 5], 2, 1, 1, 1)
     assert (t.surf_w_goal, t.surf_w_surf, t.surf_w_norm) == (0.0, 10.0, 3.0) and abs(t.surf_drive - 0.25 * 0.7) < 1e-15
     assert t.act_hi[5] == 0.0                      # horizontal surface: no yaw range (base_surface_env.py:197-206)
-    with pytest.raises(NotImplementedError):
-        surface_follow_vert_config(dict(m, noise_mode="vertical_simplex"), [64, 64], 200, 2)
+    cfg, _, _ = surface_follow_vert_config(dict(m, noise_mode="vertical_simplex", arm_type="mg400", tactile_sensor_name="tactip"), [64, 64], 200, 2)
+    assert (cfg.task.surf_mode, cfg.task.surf_vertical, cfg.task.act_hi[5] > 0) == (3, 1, True)     # base_surface_env.py:83-107, 183-194
     cfg, _, _ = surface_follow_config(dict(m, movement_mode="yzRx", reward_mode="dense"), [64, 64], 200, 2)
     assert (cfg.task.act_dim, cfg.task.surf_mode, cfg.task.surf_dir_mode, cfg.task.sparse_reward) == (2, 1, 1, 0)
     cfg, _, _ = surface_follow_goal_config(dict(m, movement_mode="yz", noise_mode="none"), [64, 64], 200, 2)
@@ -228,14 +227,10 @@ def test_reference_training_params_are_accepted():
             with pytest.raises(KeyError):
                 CONFIG_BUILDERS[env_id](*args)
             continue
-        if modes.get("noise_mode") == "vertical_simplex":
-            with pytest.raises(NotImplementedError):          # surface_follow-v2's vertical surface: SURVEY 8(f) item 2, not built
-                CONFIG_BUILDERS[env_id](*args)
-            continue
         out = CONFIG_BUILDERS[env_id](*args)
         cfg = out[0]
         assert cfg.n_envs == 2 and cfg.task.max_steps == p["max_ep_len"] and cfg.sensor.image_size == p["image_size"][0]
         built += 1
-    # every complete PPO set-up but -v2's vertical one (edge, balance, push on the MG400 + mini TacTip, roll, surface -v0, -v1)
-    # and every demo script but demo_surf_vert_env.py
-    assert built == 12
+    # every complete PPO set-up (edge, balance, push on the MG400 + mini TacTip, roll, surface -v0, -v1, -v2 on its vertical
+    # surface) and every demo script
+    assert built == 14

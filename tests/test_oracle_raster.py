@@ -73,3 +73,42 @@ def test_edge_signature(oracle):
     assert rows.min() >= 60 and cols.min() >= 60
     assert 40 < img[mask == 0].max() < 90
     assert np.array_equal(img[mask == 1], gray[mask == 1].astype(np.uint8))
+
+
+@pytest.mark.parametrize("border_on", [True, False])
+def test_body_mask_zeroing_is_an_identity_for_the_composited_depth(oracle, border_on):
+    """t_s_camera zeroes every pixel whose SEGMENTATION id is the sensor body (`pen_img[full_mask] = 0`,
+    tactile_sensor.py:283-288) before the border is pasted.  The oracle and the kernels have no segmentation image: they
+    composite the stimulus into nodef_dep, so wherever the housing is the nearest surface the current depth IS nodef_dep and
+    the pixel is already 0; wherever the stimulus is in front of the housing the segmentation id is the stimulus' and the
+    reference keeps the value too.  Checked here with a segmentation built from the sensor's own meshes (the KAT's z-buffer)
+    plus the stimulus: applying the reference's line to the oracle's image changes nothing, border on or off - including the
+    ~2 pixels where `border_mask` and the housing silhouette disagree at 128 x 128."""
+    S = 128
+    env = oracle.EdgeFollowOracle(image_size=S, seed=3)
+    env.reset()
+    q = np.array(env.s.q[:6])
+    m = env.m
+    meshes = np.load(os.path.join(GOLDEN, "sensor_visual_ur5_standard_tactip.npz"))
+    P, R = oracle.link_frames(m, q)
+    e, f, u, r = oracle.camera_frame(m, q)
+    d_body = np.ones((S, S), np.float32)
+    d_rest = np.ones((S, S), np.float32)
+    for k in meshes.files:
+        i = m._names.index(k)
+        d = oracle.depth_image(e, f, u, r, m.fov_deg, m.near_, m.far_, S, meshes[k].astype(np.float64) @ R[i].T + P[i])
+        if k == "tactip_body_link":
+            d_body = np.minimum(d_body, d)
+        else:
+            d_rest = np.minimum(d_rest, d)
+    d_stim = oracle.depth_image(e, f, u, r, m.fov_deg, m.near_, m.far_, S, env.stimulus_world())
+    full_mask = (d_body < d_rest) & (d_body <= d_stim)          # the body link wins the depth test = its segmentation id
+    img = oracle.tactile_image(m, q, S, env.stimulus_world(), env.ref, border_on=border_on)
+    dep, gray, mask = env.ref
+    ref_img = img.copy()
+    # the reference's order: zero the body pixels, THEN paste the border
+    ref_img[full_mask] = 0
+    if border_on:
+        ref_img[mask == 1] = gray[mask == 1]
+    assert full_mask.sum() > 0.3 * S * S and (d_stim < d_rest).sum() > 100   # the housing is seen, and so is the edge through the skin
+    assert np.array_equal(ref_img, img)

@@ -1,7 +1,6 @@
-"""CPU dry run of the scripts tests/test_gpu_unverified.py hands to its GPU subprocesses: with tg.make_vec replaced by an
+"""CPU dry run of the scripts tests/test_gpu_vertical_posctl.py hands to its GPU subprocesses: with tg.make_vec replaced by an
 oracle-backed stand-in (tests/_oracle_backed_vec.py) the scripts compare the oracle with itself, which exercises their own logic -
-state indices, shapes, tolerances, the "surface really shows" condition - so that the first GPU run of the not-yet-run device code
-is decided by that code and not by a slip in the test."""
+state indices, shapes, tolerances, the "surface really shows" condition - so that a GPU failure is decided by the device code and not by a slip in the test."""
 import importlib.util
 import os
 import sys
@@ -12,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _scripts():
-    spec = importlib.util.spec_from_file_location("tg_unverified_scripts", os.path.join(HERE, "test_gpu_unverified.py"))
+    spec = importlib.util.spec_from_file_location("tg_unverified_scripts", os.path.join(HERE, "test_gpu_vertical_posctl.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
