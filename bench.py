@@ -281,7 +281,8 @@ class Bench:
         st[:, 2 * wd.nb + 9] = np.random.RandomState(1000 + self.rank).randint(0, w["max_steps"], size=w["n"])   # the `steps` field
         wd.set_state(st)
         g0 = torch.Generator(device=self.dev); g0.manual_seed(12345 + self.rank)
-        for _ in range(40 if w["name"] != "push" else 8):
+        # (surface_follow's rebuild - 4,096 OpenSimplex points, IK, a ~110-substep move - spans ~75 launches)
+        for _ in range({"push": 8, "surface": 120}.get(w["name"], 40)):
             wd.step((torch.rand((w["n"], wd.act_dim), device=self.dev, generator=g0) - 0.5) * 0.5)
         torch.cuda.synchronize(self.dev)
 
