@@ -199,7 +199,9 @@ typedef struct {
 
 typedef struct {
     int32_t n_envs;
-    int32_t lanes_per_warp; /* physics kernels: active lanes per warp (8/16/32), 0 = auto */
+    int32_t lanes_per_warp; /* physics kernels: 0 = auto; 1/2/4/8/16/32 = one thread per env with that many active lanes per
+                               warp; -8 = one env per group of 8 lanes, one body per lane (csrc/tg_g8.cuh: edge_follow /
+                               surface_follow under TCP_velocity_control; what auto picks for them up to 16,384 envs) */
     TgArm arm;
     TgPhysics phys;
     TgTask task;
@@ -306,6 +308,8 @@ int tg_get_camera(TgWorld* w, double* h_cam, void* stream);
 int tg_test_inverse_dynamics(TgWorld* w, int n, const double* h_q, const double* h_qd, double* h_tau);
 int tg_test_mass_matrix(TgWorld* w, int n, const double* h_q, double* h_M /* [n][nb][nb] */);
 int tg_test_substep(TgWorld* w, int n, int nsteps, double* h_q, double* h_qd, const double* h_target_vel);
+/* the same through the 8-lanes-per-env substep (csrc/tg_g8.cuh) */
+int tg_test_substep_g8(TgWorld* w, int n, int nsteps, double* h_q, double* h_qd, const double* h_target_vel);
 
 /* number of kernels launched by this library since creation (bench.py's gpu_launches) */
 long long tg_launch_count(const TgWorld* w);

@@ -96,7 +96,7 @@ class TgHostStep(C.Structure):
 EXPORTS = [
     "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
     "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
-    "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_launch_count",
+    "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_test_substep_g8", "tg_launch_count",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load():
     lib.tg_test_inverse_dynamics.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.tg_test_mass_matrix.argtypes = [vp, C.c_int, vp, vp]
     lib.tg_test_substep.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.tg_test_substep_g8.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     lib.tg_launch_count.argtypes = [vp]
     lib.tg_launch_count.restype = C.c_longlong
     _lib = lib

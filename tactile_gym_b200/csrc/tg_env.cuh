@@ -879,43 +879,19 @@ __device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhy
     }
 }
 
+// Head of one env step for env e (BaseTactileEnv.step up to the physics): encode_actions + scale_actions, then - for
+// TCP_velocity_control - check_TCP_vel_lims, the twist in the world frame and the joint velocity targets (mot.target_vel).
+// v[6] = the scaled 6-vector (TCP_position_control consumes it as a pose delta).
 template <class T, int TASK>
-__global__ void __launch_bounds__((TASK == TG_TASK_OBJECT_PUSH || TASK == TG_TASK_OBJECT_ROLL) ? PUSH_THREADS : 128)
-step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
-            EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
+TGD void env_prologue(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const float* __restrict__ actions,
+                      const double* q, double* v, Motors<T::NB>& mot)
 {
     constexpr int NB = T::NB;
-    constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, roll = TASK == TG_TASK_OBJECT_ROLL, surface = TASK == TG_TASK_SURFACE_FOLLOW;
-    constexpr bool push = TASK == TG_TASK_OBJECT_PUSH || roll; // object_roll runs on object_push's contact machinery
-    int e;
-    int col = 0;       // object_push: this env's column in the block's shared-memory row store
-    bool owner = true; // object_push: lanes 0..PUSH_LANES-1 of a warp each step an env; the others only help in the hull scan
-    if (push) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        col = warp * PUSH_LANES + (lane & (PUSH_LANES - 1));
-        e = blockIdx.x * PUSH_BLOCK + col;
-        owner = lane < PUSH_LANES && e < b.n;
-    } else {
-        if ((int)blockIdx.x >= b.step_blocks) {
-            standby_role<T>(arm, ph, task, b, b.step_blocks, false);
-            return;
-        }
-        e = env_index(b);
-        if (e < 0) return;
-    }
-    double q[NB], qd[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) { q[i] = 0.0; qd[i] = 0.0; }
-    if (owner) {
-#pragma unroll
-        for (int i = 0; i < NB; i++) { q[i] = b.q[(size_t)i * b.n + e]; qd[i] = b.qd[(size_t)i * b.n + e]; }
-    }
-
+    constexpr bool roll = TASK == TG_TASK_OBJECT_ROLL, surface = TASK == TG_TASK_SURFACE_FOLLOW;
+    constexpr bool push = TASK == TG_TASK_OBJECT_PUSH || roll;
     // encode_actions + scale_actions (edge_follow_env.py:345-369, base_tactile_env.py:141-164)
-    double v[6];
-    Motors<NB> mot;
     mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
-    if (owner) {
+    {
         Kin<NB> k;
         fk<T>(arm, q, k);
         double tp[3], tq[4], wq[4], Rw[9];
@@ -1002,30 +978,17 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int i = 0; i < NB; i++) mot.target_pos[i] = 0.0;
         }
     }
-    ObjState ob;
-    {
-        double sc[NB][2]; // (sin q, cos q): exact here, then advanced by the trig identity after every substep
-#pragma unroll
-        for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
-        if (push) {
-            if (owner) obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
-#pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col, owner); // whole warp
-            if (owner) obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
-        } else if (balance) {
-            obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);
-#pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep_obj<T>(arm, ph, task, q, qd, sc, mot, ob);
-            obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
-        } else if (task.control_mode == 1) {
-            position_control_move<T>(arm, ph, task, q, qd, v);
-        } else {
-#pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, sc, mot);
-        }
-    }
+}
 
-    if (!owner) return;
+// Tail of one env step for env e: store the joint state, step data (reward / done), features / oracle vector, then either the
+// camera for the raster or - for a finished env under auto-reset - the terminal camera and the swap to the next episode.
+template <class T, int TASK>
+TGD void env_epilogue(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const double* q, const double* qd,
+                      const ObjState& ob, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
+{
+    constexpr int NB = T::NB;
+    constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, roll = TASK == TG_TASK_OBJECT_ROLL, surface = TASK == TG_TASK_SURFACE_FOLLOW;
+    constexpr bool push = TASK == TG_TASK_OBJECT_PUSH || roll;
     const int steps = b.steps[e] + 1;
     b.steps[e] = steps;
 #pragma unroll
@@ -1091,6 +1054,69 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int c = 0; c < 4; c++) b.tcp[(size_t)e * 7 + 3 + c] = tq[c];
     }
     if (push && b.pipeline) standby_work<T>(arm, ph, task, b, e, false); // one quantum of this env's next-episode rebuild, if due
+}
+
+template <class T, int TASK>
+__global__ void __launch_bounds__((TASK == TG_TASK_OBJECT_PUSH || TASK == TG_TASK_OBJECT_ROLL) ? PUSH_THREADS : 128)
+step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
+            EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
+{
+    constexpr int NB = T::NB;
+    constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, roll = TASK == TG_TASK_OBJECT_ROLL, surface = TASK == TG_TASK_SURFACE_FOLLOW;
+    constexpr bool push = TASK == TG_TASK_OBJECT_PUSH || roll; // object_roll runs on object_push's contact machinery
+    int e;
+    int col = 0;       // object_push: this env's column in the block's shared-memory row store
+    bool owner = true; // object_push: lanes 0..PUSH_LANES-1 of a warp each step an env; the others only help in the hull scan
+    if (push) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        col = warp * PUSH_LANES + (lane & (PUSH_LANES - 1));
+        e = blockIdx.x * PUSH_BLOCK + col;
+        owner = lane < PUSH_LANES && e < b.n;
+    } else {
+        if ((int)blockIdx.x >= b.step_blocks) {
+            standby_role<T>(arm, ph, task, b, b.step_blocks, false);
+            return;
+        }
+        e = env_index(b);
+        if (e < 0) return;
+    }
+    double q[NB], qd[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) { q[i] = 0.0; qd[i] = 0.0; }
+    if (owner) {
+#pragma unroll
+        for (int i = 0; i < NB; i++) { q[i] = b.q[(size_t)i * b.n + e]; qd[i] = b.qd[(size_t)i * b.n + e]; }
+    }
+
+    double v[6];
+    Motors<NB> mot;
+    mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
+    if (owner) env_prologue<T, TASK>(arm, ph, task, b, e, actions, q, v, mot);
+    ObjState ob;
+    {
+        double sc[NB][2]; // (sin q, cos q): exact here, then advanced by the trig identity after every substep
+#pragma unroll
+        for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
+        if (push) {
+            if (owner) obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
+#pragma unroll 1
+            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col, owner); // whole warp
+            if (owner) obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
+        } else if (balance) {
+            obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);
+#pragma unroll 1
+            for (int s = 0; s < ph.substeps; s++) substep_obj<T>(arm, ph, task, q, qd, sc, mot, ob);
+            obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
+        } else if (task.control_mode == 1) {
+            position_control_move<T>(arm, ph, task, q, qd, v);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, sc, mot);
+        }
+    }
+
+    if (!owner) return;
+    env_epilogue<T, TASK>(arm, ph, task, b, e, q, qd, ob, reward, done, autoreset);
 }
 
 // explicit reset of the masked envs.  With the pipeline on, an env's standby IS its next episode: take it and

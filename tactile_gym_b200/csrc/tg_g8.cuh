@@ -1,0 +1,460 @@
+// tg_g8.cuh - the physics substep with one env per GROUP OF 8 LANES (four envs per warp), one body / joint per lane.
+//
+// north_star's mapping ("one warp-group per env instance, ... warp-shuffle reductions") for the motor-row tasks.  The
+// one-thread-per-env substep (tg_dyn.cuh) keeps every per-joint quantity in the registers of a single thread: ~5.2 k
+// instructions per substep in one dependent fp64 chain, 255 registers, ~80 KB of unrolled code - at N = 4096 the SMs hold one
+// warp per scheduler with 8 active lanes and wait on instruction fetch and fp64 latency (profiles/r01_step_kernel_final.md).
+// Here lane j of a group owns body j:
+//   * forward kinematics and body velocities are PREFIX operations over the kinematic tree: pointer jumping with shuffles,
+//     3 rounds for any tree of depth <= 8;
+//   * the per-body work (spatial inertia, bullet's per-link damping wrench) is lane-local;
+//   * composite inertias and subtree wrenches are SUFFIX sums over the tree (shuffle-down rounds, specialised per topology);
+//   * CRBA: lane j walks up its ancestors and holds column j of M; the matrix is then all-gathered, every lane runs the same
+//     small Cholesky factorisation and solves for its OWN column of A = M^-1 (the constraint response of motor row j);
+//   * projected Gauss-Seidel over the motor rows: the lane that owns row r computes its impulse from lane-local data, one
+//     broadcast, one FMA per lane (dv_i += A[r][i] delta) - same row order, same clamp, same residual exit as tg_dyn.cuh.
+// ~1.4 k instructions per substep for four envs, a loop body that fits the instruction cache, and two warps per scheduler at
+// N = 4096 to hide the fp64 latency.  Arithmetic per entry is the same as in tg_dyn.cuh; only the order of a few sums differs
+// (1e-16), the oracle tolerance (1e-10) is unchanged.
+#pragma once
+#include "tg_env.cuh"
+
+#define G8 8
+#define G8_FULL 0xffffffffu
+
+TGD double g8_get(double v, int src) { return __shfl_sync(G8_FULL, v, src, G8); }
+TGD int g8_geti(int v, int src) { return __shfl_sync(G8_FULL, v, src, G8); }
+TGD double g8_down(double v, int d) { return __shfl_down_sync(G8_FULL, v, d, G8); }
+
+// ---------------------------------------------------------------- topology helpers (lane = body index)
+template <class T> struct G8Topo;
+template <> struct G8Topo<TopoChain6> {
+    static constexpr int MAXDEPTH = 5;
+    __host__ __device__ static constexpr int depth(int i) { return i; }
+    __host__ __device__ static constexpr bool is_anc(int k, int j) { return k <= j; } // k ancestor-or-self of j
+    // v <- sum of v over the subtree of each lane (lanes >= NB hold zeros)
+    template <int CNT> TGD static void subtree_sum(double (&v)[CNT], int j)
+    {
+#pragma unroll
+        for (int d = 1; d < G8; d <<= 1) {
+#pragma unroll
+            for (int c = 0; c < CNT; c++) {
+                const double t = g8_down(v[c], d);
+                v[c] += (j + d < G8) ? t : 0.0;
+            }
+        }
+    }
+};
+template <> struct G8Topo<TopoMG400> {
+    static constexpr int MAXDEPTH = 4;
+    __host__ __device__ static constexpr int depth(int i) { return i < 5 ? i : i - 4; }
+    __host__ __device__ static constexpr bool is_anc(int k, int j)
+    {
+        return k == j || k == 0 || (k < j && ((k >= 1 && j <= 4) || (k >= 5 && j >= 5)));
+    }
+    // tree 0 - {1-2-3-4, 5-6-7}: suffix sums inside the two chains, then the root takes both chain heads
+    template <int CNT> TGD static void subtree_sum(double (&v)[CNT], int j)
+    {
+        const bool a1 = (j >= 1 && j <= 3) || (j >= 5 && j <= 6);
+        const bool a2 = (j >= 1 && j <= 2) || j == 5;
+#pragma unroll
+        for (int c = 0; c < CNT; c++) {
+            double t = g8_down(v[c], 1);
+            v[c] += a1 ? t : 0.0;
+            t = g8_down(v[c], 2);
+            v[c] += a2 ? t : 0.0;
+            const double h1 = g8_get(v[c], 1), h5 = g8_get(v[c], 5);
+            v[c] += j == 0 ? h1 + h5 : 0.0;
+        }
+    }
+};
+
+// per-lane constants of body j (read once per kernel)
+struct G8Body {
+    double jpos[3], axis[3], mass, com[3], inertia[6];
+    int par;        // parent lane, -1 for the root and for idle lanes
+    int sub0, sub1; // this body's mass-carrying URDF links (per-link damping)
+};
+
+// sub-link table in shared memory: [TG_MAXSUB][G8_SUBW] doubles: com(3) rot(9) inertia(3) mass(1) (+1 pad: conflict-free rows)
+#define G8_SUBW 17
+
+template <class T>
+TGD void g8_load_body(const TgArm& arm, int j, G8Body& c)
+{
+    const bool live = j < T::NB;
+    const int jj = live ? j : 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { c.jpos[k] = live ? arm.jpos[jj][k] : 0.0; c.axis[k] = live ? arm.axis[jj][k] : 0.0; c.com[k] = live ? arm.com[jj][k] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) c.inertia[k] = live ? arm.inertia[jj][k] : 0.0;
+    c.mass = live ? arm.mass[jj] : 0.0;
+    c.par = live ? T::parent(jj) : -1;
+    c.sub0 = live ? arm.sub_start[jj] : 0;
+    c.sub1 = live ? arm.sub_start[jj + 1] : 0;
+}
+
+TGD void g8_fill_sub_table(const TgArm& arm, double* s_sub)
+{
+    for (int t = threadIdx.x; t < TG_MAXSUB * 16; t += blockDim.x) {
+        const int s = t >> 4, c = t & 15;
+        double v;
+        if (c < 3) v = arm.sub_com[s][c];
+        else if (c < 12) v = arm.sub_rot[s][c - 3];
+        else if (c < 15) v = arm.sub_inertia[s][c - 12];
+        else v = arm.sub_mass[s];
+        s_sub[s * G8_SUBW + c] = v;
+    }
+}
+
+// Cholesky factor of the SPD matrix M (upper part given as Mf[k][j], k <= j): L[i][k] for i > k, dinv[k] = 1 / L[k][k].
+// Same operation order as spd_inverse (tg_dyn.cuh).
+template <int NB>
+TGD void g8_cholesky(const double (&Mf)[NB][NB], double (&L)[NB][NB], double (&dinv)[NB])
+{
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        double d = Mf[j][j];
+#pragma unroll
+        for (int k2 = 0; k2 < j; k2++) d -= L[j][k2] * L[j][k2];
+        const double inv = rsqrt(d);
+        dinv[j] = inv;
+        L[j][j] = d * inv;
+#pragma unroll
+        for (int i = j + 1; i < NB; i++) {
+            double s = Mf[j][i];
+#pragma unroll
+            for (int k2 = 0; k2 < j; k2++) s -= L[i][k2] * L[j][k2];
+            L[i][j] = s * inv;
+        }
+    }
+}
+
+// state of one lane between substeps
+struct G8Lane {
+    double q, qd, s, c; // joint angle, rate, sin, cos
+};
+
+// One Robot.step_sim() (gravity compensation + stepSimulation with motor rows only) for the four envs of a warp.
+// mode / kp / kd / max_force as in Motors<>; tpos / tvel = this lane's motor target.  `live` = the group carries an env.
+template <class T>
+TGD void g8_substep(const TgPhysics& ph, const G8Body& bc, const double* __restrict__ s_sub, int max_sub, int j, bool live, G8Lane& st,
+                    int mode, double kp, double kd, double max_force, double tpos, double tvel)
+{
+    constexpr int NB = T::NB;
+    using Tp = G8Topo<T>;
+    // ---- forward kinematics: T_j = T_parent o (Rot(axis, q), jpos), composed by pointer jumping
+    double R[9], p[3];
+    {
+        const double s = st.s, c = st.c, ax = bc.axis[0], ay = bc.axis[1], az = bc.axis[2], t1 = 1.0 - c;
+        R[0] = t1 * ax * ax + c;      R[1] = t1 * ax * ay - s * az; R[2] = t1 * ax * az + s * ay;
+        R[3] = t1 * ax * ay + s * az; R[4] = t1 * ay * ay + c;      R[5] = t1 * ay * az - s * ax;
+        R[6] = t1 * ax * az - s * ay; R[7] = t1 * ay * az + s * ax; R[8] = t1 * az * az + c;
+        p[0] = bc.jpos[0]; p[1] = bc.jpos[1]; p[2] = bc.jpos[2];
+    }
+    {
+        int anc = bc.par;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int src = anc < 0 ? j : anc;
+            double Ra[9], pa[3];
+#pragma unroll
+            for (int k = 0; k < 9; k++) Ra[k] = g8_get(R[k], src);
+#pragma unroll
+            for (int k = 0; k < 3; k++) pa[k] = g8_get(p[k], src);
+            const int anc2 = g8_geti(anc, src);
+            if (anc >= 0) {
+                double t[3];
+                m3mulv(t, Ra, p);
+                p[0] = pa[0] + t[0]; p[1] = pa[1] + t[1]; p[2] = pa[2] + t[2];
+                m3mul(R, Ra, R);
+                anc = anc2;
+            }
+        }
+    }
+    double a[3], lin[3];
+    m3mulv(a, R, bc.axis);
+    v3cross(lin, p, a); // velocity of the origin-coincident point for unit joint rate
+
+    // ---- body velocities about the world origin: prefix sums of a qd, lin qd over ancestors-or-self
+    double w[3], vO[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { w[k] = a[k] * st.qd; vO[k] = lin[k] * st.qd; }
+    {
+        int anc = bc.par;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int src = anc < 0 ? j : anc;
+            double wa[3], va[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { wa[k] = g8_get(w[k], src); va[k] = g8_get(vO[k], src); }
+            const int anc2 = g8_geti(anc, src);
+            if (anc >= 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { w[k] += wa[k]; vO[k] += va[k]; }
+                anc = anc2;
+            }
+        }
+    }
+
+    // ---- lane-local: spatial inertia about the world origin (body_inertias) and bullet's per-link damping wrench (damping_forces)
+    double acc[16]; // [0..5] damping wrench (N, F) about the origin, [6..15] spatial inertia m, h(3), I(6): summed over subtrees below
+    {
+        double cw[3], t[3];
+        m3mulv(t, R, bc.com);
+        cw[0] = p[0] + t[0]; cw[1] = p[1] + t[1]; cw[2] = p[2] + t[2];
+        const double m = bc.mass;
+        const double* I = bc.inertia;
+        double Ic[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]}, RI[9];
+        m3mul(RI, R, Ic);
+        const double xx = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2];
+        const double xy = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5];
+        const double xz = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8];
+        const double yy = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5];
+        const double yz = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8];
+        const double zz = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8];
+        const double c2 = v3dot(cw, cw);
+        acc[6] = m;
+        acc[7] = m * cw[0]; acc[8] = m * cw[1]; acc[9] = m * cw[2];
+        acc[10] = xx + m * (c2 - cw[0] * cw[0]);
+        acc[11] = xy - m * cw[0] * cw[1];
+        acc[12] = xz - m * cw[0] * cw[2];
+        acc[13] = yy + m * (c2 - cw[1] * cw[1]);
+        acc[14] = yz - m * cw[1] * cw[2];
+        acc[15] = zz + m * (c2 - cw[2] * cw[2]);
+    }
+    {
+        const double ka = ph.ang_damping * (1.0 + (double)sqrtf((float)v3dot(w, w)));
+        double wb[3], Nb[3] = {0, 0, 0}, Na[3] = {0, 0, 0}, Fa[3] = {0, 0, 0};
+        m3tmulv(wb, R, w);
+#pragma unroll 1
+        for (int it = 0; it < max_sub; it++) {
+            const int s = bc.sub0 + it;
+            if (s < bc.sub1) {
+                const double* sd = s_sub + s * G8_SUBW;
+                const double scom[3] = {sd[0], sd[1], sd[2]};
+                double srot[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) srot[k] = sd[3 + k];
+                double t[3], x[3], v[3], wl[3], nl[3], nb[3], xf[3];
+                m3mulv(t, R, scom);
+                x[0] = p[0] + t[0]; x[1] = p[1] + t[1]; x[2] = p[2] + t[2];
+                v3cross(v, w, x);
+                v[0] += vO[0]; v[1] += vO[1]; v[2] += vO[2];
+                const double kl = ph.lin_damping * (1.0 + (double)sqrtf((float)v3dot(v, v)));
+                m3tmulv(wl, srot, wb);
+#pragma unroll
+                for (int k = 0; k < 3; k++) nl[k] = -sd[12 + k] * wl[k] * ka;
+                m3mulv(nb, srot, nl);
+                const double ms = sd[15];
+                const double f[3] = {-ms * v[0] * kl, -ms * v[1] * kl, -ms * v[2] * kl};
+                v3cross(xf, x, f);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { Nb[k] += nb[k]; Na[k] += xf[k]; Fa[k] += f[k]; }
+            }
+        }
+        double nwv[3];
+        m3mulv(nwv, R, Nb);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { acc[k] = nwv[k] + Na[k]; acc[3 + k] = Fa[k]; }
+    }
+    // ---- suffix sums over the tree: subtree damping wrench, composite inertia
+    Tp::template subtree_sum<16>(acc, j);
+    double tau = v3dot(a, acc) + v3dot(lin, acc + 3) - ph.joint_damping * st.qd;
+
+    // ---- CRBA: (n, f) = composite inertia of subtree j applied to joint j's motion; M[k][j] = S_k . (n, f) for ancestors k
+    double Mcol[Tp::MAXDEPTH + 1];
+    {
+        double n[3], f[3];
+        SpI sp;
+        sp.m = acc[6];
+#pragma unroll
+        for (int k = 0; k < 3; k++) sp.h[k] = acc[7 + k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) sp.I[k] = acc[10 + k];
+        spi_apply(sp, a, lin, n, f);
+        Mcol[0] = v3dot(a, n) + v3dot(lin, f);
+        int anc = bc.par;
+#pragma unroll
+        for (int d = 1; d <= Tp::MAXDEPTH; d++) {
+            const int src = anc < 0 ? j : anc;
+            double ak[3], lk[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { ak[k] = g8_get(a[k], src); lk[k] = g8_get(lin[k], src); }
+            const int anc2 = g8_geti(bc.par, src);
+            Mcol[d] = anc >= 0 ? v3dot(ak, n) + v3dot(lk, f) : 0.0;
+            anc = anc >= 0 ? anc2 : -1;
+        }
+    }
+    // ---- every lane gathers the whole matrix, factorises it, and solves for its own column of A = M^-1
+    double A[NB]; // A[r] = A[r][j] = A[j][r]
+    {
+        double Mf[NB][NB], L[NB][NB], dinv[NB];
+#pragma unroll
+        for (int jj = 0; jj < NB; jj++)
+#pragma unroll
+            for (int k = 0; k <= jj; k++)
+                Mf[k][jj] = Tp::is_anc(k, jj) ? g8_get(Mcol[Tp::depth(jj) - Tp::depth(k)], jj) : 0.0;
+        g8_cholesky<NB>(Mf, L, dinv);
+        double y[NB];
+#pragma unroll
+        for (int k = 0; k < NB; k++) {      // L y = e_j
+            double s = j == k ? 1.0 : 0.0;
+#pragma unroll
+            for (int m = 0; m < k; m++) s -= L[k][m] * y[m];
+            y[k] = s * dinv[k];
+        }
+#pragma unroll
+        for (int k = NB - 1; k >= 0; k--) { // L^T x = y
+            double s = y[k];
+#pragma unroll
+            for (int m = k + 1; m < NB; m++) s -= L[m][k] * A[m];
+            A[k] = s * dinv[k];
+        }
+    }
+    // ---- unconstrained velocity update: qdd_j = sum_k A[j][k] tau_k
+    double Ajj = 0.0;
+    {
+        double qdd = 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; k++) { qdd += A[k] * g8_get(tau, k); Ajj = j == k ? A[k] : Ajj; }
+        st.qd += ph.dt * qdd;
+    }
+
+    // ---- motor rows (J = e_i, response column A[:, i], |impulse| <= force * dt) and projected Gauss-Seidel
+    const double lim = max_force * ph.dt;
+    const double dinv_m = Ajj > 2.2204460492503131e-16 ? 1.0 / Ajj : 0.0;
+    double rhs;
+    {
+        const double v = st.qd;
+        const double pos_stab = mode == 1 ? kp * ((tpos - st.q) / ph.dt) : 0.0;
+        const double rhs_v = pos_stab + v + kd * (tvel - v);
+        rhs = (rhs_v - v) * dinv_m;
+    }
+    double applied = 0.0, dv = 0.0;
+    if (lim != 0.0) {
+        bool active = live;
+        const unsigned gshift = (threadIdx.x & 24);  // bit offset of this group's lanes in a warp ballot
+#pragma unroll 1
+        for (int it = 0; it < ph.solver_iters; it++) {
+            if (__ballot_sync(G8_FULL, active) == 0u) break;
+            double resid = 0.0;
+            auto row = [&](int r) {
+                double delta = rhs - dv * dinv_m;
+                const double sum = applied + delta;
+                const bool lo = sum < -lim, hi = sum > lim;
+                delta = lo ? (-lim - applied) : (hi ? (lim - applied) : delta);
+                const double napp = lo ? -lim : (hi ? lim : sum);
+                const bool mine = active && j == r;
+                applied = mine ? napp : applied;
+                const double dvel = delta * Ajj;
+                resid = mine ? dvel * dvel : resid;
+                const double dl = g8_get(active ? delta : 0.0, r);
+                dv += A[r] * dl;
+            };
+            if (it & 1) {
+#pragma unroll
+                for (int r = 0; r < NB; r++) row(r);
+            } else {
+#pragma unroll
+                for (int r = NB - 1; r >= 0; r--) row(r);
+            }
+            const unsigned big = __ballot_sync(G8_FULL, active && resid > ph.solver_residual_threshold);
+            if (((big >> gshift) & 0xffu) == 0u) active = false;
+        }
+    }
+    st.qd += dv;
+    const double d = ph.dt * st.qd;
+    st.q += d;
+    double sc[2] = {st.s, st.c};
+    sc_advance(sc, st.q, d);
+    st.s = sc[0]; st.c = sc[1];
+}
+
+// step kernel, 8 lanes per env: tasks with motor rows only (edge_follow, surface_follow), TCP_velocity_control, gravity
+// compensation on.  Blocks >= b.step_blocks keep the standby role of step_kernel.
+template <class T, int TASK>
+__global__ void __launch_bounds__(128)
+step_kernel_g8(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
+               EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
+{
+    constexpr int NB = T::NB;
+    if ((int)blockIdx.x >= b.step_blocks) {
+        standby_role<T>(arm, ph, task, b, b.step_blocks, false);
+        return;
+    }
+    __shared__ double s_sub[TG_MAXSUB * G8_SUBW];
+    g8_fill_sub_table(arm, s_sub);
+    __syncthreads();
+    const int j = threadIdx.x & (G8 - 1);
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = e < b.n;
+    G8Body bc;
+    g8_load_body<T>(arm, j, bc);
+    int max_sub = 0;
+#pragma unroll
+    for (int i = 0; i < NB; i++) max_sub = max(max_sub, arm.sub_start[i + 1] - arm.sub_start[i]);
+
+    G8Lane st;
+    st.q = 0.0; st.qd = 0.0;
+    if (live && j < NB) { st.q = b.q[(size_t)j * b.n + e]; st.qd = b.qd[(size_t)j * b.n + e]; }
+    sincos(st.q, &st.s, &st.c);
+
+    // the head of the step runs on the group's first lane, with the one-thread formulation (once per env step)
+    double q[NB], qd[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) q[i] = g8_get(st.q, i);
+    double tv_all[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) tv_all[i] = 0.0;
+    if (live && j == 0) {
+        double v[6];
+        Motors<NB> mot;
+        env_prologue<T, TASK>(arm, ph, task, b, e, actions, q, v, mot);
+#pragma unroll
+        for (int i = 0; i < NB; i++) tv_all[i] = mot.target_vel[i];
+    }
+    double tvel = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const double t = g8_get(tv_all[i], 0);
+        tvel = j == i ? t : tvel;
+    }
+#pragma unroll 1
+    for (int s = 0; s < ph.substeps; s++) g8_substep<T>(ph, bc, s_sub, max_sub, j, live, st, 0, 0.0, ph.vel_gain, ph.max_force, 0.0, tvel);
+
+#pragma unroll
+    for (int i = 0; i < NB; i++) { q[i] = g8_get(st.q, i); qd[i] = g8_get(st.qd, i); }
+    if (live && j == 0) {
+        ObjState ob;
+        env_epilogue<T, TASK>(arm, ph, task, b, e, q, qd, ob, reward, done, autoreset);
+    }
+}
+
+// test hook: nsteps x g8_substep with velocity motors from given joint states (tg_test_substep_g8)
+template <class T>
+__global__ void __launch_bounds__(128)
+test_substep_g8_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, int n, int nsteps, double* q_io, double* qd_io,
+                       const double* target_vel)
+{
+    constexpr int NB = T::NB;
+    __shared__ double s_sub[TG_MAXSUB * G8_SUBW];
+    g8_fill_sub_table(arm, s_sub);
+    __syncthreads();
+    const int j = threadIdx.x & (G8 - 1);
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = e < n, mine = live && j < NB;
+    G8Body bc;
+    g8_load_body<T>(arm, j, bc);
+    int max_sub = 0;
+#pragma unroll
+    for (int i = 0; i < NB; i++) max_sub = max(max_sub, arm.sub_start[i + 1] - arm.sub_start[i]);
+    G8Lane st;
+    st.q = mine ? q_io[e * NB + j] : 0.0;
+    st.qd = mine ? qd_io[e * NB + j] : 0.0;
+    const double tv = mine ? target_vel[e * NB + j] : 0.0;
+    sincos(st.q, &st.s, &st.c);
+#pragma unroll 1
+    for (int s = 0; s < nsteps; s++) g8_substep<T>(ph, bc, s_sub, max_sub, j, live, st, 0, 0.0, ph.vel_gain, ph.max_force, 0.0, tv);
+    if (mine) { q_io[e * NB + j] = st.q; qd_io[e * NB + j] = st.qd; }
+}

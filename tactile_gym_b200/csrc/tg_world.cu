@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "tg_env.cuh"
+#include "tg_g8.cuh"
 #include "tg_raster.cuh"
 #include "tg_raster_hf.cuh"
 #include "tg_raster_sphere.cuh"
@@ -58,6 +59,8 @@ struct TgWorld {
     size_t push_smem = 0;
     int raster_grid = 0;
     int standby_blocks = 0;
+    bool use_g8 = false;              // 8 lanes per env (tg_g8.cuh) instead of one thread per env
+    int g8_blocks = 0;
     long long launches = 0;
     // tg_step_host: device staging for the actions, a copy stream and one event per observation chunk
     double* cam_local = nullptr;      // surface_follow-v2 (vertical): the cameras in the heightfield's frame, [N][12]
@@ -132,6 +135,16 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     w->sm_count = prop.multiProcessorCount;
     const int n = w->n, nb = w->nb;
     int lanes = cfg->lanes_per_warp;
+    {
+        // the 8-lanes-per-env kernel: motor-row tasks under TCP_velocity_control with gravity compensation.  One warp carries 4
+        // envs (against up to 32 of the one-thread kernel), so it wins while the device is not yet full of warps
+        const bool can = (cfg->task.task == TG_TASK_EDGE_FOLLOW || cfg->task.task == TG_TASK_SURFACE_FOLLOW) && cfg->task.control_mode == 0 &&
+                         cfg->phys.gravity_comp == 1;
+        if (lanes == -8 && !can) return fail(TG_EUNSUPPORTED, "lanes_per_warp = -8 (8 lanes per env) is built for edge_follow / surface_follow under TCP_velocity_control");
+        w->use_g8 = can && (lanes == -8 || (lanes == 0 && n <= 16384));
+        if (const char* ev = getenv("TG_G8")) w->use_g8 = can && atoi(ev) != 0;     // tuning hook
+        w->g8_blocks = (n + 15) / 16;
+    }
     if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) {
         // The per-env work is one long dependent fp64 chain and a warp costs the same issue slots whether 1 or
         // 32 lanes are active, so the kernel time is the chain latency as long as every SM sub-partition has
@@ -464,6 +477,19 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
 static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, int autoreset, cudaStream_t st)
 {
     w->eb.epoch = ++w->epoch;
+    if (w->use_g8) {
+        EnvBuffers eb = w->eb;
+        eb.step_blocks = w->g8_blocks;
+        const dim3 grid(w->g8_blocks + w->standby_blocks);
+#define G8_LAUNCH(Topo, TASK) step_kernel_g8<Topo, TASK><<<grid, 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, eb, d_actions, d_reward, d_done, autoreset)
+        const bool surf = w->cfg.task.task == TG_TASK_SURFACE_FOLLOW;
+        if (w->cfg.arm.topo == TG_TOPO_MG400) { if (surf) G8_LAUNCH(TopoMG400, TG_TASK_SURFACE_FOLLOW); else G8_LAUNCH(TopoMG400, TG_TASK_EDGE_FOLLOW); }
+        else { if (surf) G8_LAUNCH(TopoChain6, TG_TASK_SURFACE_FOLLOW); else G8_LAUNCH(TopoChain6, TG_TASK_EDGE_FOLLOW); }
+#undef G8_LAUNCH
+        w->launches++;
+        CK(cudaGetLastError());
+        return TG_OK;
+    }
     const dim3 grid(w->eb.step_blocks + w->standby_blocks); // the extra blocks recompute consumed standbys meanwhile
     const dim3 pgrid((w->n + PUSH_BLOCK - 1) / PUSH_BLOCK);  // object_push: PUSH_BLOCK envs per block, rows in shared memory
     if (w->cfg.arm.topo == TG_TOPO_MG400) { STEP_DISPATCH(TopoMG400) } else { STEP_DISPATCH(TopoChain6) }
@@ -727,6 +753,26 @@ extern "C" int tg_test_substep(TgWorld* w, int n, int nsteps, double* h_q, doubl
     if (e == cudaSuccess) e = cudaMemcpy(h_qd, qd, bytes, cudaMemcpyDeviceToHost);
     cudaFree(q); cudaFree(qd); cudaFree(tv);
     if (e != cudaSuccess) return fail(TG_ECUDA, "test_substep failed: %s", cudaGetErrorString(e));
+    return TG_OK;
+}
+
+extern "C" int tg_test_substep_g8(TgWorld* w, int n, int nsteps, double* h_q, double* h_qd, const double* h_target_vel)
+{
+    if (!w || n <= 0) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    const size_t bytes = sizeof(double) * n * w->nb;
+    double *q, *qd, *tv;
+    CK(cudaMalloc(&q, bytes)); CK(cudaMalloc(&qd, bytes)); CK(cudaMalloc(&tv, bytes));
+    CK(cudaMemcpy(q, h_q, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(qd, h_qd, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tv, h_target_vel, bytes, cudaMemcpyHostToDevice));
+    TOPO_DISPATCH(w, (test_substep_g8_kernel<Topo><<<(n + 15) / 16, 128>>>(w->cfg.arm, w->cfg.phys, n, nsteps, q, qd, tv)));
+    w->launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(h_q, q, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_qd, qd, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(q); cudaFree(qd); cudaFree(tv);
+    if (e != cudaSuccess) return fail(TG_ECUDA, "test_substep_g8 failed: %s", cudaGetErrorString(e));
     return TG_OK;
 }
 
