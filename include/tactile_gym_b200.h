@@ -201,7 +201,7 @@ typedef struct {
     int32_t n_envs;
     int32_t lanes_per_warp; /* physics kernels: 0 = auto; 1/2/4/8/16/32 = one thread per env with that many active lanes per
                                warp; -8 = one env per group of 8 lanes, one body per lane (csrc/tg_g8.cuh: edge_follow /
-                               surface_follow under TCP_velocity_control; what auto picks for them up to 16,384 envs) */
+                               surface_follow under TCP_velocity_control; what auto picks for them up to 6,144 envs) */
     TgArm arm;
     TgPhysics phys;
     TgTask task;

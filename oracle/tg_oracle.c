@@ -488,6 +488,9 @@ void or_forward_dynamics(const OrModel* m, const double* q, const double* qd, co
  *   5. qd += delta; q += dt * qd
  * Call site: robots/arms/robot.py:141; parameters rl_envs/base_tactile_env.py:127-130.
  */
+/* diagnostics (tools/sweep_stats.py): PGS sweeps executed and calls, summed since the library was loaded */
+long long or_dbg_sweeps = 0, or_dbg_calls = 0;
+
 void or_step_simulation(const OrModel* m, OrState* s, const double* tau_applied)
 {
     int n = m->ndof;
@@ -531,8 +534,10 @@ void or_step_simulation(const OrModel* m, OrState* s, const double* tau_applied)
             double dvel = diaginv[r] != 0 ? delta / diaginv[r] : 0.0;
             if (dvel * dvel > resid) resid = dvel * dvel;
         }
+        or_dbg_sweeps++;
         if (resid <= m->solver_residual_threshold) break;
     }
+    or_dbg_calls++;
     for (int i = 0; i < n; i++) { s->qd[i] += dv[i]; s->q[i] += m->dt * s->qd[i]; }
 }
 

@@ -170,13 +170,8 @@ TGD int env_index(const EnvBuffers& b)
 
 // camera frame (sensors/tactile_sensor.py:150-229): eye, forward = R ex, up = R ez, then computeViewMatrix's
 // orthonormalisation: f = norm(target - eye), s = norm(f x up), u = s x f
-template <class T>
-TGD void write_camera(const TgArm& arm, const Kin<T::NB>& k, double* cam)
+TGD void camera_from_frame(const double* pos, const double* R, double* cam)
 {
-    double pos[3], R[9];
-#pragma unroll
-    for (int b = 0; b < T::NB; b++)
-        if (arm.cam_body == b) frame_pose<T::NB>(k, b, arm.cam_pos, arm.cam_rot, pos, R);
     double f[3] = {R[0], R[3], R[6]}, u[3] = {R[2], R[5], R[8]}, s[3];
     double fn = 1.0 / sqrt(v3dot(f, f)); f[0] *= fn; f[1] *= fn; f[2] *= fn;
     double un = 1.0 / sqrt(v3dot(u, u)); u[0] *= un; u[1] *= un; u[2] *= un;
@@ -185,6 +180,15 @@ TGD void write_camera(const TgArm& arm, const Kin<T::NB>& k, double* cam)
     v3cross(u, s, f);
 #pragma unroll
     for (int c = 0; c < 3; c++) { cam[c] = pos[c]; cam[3 + c] = f[c]; cam[6 + c] = u[c]; cam[9 + c] = s[c]; }
+}
+template <class T>
+TGD void write_camera(const TgArm& arm, const Kin<T::NB>& k, double* cam)
+{
+    double pos[3], R[9];
+#pragma unroll
+    for (int b = 0; b < T::NB; b++)
+        if (arm.cam_body == b) frame_pose<T::NB>(k, b, arm.cam_pos, arm.cam_rot, pos, R);
+    camera_from_frame(pos, R, cam);
 }
 
 // edge_follow reward / termination (edge_follow_env.py:371-452)
@@ -883,8 +887,8 @@ __device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhy
 // TCP_velocity_control - check_TCP_vel_lims, the twist in the world frame and the joint velocity targets (mot.target_vel).
 // v[6] = the scaled 6-vector (TCP_position_control consumes it as a pose delta).
 template <class T, int TASK>
-TGD void env_prologue(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const float* __restrict__ actions,
-                      const double* q, double* v, Motors<T::NB>& mot)
+TGD void env_prologue_core(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const float* __restrict__ actions,
+                           const double* tp, const double* tq, const double (&J)[6][T::NB], double* v, Motors<T::NB>& mot)
 {
     constexpr int NB = T::NB;
     constexpr bool roll = TASK == TG_TASK_OBJECT_ROLL, surface = TASK == TG_TASK_SURFACE_FOLLOW;
@@ -892,10 +896,7 @@ TGD void env_prologue(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
     // encode_actions + scale_actions (edge_follow_env.py:345-369, base_tactile_env.py:141-164)
     mot.mode = 0; mot.kp = 0; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
     {
-        Kin<NB> k;
-        fk<T>(arm, q, k);
-        double tp[3], tq[4], wq[4], Rw[9];
-        tcp_world<T>(arm, k, tp, tq);
+        double wq[4], Rw[9];
         quat_from_euler(task.workframe_rpy, wq);
         mat_from_quat(wq, Rw);
         double enc[6] = {0, 0, 0, 0, 0, 0};
@@ -954,8 +955,6 @@ TGD void env_prologue(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
         }
         double vw[6];
         m3mulv(vw, Rw, v); m3mulv(vw + 3, Rw, v + 3);
-        double J[6][NB];
-        tcp_jacobian<T>(arm, k, tp, J);
         bool use_pinv = NB != 6 || arm.topo == TG_TOPO_MG400;   // mg400.py:109 always uses the pseudo-inverse
         if (NB == 6) {
             double Mx[6][7];
@@ -980,11 +979,25 @@ TGD void env_prologue(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
     }
 }
 
+// the same from the joint angles (one-thread-per-env kernels): FK, TCP pose, Jacobian, then the core
+template <class T, int TASK>
+TGD void env_prologue(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const float* __restrict__ actions,
+                      const double* q, double* v, Motors<T::NB>& mot)
+{
+    Kin<T::NB> k;
+    fk<T>(arm, q, k);
+    double tp[3], tq[4], J[6][T::NB];
+    tcp_world<T>(arm, k, tp, tq);
+    tcp_jacobian<T>(arm, k, tp, J);
+    env_prologue_core<T, TASK>(arm, ph, task, b, e, actions, tp, tq, J, v, mot);
+}
+
 // Tail of one env step for env e: store the joint state, step data (reward / done), features / oracle vector, then either the
 // camera for the raster or - for a finished env under auto-reset - the terminal camera and the swap to the next episode.
 template <class T, int TASK>
-TGD void env_epilogue(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const double* q, const double* qd,
-                      const ObjState& ob, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
+TGD void env_epilogue_core(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const double* q, const double* qd,
+                           const double* tp, const double* tq, const double* cam, const ObjState& ob, float* __restrict__ reward,
+                           unsigned char* __restrict__ done, int autoreset)
 {
     constexpr int NB = T::NB;
     constexpr bool balance = TASK == TG_TASK_OBJECT_BALANCE, roll = TASK == TG_TASK_OBJECT_ROLL, surface = TASK == TG_TASK_SURFACE_FOLLOW;
@@ -993,10 +1006,6 @@ TGD void env_epilogue(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
     b.steps[e] = steps;
 #pragma unroll
     for (int i = 0; i < NB; i++) { b.q[(size_t)i * b.n + e] = q[i]; b.qd[(size_t)i * b.n + e] = qd[i]; }
-    Kin<NB> k;
-    fk<T>(arm, q, k);
-    double tp[3], tq[4];
-    tcp_world<T>(arm, k, tp, tq);
     float r; unsigned char d;
     if (roll) {
         const double* tr = b.traj + (size_t)e * PUSH_TRAJ_SZ;
@@ -1039,21 +1048,34 @@ TGD void env_epilogue(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
     }
     if (d && autoreset && b.pipeline) {
         // terminal camera for the terminal observation, then the standby becomes the live state
-        write_camera<T>(arm, k, b.term_cam + (size_t)e * 12);
 #pragma unroll
-        for (int c = 0; c < 12; c++) b.term_stim[(size_t)e * 12 + c] = b.stim[(size_t)e * 12 + c];
+        for (int c = 0; c < 12; c++) { b.term_cam[(size_t)e * 12 + c] = cam[c]; b.term_stim[(size_t)e * 12 + c] = b.stim[(size_t)e * 12 + c]; }
         acquire_standby<T>(arm, ph, task, b, e);
         write_live_features(task, b, e);
         if (surface && task.sparse_reward) surface_accum_start(task, b, e);
         if (b.oracle) oracle_obs_env<T>(arm, task, b, e, b.oracle + (size_t)e * TG_ORACLE_NOBS);
     } else {
-        write_camera<T>(arm, k, b.cam + (size_t)e * 12);
+#pragma unroll
+        for (int c = 0; c < 12; c++) b.cam[(size_t)e * 12 + c] = cam[c];
 #pragma unroll
         for (int c = 0; c < 3; c++) b.tcp[(size_t)e * 7 + c] = tp[c];
 #pragma unroll
         for (int c = 0; c < 4; c++) b.tcp[(size_t)e * 7 + 3 + c] = tq[c];
     }
     if (push && b.pipeline) standby_work<T>(arm, ph, task, b, e, false); // one quantum of this env's next-episode rebuild, if due
+}
+
+// the same from the joint angles (one-thread-per-env kernels)
+template <class T, int TASK>
+TGD void env_epilogue(const TgArm& arm, const TgPhysics& ph, const TgTask& task, const EnvBuffers& b, int e, const double* q, const double* qd,
+                      const ObjState& ob, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
+{
+    Kin<T::NB> k;
+    fk<T>(arm, q, k);
+    double tp[3], tq[4], cam[12];
+    tcp_world<T>(arm, k, tp, tq);
+    write_camera<T>(arm, k, cam);
+    env_epilogue_core<T, TASK>(arm, ph, task, b, e, q, qd, tp, tq, cam, ob, reward, done, autoreset);
 }
 
 template <class T, int TASK>

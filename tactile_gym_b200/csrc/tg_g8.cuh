@@ -32,15 +32,17 @@ template <> struct G8Topo<TopoChain6> {
     static constexpr int MAXDEPTH = 5;
     __host__ __device__ static constexpr int depth(int i) { return i; }
     __host__ __device__ static constexpr bool is_anc(int k, int j) { return k <= j; } // k ancestor-or-self of j
-    // v <- sum of v over the subtree of each lane (lanes >= NB hold zeros)
+    // v <- sum of v over the subtree of each lane: suffix sums along the chain.  Lanes 6, 7 are leaves below lane 5 when they
+    // lend a hand with its sub-links (their own "subtree" sums are never read), zero otherwise.
     template <int CNT> TGD static void subtree_sum(double (&v)[CNT], int j)
     {
 #pragma unroll
         for (int d = 1; d < G8; d <<= 1) {
+            const bool in = j + d < G8;
 #pragma unroll
             for (int c = 0; c < CNT; c++) {
                 const double t = g8_down(v[c], d);
-                v[c] += (j + d < G8) ? t : 0.0;
+                v[c] += in ? t : 0.0;
             }
         }
     }
@@ -92,6 +94,34 @@ TGD void g8_load_body(const TgArm& arm, int j, G8Body& c)
     c.par = live ? T::parent(jj) : -1;
     c.sub0 = live ? arm.sub_start[jj] : 0;
     c.sub1 = live ? arm.sub_start[jj + 1] : 0;
+    if (T::NB < G8) {
+        // Idle lanes lend a hand with the per-link damping: a body's sub-links beyond its first move (last first) to idle
+        // lanes, which sit in the tree as massless leaves rigidly below that body (zero axis: same frame, same velocity, no
+        // joint), so the scans hand them the body's kinematics and the suffix sums hand the body their wrench.  UR5: wrist 3
+        // carries three links (wrist, sensor body, tip) and lanes 6, 7 are idle - no lane loops over sub-links at all.
+        int extra = 0, taken = 0; // extras handed out so far; those of THIS lane's body
+#pragma unroll
+        for (int bdy = 0; bdy < T::NB; bdy++) {
+            const int s0 = arm.sub_start[bdy], s1 = arm.sub_start[bdy + 1];
+            for (int sx = s1 - 1; sx > s0; sx--) {
+                const int lane_x = T::NB + extra;
+                if (lane_x >= G8) break;
+                if (j == lane_x) { c.par = bdy; c.sub0 = sx; c.sub1 = sx + 1; }
+                if (j == bdy) taken++;
+                extra++;
+            }
+        }
+        if (live) c.sub1 -= taken; // the body keeps the head of its range
+    }
+}
+
+// the longest sub-link range any lane of the warp carries (trip count of the damping loop)
+TGD int g8_max_sub(const G8Body& c)
+{
+    int m = c.sub1 - c.sub0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) m = max(m, __shfl_xor_sync(G8_FULL, m, d));
+    return m;
 }
 
 TGD void g8_fill_sub_table(const TgArm& arm, double* s_sub)
@@ -130,6 +160,60 @@ TGD void g8_cholesky(const double (&Mf)[NB][NB], double (&L)[NB][NB], double (&d
     }
 }
 
+// forward kinematics of the group: T_j = T_parent o (Rot(axis, q), jpos), composed by pointer jumping (3 rounds: depth <= 8).
+// R, p: world rotation of body j's frame and world position of its joint origin (Kin<>::R, Kin<>::p of tg_dyn.cuh).
+TGD void g8_fk(const G8Body& bc, int j, double sn, double cs, double (&R)[9], double (&p)[3])
+{
+    {
+        const double s = sn, c = cs, ax = bc.axis[0], ay = bc.axis[1], az = bc.axis[2], t1 = 1.0 - c;
+        R[0] = t1 * ax * ax + c;      R[1] = t1 * ax * ay - s * az; R[2] = t1 * ax * az + s * ay;
+        R[3] = t1 * ax * ay + s * az; R[4] = t1 * ay * ay + c;      R[5] = t1 * ay * az - s * ax;
+        R[6] = t1 * ax * az - s * ay; R[7] = t1 * ay * az + s * ax; R[8] = t1 * az * az + c;
+        p[0] = bc.jpos[0]; p[1] = bc.jpos[1]; p[2] = bc.jpos[2];
+    }
+    int anc = bc.par;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const int src = anc < 0 ? j : anc;
+        double Ra[9], pa[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Ra[k] = g8_get(R[k], src);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pa[k] = g8_get(p[k], src);
+        const int anc2 = g8_geti(anc, src);
+        if (anc >= 0) {
+            double t[3];
+            m3mulv(t, Ra, p);
+            p[0] = pa[0] + t[0]; p[1] = pa[1] + t[1]; p[2] = pa[2] + t[2];
+            m3mul(R, Ra, R);
+            anc = anc2;
+        }
+    }
+}
+
+// TCP pose (getLinkState(tcp)[0:2]) and camera frame of the group from the lanes' body frames: computed on the lane that carries
+// the body, handed to every lane.  tp[3], tq[4], cam[12] as tcp_world / write_camera give them.
+TGD void g8_tcp_and_camera(const TgArm& arm, const double (&R)[9], const double (&p)[3], double* tp, double* tq, double* cam)
+{
+    double pos[3], Rt[9], t[3], q4[4], c12[12];
+    m3mulv(t, R, arm.tcp_pos);
+    pos[0] = p[0] + t[0]; pos[1] = p[1] + t[1]; pos[2] = p[2] + t[2];
+    m3mul(Rt, R, arm.tcp_rot);
+    quat_from_mat(q4, Rt);
+#pragma unroll
+    for (int k = 0; k < 3; k++) tp[k] = g8_get(pos[k], arm.tcp_body);
+#pragma unroll
+    for (int k = 0; k < 4; k++) tq[k] = g8_get(q4[k], arm.tcp_body);
+    if (cam) {
+        m3mulv(t, R, arm.cam_pos);
+        pos[0] = p[0] + t[0]; pos[1] = p[1] + t[1]; pos[2] = p[2] + t[2];
+        m3mul(Rt, R, arm.cam_rot);
+        camera_from_frame(pos, Rt, c12);
+#pragma unroll
+        for (int k = 0; k < 12; k++) cam[k] = g8_get(c12[k], arm.cam_body);
+    }
+}
+
 // state of one lane between substeps
 struct G8Lane {
     double q, qd, s, c; // joint angle, rate, sin, cos
@@ -143,35 +227,8 @@ TGD void g8_substep(const TgPhysics& ph, const G8Body& bc, const double* __restr
 {
     constexpr int NB = T::NB;
     using Tp = G8Topo<T>;
-    // ---- forward kinematics: T_j = T_parent o (Rot(axis, q), jpos), composed by pointer jumping
     double R[9], p[3];
-    {
-        const double s = st.s, c = st.c, ax = bc.axis[0], ay = bc.axis[1], az = bc.axis[2], t1 = 1.0 - c;
-        R[0] = t1 * ax * ax + c;      R[1] = t1 * ax * ay - s * az; R[2] = t1 * ax * az + s * ay;
-        R[3] = t1 * ax * ay + s * az; R[4] = t1 * ay * ay + c;      R[5] = t1 * ay * az - s * ax;
-        R[6] = t1 * ax * az - s * ay; R[7] = t1 * ay * az + s * ax; R[8] = t1 * az * az + c;
-        p[0] = bc.jpos[0]; p[1] = bc.jpos[1]; p[2] = bc.jpos[2];
-    }
-    {
-        int anc = bc.par;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const int src = anc < 0 ? j : anc;
-            double Ra[9], pa[3];
-#pragma unroll
-            for (int k = 0; k < 9; k++) Ra[k] = g8_get(R[k], src);
-#pragma unroll
-            for (int k = 0; k < 3; k++) pa[k] = g8_get(p[k], src);
-            const int anc2 = g8_geti(anc, src);
-            if (anc >= 0) {
-                double t[3];
-                m3mulv(t, Ra, p);
-                p[0] = pa[0] + t[0]; p[1] = pa[1] + t[1]; p[2] = pa[2] + t[2];
-                m3mul(R, Ra, R);
-                anc = anc2;
-            }
-        }
-    }
+    g8_fk(bc, j, st.s, st.c, R, p);
     double a[3], lin[3];
     m3mulv(a, R, bc.axis);
     v3cross(lin, p, a); // velocity of the origin-coincident point for unit joint rate
@@ -391,43 +448,71 @@ step_kernel_g8(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhys
     const bool live = e < b.n;
     G8Body bc;
     g8_load_body<T>(arm, j, bc);
-    int max_sub = 0;
-#pragma unroll
-    for (int i = 0; i < NB; i++) max_sub = max(max_sub, arm.sub_start[i + 1] - arm.sub_start[i]);
+    const int max_sub = g8_max_sub(bc);
 
     G8Lane st;
     st.q = 0.0; st.qd = 0.0;
     if (live && j < NB) { st.q = b.q[(size_t)j * b.n + e]; st.qd = b.qd[(size_t)j * b.n + e]; }
     sincos(st.q, &st.s, &st.c);
 
-    // the head of the step runs on the group's first lane, with the one-thread formulation (once per env step)
-    double q[NB], qd[NB];
+    // ---- head of the step.  Lane-parallel: FK, TCP pose, the TCP Jacobian (column j on lane j).  On the group's first lane:
+    // action encoding, TCP limits, the 6 x NB solve (env_prologue_core, the one-thread formulation, once per env step).
+    double q[NB], qd[NB], tvel = 0.0;
+    {
+        double R[9], p[3], tp[3], tq[4];
+        g8_fk(bc, j, st.s, st.c, R, p);
+        g8_tcp_and_camera(arm, R, p, tp, tq, nullptr);
+        // geometric Jacobian column of joint j (tcp_jacobian): a_j x (tcp - p_j), a_j for the ancestors-or-self of the TCP body
+        double ax[3], col[6];
+        m3mulv(ax, R, bc.axis);
+        const double r[3] = {tp[0] - p[0], tp[1] - p[1], tp[2] - p[2]};
+        v3cross(col, ax, r);
+        col[3] = ax[0]; col[4] = ax[1]; col[5] = ax[2];
+        bool on_path = false; // body j is the TCP body or one of its ancestors
+        {
+            int a = arm.tcp_body;
 #pragma unroll
-    for (int i = 0; i < NB; i++) q[i] = g8_get(st.q, i);
-    double tv_all[NB];
+            for (int k = 0; k < G8; k++) { on_path = on_path || a == j; const int pa = g8_geti(bc.par, a < 0 ? 0 : a); a = a >= 0 ? pa : -1; }
+        }
+        double J[6][NB];
 #pragma unroll
-    for (int i = 0; i < NB; i++) tv_all[i] = 0.0;
-    if (live && j == 0) {
-        double v[6];
-        Motors<NB> mot;
-        env_prologue<T, TASK>(arm, ph, task, b, e, actions, q, v, mot);
+        for (int c = 0; c < 6; c++) {
+            const double v = on_path && j < NB ? col[c] : 0.0;
 #pragma unroll
-        for (int i = 0; i < NB; i++) tv_all[i] = mot.target_vel[i];
-    }
-    double tvel = 0.0;
+            for (int i = 0; i < NB; i++) J[c][i] = g8_get(v, i);
+        }
+        double tv_all[NB];
 #pragma unroll
-    for (int i = 0; i < NB; i++) {
-        const double t = g8_get(tv_all[i], 0);
-        tvel = j == i ? t : tvel;
+        for (int i = 0; i < NB; i++) tv_all[i] = 0.0;
+        if (live && j == 0) {
+            double v[6];
+            Motors<NB> mot;
+            env_prologue_core<T, TASK>(arm, ph, task, b, e, actions, tp, tq, J, v, mot);
+#pragma unroll
+            for (int i = 0; i < NB; i++) tv_all[i] = mot.target_vel[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const double t = g8_get(tv_all[i], 0);
+            tvel = j == i ? t : tvel;
+        }
     }
 #pragma unroll 1
     for (int s = 0; s < ph.substeps; s++) g8_substep<T>(ph, bc, s_sub, max_sub, j, live, st, 0, 0.0, ph.vel_gain, ph.max_force, 0.0, tvel);
 
+    // ---- tail of the step: FK of the final pose on the lanes (exact sin / cos, as the one-thread kernels take them), TCP pose
+    // and camera frame handed to the first lane, which writes the step data
+    {
+        double R[9], p[3], tp[3], tq[4], cam[12], sn, cs;
+        sincos(st.q, &sn, &cs);
+        g8_fk(bc, j, sn, cs, R, p);
+        g8_tcp_and_camera(arm, R, p, tp, tq, cam);
 #pragma unroll
-    for (int i = 0; i < NB; i++) { q[i] = g8_get(st.q, i); qd[i] = g8_get(st.qd, i); }
-    if (live && j == 0) {
-        ObjState ob;
-        env_epilogue<T, TASK>(arm, ph, task, b, e, q, qd, ob, reward, done, autoreset);
+        for (int i = 0; i < NB; i++) { q[i] = g8_get(st.q, i); qd[i] = g8_get(st.qd, i); }
+        if (live && j == 0) {
+            ObjState ob;
+            env_epilogue_core<T, TASK>(arm, ph, task, b, e, q, qd, tp, tq, cam, ob, reward, done, autoreset);
+        }
     }
 }
 
@@ -446,9 +531,7 @@ test_substep_g8_kernel(const __grid_constant__ TgArm arm, const __grid_constant_
     const bool live = e < n, mine = live && j < NB;
     G8Body bc;
     g8_load_body<T>(arm, j, bc);
-    int max_sub = 0;
-#pragma unroll
-    for (int i = 0; i < NB; i++) max_sub = max(max_sub, arm.sub_start[i + 1] - arm.sub_start[i]);
+    const int max_sub = g8_max_sub(bc);
     G8Lane st;
     st.q = mine ? q_io[e * NB + j] : 0.0;
     st.qd = mine ? qd_io[e * NB + j] : 0.0;

@@ -137,11 +137,12 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     int lanes = cfg->lanes_per_warp;
     {
         // the 8-lanes-per-env kernel: motor-row tasks under TCP_velocity_control with gravity compensation.  One warp carries 4
-        // envs (against up to 32 of the one-thread kernel), so it wins while the device is not yet full of warps
+        // envs (against up to 32 of the one-thread kernel), so it wins while the device is not yet full of warps: measured on
+        // B200 (edge_follow, L2 flushed) 0.180 against 0.267 ms at N = 4096, 0.294 against 0.276 ms at N = 8192
         const bool can = (cfg->task.task == TG_TASK_EDGE_FOLLOW || cfg->task.task == TG_TASK_SURFACE_FOLLOW) && cfg->task.control_mode == 0 &&
                          cfg->phys.gravity_comp == 1;
         if (lanes == -8 && !can) return fail(TG_EUNSUPPORTED, "lanes_per_warp = -8 (8 lanes per env) is built for edge_follow / surface_follow under TCP_velocity_control");
-        w->use_g8 = can && (lanes == -8 || (lanes == 0 && n <= 16384));
+        w->use_g8 = can && (lanes == -8 || (lanes == 0 && n <= 6144));
         if (const char* ev = getenv("TG_G8")) w->use_g8 = can && atoi(ev) != 0;     // tuning hook
         w->g8_blocks = (n + 15) / 16;
     }
