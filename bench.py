@@ -384,6 +384,26 @@ class Bench:
         t_e2e = e0.elapsed_time(e1)
         self.barrier()
 
+        # the floor under e2e: this step's observation bytes over the box's pinned D2H path, all ranks copying at once (PCIe /
+        # host memory, no kernels) - what the VecEnv API costs even with infinitely fast kernels
+        t_floor = None
+        if not env._oracle:
+            pin = torch.empty(wd.obs.numel(), dtype=torch.uint8).pin_memory()
+            src = wd.obs.view(-1)
+            for _ in range(2):
+                pin.copy_(src, non_blocking=True)
+            self.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(10):
+                pin.copy_(src, non_blocking=True)
+            f1.record()
+            torch.cuda.synchronize(self.dev)
+            t_floor = f0.elapsed_time(f1) / 10
+            (t_floor,), _, _ = self.over_ranks([t_floor])
+            del pin
+            self.barrier()
+
         t_raster, t_phys = self.kernels_alone(env, acts, 20)
         clocks = sampler.stop() if sampler else None     # sampled across all timed regions of the headline workload
         mx, mn, md = self.over_ranks([t_ms, t_e2e, t_raster, t_phys])
@@ -428,6 +448,11 @@ class Bench:
                 "e2e": {"value": n * self.world * Ke / (t_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "steps": Ke,
                         "per_rank_ms_per_step": {"min": mn[1] / Ke, "median": md[1] / Ke, "max": mx[1] / Ke},
+                        "floor": None if t_floor is None else {
+                            "value": n * self.world / (t_floor * 1e-3), "unit": "env-steps/s", "ms_per_step": t_floor,
+                            "d2h_GBps_aggregate": n * self.world * w["img"] * w["img"] / (t_floor * 1e-3) / 1e9,
+                            "what": "the step's observation bytes copied device -> pinned host by all %d ranks at once, nothing else: "
+                                    "the PCIe / host-memory ceiling of the numpy VecEnv API on this box" % self.world},
                         "path": ("TactileVecEnv.step (numpy in/out) -> tg_step_host: obs rendered + copied out in chunks, D2H overlapped"
                                  if host_path else "TactileVecEnv.step (numpy in/out) -> tg_step + torch copies")},
                 "gpu_launches": int(launches),

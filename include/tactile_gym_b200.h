@@ -151,7 +151,7 @@ typedef struct {
      * out at the goal, surface_follow_auto_env.py:59-73 / surface_follow_goal_env.py:53-67); object_push / object_roll keep
      * push_sparse_reward */
     int32_t sparse_reward;
-    int32_t surf_mode;               /* heights: 0 simplex 2-d (xyz, xyzRxRy), 1 simplex 1-d along y (yz, yzRx; :339-357), 2 flat (noise_mode "none"), 3 simplex 1-d along the rows (vertical) */
+    int32_t surf_mode;               /* heights: 0 simplex 2-d (xyz, xyzRxRy), 1 simplex 1-d along y (yz, yzRx; :339-357), 2 flat (noise_mode "none"), 3 simplex 1-d along the rows (vertical), 4 uniform noise on 2 x 2 blocks (noise_mode "random", :302-318; device RNG only) */
     int32_t surf_dir_mode;           /* goal direction: 0 (cos, sin) of the drawn angle; 1 (0, +-1) = the drawn choice([-1, 1]) (:512-514) */
     int32_t surf_drive_y_only;       /* 1: surface_follow-v2 drives along y only, x stays the policy's (surface_follow_vert_env.py:30-45) */
     /* control_mode (robots/arms/robot.py:156-186): 0 TCP_velocity_control (Jacobian inverse, velocity motors, `substeps` steps);
@@ -182,6 +182,13 @@ typedef struct {
     double roll_radius;              /* default_obj_radius 0.0025 (:166) */
     double roll_cyl_pos[3], roll_cyl_axis[3]; /* cylinder centre / unit axis in the frame of arm.tcp_body */
     double roll_cyl_half_len, roll_cyl_radius; /* 0.00325, 0.02 */
+    /* The reset draws as a PROGRAM over the env's own random stream (device RNG, tg_set_rng_state; csrc/tg_rng.cuh): draw d is
+     * produced by draw_kind[d] - 0 constant draw_default[d] (consumes nothing), 1 uniform(draw_lo, draw_hi), 2 randint(draw_hi),
+     * 3 choice([-1, 1]), 4 choice([-1, 1]) * rand() - in index order, which is the reference's call order for every task.
+     * surf_mode 4 (noise_mode "random", base_surface_env.py:290-309) additionally draws 1,024 uniform(0, 0.2 surf_range) heights
+     * between draw 0 and draw 1, as the reference does (update_surface before make_goal, :539-547). */
+    int32_t draw_kind[TG_MAXDRAW];
+    double draw_lo[TG_MAXDRAW], draw_hi[TG_MAXDRAW];
 } TgTask;
 
 typedef struct {
@@ -231,6 +238,11 @@ int tg_set_draws(TgWorld* w, const double* h_draws, int rounds);
  *   tg_draws_upload: enqueue the host->device copy of the whole ring h_ring[N][rounds][n_draws] and of h_avail[N] (both
  *                    page-locked, untouched until the copy has run).  The caller may only have changed slots whose draws were
  *                    consumed (r < counts[i]); every other slot must hold what the device already has. */
+/* The alternative to streaming draws from the host: every env carries the reference's own generator (numpy RandomState =
+ * MT19937) on the device and the resets pull from it with numpy's call semantics (TgTask.draw_kind).  h_key[n_envs][624] +
+ * h_pos[n_envs] are the generators' states (numpy's get_state() after gym's seeding; pos 624 = freshly seeded).  Starts a new
+ * sequence like tg_set_draws (synchronous; pre-computed next episodes are recomputed) and stays in force until tg_set_draws. */
+int tg_set_rng_state(TgWorld* w, const uint32_t* h_key, const int32_t* h_pos);
 int tg_draws_poll(TgWorld* w, int32_t* h_counts, void* stream);
 int tg_draws_upload(TgWorld* w, const double* h_ring, const int32_t* h_avail, void* stream);
 /* Sticky error flags (0: none).  bit 0: reset pipeline / heightfield raster overflow; bit 1: a reset found no draw left in the

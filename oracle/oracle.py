@@ -593,7 +593,7 @@ class SurfaceFollowOracle:
         """variant "auto": SurfaceFollowAutoEnv (surface_follow-v0); "goal": SurfaceFollowGoalEnv (surface_follow-v1,
         surface_follow_goal/surface_follow_goal_env.py: the policy steers x / y, the reward adds the goal distance); "vert":
         SurfaceFollowVertEnv (surface_follow-v2, surface_follow_vert/surface_follow_vert_env.py: x steered, y driven, 10 / 3 weights).
-        noise_mode "simplex" | "none" | "vertical_simplex" (the upright surface of -v2, `forward` sensors); movement modes
+        noise_mode "simplex" | "none" | "random" | "vertical_simplex" (the upright surface of -v2, `forward` sensors); movement modes
         yz / xyz / yzRx / xyzRxRy (+ xRz for "vert"); reward_mode dense | sparse; render=False skips the images."""
         self.control_mode = control_mode
         self.S, self.arm, self.sensor, self.typ = image_size, arm, sensor, "standard"
@@ -641,8 +641,17 @@ class SurfaceFollowOracle:
     def draw(self):
         """reset_task order (:539-547): update_surface's randint(1e8) (:448), then make_goal's uniform(-pi, pi) (:508)"""
         seed_int = self.np_random.randint(1e8) if self.noise_mode in ("simplex", "vertical_simplex") else 0      # :436-458
+        if self.noise_mode == "random":
+            # gen_heigtfield_noisey (:302-318): 32 x 32 uniform draws, columns outer, rows inner, each filling a 2 x 2 block -
+            # drawn by update_surface BEFORE make_goal's draw; the heights ride in the first slot instead of a seed
+            h = np.zeros((self.rows, self.cols))
+            for j in range(self.cols // 2):
+                for i in range(self.rows // 2):
+                    height = self.np_random.uniform(0, self.hrange * 0.2)
+                    h[2 * i, 2 * j] = h[2 * i + 1, 2 * j] = h[2 * i, 2 * j + 1] = h[2 * i + 1, 2 * j + 1] = height
+            seed_int = h
         ang = float(self.np_random.choice([-1, 1])) if self.one_d else self.np_random.uniform(-np.pi, np.pi)   # :512-520
-        return float(seed_int), ang
+        return (seed_int if self.noise_mode == "random" else float(seed_int)), ang
 
     def xy_to_surface_idx(self, x, y):   # :273-288
         i = int(np.digitize(y, self.y_bins)); j = int(np.digitize(x, self.x_bins))
@@ -656,6 +665,8 @@ class SurfaceFollowOracle:
         if self.vertical:                                                               # gen_heigtfield_simplex_1d_vertical :359-379
             col = np.array([opensimplex_noise2(int(seed_int), x * self.interp, 1 * self.interp) * self.hrange for x in range(self.rows)])
             self.h = np.tile(col[:, None], (1, self.cols))
+        elif self.noise_mode == "random":                                               # :438-439
+            self.h = np.array(seed_int, dtype=np.float64)
         elif self.noise_mode == "none" or self.movement_mode == "xRz":                 # :436-437; "xRz" is in neither list of :450-455
             self.h = np.zeros((self.rows, self.cols))
         elif self.one_d:                                                                # gen_heigtfield_simplex_1d :339-357

@@ -14,6 +14,8 @@ TG_TASK_EDGE_FOLLOW, TG_TASK_OBJECT_BALANCE, TG_TASK_SURFACE_FOLLOW, TG_TASK_OBJ
 TG_PUSH_NTRAJ, TG_PUSH_NFEAT = 10, 12
 TG_ORACLE_NOBS = 36
 TG_PUSH_WORK, TG_PUSH_WORK_DRIVE, TG_PUSH_TCP_TYRZ, TG_PUSH_TCP_TXTYRZ = 0, 1, 2, 3
+TG_DRAW_CONST, TG_DRAW_UNIFORM, TG_DRAW_RANDINT, TG_DRAW_CHOICE_PM1, TG_DRAW_CHOICE_RAND = 0, 1, 2, 3, 4
+MT_N = 624
 
 D3 = C.c_double * 3
 D9 = C.c_double * 9
@@ -64,6 +66,7 @@ class TgTask(C.Structure):
         ("push_lin_damping", C.c_double), ("push_ang_damping", C.c_double), ("push_init_pos", D3), ("push_inertia_per_mass", D3),
         ("push_term_dist", C.c_double), ("push_traj_spacing", C.c_double), ("push_traj_perturb", C.c_double), ("push_traj_offset", C.c_double),
         ("roll_radius", C.c_double), ("roll_cyl_pos", D3), ("roll_cyl_axis", D3), ("roll_cyl_half_len", C.c_double), ("roll_cyl_radius", C.c_double),
+        ("draw_kind", C.c_int32 * TG_MAXDRAW), ("draw_lo", C.c_double * TG_MAXDRAW), ("draw_hi", C.c_double * TG_MAXDRAW),
     ]
 
 
@@ -94,7 +97,7 @@ class TgHostStep(C.Structure):
 
 
 EXPORTS = [
-    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
+    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_set_rng_state", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
     "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
     "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_test_substep_g8", "tg_launch_count",
 ]
@@ -120,6 +123,7 @@ def load():
     lib.tg_create.argtypes = [C.POINTER(TgConfig), C.c_int, C.POINTER(vp)]
     lib.tg_destroy.argtypes = [vp]
     lib.tg_set_draws.argtypes = [vp, vp, C.c_int]
+    lib.tg_set_rng_state.argtypes = [vp, vp, vp]
     lib.tg_draws_poll.argtypes = [vp, vp, vp]
     lib.tg_draws_upload.argtypes = [vp, vp, vp, vp]
     lib.tg_pipeline_error.argtypes = [vp, vp]

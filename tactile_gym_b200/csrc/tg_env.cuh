@@ -19,6 +19,7 @@
 // re-synchronised every RESET_CHUNK iterations on every path), so results do not depend on who ran which chunk.
 #pragma once
 #include "tg_dyn.cuh"
+#include "tg_rng.cuh"
 #include "tg_surface.cuh"
 #include "tg_push.cuh"
 
@@ -40,6 +41,9 @@ struct EnvBuffers {
     const double* draws;  // [N][rounds][n_draws] or null: a ring, the k-th reset of env e reads slot k % rounds
     int draw_rounds;
     const int* draw_avail; // [N] draws uploaded so far per env (reset_count[e] < draw_avail[e] or the draw is missing)
+    uint32_t* mt;         // [N][624] device RNG: every env's MT19937 state (tg_set_rng_state), or null
+    int* mt_pos;          // [N]
+    int mt_active;        // 1: resets draw from the device RNG (TgTask.draw_kind), 0: from the host's ring
     int epoch;            // launch counter: tags the slots consumed in THIS launch (SB_CONSUMED + epoch)
     double* cam;          // [N][12] eye fwd up right
     double* stim;         // [N][12] R(9) t(3) of the stimulus frame
@@ -309,7 +313,16 @@ __device__ __noinline__ void reset_begin(const TgArm& arm, const TgTask& task, c
     for (int d = 0; d < TG_MAXDRAW; d++) r.draw[d] = task.draw_default[d];
     {
         const int cnt = b.reset_count[e];
-        if (b.draws) {
+        if (b.mt_active) {
+            // the env's own generator, numpy call semantics, the reference's call order (tg_rng.cuh)
+            MtState ms{b.mt + (size_t)e * MT_N, b.mt_pos[e]};
+#pragma unroll 1
+            for (int d = 0; d < task.n_draws; d++) {
+                if (task.surf_mode == 4 && task.task == TG_TASK_SURFACE_FOLLOW && d == 1) break; // drawn after the heights (reset_advance)
+                r.draw[d] = mt_draw(ms, task.draw_kind[d], task.draw_lo[d], task.draw_hi[d], task.draw_default[d]);
+            }
+            b.mt_pos[e] = ms.pos;
+        } else if (b.draws) {
             if (cnt < b.draw_avail[e]) {
                 const int slot = cnt % b.draw_rounds;
 #pragma unroll
@@ -356,13 +369,34 @@ __device__ __noinline__ bool reset_advance(const TgArm& arm, const TgPhysics& ph
             // gen_heigtfield_simplex_2d (base_surface_env.py:311-327): h[x][y] = noise2(x * 0.05, y * 0.05) * 0.025
             const unsigned char* perm = b.sb_perm + (size_t)e * 256;
             const int end = min(r.surf_it + b.surf_chunk, SURF_PTS);
+            if (task.surf_mode == 4 && b.mt_active) {
+                // gen_heigtfield_noisey (base_surface_env.py:302-318): one uniform(0, 0.2 range) per 2 x 2 block, columns outer,
+                // rows inner; then make_goal's draw (:508 / :513), which the reference makes after the surface
+                MtState ms{b.mt + (size_t)e * MT_N, b.mt_pos[e]};
+                const int half = SURF_N / 2;
+#pragma unroll 1
+                for (int t = r.surf_it / 4; t < end / 4; t++) {
+                    const int jj = t / half, ii = t % half;
+                    const double h = mt_uniform(ms, 0.0, task.surf_range * 0.2);
+                    H[(2 * ii) * SURF_N + 2 * jj] = h; H[(2 * ii + 1) * SURF_N + 2 * jj] = h;
+                    H[(2 * ii) * SURF_N + 2 * jj + 1] = h; H[(2 * ii + 1) * SURF_N + 2 * jj + 1] = h;
+                    r.hmin = fminf(r.hmin, (float)h); r.hmax = fmaxf(r.hmax, (float)h);
+                }
+                if (end == SURF_PTS) {
+                    r.draw[1] = mt_draw(ms, task.draw_kind[1], task.draw_lo[1], task.draw_hi[1], task.draw_default[1]);
+                    r.edge_ang = r.draw[1];
+                }
+                b.mt_pos[e] = ms.pos;
+                r.surf_it = end;
+                return false;
+            }
 #pragma unroll 1
             for (int k = r.surf_it; k < end; k++) {
                 // surf_mode 1: gen_heigtfield_simplex_1d (:339-357), noise along y only; 2: noise_mode "none" (:436-437)
                 // 3: gen_heigtfield_simplex_1d_vertical (:359-379), noise along the rows only
                 const double nx = task.surf_mode == 1 ? 1.0 * task.surf_interp : (double)(k / SURF_N) * task.surf_interp;
                 const double ny = task.surf_mode == 3 ? 1.0 * task.surf_interp : (double)(k % SURF_N) * task.surf_interp;
-                const double h = task.surf_mode == 2 ? 0.0 : os_noise2(perm, nx, ny) * task.surf_range;
+                const double h = (task.surf_mode == 2 || task.surf_mode == 4) ? 0.0 : os_noise2(perm, nx, ny) * task.surf_range;
                 H[k] = h;
                 r.hmin = fminf(r.hmin, (float)h); r.hmax = fmaxf(r.hmax, (float)h);
             }

@@ -51,6 +51,8 @@ struct TgWorld {
     std::vector<void*> allocs;
     double* d_draws = nullptr;
     int* d_draw_avail = nullptr;
+    uint32_t* d_mt = nullptr;         // device RNG states [N][624] (allocated by the first tg_set_rng_state)
+    int* d_mt_pos = nullptr;
     int draw_capacity = 0;            // doubles allocated behind d_draws
     int epoch = 0;                    // bumped by every launch that may touch the standby slots
     unsigned char* d_done_internal = nullptr;
@@ -323,6 +325,8 @@ extern "C" int tg_destroy(TgWorld* w)
 extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds)
 {
     if (!w || !h_draws || rounds <= 0) return fail(TG_EINVAL, "bad arguments");
+    if (w->cfg.task.task == TG_TASK_SURFACE_FOLLOW && w->cfg.task.surf_mode == 4)
+        return fail(TG_EUNSUPPORTED, "noise_mode 'random' draws 1,024 heights per reset: it runs on the device RNG (tg_set_rng_state) only");
     CK(cudaSetDevice(w->device));
     CK(cudaDeviceSynchronize());
     const size_t cnt = (size_t)w->n * rounds * w->cfg.task.n_draws;
@@ -336,6 +340,7 @@ extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds)
     std::vector<int> avail(w->n, rounds);
     CK(cudaMemcpy(w->d_draw_avail, avail.data(), sizeof(int) * w->n, cudaMemcpyHostToDevice));
     w->eb.draws = w->d_draws; w->eb.draw_rounds = rounds;
+    w->eb.mt_active = 0;
     {
         int flag = 0;   // a new sequence: forget that the old one ran dry
         CK(cudaMemcpy(&flag, w->eb.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
@@ -344,6 +349,38 @@ extern "C" int tg_set_draws(TgWorld* w, const double* h_draws, int rounds)
     }
     if (w->eb.pipeline) {
         // a new draw sequence starts: standbys computed from the old one are recomputed now
+        CK(cudaMemset(w->eb.sb_ready, 0, sizeof(int) * w->n));
+        w->eb.epoch = ++w->epoch;
+        TOPO_DISPATCH(w, (standby_kernel<Topo><<<(w->n + 127) / 128, 128>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb)));
+        w->launches++;
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    return TG_OK;
+}
+
+extern "C" int tg_set_rng_state(TgWorld* w, const uint32_t* h_key, const int32_t* h_pos)
+{
+    if (!w || !h_key || !h_pos) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    CK(cudaDeviceSynchronize());
+    for (int d = 0; d < w->cfg.task.n_draws; d++)
+        if (w->cfg.task.draw_kind[d] < TG_DRAW_CONST || w->cfg.task.draw_kind[d] > TG_DRAW_CHOICE_RAND) return fail(TG_EINVAL, "draw_kind[%d] = %d", d, w->cfg.task.draw_kind[d]);
+    if (!w->d_mt) {
+        int rc;
+        if ((rc = dalloc(w, &w->d_mt, (size_t)w->n * MT_N)) || (rc = dalloc(w, &w->d_mt_pos, w->n))) return rc;
+    }
+    CK(cudaMemcpy(w->d_mt, h_key, sizeof(uint32_t) * MT_N * w->n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->d_mt_pos, h_pos, sizeof(int) * w->n, cudaMemcpyHostToDevice));
+    CK(cudaMemset(w->eb.reset_count, 0, sizeof(int) * w->n));
+    w->eb.mt = w->d_mt; w->eb.mt_pos = w->d_mt_pos; w->eb.mt_active = 1;
+    {
+        int flag = 0;
+        CK(cudaMemcpy(&flag, w->eb.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        flag &= ~2;
+        CK(cudaMemcpy(w->eb.error_flag, &flag, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (w->eb.pipeline) {
         CK(cudaMemset(w->eb.sb_ready, 0, sizeof(int) * w->n));
         w->eb.epoch = ++w->epoch;
         TOPO_DISPATCH(w, (standby_kernel<Topo><<<(w->n + 127) / 128, 128>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb)));

@@ -25,6 +25,21 @@ def _sparse_flag(env_modes):
     return 1 if mode == "sparse" else 0
 
 
+def _program(task, entries):
+    """The reset draws as a program over numpy's MT19937 stream for the device RNG (TgTask.draw_kind, csrc/tg_rng.cuh): one
+    (kind, lo, hi) per draw, in the reference's call order.  Constants take TgTask.draw_default[d]."""
+    assert len(entries) == task.n_draws, (len(entries), task.n_draws)
+    for d, (kind, lo, hi) in enumerate(entries):
+        task.draw_kind[d], task.draw_lo[d], task.draw_hi[d] = kind, lo, hi
+
+
+_CONST = (L.TG_DRAW_CONST, 0.0, 0.0)
+
+
+def _uni(lo, hi):
+    return (L.TG_DRAW_UNIFORM, lo, hi)
+
+
 def _control_mode(env_modes, arm_type):
     """control_mode -> (TgTask.control_mode, pos_max_steps).  robot.py:156-186; _max_blocking_pos_move_steps = 10 in every env."""
     mode = env_modes["control_mode"]
@@ -100,6 +115,7 @@ def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
         t.embed_lo = t.embed_hi = embed_default
     t.n_draws = 2
     t.draw_default[0], t.draw_default[1] = embed_default, 0.0
+    _program(t, [_uni(t.embed_lo, t.embed_hi) if t.embed_lo != t.embed_hi else _CONST, _uni(-np.pi, np.pi)])   # :293-297, :240
 
     dep, gray, mask = scene.load_refimg(sensor, typ, S)
     tris = scene.load_stimulus(stim)
@@ -221,6 +237,9 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     lo, hi_e = {"tactip": (0.003, 0.006), "digitac": (0.001, 0.0025), "digit": (0.0015, 0.0025)}[sensor]   # :307-312
     t.n_draws = 4
     t.draw_default[0], t.draw_default[1], t.draw_default[2], t.draw_default[3] = -0.1, embed_default, 0.0, 0.0
+    _program(t, [_uni(-1.0, -0.1) if env_modes.get("rand_gravity", False) else _CONST,                  # :300-305
+                 _uni(lo, hi_e) if env_modes.get("rand_embed_dist", False) else _CONST,                  # :307-313
+                 (L.TG_DRAW_CHOICE_RAND, 0.0, 0.0), (L.TG_DRAW_CHOICE_RAND, 0.0, 0.0)])                  # :366-371
     dep, gray, mask = scene.load_refimg(sensor, typ, S)
     tris = scene.load_stimulus("pole")
     rest = scene.load_rest_pose("object_balance", arm_type, sensor, typ, control_links)
@@ -274,14 +293,12 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     Returns (cfg, keepalive, draw_fn)."""
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
     noise_mode, movement_mode = env_modes.get("noise_mode", "simplex"), env_modes["movement_mode"]
-    if noise_mode == "random":
-        raise NotImplementedError("noise_mode 'random' (1,024 uniform draws per reset, base_surface_env.py:290-309) is not built")
     vertical = noise_mode == "vertical_simplex"
     if vertical:
         # upright heightfield + `forward` sensor type (base_surface_env.py:60-63, 83-107): TgTask.surf_vertical
         if variant != "vert" or movement_mode != "xRz":
             raise ValueError("Incorrect movement mode specified")                                # update_surface :459-463 knows "xRz" only
-    elif noise_mode not in ("simplex", "none"):
+    elif noise_mode not in ("simplex", "none", "random"):
         raise ValueError("Incorrect noise mode specified")                                       # :461, :463
     if variant == "vert":
         if movement_mode != "xRz":
@@ -313,6 +330,10 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     t.surf_mode = 2 if noise_mode == "none" or movement_mode == "xRz" else (1 if one_d else 0)
     if vertical:
         t.surf_mode, t.surf_vertical = 3, 1                                                      # gen_heigtfield_simplex_1d_vertical :359-379
+    if noise_mode == "random":
+        # gen_heigtfield_noisey :302-318: 1,024 uniform draws per reset, whatever the movement mode - far too many to stream
+        # from the host, so this mode runs on the device RNG (the world switches to it by itself)
+        t.surf_mode = 4
     t.surf_dir_mode = 1 if one_d else 0
     t.act_dim = len(idx)
     for k in range(6):
@@ -350,6 +371,8 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
         t.surf_drive_y_only, t.surf_w_goal, t.surf_w_surf, t.surf_w_norm = 1, 0.0, 10.0, 3.0
     t.n_draws = 2
     t.draw_default[0], t.draw_default[1] = 0.0, 0.0
+    _program(t, [(L.TG_DRAW_RANDINT, 0.0, 1e8) if noise_mode in ("simplex", "vertical_simplex") else _CONST,   # :448, :458
+                 (L.TG_DRAW_CHOICE_PM1, 0.0, 0.0) if one_d else _uni(-np.pi, np.pi)])                            # :508, :513
     dep, gray, mask = scene.load_refimg(sensor, typ, S)
     rest = scene.load_rest_pose("surface_follow", arm_type, sensor, typ, control_links)
     s = cfg.sensor
@@ -360,7 +383,7 @@ def surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     s.h_border_mask = mask.ctypes.data_as(C.POINTER(C.c_uint8))
     s.n_prim = 0                                                                                 # the stimulus is the per-env heightfield
     cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
-    return cfg, (dep, gray, mask, rest), surface_follow_draws("simplex" if vertical else noise_mode, one_d)
+    return cfg, (dep, gray, mask, rest), surface_follow_draws("simplex" if vertical else ("none" if noise_mode == "random" else noise_mode), one_d)
 
 
 def object_push_draws(rand_init_orn, rand_obj_mass, traj_type, default_mass):
@@ -451,6 +474,9 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     t.push_sparse_reward = 1 if env_modes.get("reward_mode", "dense") == "sparse" else 0
     t.n_draws = 3
     t.draw_default[0], t.draw_default[1], t.draw_default[2] = 0.0, cube["mass"], 0.0
+    _program(t, [_uni(-np.pi / 32, np.pi / 32) if env_modes.get("rand_init_orn", False) else _CONST,    # :204-229
+                 _uni(0.4, 0.8) if env_modes.get("rand_obj_mass", False) else _CONST,
+                 (L.TG_DRAW_RANDINT, 0.0, 1e8) if traj_type == "simplex" else _uni(-np.pi / 8, np.pi / 8)])   # :289, :310
     dep, gray, mask = scene.load_refimg(sensor, typ, S)
     tris = scene.load_stimulus("cube")
     rest = scene.load_rest_pose("object_push", arm_type, sensor, typ, control_links)
@@ -560,6 +586,11 @@ def object_roll_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     t.n_draws = 6
     for k, v in enumerate([1.0, embed, 0.0, 0.0, 0.0, 0.01]):
         t.draw_default[k] = v
+    rp = bool(env_modes.get("rand_init_obj_pos", False))
+    _program(t, [_uni(1.0, 2.0) if env_modes.get("rand_obj_size", False) else _CONST,                   # :182-195
+                 _uni(0.0015, 0.003) if env_modes.get("rand_embed_dist", False) else _CONST,
+                 _uni(-0.009, 0.009) if rp else _CONST, _uni(-0.009, 0.009) if rp else _CONST,           # :209-216
+                 _uni(-np.pi, np.pi), _uni(0.0, 0.015) if rp else _uni(0.005, 0.015)])                   # :244-250
     dep, gray, mask = scene.load_refimg(sensor, typ, S)
     rest = scene.load_rest_pose("object_roll", arm_type, sensor, typ, control_links)
     s = cfg.sensor
@@ -578,7 +609,11 @@ def object_roll_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
 class TactileWorld:
     """N envs of one task on one device."""
 
-    def __init__(self, cfg, keepalive, device=0, draw_fn=None):
+    def __init__(self, cfg, keepalive, device=0, draw_fn=None, rng=None):
+        """rng: "host" - reset draws come from one numpy RandomState per env on the host, streamed through the device ring;
+        "device" - every env carries that RandomState's MT19937 state on the device and draws there (same sequence, no host in
+        the loop; csrc/tg_rng.cuh; bit-identical episodes, tests/test_gpu_rng.py).  Default: TG_RNG or "device"; surface_follow's
+        noise_mode "random" always runs on "device"; explicit set_draws() (parity tests) switches to the ring."""
         import torch
 
         if not torch.cuda.is_available():
@@ -614,6 +649,11 @@ class TactileWorld:
         self.oracle_obs = self.term_oracle_obs = None
         self._draw = draw_fn if draw_fn is not None else edge_follow_draws(cfg.task)
         self._rngs = [seeding.np_random(None)[0] for _ in range(self.n)]
+        self.rng_mode = rng or os.environ.get("TG_RNG", "device")
+        if cfg.task.task == L.TG_TASK_SURFACE_FOLLOW and cfg.task.surf_mode == 4:
+            self.rng_mode = "device"
+        if self.rng_mode not in ("host", "device"):
+            raise ValueError("rng must be 'host' or 'device', got %r" % (self.rng_mode,))
         self._pin_ring = self._pin_avail = self._pin_counts = None
         self._poll_ev = self._upload_ev = None
         self._managed, self._since_poll = True, 0
@@ -661,6 +701,16 @@ class TactileWorld:
         k % DRAW_ROUNDS, `_avail[i]` counts the draws produced so far."""
         torch = self.torch
         nd = self.cfg.task.n_draws
+        if self.rng_mode == "device":
+            # hand the generators themselves to the device: numpy's MT19937 key + position per env
+            keys = np.empty((self.n, L.MT_N), dtype=np.uint32)
+            pos = np.empty(self.n, dtype=np.int32)
+            for i, r in enumerate(self._rngs):
+                st = r.get_state()
+                keys[i], pos[i] = st[1], st[2]
+            L.check(self.lib.tg_set_rng_state(self.h, keys.ctypes.data, pos.ctypes.data))
+            self._managed = False
+            return
         if self._pin_ring is None:
             self._pin_ring = torch.zeros((self.n, DRAW_ROUNDS, nd), dtype=torch.float64).pin_memory()
             self._pin_avail = torch.zeros(self.n, dtype=torch.int32).pin_memory()

@@ -58,7 +58,7 @@ class _Info(dict):
 
 
 class TactileVecEnv(_VecEnvBase):
-    def __init__(self, env_id, n_envs, seed=None, env_kwargs=None, device=0, lanes_per_warp=0, copy_chunks=0):
+    def __init__(self, env_id, n_envs, seed=None, env_kwargs=None, device=0, lanes_per_warp=0, copy_chunks=0, rng=None):
         kw = dict(env_kwargs or {})
         if env_id not in CONFIG_BUILDERS:
             raise NotImplementedError("%s is not built yet in tactile_gym_b200" % env_id)
@@ -74,7 +74,7 @@ class TactileVecEnv(_VecEnvBase):
         max_steps = kw.get("max_steps", 250)
         built = CONFIG_BUILDERS[env_id](env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp)
         cfg, keep, draw = built if len(built) == 3 else (built[0], built[1], None)
-        self.world = TactileWorld(cfg, keep, device=device, draw_fn=draw)
+        self.world = TactileWorld(cfg, keep, device=device, draw_fn=draw, rng=rng)
         self.num_envs = n_envs
         # tg_step_host needs the standby reset pipeline (episodes of >= 2 steps); copy_chunks < 0 forces the torch copy path
         self.copy_chunks = copy_chunks

@@ -44,10 +44,12 @@ full = tg.make_vec(env_id, G, env_kwargs=kw, device=local)
 full.world.set_draws(draws)
 full.reset()
 prev = None
+any_done = False
 for k in range(9):
     h = shard.step_collated(acts[k, rank * n:(rank + 1) * n])
     o, r, d = full.world.step(acts[k])
     want = (o.clone(), r.clone(), d.clone(), full.world.feat.clone() if full.world.nfeat else None)
+    any_done = any_done or bool(d.any())
     if prev is not None:
         # consume batch k-1 while step k is in flight (the overlap the double buffer exists for)
         go, gr, gd, gf = shard.collated_wait(prev[0])
@@ -60,7 +62,7 @@ for k in range(9):
     prev = (h, want)
 go, gr, gd, gf = shard.collated_wait(prev[0])
 assert torch.equal(go.flatten(0, 1), prev[1][0]) and torch.equal(gr.flatten(), prev[1][1])
-assert bool(prev[1][2].any()) or ms > 9           # episode ends went through the gather too
+assert any_done                                   # episode ends went through the gather too
 torch.cuda.synchronize(dev)
 shard.close(); full.close()
 dist.barrier()

@@ -285,11 +285,14 @@ def test_object_balance_free_running_200_steps(oracle):
     env.close()
 
 
-def test_single_env_draws_follow_the_seed_past_the_ring(oracle):
+@pytest.mark.parametrize("rng_mode", ["host", "device"])
+def test_single_env_draws_follow_the_seed_past_the_ring(oracle, monkeypatch, rng_mode):
     """the gym.Env path used to stop refilling the reset draws after 64 episodes and fall back to the default
-    draws silently.  150 resets of one tg.make env: every episode's (embed_dist, edge_ang) is the reference's next pair."""
+    draws silently.  150 resets of one tg.make env: every episode's (embed_dist, edge_ang) is the reference's next pair - with the
+    host-fed ring (which must be refilled on the way) and with the device RNG."""
     import tactile_gym_b200 as tg
 
+    monkeypatch.setenv("TG_RNG", rng_mode)
     env = tg.make("edge_follow-v0", env_modes=EDGE, image_size=[64, 64], max_steps=50)
     env.seed(3)
     rng = oracle.gym_np_random(3)
@@ -302,7 +305,7 @@ def test_single_env_draws_follow_the_seed_past_the_ring(oracle):
         seen.append(ang)
         if ep % 3 == 0:
             env.step(np.zeros(2, dtype=np.float32))
-    assert len(set(seen)) == 150
+    assert len(set(seen)) == 150 and env.world.rng_mode == rng_mode
     assert not env.world.draws_exhausted()
     env.close()
 

@@ -18,11 +18,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _world(edge_modes, n, S=128, max_steps=200, lanes=0):
+def _world(edge_modes, n, S=128, max_steps=200, lanes=0, rng=None):
     import tactile_gym_b200 as tg
 
     return tg.make_vec("edge_follow-v0", n, env_kwargs={"env_modes": edge_modes, "image_size": [S, S], "max_steps": max_steps},
-                       lanes_per_warp=lanes)
+                       lanes_per_warp=lanes, rng=rng)
 
 
 def _draws(rng, n, rounds=4):
@@ -303,7 +303,7 @@ def test_draw_refill_keeps_the_rng_sequence(oracle, edge_modes):
     """Many short episodes: draws are consumed in episode order across host refills of the device-side ring and
     across the standby pipeline (which always holds one pre-computed episode)."""
     n, max_steps, steps = 4, 2, 150
-    env = _world(edge_modes, n, S=64, max_steps=max_steps)
+    env = _world(edge_modes, n, S=64, max_steps=max_steps, rng="host")     # the host-fed ring is what this test is about
     env.seed(7)
     env.reset()
     act = np.zeros((n, 2), dtype=np.float32)
