@@ -83,8 +83,10 @@ def test_surface_config_modes():
     assert (cfg.task.act_dim, cfg.task.surf_mode, cfg.task.surf_dir_mode, cfg.task.sparse_reward) == (2, 1, 1, 0)
     cfg, _, _ = surface_follow_goal_config(dict(m, movement_mode="yz", noise_mode="none"), [64, 64], 200, 2)
     assert (cfg.task.act_dim, list(cfg.task.act_index[:2]), cfg.task.surf_mode) == (2, [1, 2], 2)
-    with pytest.raises(NotImplementedError):
-        surface_follow_config(dict(m, movement_mode="xyz", noise_mode="random"), [64, 64], 200, 2)
+    cfg, _, _ = surface_follow_config(dict(m, movement_mode="xyz", noise_mode="random", reward_mode="dense"), [64, 64], 200, 2)
+    assert (cfg.task.surf_mode, cfg.task.draw_kind[0], cfg.task.draw_kind[1]) == (4, 0, 1)     # base_surface_env.py:302-318: device RNG only
+    with pytest.raises(ValueError):
+        surface_follow_config(dict(m, movement_mode="xyz", noise_mode="perlin"), [64, 64], 200, 2)
     with pytest.raises(ValueError):
         surface_follow_config(dict(m, movement_mode="xyz", reward_mode="shaped"), [64, 64], 200, 2)
     # draws follow the reference's RNG call order: randint(1e8) only for simplex, choice([-1, 1]) for the 1-d modes
