@@ -202,6 +202,11 @@ typedef struct {
     const double* h_prims;         /* [n_prim][4][3] stimulus primitives in the stimulus frame: convex planar polygons
                                       with 3 or 4 vertices (coplanar triangle pairs merged; unused 4th vertex ignored) */
     const int32_t* h_prim_nv;      /* [n_prim] vertex counts */
+    /* optional: the primitives grouped into CONVEX parts (closed convex polyhedra: the edge box, the cube, the pole's plate and
+     * post).  With it the scanline raster (csrc/tg_raster_scan.cuh) renders the stimulus; NULL / 0: the general kernel does. */
+    const int32_t* h_prim_part;    /* [n_prim] part index of each primitive */
+    const double* h_part_centroid; /* [n_parts][3] an interior point of each part, stimulus frame */
+    int32_t n_parts, pad1;
 } TgSensor;
 
 typedef struct {

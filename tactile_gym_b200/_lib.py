@@ -76,6 +76,7 @@ class TgSensor(C.Structure):
         ("fov_deg", C.c_double), ("near_", C.c_double), ("far_", C.c_double),
         ("h_nodef_dep", C.POINTER(C.c_float)), ("h_nodef_gray", C.POINTER(C.c_float)), ("h_border_mask", C.POINTER(C.c_uint8)),
         ("n_prim", C.c_int32), ("pad0", C.c_int32), ("h_prims", C.POINTER(C.c_double)), ("h_prim_nv", C.POINTER(C.c_int32)),
+        ("h_prim_part", C.POINTER(C.c_int32)), ("h_part_centroid", C.POINTER(C.c_double)), ("n_parts", C.c_int32), ("pad1", C.c_int32),
     ]
 
 

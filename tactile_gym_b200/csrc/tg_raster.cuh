@@ -78,6 +78,7 @@ struct RasterArgs {
     int hf_flip;           // 1: use the OTHER buffer (terminal observation of an env that has just been reset)
     int hf_tile_rows, hf_tile_cols; // tile of the heightfield kernel: rows x cols pixels, rows * cols / 16 <= 32 spans
     double surf_pos[3], surf_grid;
+    int scan_test_fallback; // test hook (TG_SCAN_TEST_FALLBACK): the scanline raster flags every odd env for the general kernel
 };
 
 struct SpanEntry {
@@ -366,9 +367,12 @@ __device__ __forceinline__ void flush_exact(const RasterArgs& a, const WarpCtx& 
     __syncwarp();
 }
 
+// `need`: optional device counter; a launch that finds it zero has nothing to render and returns at once (the scanline
+// raster's fallback pass, tg_raster_scan.cuh)
 __global__ void __launch_bounds__(RASTER_THREADS)
-raster_kernel(const RasterArgs a)
+raster_kernel(const RasterArgs a, const int* __restrict__ need)
 {
+    if (need && *need == 0) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S, band_rows = S / a.bands, band_px = band_rows * S;
     float* s_nodef = reinterpret_cast<float*>(smem_raw);

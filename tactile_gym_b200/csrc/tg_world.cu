@@ -13,6 +13,7 @@
 #include "tg_g8.cuh"
 #include "tg_raster.cuh"
 #include "tg_raster_hf.cuh"
+#include "tg_raster_scan.cuh"
 #include "tg_raster_sphere.cuh"
 
 static thread_local std::string g_err;
@@ -58,6 +59,9 @@ struct TgWorld {
     unsigned char* d_done_internal = nullptr;
     float* d_reward_internal = nullptr;
     size_t raster_smem = 0;
+    // scanline raster (convex parts): tables, the per-env fallback mask + counter, launch shape
+    int* d_prim_part = nullptr; double* d_part_cen = nullptr; uint8_t* d_fallback = nullptr; int* d_fb_count = nullptr;
+    size_t scan_smem = 0; int scan_grid = 0; bool scan_ok = false, scan_multi = false;
     size_t push_smem = 0;
     int raster_grid = 0;
     int standby_blocks = 0;
@@ -278,6 +282,33 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         if (grid > need) grid = need;
         w->raster_grid = grid;
         r.hf = nullptr; r.hf_cur = nullptr; r.hf_meta = nullptr; r.hf_flip = 0; r.hf_tile_rows = 16; r.hf_tile_cols = 32;
+        r.scan_test_fallback = getenv("TG_SCAN_TEST_FALLBACK") ? 1 : 0;
+        if (np > 0 && cfg->sensor.n_parts > 0 && cfg->sensor.h_prim_part && cfg->sensor.h_part_centroid && !getenv("TG_NO_SCAN")) {
+            // convex parts: the scanline raster renders, raster_kernel only takes the envs it flags
+            for (int i = 0; i < np; i++)
+                if (cfg->sensor.h_prim_part[i] < 0 || cfg->sensor.h_prim_part[i] >= cfg->sensor.n_parts) return fail(TG_EINVAL, "h_prim_part[%d] out of range", i);
+            if ((rc = dalloc(w, &w->d_prim_part, np)) || (rc = dalloc(w, &w->d_part_cen, (size_t)3 * cfg->sensor.n_parts)) ||
+                (rc = dalloc(w, &w->d_fallback, n)) || (rc = dalloc(w, &w->d_fb_count, 1))) return rc;
+            CK(cudaMemcpy(w->d_prim_part, cfg->sensor.h_prim_part, sizeof(int) * np, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(w->d_part_cen, cfg->sensor.h_part_centroid, sizeof(double) * 3 * cfg->sensor.n_parts, cudaMemcpyHostToDevice));
+            const size_t band_rows = (size_t)S / r.bands;
+            const size_t nsp = band_px / 16;
+            const size_t pw = (SCAN_PER_WARP_SMEM + (size_t)SCAN_MAXFRONT * band_rows * 2 + nsp * 4 + 15) & ~size_t(15);
+            w->scan_smem = ((band_px * 5 + ((px / 16 + 31) / 32) * 4 + 15) & ~size_t(15)) + pw * SCAN_WARPS;
+            w->scan_multi = cfg->sensor.n_parts > 1;
+            int ps = 0;
+            if (w->scan_multi) {
+                CK(cudaFuncSetAttribute(raster_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel<true>, SCAN_THREADS, w->scan_smem));
+            } else {
+                CK(cudaFuncSetAttribute(raster_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel<false>, SCAN_THREADS, w->scan_smem));
+            }
+            if (ps >= 1) {
+                w->scan_grid = w->sm_count * ps;      // every CTA walks all bands itself
+                w->scan_ok = true;
+            }
+        }
         if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
             // heightfield stimulus: per-tile primitive lists (tg_raster_hf.cuh).  Tile size: its footprint on the surface
             // (at the deepest skin depth) should stay within ~1.5 grid cells so that a tile sees <= 32 triangles
@@ -484,7 +515,18 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
         const int wp = r.hf ? HF_WARPS : RASTER_WARPS;
         const int grid = std::min(w->raster_grid, ((cnt + wp - 1) / wp) * r.bands);
         if (r.hf) raster_hf_kernel<<<grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
-        else raster_kernel<<<grid, RASTER_THREADS, w->raster_smem, st>>>(r);
+        else if (w->scan_ok) {
+            // convex stimulus: scanline raster, then raster_kernel for the envs it flagged (returns at once when there are none)
+            const int sgrid = std::min(w->scan_grid, (cnt + SCAN_WARPS - 1) / SCAN_WARPS);
+            CK(cudaMemsetAsync(w->d_fb_count, 0, sizeof(int), st));
+            if (w->scan_multi) raster_scan_kernel<true><<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_prim_part, w->d_part_cen, w->d_fallback + e0, w->d_fb_count);
+            else raster_scan_kernel<false><<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_prim_part, w->d_part_cen, w->d_fallback + e0, w->d_fb_count);
+            w->launches++;
+            CK(cudaGetLastError());
+            RasterArgs r2 = r;
+            r2.mask = w->d_fallback + e0;
+            raster_kernel<<<grid, RASTER_THREADS, w->raster_smem, st>>>(r2, w->d_fb_count);
+        } else raster_kernel<<<grid, RASTER_THREADS, w->raster_smem, st>>>(r, nullptr);
     }
     w->launches++;
     CK(cudaGetLastError());

@@ -130,8 +130,14 @@ def edge_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     s.n_prim = len(prims)
     s.h_prims = prims.ctypes.data_as(C.POINTER(C.c_double))
     s.h_prim_nv = prim_nv.ctypes.data_as(C.POINTER(C.c_int32))
+    parts, part_cen = scene.convex_parts(prims, prim_nv)           # boxes: the scanline raster applies
+    if parts is not None:
+        part_cen = np.ascontiguousarray(part_cen, dtype=np.float64)
+        s.h_prim_part = parts.ctypes.data_as(C.POINTER(C.c_int32))
+        s.h_part_centroid = part_cen.ctypes.data_as(C.POINTER(C.c_double))
+        s.n_parts = len(part_cen)
     cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
-    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv)
+    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv, parts, part_cen)
 
 
 def _uniform53(a, b):
@@ -253,9 +259,15 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     s.n_prim = len(prims)
     s.h_prims = prims.ctypes.data_as(C.POINTER(C.c_double))
     s.h_prim_nv = prim_nv.ctypes.data_as(C.POINTER(C.c_int32))
+    parts, part_cen = scene.convex_parts(prims, prim_nv)           # boxes: the scanline raster applies
+    if parts is not None:
+        part_cen = np.ascontiguousarray(part_cen, dtype=np.float64)
+        s.h_prim_part = parts.ctypes.data_as(C.POINTER(C.c_int32))
+        s.h_part_centroid = part_cen.ctypes.data_as(C.POINTER(C.c_double))
+        s.n_parts = len(part_cen)
     cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
     draw = object_balance_draws(bool(env_modes.get("rand_gravity", False)), bool(env_modes.get("rand_embed_dist", False)), lo, hi_e, embed_default)
-    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv), draw
+    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv, parts, part_cen), draw
 
 
 def surface_follow_draws(noise_mode="simplex", one_d=False):
@@ -494,11 +506,17 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     s.n_prim = len(prims)
     s.h_prims = prims.ctypes.data_as(C.POINTER(C.c_double))
     s.h_prim_nv = prim_nv.ctypes.data_as(C.POINTER(C.c_int32))
+    parts, part_cen = scene.convex_parts(prims, prim_nv)           # boxes: the scanline raster applies
+    if parts is not None:
+        part_cen = np.ascontiguousarray(part_cen, dtype=np.float64)
+        s.h_prim_part = parts.ctypes.data_as(C.POINTER(C.c_int32))
+        s.h_part_centroid = part_cen.ctypes.data_as(C.POINTER(C.c_double))
+        s.n_parts = len(part_cen)
     cfg.h_rest_q = rest.ctypes.data_as(C.POINTER(C.c_double))
     cfg.h_tip_hull = hull.ctypes.data_as(C.POINTER(C.c_double))
     cfg.n_tip_hull = len(hull)
     draw = object_push_draws(bool(env_modes.get("rand_init_orn", False)), bool(env_modes.get("rand_obj_mass", False)), traj_type, cube["mass"])
-    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv, hull), draw
+    return cfg, (dep, gray, mask, tris, rest, prims, prim_nv, hull, parts, part_cen), draw
 
 
 def object_roll_draws(rand_obj_size, rand_embed_dist, rand_init_obj_pos):

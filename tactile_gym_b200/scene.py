@@ -310,3 +310,57 @@ def default_physics(substeps=24, gravity=(0.0, 0.0, -9.81)):
     p.blocking_force = 100000.0
     p.gravity_comp = 1
     return p
+
+
+def convex_parts(prims, prim_nv, tol=1e-9):
+    """Group the stimulus primitives into CONVEX parts for the scanline raster (csrc/tg_raster_scan.cuh).
+
+    Primitives that share vertices form one component (the edge stimulus and the cube are one box each, the pole a base plate
+    and a post); a component is a convex part when it is closed and every vertex of it lies on or inside every face plane.
+    Returns (part id per primitive [P] int32, part centroids [n_parts, 3]) - or (None, None) when some component is not
+    convex (the general raster kernel renders such scenes; none of the reference's stimuli for the tasks built here is)."""
+    prims = np.asarray(prims, dtype=np.float64)
+    P = len(prims)
+    parent = list(range(P))
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+
+    verts = [prims[t][: int(prim_nv[t])] for t in range(P)]
+    for a in range(P):
+        for b in range(a + 1, P):
+            if any(np.allclose(va, vb, atol=tol, rtol=0) for va in verts[a] for vb in verts[b]):
+                parent[find(a)] = find(b)
+    roots = sorted({find(t) for t in range(P)})
+    part = np.array([roots.index(find(t)) for t in range(P)], dtype=np.int32)
+    cens = np.zeros((len(roots), 3))
+    for k in range(len(roots)):
+        pts = np.concatenate([verts[t] for t in range(P) if part[t] == k])
+        uniq = np.unique(np.round(pts / tol).astype(np.int64), axis=0) * tol
+        cens[k] = uniq.mean(axis=0)
+        scale = max(np.abs(pts - cens[k]).max(), 1e-12)
+        # every edge of the component must be shared by exactly two faces (closed surface)
+        edges = {}
+        for t in range(P):
+            if part[t] != k:
+                continue
+            v = verts[t]
+            for m in range(len(v)):
+                key = tuple(sorted((tuple(np.round(v[m] / tol).astype(np.int64)), tuple(np.round(v[(m + 1) % len(v)] / tol).astype(np.int64)))))
+                edges[key] = edges.get(key, 0) + 1
+        if any(c != 2 for c in edges.values()):
+            return None, None
+        for t in range(P):
+            if part[t] != k:
+                continue
+            v = verts[t]
+            n = np.cross(v[1] - v[0], v[2] - v[0])
+            n /= np.linalg.norm(n)
+            if np.dot(n, cens[k] - v[0]) > 0:
+                n = -n                                   # outward
+            if ((pts - v[0]) @ n).max() > 1e-7 * scale:
+                return None, None                        # a vertex outside this face's plane: not convex
+    return part, cens
