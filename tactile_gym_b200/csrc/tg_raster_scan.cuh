@@ -20,9 +20,9 @@
 #pragma once
 #include "tg_raster.cuh"
 
-#define SCAN_THREADS 512
+#define SCAN_THREADS 1024  // 32 warps per SM: the render kernel is kept under 64 registers (the fp64 face set-up lives in its own kernel)
 #define SCAN_WARPS (SCAN_THREADS / 32)
-#define SCAN_MAXFRONT 8 // front faces per env kept in the interval table (a box shows <= 3, the pole <= 6; hit masks are 16 bits)
+#define SCAN_MAXFRONT 8 // front faces per env kept in the interval table (a box shows <= 3, the pole <= 6)
 
 struct ScanFace {
     double wA, wB, wC;          // 1/z_eye = wA c + wB r + wC on this face's plane (PrimCoef index 4)
@@ -32,7 +32,14 @@ struct ScanFace {
     int part;
 };
 
-#define SCAN_PER_WARP_SMEM (sizeof(ScanFace) * SCAN_MAXFRONT + 16)
+// what scan_setup_kernel leaves per env for the render kernel
+struct ScanEnv {
+    int nf, c_lo, c_hi, r_lo, r_hi, pad[3]; // front faces; columns / rows any of them can touch (nf < 0: rendered by raster_kernel)
+    ScanFace face[SCAN_MAXFRONT];
+};
+
+// per warp of the render kernel: 1/z coefficients of the front faces, their row intervals, the span list
+#define SCAN_PER_WARP_SMEM (sizeof(double) * 3 * SCAN_MAXFRONT)
 
 // one front face, one row: the inclusive column interval [lo, hi] it covers (lo > hi: none)
 __device__ __forceinline__ void scan_interval(const ScanFace& f, int r, int S, int& lo, int& hi)
@@ -51,30 +58,122 @@ __device__ __forceinline__ void scan_interval(const ScanFace& f, int r, int S, i
     }
 }
 
+// Pre-pass, one warp per env, lane = primitive: eye-space vertices, plane, edge lines, front-facing test (fp64, a few hundred
+// instructions per env - kept out of the render kernel so that one stays small in registers and code).
+__global__ void __launch_bounds__(128)
+scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const double* __restrict__ part_cen, ScanEnv* __restrict__ out,
+                  uint8_t* __restrict__ fallback, int* __restrict__ fb_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= a.n) return;
+    const int S = a.S;
+    if (a.mask && !a.mask[e]) { if (lane == 0) { fallback[e] = 0; out[e].nf = -1; } return; }
+    bool bad = false, front = false;
+    ScanFace mine;
+    int c_lo = S, c_hi = -1, r_lo = S, r_hi = -1;
+        if (lane < a.nprim) {
+            const double* cam = a.cam + (size_t)e * 12;
+            const double* stim = a.stim + (size_t)e * 12;
+            const int nv = a.prim_nv[lane];
+            double ve[4][3], vp[4][3];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double* v = a.prims + 12 * lane + 3 * (k < nv ? k : nv - 1);
+                double w[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) w[c] = stim[3 * c] * v[0] + stim[3 * c + 1] * v[1] + stim[3 * c + 2] * v[2] + stim[9 + c] - cam[c];
+                ve[k][0] = w[0] * cam[9] + w[1] * cam[10] + w[2] * cam[11];
+                ve[k][1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
+                ve[k][2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
+            }
+            PrimCoef pc;
+            const bool infront = prim_from_eye(a, ve, nv, pc, vp);
+            bad = !pc.valid || !infront || pc.clipped;
+            if (!bad) {
+                // camera outside this face's half-space <=> the face is a front face.  Plane n . x = h through the face, the
+                // part's centroid on the inner side: outside <=> (n . 0 - h) = -h and sc = (n . cen - h) have opposite signs,
+                // i.e. h and sc have the same sign
+                const int part = prim_part[lane];
+                const double* pcn = part_cen + 3 * part;
+                double cw[3], ce[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) cw[c] = stim[3 * c] * pcn[0] + stim[3 * c + 1] * pcn[1] + stim[3 * c + 2] * pcn[2] + stim[9 + c];
+                world_to_eye(cam, cw, ce);
+                const double e1[3] = {ve[1][0] - ve[0][0], ve[1][1] - ve[0][1], ve[1][2] - ve[0][2]};
+                const double e2[3] = {ve[2][0] - ve[0][0], ve[2][1] - ve[0][1], ve[2][2] - ve[0][2]};
+                const double nrm[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+                const double h = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
+                const double sc = nrm[0] * ce[0] + nrm[1] * ce[1] + nrm[2] * ce[2] - h;
+                front = (h > 0.0) == (sc > 0.0) && sc != 0.0;
+                mine.wA = pc.eA[4]; mine.wB = pc.eB[4]; mine.wC = pc.eC[4];
+                mine.part = part;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    mine.dir[i] = 2; mine.es[i] = 0; mine.et[i] = 0; mine.eB[i] = 0; mine.eC[i] = 0;
+                    if (i < nv) {
+                        const double A = pc.eA[i], B = pc.eB[i], C = pc.eC[i];
+                        if (fabs(A) * (double)S < 1e-9 * (fabs(B) * (double)S + fabs(C) + 1e-300)) {
+                            mine.dir[i] = 0; mine.eB[i] = B; mine.eC[i] = C;         // edge line parallel to the rows
+                        } else {
+                            // A c + B r + C >= -1e-12  <=>  c >= (-1e-12 - C - B r) / A  (A > 0), <= for A < 0
+                            const double inv = 1.0 / A;
+                            mine.dir[i] = A > 0.0 ? 1 : -1;
+                            mine.es[i] = -B * inv; mine.et[i] = (-1e-12 - C) * inv;
+                        }
+                    }
+                }
+                if (front) {
+                    c_lo = max(0, (int)floor(fmin(fmax((double)pc.c_lo, -1.0), (double)S)));
+                    c_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.c_hi, -1.0), (double)S)));
+                    r_lo = max(0, (int)floor(fmin(fmax((double)pc.r_lo, -1.0), (double)S)));
+                    r_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.r_hi, -1.0), (double)S)));
+                }
+            }
+        }
+    if (a.scan_test_fallback && (e & 1)) bad = true;
+    const uint32_t bad_m = __ballot_sync(0xffffffffu, bad);
+    const uint32_t front_m = __ballot_sync(0xffffffffu, front);
+    const int nf = __popc(front_m);
+    if (bad_m != 0u || nf > SCAN_MAXFRONT) {
+        // raster_kernel renders this env (masked second launch)
+        if (lane == 0) { fallback[e] = 1; atomicAdd(fb_count, 1); out[e].nf = -1; }
+        return;
+    }
+    if (front) out[e].face[__popc(front_m & ((1u << lane) - 1u))] = mine;
+    // the rows / columns any front face can touch (union of the conservative screen boxes)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, d)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, d));
+        r_lo = min(r_lo, __shfl_xor_sync(0xffffffffu, r_lo, d)); r_hi = max(r_hi, __shfl_xor_sync(0xffffffffu, r_hi, d));
+    }
+    if (lane == 0) { fallback[e] = 0; out[e].nf = nf; out[e].c_lo = c_lo; out[e].c_hi = c_hi; out[e].r_lo = r_lo; out[e].r_hi = r_hi; }
+}
+
+// Work unit of a warp: (env, row part) - `parts` consecutive slices of every band's rows, chosen by the host so that the units
+// fill the device's warps (1 at 4096 envs and up, 2 at 2048, 4 at 1024).  Unit u = env * parts + part goes to CTA u mod gridDim.
 template <bool MULTI>
-__global__ void __launch_bounds__(SCAN_THREADS)
-raster_scan_kernel(const RasterArgs a, const int* __restrict__ prim_part, const double* __restrict__ part_cen, uint8_t* __restrict__ fallback,
-                   int* __restrict__ fb_count)
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int parts)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S, bands = a.bands, band_rows = S / bands, band_px = band_rows * S;
     float* s_nodef = reinterpret_cast<float*>(smem_raw);
     uint8_t* s_base = smem_raw + (size_t)band_px * 4;
-    const int n_spans = band_px / 16, all_spans = S * S / 16;
+    const int part_rows = band_rows / parts;
+    const int n_spans = part_rows * S / 16, all_spans = S * S / 16;   // spans of one unit's slice of a band; of the whole image
     uint32_t* s_skin = reinterpret_cast<uint32_t*>(smem_raw + (size_t)band_px * 5);   // 1 bit per span of the WHOLE image: has a non-border pixel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t wbase = ((size_t)band_px * 5 + (size_t)((all_spans + 31) / 32) * 4 + 15) & ~size_t(15);
-    // per warp: the front faces, their row intervals [SCAN_MAXFRONT][band_rows] as (lo, hi) byte pairs, the span list
-    const size_t per_warp = (SCAN_PER_WARP_SMEM + (size_t)SCAN_MAXFRONT * band_rows * 2 + (size_t)n_spans * 4 + 15) & ~size_t(15);
-    ScanFace* faces = reinterpret_cast<ScanFace*>(smem_raw + wbase + per_warp * warp);
-    uchar2* s_iv = reinterpret_cast<uchar2*>(faces + SCAN_MAXFRONT);
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_iv + (size_t)SCAN_MAXFRONT * band_rows);   // [n_spans] span | hit mask << 16
+    const size_t per_warp = (SCAN_PER_WARP_SMEM + (size_t)SCAN_MAXFRONT * part_rows * 2 + (size_t)n_spans * 2 + 15) & ~size_t(15);
+    double* s_w = reinterpret_cast<double*>(smem_raw + wbase + per_warp * warp);               // [SCAN_MAXFRONT][3] wA wB wC
+    uchar2* s_iv = reinterpret_cast<uchar2*>(s_w + 3 * SCAN_MAXFRONT);                         // [SCAN_MAXFRONT][part_rows] (lo, hi)
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_iv + (size_t)SCAN_MAXFRONT * part_rows);  // [n_spans] spans some face touches
     __shared__ __align__(8) uint64_t bar;
     uint32_t bar_phase = 0;
 
     // TMA bulk copy of one band of the static tables (nodef_dep f32 + baked border bytes) into shared memory.  128 x 128 and
-    // smaller: one band = the whole image, fetched once per CTA.  256 x 256: the CTA walks the four bands in turn, every warp
-    // keeping its env's face set-up across them.
+    // smaller: one band = the whole image, fetched once per CTA.  256 x 256: the CTA walks the four bands in turn.
     auto load_band = [&](int band) {
         if (threadIdx.x == 0) {
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -112,96 +211,20 @@ raster_scan_kernel(const RasterArgs a, const int* __restrict__ prim_part, const 
     if (bands == 1) load_band(0);
     const int sh_S = 31 - __clz(S);
     const double Fn = a.F * a.near_;
-    const int per_round = gridDim.x * SCAN_WARPS, rounds = (a.n + per_round - 1) / per_round;
+    const int units = a.n * parts, per_cta = (units + gridDim.x - 1) / gridDim.x, rounds = (per_cta + SCAN_WARPS - 1) / SCAN_WARPS;
 
     for (int rd = 0; rd < rounds; rd++) {
-        const int e = rd * per_round + blockIdx.x * SCAN_WARPS + warp;
-        bool render = e < a.n;
-        if (render && a.mask && !a.mask[e]) { if (lane == 0) fallback[e] = 0; render = false; }
+        const int slot = rd * SCAN_WARPS + warp;                 // this warp's unit among the CTA's
+        const int u = slot < per_cta ? slot * gridDim.x + blockIdx.x : units;
+        const int e = u < units ? u / parts : a.n, part = u < units ? u % parts : 0;
+        int nf = -1, c_lo = 0, c_hi = 0, r_lo = 0, r_hi = 0;
+        if (e < a.n) {
+            const ScanEnv& se = envs[e];
+            nf = se.nf; c_lo = se.c_lo; c_hi = se.c_hi; r_lo = se.r_lo; r_hi = se.r_hi;
+        }
+        const bool render = nf >= 0;       // masked-out envs and the ones handed to raster_kernel carry nf = -1
         __syncwarp();
-        bool bad = false, front = false;
-        ScanFace mine;
-        int c_lo = S, c_hi = -1, r_lo = S, r_hi = -1;
-        if (render) {
-            // ---- per-face set-up, lane = primitive: eye-space vertices, plane, edge lines; front-facing test against the part centroid
-            if (lane < a.nprim) {
-                const double* cam = a.cam + (size_t)e * 12;
-                const double* stim = a.stim + (size_t)e * 12;
-                const int nv = a.prim_nv[lane];
-                double ve[4][3], vp[4][3];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const double* v = a.prims + 12 * lane + 3 * (k < nv ? k : nv - 1);
-                    double w[3];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) w[c] = stim[3 * c] * v[0] + stim[3 * c + 1] * v[1] + stim[3 * c + 2] * v[2] + stim[9 + c] - cam[c];
-                    ve[k][0] = w[0] * cam[9] + w[1] * cam[10] + w[2] * cam[11];
-                    ve[k][1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
-                    ve[k][2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
-                }
-                PrimCoef pc;
-                const bool infront = prim_from_eye(a, ve, nv, pc, vp);
-                bad = !pc.valid || !infront || pc.clipped;
-                if (!bad) {
-                    // camera outside this face's half-space <=> the face is a front face.  Plane n . x = h through the face, the
-                    // part's centroid on the inner side: outside <=> (n . 0 - h) = -h and sc = (n . cen - h) have opposite signs,
-                    // i.e. h and sc have the same sign
-                    const int part = prim_part[lane];
-                    const double* pcn = part_cen + 3 * part;
-                    double cw[3], ce[3];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) cw[c] = stim[3 * c] * pcn[0] + stim[3 * c + 1] * pcn[1] + stim[3 * c + 2] * pcn[2] + stim[9 + c];
-                    world_to_eye(cam, cw, ce);
-                    const double e1[3] = {ve[1][0] - ve[0][0], ve[1][1] - ve[0][1], ve[1][2] - ve[0][2]};
-                    const double e2[3] = {ve[2][0] - ve[0][0], ve[2][1] - ve[0][1], ve[2][2] - ve[0][2]};
-                    const double nrm[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-                    const double h = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
-                    const double sc = nrm[0] * ce[0] + nrm[1] * ce[1] + nrm[2] * ce[2] - h;
-                    front = (h > 0.0) == (sc > 0.0) && sc != 0.0;
-                    mine.wA = pc.eA[4]; mine.wB = pc.eB[4]; mine.wC = pc.eC[4];
-                    mine.part = part;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        mine.dir[i] = 2; mine.es[i] = 0; mine.et[i] = 0; mine.eB[i] = 0; mine.eC[i] = 0;
-                        if (i < nv) {
-                            const double A = pc.eA[i], B = pc.eB[i], C = pc.eC[i];
-                            if (fabs(A) * (double)S < 1e-9 * (fabs(B) * (double)S + fabs(C) + 1e-300)) {
-                                mine.dir[i] = 0; mine.eB[i] = B; mine.eC[i] = C;         // edge line parallel to the rows
-                            } else {
-                                // A c + B r + C >= -1e-12  <=>  c >= (-1e-12 - C - B r) / A  (A > 0), <= for A < 0
-                                const double inv = 1.0 / A;
-                                mine.dir[i] = A > 0.0 ? 1 : -1;
-                                mine.es[i] = -B * inv; mine.et[i] = (-1e-12 - C) * inv;
-                            }
-                        }
-                    }
-                    if (front) {
-                        c_lo = max(0, (int)floor(fmin(fmax((double)pc.c_lo, -1.0), (double)S)));
-                        c_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.c_hi, -1.0), (double)S)));
-                        r_lo = max(0, (int)floor(fmin(fmax((double)pc.r_lo, -1.0), (double)S)));
-                        r_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.r_hi, -1.0), (double)S)));
-                    }
-                }
-            }
-            if (a.scan_test_fallback && (e & 1)) bad = true;
-        }
-        const uint32_t bad_m = __ballot_sync(0xffffffffu, bad);
-        const uint32_t front_m = __ballot_sync(0xffffffffu, front);
-        const int nf = __popc(front_m);
-        if (render) {
-            if (bad_m != 0u || nf > SCAN_MAXFRONT) {
-                // raster_kernel renders this env (masked second launch)
-                if (lane == 0) { fallback[e] = 1; atomicAdd(fb_count, 1); }
-                render = false;
-            } else if (lane == 0) fallback[e] = 0;
-        }
-        if (render && front) faces[__popc(front_m & ((1u << lane) - 1u))] = mine;
-        // the rows / columns any front face can touch (union of the conservative screen boxes)
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, d)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, d));
-            r_lo = min(r_lo, __shfl_xor_sync(0xffffffffu, r_lo, d)); r_hi = max(r_hi, __shfl_xor_sync(0xffffffffu, r_hi, d));
-        }
+        if (render && lane < 3 * nf) s_w[lane] = lane % 3 == 0 ? envs[e].face[lane / 3].wA : (lane % 3 == 1 ? envs[e].face[lane / 3].wB : envs[e].face[lane / 3].wC);
         __syncwarp();
         for (int band = 0; band < bands; band++) {
             if (bands > 1) {
@@ -209,104 +232,90 @@ raster_scan_kernel(const RasterArgs a, const int* __restrict__ prim_part, const 
                 load_band(band);
             }
             if (!render) continue;
-            const int row0 = band * band_rows;
-            // ---- row intervals of the front faces inside this band
-            const int br0 = max(r_lo, row0), br1 = min(r_hi, row0 + band_rows - 1);
+            const int row0 = band * band_rows + part * part_rows;     // first image row of this unit's slice; its table rows start at trow0
+            const int trow0 = part * part_rows;
+            // ---- row intervals of the front faces inside this slice
+            const int br0 = max(r_lo, row0), br1 = min(r_hi, row0 + part_rows - 1);
             const int nrows = max(0, br1 - br0 + 1);
             for (int idx = lane; idx < nf * nrows; idx += 32) {
                 const int f = idx / nrows, r = br0 + idx % nrows;
                 int lo, hi;
-                scan_interval(faces[f], r, S, lo, hi);
-                s_iv[f * band_rows + (r - row0)] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
+                scan_interval(envs[e].face[f], r, S, lo, hi);
+                s_iv[f * part_rows + (r - row0)] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
             }
             __syncwarp();
             // ---- pass A: every 16-pixel span of the band, one per lane.  Spans no front face touches (or that are all border)
             // get their baked bytes at once; the others are compacted (ballot + popc) into the warp's list so that pass B runs
             // with all 32 lanes busy
             uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
-            const int span_base = band * n_spans;
+            const float* t_nodef = s_nodef + (size_t)trow0 * S;
+            const uint8_t* t_base = s_base + (size_t)trow0 * S;
+            const int span_base = row0 * (S / 16);
             int cnt = 0;
             for (int s0 = 0; s0 < n_spans; s0 += 32) {
                 const int span = s0 + lane;
-                uint32_t hit = 0;      // front faces whose interval on this row meets the span
+                bool hit = false;      // some front face's interval on this row meets the span
                 if (span < n_spans) {
                     const int off = span << 4, lr = off >> sh_S, c0 = off & (S - 1), r = row0 + lr;
                     const bool skin = (s_skin[(span_base + span) >> 5] >> ((span_base + span) & 31)) & 1u;
                     if (skin && r >= br0 && r <= br1 && c0 <= c_hi && c0 + 15 >= c_lo) {
                         for (int f = 0; f < nf; f++) {
-                            const uchar2 iv = s_iv[f * band_rows + lr];
-                            if ((int)iv.x <= c0 + 15 && (int)iv.y >= c0 && iv.x <= iv.y) hit |= 1u << f;
+                            const uchar2 iv = s_iv[f * part_rows + lr];
+                            hit = hit || ((int)iv.x <= c0 + 15 && (int)iv.y >= c0 && iv.x <= iv.y);
                         }
                     }
-                    if (hit == 0u) *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(s_base + off);
+                    if (!hit) *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(t_base + off);
                 }
-                const uint32_t bal = __ballot_sync(0xffffffffu, hit != 0u);
-                if (hit) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)span | (hit << 16);
+                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)span;
                 cnt += __popc(bal);
             }
             __syncwarp();
-            // ---- pass B: the listed spans, 32 at a time
+            // ---- pass B: the listed spans, 32 at a time, each lane its span in two halves of 8 pixels (register budget)
             for (int i0 = 0; i0 < cnt; i0 += 32) {
                 if (i0 + lane >= cnt) continue;
-                const uint32_t en = s_list[i0 + lane];
-                const int span = (int)(en & 0xffffu);
-                uint32_t hit = en >> 16;
+                const int span = (int)s_list[i0 + lane];
                 const int off = span << 4, lr = off >> sh_S, c0 = off & (S - 1), r = row0 + lr;
-                // window depth along the span, per face affine in the column: d = F - F near / z = (F - Fn w0) - Fn wA k
-                double db[16];
-                uint32_t cov;          // pixels of the span some front face covers
-                {
-                    // first face: no select needed
-                    const int f = __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    const ScanFace& fc = faces[f];
-                    const uchar2 iv = s_iv[f * band_rows + lr];
-                    const int l = max((int)iv.x - c0, 0), h = min((int)iv.y - c0, 15);
-                    cov = (0xffffu >> (15 - h)) & (0xffffu << l);
-                    const double w0 = fc.wA * (double)c0 + (fc.wB * (double)r + fc.wC);   // the oracle's 1/z: eA c + eB r + eC
-                    const double dA = -Fn * fc.wA, d0 = a.F - Fn * w0;
+                uint32_t wds[4];
 #pragma unroll
-                    for (int k = 0; k < 16; k++) db[k] = fma(dA, (double)k, d0);
-                }
-                while (hit) {
-                    const int f = __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    const ScanFace& fc = faces[f];
-                    const uchar2 iv = s_iv[f * band_rows + lr];
-                    const int l = max((int)iv.x - c0, 0), h = min((int)iv.y - c0, 15);
-                    const uint32_t m = (0xffffu >> (15 - h)) & (0xffffu << l);
-                    const double w0 = fc.wA * (double)c0 + (fc.wB * (double)r + fc.wC);
-                    const double dA = -Fn * fc.wA, d0 = a.F - Fn * w0;
+                for (int hf = 0; hf < 2; hf++) {
+                    const int cb = c0 + 8 * hf;
+                    // window depth along the half span, per face affine in the column: d = F - F near / z = (F - Fn w0) - Fn wA k
+                    double db[8];
+                    uint32_t cov = 0;          // pixels some front face covers
+                    for (int f = 0; f < nf; f++) {
+                        const uchar2 iv = s_iv[f * part_rows + lr];
+                        const int l = max((int)iv.x - cb, 0), h = min((int)iv.y - cb, 7);
+                        if (l > h || iv.x > iv.y) continue;
+                        const uint32_t m = (0xffu >> (7 - h)) & (0xffu << l);
+                        const double wA = s_w[3 * f];
+                        const double w0 = wA * (double)cb + (s_w[3 * f + 1] * (double)r + s_w[3 * f + 2]);   // the oracle's 1/z: eA c + eB r + eC
+                        const double dA = -Fn * wA, d0 = a.F - Fn * w0;
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        const double d = fma(dA, (double)k, d0);
-                        const bool in = (m >> k) & 1u, had = (cov >> k) & 1u;
-                        // faces of ONE part never overlap; with several parts the nearest (smallest depth) wins
-                        db[k] = in ? ((MULTI && had) ? fmin(db[k], d) : d) : db[k];
+                        for (int k = 0; k < 8; k++) {
+                            const double d = fma(dA, (double)k, d0);
+                            const bool in = (m >> k) & 1u, had = (cov >> k) & 1u;
+                            // faces of ONE part never overlap; with several parts the nearest (smallest depth) wins
+                            db[k] = in ? ((MULTI && had) ? fmin(db[k], d) : d) : db[k];
+                        }
+                        cov |= m;
                     }
-                    cov |= m;
-                }
-                float nd[16];
-                {
-                    const float4* p = reinterpret_cast<const float4*>(s_nodef + off);
+                    const float4 n0 = *reinterpret_cast<const float4*>(t_nodef + off + 8 * hf), n1 = *reinterpret_cast<const float4*>(t_nodef + off + 8 * hf + 4);
+                    const float nd[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                    const uint2 bres = *reinterpret_cast<const uint2*>(t_base + off + 8 * hf);
+                    uint32_t w2[2] = {bres.x, bres.y};
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const float4 v = p[k];
-                        nd[4 * k] = v.x; nd[4 * k + 1] = v.y; nd[4 * k + 2] = v.z; nd[4 * k + 3] = v.w;
+                    for (int k = 0; k < 8; k++) {
+                        // exact_pixel's arithmetic (tg_raster.cuh) for a covered skin pixel: d as float32, cur = min(nodef, d), then
+                        // t_s_camera's float32 post-process.  cur - nodef = -(nodef - d) when d < nodef, else 0: pen = nodef - d
+                        // where that exceeds the 1e-4 dead zone.  Border pixels (nodef = -1) keep the baked byte, uncovered ones 0.
+                        float pen = ((cov >> k) & 1u) ? nd[k] - (float)db[k] : 0.0f;
+                        pen = (pen > 1e-4f && nd[k] >= 0.0f) ? fminf(pen, 0.05f) : 0.0f;
+                        const float q0 = __fmul_rn(pen, 20.0f);
+                        const float q = __fmaf_rn(__fmaf_rn(-0.05f, q0, pen), 20.0f, q0);
+                        w2[k >> 2] |= (uint32_t)__float2uint_rz(__fmul_rn(q, 255.0f)) << (8 * (k & 3));
                     }
-                }
-                const uint4 bres = *reinterpret_cast<const uint4*>(s_base + off);
-                uint32_t wds[4] = {bres.x, bres.y, bres.z, bres.w};
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    // exact_pixel's arithmetic (tg_raster.cuh) for a covered skin pixel: d as float32, cur = min(nodef, d), then
-                    // t_s_camera's float32 post-process.  cur - nodef = -(nodef - d) when d < nodef, else 0: pen = nodef - d where
-                    // that exceeds the 1e-4 dead zone.  Border pixels (nodef = -1) keep the baked byte, uncovered ones stay 0.
-                    float pen = nd[k] - (float)db[k];
-                    pen = (pen > 1e-4f && ((cov >> k) & 1u) && nd[k] >= 0.0f) ? fminf(pen, 0.05f) : 0.0f;
-                    const float q0 = __fmul_rn(pen, 20.0f);
-                    const float q = __fmaf_rn(__fmaf_rn(-0.05f, q0, pen), 20.0f, q0);
-                    wds[k >> 2] |= (uint32_t)__float2uint_rz(__fmul_rn(q, 255.0f)) << (8 * (k & 3));
+                    wds[2 * hf] = w2[0]; wds[2 * hf + 1] = w2[1];
                 }
                 *reinterpret_cast<uint4*>(obs_e + off) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
             }

@@ -151,7 +151,7 @@ def test_push_config_tables():
     assert abs(t.push_mu_table - 0.065) < 1e-15 and abs(t.push_mu_tip - 0.65) < 1e-15
     assert abs(t.push_tip_k - 300) < 1e-9 and abs(t.push_tip_d - 100.1) < 1e-12
     assert list(t.push_init_pos) == [0.25, -0.1 + 0.04, 0.04] and cfg.n_tip_hull == 610 and cfg.sensor.n_prim == 6
-    hull = keep[-1]
+    hull = keep[7]                       # (dep, gray, mask, tris, rest, prims, prim_nv, hull, parts, part_cen)
     assert hull.shape == (610, 3)
     # the hull rides on the TCP's body, a few mm behind the TCP point
     tcp = np.array(cfg.arm.tcp_pos[:])
