@@ -38,8 +38,13 @@ struct ScanEnv {
     ScanFace face[SCAN_MAXFRONT];
 };
 
-// per warp of the render kernel: 1/z coefficients of the front faces, their row intervals, the span list
-#define SCAN_PER_WARP_SMEM (sizeof(double) * 3 * SCAN_MAXFRONT)
+#define SCAN_UNIT_ROWS 16 // rows of one work unit of the render kernel
+
+// per warp of the render kernel: 1/z coefficients of the front faces, their row intervals, the half-span list
+__host__ __device__ inline size_t scan_per_warp_smem(int S)
+{
+    return (sizeof(double) * 3 * SCAN_MAXFRONT + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS * 2 + (size_t)SCAN_UNIT_ROWS * S / 8 * 2 + 15) & ~size_t(15);
+}
 
 // one front face, one row: the inclusive column interval [lo, hi] it covers (lo > hi: none)
 __device__ __forceinline__ void scan_interval(const ScanFace& f, int r, int S, int& lo, int& hi)
@@ -58,268 +63,264 @@ __device__ __forceinline__ void scan_interval(const ScanFace& f, int r, int S, i
     }
 }
 
-// Pre-pass, one warp per env, lane = primitive: eye-space vertices, plane, edge lines, front-facing test (fp64, a few hundred
-// instructions per env - kept out of the render kernel so that one stays small in registers and code).
+// Pre-pass, `lpe` lanes per env (8 / 16 / 32, the next power of two above the primitive count), lane = primitive: eye-space
+// vertices, plane, edge lines, front-facing test (fp64, a few hundred instructions per env - kept out of the render kernel so
+// that one stays small in registers and code).
 __global__ void __launch_bounds__(128)
 scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const double* __restrict__ part_cen, ScanEnv* __restrict__ out,
-                  uint8_t* __restrict__ fallback, int* __restrict__ fb_count)
+                  uint8_t* __restrict__ fallback, int* __restrict__ fb_count, int lpe)
 {
-    const int lane = threadIdx.x & 31;
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (e >= a.n) return;
+    const int lane = threadIdx.x & 31, sub = lane & (lpe - 1), gbase = lane - sub;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) / lpe;
+    const uint32_t gmask = (lpe == 32 ? 0xffffffffu : ((1u << lpe) - 1u)) << gbase;
     const int S = a.S;
-    if (a.mask && !a.mask[e]) { if (lane == 0) { fallback[e] = 0; out[e].nf = -1; } return; }
+    const bool live = e < a.n;
+    const bool masked = live && a.mask && !a.mask[e];
     bool bad = false, front = false;
     ScanFace mine;
     int c_lo = S, c_hi = -1, r_lo = S, r_hi = -1;
-        if (lane < a.nprim) {
-            const double* cam = a.cam + (size_t)e * 12;
-            const double* stim = a.stim + (size_t)e * 12;
-            const int nv = a.prim_nv[lane];
-            double ve[4][3], vp[4][3];
+    if (live && !masked && sub < a.nprim) {
+        const double* cam = a.cam + (size_t)e * 12;
+        const double* stim = a.stim + (size_t)e * 12;
+        const int nv = a.prim_nv[sub];
+        double ve[4][3], vp[4][3];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const double* v = a.prims + 12 * lane + 3 * (k < nv ? k : nv - 1);
-                double w[3];
+        for (int k = 0; k < 4; k++) {
+            const double* v = a.prims + 12 * sub + 3 * (k < nv ? k : nv - 1);
+            double w[3];
 #pragma unroll
-                for (int c = 0; c < 3; c++) w[c] = stim[3 * c] * v[0] + stim[3 * c + 1] * v[1] + stim[3 * c + 2] * v[2] + stim[9 + c] - cam[c];
-                ve[k][0] = w[0] * cam[9] + w[1] * cam[10] + w[2] * cam[11];
-                ve[k][1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
-                ve[k][2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
-            }
-            PrimCoef pc;
-            const bool infront = prim_from_eye(a, ve, nv, pc, vp);
-            bad = !pc.valid || !infront || pc.clipped;
-            if (!bad) {
-                // camera outside this face's half-space <=> the face is a front face.  Plane n . x = h through the face, the
-                // part's centroid on the inner side: outside <=> (n . 0 - h) = -h and sc = (n . cen - h) have opposite signs,
-                // i.e. h and sc have the same sign
-                const int part = prim_part[lane];
-                const double* pcn = part_cen + 3 * part;
-                double cw[3], ce[3];
+            for (int c = 0; c < 3; c++) w[c] = stim[3 * c] * v[0] + stim[3 * c + 1] * v[1] + stim[3 * c + 2] * v[2] + stim[9 + c] - cam[c];
+            ve[k][0] = w[0] * cam[9] + w[1] * cam[10] + w[2] * cam[11];
+            ve[k][1] = w[0] * cam[6] + w[1] * cam[7] + w[2] * cam[8];
+            ve[k][2] = w[0] * cam[3] + w[1] * cam[4] + w[2] * cam[5];
+        }
+        PrimCoef pc;
+        const bool infront = prim_from_eye(a, ve, nv, pc, vp);
+        bad = !pc.valid || !infront || pc.clipped;
+        if (!bad) {
+            // camera outside this face's half-space <=> the face is a front face.  Plane n . x = h through the face, the
+            // part's centroid on the inner side: outside <=> (n . 0 - h) = -h and sc = (n . cen - h) have opposite signs,
+            // i.e. h and sc have the same sign
+            const int part = prim_part[sub];
+            const double* pcn = part_cen + 3 * part;
+            double cw[3], ce[3];
 #pragma unroll
-                for (int c = 0; c < 3; c++) cw[c] = stim[3 * c] * pcn[0] + stim[3 * c + 1] * pcn[1] + stim[3 * c + 2] * pcn[2] + stim[9 + c];
-                world_to_eye(cam, cw, ce);
-                const double e1[3] = {ve[1][0] - ve[0][0], ve[1][1] - ve[0][1], ve[1][2] - ve[0][2]};
-                const double e2[3] = {ve[2][0] - ve[0][0], ve[2][1] - ve[0][1], ve[2][2] - ve[0][2]};
-                const double nrm[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-                const double h = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
-                const double sc = nrm[0] * ce[0] + nrm[1] * ce[1] + nrm[2] * ce[2] - h;
-                front = (h > 0.0) == (sc > 0.0) && sc != 0.0;
-                mine.wA = pc.eA[4]; mine.wB = pc.eB[4]; mine.wC = pc.eC[4];
-                mine.part = part;
+            for (int c = 0; c < 3; c++) cw[c] = stim[3 * c] * pcn[0] + stim[3 * c + 1] * pcn[1] + stim[3 * c + 2] * pcn[2] + stim[9 + c];
+            world_to_eye(cam, cw, ce);
+            const double e1[3] = {ve[1][0] - ve[0][0], ve[1][1] - ve[0][1], ve[1][2] - ve[0][2]};
+            const double e2[3] = {ve[2][0] - ve[0][0], ve[2][1] - ve[0][1], ve[2][2] - ve[0][2]};
+            const double nrm[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            const double h = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
+            const double sc = nrm[0] * ce[0] + nrm[1] * ce[1] + nrm[2] * ce[2] - h;
+            front = (h > 0.0) == (sc > 0.0) && sc != 0.0;
+            mine.wA = pc.eA[4]; mine.wB = pc.eB[4]; mine.wC = pc.eC[4];
+            mine.part = part;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    mine.dir[i] = 2; mine.es[i] = 0; mine.et[i] = 0; mine.eB[i] = 0; mine.eC[i] = 0;
-                    if (i < nv) {
-                        const double A = pc.eA[i], B = pc.eB[i], C = pc.eC[i];
-                        if (fabs(A) * (double)S < 1e-9 * (fabs(B) * (double)S + fabs(C) + 1e-300)) {
-                            mine.dir[i] = 0; mine.eB[i] = B; mine.eC[i] = C;         // edge line parallel to the rows
-                        } else {
-                            // A c + B r + C >= -1e-12  <=>  c >= (-1e-12 - C - B r) / A  (A > 0), <= for A < 0
-                            const double inv = 1.0 / A;
-                            mine.dir[i] = A > 0.0 ? 1 : -1;
-                            mine.es[i] = -B * inv; mine.et[i] = (-1e-12 - C) * inv;
-                        }
+            for (int i = 0; i < 4; i++) {
+                mine.dir[i] = 2; mine.es[i] = 0; mine.et[i] = 0; mine.eB[i] = 0; mine.eC[i] = 0;
+                if (i < nv) {
+                    const double A = pc.eA[i], B = pc.eB[i], C = pc.eC[i];
+                    if (fabs(A) * (double)S < 1e-9 * (fabs(B) * (double)S + fabs(C) + 1e-300)) {
+                        mine.dir[i] = 0; mine.eB[i] = B; mine.eC[i] = C;         // edge line parallel to the rows
+                    } else {
+                        // A c + B r + C >= -1e-12  <=>  c >= (-1e-12 - C - B r) / A  (A > 0), <= for A < 0
+                        const double inv = 1.0 / A;
+                        mine.dir[i] = A > 0.0 ? 1 : -1;
+                        mine.es[i] = -B * inv; mine.et[i] = (-1e-12 - C) * inv;
                     }
                 }
-                if (front) {
-                    c_lo = max(0, (int)floor(fmin(fmax((double)pc.c_lo, -1.0), (double)S)));
-                    c_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.c_hi, -1.0), (double)S)));
-                    r_lo = max(0, (int)floor(fmin(fmax((double)pc.r_lo, -1.0), (double)S)));
-                    r_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.r_hi, -1.0), (double)S)));
-                }
+            }
+            if (front) {
+                c_lo = max(0, (int)floor(fmin(fmax((double)pc.c_lo, -1.0), (double)S)));
+                c_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.c_hi, -1.0), (double)S)));
+                r_lo = max(0, (int)floor(fmin(fmax((double)pc.r_lo, -1.0), (double)S)));
+                r_hi = min(S - 1, (int)ceil(fmin(fmax((double)pc.r_hi, -1.0), (double)S)));
             }
         }
-    if (a.scan_test_fallback && (e & 1)) bad = true;
-    const uint32_t bad_m = __ballot_sync(0xffffffffu, bad);
-    const uint32_t front_m = __ballot_sync(0xffffffffu, front);
-    const int nf = __popc(front_m);
-    if (bad_m != 0u || nf > SCAN_MAXFRONT) {
-        // raster_kernel renders this env (masked second launch)
-        if (lane == 0) { fallback[e] = 1; atomicAdd(fb_count, 1); out[e].nf = -1; }
-        return;
     }
-    if (front) out[e].face[__popc(front_m & ((1u << lane) - 1u))] = mine;
+    if (a.scan_test_fallback && (e & 1) && live && !masked) bad = true;
+    const uint32_t bad_m = __ballot_sync(0xffffffffu, bad) & gmask;
+    const uint32_t front_m = __ballot_sync(0xffffffffu, front) & gmask;
+    const int nf = __popc(front_m);
+    const bool give_up = bad_m != 0u || nf > SCAN_MAXFRONT;   // raster_kernel renders this env (masked second launch)
+    if (front && !give_up) out[e].face[__popc(front_m & ((1u << lane) - 1u))] = mine;
     // the rows / columns any front face can touch (union of the conservative screen boxes)
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
+    for (int d = lpe >> 1; d > 0; d >>= 1) {
         c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, d)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, d));
         r_lo = min(r_lo, __shfl_xor_sync(0xffffffffu, r_lo, d)); r_hi = max(r_hi, __shfl_xor_sync(0xffffffffu, r_hi, d));
     }
-    if (lane == 0) { fallback[e] = 0; out[e].nf = nf; out[e].c_lo = c_lo; out[e].c_hi = c_hi; out[e].r_lo = r_lo; out[e].r_hi = r_hi; }
+    if (live && sub == 0) {
+        if (masked) { fallback[e] = 0; out[e].nf = -1; }
+        else if (give_up) { fallback[e] = 1; atomicAdd(fb_count, 1); out[e].nf = -1; }
+        else { fallback[e] = 0; out[e].nf = nf; out[e].c_lo = c_lo; out[e].c_hi = c_hi; out[e].r_lo = r_lo; out[e].r_hi = r_hi; }
+    }
 }
 
-// Work unit of a warp: (env, row part) - `parts` consecutive slices of every band's rows, chosen by the host so that the units
-// fill the device's warps (1 at 4096 envs and up, 2 at 2048, 4 at 1024).  Unit u = env * parts + part goes to CTA u mod gridDim.
-template <bool MULTI>
+// Render kernel.  A CTA owns ONE row band of the image (128 x 128 and smaller: the whole image; 256 x 256: a quarter) and
+// fetches that band's static tables (nodef_dep f32 + baked border bytes) once, by TMA bulk copies into shared memory.  After
+// that its 32 warps run on their own: a work unit is (env, SCAN_UNIT_ROWS consecutive rows of the band), handed out through
+// one global counter per band (`ctr[band]`, zeroed by the host before the launch; the next unit is requested before the
+// current one is rendered, so the atomic's latency is hidden) - units that the stimulus does not touch are a plain copy and
+// cost a fraction of the others, and the counter evens that out.
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int parts)
+raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __restrict__ ctr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S, bands = a.bands, band_rows = S / bands, band_px = band_rows * S;
+    const int unit_rows = min(SCAN_UNIT_ROWS, band_rows), parts = band_rows / unit_rows;
     float* s_nodef = reinterpret_cast<float*>(smem_raw);
     uint8_t* s_base = smem_raw + (size_t)band_px * 4;
-    const int part_rows = band_rows / parts;
-    const int n_spans = part_rows * S / 16, all_spans = S * S / 16;   // spans of one unit's slice of a band; of the whole image
-    uint32_t* s_skin = reinterpret_cast<uint32_t*>(smem_raw + (size_t)band_px * 5);   // 1 bit per span of the WHOLE image: has a non-border pixel
+    uint32_t* s_skin = reinterpret_cast<uint32_t*>(smem_raw + (size_t)band_px * 5);   // 1 bit per 8-pixel half span of the band: has a non-border pixel
+    const int band_halves = band_px / 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t wbase = ((size_t)band_px * 5 + (size_t)((all_spans + 31) / 32) * 4 + 15) & ~size_t(15);
-    const size_t per_warp = (SCAN_PER_WARP_SMEM + (size_t)SCAN_MAXFRONT * part_rows * 2 + (size_t)n_spans * 2 + 15) & ~size_t(15);
-    double* s_w = reinterpret_cast<double*>(smem_raw + wbase + per_warp * warp);               // [SCAN_MAXFRONT][3] wA wB wC
-    uchar2* s_iv = reinterpret_cast<uchar2*>(s_w + 3 * SCAN_MAXFRONT);                         // [SCAN_MAXFRONT][part_rows] (lo, hi)
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_iv + (size_t)SCAN_MAXFRONT * part_rows);  // [n_spans] spans some face touches
+    const size_t wbase = ((size_t)band_px * 5 + (size_t)((band_halves + 31) / 32) * 4 + 15) & ~size_t(15);
+    const size_t per_warp = scan_per_warp_smem(S);
+    double* s_w = reinterpret_cast<double*>(smem_raw + wbase + per_warp * warp);                  // [SCAN_MAXFRONT][3] wA wB wC
+    uchar2* s_iv = reinterpret_cast<uchar2*>(s_w + 3 * SCAN_MAXFRONT);                            // [SCAN_MAXFRONT][unit_rows] (lo, hi)
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_iv + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS); // [unit_rows * S / 8] half spans some face touches
     __shared__ __align__(8) uint64_t bar;
-    uint32_t bar_phase = 0;
 
-    // TMA bulk copy of one band of the static tables (nodef_dep f32 + baked border bytes) into shared memory.  128 x 128 and
-    // smaller: one band = the whole image, fetched once per CTA.  256 x 256: the CTA walks the four bands in turn.
-    auto load_band = [&](int band) {
-        if (threadIdx.x == 0) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            const uint32_t bytes = (uint32_t)band_px * 5u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
-            tma_bulk_load(s_nodef, a.nodef + (size_t)band * band_px, (uint32_t)band_px * 4u, &bar);
-            tma_bulk_load(s_base, a.base + (size_t)band * band_px, (uint32_t)band_px, &bar);
-        }
+    const int band = blockIdx.x % bands;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        const uint32_t bytes = (uint32_t)band_px * 5u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        tma_bulk_load(s_nodef, a.nodef + (size_t)band * band_px, (uint32_t)band_px * 4u, &bar);
+        tma_bulk_load(s_base, a.base + (size_t)band * band_px, (uint32_t)band_px, &bar);
+    }
+    // first unit of every warp, requested while the tables are in flight
+    const int units = a.n * parts;
+    int u_req = lane == 0 ? atomicAdd(ctr + band, 1) : 0;
+    __syncthreads();
+    {
         uint32_t ok = 0;
         while (!ok) {
             asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                          : "=r"(ok)
-                         : "r"(smem_u32(&bar)), "r"(bar_phase)
+                         : "r"(smem_u32(&bar)), "r"(0u)
                          : "memory");
         }
-        bar_phase ^= 1u;
-    };
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
-    // span skin bitmap of the whole image, once per CTA (from the L2-resident table)
-    for (int w0 = threadIdx.x; w0 < (all_spans + 31) / 32; w0 += SCAN_THREADS) {
-        uint32_t bits = 0;
-        for (int jj = 0; jj < 32 && w0 * 32 + jj < all_spans; jj++) {
-            const float4* p = reinterpret_cast<const float4*>(a.nodef + (size_t)(w0 * 32 + jj) * 16);
-            bool skin = false;
-#pragma unroll
-            for (int k = 0; k < 4; k++) { const float4 v = __ldg(p + k); skin = skin || v.x >= 0.0f || v.y >= 0.0f || v.z >= 0.0f || v.w >= 0.0f; }
-            bits |= (skin ? 1u : 0u) << jj;
+    // skin bitmap of the band's half spans, from the tables just loaded
+    for (int h0 = warp * 32; h0 < band_halves; h0 += SCAN_THREADS) {
+        const int h = h0 + lane;
+        bool skin = false;
+        if (h < band_halves) {
+            const float4 v0 = *reinterpret_cast<const float4*>(s_nodef + (size_t)h * 8), v1 = *reinterpret_cast<const float4*>(s_nodef + (size_t)h * 8 + 4);
+            skin = v0.x >= 0.0f || v0.y >= 0.0f || v0.z >= 0.0f || v0.w >= 0.0f || v1.x >= 0.0f || v1.y >= 0.0f || v1.z >= 0.0f || v1.w >= 0.0f;
         }
-        s_skin[w0] = bits;
+        const uint32_t bits = __ballot_sync(0xffffffffu, skin);
+        if (lane == 0) s_skin[h0 >> 5] = bits;
     }
     __syncthreads();
-    if (bands == 1) load_band(0);
     const int sh_S = 31 - __clz(S);
     const double Fn = a.F * a.near_;
-    const int units = a.n * parts, per_cta = (units + gridDim.x - 1) / gridDim.x, rounds = (per_cta + SCAN_WARPS - 1) / SCAN_WARPS;
+    const int spans = unit_rows * S / 16;     // 16-pixel spans of one unit
 
-    for (int rd = 0; rd < rounds; rd++) {
-        const int slot = rd * SCAN_WARPS + warp;                 // this warp's unit among the CTA's
-        const int u = slot < per_cta ? slot * gridDim.x + blockIdx.x : units;
-        const int e = u < units ? u / parts : a.n, part = u < units ? u % parts : 0;
-        int nf = -1, c_lo = 0, c_hi = 0, r_lo = 0, r_hi = 0;
-        if (e < a.n) {
-            const ScanEnv& se = envs[e];
-            nf = se.nf; c_lo = se.c_lo; c_hi = se.c_hi; r_lo = se.r_lo; r_hi = se.r_hi;
+    for (;;) {
+        const int u = __shfl_sync(0xffffffffu, u_req, 0);
+        if (u >= units) break;
+        if (lane == 0) u_req = atomicAdd(ctr + band, 1);
+        const int e = u / parts, part = u - e * parts;
+        const ScanEnv& se = envs[e];
+        const int nf = se.nf;
+        if (nf < 0) continue;              // masked-out envs and the ones handed to raster_kernel
+        const int trow0 = part * unit_rows, row0 = band * band_rows + trow0;     // first row of the unit in the band's tables / in the image
+        const int c_lo = se.c_lo, c_hi = se.c_hi;
+        const int br0 = max(se.r_lo, row0), br1 = min(se.r_hi, row0 + unit_rows - 1);
+        const int nrows = max(0, br1 - br0 + 1);
+        uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
+        const float* t_nodef = s_nodef + (size_t)trow0 * S;
+        const uint8_t* t_base = s_base + (size_t)trow0 * S;
+        if (nrows == 0) {
+            // the stimulus does not reach these rows: the baked bytes
+            for (int sp = lane; sp < spans; sp += 32) *reinterpret_cast<uint4*>(obs_e + (sp << 4)) = *reinterpret_cast<const uint4*>(t_base + (sp << 4));
+            continue;
         }
-        const bool render = nf >= 0;       // masked-out envs and the ones handed to raster_kernel carry nf = -1
         __syncwarp();
-        if (render && lane < 3 * nf) s_w[lane] = lane % 3 == 0 ? envs[e].face[lane / 3].wA : (lane % 3 == 1 ? envs[e].face[lane / 3].wB : envs[e].face[lane / 3].wC);
+        if (lane < 3 * nf) { const ScanFace& fc = se.face[lane / 3]; s_w[lane] = lane % 3 == 0 ? fc.wA : (lane % 3 == 1 ? fc.wB : fc.wC); }
+        // ---- row intervals of the front faces inside this unit
+        for (int idx = lane; idx < nf * nrows; idx += 32) {
+            const int f = idx / nrows, r = br0 + idx - f * nrows;
+            int lo, hi;
+            scan_interval(se.face[f], r, S, lo, hi);
+            s_iv[f * SCAN_UNIT_ROWS + (r - row0)] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
+        }
         __syncwarp();
-        for (int band = 0; band < bands; band++) {
-            if (bands > 1) {
-                __syncthreads();          // every warp is done with the previous band's tables
-                load_band(band);
-            }
-            if (!render) continue;
-            const int row0 = band * band_rows + part * part_rows;     // first image row of this unit's slice; its table rows start at trow0
-            const int trow0 = part * part_rows;
-            // ---- row intervals of the front faces inside this slice
-            const int br0 = max(r_lo, row0), br1 = min(r_hi, row0 + part_rows - 1);
-            const int nrows = max(0, br1 - br0 + 1);
-            for (int idx = lane; idx < nf * nrows; idx += 32) {
-                const int f = idx / nrows, r = br0 + idx % nrows;
-                int lo, hi;
-                scan_interval(envs[e].face[f], r, S, lo, hi);
-                s_iv[f * part_rows + (r - row0)] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
-            }
-            __syncwarp();
-            // ---- pass A: every 16-pixel span of the band, one per lane.  Spans no front face touches (or that are all border)
-            // get their baked bytes at once; the others are compacted (ballot + popc) into the warp's list so that pass B runs
-            // with all 32 lanes busy
-            uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
-            const float* t_nodef = s_nodef + (size_t)trow0 * S;
-            const uint8_t* t_base = s_base + (size_t)trow0 * S;
-            const int span_base = row0 * (S / 16);
-            int cnt = 0;
-            for (int s0 = 0; s0 < n_spans; s0 += 32) {
-                const int span = s0 + lane;
-                bool hit = false;      // some front face's interval on this row meets the span
-                if (span < n_spans) {
-                    const int off = span << 4, lr = off >> sh_S, c0 = off & (S - 1), r = row0 + lr;
-                    const bool skin = (s_skin[(span_base + span) >> 5] >> ((span_base + span) & 31)) & 1u;
-                    if (skin && r >= br0 && r <= br1 && c0 <= c_hi && c0 + 15 >= c_lo) {
-                        for (int f = 0; f < nf; f++) {
-                            const uchar2 iv = s_iv[f * part_rows + lr];
-                            hit = hit || ((int)iv.x <= c0 + 15 && (int)iv.y >= c0 && iv.x <= iv.y);
-                        }
-                    }
-                    if (!hit) *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(t_base + off);
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)span;
-                cnt += __popc(bal);
-            }
-            __syncwarp();
-            // ---- pass B: the listed spans, 32 at a time, each lane its span in two halves of 8 pixels (register budget)
-            for (int i0 = 0; i0 < cnt; i0 += 32) {
-                if (i0 + lane >= cnt) continue;
-                const int span = (int)s_list[i0 + lane];
+        // ---- pass A: every 16-pixel span of the unit, one per lane.  8-pixel halves no front face touches (or that are all
+        // border) get their baked bytes at once; the others are compacted (ballot + popc) into the warp's list so that pass B
+        // runs with all 32 lanes busy
+        const int half_base = trow0 * (S / 8);
+        int cnt = 0;
+        for (int s0 = 0; s0 < spans; s0 += 32) {
+            const int span = s0 + lane;
+            bool hit0 = false, hit1 = false;      // some front face's interval on this row meets the first / second half
+            if (span < spans) {
                 const int off = span << 4, lr = off >> sh_S, c0 = off & (S - 1), r = row0 + lr;
-                uint32_t wds[4];
-#pragma unroll
-                for (int hf = 0; hf < 2; hf++) {
-                    const int cb = c0 + 8 * hf;
-                    // window depth along the half span, per face affine in the column: d = F - F near / z = (F - Fn w0) - Fn wA k
-                    double db[8];
-                    uint32_t cov = 0;          // pixels some front face covers
+                const uint32_t skin = (s_skin[(half_base + 2 * span) >> 5] >> ((half_base + 2 * span) & 31)) & 3u;
+                if (skin && r >= br0 && r <= br1 && c0 <= c_hi && c0 + 15 >= c_lo) {
                     for (int f = 0; f < nf; f++) {
-                        const uchar2 iv = s_iv[f * part_rows + lr];
-                        const int l = max((int)iv.x - cb, 0), h = min((int)iv.y - cb, 7);
-                        if (l > h || iv.x > iv.y) continue;
-                        const uint32_t m = (0xffu >> (7 - h)) & (0xffu << l);
-                        const double wA = s_w[3 * f];
-                        const double w0 = wA * (double)cb + (s_w[3 * f + 1] * (double)r + s_w[3 * f + 2]);   // the oracle's 1/z: eA c + eB r + eC
-                        const double dA = -Fn * wA, d0 = a.F - Fn * w0;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            const double d = fma(dA, (double)k, d0);
-                            const bool in = (m >> k) & 1u, had = (cov >> k) & 1u;
-                            // faces of ONE part never overlap; with several parts the nearest (smallest depth) wins
-                            db[k] = in ? ((MULTI && had) ? fmin(db[k], d) : d) : db[k];
-                        }
-                        cov |= m;
+                        const uchar2 iv = s_iv[f * SCAN_UNIT_ROWS + lr];
+                        const bool some = iv.x <= iv.y;
+                        hit0 = hit0 || (some && (int)iv.x <= c0 + 7 && (int)iv.y >= c0);
+                        hit1 = hit1 || (some && (int)iv.x <= c0 + 15 && (int)iv.y >= c0 + 8);
                     }
-                    const float4 n0 = *reinterpret_cast<const float4*>(t_nodef + off + 8 * hf), n1 = *reinterpret_cast<const float4*>(t_nodef + off + 8 * hf + 4);
-                    const float nd[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-                    const uint2 bres = *reinterpret_cast<const uint2*>(t_base + off + 8 * hf);
-                    uint32_t w2[2] = {bres.x, bres.y};
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        // exact_pixel's arithmetic (tg_raster.cuh) for a covered skin pixel: d as float32, cur = min(nodef, d), then
-                        // t_s_camera's float32 post-process.  cur - nodef = -(nodef - d) when d < nodef, else 0: pen = nodef - d
-                        // where that exceeds the 1e-4 dead zone.  Border pixels (nodef = -1) keep the baked byte, uncovered ones 0.
-                        float pen = ((cov >> k) & 1u) ? nd[k] - (float)db[k] : 0.0f;
-                        pen = (pen > 1e-4f && nd[k] >= 0.0f) ? fminf(pen, 0.05f) : 0.0f;
-                        const float q0 = __fmul_rn(pen, 20.0f);
-                        const float q = __fmaf_rn(__fmaf_rn(-0.05f, q0, pen), 20.0f, q0);
-                        w2[k >> 2] |= (uint32_t)__float2uint_rz(__fmul_rn(q, 255.0f)) << (8 * (k & 3));
-                    }
-                    wds[2 * hf] = w2[0]; wds[2 * hf + 1] = w2[1];
+                    hit0 = hit0 && (skin & 1u); hit1 = hit1 && (skin & 2u);
                 }
-                *reinterpret_cast<uint4*>(obs_e + off) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                if (!hit0 && !hit1) *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(t_base + off);
+                else if (!hit0) *reinterpret_cast<uint2*>(obs_e + off) = *reinterpret_cast<const uint2*>(t_base + off);
+                else if (!hit1) *reinterpret_cast<uint2*>(obs_e + off + 8) = *reinterpret_cast<const uint2*>(t_base + off + 8);
             }
-            __syncwarp();
+            const uint32_t b0 = __ballot_sync(0xffffffffu, hit0), b1 = __ballot_sync(0xffffffffu, hit1);
+            const uint32_t below = (1u << lane) - 1u;
+            if (hit0) s_list[cnt + __popc(b0 & below)] = (uint16_t)(2 * span);
+            cnt += __popc(b0);
+            if (hit1) s_list[cnt + __popc(b1 & below)] = (uint16_t)(2 * span + 1);
+            cnt += __popc(b1);
+        }
+        __syncwarp();
+        // ---- pass B: the listed half spans, 32 at a time, one per lane
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            if (i0 + lane >= cnt) continue;
+            const int off = (int)s_list[i0 + lane] << 3, lr = off >> sh_S, cb = off & (S - 1), r = row0 + lr;
+            const float4 n0 = *reinterpret_cast<const float4*>(t_nodef + off), n1 = *reinterpret_cast<const float4*>(t_nodef + off + 4);
+            const float nd[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+            // pen = nodef - d of the NEAREST front face covering the pixel (several parts overlap on the screen; the faces of one
+            // part do not): the max over the covering faces of nodef - (float)d, since both roundings are monotonic.  Per face the
+            // window depth is affine in the column: d = F - F near / z = (F - Fn w0) - Fn wA k, w = the oracle's 1/z = eA c + eB r + eC
+            float pen[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) pen[k] = -1.0f;
+            for (int f = 0; f < nf; f++) {
+                const uchar2 iv = s_iv[f * SCAN_UNIT_ROWS + lr];
+                const int l = max((int)iv.x - cb, 0), h = min((int)iv.y - cb, 7);
+                if (l > h || iv.x > iv.y) continue;
+                const uint32_t m = (0xffu >> (7 - h)) & (0xffu << l);
+                const double wA = s_w[3 * f];
+                const double w0 = wA * (double)cb + (s_w[3 * f + 1] * (double)r + s_w[3 * f + 2]);
+                const double dA = -Fn * wA, d0 = a.F - Fn * w0;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if ((m >> k) & 1u) pen[k] = fmaxf(pen[k], nd[k] - (float)fma(dA, (double)k, d0));
+            }
+            const uint2 bres = *reinterpret_cast<const uint2*>(t_base + off);
+            uint32_t q8[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                // exact_pixel's arithmetic (tg_raster.cuh) for a covered skin pixel: d as float32, cur = min(nodef, d), then
+                // t_s_camera's float32 post-process.  cur - nodef = -(nodef - d) when d < nodef, else 0: pen = nodef - d where that
+                // exceeds the 1e-4 dead zone.  Border pixels carry nodef = -1 and d >= 0 (no vertex is nearer than the near
+                // plane here), so their pen stays negative and they keep the baked byte; uncovered pixels stay 0.
+                const float p = pen[k] > 1e-4f ? fminf(pen[k], 0.05f) : 0.0f;
+                const float q0 = __fmul_rn(p, 20.0f);
+                const float q = __fmaf_rn(__fmaf_rn(-0.05f, q0, p), 20.0f, q0);
+                q8[k] = __float2uint_rz(__fmul_rn(q, 255.0f));
+            }
+            uint2 o;
+            o.x = bres.x | q8[0] | (q8[1] << 8) | (q8[2] << 16) | (q8[3] << 24);
+            o.y = bres.y | q8[4] | (q8[5] << 8) | (q8[6] << 16) | (q8[7] << 24);
+            *reinterpret_cast<uint2*>(obs_e + off) = o;
         }
     }
 }

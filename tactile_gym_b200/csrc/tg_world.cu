@@ -62,7 +62,7 @@ struct TgWorld {
     // scanline raster (convex parts): tables, the per-env fallback mask + counter, launch shape
     int* d_prim_part = nullptr; double* d_part_cen = nullptr; uint8_t* d_fallback = nullptr; int* d_fb_count = nullptr;
     ScanEnv* d_scan_envs = nullptr;
-    size_t scan_smem = 0; int scan_grid = 0; bool scan_ok = false, scan_multi = false;   // scan_smem: sized for parts = 1 (the largest)
+    size_t scan_smem = 0; int scan_grid = 0, scan_lpe = 32; bool scan_ok = false;   // d_fb_count: [0] envs handed to raster_kernel, [1 + band] the render kernel's unit counters
     size_t push_smem = 0;
     int raster_grid = 0;
     int standby_blocks = 0;
@@ -289,24 +289,18 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             for (int i = 0; i < np; i++)
                 if (cfg->sensor.h_prim_part[i] < 0 || cfg->sensor.h_prim_part[i] >= cfg->sensor.n_parts) return fail(TG_EINVAL, "h_prim_part[%d] out of range", i);
             if ((rc = dalloc(w, &w->d_prim_part, np)) || (rc = dalloc(w, &w->d_part_cen, (size_t)3 * cfg->sensor.n_parts)) ||
-                (rc = dalloc(w, &w->d_fallback, n)) || (rc = dalloc(w, &w->d_fb_count, 1)) || (rc = dalloc(w, &w->d_scan_envs, n))) return rc;
+                (rc = dalloc(w, &w->d_fallback, n)) || (rc = dalloc(w, &w->d_fb_count, 1 + 8)) || (rc = dalloc(w, &w->d_scan_envs, n))) return rc;
             CK(cudaMemcpy(w->d_prim_part, cfg->sensor.h_prim_part, sizeof(int) * np, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(w->d_part_cen, cfg->sensor.h_part_centroid, sizeof(double) * 3 * cfg->sensor.n_parts, cudaMemcpyHostToDevice));
-            const size_t band_rows = (size_t)S / r.bands;
-            const size_t nsp = band_px / 16;
-            const size_t pw = (SCAN_PER_WARP_SMEM + (size_t)SCAN_MAXFRONT * band_rows * 2 + nsp * 2 + 15) & ~size_t(15);
-            w->scan_smem = ((band_px * 5 + ((px / 16 + 31) / 32) * 4 + 15) & ~size_t(15)) + pw * SCAN_WARPS;
-            w->scan_multi = cfg->sensor.n_parts > 1;
+            // band tables + half-span skin bitmap + the warps' own tables
+            w->scan_smem = ((band_px * 5 + ((band_px / 8 + 31) / 32) * 4 + 15) & ~size_t(15)) + scan_per_warp_smem(S) * SCAN_WARPS;
+            w->scan_lpe = np <= 8 ? 8 : (np <= 16 ? 16 : 32);
             int ps = 0;
-            if (w->scan_multi) {
-                CK(cudaFuncSetAttribute(raster_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel<true>, SCAN_THREADS, w->scan_smem));
-            } else {
-                CK(cudaFuncSetAttribute(raster_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel<false>, SCAN_THREADS, w->scan_smem));
-            }
+            CK(cudaFuncSetAttribute(raster_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel, SCAN_THREADS, w->scan_smem));
             if (ps >= 1) {
-                w->scan_grid = w->sm_count * ps;      // every CTA walks all bands itself
+                w->scan_grid = w->sm_count * ps;
+                w->scan_grid -= w->scan_grid % r.bands;   // the same number of CTAs on every band
                 w->scan_ok = true;
             }
         }
@@ -518,14 +512,12 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
         if (r.hf) raster_hf_kernel<<<grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
         else if (w->scan_ok) {
             // convex stimulus: scanline raster, then raster_kernel for the envs it flagged (returns at once when there are none)
-            // row parts per image so that (envs x parts) fills the device's warps; every SM gets a CTA
-            int parts = 1;
-            while (parts < 4 && (long)cnt * parts < (long)w->scan_grid * SCAN_WARPS * 3 / 4) parts <<= 1;
-            const int sgrid = std::min(w->scan_grid, cnt * parts);
-            CK(cudaMemsetAsync(w->d_fb_count, 0, sizeof(int), st));
-            scan_setup_kernel<<<(cnt + 3) / 4, 128, 0, st>>>(r, w->d_prim_part, w->d_part_cen, w->d_scan_envs + e0, w->d_fallback + e0, w->d_fb_count);
-            if (w->scan_multi) raster_scan_kernel<true><<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, parts);
-            else raster_scan_kernel<false><<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, parts);
+            const int band_rows = r.S / r.bands, unit_rows = std::min(SCAN_UNIT_ROWS, band_rows), units_per_band = cnt * (band_rows / unit_rows);
+            const int sgrid = std::min(w->scan_grid, ((units_per_band + SCAN_WARPS - 1) / SCAN_WARPS) * r.bands);
+            CK(cudaMemsetAsync(w->d_fb_count, 0, sizeof(int) * (1 + 8), st));
+            const int per_blk = 128 / w->scan_lpe;
+            scan_setup_kernel<<<(cnt + per_blk - 1) / per_blk, 128, 0, st>>>(r, w->d_prim_part, w->d_part_cen, w->d_scan_envs + e0, w->d_fallback + e0, w->d_fb_count, w->scan_lpe);
+            raster_scan_kernel<<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, w->d_fb_count + 1);
             w->launches += 2;
             CK(cudaGetLastError());
             RasterArgs r2 = r;
