@@ -38,12 +38,12 @@ struct ScanEnv {
     ScanFace face[SCAN_MAXFRONT];
 };
 
-#define SCAN_UNIT_ROWS 16 // rows of one work unit of the render kernel
+#define SCAN_UNIT_ROWS 32 // most rows a work unit of the render kernel can have (16 by default, TG_SCAN_UNIT_ROWS)
 
 // per warp of the render kernel: 1/z coefficients of the front faces, their row intervals, the half-span list
 __host__ __device__ inline size_t scan_per_warp_smem(int S)
 {
-    return (sizeof(double) * 3 * SCAN_MAXFRONT + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS * 2 + (size_t)SCAN_UNIT_ROWS * S / 8 * 2 + 15) & ~size_t(15);
+    return (sizeof(double) * 3 * SCAN_MAXFRONT + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS * 2 + SCAN_UNIT_ROWS * 4 + (size_t)SCAN_UNIT_ROWS * S / 8 * 2 + 15) & ~size_t(15);
 }
 
 // one front face, one row: the inclusive column interval [lo, hi] it covers (lo > hi: none)
@@ -57,9 +57,9 @@ __device__ __forceinline__ void scan_interval(const ScanFace& f, int r, int S, i
         if (d == 2) continue;
         if (d == 0) { if (f.eB[i] * dr + f.eC[i] < -1e-12) { lo = 1; hi = 0; } continue; }
         const double x = fma(f.es[i], dr, f.et[i]);
-        // the clamps keep the conversions in range; a crossing far off the image leaves the interval empty or untouched
-        if (d > 0) lo = max(lo, (int)ceil(fmin(fmax(x, -1.0), (double)S)));
-        else hi = min(hi, (int)floor(fmin(fmax(x, -2.0), (double)S)));
+        // ceil / floor inside the conversion, which saturates: a crossing far off the image leaves the interval empty or untouched
+        if (d > 0) lo = max(lo, __double2int_ru(x));
+        else hi = min(hi, __double2int_rd(x));
     }
 }
 
@@ -158,16 +158,16 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
 
 // Render kernel.  A CTA owns ONE row band of the image (128 x 128 and smaller: the whole image; 256 x 256: a quarter) and
 // fetches that band's static tables (nodef_dep f32 + baked border bytes) once, by TMA bulk copies into shared memory.  After
-// that its 32 warps run on their own: a work unit is (env, SCAN_UNIT_ROWS consecutive rows of the band), handed out through
+// that its 32 warps run on their own: a work unit is (env, `unit_rows` consecutive rows of the band), handed out through
 // one global counter per band (`ctr[band]`, zeroed by the host before the launch; the next unit is requested before the
 // current one is rendered, so the atomic's latency is hidden) - units that the stimulus does not touch are a plain copy and
-// cost a fraction of the others, and the counter evens that out.
+// cost a fraction of the others, and the counter evens that out.  unit_rows (16 or 32) and band_rows / unit_rows are powers of two.
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __restrict__ ctr)
+raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __restrict__ ctr, int sh_unit)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S, bands = a.bands, band_rows = S / bands, band_px = band_rows * S;
-    const int unit_rows = min(SCAN_UNIT_ROWS, band_rows), parts = band_rows / unit_rows;
+    const int unit_rows = 1 << sh_unit, sh_parts = (31 - __clz(band_rows)) - sh_unit;
     float* s_nodef = reinterpret_cast<float*>(smem_raw);
     uint8_t* s_base = smem_raw + (size_t)band_px * 4;
     uint32_t* s_skin = reinterpret_cast<uint32_t*>(smem_raw + (size_t)band_px * 5);   // 1 bit per 8-pixel half span of the band: has a non-border pixel
@@ -177,7 +177,8 @@ raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __
     const size_t per_warp = scan_per_warp_smem(S);
     double* s_w = reinterpret_cast<double*>(smem_raw + wbase + per_warp * warp);                  // [SCAN_MAXFRONT][3] wA wB wC
     uchar2* s_iv = reinterpret_cast<uchar2*>(s_w + 3 * SCAN_MAXFRONT);                            // [SCAN_MAXFRONT][unit_rows] (lo, hi)
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_iv + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS); // [unit_rows * S / 8] half spans some face touches
+    uint32_t* s_rowm = reinterpret_cast<uint32_t*>(s_iv + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS); // [unit_rows] half spans of the row to shade
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_rowm + SCAN_UNIT_ROWS);                      // [unit_rows * S / 8] the same as a list
     __shared__ __align__(8) uint64_t bar;
 
     const int band = blockIdx.x % bands;
@@ -189,9 +190,20 @@ raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __
         tma_bulk_load(s_nodef, a.nodef + (size_t)band * band_px, (uint32_t)band_px * 4u, &bar);
         tma_bulk_load(s_base, a.base + (size_t)band * band_px, (uint32_t)band_px, &bar);
     }
-    // first unit of every warp, requested while the tables are in flight
-    const int units = a.n * parts;
-    int u_req = lane == 0 ? atomicAdd(ctr + band, 1) : 0;
+    // a warp's next unit: lane 0 asks the band's counter; the result register is only read at the top of the next round, so the
+    // atomic's latency is hidden behind the current unit.  ptxas rewrites atomic adds it can prove warp-uniform into its
+    // aggregated form (vote, one atomic, a SHUFFLE OF THE RESULT right behind it - which waits for the whole round trip); an
+    // addend it cannot see through (a 1 read back from shared memory) under a real branch keeps the plain instruction.
+    const int units = a.n << sh_parts;
+    __shared__ int s_one[32];
+    if (warp == 0) s_one[lane] = S > 0;
+    __syncthreads();
+    const int one = *reinterpret_cast<volatile int*>(&s_one[lane]);
+    int u_req = 0;
+    auto request = [&]() {
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;\n" : "+r"(u_req) : "l"(ctr + band), "r"(one) : "memory");
+    };
+    request();
     __syncthreads();
     {
         uint32_t ok = 0;
@@ -214,26 +226,25 @@ raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __
         if (lane == 0) s_skin[h0 >> 5] = bits;
     }
     __syncthreads();
-    const int sh_S = 31 - __clz(S);
+    const int sh_S = 31 - __clz(S), sh_H = sh_S - 3;      // S / 8 = 1 << sh_H half spans per row (8, 16 or 32)
     const double Fn = a.F * a.near_;
-    const int spans = unit_rows * S / 16;     // 16-pixel spans of one unit
+    const int spans = (unit_rows << sh_S) >> 4;           // 16-pixel spans of one unit
+    const uint32_t row_all = sh_H == 5 ? 0xffffffffu : ((1u << (1 << sh_H)) - 1u);
 
     for (;;) {
         const int u = __shfl_sync(0xffffffffu, u_req, 0);
         if (u >= units) break;
-        if (lane == 0) u_req = atomicAdd(ctr + band, 1);
-        const int e = u / parts, part = u - e * parts;
+        request();
+        const int e = u >> sh_parts, part = u & ((1 << sh_parts) - 1);
         const ScanEnv& se = envs[e];
         const int nf = se.nf;
         if (nf < 0) continue;              // masked-out envs and the ones handed to raster_kernel
-        const int trow0 = part * unit_rows, row0 = band * band_rows + trow0;     // first row of the unit in the band's tables / in the image
-        const int c_lo = se.c_lo, c_hi = se.c_hi;
+        const int trow0 = part << sh_unit, row0 = band * band_rows + trow0;     // first row of the unit in the band's tables / in the image
         const int br0 = max(se.r_lo, row0), br1 = min(se.r_hi, row0 + unit_rows - 1);
-        const int nrows = max(0, br1 - br0 + 1);
-        uint8_t* obs_e = a.obs + (size_t)e * S * S + (size_t)row0 * S;
-        const float* t_nodef = s_nodef + (size_t)trow0 * S;
-        const uint8_t* t_base = s_base + (size_t)trow0 * S;
-        if (nrows == 0) {
+        uint8_t* obs_e = a.obs + (((size_t)e << (2 * sh_S)) + ((size_t)row0 << sh_S));
+        const float* t_nodef = s_nodef + ((size_t)trow0 << sh_S);
+        const uint8_t* t_base = s_base + ((size_t)trow0 << sh_S);
+        if (br1 < br0) {
             // the stimulus does not reach these rows: the baked bytes
             for (int sp = lane; sp < spans; sp += 32) *reinterpret_cast<uint4*>(obs_e + (sp << 4)) = *reinterpret_cast<const uint4*>(t_base + (sp << 4));
             continue;
@@ -241,42 +252,49 @@ raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __
         __syncwarp();
         if (lane < 3 * nf) { const ScanFace& fc = se.face[lane / 3]; s_w[lane] = lane % 3 == 0 ? fc.wA : (lane % 3 == 1 ? fc.wB : fc.wC); }
         // ---- row intervals of the front faces inside this unit
-        for (int idx = lane; idx < nf * nrows; idx += 32) {
-            const int f = idx / nrows, r = br0 + idx - f * nrows;
-            int lo, hi;
-            scan_interval(se.face[f], r, S, lo, hi);
-            s_iv[f * SCAN_UNIT_ROWS + (r - row0)] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
+        for (int idx = lane; idx < (nf << sh_unit); idx += 32) {
+            const int f = idx >> sh_unit, lr = idx & (unit_rows - 1), r = row0 + lr;
+            int lo = 1, hi = 0;
+            if (r >= br0 && r <= br1) scan_interval(se.face[f], r, S, lo, hi);
+            s_iv[f * SCAN_UNIT_ROWS + lr] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
         }
         __syncwarp();
-        // ---- pass A: every 16-pixel span of the unit, one per lane.  8-pixel halves no front face touches (or that are all
-        // border) get their baked bytes at once; the others are compacted (ballot + popc) into the warp's list so that pass B
-        // runs with all 32 lanes busy
-        const int half_base = trow0 * (S / 8);
+        // ---- per row: the half spans between the leftmost and the rightmost covered column that have skin pixels
+        if (lane < unit_rows) {
+            int ulo = S, uhi = -1;
+            for (int f = 0; f < nf; f++) {
+                const uchar2 iv = s_iv[f * SCAN_UNIT_ROWS + lane];
+                if (iv.x <= iv.y) { ulo = min(ulo, (int)iv.x); uhi = max(uhi, (int)iv.y); }
+            }
+            uint32_t m = 0;
+            if (ulo <= uhi) {
+                const int hb = ((trow0 + lane) << sh_H);        // first half span of the row in the band's bitmap
+                const uint32_t skin = (s_skin[hb >> 5] >> (hb & 31)) & row_all;
+                const int h_lo = ulo >> 3, h_hi = uhi >> 3;
+                m = skin & (0xffffffffu >> (31 - h_hi)) & (0xffffffffu << h_lo);
+            }
+            s_rowm[lane] = m;
+        }
+        __syncwarp();
+        // ---- pass A: every 16-pixel span of the unit, one per lane.  8-pixel halves that are not to be shaded get their baked
+        // bytes at once; the others are compacted (ballot + popc) into the warp's list so that pass B runs with all lanes busy
         int cnt = 0;
         for (int s0 = 0; s0 < spans; s0 += 32) {
             const int span = s0 + lane;
-            bool hit0 = false, hit1 = false;      // some front face's interval on this row meets the first / second half
+            uint32_t bits = 0;
             if (span < spans) {
-                const int off = span << 4, lr = off >> sh_S, c0 = off & (S - 1), r = row0 + lr;
-                const uint32_t skin = (s_skin[(half_base + 2 * span) >> 5] >> ((half_base + 2 * span) & 31)) & 3u;
-                if (skin && r >= br0 && r <= br1 && c0 <= c_hi && c0 + 15 >= c_lo) {
-                    for (int f = 0; f < nf; f++) {
-                        const uchar2 iv = s_iv[f * SCAN_UNIT_ROWS + lr];
-                        const bool some = iv.x <= iv.y;
-                        hit0 = hit0 || (some && (int)iv.x <= c0 + 7 && (int)iv.y >= c0);
-                        hit1 = hit1 || (some && (int)iv.x <= c0 + 15 && (int)iv.y >= c0 + 8);
-                    }
-                    hit0 = hit0 && (skin & 1u); hit1 = hit1 && (skin & 2u);
-                }
-                if (!hit0 && !hit1) *reinterpret_cast<uint4*>(obs_e + off) = *reinterpret_cast<const uint4*>(t_base + off);
-                else if (!hit0) *reinterpret_cast<uint2*>(obs_e + off) = *reinterpret_cast<const uint2*>(t_base + off);
-                else if (!hit1) *reinterpret_cast<uint2*>(obs_e + off + 8) = *reinterpret_cast<const uint2*>(t_base + off + 8);
+                const int off = span << 4, lr = off >> sh_S, si = span & ((1 << (sh_H - 1)) - 1);
+                bits = (s_rowm[lr] >> (2 * si)) & 3u;
+                const uint4 bb = *reinterpret_cast<const uint4*>(t_base + off);
+                if (bits == 0u) *reinterpret_cast<uint4*>(obs_e + off) = bb;
+                else if (bits == 2u) *reinterpret_cast<uint2*>(obs_e + off) = make_uint2(bb.x, bb.y);
+                else if (bits == 1u) *reinterpret_cast<uint2*>(obs_e + off + 8) = make_uint2(bb.z, bb.w);
             }
-            const uint32_t b0 = __ballot_sync(0xffffffffu, hit0), b1 = __ballot_sync(0xffffffffu, hit1);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, bits & 1u), b1 = __ballot_sync(0xffffffffu, bits & 2u);
             const uint32_t below = (1u << lane) - 1u;
-            if (hit0) s_list[cnt + __popc(b0 & below)] = (uint16_t)(2 * span);
+            if (bits & 1u) s_list[cnt + __popc(b0 & below)] = (uint16_t)(2 * span);
             cnt += __popc(b0);
-            if (hit1) s_list[cnt + __popc(b1 & below)] = (uint16_t)(2 * span + 1);
+            if (bits & 2u) s_list[cnt + __popc(b1 & below)] = (uint16_t)(2 * span + 1);
             cnt += __popc(b1);
         }
         __syncwarp();

@@ -62,7 +62,7 @@ struct TgWorld {
     // scanline raster (convex parts): tables, the per-env fallback mask + counter, launch shape
     int* d_prim_part = nullptr; double* d_part_cen = nullptr; uint8_t* d_fallback = nullptr; int* d_fb_count = nullptr;
     ScanEnv* d_scan_envs = nullptr;
-    size_t scan_smem = 0; int scan_grid = 0, scan_lpe = 32; bool scan_ok = false;   // d_fb_count: [0] envs handed to raster_kernel, [1 + band] the render kernel's unit counters
+    size_t scan_smem = 0; int scan_grid = 0, scan_lpe = 32, scan_unit_rows = 16; bool scan_ok = false;   // d_fb_count: [0] envs handed to raster_kernel, [1 + band] the render kernel's unit counters
     size_t push_smem = 0;
     int raster_grid = 0;
     int standby_blocks = 0;
@@ -295,6 +295,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             // band tables + half-span skin bitmap + the warps' own tables
             w->scan_smem = ((band_px * 5 + ((band_px / 8 + 31) / 32) * 4 + 15) & ~size_t(15)) + scan_per_warp_smem(S) * SCAN_WARPS;
             w->scan_lpe = np <= 8 ? 8 : (np <= 16 ? 16 : 32);
+            if (const char* ur = getenv("TG_SCAN_UNIT_ROWS")) w->scan_unit_rows = atoi(ur) == 32 ? 32 : 16;   // experiment knob
             int ps = 0;
             CK(cudaFuncSetAttribute(raster_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel, SCAN_THREADS, w->scan_smem));
@@ -512,12 +513,14 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
         if (r.hf) raster_hf_kernel<<<grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
         else if (w->scan_ok) {
             // convex stimulus: scanline raster, then raster_kernel for the envs it flagged (returns at once when there are none)
-            const int band_rows = r.S / r.bands, unit_rows = std::min(SCAN_UNIT_ROWS, band_rows), units_per_band = cnt * (band_rows / unit_rows);
+            const int band_rows = r.S / r.bands, unit_rows = std::min(w->scan_unit_rows, band_rows), units_per_band = cnt * (band_rows / unit_rows);
+            int sh_unit = 0;
+            while ((1 << sh_unit) < unit_rows) sh_unit++;
             const int sgrid = std::min(w->scan_grid, ((units_per_band + SCAN_WARPS - 1) / SCAN_WARPS) * r.bands);
             CK(cudaMemsetAsync(w->d_fb_count, 0, sizeof(int) * (1 + 8), st));
             const int per_blk = 128 / w->scan_lpe;
             scan_setup_kernel<<<(cnt + per_blk - 1) / per_blk, 128, 0, st>>>(r, w->d_prim_part, w->d_part_cen, w->d_scan_envs + e0, w->d_fallback + e0, w->d_fb_count, w->scan_lpe);
-            raster_scan_kernel<<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, w->d_fb_count + 1);
+            raster_scan_kernel<<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, w->d_fb_count + 1, sh_unit);
             w->launches += 2;
             CK(cudaGetLastError());
             RasterArgs r2 = r;
