@@ -22,41 +22,47 @@
 
 #define SCAN_THREADS 1024  // 32 warps per SM: the render kernel is kept under 64 registers (the fp64 face set-up lives in its own kernel)
 #define SCAN_WARPS (SCAN_THREADS / 32)
+#define SCAN_MAXPOOLS 32 // unit counters per band
 #define SCAN_MAXFRONT 8 // front faces per env kept in the interval table (a box shows <= 3, the pole <= 6)
 
 struct ScanFace {
-    double wA, wB, wC;          // 1/z_eye = wA c + wB r + wC on this face's plane (PrimCoef index 4)
-    double es[4], et[4];        // edge i crosses row r at column es[i] r + et[i] (tolerance folded in)
-    double eB[4], eC[4];        // for edges parallel to the rows (eA == 0): inside <=> eB r + eC >= -1e-12
-    int dir[4];                 // +1: columns >= crossing are inside, -1: columns <= crossing, 0: row-parallel edge, 2: unused slot
+    double w[3];                // 1/z_eye = w[0] c + w[1] r + w[2] on this face's plane (PrimCoef index 4)
+    double ea[4], eb[4];        // edge i crosses row r at column ea[i] r + eb[i] (tolerance folded in); for an edge parallel to
+                                // the rows (dir 0) they hold its (eB, eC): inside <=> eB r + eC >= -1e-12
+    signed char dir[4];         // +1: columns >= crossing are inside, -1: columns <= crossing, 0: row-parallel edge, 2: unused slot
     int part;
 };
 
-// what scan_setup_kernel leaves per env for the render kernel
-struct ScanEnv {
+// what scan_setup_kernel leaves per env for the render kernel (800 bytes, fetched per work unit with 16-byte cp.async's)
+struct __align__(16) ScanEnv {
     int nf, c_lo, c_hi, r_lo, r_hi, pad[3]; // front faces; columns / rows any of them can touch (nf < 0: rendered by raster_kernel)
     ScanFace face[SCAN_MAXFRONT];
 };
+static_assert(sizeof(ScanFace) == 96 && sizeof(ScanEnv) == 32 + 96 * SCAN_MAXFRONT && sizeof(ScanEnv) % 16 == 0, "ScanEnv layout");
 
 #define SCAN_UNIT_ROWS 32 // most rows a work unit of the render kernel can have (16 by default, TG_SCAN_UNIT_ROWS)
 
-// per warp of the render kernel: 1/z coefficients of the front faces, their row intervals, the half-span list
-__host__ __device__ inline size_t scan_per_warp_smem(int S)
+// per warp of the render kernel: two ScanEnv buffers (the next unit's is prefetched), the faces' row intervals, the rows' shade
+// masks, the half-span list
+__host__ __device__ inline size_t scan_per_warp_smem(int S, int unit_rows)
 {
-    return (sizeof(double) * 3 * SCAN_MAXFRONT + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS * 2 + SCAN_UNIT_ROWS * 4 + (size_t)SCAN_UNIT_ROWS * S / 8 * 2 + 15) & ~size_t(15);
+    return (2 * sizeof(ScanEnv) + (size_t)SCAN_MAXFRONT * unit_rows * 2 + (size_t)unit_rows * 4 + (size_t)unit_rows * S / 8 * 2 + 15) & ~size_t(15);
 }
+// band tables (nodef f32, baked bytes, half-span skin bitmap) in front of the warps' tables
+__host__ __device__ inline size_t scan_tables_smem(int band_px) { return ((size_t)band_px * 5 + (size_t)((band_px / 8 + 31) / 32) * 4 + 15) & ~size_t(15); }
 
 // one front face, one row: the inclusive column interval [lo, hi] it covers (lo > hi: none)
 __device__ __forceinline__ void scan_interval(const ScanFace& f, int r, int S, int& lo, int& hi)
 {
     lo = 0; hi = S - 1;
     const double dr = (double)r;
+    const int dirs = *reinterpret_cast<const int*>(f.dir);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int d = f.dir[i];
+        const int d = (int)(signed char)(dirs >> (8 * i));
         if (d == 2) continue;
-        if (d == 0) { if (f.eB[i] * dr + f.eC[i] < -1e-12) { lo = 1; hi = 0; } continue; }
-        const double x = fma(f.es[i], dr, f.et[i]);
+        const double x = fma(f.ea[i], dr, f.eb[i]);
+        if (d == 0) { if (x < -1e-12) { lo = 1; hi = 0; } continue; }
         // ceil / floor inside the conversion, which saturates: a crossing far off the image leaves the interval empty or untouched
         if (d > 0) lo = max(lo, __double2int_ru(x));
         else hi = min(hi, __double2int_rd(x));
@@ -68,8 +74,11 @@ __device__ __forceinline__ void scan_interval(const ScanFace& f, int r, int S, i
 // that one stays small in registers and code).
 __global__ void __launch_bounds__(128)
 scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const double* __restrict__ part_cen, ScanEnv* __restrict__ out,
-                  uint8_t* __restrict__ fallback, int* __restrict__ fb_count, int lpe)
+                  uint8_t* __restrict__ fallback, int* __restrict__ fb_count, int* __restrict__ fb_next, int* __restrict__ ctr, int lpe)
 {
+    // house-keeping for the launches behind this one (stream order): the render kernel's unit counters and the fallback counter
+    // of the NEXT raster pass start from zero (this pass counts in `fb_count`, which the previous pass's set-up cleared)
+    if (blockIdx.x == 0) { ctr[threadIdx.x] = 0; if (threadIdx.x == 0) *fb_next = 0; }   // 128 threads = 4 bands x SCAN_MAXPOOLS counters
     const int lane = threadIdx.x & 31, sub = lane & (lpe - 1), gbase = lane - sub;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) / lpe;
     const uint32_t gmask = (lpe == 32 ? 0xffffffffu : ((1u << lpe) - 1u)) << gbase;
@@ -113,20 +122,20 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
             const double h = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
             const double sc = nrm[0] * ce[0] + nrm[1] * ce[1] + nrm[2] * ce[2] - h;
             front = (h > 0.0) == (sc > 0.0) && sc != 0.0;
-            mine.wA = pc.eA[4]; mine.wB = pc.eB[4]; mine.wC = pc.eC[4];
+            mine.w[0] = pc.eA[4]; mine.w[1] = pc.eB[4]; mine.w[2] = pc.eC[4];
             mine.part = part;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                mine.dir[i] = 2; mine.es[i] = 0; mine.et[i] = 0; mine.eB[i] = 0; mine.eC[i] = 0;
+                mine.dir[i] = 2; mine.ea[i] = 0; mine.eb[i] = 0;
                 if (i < nv) {
                     const double A = pc.eA[i], B = pc.eB[i], C = pc.eC[i];
                     if (fabs(A) * (double)S < 1e-9 * (fabs(B) * (double)S + fabs(C) + 1e-300)) {
-                        mine.dir[i] = 0; mine.eB[i] = B; mine.eC[i] = C;         // edge line parallel to the rows
+                        mine.dir[i] = 0; mine.ea[i] = B; mine.eb[i] = C;         // edge line parallel to the rows
                     } else {
                         // A c + B r + C >= -1e-12  <=>  c >= (-1e-12 - C - B r) / A  (A > 0), <= for A < 0
                         const double inv = 1.0 / A;
                         mine.dir[i] = A > 0.0 ? 1 : -1;
-                        mine.es[i] = -B * inv; mine.et[i] = (-1e-12 - C) * inv;
+                        mine.ea[i] = -B * inv; mine.eb[i] = (-1e-12 - C) * inv;
                     }
                 }
             }
@@ -157,86 +166,93 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
 }
 
 // Render kernel.  A CTA owns ONE row band of the image (128 x 128 and smaller: the whole image; 256 x 256: a quarter) and
-// fetches that band's static tables (nodef_dep f32 + baked border bytes) once, by TMA bulk copies into shared memory.  After
-// that its 32 warps run on their own: a work unit is (env, `unit_rows` consecutive rows of the band), handed out through
-// one global counter per band (`ctr[band]`, zeroed by the host before the launch; the next unit is requested before the
-// current one is rendered, so the atomic's latency is hidden) - units that the stimulus does not touch are a plain copy and
-// cost a fraction of the others, and the counter evens that out.  unit_rows (16 or 32) and band_rows / unit_rows are powers of two.
+// fetches that band's static tables (nodef_dep f32, baked border bytes, the half-span skin bitmap) once, by TMA bulk copies
+// into shared memory.  After that its 32 warps run on their own: a work unit is (env, `unit_rows` consecutive rows of the band),
+// handed out through one global counter per band (`ctr[band]`, zeroed by the set-up kernel).  Units the stimulus does not touch
+// are a plain copy and cost a fraction of the others; the counter evens that out.  Both round trips a unit needs - the counter
+// and the env's ScanEnv record - are software-pipelined: while unit i is rendered, unit i+1's record is on its way into the
+// warp's second buffer (cp.async) and the counter is being asked for unit i+2.
+// unit_rows (16 or 32) and band_rows / unit_rows are powers of two.
+template <int sh_unit>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __restrict__ ctr, int sh_unit)
+raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, const uint32_t* __restrict__ skin8, int* __restrict__ ctr, int pools)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S, bands = a.bands, band_rows = S / bands, band_px = band_rows * S;
-    const int unit_rows = 1 << sh_unit, sh_parts = (31 - __clz(band_rows)) - sh_unit;
+    constexpr int unit_rows = 1 << sh_unit;
+    const int sh_parts = (31 - __clz(band_rows)) - sh_unit;
     float* s_nodef = reinterpret_cast<float*>(smem_raw);
     uint8_t* s_base = smem_raw + (size_t)band_px * 4;
     uint32_t* s_skin = reinterpret_cast<uint32_t*>(smem_raw + (size_t)band_px * 5);   // 1 bit per 8-pixel half span of the band: has a non-border pixel
-    const int band_halves = band_px / 8;
+    const int skin_words = (band_px / 8 + 31) / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t wbase = ((size_t)band_px * 5 + (size_t)((band_halves + 31) / 32) * 4 + 15) & ~size_t(15);
-    const size_t per_warp = scan_per_warp_smem(S);
-    double* s_w = reinterpret_cast<double*>(smem_raw + wbase + per_warp * warp);                  // [SCAN_MAXFRONT][3] wA wB wC
-    uchar2* s_iv = reinterpret_cast<uchar2*>(s_w + 3 * SCAN_MAXFRONT);                            // [SCAN_MAXFRONT][unit_rows] (lo, hi)
-    uint32_t* s_rowm = reinterpret_cast<uint32_t*>(s_iv + (size_t)SCAN_MAXFRONT * SCAN_UNIT_ROWS); // [unit_rows] half spans of the row to shade
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_rowm + SCAN_UNIT_ROWS);                      // [unit_rows * S / 8] the same as a list
+    unsigned char* wsm = smem_raw + scan_tables_smem(band_px) + scan_per_warp_smem(S, unit_rows) * warp;
+    ScanEnv* s_env = reinterpret_cast<ScanEnv*>(wsm);                                             // [2]
+    uchar2* s_iv = reinterpret_cast<uchar2*>(wsm + 2 * sizeof(ScanEnv));                          // [SCAN_MAXFRONT][unit_rows] (lo, hi)
+    uint32_t* s_rowm = reinterpret_cast<uint32_t*>(s_iv + (size_t)SCAN_MAXFRONT * unit_rows);     // [unit_rows] half spans of the row to shade
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_rowm + unit_rows);                           // [unit_rows * S / 8] the same as a list
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_one[32];
 
     const int band = blockIdx.x % bands;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        const uint32_t bytes = (uint32_t)band_px * 5u;
+        const uint32_t bytes = (uint32_t)band_px * 5u + (uint32_t)skin_words * 4u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
         tma_bulk_load(s_nodef, a.nodef + (size_t)band * band_px, (uint32_t)band_px * 4u, &bar);
         tma_bulk_load(s_base, a.base + (size_t)band * band_px, (uint32_t)band_px, &bar);
+        tma_bulk_load(s_skin, skin8 + (size_t)band * skin_words, (uint32_t)skin_words * 4u, &bar);
     }
-    // a warp's next unit: lane 0 asks the band's counter; the result register is only read at the top of the next round, so the
-    // atomic's latency is hidden behind the current unit.  ptxas rewrites atomic adds it can prove warp-uniform into its
-    // aggregated form (vote, one atomic, a SHUFFLE OF THE RESULT right behind it - which waits for the whole round trip); an
-    // addend it cannot see through (a 1 read back from shared memory) under a real branch keeps the plain instruction.
-    const int units = a.n << sh_parts;
-    __shared__ int s_one[32];
+    // a warp's next unit: lane 0 asks the band's counter; the result register is only read a round later, so the atomic's
+    // latency is hidden behind the current unit.  ptxas rewrites atomic adds it can prove warp-uniform into its aggregated form
+    // (vote, one atomic, a SHUFFLE OF THE RESULT right behind it - which waits for the whole round trip); an addend it cannot
+    // see through (a 1 read back from shared memory) under a real branch keeps the plain instruction.
+    // One counter for the whole band would see ~0.8 atomics per ns at 4096 envs - which is as fast as one address goes, and was
+    // measured to pin the kernel's duration.  So the band's units are cut into `pools` contiguous slices, each with its own
+    // counter and its own ~8 CTAs (the CTAs of a band take the pools round robin): still hundreds of envs per pool to even out.
+    const int units_band = a.n << sh_parts;
+    const int pool = (blockIdx.x / bands) % pools;
+    const int u_first = (int)(((long long)units_band * pool) / pools), units = (int)(((long long)units_band * (pool + 1)) / pools);
+    int* my_ctr = ctr + band * SCAN_MAXPOOLS + pool;
     if (warp == 0) s_one[lane] = S > 0;
-    __syncthreads();
+    __syncthreads();      // s_one, and the mbarrier's init, are visible to every warp
     const int one = *reinterpret_cast<volatile int*>(&s_one[lane]);
     int u_req = 0;
     auto request = [&]() {
-        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;\n" : "+r"(u_req) : "l"(ctr + band), "r"(one) : "memory");
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;\n" : "+r"(u_req) : "l"(my_ctr), "r"(one) : "memory");
+    };
+    // unit u's env record -> buffer `b` of this warp: 50 16-byte pieces
+    auto fetch = [&](int u, int b) {
+        if (u < units) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(envs + (u >> sh_parts));
+            const uint32_t dst = smem_u32(s_env + b);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + lane * 16u), "l"(src + lane * 16) : "memory");
+            if (lane < (int)(sizeof(ScanEnv) / 16) - 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (lane + 32) * 16u), "l"(src + (lane + 32) * 16) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
     request();
-    __syncthreads();
-    {
-        uint32_t ok = 0;
-        while (!ok) {
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                         : "=r"(ok)
-                         : "r"(smem_u32(&bar)), "r"(0u)
-                         : "memory");
-        }
-    }
-    // skin bitmap of the band's half spans, from the tables just loaded
-    for (int h0 = warp * 32; h0 < band_halves; h0 += SCAN_THREADS) {
-        const int h = h0 + lane;
-        bool skin = false;
-        if (h < band_halves) {
-            const float4 v0 = *reinterpret_cast<const float4*>(s_nodef + (size_t)h * 8), v1 = *reinterpret_cast<const float4*>(s_nodef + (size_t)h * 8 + 4);
-            skin = v0.x >= 0.0f || v0.y >= 0.0f || v0.z >= 0.0f || v0.w >= 0.0f || v1.x >= 0.0f || v1.y >= 0.0f || v1.z >= 0.0f || v1.w >= 0.0f;
-        }
-        const uint32_t bits = __ballot_sync(0xffffffffu, skin);
-        if (lane == 0) s_skin[h0 >> 5] = bits;
-    }
-    __syncthreads();
-    const int sh_S = 31 - __clz(S), sh_H = sh_S - 3;      // S / 8 = 1 << sh_H half spans per row (8, 16 or 32)
+    int u = u_first + __shfl_sync(0xffffffffu, u_req, 0);     // start-up: the one exposed round trip
+    request();
+    fetch(u, 0);
+    const int sh_S = 31 - __clz(S), sh_H = sh_S - 3;      // S / 8 = 1 << sh_H half spans per row (4 .. 32)
     const double Fn = a.F * a.near_;
     const int spans = (unit_rows << sh_S) >> 4;           // 16-pixel spans of one unit
     const uint32_t row_all = sh_H == 5 ? 0xffffffffu : ((1u << (1 << sh_H)) - 1u);
+    bool tables = false;                                  // this thread has seen the band tables arrive
+    int buf = 0;
 
-    for (;;) {
-        const int u = __shfl_sync(0xffffffffu, u_req, 0);
-        if (u >= units) break;
+    for (; u < units; buf ^= 1) {
+        const int u_next = u_first + __shfl_sync(0xffffffffu, u_req, 0);
         request();
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+        fetch(u_next, buf ^ 1);
         const int e = u >> sh_parts, part = u & ((1 << sh_parts) - 1);
-        const ScanEnv& se = envs[e];
+        u = u_next;
+        const ScanEnv& se = s_env[buf];
         const int nf = se.nf;
         if (nf < 0) continue;              // masked-out envs and the ones handed to raster_kernel
         const int trow0 = part << sh_unit, row0 = band * band_rows + trow0;     // first row of the unit in the band's tables / in the image
@@ -244,26 +260,36 @@ raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __
         uint8_t* obs_e = a.obs + (((size_t)e << (2 * sh_S)) + ((size_t)row0 << sh_S));
         const float* t_nodef = s_nodef + ((size_t)trow0 << sh_S);
         const uint8_t* t_base = s_base + ((size_t)trow0 << sh_S);
+        // ---- row intervals of the front faces inside this unit (needs no table: runs under the table fetch in the first round)
+        if (br1 >= br0) {
+            for (int idx = lane; idx < (nf << sh_unit); idx += 32) {
+                const int f = idx >> sh_unit, lr = idx & (unit_rows - 1), r = row0 + lr;
+                int lo = 1, hi = 0;
+                if (r >= br0 && r <= br1) scan_interval(se.face[f], r, S, lo, hi);
+                s_iv[f * unit_rows + lr] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
+            }
+        }
+        if (!tables) {
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(ok)
+                             : "r"(smem_u32(&bar)), "r"(0u)
+                             : "memory");
+            }
+            tables = true;
+        }
         if (br1 < br0) {
             // the stimulus does not reach these rows: the baked bytes
             for (int sp = lane; sp < spans; sp += 32) *reinterpret_cast<uint4*>(obs_e + (sp << 4)) = *reinterpret_cast<const uint4*>(t_base + (sp << 4));
             continue;
         }
         __syncwarp();
-        if (lane < 3 * nf) { const ScanFace& fc = se.face[lane / 3]; s_w[lane] = lane % 3 == 0 ? fc.wA : (lane % 3 == 1 ? fc.wB : fc.wC); }
-        // ---- row intervals of the front faces inside this unit
-        for (int idx = lane; idx < (nf << sh_unit); idx += 32) {
-            const int f = idx >> sh_unit, lr = idx & (unit_rows - 1), r = row0 + lr;
-            int lo = 1, hi = 0;
-            if (r >= br0 && r <= br1) scan_interval(se.face[f], r, S, lo, hi);
-            s_iv[f * SCAN_UNIT_ROWS + lr] = lo <= hi ? make_uchar2((unsigned char)lo, (unsigned char)hi) : make_uchar2(1, 0);
-        }
-        __syncwarp();
         // ---- per row: the half spans between the leftmost and the rightmost covered column that have skin pixels
         if (lane < unit_rows) {
             int ulo = S, uhi = -1;
             for (int f = 0; f < nf; f++) {
-                const uchar2 iv = s_iv[f * SCAN_UNIT_ROWS + lane];
+                const uchar2 iv = s_iv[f * unit_rows + lane];
                 if (iv.x <= iv.y) { ulo = min(ulo, (int)iv.x); uhi = max(uhi, (int)iv.y); }
             }
             uint32_t m = 0;
@@ -311,12 +337,12 @@ raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __
 #pragma unroll
             for (int k = 0; k < 8; k++) pen[k] = -1.0f;
             for (int f = 0; f < nf; f++) {
-                const uchar2 iv = s_iv[f * SCAN_UNIT_ROWS + lr];
+                const uchar2 iv = s_iv[f * unit_rows + lr];
                 const int l = max((int)iv.x - cb, 0), h = min((int)iv.y - cb, 7);
                 if (l > h || iv.x > iv.y) continue;
                 const uint32_t m = (0xffu >> (7 - h)) & (0xffu << l);
-                const double wA = s_w[3 * f];
-                const double w0 = wA * (double)cb + (s_w[3 * f + 1] * (double)r + s_w[3 * f + 2]);
+                const double wA = se.face[f].w[0];
+                const double w0 = wA * (double)cb + (se.face[f].w[1] * (double)r + se.face[f].w[2]);
                 const double dA = -Fn * wA, d0 = a.F - Fn * w0;
 #pragma unroll
                 for (int k = 0; k < 8; k++)
@@ -339,6 +365,16 @@ raster_scan_kernel(const RasterArgs a, const ScanEnv* __restrict__ envs, int* __
             o.x = bres.x | q8[0] | (q8[1] << 8) | (q8[2] << 16) | (q8[3] << 24);
             o.y = bres.y | q8[4] | (q8[5] << 8) | (q8[6] << 16) | (q8[7] << 24);
             *reinterpret_cast<uint2*>(obs_e + off) = o;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (!tables) {       // never leave while the bulk copies into this CTA's shared memory are in flight
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok)
+                         : "r"(smem_u32(&bar)), "r"(0u)
+                         : "memory");
         }
     }
 }

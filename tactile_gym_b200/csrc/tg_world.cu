@@ -61,8 +61,10 @@ struct TgWorld {
     size_t raster_smem = 0;
     // scanline raster (convex parts): tables, the per-env fallback mask + counter, launch shape
     int* d_prim_part = nullptr; double* d_part_cen = nullptr; uint8_t* d_fallback = nullptr; int* d_fb_count = nullptr;
-    ScanEnv* d_scan_envs = nullptr;
-    size_t scan_smem = 0; int scan_grid = 0, scan_lpe = 32, scan_unit_rows = 16; bool scan_ok = false;   // d_fb_count: [0] envs handed to raster_kernel, [1 + band] the render kernel's unit counters
+    ScanEnv* d_scan_envs = nullptr; uint32_t* d_skin8 = nullptr; unsigned raster_pass = 0;
+    // d_fb_count: [0], [1] envs handed to raster_kernel (even / odd passes), [2 + band * SCAN_MAXPOOLS + pool] the render kernel's unit counters
+    // scan_max_pools: unit-counter pools per band - measured no faster than one counter (same-box A/B), kept as the TG_SCAN_POOLS knob
+    size_t scan_smem = 0; int scan_grid = 0, scan_lpe = 32, scan_unit_rows = 16, scan_max_pools = 1; bool scan_ok = false;
     size_t push_smem = 0;
     int raster_grid = 0;
     int standby_blocks = 0;
@@ -289,16 +291,28 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             for (int i = 0; i < np; i++)
                 if (cfg->sensor.h_prim_part[i] < 0 || cfg->sensor.h_prim_part[i] >= cfg->sensor.n_parts) return fail(TG_EINVAL, "h_prim_part[%d] out of range", i);
             if ((rc = dalloc(w, &w->d_prim_part, np)) || (rc = dalloc(w, &w->d_part_cen, (size_t)3 * cfg->sensor.n_parts)) ||
-                (rc = dalloc(w, &w->d_fallback, n)) || (rc = dalloc(w, &w->d_fb_count, 1 + 8)) || (rc = dalloc(w, &w->d_scan_envs, n))) return rc;
+                (rc = dalloc(w, &w->d_fallback, n)) || (rc = dalloc(w, &w->d_fb_count, 2 + 4 * SCAN_MAXPOOLS)) || (rc = dalloc(w, &w->d_scan_envs, n))) return rc;
             CK(cudaMemcpy(w->d_prim_part, cfg->sensor.h_prim_part, sizeof(int) * np, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(w->d_part_cen, cfg->sensor.h_part_centroid, sizeof(double) * 3 * cfg->sensor.n_parts, cudaMemcpyHostToDevice));
             // band tables + half-span skin bitmap + the warps' own tables
-            w->scan_smem = ((band_px * 5 + ((band_px / 8 + 31) / 32) * 4 + 15) & ~size_t(15)) + scan_per_warp_smem(S) * SCAN_WARPS;
-            w->scan_lpe = np <= 8 ? 8 : (np <= 16 ? 16 : 32);
             if (const char* ur = getenv("TG_SCAN_UNIT_ROWS")) w->scan_unit_rows = atoi(ur) == 32 ? 32 : 16;   // experiment knob
+            if (const char* mp = getenv("TG_SCAN_POOLS")) w->scan_max_pools = std::max(1, std::min(SCAN_MAXPOOLS, atoi(mp)));
+            const int unit_rows = std::min(w->scan_unit_rows, S / r.bands);
+            w->scan_smem = scan_tables_smem((int)band_px) + scan_per_warp_smem(S, unit_rows) * SCAN_WARPS;
+            {
+                // 1 bit per 8-pixel half span, band by band: has a non-border pixel
+                const size_t words = (band_px / 8 + 31) / 32;
+                std::vector<uint32_t> bits(words * r.bands, 0u);
+                for (size_t i = 0; i < px; i++)
+                    if (nd[i] >= 0.0f) { const size_t bnd = i / band_px, h = (i % band_px) / 8; bits[bnd * words + h / 32] |= 1u << (h % 32); }
+                if ((rc = dalloc(w, &w->d_skin8, bits.size()))) return rc;
+                CK(cudaMemcpy(w->d_skin8, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+            }
+            w->scan_lpe = np <= 8 ? 8 : (np <= 16 ? 16 : 32);
             int ps = 0;
-            CK(cudaFuncSetAttribute(raster_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel, SCAN_THREADS, w->scan_smem));
+            CK(cudaFuncSetAttribute(raster_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
+            CK(cudaFuncSetAttribute(raster_scan_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->scan_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, raster_scan_kernel<4>, SCAN_THREADS, w->scan_smem));
             if (ps >= 1) {
                 w->scan_grid = w->sm_count * ps;
                 w->scan_grid -= w->scan_grid % r.bands;   // the same number of CTAs on every band
@@ -517,15 +531,21 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
             int sh_unit = 0;
             while ((1 << sh_unit) < unit_rows) sh_unit++;
             const int sgrid = std::min(w->scan_grid, ((units_per_band + SCAN_WARPS - 1) / SCAN_WARPS) * r.bands);
-            CK(cudaMemsetAsync(w->d_fb_count, 0, sizeof(int) * (1 + 8), st));
+            // d_fb_count: [0], [1] the fallback counters of even / odd raster passes, [2 + band] the render kernel's unit counters.
+            // No memset: a pass's set-up kernel clears the unit counters and the NEXT pass's fallback counter (stream order)
+            int* fb = w->d_fb_count + (w->raster_pass & 1u);
+            int* fb_next = w->d_fb_count + ((w->raster_pass + 1u) & 1u);
+            w->raster_pass++;
             const int per_blk = 128 / w->scan_lpe;
-            scan_setup_kernel<<<(cnt + per_blk - 1) / per_blk, 128, 0, st>>>(r, w->d_prim_part, w->d_part_cen, w->d_scan_envs + e0, w->d_fallback + e0, w->d_fb_count, w->scan_lpe);
-            raster_scan_kernel<<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, w->d_fb_count + 1, sh_unit);
+            scan_setup_kernel<<<(cnt + per_blk - 1) / per_blk, 128, 0, st>>>(r, w->d_prim_part, w->d_part_cen, w->d_scan_envs + e0, w->d_fallback + e0, fb, fb_next, w->d_fb_count + 2, w->scan_lpe);
+            const int pools = std::max(1, std::min(w->scan_max_pools, (sgrid / r.bands) / 8));
+            if (sh_unit == 5) raster_scan_kernel<5><<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, w->d_skin8, w->d_fb_count + 2, pools);
+            else raster_scan_kernel<4><<<sgrid, SCAN_THREADS, w->scan_smem, st>>>(r, w->d_scan_envs + e0, w->d_skin8, w->d_fb_count + 2, pools);
             w->launches += 2;
             CK(cudaGetLastError());
             RasterArgs r2 = r;
             r2.mask = w->d_fallback + e0;
-            raster_kernel<<<grid, RASTER_THREADS, w->raster_smem, st>>>(r2, w->d_fb_count);
+            raster_kernel<<<grid, RASTER_THREADS, w->raster_smem, st>>>(r2, fb);
         } else raster_kernel<<<grid, RASTER_THREADS, w->raster_smem, st>>>(r, nullptr);
     }
     w->launches++;
