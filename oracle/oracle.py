@@ -457,8 +457,9 @@ class ObjectBalanceOracle:
     solver residual (<= 3e-4 rad/s over <= 10 substeps, < 1e-5 rad) and is what makes resets independent of history."""
 
     def __init__(self, image_size=256, sensor="tactip", max_steps=250, movement_mode="xy", rand_gravity=True,
-                 rand_embed_dist=True, seed=None):
+                 rand_embed_dist=True, seed=None, control_mode="TCP_velocity_control"):
         self.S, self.sensor, self.max_steps, self.movement_mode = image_size, sensor, max_steps, movement_mode
+        self.control_mode = control_mode
         self.rand_gravity, self.rand_embed_dist = rand_gravity, rand_embed_dist
         self.workframe_pos = np.array([0.55, 0.0, 0.35]); self.workframe_rpy = np.zeros(3)
         lims = np.zeros((6, 2))
@@ -536,15 +537,20 @@ class ObjectBalanceOracle:
         enc[idx] = a
         enc = np.clip(enc, -0.25, 0.25)
         mv, ma = 0.01, 5.0 * (np.pi / 180)
+        if self.control_mode == "TCP_position_control":   # object_balance_env.py:129-139: m / rad per step
+            mv, ma = 0.001, 1 * (np.pi / 180)
         amax = np.array([mv, mv, mv, ma, ma, 0.0]); amin = -amax
         return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
 
     def step(self, action):
         v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
         self.steps += 1
-        lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
-        for _ in range(self.repeat):
-            lib().or_step_sim_obj(C.byref(self.m), C.byref(self.s), C.byref(self.o))
+        if self.control_mode == "TCP_position_control":   # robot.py:156-186, _max_blocking_pos_move_steps = 10 (object_balance_env.py:36)
+            self.last_move_substeps = lib().or_tcp_position_control_world(C.byref(self.m), C.byref(self.s), C.byref(self.o), None, _dptr(v), C.c_int(10))
+        else:
+            lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
+            for _ in range(self.repeat):
+                lib().or_step_sim_obj(C.byref(self.m), C.byref(self.s), C.byref(self.o))
         self.reward, self.done = self.step_data()
         return self.observation(), self.reward, self.done, {}
 
@@ -836,9 +842,10 @@ class ObjectPushOracle:
     the cube in the world (the reference repositions the arm with the previous episode's cube still lying around)."""
 
     def __init__(self, image_size=128, arm="mg400", sensor="digitac", max_steps=1000, movement_mode="TyRz", traj_type="simplex",
-                 rand_init_orn=False, rand_obj_mass=False, reward_mode="dense", seed=None):
+                 rand_init_orn=False, rand_obj_mass=False, reward_mode="dense", seed=None, control_mode="TCP_velocity_control"):
         self.S, self.arm, self.sensor, self.max_steps = image_size, arm, sensor, max_steps
         self.movement_mode, self.traj_type, self.reward_mode = movement_mode, traj_type, reward_mode
+        self.control_mode = control_mode
         self.rand_init_orn, self.rand_obj_mass = rand_init_orn, rand_obj_mass
         self.typ = "right_angle"
         self.obj_w = self.obj_h = 0.08
@@ -1010,15 +1017,20 @@ class ObjectPushOracle:
                 enc[0] += pe[0] + pa[0]; enc[1] += pe[1] + pa[1]; enc[5] += a[2]
         enc = np.clip(enc, -0.25, 0.25)
         mv, ma = 0.01, 5.0 * (np.pi / 180)
+        if self.control_mode == "TCP_position_control":   # object_push_env.py:137-147: m / rad per step
+            mv, ma = 0.001, 1 * (np.pi / 180)
         amax = np.array([mv, mv, 0.0, 0.0, 0.0, ma]); amin = -amax
         return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
 
     def step(self, action):
         v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
         self.steps += 1
-        lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
-        for _ in range(self.repeat):
-            lib().or_step_sim_push(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p))
+        if self.control_mode == "TCP_position_control":   # robot.py:156-186, _max_blocking_pos_move_steps = 10 (object_push_env.py:39)
+            self.last_move_substeps = lib().or_tcp_position_control_world(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p), _dptr(v), C.c_int(10))
+        else:
+            lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
+            for _ in range(self.repeat):
+                lib().or_step_sim_push(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p))
         self.reward, self.done = self.step_data()
         return self.observation(), self.reward, self.done, {}
 
@@ -1052,8 +1064,9 @@ class ObjectRollOracle:
     marble in the world; the semi-transparent goal indicator is not drawn (as for the other tasks)."""
 
     def __init__(self, image_size=128, sensor="tactip", max_steps=250, movement_mode="xy", rand_obj_size=False, rand_embed_dist=False,
-                 rand_init_obj_pos=False, reward_mode="dense", seed=None):
+                 rand_init_obj_pos=False, reward_mode="dense", seed=None, control_mode="TCP_velocity_control"):
         self.S, self.sensor, self.max_steps, self.movement_mode, self.reward_mode = image_size, sensor, max_steps, movement_mode, reward_mode
+        self.control_mode = control_mode
         self.rand_obj_size, self.rand_embed_dist, self.rand_init_obj_pos = rand_obj_size, rand_embed_dist, rand_init_obj_pos
         self.typ = "flat"
         self.default_obj_radius = 0.0025
@@ -1150,15 +1163,18 @@ class ObjectRollOracle:
         enc = np.zeros(6); a = np.asarray(action, dtype=np.float64)
         enc[0], enc[1] = a[0], a[1]
         enc = np.clip(enc, -0.25, 0.25)
-        mv = 0.01
+        mv = 0.001 if self.control_mode == "TCP_position_control" else 0.01   # object_roll_env.py:112-139
         amax = np.array([mv, mv, 0.0, 0.0, 0.0, 0.0]); amin = -amax
         return (((enc - (-0.25)) * (amax - amin)) / 0.5) + amin
 
     def step(self, action):
         v = np.ascontiguousarray(self.encode_scale(action), dtype=np.float64)
         self.steps += 1
-        lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
-        for _ in range(self.repeat):
-            lib().or_step_sim_push(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p))
+        if self.control_mode == "TCP_position_control":   # robot.py:156-186, _max_blocking_pos_move_steps = 10 (object_roll_env.py:37)
+            self.last_move_substeps = lib().or_tcp_position_control_world(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p), _dptr(v), C.c_int(10))
+        else:
+            lib().or_tcp_velocity_control(C.byref(self.m), C.byref(self.s), _dptr(v))
+            for _ in range(self.repeat):
+                lib().or_step_sim_push(C.byref(self.m), C.byref(self.s), C.byref(self.o), C.byref(self.p))
         self.reward, self.done = self.step_data()
         return self.observation(), self.reward, self.done, {}

@@ -916,7 +916,10 @@ void or_tcp_position_target(const OrModel* m, const double* q, const double delt
     or_quat_from_euler(trpy, targ_orn);
 }
 
-int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_work[6], int max_steps)
+/* Robot.apply_action(control_mode="TCP_position_control") (robot.py:156-186): tcp_position_control (base_robot_arm.py:228-279) then
+ * blocking_move(max_steps, constant_vel=None) (robot.py:188-260).  The world stepped inside the blocking move is the env's:
+ * arm only (o == NULL), arm + constrained object (object_balance: P == NULL), arm + cube / marble with contacts (P != NULL). */
+int or_tcp_position_control_world(const OrModel* m, OrState* s, OrObject* o, OrPush* P, const double delta_work[6], int max_steps)
 {
     int n = m->ndof;
     double tpos[3], targ_orn[4], targ_j[OR_MAXD];
@@ -931,14 +934,21 @@ int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_wor
     }
     int steps = 0;
     for (int it = 0; it < max_steps; it++) {
-        double P[OR_MAXL][3], Q[OR_MAXL][4], curqd[OR_MAXD];
-        or_link_states(m, s->q, P, Q);
+        double Pl[OR_MAXL][3], Q[OR_MAXL][4], curqd[OR_MAXD];
+        or_link_states(m, s->q, Pl, Q);
         for (int i = 0; i < n; i++) curqd[i] = s->qd[i];
-        or_step_sim(m, s);
+        if (o && P) or_step_sim_push(m, s, o, P);
+        else if (o) or_step_sim_obj(m, s, o);
+        else or_step_sim(m, s);
         steps++;
-        if (or_blocking_reached(tpos, targ_orn, P[m->tcp_link], Q[m->tcp_link], curqd, n)) break;
+        if (or_blocking_reached(tpos, targ_orn, Pl[m->tcp_link], Q[m->tcp_link], curqd, n)) break;
     }
     return steps;
+}
+
+int or_tcp_position_control(const OrModel* m, OrState* s, const double delta_work[6], int max_steps)
+{
+    return or_tcp_position_control_world(m, s, NULL, NULL, delta_work, max_steps);
 }
 
 /* ------------------------------------------------------------------ tactile raster */

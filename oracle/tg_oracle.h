@@ -208,6 +208,8 @@ typedef struct {
 } OrPush;
 /* Robot.step_sim() with the cube in the world: gravity compensation + stepSimulation (motor + contact rows) */
 void or_step_sim_push(const OrModel* m, OrState* s, OrObject* cube, OrPush* p);
+/* TCP_position_control's blocking move in the env's own world: o / p NULL = arm only, p NULL = arm + constrained object */
+int or_tcp_position_control_world(const OrModel* m, OrState* s, OrObject* o, OrPush* p, const double delta_work[6], int max_steps);
 /* object_roll tactile image: analytic sphere composited over nodef_dep, then the t_s_camera post-process */
 void or_tactile_image_sphere(const OrModel* m, const double* q, int S, const double centre[3], double radius,
                              const float* nodef_dep, const float* nodef_gray, const unsigned char* border_mask,

@@ -867,25 +867,27 @@ TGD void standby_role(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
 // frame, solved by IK from the current joints, held by position motors - then blocking_move(max_steps, constant_vel=None)
 // (robot.py:188-260): step until pose error and joint speed, both read BEFORE the step, pass.  Out of line: the velocity
 // mode's registers stay what they were.
+// the IK target of tcp_position_control and the joint targets it leads to; `wf` = the work frame's origin (object_roll moves
+// it with the marble's size every episode, the other tasks pass task.workframe_pos)
 template <class T>
-__device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhysics& ph, const TgTask& task, double* q, double* qd, const double* delta)
+__device__ __noinline__ void position_control_target(const TgArm& arm, const TgTask& task, const double* wf, const double* q, const double* delta,
+                                                     Motors<T::NB>& mot, double* tpos, double* torn)
 {
     constexpr int NB = T::NB;
-    double tpos[3], torn[4];
-    Motors<NB> mot;
-    mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
     {
         Kin<NB> k;
         fk<T>(arm, q, k);
         double tp[3], tq[4], wp[3], wr[3], np_[3], nr[3];
         tcp_world<T>(arm, k, tp, tq);
-        world_to_work(task, tp, tq, wp, wr);
+        world_to_work_at(task, wf, tp, tq, wp, wr);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             np_[c] = fmin(fmax(wp[c] + delta[c], task.tcp_lims[c][0]), task.tcp_lims[c][1]);
             nr[c] = fmin(fmax(wr[c] + delta[3 + c], task.tcp_lims[3 + c][0]), task.tcp_lims[3 + c][1]);
         }
         work_to_world(task, np_, nr, tpos, torn);
+#pragma unroll
+        for (int c = 0; c < 3; c++) tpos[c] += wf[c] - task.workframe_pos[c];
     }
 #pragma unroll
     for (int i = 0; i < NB; i++) { mot.target_pos[i] = q[i]; mot.target_vel[i] = 0.0; }
@@ -896,24 +898,50 @@ __device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhy
         mot.target_pos[NB - 2] = -mot.target_pos[1];
         mot.target_pos[NB - 1] = mot.target_pos[1] + mot.target_pos[2];
     }
+}
+
+// blocking_move's exit test (robot.py:222-245) on the TCP pose and the joint speeds read BEFORE the step
+template <class T>
+TGD bool position_control_reached(const TgArm& arm, const double (&sc)[T::NB][2], const double* qd, const double* tpos, const double* torn)
+{
+    constexpr int NB = T::NB;
+    double tp[3], tq[4], tot = 0.0;
+    {
+        Kin<NB> k;
+        fk_sc<T>(arm, sc, k);
+        tcp_world<T>(arm, k, tp, tq);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) tot += fabs(qd[i]);
+    const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
+    const double ip = torn[0] * tq[0] + torn[1] * tq[1] + torn[2] * tq[2] + torn[3] * tq[3];
+    const double oe = acos(fmin(fmax(2 * ip * ip - 1, -1.0), 1.0));
+    return pe < 2e-4 && oe < 1e-3 && tot < 0.1;
+}
+
+// Robot.apply_action(control_mode="TCP_position_control") (robot.py:156-186): tcp_position_control (base_robot_arm.py:228-279:
+// work-frame pose + delta, check_TCP_pos_lims, IK from the current joints, position motors at the env's max force), then
+// blocking_move(max_steps=_max_blocking_pos_move_steps, constant_vel=None) (robot.py:188-260): step until pose error and joint
+// speed, both read BEFORE the step, pass.  Out of line: the velocity mode's registers stay what they were.  `ob`: the
+// constrained object of object_balance (enabled) steps with the arm.
+template <class T>
+__device__ __noinline__ void position_control_move(const TgArm& arm, const TgPhysics& ph, const TgTask& task, double* q, double* qd, const double* delta,
+                                                   ObjState* ob)
+{
+    constexpr int NB = T::NB;
+    double tpos[3], torn[4];
+    Motors<NB> mot;
+    mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
+    position_control_target<T>(arm, task, task.workframe_pos, q, delta, mot, tpos, torn);
     double sc[NB][2];
 #pragma unroll
     for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
 #pragma unroll 1
     for (int s = 0; s < task.pos_max_steps; s++) {
-        double tp[3], tq[4], tot = 0.0;
-        {
-            Kin<NB> k;
-            fk_sc<T>(arm, sc, k);
-            tcp_world<T>(arm, k, tp, tq);
-        }
-#pragma unroll
-        for (int i = 0; i < NB; i++) tot += fabs(qd[i]);
-        substep<T>(arm, ph, q, qd, sc, mot);
-        const double pe = fabs(tpos[0] - tp[0]) + fabs(tpos[1] - tp[1]) + fabs(tpos[2] - tp[2]);
-        const double ip = torn[0] * tq[0] + torn[1] * tq[1] + torn[2] * tq[2] + torn[3] * tq[3];
-        const double oe = acos(fmin(fmax(2 * ip * ip - 1, -1.0), 1.0));
-        if (pe < 2e-4 && oe < 1e-3 && tot < 0.1) break;
+        const bool reached = position_control_reached<T>(arm, sc, qd, tpos, torn);
+        if (ob) substep_obj<T>(arm, ph, task, q, qd, sc, mot, *ob);
+        else substep<T>(arm, ph, q, qd, sc, mot);
+        if (reached) break;
     }
 }
 
@@ -1112,7 +1140,10 @@ TGD void env_epilogue(const TgArm& arm, const TgPhysics& ph, const TgTask& task,
     env_epilogue_core<T, TASK>(arm, ph, task, b, e, q, qd, tp, tq, cam, ob, reward, done, autoreset);
 }
 
-template <class T, int TASK>
+// POSCTL: object_push / object_roll compile their TCP_position_control step as its own kernel (with the blocking-move loop
+// behind a run-time branch the velocity-control step of config 4 was measured 6 % slower, same-box A/B); the other tasks
+// branch at run time on task.control_mode (their position-control move is one out-of-line call).
+template <class T, int TASK, bool POSCTL = false>
 __global__ void __launch_bounds__((TASK == TG_TASK_OBJECT_PUSH || TASK == TG_TASK_OBJECT_ROLL) ? PUSH_THREADS : 128)
 step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics ph, const __grid_constant__ TgTask task,
             EnvBuffers b, const float* __restrict__ actions, float* __restrict__ reward, unsigned char* __restrict__ done, int autoreset)
@@ -1155,16 +1186,40 @@ step_kernel(const __grid_constant__ TgArm arm, const __grid_constant__ TgPhysics
         for (int i = 0; i < NB; i++) sincos(q[i], &sc[i][0], &sc[i][1]);
         if (push) {
             if (owner) obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], 0.0, task, ob);
+            if (POSCTL) {
+                // TCP_position_control with the cube / marble in the world: the blocking move's steps are whole-warp substeps, so
+                // the warp loops until its last env has reached its target (or used its pos_max_steps); lanes that are through
+                // only help in the hull scan from then on (substep_push returns before touching the state of a non-owner)
+                double tpos[3] = {0, 0, 0}, torn[4] = {0, 0, 0, 1};
+                if (owner) {
+                    mot.mode = 1; mot.kp = ph.pos_gain; mot.kd = ph.vel_gain; mot.max_force = ph.max_force;
+                    double wf[3] = {task.workframe_pos[0], task.workframe_pos[1], task.workframe_pos[2]};
+                    if (roll) wf[2] = b.obj_ext[(size_t)e * 4 + 1];   // this episode's work frame
+                    position_control_target<T>(arm, task, wf, q, v, mot, tpos, torn);
+                }
+                bool moving = owner;
 #pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col, owner); // whole warp
+                for (int s = 0; s < task.pos_max_steps; s++) {
+                    if (!__any_sync(0xffffffffu, moving)) break;
+                    const bool reached = moving && position_control_reached<T>(arm, sc, qd, tpos, torn);
+                    substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col, moving);
+                    if (reached) moving = false;
+                }
+            } else {
+#pragma unroll 1
+                for (int s = 0; s < ph.substeps; s++) substep_push<T>(arm, ph, task, b.hull, b.n_hull, q, qd, sc, mot, ob, col, owner); // whole warp
+            }
             if (owner) obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
         } else if (balance) {
             obj_load(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, b.grav[e], b.embed[e], task, ob);
+            if (task.control_mode == 1) position_control_move<T>(arm, ph, task, q, qd, v, &ob);
+            else {
 #pragma unroll 1
-            for (int s = 0; s < ph.substeps; s++) substep_obj<T>(arm, ph, task, q, qd, sc, mot, ob);
+                for (int s = 0; s < ph.substeps; s++) substep_obj<T>(arm, ph, task, q, qd, sc, mot, ob);
+            }
             obj_store(b.obj + (size_t)e * 13, b.obj_ext + (size_t)e * 4, ob);
         } else if (task.control_mode == 1) {
-            position_control_move<T>(arm, ph, task, q, qd, v);
+            position_control_move<T>(arm, ph, task, q, qd, v, nullptr);
         } else {
 #pragma unroll 1
             for (int s = 0; s < ph.substeps; s++) substep<T>(arm, ph, q, qd, sc, mot);

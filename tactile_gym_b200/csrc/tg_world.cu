@@ -198,6 +198,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         w->standby_blocks = 0;
         w->push_smem = sizeof(double) * PushLayout<TopoChain6>::SLOTS * PUSH_BLOCK;
         CK(cudaFuncSetAttribute(step_kernel<TopoChain6, TG_TASK_OBJECT_ROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
+        CK(cudaFuncSetAttribute(step_kernel<TopoChain6, TG_TASK_OBJECT_ROLL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
     }
     if (cfg->task.task == TG_TASK_OBJECT_PUSH) {
         // object_push steps PUSH_BLOCK envs per block with its constraint rows in dynamic shared memory (tg_push.cuh);
@@ -206,9 +207,11 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         if (cfg->arm.topo == TG_TOPO_MG400) {
             w->push_smem = sizeof(double) * PushLayout<TopoMG400>::SLOTS * PUSH_BLOCK;
             CK(cudaFuncSetAttribute(step_kernel<TopoMG400, TG_TASK_OBJECT_PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
+            CK(cudaFuncSetAttribute(step_kernel<TopoMG400, TG_TASK_OBJECT_PUSH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
         } else {
             w->push_smem = sizeof(double) * PushLayout<TopoChain6>::SLOTS * PUSH_BLOCK;
             CK(cudaFuncSetAttribute(step_kernel<TopoChain6, TG_TASK_OBJECT_PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
+            CK(cudaFuncSetAttribute(step_kernel<TopoChain6, TG_TASK_OBJECT_PUSH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->push_smem));
         }
     }
     if (cfg->task.task == TG_TASK_SURFACE_FOLLOW) {
@@ -565,12 +568,14 @@ static int launch_reset(TgWorld* w, const uint8_t* mask, cudaStream_t st)
 // step kernels are specialised per (topology, task)
 #define STEP_LAUNCH(Topo, TASK, grid, block, smem) \
     step_kernel<Topo, TASK><<<grid, block, smem, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done, autoreset)
+#define STEP_LAUNCH_P(Topo, TASK) \
+    step_kernel<Topo, TASK, true><<<pgrid, PUSH_THREADS, w->push_smem, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, w->eb, d_actions, d_reward, d_done, autoreset)
 #define STEP_DISPATCH(Topo)                                                                               \
     switch (w->cfg.task.task) {                                                                           \
     case TG_TASK_OBJECT_BALANCE: STEP_LAUNCH(Topo, TG_TASK_OBJECT_BALANCE, grid, 128, 0); break;          \
     case TG_TASK_SURFACE_FOLLOW: STEP_LAUNCH(Topo, TG_TASK_SURFACE_FOLLOW, grid, 128, 0); break;          \
-    case TG_TASK_OBJECT_PUSH: STEP_LAUNCH(Topo, TG_TASK_OBJECT_PUSH, pgrid, PUSH_THREADS, w->push_smem); break; \
-    case TG_TASK_OBJECT_ROLL: STEP_LAUNCH(Topo, TG_TASK_OBJECT_ROLL, pgrid, PUSH_THREADS, w->push_smem); break; \
+    case TG_TASK_OBJECT_PUSH: if (posctl) STEP_LAUNCH_P(Topo, TG_TASK_OBJECT_PUSH); else STEP_LAUNCH(Topo, TG_TASK_OBJECT_PUSH, pgrid, PUSH_THREADS, w->push_smem); break; \
+    case TG_TASK_OBJECT_ROLL: if (posctl) STEP_LAUNCH_P(Topo, TG_TASK_OBJECT_ROLL); else STEP_LAUNCH(Topo, TG_TASK_OBJECT_ROLL, pgrid, PUSH_THREADS, w->push_smem); break; \
     default: STEP_LAUNCH(Topo, TG_TASK_EDGE_FOLLOW, grid, 128, 0); break;                                 \
     }
 
@@ -592,6 +597,7 @@ static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint
     }
     const dim3 grid(w->eb.step_blocks + w->standby_blocks); // the extra blocks recompute consumed standbys meanwhile
     const dim3 pgrid((w->n + PUSH_BLOCK - 1) / PUSH_BLOCK);  // object_push: PUSH_BLOCK envs per block, rows in shared memory
+    const bool posctl = w->cfg.task.control_mode == 1;
     if (w->cfg.arm.topo == TG_TOPO_MG400) { STEP_DISPATCH(TopoMG400) } else { STEP_DISPATCH(TopoChain6) }
     w->launches++;
     CK(cudaGetLastError());

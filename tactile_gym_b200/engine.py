@@ -200,8 +200,6 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
     if env_modes.get("object_mode", "pole") != "pole":
         raise NotImplementedError("object_mode %r: only 'pole' is built" % env_modes.get("object_mode"))
-    if env_modes["control_mode"] != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: TCP_position_control is built for edge_follow / surface_follow only (SURVEY 8(f) item 4)" % env_modes["control_mode"])
     if arm_type != "ur5":
         raise ValueError("object_balance has rest poses for the ur5 only among the built arms (rest_poses.py)")
     typ, S = "standard", int(image_size[0])
@@ -220,7 +218,10 @@ def object_balance_config(env_modes, image_size, max_steps, n_envs, lanes_per_wa
     for k in range(6):
         t.act_index[k] = idx[k] if k < len(idx) else -1
     t.act_min, t.act_max = -0.25, 0.25
+    t.control_mode, t.pos_max_steps = _control_mode(env_modes, arm_type)                          # :36: _max_blocking_pos_move_steps = 10
     mv, ma = 0.01, 5.0 * (np.pi / 180)                                                          # :141-151
+    if t.control_mode == 1:                                                                      # :129-139: m / rad per step
+        mv, ma = 0.001, 1 * (np.pi / 180)
     hi = [mv, mv, mv, ma, ma, 0.0]
     for k in range(6):
         t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
@@ -419,8 +420,6 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     as a TgConfig.  Returns (cfg, keepalive, draw_fn)."""
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
     movement_mode, traj_type = env_modes["movement_mode"], env_modes.get("traj_type", "simplex")
-    if env_modes["control_mode"] != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: TCP_position_control is built for edge_follow / surface_follow only (SURVEY 8(f) item 4)" % env_modes["control_mode"])
     if arm_type not in ("ur5", "mg400"):
         raise ValueError("Incorrect arm type specified {}".format(arm_type))
     if traj_type not in ("simplex", "straight"):
@@ -447,7 +446,10 @@ def object_push_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     for k in range(6):
         t.act_index[k] = idx[k] if k < len(idx) else -1
     t.act_min, t.act_max = -0.25, 0.25
+    t.control_mode, t.pos_max_steps = _control_mode(env_modes, arm_type)                          # :39: _max_blocking_pos_move_steps = 10
     mv, ma = 0.01, 5.0 * (np.pi / 180)                                                          # :150-160
+    if t.control_mode == 1:                                                                      # :137-147: m / rad per step
+        mv, ma = 0.001, 1 * (np.pi / 180)
     hi = [mv, mv, 0.0, 0.0, 0.0, ma]
     for k in range(6):
         t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
@@ -542,8 +544,6 @@ def object_roll_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     """ObjectRollEnv.__init__ (rl_envs/nonprehensile_manipulation/object_roll/object_roll_env.py:23-104) + BaseObjectEnv as a
     TgConfig.  Returns (cfg, keepalive, draw_fn)."""
     arm_type, sensor = env_modes["arm_type"], env_modes["tactile_sensor_name"]
-    if env_modes["control_mode"] != "TCP_velocity_control":
-        raise NotImplementedError("control_mode %r: TCP_position_control is built for edge_follow / surface_follow only (SURVEY 8(f) item 4)" % env_modes["control_mode"])
     if env_modes["movement_mode"] != "xy":
         raise ValueError("Incorrect movement_mode specified: {}".format(env_modes["movement_mode"]))      # :288-297 knows "xy" only
     if arm_type != "ur5":
@@ -564,7 +564,8 @@ def object_roll_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=
     for k in range(6):
         t.act_index[k] = [0, 1][k] if k < 2 else -1                                              # :288-297
     t.act_min, t.act_max = -0.25, 0.25
-    mv = 0.01                                                                                    # :129-139
+    t.control_mode, t.pos_max_steps = _control_mode(env_modes, arm_type)                          # :37: _max_blocking_pos_move_steps = 10
+    mv = 0.001 if t.control_mode == 1 else 0.01                                                  # :112-139
     hi = [mv, mv, 0.0, 0.0, 0.0, 0.0]
     for k in range(6):
         t.act_lo[k], t.act_hi[k] = -hi[k], hi[k]
