@@ -251,8 +251,20 @@ int tg_set_rng_state(TgWorld* w, const uint32_t* h_key, const int32_t* h_pos);
 int tg_draws_poll(TgWorld* w, int32_t* h_counts, void* stream);
 int tg_draws_upload(TgWorld* w, const double* h_ring, const int32_t* h_avail, void* stream);
 /* Sticky error flags (0: none).  bit 0: reset pipeline / heightfield raster overflow; bit 1: a reset found no draw left in the
- * ring (it used TgTask.draw_default): the host fell behind with tg_draws_upload.  Synchronises. */
+ * ring (it used TgTask.draw_default): the host fell behind with tg_draws_upload; bit 2: an env step ended in a non-finite
+ * state (see tg_nan_resets).  Synchronises. */
 int tg_pipeline_error(TgWorld* w, void* stream);
+/* Per-env NaN / inf guard: env steps so far whose state came out non-finite.  Such a step reports done = 1,
+ * reward = 0 and - under auto-reset - the env starts its next episode like after any other episode end.  Synchronises. */
+int tg_nan_resets(TgWorld* w, void* stream);
+
+/* Full checkpoint / resume: every device buffer of the world - live state, pre-computed next episodes and
+ * partial rebuilds, both heightfields, per-env RNG states, the draw ring, counters.  After tg_checkpoint_load into a world
+ * created from the same TgConfig the following steps reproduce the original run bit for bit.  (tg_get_state / tg_set_state
+ * carry the live episode only: test and debugging hooks.)  The caller's output buffers are its own to save. */
+size_t tg_checkpoint_bytes(const TgWorld* w);
+int tg_checkpoint_save(TgWorld* w, void* h_blob, size_t bytes, void* stream);
+int tg_checkpoint_load(TgWorld* w, const void* h_blob, size_t bytes, void* stream);
 /* Number of episode ends so far that found their pre-computed next episode unfinished and completed it inline
  * (exact either way; a performance counter: episodes shorter than the ~8 launches a rebuild takes).  Synchronises. */
 int tg_pipeline_stalls(TgWorld* w, void* stream);

@@ -98,7 +98,7 @@ class TgHostStep(C.Structure):
 
 
 EXPORTS = [
-    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_set_rng_state", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
+    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_set_rng_state", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_nan_resets", "tg_checkpoint_bytes", "tg_checkpoint_save", "tg_checkpoint_load", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
     "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
     "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_test_substep_g8", "tg_launch_count",
 ]
@@ -129,6 +129,11 @@ def load():
     lib.tg_draws_upload.argtypes = [vp, vp, vp, vp]
     lib.tg_pipeline_error.argtypes = [vp, vp]
     lib.tg_pipeline_stalls.argtypes = [vp, vp]
+    lib.tg_nan_resets.argtypes = [vp, vp]
+    lib.tg_checkpoint_bytes.argtypes = [vp]
+    lib.tg_checkpoint_bytes.restype = C.c_size_t
+    lib.tg_checkpoint_save.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.tg_checkpoint_load.argtypes = [vp, vp, C.c_size_t, vp]
     lib.tg_get_reset_counts.argtypes = [vp, vp, vp]
     lib.tg_reset.argtypes = [vp, vp, vp, vp]
     lib.tg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]

@@ -80,6 +80,7 @@ struct EnvBuffers {
     double *term_cam, *term_stim;
     int* error_flag;         // sticky error flag (unused slots of the pipeline; kept for the C-ABI)
     int* stall_count;        // episode ends that had to complete their standby inline
+    int* nan_count;          // env steps that ended in a non-finite state (the episode is ended, error flag bit 2)
 };
 
 // SB_CONSUMED + epoch: swapped in during launch `epoch`.  It is EMPTY for every later launch, but the launch that consumed it
@@ -1103,6 +1104,16 @@ TGD void env_epilogue_core(const TgArm& arm, const TgPhysics& ph, const TgTask& 
         float* f = (d && autoreset && b.term_feat) ? b.term_feat : b.feat;
         if (f) surface_features(task, b.hf_meta + hb * SURF_META, tp, tq, f + (size_t)e * TG_PUSH_NFEAT);
     } else edge_step_data(task, tp, b.edge_ang[e], steps, &r, &d);
+    {
+        // SURVEY 5 (per-env NaN / inf guard): a diverged env ends its episode here - with auto-reset its next episode starts from
+        // the pre-computed standby as usual - instead of carrying non-finite numbers through the batch; counted and flagged
+        double chk = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB; i++) chk += q[i] + qd[i];
+        if (push || balance) chk += (ob.pos[0] + ob.pos[1] + ob.pos[2]) + (ob.vel[0] + ob.vel[1] + ob.vel[2]) + (ob.omg[0] + ob.omg[1] + ob.omg[2]) +
+                                    (ob.quat[0] + ob.quat[1] + ob.quat[2] + ob.quat[3]);
+        if (!isfinite(chk)) { d = 1; r = 0.0f; atomicAdd(b.nan_count, 1); atomicOr(b.error_flag, 4); }
+    }
     reward[e] = r; done[e] = d;
     if (b.oracle) {
         float* oo = (d && autoreset) ? b.term_oracle : b.oracle;   // a finished env's last state goes to the terminal buffer

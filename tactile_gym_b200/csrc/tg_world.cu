@@ -1,5 +1,6 @@
 // tg_world.cu - C ABI of libtactile_gym_b200.so (include/tactile_gym_b200.h): world lifetime, buffers, launches.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges are no-ops unless a tool (nsys, ncu --nvtx) injects itself
 
 #include <algorithm>
 #include <cstdarg>
@@ -49,7 +50,8 @@ struct TgWorld {
     int sm_count = 0;
     EnvBuffers eb{};
     RasterArgs ra{};
-    std::vector<void*> allocs;
+    struct Alloc { void* p; size_t bytes; };
+    std::vector<Alloc> allocs;        // every device buffer of the world, in creation order (tg_checkpoint_* walks this list)
     double* d_draws = nullptr;
     int* d_draw_avail = nullptr;
     uint32_t* d_mt = nullptr;         // device RNG states [N][624] (allocated by the first tg_set_rng_state)
@@ -86,10 +88,16 @@ static int dalloc(TgWorld* w, Tp** p, size_t count)
     cudaError_t e = cudaMalloc(&v, count * sizeof(Tp));
     if (e != cudaSuccess) return fail(TG_ENOMEM, "cudaMalloc(%zu) failed: %s", count * sizeof(Tp), cudaGetErrorString(e));
     cudaMemset(v, 0, count * sizeof(Tp));
-    w->allocs.push_back(v);
+    w->allocs.push_back({v, count * sizeof(Tp)});
     *p = static_cast<Tp*>(v);
     return TG_OK;
 }
+
+// NVTX range over one C-ABI call: shows up as tg_step / tg_step_host / tg_reset ... on a profiler's timeline
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 extern "C" int tg_version(void) { return TG_VERSION; }
 extern "C" const char* tg_last_error(void) { return g_err.c_str(); }
@@ -189,7 +197,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         (rc = dalloc(w, &b.sb_ang, n)) || (rc = dalloc(w, &b.sb_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.sb_stim, (size_t)12 * n)) ||
         (rc = dalloc(w, &b.sb_tcp, (size_t)7 * n)) || (rc = dalloc(w, &b.sb_substeps, n)) || (rc = dalloc(w, &b.sb_ready, n)) ||
         (rc = dalloc(w, &b.term_cam, (size_t)12 * n)) || (rc = dalloc(w, &b.term_stim, (size_t)12 * n)) || (rc = dalloc(w, &b.error_flag, 1)) ||
-        (rc = dalloc(w, &b.stall_count, 1)) || (rc = dalloc(w, &b.sb_targ, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_cv, n)) || (rc = dalloc(w, &b.sb_ik, n)) ||
+        (rc = dalloc(w, &b.stall_count, 1)) || (rc = dalloc(w, &b.nan_count, 1)) || (rc = dalloc(w, &b.sb_targ, (size_t)nb * n)) || (rc = dalloc(w, &b.sb_cv, n)) || (rc = dalloc(w, &b.sb_ik, n)) ||
         (rc = dalloc(w, &b.sb_draw, (size_t)TG_MAXDRAW * n))) {
         return rc;
     }
@@ -353,7 +361,7 @@ extern "C" int tg_destroy(TgWorld* w)
 {
     if (!w) return TG_OK;
     cudaSetDevice(w->device);
-    for (void* p : w->allocs) cudaFree(p);
+    for (const TgWorld::Alloc& a : w->allocs) cudaFree(a.p);
     if (w->d_draws) cudaFree(w->d_draws);
     if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
     for (cudaEvent_t ev : w->chunk_ev) if (ev) cudaEventDestroy(ev);
@@ -475,6 +483,96 @@ extern "C" int tg_pipeline_stalls(TgWorld* w, void* stream)
     CK(cudaMemcpyAsync(&cnt, w->eb.stall_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return cnt;
+}
+
+extern "C" int tg_nan_resets(TgWorld* w, void* stream)
+{
+    if (!w) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, w->eb.nan_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return cnt;
+}
+
+// ---- full checkpoint: every device buffer of the world (live state, standby slots and partial rebuilds, both heightfields,
+// RNG states, draw ring, counters) plus the host-side launch counters the kernels are handed.  The caller's own output
+// buffers (obs / reward / done / features) are not part of the world; the Python layer saves those it needs.
+struct CkptHeader {
+    uint32_t magic, version;
+    int32_t n, nb, task, S, n_allocs, draw_rounds;
+    int64_t draw_doubles;
+    int32_t epoch; uint32_t raster_pass;
+    int64_t launches;
+};
+static const uint32_t CKPT_MAGIC = 0x54474350u; // "TGCP"
+
+extern "C" size_t tg_checkpoint_bytes(const TgWorld* w)
+{
+    if (!w) return 0;
+    size_t tot = sizeof(CkptHeader) + sizeof(uint64_t) * w->allocs.size();
+    for (const TgWorld::Alloc& a : w->allocs) tot += a.bytes;
+    if (w->d_draws && w->eb.draw_rounds > 0) tot += sizeof(double) * (size_t)w->n * w->eb.draw_rounds * w->cfg.task.n_draws;
+    return tot;
+}
+
+extern "C" int tg_checkpoint_save(TgWorld* w, void* host, size_t bytes, void* stream)
+{
+    NvtxRange nvtx_("tg_checkpoint_save");
+    if (!w || !host) return fail(TG_EINVAL, "bad arguments");
+    if (bytes < tg_checkpoint_bytes(w)) return fail(TG_EINVAL, "checkpoint buffer too small: %zu < %zu", bytes, tg_checkpoint_bytes(w));
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (w->copy_stream) CK(cudaStreamSynchronize(w->copy_stream));
+    unsigned char* o = static_cast<unsigned char*>(host);
+    CkptHeader h{};
+    h.magic = CKPT_MAGIC; h.version = (uint32_t)TG_VERSION; h.n = w->n; h.nb = w->nb; h.task = w->cfg.task.task; h.S = w->S;
+    h.n_allocs = (int32_t)w->allocs.size(); h.draw_rounds = w->d_draws ? w->eb.draw_rounds : 0;
+    h.draw_doubles = h.draw_rounds > 0 ? (int64_t)w->n * h.draw_rounds * w->cfg.task.n_draws : 0;
+    h.epoch = w->epoch; h.raster_pass = w->raster_pass; h.launches = w->launches;
+    memcpy(o, &h, sizeof(h)); o += sizeof(h);
+    for (const TgWorld::Alloc& a : w->allocs) { const uint64_t b = a.bytes; memcpy(o, &b, sizeof(b)); o += sizeof(b); }
+    for (const TgWorld::Alloc& a : w->allocs) { CK(cudaMemcpy(o, a.p, a.bytes, cudaMemcpyDeviceToHost)); o += a.bytes; }
+    if (h.draw_doubles > 0) CK(cudaMemcpy(o, w->d_draws, sizeof(double) * (size_t)h.draw_doubles, cudaMemcpyDeviceToHost));
+    return TG_OK;
+}
+
+extern "C" int tg_checkpoint_load(TgWorld* w, const void* host, size_t bytes, void* stream)
+{
+    NvtxRange nvtx_("tg_checkpoint_load");
+    if (!w || !host || bytes < sizeof(CkptHeader)) return fail(TG_EINVAL, "bad arguments");
+    CK(cudaSetDevice(w->device));
+    const unsigned char* o = static_cast<const unsigned char*>(host);
+    CkptHeader h;
+    memcpy(&h, o, sizeof(h)); o += sizeof(h);
+    if (h.magic != CKPT_MAGIC || h.version != (uint32_t)TG_VERSION) return fail(TG_EINVAL, "not a checkpoint of this library version");
+    if (h.n != w->n || h.nb != w->nb || h.task != w->cfg.task.task || h.S != w->S || h.n_allocs != (int32_t)w->allocs.size())
+        return fail(TG_EINVAL, "checkpoint of a different world (envs %d / %d, task %d / %d, image %d / %d, buffers %d / %zu)", h.n, w->n, h.task,
+                    w->cfg.task.task, h.S, w->S, h.n_allocs, w->allocs.size());
+    size_t need = sizeof(CkptHeader) + sizeof(uint64_t) * w->allocs.size() + sizeof(double) * (size_t)h.draw_doubles;
+    for (size_t i = 0; i < w->allocs.size(); i++) {
+        uint64_t b;
+        memcpy(&b, o + sizeof(uint64_t) * i, sizeof(b));
+        if (b != w->allocs[i].bytes) return fail(TG_EINVAL, "checkpoint buffer %zu has %llu bytes, the world's has %zu", i, (unsigned long long)b, w->allocs[i].bytes);
+        need += b;
+    }
+    if (bytes < need) return fail(TG_EINVAL, "checkpoint truncated: %zu < %zu", bytes, need);
+    o += sizeof(uint64_t) * w->allocs.size();
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (w->copy_stream) CK(cudaStreamSynchronize(w->copy_stream));
+    for (const TgWorld::Alloc& a : w->allocs) { CK(cudaMemcpy(a.p, o, a.bytes, cudaMemcpyHostToDevice)); o += a.bytes; }
+    if (h.draw_doubles > 0) {
+        if (w->draw_capacity < h.draw_doubles) {
+            if (w->d_draws) cudaFree(w->d_draws);
+            w->d_draws = nullptr; w->draw_capacity = 0;
+            CK(cudaMalloc(&w->d_draws, sizeof(double) * (size_t)h.draw_doubles));
+            w->draw_capacity = (int)h.draw_doubles;
+        }
+        CK(cudaMemcpy(w->d_draws, o, sizeof(double) * (size_t)h.draw_doubles, cudaMemcpyHostToDevice));
+        w->eb.draws = w->d_draws; w->eb.draw_rounds = h.draw_rounds;
+    }
+    w->epoch = h.epoch; w->eb.epoch = h.epoch; w->raster_pass = h.raster_pass; w->launches = h.launches;
+    return TG_OK;
 }
 
 extern "C" int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream)
@@ -624,6 +722,7 @@ extern "C" int tg_bind_oracle_obs(TgWorld* w, float* d_oracle, float* d_term_ora
 
 extern "C" int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void* stream)
 {
+    NvtxRange nvtx_("tg_reset");
     if (!w || !d_obs) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
     int rc;
@@ -633,6 +732,7 @@ extern "C" int tg_reset(TgWorld* w, const uint8_t* d_mask, uint8_t* d_obs, void*
 
 extern "C" int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream)
 {
+    NvtxRange nvtx_("tg_reset_only");
     if (!w) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
     return launch_reset(w, d_mask, (cudaStream_t)stream);
@@ -640,6 +740,7 @@ extern "C" int tg_reset_only(TgWorld* w, const uint8_t* d_mask, void* stream)
 
 extern "C" int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float* d_reward, uint8_t* d_done, uint8_t* d_term_obs, void* stream)
 {
+    NvtxRange nvtx_("tg_step");
     if (!w || !d_actions || !d_obs || !d_reward || !d_done) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -662,6 +763,7 @@ extern "C" int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float
 // device->host copy (copy stream) overlapping the next chunk's raster and the terminal-observation raster (caller's stream).
 extern "C" int tg_step_host(TgWorld* w, const TgHostStep* hs, void* stream)
 {
+    NvtxRange nvtx_("tg_step_host");
     if (!w || !hs || !hs->h_actions || !hs->d_reward || !hs->d_done || !hs->h_reward || !hs->h_done) return fail(TG_EINVAL, "bad arguments");
     if ((hs->h_obs != nullptr) != (hs->d_obs != nullptr)) return fail(TG_EINVAL, "h_obs and d_obs go together");
     if (!hs->h_obs && !hs->h_oracle) return fail(TG_EINVAL, "no observation requested (h_obs and h_oracle are both NULL)");
@@ -706,6 +808,7 @@ extern "C" int tg_step_host(TgWorld* w, const TgHostStep* hs, void* stream)
 
 extern "C" int tg_physics_only(TgWorld* w, const float* d_actions, float* d_reward, uint8_t* d_done, void* stream)
 {
+    NvtxRange nvtx_("tg_physics_only");
     if (!w || !d_actions) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
     return launch_step(w, d_actions, d_reward ? d_reward : w->d_reward_internal, d_done ? d_done : w->d_done_internal, 0, (cudaStream_t)stream);
@@ -713,6 +816,7 @@ extern "C" int tg_physics_only(TgWorld* w, const float* d_actions, float* d_rewa
 
 extern "C" int tg_raster_only(TgWorld* w, uint8_t* d_obs, void* stream)
 {
+    NvtxRange nvtx_("tg_raster_only");
     if (!w || !d_obs) return fail(TG_EINVAL, "bad arguments");
     CK(cudaSetDevice(w->device));
     return launch_raster(w, d_obs, nullptr, (cudaStream_t)stream);

@@ -885,6 +885,54 @@ class TactileWorld:
         explicit set_draws() once its rounds are used up (the pipeline pre-computes one episode ahead); an error otherwise."""
         return bool(self.lib.tg_pipeline_error(self.h, self._stream()) & 2)
 
+    def nan_resets(self):
+        """env steps whose state came out non-finite (reported as done, reward 0; the env then starts its next episode)"""
+        return int(self.lib.tg_nan_resets(self.h, self._stream()))
+
+    def save_checkpoint(self):
+        """Everything needed to resume this world bit for bit (tg_checkpoint_save: every device buffer incl. the pre-computed next
+        episodes, heightfields and RNG states) plus the host side of the draw stream.  Returns a dict of numpy arrays / plain
+        values (picklable, np.savez-able)."""
+        nbytes = int(self.lib.tg_checkpoint_bytes(self.h))
+        blob = np.empty(nbytes, dtype=np.uint8)
+        L.check(self.lib.tg_checkpoint_save(self.h, blob.ctypes.data, nbytes, self._stream()))
+        ck = {"blob": blob, "rng_mode": self.rng_mode, "managed": bool(self._managed), "reward": self.reward.cpu().numpy(),
+              "done": self.done.cpu().numpy(), "rngs": [r.get_state() for r in self._rngs]}
+        if self.feat is not None:
+            ck["feat"] = self.feat.cpu().numpy()
+        if self._managed and self._pin_ring is not None:
+            # host-drawn ring: what is on the device is in the blob; the host copy and its counters ride along
+            if self._upload_ev is not None:
+                self._upload_ev.synchronize()
+            ck["ring"], ck["avail"] = self._pin_ring.numpy().copy(), self._pin_avail.numpy().copy()
+        return ck
+
+    def load_checkpoint(self, ck):
+        """Resume from save_checkpoint() of a world built from the same configuration."""
+        torch = self.torch
+        if ck["rng_mode"] != self.rng_mode:
+            raise ValueError("checkpoint was taken with rng %r, this world runs %r" % (ck["rng_mode"], self.rng_mode))
+        blob = np.ascontiguousarray(ck["blob"], dtype=np.uint8)
+        L.check(self.lib.tg_checkpoint_load(self.h, blob.ctypes.data, blob.nbytes, self._stream()))
+        self.reward.copy_(torch.from_numpy(np.asarray(ck["reward"])))
+        self.done.copy_(torch.from_numpy(np.asarray(ck["done"])))
+        if self.feat is not None and "feat" in ck:
+            self.feat.copy_(torch.from_numpy(np.asarray(ck["feat"])))
+        for r, st in zip(self._rngs, ck["rngs"]):
+            r.set_state(st)
+        self._managed = bool(ck["managed"])
+        if self._managed and "ring" in ck:
+            if self._pin_ring is None:
+                nd = self.cfg.task.n_draws
+                self._pin_ring = torch.zeros((self.n, DRAW_ROUNDS, nd), dtype=torch.float64).pin_memory()
+                self._pin_avail = torch.zeros(self.n, dtype=torch.int32).pin_memory()
+                self._pin_counts = torch.zeros(self.n + 1, dtype=torch.int32).pin_memory()
+            self._pin_ring.numpy()[...] = ck["ring"]
+            self._pin_avail.numpy()[...] = ck["avail"]
+            self._poll_ev, self._since_poll = None, 0
+        if self._obs is not None:
+            self.raster_only()                      # the live observation is a function of the restored state
+
     def pipeline_stalls(self):
         """episode ends that had to finish their pre-computed next episode inline (exact, just slower)"""
         return int(self.lib.tg_pipeline_stalls(self.h, self._stream()))
