@@ -257,6 +257,12 @@ int tg_pipeline_error(TgWorld* w, void* stream);
 /* Per-env NaN / inf guard: env steps so far whose state came out non-finite.  Such a step reports done = 1,
  * reward = 0 and - under auto-reset - the env starts its next episode like after any other episode end.  Synchronises. */
 int tg_nan_resets(TgWorld* w, void* stream);
+/* Profiling counter: envs of the LAST raster pass that the scanline raster (convex stimuli) handed to the general raster kernel
+ * (a face plane seen edge-on, a vertex behind the eye or outside [near, far]).  Synchronises. */
+int tg_scan_fallbacks(TgWorld* w, void* stream);
+/* ... and why: h_counts[8] = envs of the last raster pass per reason code (0 kept, 1 near-plane cut, 2 eye inside a part,
+ * 3 more front faces than the table holds, 4 test hook).  Synchronises. */
+int tg_scan_fallback_reasons(TgWorld* w, int32_t* h_counts, void* stream);
 
 /* Full checkpoint / resume: every device buffer of the world - live state, pre-computed next episodes and
  * partial rebuilds, both heightfields, per-env RNG states, the draw ring, counters.  After tg_checkpoint_load into a world
@@ -301,6 +307,16 @@ typedef struct TgHostStep {
     float* h_feat;          /* or NULL */
     float* h_oracle;        /* [N][TG_ORACLE_NOBS] or NULL: the buffer bound with tg_bind_oracle_obs, copied out */
     int chunks;             /* <= 0: 4 */
+    /* Terminal observations of the envs that finished in this step, compacted on the device (ascending env index) and copied
+     * out with everything else, so that the caller needs no second round trip: h_term_idx[0] = how many finished (all of them,
+     * also beyond term_cap); h_term_idx[1 + j] / h_term_obs[j] / h_term_feat[j] = env index, terminal image [S][S][1] and
+     * terminal feature row [TG_PUSH_NFEAT] of the j-th, for j < min(count, term_cap).  term_cap rows are copied every step
+     * whatever the count (the copy is enqueued before the count is known): keep it near the number of episode ends a step
+     * really sees.  term_cap 0 or h_term_idx NULL: off.  Needs d_term_obs.  h_term_feat may be NULL. */
+    uint8_t* h_term_obs;    /* [term_cap][S][S][1] pinned, or NULL */
+    int32_t* h_term_idx;    /* [1 + term_cap] */
+    float* h_term_feat;     /* [term_cap][TG_PUSH_NFEAT] or NULL */
+    int term_cap;
 } TgHostStep;
 int tg_step_host(TgWorld* w, const TgHostStep* hs, void* stream);
 

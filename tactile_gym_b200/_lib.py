@@ -94,11 +94,12 @@ class TgHostStep(C.Structure):
         ("h_actions", C.c_void_p), ("d_obs", C.c_void_p), ("d_reward", C.c_void_p), ("d_done", C.c_void_p), ("d_term_obs", C.c_void_p),
         ("d_feat", C.c_void_p), ("h_obs", C.c_void_p), ("h_reward", C.c_void_p), ("h_done", C.c_void_p), ("h_feat", C.c_void_p), ("h_oracle", C.c_void_p),
         ("chunks", C.c_int32),
+        ("h_term_obs", C.c_void_p), ("h_term_idx", C.c_void_p), ("h_term_feat", C.c_void_p), ("term_cap", C.c_int32),
     ]
 
 
 EXPORTS = [
-    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_set_rng_state", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_nan_resets", "tg_checkpoint_bytes", "tg_checkpoint_save", "tg_checkpoint_load", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
+    "tg_version", "tg_last_error", "tg_create", "tg_destroy", "tg_set_draws", "tg_set_rng_state", "tg_draws_poll", "tg_draws_upload", "tg_pipeline_error", "tg_pipeline_stalls", "tg_nan_resets", "tg_scan_fallbacks", "tg_scan_fallback_reasons", "tg_checkpoint_bytes", "tg_checkpoint_save", "tg_checkpoint_load", "tg_get_reset_counts", "tg_reset", "tg_step", "tg_step_host", "tg_bind_features", "tg_bind_oracle_obs",
     "tg_physics_only", "tg_raster_only", "tg_reset_only", "tg_state_size", "tg_get_state", "tg_set_state", "tg_get_camera",
     "tg_test_inverse_dynamics", "tg_test_mass_matrix", "tg_test_substep", "tg_test_substep_g8", "tg_launch_count",
 ]
@@ -130,6 +131,8 @@ def load():
     lib.tg_pipeline_error.argtypes = [vp, vp]
     lib.tg_pipeline_stalls.argtypes = [vp, vp]
     lib.tg_nan_resets.argtypes = [vp, vp]
+    lib.tg_scan_fallbacks.argtypes = [vp, vp]
+    lib.tg_scan_fallback_reasons.argtypes = [vp, vp, vp]
     lib.tg_checkpoint_bytes.argtypes = [vp]
     lib.tg_checkpoint_bytes.restype = C.c_size_t
     lib.tg_checkpoint_save.argtypes = [vp, vp, C.c_size_t, vp]

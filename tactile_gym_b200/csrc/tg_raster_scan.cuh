@@ -14,15 +14,16 @@
 //     construction, so there is no float-margin analysis, no uncertainty queue and no second pass;
 //   * several parts (the pole): nearest wins per pixel, max over parts of 1/z.
 // Every output row segment is written exactly once (16-byte stores), baked border bytes included.
-// Envs the shortcut does not cover - a degenerate (edge-on) face plane, a vertex behind the eye or outside [near, far], where
-// clipped fragments could expose back faces - are flagged in `fallback` and rendered by raster_kernel in a masked second launch
-// that exits at once when nothing was flagged.  None occurs in the reference's work spaces; the path is there for exactness.
+// Envs the shortcut does not cover - a front face cut by the NEAR plane inside the image, or the eye inside a part: GL then shows
+// back faces - are flagged in `fallback` and rendered by raster_kernel in a masked second launch that exits at once when nothing
+// was flagged.  (Faces reaching behind the eye or beyond the far plane are fine, see scan_setup_kernel: a tilted pole's plate does.)
 #pragma once
 #include "tg_raster.cuh"
 
 #define SCAN_THREADS 1024  // 32 warps per SM: the render kernel is kept under 64 registers (the fp64 face set-up lives in its own kernel)
 #define SCAN_WARPS (SCAN_THREADS / 32)
 #define SCAN_MAXPOOLS 32 // unit counters per band
+#define SCAN_MAXPARTS 4  // convex parts of a stimulus (the pole has 2)
 #define SCAN_MAXFRONT 8 // front faces per env kept in the interval table (a box shows <= 3, the pole <= 6)
 
 struct ScanFace {
@@ -86,6 +87,7 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
     const bool live = e < a.n;
     const bool masked = live && a.mask && !a.mask[e];
     bool bad = false, front = false;
+    int my_part = -1, why = 0;   // why: 1 near-plane cut, 2 eye inside a part, 3 too many front faces, 4 test hook (profiling: the value stored in `fallback`)
     ScanFace mine;
     int c_lo = S, c_hi = -1, r_lo = S, r_hi = -1;
     if (live && !masked && sub < a.nprim) {
@@ -105,8 +107,9 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
         }
         PrimCoef pc;
         const bool infront = prim_from_eye(a, ve, nv, pc, vp);
-        bad = !pc.valid || !infront || pc.clipped;
-        if (!bad) {
+        my_part = prim_part[sub];
+        // (a face whose plane passes through the eye - pc.valid == 0 - is seen edge-on: no area, no 1/z form, skipped as in raster_kernel)
+        if (pc.valid) {
             // camera outside this face's half-space <=> the face is a front face.  Plane n . x = h through the face, the
             // part's centroid on the inner side: outside <=> (n . 0 - h) = -h and sc = (n . cen - h) have opposite signs,
             // i.e. h and sc have the same sign
@@ -122,6 +125,26 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
             const double h = nrm[0] * ve[0][0] + nrm[1] * ve[0][1] + nrm[2] * ve[0][2];
             const double sc = nrm[0] * ce[0] + nrm[1] * ce[1] + nrm[2] * ce[2] - h;
             front = (h > 0.0) == (sc > 0.0) && sc != 0.0;
+            // Clipping.  The edge functions are homogeneous (built from the eye-space vertices, no projection), so a face with
+            // vertices behind the eye or beyond the far plane needs nothing special: where its plane is behind the eye or
+            // beyond `far`, the window depth d = F - F near / z comes out >= 1 > nodef and the pixel stays 0, as in the oracle,
+            // which does not count it as covered.  The NEAR plane is different: a front face nearer than `near` is cut open
+            // there and GL shows the part's inside (its back faces), which this kernel never looks at - such envs go to
+            // raster_kernel.  Two necessary conditions for such a cut inside the image, both cheap: the face's PLANE is nearer than
+            // `near` on some pixel of the image (1/z is affine in the pixel: test the four corner pixels), and - when all vertices
+            // are in front of the eye, so that 1/z is affine on the face with its extremes at the vertices - some VERTEX is.
+            if (front) {
+                const double cS = (double)(S - 1);
+                const double w00 = pc.eC[4], w01 = pc.eA[4] * cS + pc.eC[4], w10 = pc.eB[4] * cS + pc.eC[4], w11 = pc.eA[4] * cS + pc.eB[4] * cS + pc.eC[4];
+                bool near_cut = !(fmax(fmax(w00, w01), fmax(w10, w11)) < (1.0 - 1e-9) / a.near_);
+                if (near_cut && infront) {
+                    bool vertex_near = false;
+                    for (int k = 0; k < nv; k++) vertex_near = vertex_near || !(ve[k][2] >= a.near_);
+                    near_cut = vertex_near;
+                }
+                bad = near_cut;
+                if (bad) why = 1;
+            }
             mine.w[0] = pc.eA[4]; mine.w[1] = pc.eB[4]; mine.w[2] = pc.eC[4];
             mine.part = part;
 #pragma unroll
@@ -147,11 +170,19 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
             }
         }
     }
-    if (a.scan_test_fallback && (e & 1) && live && !masked) bad = true;
+    if (a.scan_test_fallback && (e & 1) && live && !masked) { bad = true; why = 4; }
+    // a convex part shows at least one front face to any eye outside it: a part without one has the eye inside (its back faces
+    // would be what GL draws) - raster_kernel's case
+    for (int p = 0; p < SCAN_MAXPARTS; p++) {
+        const uint32_t has = __ballot_sync(0xffffffffu, my_part == p) & gmask, shows = __ballot_sync(0xffffffffu, my_part == p && front) & gmask;
+        if (has != 0u && shows == 0u) { bad = true; why = max(why, 2); }
+    }
     const uint32_t bad_m = __ballot_sync(0xffffffffu, bad) & gmask;
     const uint32_t front_m = __ballot_sync(0xffffffffu, front) & gmask;
     const int nf = __popc(front_m);
     const bool give_up = bad_m != 0u || nf > SCAN_MAXFRONT;   // raster_kernel renders this env (masked second launch)
+    if (nf > SCAN_MAXFRONT) why = 3;
+    for (int d = lpe >> 1; d > 0; d >>= 1) why = max(why, __shfl_xor_sync(0xffffffffu, why, d));
     if (front && !give_up) out[e].face[__popc(front_m & ((1u << lane) - 1u))] = mine;
     // the rows / columns any front face can touch (union of the conservative screen boxes)
     for (int d = lpe >> 1; d > 0; d >>= 1) {
@@ -160,7 +191,7 @@ scan_setup_kernel(const RasterArgs a, const int* __restrict__ prim_part, const d
     }
     if (live && sub == 0) {
         if (masked) { fallback[e] = 0; out[e].nf = -1; }
-        else if (give_up) { fallback[e] = 1; atomicAdd(fb_count, 1); out[e].nf = -1; }
+        else if (give_up) { fallback[e] = (uint8_t)max(why, 1); atomicAdd(fb_count, 1); out[e].nf = -1; }
         else { fallback[e] = 0; out[e].nf = nf; out[e].c_lo = c_lo; out[e].c_hi = c_hi; out[e].r_lo = r_lo; out[e].r_hi = r_hi; }
     }
 }

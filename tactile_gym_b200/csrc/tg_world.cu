@@ -76,6 +76,8 @@ struct TgWorld {
     // tg_step_host: device staging for the actions, a copy stream and one event per observation chunk
     double* cam_local = nullptr;      // surface_follow-v2 (vertical): the cameras in the heightfield's frame, [N][12]
     float* d_actions_stage = nullptr;
+    // tg_step_host's compacted terminal observations: indices + count, image / feature rows (grown on demand; not world state)
+    int* d_term_idx = nullptr; uint8_t* d_term_stage = nullptr; float* d_term_feat_stage = nullptr; int term_stage_cap = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[TG_HOST_MAX_CHUNKS] = {};
     cudaEvent_t step_ev = nullptr, copy_done_ev = nullptr;
@@ -297,7 +299,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         w->raster_grid = grid;
         r.hf = nullptr; r.hf_cur = nullptr; r.hf_meta = nullptr; r.hf_flip = 0; r.hf_tile_rows = 16; r.hf_tile_cols = 32;
         r.scan_test_fallback = getenv("TG_SCAN_TEST_FALLBACK") ? 1 : 0;
-        if (np > 0 && cfg->sensor.n_parts > 0 && cfg->sensor.h_prim_part && cfg->sensor.h_part_centroid && !getenv("TG_NO_SCAN")) {
+        if (np > 0 && cfg->sensor.n_parts > 0 && cfg->sensor.n_parts <= SCAN_MAXPARTS && cfg->sensor.h_prim_part && cfg->sensor.h_part_centroid && !getenv("TG_NO_SCAN")) {
             // convex parts: the scanline raster renders, raster_kernel only takes the envs it flags
             for (int i = 0; i < np; i++)
                 if (cfg->sensor.h_prim_part[i] < 0 || cfg->sensor.h_prim_part[i] >= cfg->sensor.n_parts) return fail(TG_EINVAL, "h_prim_part[%d] out of range", i);
@@ -363,6 +365,9 @@ extern "C" int tg_destroy(TgWorld* w)
     cudaSetDevice(w->device);
     for (const TgWorld::Alloc& a : w->allocs) cudaFree(a.p);
     if (w->d_draws) cudaFree(w->d_draws);
+    if (w->d_term_idx) cudaFree(w->d_term_idx);
+    if (w->d_term_stage) cudaFree(w->d_term_stage);
+    if (w->d_term_feat_stage) cudaFree(w->d_term_feat_stage);
     if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
     for (cudaEvent_t ev : w->chunk_ev) if (ev) cudaEventDestroy(ev);
     if (w->step_ev) cudaEventDestroy(w->step_ev);
@@ -483,6 +488,30 @@ extern "C" int tg_pipeline_stalls(TgWorld* w, void* stream)
     CK(cudaMemcpyAsync(&cnt, w->eb.stall_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return cnt;
+}
+
+extern "C" int tg_scan_fallbacks(TgWorld* w, void* stream)
+{
+    if (!w) return fail(TG_EINVAL, "bad arguments");
+    if (!w->scan_ok || w->raster_pass == 0) return 0;
+    CK(cudaSetDevice(w->device));
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, w->d_fb_count + ((w->raster_pass - 1u) & 1u), sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return cnt;
+}
+
+extern "C" int tg_scan_fallback_reasons(TgWorld* w, int32_t* h_counts, void* stream)
+{
+    if (!w || !h_counts) return fail(TG_EINVAL, "bad arguments");
+    for (int i = 0; i < 8; i++) h_counts[i] = 0;
+    if (!w->scan_ok) return TG_OK;
+    CK(cudaSetDevice(w->device));
+    std::vector<uint8_t> fb(w->n);
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaMemcpy(fb.data(), w->d_fallback, w->n, cudaMemcpyDeviceToHost));
+    for (int e = 0; e < w->n; e++) h_counts[fb[e] & 7]++;
+    return TG_OK;
 }
 
 extern "C" int tg_nan_resets(TgWorld* w, void* stream)
@@ -761,6 +790,45 @@ extern "C" int tg_step(TgWorld* w, const float* d_actions, uint8_t* d_obs, float
 
 // One env step with HOST buffers (the call a numpy VecEnv makes): the observation leaves in chunks, each chunk's
 // device->host copy (copy stream) overlapping the next chunk's raster and the terminal-observation raster (caller's stream).
+// ascending list of the envs with done != 0 (one block: per-thread segment counts, block scan, ordered write): idx[0] = how many,
+// idx[1 + j] = the j-th (j < cap)
+__global__ void __launch_bounds__(1024)
+done_compact_kernel(const uint8_t* __restrict__ done, int n, int cap, int* __restrict__ idx)
+{
+    __shared__ int s_warp[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int per = (n + 1023) / 1024, b0 = min(n, t * per), b1 = min(n, b0 + per);
+    int cnt = 0;
+    for (int e = b0; e < b1; e++) cnt += done[e] != 0;
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += v; }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    int pos = inc - cnt + (warp > 0 ? s_warp[warp - 1] : 0);
+    for (int e = b0; e < b1; e++)
+        if (done[e] != 0) { if (pos < cap) idx[1 + pos] = e; pos++; }
+    if (t == 1023) idx[0] = s_warp[31];
+}
+
+// row j of dst = row idx[1 + j] of src, j < min(idx[0], cap); 16-byte pieces
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, int cap, int row_vec, uint4* __restrict__ dst)
+{
+    const int j = blockIdx.x;
+    if (j >= min(idx[0], cap)) return;
+    const uint4* s = src + (size_t)idx[1 + j] * row_vec;
+    uint4* d = dst + (size_t)j * row_vec;
+    for (int k = threadIdx.x; k < row_vec; k += blockDim.x) d[k] = s[k];
+}
+
 extern "C" int tg_step_host(TgWorld* w, const TgHostStep* hs, void* stream)
 {
     NvtxRange nvtx_("tg_step_host");
@@ -801,6 +869,36 @@ extern "C" int tg_step_host(TgWorld* w, const TgHostStep* hs, void* stream)
         CK(cudaMemcpyAsync(hs->h_obs + img * e0, hs->d_obs + img * e0, img * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, w->copy_stream));
     }
     if (hs->d_obs && hs->d_term_obs && (rc = launch_raster(w, hs->d_term_obs, hs->d_done, st, true))) return rc;
+    if (hs->d_obs && hs->d_term_obs && hs->term_cap > 0 && hs->h_term_idx && hs->h_term_obs) {
+        // the finished envs' terminal images (and feature rows), compacted and sent with the rest: no second round trip for the caller
+        const int cap = std::min(hs->term_cap, n);
+        if (w->term_stage_cap < cap) {
+            // (rare: the caller grows term_cap geometrically) - not part of the world's state, so outside `allocs`
+            CK(cudaStreamSynchronize(st)); CK(cudaStreamSynchronize(w->copy_stream));
+            if (w->d_term_idx) cudaFree(w->d_term_idx);
+            if (w->d_term_stage) cudaFree(w->d_term_stage);
+            if (w->d_term_feat_stage) cudaFree(w->d_term_feat_stage);
+            w->d_term_idx = nullptr; w->d_term_stage = nullptr; w->d_term_feat_stage = nullptr; w->term_stage_cap = 0;
+            CK(cudaMalloc(&w->d_term_idx, sizeof(int) * ((size_t)cap + 1)));
+            CK(cudaMalloc(&w->d_term_stage, img * (size_t)cap));
+            CK(cudaMalloc(&w->d_term_feat_stage, sizeof(float) * TG_PUSH_NFEAT * (size_t)cap));
+            w->term_stage_cap = cap;
+        }
+        done_compact_kernel<<<1, 1024, 0, st>>>(hs->d_done, n, cap, w->d_term_idx);
+        gather_rows_kernel<<<cap, 256, 0, st>>>(reinterpret_cast<const uint4*>(hs->d_term_obs), w->d_term_idx, cap, (int)(img / 16), reinterpret_cast<uint4*>(w->d_term_stage));
+        w->launches += 2;
+        const bool feats = hs->h_term_feat && w->eb.term_feat;
+        if (feats) {
+            gather_rows_kernel<<<cap, 32, 0, st>>>(reinterpret_cast<const uint4*>(w->eb.term_feat), w->d_term_idx, cap, (int)(sizeof(float) * TG_PUSH_NFEAT / 16), reinterpret_cast<uint4*>(w->d_term_feat_stage));
+            w->launches++;
+        }
+        CK(cudaGetLastError());
+        // small copies, on the caller's stream: they run beside the observation chunks on the copy stream instead of queueing
+        // behind them (the stream ends with a wait on the copy stream anyway)
+        CK(cudaMemcpyAsync(hs->h_term_idx, w->d_term_idx, sizeof(int) * ((size_t)cap + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hs->h_term_obs, w->d_term_stage, img * (size_t)cap, cudaMemcpyDeviceToHost, st));
+        if (feats) CK(cudaMemcpyAsync(hs->h_term_feat, w->d_term_feat_stage, sizeof(float) * TG_PUSH_NFEAT * (size_t)cap, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(w->copy_done_ev, w->copy_stream));
     CK(cudaStreamWaitEvent(st, w->copy_done_ev, 0));   // the caller's stream is complete only when the host buffers are
     return TG_OK;

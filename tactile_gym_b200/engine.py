@@ -831,10 +831,11 @@ class TactileWorld:
         self._feed_draws()
         return obs, reward, done
 
-    def step_host(self, h_actions, h_obs, h_reward, h_done, h_feat=None, h_oracle=None, want_terminal_obs=True, chunks=0):
+    def step_host(self, h_actions, h_obs, h_reward, h_done, h_feat=None, h_oracle=None, want_terminal_obs=True, chunks=0, term=None):
         """One env step with pinned HOST tensors in and out (tg_step_host): the observation is rendered and copied out in
         chunks so the PCIe transfer overlaps the raster.  h_obs None (observation_mode "oracle"): nothing is rendered.
-        Valid after synchronising the current stream."""
+        Valid after synchronising the current stream.  term = (h_term_obs [cap, S, S, 1] u8, h_term_idx [1 + cap] i32 (count first),
+        h_term_feat [cap, 12] f32 or None), pinned: the finished envs' terminal observations arrive compacted with the same call."""
         hs = L.TgHostStep()
         hs.h_actions, hs.h_reward, hs.h_done = h_actions.data_ptr(), h_reward.data_ptr(), h_done.data_ptr()
         hs.d_reward, hs.d_done = self.reward.data_ptr(), self.done.data_ptr()
@@ -847,6 +848,11 @@ class TactileWorld:
             self.bind_oracle_obs()
             hs.h_oracle = h_oracle.data_ptr()
         hs.chunks = chunks
+        if term is not None and h_obs is not None and want_terminal_obs:
+            t_obs, t_idx, t_feat = term
+            hs.h_term_obs, hs.h_term_idx, hs.term_cap = t_obs.data_ptr(), t_idx.data_ptr(), int(t_obs.shape[0])
+            if t_feat is not None and self.term_feat is not None:
+                hs.h_term_feat = t_feat.data_ptr()
         L.check(self.lib.tg_step_host(self.h, C.byref(hs), self._stream()))
         self._feed_draws()
 
@@ -884,6 +890,16 @@ class TactileWorld:
         """a reset found the draw ring empty and used the task's default draws (bit 1 of tg_pipeline_error).  Expected with
         explicit set_draws() once its rounds are used up (the pipeline pre-computes one episode ahead); an error otherwise."""
         return bool(self.lib.tg_pipeline_error(self.h, self._stream()) & 2)
+
+    def scan_fallbacks(self):
+        """envs of the last raster pass that the scanline raster handed to the general raster kernel (profiling counter)"""
+        return int(self.lib.tg_scan_fallbacks(self.h, self._stream()))
+
+    def scan_fallback_reasons(self):
+        """per reason code: [kept, near-plane cut, eye inside a part, too many front faces, test hook, ...] of the last raster pass"""
+        c = np.zeros(8, dtype=np.int32)
+        L.check(self.lib.tg_scan_fallback_reasons(self.h, c.ctypes.data, self._stream()))
+        return c
 
     def nan_resets(self):
         """env steps whose state came out non-finite (reported as done, reward 0; the env then starts its next episode)"""

@@ -121,13 +121,26 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_idx = torch.zeros(n_envs, dtype=torch.int64).pin_memory()
         self._term_dev = self._term_stage = None
         self._grow_term_stage(min(n_envs, 64))
+        # tg_step_host delivers the finished envs' terminal observations compacted, with the step's own copies: a pinned stage
+        # of `cap` rows (copied every step whatever the count, so it follows the number of episode ends really seen)
+        self._tstage = None
+        self._tstage_used = False
+        self._grow_tstage(3 * n_envs // max(int(max_steps), 1))    # three times a steady state's episode ends per step
         if _VecEnvBase is not object:  # pragma: no cover - needs stable_baselines3
             # SB3's wrappers read reset_infos / _seeds / _options / render_mode off the base class
             self._sb3_init()
         if seed is not None:
             self.seed(seed)
         self.h2d_bytes_per_step = self._pin_actions.numel() * 4
-        self.d2h_bytes_per_step = (self._pin_oracle.numel() * 4 if self._oracle else self._pin_obs.numel()) + self._pin_rew.numel() * 4 + self._pin_done.numel() + (self._pin_feat.numel() * 4 if self._with_feat else 0)
+
+    @property
+    def d2h_bytes_per_step(self):
+        """bytes a step copies device -> host: observations, rewards, dones, features, and the terminal-observation stage"""
+        b = (self._pin_oracle.numel() * 4 if self._oracle else self._pin_obs.numel()) + self._pin_rew.numel() * 4 + self._pin_done.numel()
+        b += self._pin_feat.numel() * 4 if self._with_feat else 0
+        if self._host_step and self._tstage is not None:
+            b += self._tstage[0].numel() + self._tstage[1].numel() * 4 + (self._tstage[2].numel() * 4 if self._tstage[2] is not None else 0)
+        return b
 
     def _sb3_init(self):  # pragma: no cover - needs stable_baselines3
         import inspect
@@ -179,8 +192,10 @@ class TactileVecEnv(_VecEnvBase):
         if self._host_step:
             # one C-ABI call with the pinned host buffers: chunked raster, D2H overlapped on the library's copy stream
             self.world.step_host(self._pin_actions, None if self._oracle else self._next_obs_buffer(), self._pin_rew, self._pin_done,
-                                 h_feat=self._pin_feat, h_oracle=self._pin_oracle, want_terminal_obs=True, chunks=self.copy_chunks)
+                                 h_feat=self._pin_feat, h_oracle=self._pin_oracle, want_terminal_obs=True, chunks=self.copy_chunks, term=self._tstage)
+            self._tstage_used = self._tstage is not None
             return
+        self._tstage_used = False
         a = self._pin_actions.to(self.world.device, non_blocking=True)
         self.world.step(a, want_terminal_obs=True)
         if self._oracle:
@@ -191,6 +206,17 @@ class TactileVecEnv(_VecEnvBase):
         self._pin_done.copy_(self.world.done, non_blocking=True)
         if self._with_feat:
             self._pin_feat.copy_(self.world.feat, non_blocking=True)
+
+    def _grow_tstage(self, k):
+        torch = self.world.torch
+        if self._oracle:
+            return
+        cap = min(self.num_envs, max(32, 1 << int(max(k, 1) - 1).bit_length()))
+        if self._tstage is not None and self._tstage[0].shape[0] >= cap:
+            return
+        S = self.world.S
+        self._tstage = (torch.zeros((cap, S, S, 1), dtype=torch.uint8).pin_memory(), torch.zeros(1 + cap, dtype=torch.int32).pin_memory(),
+                        torch.zeros((cap, 12), dtype=torch.float32).pin_memory() if self._with_feat else None)
 
     def _grow_term_stage(self, k):
         torch = self.world.torch
@@ -218,18 +244,33 @@ class TactileVecEnv(_VecEnvBase):
         idx = np.flatnonzero(done)
         if idx.size:
             k = idx.size
-            self._grow_term_stage(k)
-            didx = self._pin_idx[:k]
-            didx.copy_(torch.from_numpy(idx))
-            didx = didx.to(self.world.device, non_blocking=True)
             now = round(time.time() - self._t0, 6)
+            fast = (not self._oracle) and self._tstage_used and k <= self._tstage[0].shape[0] and int(self._tstage[1][0]) == k
+            if not fast:
+                self._grow_term_stage(k)
+                didx = self._pin_idx[:k]
+                didx.copy_(torch.from_numpy(idx))
+                didx = didx.to(self.world.device, non_blocking=True)
             if self._oracle:
                 term = self.world.term_oracle_obs[didx].cpu().numpy()[:, : self._noracle]
                 for j, i in enumerate(idx):
                     infos[i] = {"terminal_observation": {"oracle": term[j]},
                                 "episode": {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": now}}
+            elif fast:
+                # they came with the step (tg_step_host's compacted terminal rows, ascending env index like `idx`)
+                term = self._tstage[0].numpy()[:k].copy()
+                tfeat = self._tstage[2].numpy()[:k].copy() if self._with_feat else None
+                for j, i in enumerate(idx):
+                    info = {"terminal_observation": {"tactile": term[j]},
+                            "episode": {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": now}}
+                    if self._with_feat:
+                        info["terminal_observation"]["extended_feature"] = tfeat[j][: self._nfeat]
+                    infos[i] = info
             else:
-                # gather the finished envs' terminal observations on the device, one small pinned copy out
+                # (more episode ends than the stage holds, or the torch-copy path) gather the finished envs' terminal
+                # observations on the device, one small pinned copy out
+                if self._tstage_used:
+                    self._grow_tstage(2 * k)       # the next steps carry them along
                 term = self._term_stage[:k]
                 torch.index_select(self.world.term_obs, 0, didx, out=self._term_dev[:k])
                 term.copy_(self._term_dev[:k], non_blocking=True)

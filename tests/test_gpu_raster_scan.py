@@ -20,10 +20,10 @@ import numpy as np
 import tactile_gym_b200 as tg
 env_id, S, n = %(env_id)r, %(S)d, 97
 modes = %(modes)r
-env = tg.make_vec(env_id, n, seed=5, env_kwargs={"env_modes": modes, "image_size": [S, S], "max_steps": 7})
+env = tg.make_vec(env_id, n, seed=5, env_kwargs={"env_modes": modes, "image_size": [S, S], "max_steps": %(max_steps)d})
 obs = [env.reset()["tactile"].copy()]
 rs = np.random.RandomState(0)
-for k in range(10):
+for k in range(%(steps)d):
     a = rs.uniform(-0.25, 0.25, (n, env.world.act_dim)).astype(np.float32)
     o, r, d, infos = env.step(a)
     obs.append(o["tactile"].copy())
@@ -41,9 +41,9 @@ PUSH = {"movement_mode": "TyRz", "control_mode": "TCP_velocity_control", "rand_i
         "observation_mode": "tactile_and_feature", "reward_mode": "dense", "arm_type": "mg400", "tactile_sensor_name": "digitac"}
 
 
-def _run(tmp_path, name, env_id, modes, S, extra_env):
+def _run(tmp_path, name, env_id, modes, S, extra_env, steps=10, max_steps=7):
     out = str(tmp_path / (name + ".npy"))
-    code = CHILD % {"root": ROOT, "env_id": env_id, "modes": modes, "S": S, "out": out}
+    code = CHILD % {"root": ROOT, "env_id": env_id, "modes": modes, "S": S, "out": out, "steps": steps, "max_steps": max_steps}
     env = dict(os.environ, **extra_env)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-3000:]
@@ -63,3 +63,14 @@ def test_scanline_raster_equals_general_raster(tmp_path, env_id, modes, S):
     d2 = np.abs(half.astype(np.int32) - gen.astype(np.int32))
     assert d2.max() <= 1 and (d2 != 0).mean() < 1e-3
     assert (half[1::2] != gen[1::2]).mean() <= (scan[1::2] != gen[1::2]).mean()      # the handed-back envs ARE the general kernel's
+
+
+def test_scanline_raster_takes_tilted_poles(tmp_path):
+    """Poles left to tip over for 70 steps (up to the 35 degree termination): the plate's far corners go behind the eye plane and
+    beyond the far plane.  The scanline raster keeps those envs (homogeneous edge functions, see scan_setup_kernel) and its images
+    equal the general kernel's; only near-plane cuts are handed back, and those stay rare."""
+    scan = _run(tmp_path, "scan_t", "object_balance-v0", BALANCE, 128, {}, steps=70, max_steps=250)
+    gen = _run(tmp_path, "gen_t", "object_balance-v0", BALANCE, 128, {"TG_NO_SCAN": "1"}, steps=70, max_steps=250)
+    assert scan.shape == gen.shape
+    d = np.abs(scan.astype(np.int32) - gen.astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3, (d.max(), (d != 0).mean())

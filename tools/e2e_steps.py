@@ -6,7 +6,8 @@ import bench
 import tactile_gym_b200 as tg
 n = 4096
 chunks = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-env = tg.make_vec(bench.ENV_ID, n, env_kwargs={"env_modes": bench.MODES, "image_size": [128, 128], "max_steps": 200}, copy_chunks=chunks)
+W = bench.workload("edge")
+env = tg.make_vec(W["env_id"], n, env_kwargs={"env_modes": W["modes"], "image_size": [128, 128], "max_steps": 200}, copy_chunks=chunks)
 env.world.seed([1 + i for i in range(n)])
 env.reset()
 w = env.world
