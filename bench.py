@@ -37,17 +37,17 @@ sys.path.insert(0, ROOT)
 
 # BASELINE.json configs 2..5 at their per-GPU sizes; alg_bytes = SURVEY.md 8(d)'s algorithmic bytes per env-step
 WORKLOADS = {
-    "edge": dict(env_id="edge_follow-v0", n=4096, img=128, max_steps=200, act_dim=2, extra=64, kernel="raster_kernel",
+    "edge": dict(env_id="edge_follow-v0", n=4096, img=128, max_steps=200, act_dim=2, extra=64, kernel="scan_setup_kernel + raster_scan_kernel",
                  modes={"movement_mode": "xy", "control_mode": "TCP_velocity_control", "noise_mode": "rand_height", "observation_mode": "tactile",
                         "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "tactip"}, label="edge_follow-v0 ur5+tactip"),
     "surface": dict(env_id="surface_follow-v0", n=1024, img=128, max_steps=200, act_dim=3, extra=64 + 64 * 64 * 4, kernel="raster_hf_kernel",
                     modes={"movement_mode": "xyzRxRy", "control_mode": "TCP_velocity_control", "noise_mode": "simplex", "observation_mode": "tactile",
                            "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "digit"}, label="surface_follow-v0 ur5+digit"),
-    "push": dict(env_id="object_push-v0", n=8192, img=128, max_steps=1000, act_dim=2, extra=92 + 48, kernel="raster_kernel",
+    "push": dict(env_id="object_push-v0", n=8192, img=128, max_steps=1000, act_dim=2, extra=92 + 48, kernel="scan_setup_kernel + raster_scan_kernel",
                  modes={"movement_mode": "TyRz", "control_mode": "TCP_velocity_control", "rand_init_orn": False, "rand_obj_mass": False,
                         "traj_type": "simplex", "observation_mode": "tactile_and_feature", "reward_mode": "dense", "arm_type": "mg400",
                         "tactile_sensor_name": "digitac"}, label="object_push-v0 mg400+digitac"),
-    "balance": dict(env_id="object_balance-v0", n=2048, img=256, max_steps=250, act_dim=2, extra=92, kernel="raster_kernel",
+    "balance": dict(env_id="object_balance-v0", n=2048, img=256, max_steps=250, act_dim=2, extra=92, kernel="scan_setup_kernel + raster_scan_kernel",
                     modes={"movement_mode": "xy", "control_mode": "TCP_velocity_control", "object_mode": "pole", "rand_gravity": True,
                            "rand_embed_dist": True, "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5",
                            "tactile_sensor_name": "tactip"}, label="object_balance-v0 ur5+tactip"),

@@ -15,8 +15,9 @@
 #include "tg_raster.cuh"
 #include "tg_surface.cuh"
 
-#define HF_THREADS 256
+#define HF_THREADS 320   // 10 warps: what fits beside the band tables in shared memory (12.5 KB per warp)
 #define HF_WARPS (HF_THREADS / 32)
+#define HF_UPE 8          // work units per env image (a unit = every 8th tile, diagonally)
 #define HF_MAXPRIM 32
 #define HF_QUEUE 512 // a region adds at most 32 spans x 16 pixels
 #define HF_PER_WARP_SMEM (sizeof(PrimCoef) * HF_MAXPRIM + sizeof(unsigned long long) * HF_QUEUE + 16)
@@ -71,7 +72,14 @@ raster_hf_kernel(const RasterArgs a, int* __restrict__ error_flag)
     const int tr = a.hf_tile_rows, tc = a.hf_tile_cols;
     const int tiles_x = S / tc, n_tiles = tiles_x * (band_rows / tr);
 
-    for (int e = lane_cta * HF_WARPS + warp; e < a.n; e += n_cta * HF_WARPS) {
+    // Work unit of a warp: (env, 1 / HF_UPE of the band's tiles).  One env per warp left 14 % of the warps without work at
+    // config 3's 1024 envs and made every warp walk 32 tiles in a row; with units the tiles of an image are rendered by up to
+    // HF_UPE warps side by side.  Tile t of an image belongs to part (t + t / tiles_x) mod HF_UPE - a diagonal pattern, so that
+    // every part gets its share of border tiles (cheap) and centre tiles (expensive) and a static round-robin over the units balances.
+    const int upe = min(HF_UPE, n_tiles);
+    const int units = a.n * upe;
+    for (int u = lane_cta * HF_WARPS + warp; u < units; u += n_cta * HF_WARPS) {
+        const int e = u / upe, part = u - e * upe;
         if (a.mask && !a.mask[e]) continue;
         const double* cam = a.cam + (size_t)e * 12;
         const int buf = a.hf_cur[e] ^ (a.hf_flip ? 1 : 0);
@@ -222,6 +230,7 @@ raster_hf_kernel(const RasterArgs a, int* __restrict__ error_flag)
         };
 
         for (int tile = 0; tile < n_tiles; tile++) {
+            if ((tile + tile / tiles_x) % upe != part) continue;
             const int rl0 = (tile / tiles_x) * tr, cl0 = (tile % tiles_x) * tc;
             if (region(rl0, tr, cl0, tc)) continue;
             // too many triangles under this tile: span by span

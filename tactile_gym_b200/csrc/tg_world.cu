@@ -347,7 +347,7 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             if (per_sm < 1) { return fail(TG_ECUDA, "heightfield raster kernel does not fit on an SM (smem %zu)", w->raster_smem); }
             grid = w->sm_count * per_sm;
             grid -= grid % r.bands;
-            const int need_hf = ((n + HF_WARPS - 1) / HF_WARPS) * r.bands;
+            const int need_hf = ((n * HF_UPE + HF_WARPS - 1) / HF_WARPS) * r.bands;
             if (grid > need_hf) grid = need_hf;
             w->raster_grid = grid;
         }
@@ -653,7 +653,7 @@ static int launch_raster(TgWorld* w, uint8_t* d_obs, const uint8_t* mask, cudaSt
     if (w->cfg.task.task == TG_TASK_OBJECT_ROLL) raster_sphere_kernel<<<std::min((cnt + 7) / 8, 8 * w->sm_count), SPH_THREADS, 0, st>>>(r);
     else {
         const int wp = r.hf ? HF_WARPS : RASTER_WARPS;
-        const int grid = std::min(w->raster_grid, ((cnt + wp - 1) / wp) * r.bands);
+        const int grid = std::min(w->raster_grid, (((r.hf ? cnt * HF_UPE : cnt) + wp - 1) / wp) * r.bands);
         if (r.hf) raster_hf_kernel<<<grid, HF_THREADS, w->raster_smem, st>>>(r, w->eb.error_flag);
         else if (w->scan_ok) {
             // convex stimulus: scanline raster, then raster_kernel for the envs it flagged (returns at once when there are none)
