@@ -158,8 +158,9 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
         // the 8-lanes-per-env kernel: motor-row tasks under TCP_velocity_control with gravity compensation.  One warp carries 4
         // envs (against up to 32 of the one-thread kernel), so it wins while the device is not yet full of warps: measured on
         // B200 (edge_follow, L2 flushed) 0.180 against 0.267 ms at N = 4096, 0.294 against 0.276 ms at N = 8192
-        const bool can = (cfg->task.task == TG_TASK_EDGE_FOLLOW || cfg->task.task == TG_TASK_SURFACE_FOLLOW) && cfg->task.control_mode == 0 &&
-                         cfg->phys.gravity_comp == 1;
+        const bool can = (cfg->task.task == TG_TASK_EDGE_FOLLOW || cfg->task.task == TG_TASK_SURFACE_FOLLOW ||
+                          (cfg->task.task == TG_TASK_OBJECT_BALANCE && cfg->arm.topo == TG_TOPO_CHAIN6)) &&
+                         cfg->task.control_mode == 0 && cfg->phys.gravity_comp == 1;
         if (lanes == -8 && !can) return fail(TG_EUNSUPPORTED, "lanes_per_warp = -8 (8 lanes per env) is built for edge_follow / surface_follow under TCP_velocity_control");
         w->use_g8 = can && (lanes == -8 || (lanes == 0 && n <= 6144));
         if (const char* ev = getenv("TG_G8")) w->use_g8 = can && atoi(ev) != 0;     // tuning hook
@@ -715,7 +716,8 @@ static int launch_step(TgWorld* w, const float* d_actions, float* d_reward, uint
         const dim3 grid(w->g8_blocks + w->standby_blocks);
 #define G8_LAUNCH(Topo, TASK) step_kernel_g8<Topo, TASK><<<grid, 128, 0, st>>>(w->cfg.arm, w->cfg.phys, w->cfg.task, eb, d_actions, d_reward, d_done, autoreset)
         const bool surf = w->cfg.task.task == TG_TASK_SURFACE_FOLLOW;
-        if (w->cfg.arm.topo == TG_TOPO_MG400) { if (surf) G8_LAUNCH(TopoMG400, TG_TASK_SURFACE_FOLLOW); else G8_LAUNCH(TopoMG400, TG_TASK_EDGE_FOLLOW); }
+        if (w->cfg.task.task == TG_TASK_OBJECT_BALANCE) G8_LAUNCH(TopoChain6, TG_TASK_OBJECT_BALANCE);
+        else if (w->cfg.arm.topo == TG_TOPO_MG400) { if (surf) G8_LAUNCH(TopoMG400, TG_TASK_SURFACE_FOLLOW); else G8_LAUNCH(TopoMG400, TG_TASK_EDGE_FOLLOW); }
         else { if (surf) G8_LAUNCH(TopoChain6, TG_TASK_SURFACE_FOLLOW); else G8_LAUNCH(TopoChain6, TG_TASK_EDGE_FOLLOW); }
 #undef G8_LAUNCH
         w->launches++;

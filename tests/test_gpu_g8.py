@@ -53,6 +53,11 @@ def test_g8_substep_matches_oracle_and_one_thread_kernel(oracle, arm, sensor):
     ("edge_follow-v0", dict(EDGE, arm_type="mg400", tactile_sensor_name="digitac"), 2),
     ("surface_follow-v0", {"movement_mode": "xyzRxRy", "control_mode": "TCP_velocity_control", "noise_mode": "simplex", "observation_mode": "tactile",
                            "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "digit"}, 3),
+    # the pole on its point-to-point rows (g8_substep_obj): the rows' dot products are shuffle sums there, sequential sums in the
+    # one-thread kernel - the same numbers to ~1e-12 over an episode
+    ("object_balance-v0", {"movement_mode": "xyRxRy", "control_mode": "TCP_velocity_control", "object_mode": "pole", "rand_gravity": True,
+                           "rand_embed_dist": True, "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5",
+                           "tactile_sensor_name": "tactip"}, 4),
 ])
 def test_g8_step_kernel_equals_one_thread_step_kernel(env_id, modes, act_dim):
     """whole env steps, episode ends and auto-resets included: the two kernels give the same states (1e-11), rewards, dones and
