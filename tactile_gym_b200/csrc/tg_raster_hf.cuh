@@ -22,7 +22,7 @@
 #define HF_QUEUE 512 // a region adds at most 32 spans x 16 pixels
 #define HF_PER_WARP_SMEM (sizeof(PrimCoef) * HF_MAXPRIM + sizeof(unsigned long long) * HF_QUEUE + 16)
 
-__global__ void __launch_bounds__(HF_THREADS)
+__global__ void __launch_bounds__(HF_THREADS, 1)
 raster_hf_kernel(const RasterArgs a, int* __restrict__ error_flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
