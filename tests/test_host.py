@@ -54,6 +54,27 @@ def test_config_rejects_bad_modes(edge_modes):
     assert (cfg.task.control_mode, cfg.task.pos_max_steps, cfg.task.act_hi[0]) == (1, 10, 0.001)     # edge_follow_env.py:143-153
 
 
+def test_object_tasks_take_position_control():
+    """control_mode="TCP_position_control" on the object tasks: pose-delta action ranges of the reference (1 mm / 1 degree per step:
+    object_balance_env.py:129-139, object_push_env.py:137-147, object_roll_env.py:112-122) and its 10-step blocking move"""
+    from tactile_gym_b200.engine import object_balance_config, object_push_config, object_roll_config
+
+    base = {"control_mode": "TCP_position_control", "observation_mode": "tactile", "reward_mode": "dense", "arm_type": "ur5", "tactile_sensor_name": "tactip"}
+    deg = np.pi / 180
+    cfg = object_balance_config(dict(base, movement_mode="xyRxRy", object_mode="pole", rand_gravity=True, rand_embed_dist=True), [64, 64], 250, 2)[0]
+    assert (cfg.task.control_mode, cfg.task.pos_max_steps) == (1, 10)
+    assert np.allclose(list(cfg.task.act_hi), [0.001, 0.001, 0.001, deg, deg, 0.0]) and np.allclose(list(cfg.task.act_lo), [-0.001, -0.001, -0.001, -deg, -deg, 0.0])
+    cfg = object_push_config(dict(base, movement_mode="TyRz", traj_type="simplex", rand_init_orn=False, rand_obj_mass=False), [64, 64], 1000, 2)[0]
+    assert (cfg.task.control_mode, cfg.task.pos_max_steps) == (1, 10) and np.allclose(list(cfg.task.act_hi), [0.001, 0.001, 0, 0, 0, deg])
+    cfg = object_roll_config(dict(base, movement_mode="xy", rand_init_obj_pos=True, rand_obj_size=True, rand_embed_dist=True), [64, 64], 250, 2)[0]
+    assert (cfg.task.control_mode, cfg.task.pos_max_steps) == (1, 10) and np.allclose(list(cfg.task.act_hi), [0.001, 0.001, 0, 0, 0, 0])
+    vel = object_push_config(dict(base, control_mode="TCP_velocity_control", movement_mode="TyRz", traj_type="simplex", rand_init_orn=False,
+                                  rand_obj_mass=False), [64, 64], 1000, 2)[0]
+    assert vel.task.control_mode == 0 and np.allclose(list(vel.task.act_hi), [0.01, 0.01, 0, 0, 0, 5 * deg])
+    with pytest.raises(ValueError):
+        object_balance_config(dict(base, control_mode="joint_velocity_control", movement_mode="xy", object_mode="pole"), [64, 64], 250, 2)
+
+
 def test_registry_ids():
     import tactile_gym_b200 as tg
 

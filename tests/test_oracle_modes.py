@@ -148,3 +148,44 @@ def test_mg400_position_control(oracle):
         assert abs(q[5] - q[1]) + abs(q[6] + q[1]) + abs(q[7] - (q[1] + q[2])) < 5e-6
     d = e.oracle_obs()[:3] - p0
     assert abs(d[0] - 0.005) < 1e-4 and abs(d[1]) < 1e-4 and abs(d[2]) < 1e-4
+
+
+def test_position_control_with_the_object_in_the_world(oracle):
+    """TCP_position_control on the object tasks (or_tcp_position_control_world): the blocking move steps the env's whole world -
+    the pole stays on its constraint while the tip is moved 1 mm per full-scale step, the cube is pushed, the marble is rolled
+    along; every move takes 1 .. 10 substeps"""
+    b = oracle.ObjectBalanceOracle(image_size=64, movement_mode="xy", control_mode="TCP_position_control", rand_gravity=False, rand_embed_dist=False, seed=1)
+    b.reset()
+    p0, _ = b.tcp_world() if hasattr(b, "tcp_world") else (None, None)
+    tcp0 = b.oracle_obs()[:3].copy()
+    for k in range(10):
+        o, r, d, _ = b.step(np.array([0.25, 0.0], np.float32))
+        assert 1 <= b.last_move_substeps <= 10 and r == 1.0 and not d
+    tcp1 = b.oracle_obs()[:3]
+    assert abs((tcp1[0] - tcp0[0]) - 0.010) < 3e-4 and abs(tcp1[1] - tcp0[1]) < 3e-4            # 10 x 1 mm along work-frame x
+    piv = np.array(b.o.pos[:])                                                                    # the pole followed the tip: < 1 mm behind
+    assert abs((piv[0] - b.init_obj_pos[0]) - 0.010) < 1.5e-3 and abs(piv[2] - b.init_obj_pos[2]) < 1e-3
+
+    p = oracle.ObjectPushOracle(image_size=64, arm="ur5", sensor="tactip", movement_mode="xyRz", traj_type="straight", control_mode="TCP_position_control", seed=2)
+    p.reset()
+    c0 = np.array(p.o.pos[:])
+    touched = False
+    for k in range(40):
+        o, r, d, _ = p.step(np.array([0.25, 0.0, 0.0], np.float32))
+        assert 1 <= p.last_move_substeps <= 10 and not d
+        touched = touched or p.p.n_contacts > 4
+    c1 = np.array(p.o.pos[:])
+    assert touched and 0.005 < np.linalg.norm(c1[:2] - c0[:2]) < 0.06 and abs(c1[2] - c0[2]) < 1e-4    # pushed about the 40 mm the tip moved (it coasts on mu = 0.065)
+
+    rl = oracle.ObjectRollOracle(image_size=64, control_mode="TCP_position_control", seed=3)
+    rl.reset(draws=np.array([1.0, 0.0028, 0.0, 0.0, 0.0, 0.014]))      # embedded deep enough for the tip core to hold the marble (as in test_gpu_roll.py)
+    m0 = np.array(rl.o.pos[:])
+    t0 = rl.tcp_world()[0].copy()
+    for k in range(10):
+        rl.step(np.array([0.25, 0.0], np.float32))
+        assert 1 <= rl.last_move_substeps <= 10
+    m1 = np.array(rl.o.pos[:]); t1 = rl.tcp_world()[0]
+    dt_, dm = np.linalg.norm(t1[:2] - t0[:2]), np.linalg.norm(m1[:2] - m0[:2])
+    # the tip moved its 10 x 1 mm; the marble went along (position control moves the plate in jerks - 3 substeps per move - so the
+    # marble is not in steady rolling and need not sit at half the plate's travel as under velocity control)
+    assert 0.008 < dt_ < 0.0105 and 0.002 < dm < 0.03 and np.dot(m1[:2] - m0[:2], t1[:2] - t0[:2]) > 0
