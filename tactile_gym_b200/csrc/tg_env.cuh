@@ -88,10 +88,9 @@ struct EnvBuffers {
 // the terminal-observation raster still reads after this launch.
 enum { SB_EMPTY = 0, SB_READY = 1, SB_PARTIAL = 2, SB_BUSY = 3, SB_CONSUMED = 16 };
 #define SB_EPOCH_MASK 0x0fffffff
-#define RESET_CHUNK 6  // blocking-move iterations per quantum (a quarter of an env step's work: a standby warp may
-                       // carry an IK quantum and a move quantum one after the other, plus cold code)
-#define IK_CHUNK 8     // IK iterations per quantum
-#define SURF_CHUNK 96  // heightfield points (OpenSimplex evaluations) per quantum
+// Quantum sizes of the resumable reset: blocking-move substeps and IK iterations per quantum are chosen per world from the
+// episode length (tg_create: 2 and 3 at max_steps >= 200); heightfield points (OpenSimplex evaluations) per quantum:
+#define SURF_CHUNK 96
 
 // a reset in flight (between draws + IK and the end of the blocking move)
 template <int NB>

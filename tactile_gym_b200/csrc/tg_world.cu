@@ -191,7 +191,20 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
     b.draws = nullptr; b.draw_rounds = 0;
     // standby reset pipeline (tg_env.cuh): needs episodes of at least 2 steps
     b.pipeline = cfg->task.max_steps >= 2 ? 1 : 0;
-    b.ik_chunk = IK_CHUNK; b.reset_chunk = RESET_CHUNK; b.surf_chunk = SURF_CHUNK;
+    {
+        // Quantum sizes of the resumable reset.  A standby thread's quantum runs BESIDE the step warps of the same launch, as one
+        // thread's dependent fp64 chain: it must stay well below the step's own duration or it IS the launch's duration (measured,
+        // edge_follow 4096 envs: 6 move substeps + 8 IK iterations per quantum -> 0.324 ms per vec-step, 2 + 3 -> 0.232 ms).  So
+        // the quanta are as small as the episode length allows: the rebuild (<= 100 IK iterations, then a move of typically
+        // 7 - 110 substeps; surface_follow: 4,096 heights first) has to finish within about half an episode, otherwise the env
+        // completes it inline when it needs it (exact either way, counted by tg_pipeline_stalls).
+        // object_balance's episodes end when the pole falls, typically after a few dozen steps whatever max_steps says: it keeps
+        // the larger quanta (measured at config 5: 0.383 ms per vec-step with 6 / 8, 0.407 ms with 2 / 3 - the rebuilds were late).
+        const double ms = cfg->task.task == TG_TASK_OBJECT_BALANCE ? 60.0 : std::max(2, cfg->task.max_steps);
+        b.ik_chunk = std::min(100, std::max(3, (int)ceil(100.0 / (0.25 * ms))));
+        b.reset_chunk = std::min(1000, std::max(2, (int)ceil(120.0 / (0.3 * ms))));
+        b.surf_chunk = SURF_CHUNK;
+    }
     if (const char* ev = getenv("TG_SURF_CHUNK")) b.surf_chunk = std::max(1, atoi(ev));
     if (const char* ev = getenv("TG_IK_CHUNK")) b.ik_chunk = std::max(1, atoi(ev));       // tuning hooks
     if (const char* ev = getenv("TG_RESET_CHUNK")) b.reset_chunk = std::max(1, atoi(ev));

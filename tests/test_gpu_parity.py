@@ -164,9 +164,12 @@ def test_tcp_limits_zero_the_velocity(oracle, edge_modes):
     env.close()
 
 
-def test_autoreset_and_terminal_observation(oracle, edge_modes):
+def test_autoreset_and_terminal_observation(oracle, edge_modes, monkeypatch):
     """3-step episodes: every episode ends while its next episode is still being rebuilt in chunks by the standby
-    blocks, so this drives the slot hand-over (claim / wait / complete inline) as well as the VecEnv semantics."""
+    blocks, so this drives the slot hand-over (claim / wait / complete inline) as well as the VecEnv semantics.  (The quanta are
+    pinned small here: by default tg_create sizes them from max_steps so that such short episodes rebuild in one go.)"""
+    monkeypatch.setenv("TG_IK_CHUNK", "8")
+    monkeypatch.setenv("TG_RESET_CHUNK", "6")
     n, S = 6, 64
     env = _world(edge_modes, n, S=S, max_steps=3)
     rng = np.random.RandomState(5)
