@@ -17,7 +17,11 @@
 #define SURF_PTS (SURF_N * SURF_N)
 #define SURF_META 8 // per episode: zc, dir x, dir y, goal x y z, float32 height min, max
 
-// permutation table of OpenSimplex(seed): LCG shuffle (int64 wrap-around; Python's floor modulo)
+// permutation table of OpenSimplex(seed): LCG shuffle (int64 wrap-around; Python's floor modulo).
+// One thread does this in ONE reset quantum, beside the step warps of the launch: the 64-bit signed `%` of the plain restatement
+// (~100 emulated instructions each, 3 per entry) made it the longest quantum of surface_follow's rebuild - and with ~5 envs
+// starting a rebuild every step, the critical path of every step launch.  floor_mod(s, n) for n <= 256 is taken from the two
+// 32-bit halves of the unsigned value instead (u mod n, minus 2^64 mod n when s is negative): 32-bit arithmetic only.
 TGD void os_perm(long long seed_in, unsigned char* perm /* [256], global */)
 {
     unsigned char source[256];
@@ -29,9 +33,12 @@ TGD void os_perm(long long seed_in, unsigned char* perm /* [256], global */)
 #pragma unroll 1
     for (int i = 255; i >= 0; i--) {
         seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
-        const long long sseed = (long long)seed, n = i + 1;
-        long long r = ((sseed % n) + n) % n;
-        r = (r + 31 % n) % n;
+        const unsigned n = (unsigned)(i + 1);
+        const unsigned hi = (unsigned)(seed >> 32), lo = (unsigned)seed;
+        const unsigned p32 = (0xffffffffu % n + 1u) % n;                     // 2^32 mod n
+        unsigned r = ((hi % n) * p32 + lo % n) % n;                          // u mod n
+        if ((long long)seed < 0) r = (r + n - (p32 * p32) % n) % n;          // (u - 2^64) mod n, Python's sign convention
+        r = (r + 31u % n) % n;
         perm[i] = source[r];
         source[r] = source[i];
     }
