@@ -272,7 +272,8 @@ size_t tg_checkpoint_bytes(const TgWorld* w);
 int tg_checkpoint_save(TgWorld* w, void* h_blob, size_t bytes, void* stream);
 int tg_checkpoint_load(TgWorld* w, const void* h_blob, size_t bytes, void* stream);
 /* Number of episode ends so far that found their pre-computed next episode unfinished and completed it inline
- * (exact either way; a performance counter: episodes shorter than the ~8 launches a rebuild takes).  Synchronises. */
+ * (exact either way; a performance counter: episodes shorter than the rebuild - about 40 step launches at max_steps >= 200,
+ * where the quanta are smallest, one launch for very short episodes).  Synchronises. */
 int tg_pipeline_stalls(TgWorld* w, void* stream);
 /* resets consumed per env since the last tg_set_draws (device->host, synchronises the stream) */
 int tg_get_reset_counts(TgWorld* w, int32_t* h_counts, void* stream);

@@ -294,9 +294,9 @@ def surface_follow_goal_config(env_modes, image_size, max_steps, n_envs, lanes_p
 
 
 def surface_follow_vert_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=0):
-    """surface_follow-v2: SurfaceFollowVertEnv (surface_follow_vert/surface_follow_vert_env.py) on the horizontal surfaces
-    (noise_mode 'simplex' - which leaves the surface flat for its 'xRz' movement mode, base_surface_env.py:443-452 - or 'none').
-    noise_mode 'vertical_simplex' (the `forward` sensor type on a vertical heightfield) is not built."""
+    """surface_follow-v2: SurfaceFollowVertEnv (surface_follow_vert/surface_follow_vert_env.py): on the horizontal surfaces
+    (noise_mode 'simplex' - which leaves the surface flat for its 'xRz' movement mode, base_surface_env.py:443-452 - or 'none')
+    and on its own upright one (noise_mode 'vertical_simplex': the `forward` sensor type facing a vertical heightfield)."""
     return surface_follow_config(env_modes, image_size, max_steps, n_envs, lanes_per_warp=lanes_per_warp, variant="vert")
 
 
