@@ -322,6 +322,9 @@ extern "C" int tg_create(const TgConfig* cfg, int device, TgWorld** out)
             CK(cudaMemcpy(w->d_prim_part, cfg->sensor.h_prim_part, sizeof(int) * np, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(w->d_part_cen, cfg->sensor.h_part_centroid, sizeof(double) * 3 * cfg->sensor.n_parts, cudaMemcpyHostToDevice));
             // band tables + half-span skin bitmap + the warps' own tables
+            // rows per work unit: 32 at <= 128 x 128 (fewer, fatter units: - 3.5 % at 4096 / 8192 envs), 16 for the 64-row bands of 256 x 256
+            // (32 there: + 8 %); same-box A/B, tools/raster_time.py
+            w->scan_unit_rows = S <= 128 ? 32 : 16;
             if (const char* ur = getenv("TG_SCAN_UNIT_ROWS")) w->scan_unit_rows = atoi(ur) == 32 ? 32 : 16;   // experiment knob
             if (const char* mp = getenv("TG_SCAN_POOLS")) w->scan_max_pools = std::max(1, std::min(SCAN_MAXPOOLS, atoi(mp)));
             const int unit_rows = std::min(w->scan_unit_rows, S / r.bands);
