@@ -14,7 +14,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "oracle_trajectories.npz")
 
 
 @pytest.mark.parametrize("case", ["edge", "edge_mg400_digitac", "balance", "surface", "surface_goal", "push", "roll", "edge_posctl", "edge_sparse",
-                                  "surface_yzRx_sparse", "surface_vert_flat", "surface_vertical", "surface_posctl", "push_mg400_mini_tactip"])
+                                  "surface_yzRx_sparse", "surface_vert_flat", "surface_vertical", "surface_posctl", "push_mg400_mini_tactip",
+                                  "balance_posctl", "push_posctl", "roll_posctl"])
 def test_oracle_replays_golden_trajectory(oracle, case):
     import make_oracle_golden as G
 
@@ -30,5 +31,5 @@ def test_oracle_replays_golden_trajectory(oracle, case):
     assert np.all(np.abs(dig[:, 1] - g[:, 1]) <= 8) and np.all(np.abs(dig[:, 2] - g[:, 2]) <= 4), (dig[:, 1:], g[:, 1:])
     same = (dig[:, 1] == g[:, 1]) & (dig[:, 2] == g[:, 2])
     assert np.mean(dig[same, 0] == g[same, 0]) > 0.8
-    if case not in ("edge_mg400_digitac", "push", "push_mg400_mini_tactip"):      # (those two start clear of the stimulus: DIGIT-type images stay blank)
+    if case not in ("edge_mg400_digitac", "push", "push_mg400_mini_tactip", "push_posctl"):      # (those two start clear of the stimulus: DIGIT-type images stay blank)
         assert g[:, 2].max() > 20      # the trajectories do touch the stimulus: the images are not blank
